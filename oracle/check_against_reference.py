@@ -1,0 +1,175 @@
+"""Pin the oracle against the reference's own pure-NumPy functions and write the
+golden vectors in tests/golden/ (run in the dev container only).
+
+The reference (read-only at /root/reference) is imported IN PLACE under
+``sys.modules`` stubs for its missing third-party imports; only its
+NumPy-only helpers are executed, unchanged.  This script is the generator of every
+file in tests/golden/; the GPU box never needs /root/reference.
+
+    python oracle/check_against_reference.py            # check + (re)write goldens
+"""
+import os
+import sys
+import warnings
+from unittest.mock import MagicMock
+
+import numpy as np
+
+REF = os.environ.get('NNAL_REFERENCE', '/root/reference')
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def import_reference():
+    for m in ['tensorflow', 'tensorflow.examples', 'tensorflow.examples.tutorials',
+              'tensorflow.examples.tutorials.mnist', 'tensorflow.python',
+              'tensorflow.python.ops', 'tensorflow.python.framework', 'nrrd', 'cvxopt',
+              'cvxpy', 'h5py', 'cv2', 'alexnet', 'skimage', 'skimage.measure',
+              'skimage.segmentation', 'skimage.util', 'nibabel', 'imageio', 'matplotlib',
+              'matplotlib.pyplot', 'pydensecrf', 'pydensecrf.utils', 'pydensecrf.densecrf']:
+        sys.modules.setdefault(m, MagicMock())
+    sys.path.insert(0, REF)
+    import patch_utils, NNAL_tools, PW_NNAL   # noqa: E401
+    return patch_utils, NNAL_tools, PW_NNAL
+
+
+def main():
+    sys.path.insert(0, ROOT)
+    import oracle as O
+    ref_pu, ref_tools, ref_pw = import_reference()
+    os.makedirs(GOLD, exist_ok=True)
+    gold = {}
+
+    # ---- gather: bit-exact vs patch_utils.get_patches (padded / unpadded / mask / d3>1)
+    rs = np.random.RandomState(10)
+    cases = [((9, 8, 5), (3, 3, 1), 2, np.float32), ((11, 10, 7), (5, 3, 3), 3, np.float64),
+             ((30, 29, 6), (25, 25, 1), 3, np.float32), ((6, 6, 6), (1, 1, 1), 1, np.int16)]
+    for ci, (shape, ps, m, dt) in enumerate(cases):
+        rads = [(p - 1) // 2 for p in ps]
+        imgs = [(rs.randn(*shape) * 50 + 100).astype(dt) for _ in range(m)]
+        padded = [np.pad(im, tuple((r, r) for r in rads), 'constant') for im in imgs]
+        mask = (rs.rand(*shape) > .5).astype(np.int32)
+        inds = rs.choice(int(np.prod(shape)), 17, replace=False)
+        inds[:4] = [0, np.prod(shape) - 1, shape[2] - 1, shape[1] * shape[2]]   # corners
+        r1 = ref_pu.get_patches(padded, inds, ps)
+        o1 = O.get_patches(padded, inds, ps)
+        assert r1.dtype == o1.dtype == np.float64 and np.array_equal(r1, o1), ci
+        r2, l2 = ref_pu.get_patches(imgs, inds, ps, False, mask)
+        o2, ol2 = O.get_patches(imgs, inds, ps, False, mask)
+        assert np.array_equal(r2, o2) and np.array_equal(l2, ol2) and np.array_equal(r1, r2)
+        gold['gather%d_imgs' % ci] = np.stack(padded)
+        gold['gather%d_inds' % ci] = inds
+        gold['gather%d_pshape' % ci] = np.array(ps)
+        gold['gather%d_out' % ci] = r1
+        gold['gather%d_labels' % ci] = l2
+    print('get_patches: oracle == reference (bit-exact) on %d cases' % len(cases))
+
+    # ---- multi-image gather + normalise
+    S, m, ps = 3, 2, (5, 5, 1)
+    shape = (12, 11, 4)
+    allp, img_inds = [], []
+    for s in range(S):
+        imgs = [(rs.randn(*shape) * 30 + 100).astype(np.float32) for _ in range(m)]
+        padded = [np.pad(im, ((2, 2), (2, 2), (0, 0)), 'constant') for im in imgs]
+        allp.append(padded + [(rs.rand(*shape) > .7).astype(np.int8)])
+        img_inds.append(list(rs.choice(int(np.prod(shape)), [6, 0, 9][s], replace=False)))
+    stats = np.abs(rs.randn(S, 2 * m)) * 20 + 50
+    rp, rl = ref_pu.get_patches_multimg(allp, img_inds, ps, stats)
+    op, ol = O.get_patches_multimg(allp, img_inds, ps, stats)
+    for s in range(S):
+        assert np.array_equal(np.asarray(rp[s]), np.asarray(op[s]))
+        assert np.array_equal(np.asarray(rl[s]), np.asarray(ol[s]))
+    gold['multi_imgs'] = np.stack([np.stack(a[:m]) for a in allp])
+    gold['multi_masks'] = np.stack([a[m] for a in allp])
+    for s in range(S):
+        gold['multi_inds%d' % s] = np.array(img_inds[s], dtype=np.int64)
+        gold['multi_out%d' % s] = np.asarray(rp[s], dtype=np.float64)
+        gold['multi_labels%d' % s] = np.asarray(rl[s])
+    gold['multi_stats'] = stats
+    print('get_patches_multimg: oracle == reference (bit-exact)')
+
+    # ---- global2local_inds (known answer from SURVEY §4 + random)
+    ka = ref_pu.global2local_inds([0, 3, 4, 9, 2], [3, 2, 5])
+    assert [list(a) for a in ka] == [[0, 2], [0, 1], [4]]
+    gi = rs.permutation(40)[:23]
+    sizes = [7, 0, 13, 20]
+    rr = ref_pu.global2local_inds(gi, sizes)
+    oo = O.global2local_inds(gi, sizes)
+    assert all(np.array_equal(a, b) for a, b in zip(rr, oo))
+    gold['g2l_inds'] = gi
+    gold['g2l_sizes'] = np.array(sizes)
+    for i, a in enumerate(rr):
+        gold['g2l_out%d' % i] = a
+    print('global2local_inds: oracle == reference')
+
+    # ---- entropy / uncertainty filtering (incl. in-place zero bump)
+    P = rs.dirichlet(np.ones(4), size=50).T
+    P[:, 3] = [1, 0, 0, 0]
+    P[:, 7] = [.5, .5, 0, 0]
+    Pa, Pb = P.copy(), P.copy()
+    re_, oe = ref_tools.compute_entropy(Pa), O.compute_entropy(Pb)
+    assert np.array_equal(re_, oe) and np.array_equal(Pa, Pb) and Pa[1, 3] == 10e-8
+    ka = ref_tools.compute_entropy(np.array([[.5, 1, .2], [.5, 0, .8]]))
+    assert np.allclose(ka, [0.693147181, 1.61180957e-06, 0.500402424], rtol=1e-8)
+    gold['entropy_P'] = P
+    gold['entropy_H'] = re_
+    Pa, Pb = P.copy(), P.copy()
+    ru, ou = ref_tools.uncertainty_filtering(Pa, 9), O.uncertainty_filtering(Pb, 9)
+    assert np.array_equal(ru, ou) and np.array_equal(Pa, Pb) and Pa[1, 3] == 1e-8
+    gold['unc_sel'] = ru
+    posts = rs.rand(200)
+    rb, ob = ref_pw.binary_uncertainty_filter(posts, 20), O.binary_uncertainty_filter(posts, 20)
+    assert np.array_equal(rb, ob)
+    gold['bin_posts'] = posts
+    gold['bin_sel'] = rb
+    print('compute_entropy / uncertainty_filtering / binary_uncertainty_filter: oracle == reference')
+
+    # ---- shrink_gradient on explicit gradients of a small net; closed form agrees
+    ka = ref_tools.shrink_gradient([np.ones((2, 3)), 2 * np.ones(2),
+                                    np.arange(4).reshape(2, 2), np.zeros(2)], 'sum')
+    assert np.allclose(ka, [1.25, 1.0])
+    layers = [('conv1', [4, 'conv', [3, 3]]), ('max1', [[2, 2], 'pool']),
+              ('conv2', [6, 'conv', [3, 3]]), ('max2', [[2, 2], 'pool']),
+              ('fc1', [16, 'fc']), ('fc2', [12, 'fc']), ('fc3', [3, 'fc'])]
+    w = O.he_init_weights(layers, (7, 7, 2), 11, bias_scale=0.1)
+    x = rs.randn(3, 7, 7, 2)
+    post, g = O.shrunk_class_gradients(layers, w, x)
+    for n in range(3):
+        for y in range(3):
+            grads = O.explicit_class_gradients(layers, w, x[n:n + 1], y)
+            rsg = ref_tools.shrink_gradient(grads, 'sum')
+            assert np.allclose(rsg, O.shrink_gradient(grads, 'sum'), rtol=0, atol=0)
+            assert np.allclose(rsg, g[y, n], rtol=1e-9, atol=1e-15), (rsg, g[y, n])
+    gold['shrink_x'] = x
+    gold['shrink_g'] = g
+    gold['shrink_post'] = post
+    print('shrink_gradient: reference(explicit grads) == oracle closed form')
+
+    # ---- sample_query_dstr with injected uniforms; append_zero
+    q = rs.dirichlet(np.ones(30))
+    q[3] = -1e-3
+    u = rs.rand(8)
+    state = np.random.get_state()
+    np.random.seed(123)
+    u123 = np.random.sample(8)
+    np.random.seed(123)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        rq = ref_tools.sample_query_dstr(q.copy(), 8, replacement=True)
+    np.random.set_state(state)
+    oq = O.sample_query_dstr(q.copy(), 8, u123)
+    assert np.array_equal(rq, oq)
+    gold['sample_q'] = q
+    gold['sample_u'] = u123
+    gold['sample_out'] = rq
+    A = rs.randn(3, 3)
+    assert np.array_equal(ref_tools.append_zero(A), O.append_zero(A))
+    print('sample_query_dstr / append_zero: oracle == reference')
+
+    np.savez_compressed(os.path.join(GOLD, 'reference_numpy_helpers.npz'), **gold)
+    print('wrote', os.path.join(GOLD, 'reference_numpy_helpers.npz'))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,483 @@
+"""Float64 restatement of the reference's Fisher-information (FI) scoring (TEST ORACLE).
+
+Restates NN.get_gradients (NN.py:621-645), NNAL_tools.shrink_gradient
+(NNAL_tools.py:778-831), PW_NNAL.gen_A_matrices (PW_NNAL.py:738-816), the
+multiclass twin (NNAL.py:354-414), NN.LLFC_grads / LLFC_hess (NN.py:874-955),
+NNAL_tools.FC_gradnorms_batch (NNAL_tools.py:725-775), the closed-form trace
+score (NNAL.py:121-139), the SDP objective tr((sum_i q_i A_i)^-1)
+(NNAL_tools.py:576-659) and the seeded sampler (NNAL_tools.py:844-896).
+
+The reference has NO greedy FI selection (its ``fi`` query is an SDP followed by
+unseeded random sampling); the deterministic greedy restatement adopted by this
+build is defined here:
+
+    f(S) = tr( ( (1/|S|) sum_{i in S} Abar_i + delta I )^-1 ),   Abar_i = A_i - delta I
+    greedy: S <- S + argmin_{j not in S} f(S + j)      (lowest position on ties)
+
+which is exactly the SDP objective of NNAL_tools.py:589-602 evaluated at
+q = uniform(S).
+"""
+import numpy as np
+from .nnal_oracle import forward, stable_topk
+
+__all__ = [
+    'class_score_factors', 'explicit_class_gradients', 'shrink_gradient',
+    'shrunk_class_gradients', 'gen_A_matrices', 'gen_A_matrices_multiclass',
+    'LLFC_grads', 'LLFC_hess', 'FC_gradnorms_batch', 'fi_trace_score',
+    'mnist_fi_score', 'sdp_objective', 'fi_objective_direct', 'greedy_fi_direct',
+    'fi_objective_dual', 'greedy_fi_dual_bruteforce', 'greedy_fi_rank1',
+    'last_layers_kernel', 'last_layers_dim', 'weighted_gram', 'fi_objective_from_gram',
+    'sample_query_dstr', 'append_zero',
+]
+
+
+# --------------------------------------------------------------------------
+# backward pass: d log p_y / d theta  (NN.py:621-645 builds tf.gradients(log
+# posteriors[j,0], gpars); semantics of tf.gradients through relu/max_pool/conv2d)
+# --------------------------------------------------------------------------
+def _backward(layers, weights, acts, dlogits):
+    """Back-propagate ``dlogits`` [c,N] through the stored activations.  Returns a
+    list (per layer, same order as ``layers``) of dicts holding ``dz`` (gradient at
+    the layer's pre-activation) for conv/fc layers."""
+    n_layers = len(layers)
+    N = dlogits.shape[1]
+    out = [None] * n_layers
+    d = dlogits
+    flat = True
+    for i in range(n_layers - 1, -1, -1):
+        name, spec = layers[i]
+        rec = acts[i]
+        last = (i == n_layers - 1)
+        if spec[1] == 'fc':
+            W = weights[name][0].astype(np.float64)
+            dz = d if last else d * (rec['z'] > 0)
+            out[i] = {'dz': dz}
+            d = W.T @ dz
+            flat = True
+        else:
+            nhwc = rec['out_nhwc']
+            if flat and d.ndim == 2:
+                # undo flatten_tf: flat [C*W*H, N] -> [C,W,H,N] -> transpose -> [N,H,W,C]
+                _, H, Wd, C = nhwc.shape
+                d = np.transpose(d.reshape(C, Wd, H, N))
+                flat = False
+            if spec[1] == 'pool':
+                s = spec[0][0]
+                x = rec['in']
+                _, H, Wd, C = x.shape
+                Ho, Wo = nhwc.shape[1], nhwc.shape[2]
+                am = rec['argmax']                       # [N,Ho,Wo,C] index in s*s window
+                dxp = np.zeros((N, Ho, Wo, C, s * s))
+                np.put_along_axis(dxp, am[..., None], d[..., None], axis=-1)
+                dxp = dxp.reshape(N, Ho, Wo, C, s, s).transpose(0, 1, 4, 2, 5, 3)
+                dxp = dxp.reshape(N, Ho * s, Wo * s, C)
+                d = dxp[:, :H, :Wd, :]
+            elif spec[1] == 'conv':
+                W = weights[name][0].astype(np.float64)
+                kh, kw, cin, cout = W.shape
+                ph, pw = kh // 2, kw // 2
+                dz = d * (rec['z'] > 0)
+                out[i] = {'dz': dz}
+                # dx[y',x',ci] = sum_{dy,dx,co} dz[y'-dy+ph, x'-dx+pw, co] W[dy,dx,ci,co]
+                dzp = np.pad(dz, ((0, 0), (ph, ph), (pw, pw), (0, 0)), 'constant')
+                win = np.lib.stride_tricks.sliding_window_view(dzp, (kh, kw), axis=(1, 2))
+                Wf = W[::-1, ::-1, :, :]                 # flipped taps
+                d = np.tensordot(win, Wf, axes=([4, 5, 3], [0, 1, 3]))
+    return out
+
+
+def class_score_factors(layers, weights, x, feature_layer=None):
+    """Forward + one backward per class.  Returns (fwd, back) with ``back[y][i]['dz']``
+    the gradient of log p_y at layer i's pre-activation for every sample in the batch
+    (tf.gradients(log posteriors[y, n]) semantics; the reference only ever feeds one
+    sample, NN.py:639-645 uses column 0)."""
+    fwd = forward(layers, weights, x, feature_layer, keep_acts=True)
+    post = fwd['posteriors']
+    c, N = post.shape
+    back = []
+    for y in range(c):
+        e = np.zeros((c, N))
+        e[y, :] = 1.
+        back.append(_backward(layers, weights, fwd['acts'], e - post))
+    return fwd, back
+
+
+def explicit_class_gradients(layers, weights, x1, y, grad_layers=None):
+    """Explicit gradient list [gW_1, gb_1, gW_2, gb_2, ...] of log p_y for ONE
+    sample ``x1`` [1,H,W,C] in TF variable shapes and creation order (W then b per
+    layer), as ``sess.run(model.grad_posts[str(y)])`` returns (PW_NNAL.py:795-804).
+    Small models only (materialises every parameter gradient)."""
+    fwd, back = class_score_factors(layers, weights, x1)
+    names = [n for n, s in layers if s[1] in ('conv', 'fc')]
+    if grad_layers:
+        names = list(grad_layers)
+    grads = []
+    for name in names:
+        i = [n for n, _ in layers].index(name)
+        spec = layers[i][1]
+        rec = fwd['acts'][i]
+        dz = back[y][i]['dz']
+        if spec[1] == 'fc':
+            a = rec['in'][:, 0]
+            grads += [np.outer(dz[:, 0], a), dz[:, 0].reshape(-1, 1)]
+        else:
+            W = weights[name][0]
+            kh, kw, cin, cout = W.shape
+            ph, pw = kh // 2, kw // 2
+            xin = np.pad(rec['in'], ((0, 0), (ph, ph), (pw, pw), (0, 0)), 'constant')
+            win = np.lib.stride_tricks.sliding_window_view(xin, (kh, kw), axis=(1, 2))
+            # win [1,H,W,C,kh,kw]; gW[kh,kw,ci,co] = sum_pos win[pos,ci,kh,kw] dz[pos,co]
+            gW = np.tensordot(win[0], dz[0], axes=([0, 1], [0, 1]))      # [C,kh,kw,co]
+            grads += [np.transpose(gW, (1, 2, 0, 3)), dz[0].sum(axis=(0, 1))]
+    return grads
+
+
+def shrink_gradient(grad, method='sum'):
+    """NNAL_tools.shrink_gradient(grad,'sum') (NNAL_tools.py:784-796): per layer
+    (sum gW + sum gb) / (size W + len b)."""
+    if method != 'sum':
+        raise ValueError('oracle restates only the "sum" mode used by the query code')
+    layer_num = int(len(grad) / 2)
+    shrunk = np.zeros(layer_num)
+    for t in range(layer_num):
+        grW, grb = grad[2 * t], grad[2 * t + 1]
+        shrunk[t] = (np.sum(grW) + np.sum(grb)) / (np.prod(grW.shape) + len(grb))
+    return np.ravel(shrunk)
+
+
+def shrunk_class_gradients(layers, weights, x, grad_layers=None, feature_layer=None):
+    """Closed form of shrink_gradient(...,'sum') on the factored gradients, for a
+    whole batch: returns (post [c,N], g [c,N,tau]).  FC layer: gW = dz a^T ->
+    sum gW = (sum dz)(sum a); conv layer: sum gW = sum_pos (sum_co dz)(box-sum over
+    the kh x kw window of sum_ci x_padded)."""
+    fwd, back = class_score_factors(layers, weights, x, feature_layer)
+    names = [n for n, s in layers if s[1] in ('conv', 'fc')]
+    if grad_layers:
+        names = list(grad_layers)
+    c, N = fwd['posteriors'].shape
+    g = np.zeros((c, N, len(names)))
+    lnames = [n for n, _ in layers]
+    for y in range(c):
+        for t, name in enumerate(names):
+            i = lnames.index(name)
+            spec = layers[i][1]
+            rec = fwd['acts'][i]
+            dz = back[y][i]['dz']
+            W, b = weights[name]
+            size = np.prod(W.shape) + len(b)
+            if spec[1] == 'fc':
+                sdz = dz.sum(axis=0)
+                g[y, :, t] = (sdz * rec['in'].sum(axis=0) + sdz) / size
+            else:
+                kh, kw = W.shape[0], W.shape[1]
+                ph, pw = kh // 2, kw // 2
+                D = dz.sum(axis=-1)                                   # [N,H,W]
+                xs = np.pad(rec['in'].sum(axis=-1), ((0, 0), (ph, ph), (pw, pw)), 'constant')
+                box = np.lib.stride_tricks.sliding_window_view(xs, (kh, kw), axis=(1, 2)).sum(axis=(-1, -2))
+                g[y, :, t] = ((D * box).sum(axis=(1, 2)) + D.sum(axis=(1, 2))) / size
+    return fwd['posteriors'], g
+
+
+# --------------------------------------------------------------------------
+# conditional FI matrices in shrunk coordinates
+# --------------------------------------------------------------------------
+def gen_A_matrices(g0, g1, sel_posts, diag_load=1e-5):
+    """PW_NNAL.gen_A_matrices (PW_NNAL.py:738-816), binary case.  ``g0``/``g1``
+    [B,tau] are the shrunk gradients of log p_0 / log p_1, ``sel_posts`` P(class 1).
+    p<1e-6 -> p=0 and only g0 is used; p>1-1e-6 -> p=1 and only g1 (:770-793);
+    A_i = (1-p) g0 g0^T + p g1 g1^T + diag_load I (:810-814)."""
+    A = []
+    tau = g0.shape[1]
+    for i in range(len(sel_posts)):
+        p = sel_posts[i]
+        if p < 1e-6:
+            p = 0.
+            a0, a1 = g0[i], np.zeros(tau)
+        elif p > 1 - 1e-6:
+            p = 1.
+            a0, a1 = np.zeros(tau), g1[i]
+        else:
+            a0, a1 = g0[i], g1[i]
+        Ai = (1. - p) * np.outer(a0, a0) + p * np.outer(a1, a1)
+        A += [Ai + np.eye(tau) * diag_load]
+    return A
+
+
+def gen_A_matrices_multiclass(sel_posteriors, g):
+    """Multiclass twin inside NNAL.CNN_query (NNAL.py:354-414), restated as
+    written: zero posteriors < 1e-6 IN PLACE (:361-362), renormalise the rest,
+    keep all if fewer than 10 non-zero classes else the 10 largest renormalised
+    (:379-400), A_i = sum_j [ g_j g_j^T / ptilde_j + 1e-5 I ] -- the diagonal load
+    is added once PER CLASS (:404-409).  ``g`` is [c,B,tau]."""
+    c, B = sel_posteriors.shape
+    tau = g.shape[2]
+    A = []
+    for i in range(B):
+        xp = sel_posteriors[:, i]
+        xp[xp < 1e-6] = 0.
+        nz = np.where(xp > 0.)[0]
+        nzp = xp[nz] / np.sum(xp[nz])
+        if len(nz) < 10:
+            sel_classes, new_posts = nz, nzp
+        else:
+            sel = stable_topk(-nzp, 10)
+            sel_classes = nz[sel]
+            new_posts = nzp[sel]
+            new_posts = new_posts / np.sum(new_posts)
+        Ai = np.zeros((tau, tau))
+        for j in range(len(sel_classes)):
+            sg = g[sel_classes[j], i]
+            Ai += np.outer(sg, sg) / new_posts[j] + np.eye(tau) * 1e-5
+        A += [Ai]
+    return A
+
+
+# --------------------------------------------------------------------------
+# last-layer factored scores (NN.py:874-955, NNAL_tools.py:725-775, NNAL.py:121-139)
+# --------------------------------------------------------------------------
+def LLFC_grads(pies, U, labels=None):
+    """NN.LLFC_grads (NN.py:905-955): [(e_y - pi) (x) u ; (e_y - pi)] as a
+    ((d+1)c, n) matrix; label = argmax posterior if none given (:928-931)."""
+    c, n = pies.shape
+    d = U.shape[0]
+    flag = labels is None
+    if flag:
+        labels = np.argmax(pies, axis=0)
+    hot = np.zeros((c, n))
+    for j in range(c):
+        hot[j, labels == j] = 1
+    rep_U = np.tile(U, (c, 1))
+    dJ_dW = np.repeat(hot, d, axis=0) * rep_U - np.repeat(pies, d, axis=0) * rep_U
+    dJ_db = hot - pies
+    G = np.concatenate((dJ_dW, dJ_db), axis=0)
+    return (G, labels) if flag else G
+
+
+def LLFC_hess(pi, u):
+    """NN.LLFC_hess (NN.py:874-903) for one sample: ``pi`` [c,1], ``u`` [d,1];
+    A(pi) = diag(pi) (repeat(pi) - I)^T = -(diag pi - pi pi^T); Hessian =
+    [[kron(A,uu^T), kron(A,u)],[kron(A,u^T), A]]."""
+    d = u.shape[0]
+    c = pi.shape[0]
+    repM = np.repeat(pi, c, axis=1) - np.eye(c)
+    A = np.diag(pi[:, 0]) @ repM.T
+    H = np.zeros(((d + 1) * c, (d + 1) * c))
+    H[:c * d, :c * d] = np.kron(A, np.outer(u, u))
+    H[:c * d, c * d:] = np.kron(A, u)
+    H[c * d:, :c * d] = np.kron(A, u.T)
+    H[c * d:, c * d:] = A
+    return H
+
+
+def FC_gradnorms_batch(J, fc_inputs, fc_weights):
+    """NNAL_tools.FC_gradnorms_batch (NNAL_tools.py:725-775): squared gradient
+    norms of the class-0 posterior J0 w.r.t. each FC layer's parameters,
+    ||dz||^2 (||a||^2 + 1), back-propagated with ReLU masks (:757-767).
+    ``fc_inputs[i]`` is the input activation [d_i,N] of FC layer i and
+    ``fc_weights[i]`` its W; ``J`` [2,N] posteriors."""
+    L = len(fc_inputs)
+    N = J.shape[1]
+    norms = np.zeros((L, N))
+    W = None
+    dz = None
+    a = None
+    for i in reversed(range(L)):
+        if i == L - 1:
+            dJ0_da = np.array([J[0, :] * J[1, :], -J[0, :] * J[1, :]])
+            fp_z = 1
+        else:
+            dJ0_da = W.T @ dz
+            fp_z = np.array(a > 0, dtype=int)
+        a = fc_inputs[i]
+        dz = fp_z * dJ0_da
+        norms[i, :] = np.sum(dz ** 2, axis=0) * (np.sum(a ** 2, axis=0) + 1.)
+        W = fc_weights[i]
+    return norms
+
+
+def fi_trace_score(post, U):
+    """Trace of the per-sample last-layer FI, tr((diag pi - pi pi^T) (x) [u;1][u;1]^T)
+    = (1 - ||pi||^2)(||u||^2 + 1) (closed form behind NNAL.py:124-139)."""
+    return (1. - np.sum(post ** 2, axis=0)) * (np.sum(U ** 2, axis=0) + 1.)
+
+
+def mnist_fi_score(pool_images, pool_posteriors):
+    """The score as written in NNAL.querying_iterations_MNIST (NNAL.py:124-139):
+    ``pool_images`` [d,n], ``pool_posteriors`` [n,c];
+    (||x||^2/max||x||^2 + 1)(1 - ||p||^2)."""
+    norms = np.sum(pool_images ** 2, axis=0)
+    norms = norms / norms.max()
+    return (norms + 1) * (1 - np.sum(pool_posteriors ** 2, axis=1))
+
+
+# --------------------------------------------------------------------------
+# FI objective and greedy selection
+# --------------------------------------------------------------------------
+def sdp_objective(A, q):
+    """tr((sum_i q_i A_i)^-1): the quantity sum_j t_j the SDP of
+    NNAL_tools.py:589-602 / 612-659 minimises at its optimum for a given q."""
+    Iq = sum(q[i] * A[i] for i in range(len(A)))
+    return np.trace(np.linalg.inv(Iq))
+
+
+def fi_objective_direct(Abar, S, delta):
+    """f(S) = tr(((1/|S|) sum_{i in S} Abar_i + delta I)^-1) (definition)."""
+    tau = Abar[0].shape[0]
+    M = sum(Abar[i] for i in S) / float(len(S)) + delta * np.eye(tau)
+    return np.trace(np.linalg.inv(M))
+
+
+def greedy_fi_direct(Abar, delta, k):
+    """Definitional greedy: brute-force evaluation of f(S+j) for every candidate
+    at every step.  Returns (indices in selection order, f(S_t) per step)."""
+    n = len(Abar)
+    S, objs = [], []
+    for _ in range(min(k, n)):
+        best, bj = None, -1
+        for j in range(n):
+            if j in S:
+                continue
+            v = fi_objective_direct(Abar, S + [j], delta)
+            if best is None or v < best:
+                best, bj = v, j
+        S.append(bj)
+        objs.append(best)
+    return np.array(S), np.array(objs)
+
+
+def fi_objective_dual(Kss, s, D, delta):
+    """f(S) through the kernel (dual / Gram) form.  With Abar_i = Gt_i Gt_i^T
+    (Gt_i the D x r_i scaled score factor) and Kss = Gt_S^T Gt_S (r x r):
+        f(S) = (D - r)/delta + tr((delta I_r + Kss/s)^-1)
+    (the non-zero spectra of Gt Gt^T and Gt^T Gt coincide)."""
+    r = Kss.shape[0]
+    return (D - r) / delta + np.trace(np.linalg.inv(delta * np.eye(r) + Kss / float(s)))
+
+
+def greedy_fi_dual_bruteforce(K, rank, D, delta, k):
+    """Brute-force greedy on a block kernel ``K`` [(n*rank),(n*rank)] (sample i owns
+    rows i*rank..(i+1)*rank-1).  Used for c>2 (rank = c) in config 1."""
+    n = K.shape[0] // rank
+    S, objs = [], []
+    for _ in range(min(k, n)):
+        best, bj = None, -1
+        for j in range(n):
+            if j in S:
+                continue
+            T = S + [j]
+            rows = np.concatenate([np.arange(i * rank, (i + 1) * rank) for i in T])
+            v = fi_objective_dual(K[np.ix_(rows, rows)], len(T), D, delta)
+            if best is None or v < best:
+                best, bj = v, j
+        S.append(bj)
+        objs.append(best)
+    return np.array(S), np.array(objs)
+
+
+def greedy_fi_rank1(Kt, D, delta, k, return_reduced=False):
+    """Incremental greedy for rank-one conditional FIs Abar_i = gt_i gt_i^T with
+    scaled kernel Kt_ij = <gt_i, gt_j> (this is the algorithm the CUDA path runs;
+    DESIGN.md §FI).  At step t (|S| = t), alpha = (t+1) delta, C = (alpha I +
+    Kt_SS)^-1, and for candidate j with k_j = Kt[j,S]:
+        r_j = Kt_jj - k_j^T C k_j,   e_j = ||C k_j||^2,
+        loss_j = (1 + e_j)/(alpha + r_j)
+        f(S+j) = (t+1) [ (D - t)/alpha - 1/alpha + tr(C) ... ]  (see below)
+    argmin_j loss_j = argmin_j f(S+j).  Objective after the pick:
+        f(S') = (D - s')/delta + tr((delta I + Kt_S'S'/s')^-1),  s' = t+1.
+    Returns (indices, f per step[, reduced objective per step]) where the reduced
+    objective is the kernel-dependent term tr((delta I + Kt_SS/s)^-1)."""
+    n = Kt.shape[0]
+    diag = np.diag(Kt).copy()
+    S, objs, red = [], [], []
+    avail = np.ones(n, dtype=bool)
+    for t in range(min(k, n)):
+        alpha = (t + 1) * delta
+        if t == 0:
+            r = diag.copy()
+            e = np.zeros(n)
+        else:
+            Kss = Kt[np.ix_(S, S)]
+            C = np.linalg.inv(alpha * np.eye(t) + Kss)
+            kjs = Kt[:, S]                       # [n,t]
+            Y = kjs @ C
+            r = diag - np.sum(Y * kjs, axis=1)
+            e = np.sum(Y * Y, axis=1)
+        loss = (1. + e) / (alpha + r)
+        loss[~avail] = np.inf
+        j = int(np.argmin(loss))                 # first minimum = lowest position
+        S.append(j)
+        avail[j] = False
+        s = t + 1
+        Kss = Kt[np.ix_(S, S)]
+        rv = np.trace(np.linalg.inv(delta * np.eye(s) + Kss / float(s)))
+        red.append(rv)
+        objs.append((D - s) / delta + rv)
+    if return_reduced:
+        return np.array(S), np.array(objs), np.array(red)
+    return np.array(S), np.array(objs)
+
+
+def last_layers_dim(c, d, d_prev=None):
+    """Parameter count D of the last FC layer ((d+1)c, NN.py:891-901) plus, if
+    ``d_prev`` is given, the previous FC layer (d (d_prev+1))."""
+    D = (d + 1) * c
+    if d_prev is not None:
+        D += d * (d_prev + 1)
+    return D
+
+
+def last_layers_kernel(p1, U, A_prev=None, W_last=None):
+    """Scaled score kernel Kt_ij = sqrt(w_i w_j) <gbar_i, gbar_j> for the BINARY
+    model (c=2), w_i = p_i (1-p_i).  Last layer: gbar_i = v (x) [u_i;1], v=(1,-1)
+    (F_i = (diag pi - pi pi^T) (x) ut ut^T = w_i (v v^T) (x) ut ut^T, NN.py:891-901),
+    so <gbar_i,gbar_j> = 2 (u_i.u_j + 1).  With ``A_prev``/``W_last`` the previous FC
+    layer's factor is added (FC_gradnorms_batch back-propagation,
+    NNAL_tools.py:757-767): delta2_i = (W_last^T v) * 1[u_i>0], gradient
+    delta2_i (x) [a_i;1], inner product (delta2_i.delta2_j)(a_i.a_j + 1)."""
+    w = p1 * (1. - p1)
+    K = 2. * (U.T @ U + 1.)
+    if A_prev is not None:
+        v = np.array([1., -1.])
+        beta = (W_last.T @ v)                       # [d]
+        Mk = (U > 0) * beta[:, None]                # [d,n] masked back-prop signal
+        K = K + (Mk.T @ Mk) * (A_prev.T @ A_prev + 1.)
+    sw = np.sqrt(w)
+    return K * sw[:, None] * sw[None, :]
+
+
+def weighted_gram(U, wq):
+    """Weighted penultimate-feature Gram  H = Ut diag(wq) Ut^T, Ut = [U;1]
+    ((d+1) x (d+1)); for c=2 the pool FI sum_i q_i F_i equals (v v^T) (x) H with
+    wq_i = q_i p_i (1-p_i)."""
+    Ut = np.concatenate([U, np.ones((1, U.shape[1]))], axis=0)
+    return (Ut * wq[None, :]) @ Ut.T
+
+
+def fi_objective_from_gram(H, c, delta):
+    """tr((delta I + (v v^T) (x) H)^-1) for c=2 through the (d+1)^2 Gram only:
+    (D - (d+1))/delta + tr((delta I + 2H)^-1)   (||v||^2 = 2)."""
+    assert c == 2
+    d1 = H.shape[0]
+    D = c * d1
+    return (D - d1) / delta + np.trace(np.linalg.inv(delta * np.eye(d1) + 2. * H))
+
+
+# --------------------------------------------------------------------------
+# sampling from a query distribution (NNAL_tools.py:844-896, :833-842)
+# --------------------------------------------------------------------------
+def sample_query_dstr(q_dstr, k, u):
+    """NNAL_tools.sample_query_dstr with replacement=True (NNAL_tools.py:844-872)
+    with the k uniform draws ``u`` supplied by the caller (the reference draws
+    them from the global unseeded np.random): clamp negatives IN PLACE, inverse
+    CDF, np.unique, clip index n -> n-1."""
+    q_dstr[q_dstr < 0] = 0.
+    Q = np.unique(q_dstr.cumsum().searchsorted(np.asarray(u)[:k]))
+    Q[Q == len(q_dstr)] = len(q_dstr) - 1
+    return Q
+
+
+def append_zero(A):
+    """NNAL_tools.append_zero (NNAL_tools.py:833-842)."""
+    d = A.shape[0]
+    A = np.insert(A, d, 0, axis=1)
+    return np.insert(A, d, 0, axis=0)
