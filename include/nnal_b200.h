@@ -1,0 +1,157 @@
+/* libnnal_b200 -- C ABI of the B200-native query-scoring path of nn-active-learning.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status codes,
+ * caller-owned HOST buffers unless a parameter is named d_* (device pointer).  One context per
+ * process and GPU; calls on one context are serialised by the caller.  No exceptions cross the
+ * boundary; nnal_last_error() returns the message of the last failing call.
+ *
+ * The reference is pure Python (TensorFlow 1.x + NumPy); each entry point cites the reference
+ * function (file:line in jsourati/nn-active-learning) whose work it replaces.  The Python package
+ * nn-active-learning_b200 (import name nnal_b200) binds these with ctypes and re-exposes them under
+ * the reference's own module/function names; INTEGRATION.md shows the binding.
+ */
+#ifndef NNAL_B200_H
+#define NNAL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nnal_ctx nnal_ctx;
+
+/* status codes */
+#define NNAL_OK 0
+#define NNAL_ERR_INVALID 1      /* bad argument (the reference would raise ValueError/IndexError) */
+#define NNAL_ERR_CUDA 2         /* CUDA runtime error; context is unusable afterwards */
+#define NNAL_ERR_STATE 3        /* call order violated (e.g. scoring before a pool pass) */
+#define NNAL_ERR_UNSUPPORTED 4  /* shape outside what the kernels cover */
+#define NNAL_ERR_NO_DEVICE 5    /* no CUDA device / not an sm_100 part: there is NO CPU fallback */
+
+/* layer kinds of NN.CNN's layer_dict (NN.py:98-108): [out,'conv',[kh,kw]] / [[p,p],'pool'] / [out,'fc'] */
+#define NNAL_LAYER_CONV 0
+#define NNAL_LAYER_POOL 1
+#define NNAL_LAYER_FC 2
+typedef struct { int32_t type, out, kh, kw; } nnal_layer_spec;
+
+/* element types of volumes handed to nnal_volume_set */
+#define NNAL_F32 0
+#define NNAL_F64 1
+
+/* normalisation applied by the gather */
+#define NNAL_NORM_NONE 0
+#define NNAL_NORM_BATCH_EVAL 1  /* PW_NN.py:503-506: channel ch<m uses stats[ch] */
+#define NNAL_NORM_MULTIMG 2     /* patch_utils.py:1203-1207: block ch/d3 uses stats[ch/d3] */
+
+/* score kinds */
+#define NNAL_SCORE_BINARY 0     /* |P(class1) - 0.5|          (PW_NNAL.py:64,109-110,724-730) */
+#define NNAL_SCORE_NEG_ENTROPY 1 /* sum_c p log p = -H        (NNAL.py:309-310, NNAL_tools.py:32-34) */
+#define NNAL_SCORE_ENTROPY 2    /* H                          (NNAL_tools.py:71-85) */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int nnal_version(void);
+/* Creates a context on CUDA device `device`.  Fails with NNAL_ERR_NO_DEVICE when there is no
+ * usable sm_100 GPU: the product path has no CPU fallback. */
+int nnal_ctx_create(int device, nnal_ctx** out);
+int nnal_ctx_destroy(nnal_ctx* ctx);
+const char* nnal_last_error(nnal_ctx* ctx);
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+long long nnal_launch_count(nnal_ctx* ctx);
+/* 0: every conv/fc layer on the FP32 CUDA-core kernels; 1 (default): tcgen05 tensor-core kernels
+ * (3-term bf16 split, FP32 accumulate) for the shapes they cover. */
+int nnal_set_tensor_cores(nnal_ctx* ctx, int enable);
+int nnal_synchronize(nnal_ctx* ctx);
+/* the context's CUDA stream (cudaStream_t) so host code can record CUDA events on it */
+void* nnal_stream(nnal_ctx* ctx);
+
+/* Per-kernel-class device timing (CUDA events on the context stream) for bench.py's roofline leg.
+ * cls: layer index (0..n_layers-1), 100 gather, 101 scores, 102 top-k. */
+int nnal_profile(nnal_ctx* ctx, int enable);
+int nnal_profile_read(nnal_ctx* ctx, int cls, double* total_ms, long long* count);
+
+/* ---- model: replaces the TF graph built by NN.CNN / NN.create_PW1 (NN.py:56-345, 1319-1359) --- */
+/* Input is NHWC [*, in_h, in_w, in_c]; conv = SAME/stride 1 + bias + ReLU (NN.py:285-290); pool =
+ * max, SAME, window=stride (NN.py:1473-1477); fc = W x + b with ReLU except on the last layer
+ * (NN.py:213-241, 322-327).  feature_layer is the index into `specs` whose output is
+ * model.feature_layer (NN.py:173-176); -1 = second to last. */
+int nnal_model_set(nnal_ctx* ctx, const nnal_layer_spec* specs, int n_layers, int in_h, int in_w, int in_c,
+                   int feature_layer);
+/* Weights in the reference's TF variable layouts (NN.py:270-283, 311-320; the HDF5 layout of
+ * NN.save_weights NN.py:379-396): conv W[kh][kw][cin][cout], b[cout]; fc W[out][in] with the
+ * reference's flatten order in = c*(W*H)+w*H+h (NN.py:296-301), b[out]. */
+int nnal_model_set_weights(nnal_ctx* ctx, int layer, const float* W, const float* b);
+int nnal_model_info(nnal_ctx* ctx, int* n_class, int* feat_dim, int* prev_dim);
+/* multiply-accumulates per sample of layer `layer` and whether it runs on the tensor-core path */
+int nnal_model_layer_info(nnal_ctx* ctx, int layer, int* type, long long* macs_per_sample, int* uses_tc);
+
+/* ---- volumes: the padded multi-modality images the query functions receive ----------------- */
+/* Uploads subject `subject` (m modality arrays, each C-contiguous (X,Y,Z), z fastest, as
+ * PW_AL.py:737-761 builds them) and re-lays it out as [Z][X][Y][m] in HBM.  pad_* > 0 adds zero
+ * padding on the device (get_patches(..., padded=False), patch_utils.py:1118-1132). */
+int nnal_volume_set(nnal_ctx* ctx, int subject, int m, const void* const* mods, int dtype, int64_t X, int64_t Y,
+                    int64_t Z, int64_t pad_x, int64_t pad_y, int64_t pad_z);
+int nnal_volume_clear(nnal_ctx* ctx);
+
+/* ---- patch gather: replaces patch_utils.get_patches (patch_utils.py:1087-1173) --------------- */
+/* inds: raveled C-order voxel ids of the UNPADDED volume (:1144).  out: float64
+ * [n][d1][d2][m*d3], channel j*d3+dz (:1156-1165); bit-exact.  stats: [m][2] (mu,sigma) or NULL. */
+int nnal_gather(nnal_ctx* ctx, int subject, const int64_t* inds, int64_t n, int d1, int d2, int d3,
+                const double* stats, int norm_mode, double* out);
+
+/* ---- pool pass: replaces PW_NN.batch_eval (PW_NN.py:357-539) + the TF forward --------------- */
+/* Declares a pool of n_total samples scored in this query round.  keep = 0: posteriors only; 1: also
+ * model.feature_layer; 2: also the input of the feature layer's FC (needed for two-layer FI). */
+int nnal_pool_begin(nnal_ctx* ctx, int64_t n_total, int keep);
+/* Gathers + normalises (float64 arithmetic, cast to float32 like the TF feed) + runs the forward
+ * pass for n voxels of `subject`, writing pool positions [offset, offset+n). */
+int nnal_pool_eval(nnal_ctx* ctx, int subject, const int64_t* inds, int64_t n, int64_t offset, int d1, int d2,
+                   int d3, const double* stats, int norm_mode);
+/* Same, for samples already in host memory as float32 NHWC [n][in_h][in_w][in_c] (whole-image
+ * pools of NNAL.CNN_query, NNAL.py:298-306). */
+int nnal_pool_eval_images(nnal_ctx* ctx, const float* x, int64_t n, int64_t offset);
+/* Same, for samples resident in device memory (d_inds int64 device pointer) */
+int nnal_pool_eval_device_inds(nnal_ctx* ctx, int subject, const int64_t* d_inds, int64_t n, int64_t offset, int d1,
+                               int d2, int d3, const double* stats, int norm_mode);
+/* posteriors [c][n_total] float32 (layout of model.posteriors, NN.py:184-188) */
+int nnal_pool_posteriors(nnal_ctx* ctx, float* out);
+/* model.feature_layer as [feat_dim][n] columns start..start+n (PW_NN.py:530-531 layout) */
+int nnal_pool_features(nnal_ctx* ctx, int64_t start, int64_t n, float* out);
+/* score every pool sample (float64 like the reference) and keep the scores on the device */
+int nnal_pool_score(nnal_ctx* ctx, int kind, double eps);
+int nnal_pool_scores_read(nnal_ctx* ctx, double* out);
+/* k smallest scores, ascending, ties -> lowest pool position: np.argsort(score)[:k] */
+int nnal_pool_topk(nnal_ctx* ctx, int64_t k, int64_t* idx_out, double* score_out);
+
+/* ---- stand-alone scoring helpers (host float64 in/out like the NumPy originals) -------------- */
+/* NNAL_tools.compute_entropy (NNAL_tools.py:71-85): P [c][n]; zeros are treated as eps (the
+ * in-place bump of the caller's array is done by the Python shim). kind as NNAL_SCORE_*. */
+int nnal_entropy(nnal_ctx* ctx, const double* P, int c, int64_t n, int kind, double eps, double* out);
+/* np.argsort(scores)[:k] */
+int nnal_topk(nnal_ctx* ctx, const double* scores, int64_t n, int64_t k, int64_t* idx_out);
+
+/* ---- Fisher-information scoring (PW_NNAL.py:547-627, 738-816; NN.py:874-955) ---------------- */
+/* Select the FI candidate set: pool positions (ascending argsort order irrelevant) whose factored
+ * scores take part in the greedy selection.  cand: n_cand pool positions. */
+int nnal_fi_set_candidates(nnal_ctx* ctx, const int64_t* cand, int64_t n_cand, int n_layers /*1 or 2*/);
+/* Weighted penultimate-feature Gram  H = sum_i wq_i [u_i;1][u_i;1]^T over the candidates
+ * ((d+1)x(d+1) float32, row-major) -- the last-layer FI block of NN.LLFC_hess (NN.py:891-901).
+ * wq: per-candidate weight q_i p_i (1-p_i) is formed on the device from q (host, n_cand) or
+ * uniform if q == NULL.  The result stays on the device (for NCCL all-reduce by the host layer,
+ * see nnal_fi_gram_ptr) and is copied to H_out if non-NULL. */
+int nnal_fi_gram(nnal_ctx* ctx, const double* q, float* H_out);
+void* nnal_fi_gram_ptr(nnal_ctx* ctx, int64_t* n_elems);
+/* Greedy FI selection: k candidates minimising tr(((1/|S|) sum Abar_i + delta I)^-1)
+ * step by step; sel_out: positions into the candidate list, obj_out: objective after each step,
+ * red_out: its kernel-dependent part tr((delta I + K_SS/s)^-1). */
+int nnal_fi_greedy(nnal_ctx* ctx, int64_t k, double delta, int64_t* sel_out, double* obj_out, double* red_out);
+/* Multi-GPU greedy: one step split in two so the host layer can combine ranks with NCCL:
+ * (1) local best candidate, (2) apply the globally chosen winner's factors. */
+int nnal_fi_step_local_best(nnal_ctx* ctx, int64_t step, double delta, double* loss_out, int64_t* cand_out);
+int nnal_fi_winner_factors(nnal_ctx* ctx, int64_t cand, float* factors_out, int64_t* n_floats);
+int nnal_fi_step_apply(nnal_ctx* ctx, int64_t step, const float* winner_factors, int64_t n_floats, int owner_is_local,
+                       int64_t cand_local);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNAL_B200_H */

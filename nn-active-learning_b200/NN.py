@@ -1,0 +1,142 @@
+"""Model container mirroring the parts of the reference's ``NN.CNN`` the query path reads
+(NN.py:56-345, 1319-1359): the ordered ``layer_dict``, ``var_dict`` {layer: [W, b]} in the TF
+variable layouts, ``feature_layer`` index and dropout metadata.  No TensorFlow graph is built --
+the forward pass runs in libnnal_b200."""
+from collections import OrderedDict
+
+import numpy as np
+
+
+class CNN(object):
+    """``layer_dict``: ordered {name: [out,'conv',[kh,kw]] | [[p,p],'pool'] | [out,'fc']}
+    (NN.py:98-108).  ``input_shape`` = (H, W, C) of the NHWC placeholder (NN.py:1339-1345)."""
+
+    def __init__(self, input_shape, layer_dict, name='CNN', feature_layer=None, dropout=None, probes=[]):
+        self.input_shape = tuple(int(v) for v in input_shape)
+        self.layer_dict = OrderedDict(layer_dict)
+        self.name = name
+        self.feature_layer_index = feature_layer
+        self.layer_type = [spec[1] for spec in self.layer_dict.values()]
+        if dropout:
+            self.dropout_layers, self.dropout_rate = dropout[0], dropout[1]
+        else:
+            self.dropout_layers, self.dropout_rate = [], 1.
+        self.probes = list(probes)
+        self.var_dict = {}
+        self.grad_layers = []
+        self._version = 0
+        # validate the way NN.CNN.add_layer does (NN.py:246-249)
+        for spec in self.layer_dict.values():
+            if spec[1] not in ('conv', 'fc', 'pool'):
+                raise ValueError("Layer's type should be either 'fc', 'conv' or 'pool'.")
+        last = list(self.layer_dict.values())[-1]
+        self.nclass = int(last[0])
+
+    # -- shapes -----------------------------------------------------------
+    def weight_shapes(self):
+        H, W, C = self.input_shape
+        flat = None
+        shapes = OrderedDict()
+        for name, spec in self.layer_dict.items():
+            if spec[1] == 'conv':
+                shapes[name] = ((spec[2][0], spec[2][1], C, spec[0]), (spec[0],))
+                C = spec[0]
+            elif spec[1] == 'pool':
+                s = spec[0][0]
+                H, W = -(-H // s), -(-W // s)
+            else:
+                if flat is None:
+                    flat = H * W * C
+                shapes[name] = ((spec[0], flat), (spec[0], 1))
+                flat = spec[0]
+        return shapes
+
+    # -- weights ----------------------------------------------------------
+    def set_weights(self, weights):
+        """``weights``: {layer: (W, b)} in TF layouts -- conv ``[kh,kw,cin,cout]``/``[cout]``
+        (NN.py:270-283), fc ``[out,in]``/``[out,1]`` (NN.py:311-320)."""
+        shapes = self.weight_shapes()
+        for name, (ws, bs) in shapes.items():
+            W, b = weights[name]
+            W = np.asarray(W, dtype=np.float32)
+            b = np.asarray(b, dtype=np.float32)
+            if W.shape != ws or b.size != bs[0]:
+                raise ValueError('layer %s: expected W%s b%s, got W%s b%s' % (name, ws, bs, W.shape, b.shape))
+            self.var_dict[name] = [W, b.reshape(bs)]
+        self._version += 1
+
+    def get_weights(self, sess=None):
+        if not self.var_dict:
+            raise RuntimeError('model has no weights: call set_weights / load_weights first')
+        return {k: (v[0], v[1]) for k, v in self.var_dict.items()}
+
+    def initialize(self, seed=None):
+        """He-normal weights, zero biases (NN.py:1430-1470)."""
+        rs = np.random.RandomState(seed)
+        w = {}
+        for name, (ws, bs) in self.weight_shapes().items():
+            fan_in = ws[0] * ws[1] * ws[2] if len(ws) > 2 else ws[1]
+            w[name] = ((rs.randn(*ws) * np.sqrt(2. / fan_in)).astype(np.float32), np.zeros(bs, np.float32))
+        self.set_weights(w)
+
+    def save_weights(self, file_path):
+        """NPZ with the key layout of NN.save_weights' HDF5 groups (NN.py:379-396):
+        ``<layer>/Weight`` and ``<layer>/Bias``."""
+        d = {}
+        for name, (W, b) in self.var_dict.items():
+            d[name + '/Weight'] = W
+            d[name + '/Bias'] = b
+        np.savez(file_path, **d)
+
+    def load_weights(self, file_path):
+        z = np.load(file_path)
+        self.set_weights({name: (z[name + '/Weight'], z[name + '/Bias']) for name in self.weight_shapes()})
+
+    def get_gradients(self, grad_layers=[]):
+        """Records which layers the FI score factors cover (NN.py:621-645)."""
+        self.grad_layers = list(grad_layers)
+
+
+class ReferenceModelAdapter(object):
+    """Wraps a live reference ``NN.CNN`` (TensorFlow) so the engine can read its weights the
+    way NN.save_weights does (``var.eval()``, NN.py:391-394).  ``layer_dict`` and
+    ``input_shape`` must be supplied because the reference object does not keep them."""
+
+    def __init__(self, ref_model, layer_dict, input_shape, feature_layer=None):
+        self.ref = ref_model
+        self.layer_dict = OrderedDict(layer_dict)
+        self.input_shape = tuple(input_shape)
+        self.feature_layer_index = feature_layer
+        self.dropout_rate = getattr(ref_model, 'dropout_rate', 1.)
+        self._version = 0
+
+    def refresh(self):
+        """Call after the reference fine-tunes the model so the next query re-uploads."""
+        self._version += 1
+
+    def get_weights(self, sess=None):
+        out = {}
+        for name, spec in self.layer_dict.items():
+            if spec[1] == 'pool':
+                continue
+            W, b = self.ref.var_dict[name]
+            out[name] = (np.asarray(W.eval(session=sess)), np.asarray(b.eval(session=sess)))
+        return out
+
+
+def pw1_layer_dict(nclass):
+    """Layer dictionary of create_PW1 (NN.py:1328-1336)."""
+    return OrderedDict([('conv1', [24, 'conv', [5, 5]]), ('conv2', [32, 'conv', [5, 5]]),
+                        ('max1', [[2, 2], 'pool']), ('conv3', [48, 'conv', [3, 3]]),
+                        ('conv4', [96, 'conv', [3, 3]]), ('max2', [[2, 2], 'pool']),
+                        ('fc1', [4096, 'fc']), ('fc2', [4096, 'fc']), ('fc3', [nclass, 'fc'])])
+
+
+def create_PW1(nclass, dropout_rate=1., learning_rate=None, optimizer_name=None, patch_shape=(25, 25, 3)):
+    """NN.create_PW1 (NN.py:1319-1359): same signature; optimiser arguments are accepted and
+    ignored (training stays in the reference)."""
+    d = pw1_layer_dict(nclass)
+    model = CNN((patch_shape[0], patch_shape[1], patch_shape[2]), d, 'PatchWise',
+                feature_layer=len(d) - 2, dropout=[[6, 7, 8], dropout_rate], probes=[5])
+    model.get_gradients()
+    return model

@@ -1,0 +1,133 @@
+"""Drop-in for the query dispatch of the reference's ``PW_NNAL`` (patch-wise active learning):
+``CNN_query`` (PW_NNAL.py:18-166), ``query_multimg`` (:169-629) and the helpers they call.
+Same method names, pool/index arguments and returned query positions."""
+import numpy as np
+
+from . import _lib as L
+from . import dist, patch_utils
+from .engine import get_engine
+
+
+def _stats_list(stats, m):
+    return np.array([[stats[j][0], stats[j][1]] for j in range(m)], dtype=np.float64)
+
+
+def _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=0):
+    """Gather + forward for (this rank's block of) a single-volume pool; leaves posteriors on
+    the device.  Returns (engine, lo, hi) with [lo,hi) the block of pool positions scored here."""
+    eng = get_engine()
+    eng.set_model(model, sess)
+    imgs = list(padded_imgs)
+    eng.upload(0, imgs)
+    pool_inds = np.asarray(pool_inds)
+    n = len(pool_inds)
+    rank, world = dist.rank_world()
+    b = dist.shard_bounds(n, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    eng.pool_begin(hi - lo, keep)
+    eng.pool_eval(0, pool_inds[lo:hi], 0, expr.pars['patch_shape'],
+                  _stats_list(expr.pars['stats'], len(imgs)), L.NORM_BATCH_EVAL, shape=imgs[0].shape)
+    return eng, lo, hi
+
+
+def binary_uncertainty_filter(posts, B):
+    """PW_NNAL.binary_uncertainty_filter (PW_NNAL.py:671-681)."""
+    eng = get_engine()
+    return eng.topk(np.abs(np.array(posts, dtype=np.float64) - 0.5), B)
+
+
+def CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, method_name):
+    """PW_NNAL.CNN_query (PW_NNAL.py:18-166).  Returns positions into ``pool_inds``.
+
+    ``entropy``: k pool samples with the smallest |P(class 1) - 0.5| (:51-65), ascending.
+    ``fi``: uncertainty pre-filter to B (:98-115), conditional FI of the last FC layers in
+    factored form, deterministic greedy selection of k instead of the
+    reference's SDP + random sampling (:146-163); returns ``sel_inds[Q]``."""
+    if method_name == 'random':
+        n = len(pool_inds)
+        return np.random.permutation(n)[:expr.pars['k']]
+
+    if method_name == 'entropy':
+        k = expr.pars['k']
+        eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds)
+        eng.pool_score(L.SCORE_BINARY)
+        idx, sc = eng.pool_topk(k, with_scores=True)
+        q, _ = dist.allgather_topk(sc, idx + lo, min(k, len(pool_inds)))
+        return q
+
+    if method_name == 'fi':
+        from . import fi
+        return fi.query_single(expr, model, sess, padded_imgs, pool_inds)
+
+    raise NotImplementedError('query method %r is not part of the replaced path' % method_name)
+
+
+def bin_uncertainty_filter_multimg(expr, model, sess, all_padded_imgs, pool_inds, B, x_feed_dict={},
+                                   keep=0):
+    """PW_NNAL.bin_uncertainty_filter_multimg (PW_NNAL.py:684-736): posteriors of every
+    subject's pool, rank |p - 0.5| over the CONCATENATED pool, keep B, split back with
+    global2local_inds.  Returns ``(sel_inds, sel_posts)`` lists per subject."""
+    if len(x_feed_dict) > 0:
+        raise NotImplementedError('x_feed_dict (MC-dropout) is not part of the replaced path yet')
+    eng = get_engine()
+    eng.set_model(model, sess)
+    s = len(pool_inds)
+    img_ind_sizes = [len(pool_inds[i]) for i in range(s)]
+    m = len(all_padded_imgs[0]) - 1
+    n = int(np.sum(img_ind_sizes))
+    rank, world = dist.rank_world()
+    b = dist.shard_bounds(n, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    eng.pool_begin(hi - lo, keep)
+    start = 0
+    for i in range(s):
+        ni = img_ind_sizes[i]
+        a, e = max(start, lo), min(start + ni, hi)
+        if e > a:
+            imgs = list(all_padded_imgs[i][:-1])
+            eng.upload(i, imgs)
+            stats = np.array([[expr.train_stats[i, 2 * j], expr.train_stats[i, 2 * j + 1]] for j in range(m)],
+                             dtype=np.float64)
+            inds_i = np.asarray(pool_inds[i])[a - start:e - start]
+            eng.pool_eval(i, inds_i, a - lo, expr.pars['patch_shape'], stats, L.NORM_BATCH_EVAL,
+                          shape=imgs[0].shape)
+        start += ni
+    eng.pool_score(L.SCORE_BINARY)
+    idx, sc = eng.pool_topk(B, with_scores=True)
+    post_local = eng.pool_posteriors()[1, :].astype(np.float64)
+    sorted_inds, _ = dist.allgather_topk(sc, idx + lo, min(B, n))
+    # posteriors of the selected samples (owners contribute theirs)
+    mine = (sorted_inds >= lo) & (sorted_inds < hi)
+    sel_p = np.zeros(len(sorted_inds))
+    sel_p[mine] = post_local[sorted_inds[mine] - lo]
+    if dist.is_dist():
+        import torch
+        t = torch.from_numpy(sel_p).to(dist._device())
+        dist.allreduce_sum_(t)
+        sel_p = t.cpu().numpy()
+    sel_inds = patch_utils.global2local_inds(sorted_inds, img_ind_sizes)
+    cum = np.append(-1, np.cumsum(img_ind_sizes) - 1)
+    set_of = cum.searchsorted(sorted_inds) - 1
+    sel_posts = [sel_p[set_of == i] for i in range(s)]
+    return sel_inds, sel_posts
+
+
+def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, labeled_inds, method_name):
+    """PW_NNAL.query_multimg (PW_NNAL.py:169-629): list of S arrays of local positions into
+    ``pool_inds[s]`` (possibly empty)."""
+    k = expr.pars['k']
+    img_ind_sizes = [len(pool_inds[i]) for i in range(len(pool_inds))]
+
+    if method_name == 'random':
+        npool = np.sum(img_ind_sizes)
+        inds = np.random.permutation(npool)[:k]
+        return patch_utils.global2local_inds(inds, img_ind_sizes)
+
+    if method_name == 'entropy':
+        return bin_uncertainty_filter_multimg(expr, model, sess, all_padded_imgs, pool_inds, k)[0]
+
+    if method_name == 'fi':
+        from . import fi
+        return fi.query_multimg(expr, model, sess, all_padded_imgs, pool_inds)
+
+    raise NotImplementedError('query method %r is not part of the replaced path' % method_name)

@@ -1,0 +1,542 @@
+// extern "C" boundary of libnnal_b200 (see include/nnal_b200.h).
+#include "nnal_common.cuh"
+#include "../../include/nnal_b200.h"
+#include <cstdlib>
+#include <algorithm>
+
+static const int NNAL_VERSION = 100;
+static const int64_t DEFAULT_CHUNK = 8192;
+
+static int64_t chunk_size() {
+  const char* e = getenv("NNAL_CHUNK");
+  if (e) { long v = atol(e); if (v > 0) return v; }
+  return DEFAULT_CHUNK;
+}
+
+extern "C" int nnal_version(void) { return NNAL_VERSION; }
+
+extern "C" int nnal_ctx_create(int device, nnal_ctx** out) {
+  if (!out) return NNAL_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return NNAL_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NNAL_ERR_NO_DEVICE;
+  if (prop.major != 10) return NNAL_ERR_NO_DEVICE;     // sm_100a kernels only
+  if (cudaSetDevice(device) != cudaSuccess) return NNAL_ERR_NO_DEVICE;
+  nnal_ctx* ctx = new nnal_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return NNAL_ERR_CUDA; }
+  const char* f = getenv("NNAL_FORCE_SIMT");
+  ctx->use_tc = (f && atoi(f)) ? 0 : 1;
+  *out = ctx;
+  return NNAL_OK;
+}
+
+static void free_layers(nnal_ctx* ctx) {
+  for (auto& L : ctx->layers) {
+    if (L.W) cudaFree(L.W);
+    if (L.b) cudaFree(L.b);
+    if (L.Wh) cudaFree(L.Wh);
+    if (L.Wl) cudaFree(L.Wl);
+  }
+  ctx->layers.clear();
+}
+static void free_buf(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+static void free_pool(nnal_ctx* ctx) {
+  if (ctx->pool_post) cudaFree(ctx->pool_post);
+  if (ctx->pool_score) cudaFree(ctx->pool_score);
+  if (ctx->pool_feat) cudaFree(ctx->pool_feat);
+  if (ctx->pool_prev) cudaFree(ctx->pool_prev);
+  ctx->pool_post = nullptr; ctx->pool_score = nullptr; ctx->pool_feat = nullptr; ctx->pool_prev = nullptr;
+  ctx->pool_n = 0; ctx->pool_cap_n = 0; ctx->pool_cap_keep = -1;
+}
+
+extern "C" int nnal_volume_clear(nnal_ctx* ctx) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& v : ctx->vols) if (v.data) cudaFree(v.data);
+  ctx->vols.clear();
+  return NNAL_OK;
+}
+
+int nnal_fi_release(nnal_ctx* ctx);
+
+extern "C" int nnal_ctx_destroy(nnal_ctx* ctx) {
+  if (!ctx) return NNAL_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  nnal_volume_clear(ctx);
+  free_layers(ctx);
+  free_pool(ctx);
+  nnal_fi_release(ctx);
+  nnal_tc_release(ctx);
+  free_buf(ctx->stage); free_buf(ctx->inds); free_buf(ctx->act[0]); free_buf(ctx->act[1]); free_buf(ctx->xin);
+  free_buf(ctx->featbuf); free_buf(ctx->prevbuf); free_buf(ctx->logits); free_buf(ctx->splitA[0]); free_buf(ctx->splitA[1]);
+  free_buf(ctx->topk_ws); free_buf(ctx->fi_ws);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NNAL_OK;
+}
+
+extern "C" const char* nnal_last_error(nnal_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" long long nnal_launch_count(nnal_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int nnal_set_tensor_cores(nnal_ctx* ctx, int enable) { if (!ctx) return NNAL_ERR_INVALID; ctx->use_tc = enable ? 1 : 0; return NNAL_OK; }
+extern "C" void* nnal_stream(nnal_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int nnal_synchronize(nnal_ctx* ctx) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+extern "C" int nnal_profile(nnal_ctx* ctx, int enable) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  ctx->prof.clear();
+  ctx->profile = enable ? 1 : 0;
+  return NNAL_OK;
+}
+
+extern "C" int nnal_profile_read(nnal_ctx* ctx, int cls, double* total_ms, long long* count) {
+  if (!ctx || !total_ms || !count) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  double t = 0; long long c = 0;
+  for (auto& r : ctx->prof) {
+    if (r.cls != cls) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { t += ms; ++c; }
+  }
+  *total_ms = t; *count = c;
+  return NNAL_OK;
+}
+
+extern "C" int nnal_model_layer_info(nnal_ctx* ctx, int layer, int* type, long long* macs_per_sample, int* uses_tc) {
+  if (!ctx || layer < 0 || layer >= (int)ctx->layers.size()) return NNAL_ERR_INVALID;
+  const Layer& L = ctx->layers[layer];
+  if (type) *type = L.type;
+  long long macs = 0;
+  if (L.type == NNAL_LAYER_CONV) macs = (long long)L.out_h * L.out_w * L.out_c * L.kh * L.kw * L.in_c;
+  else if (L.type == NNAL_LAYER_FC) macs = (long long)L.in_dim * L.out_dim;
+  if (macs_per_sample) *macs_per_sample = macs;
+  if (uses_tc) *uses_tc = (ctx->use_tc && L.type == NNAL_LAYER_FC && layer != (int)ctx->layers.size() - 1 && nnal_tc_fc_supported(ctx, L)) ? 1 : 0;
+  return NNAL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------
+extern "C" int nnal_model_set(nnal_ctx* ctx, const nnal_layer_spec* specs, int n_layers, int in_h, int in_w, int in_c,
+                              int feature_layer) {
+  if (!ctx || !specs || n_layers <= 0 || in_h <= 0 || in_w <= 0 || in_c <= 0) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  free_layers(ctx);
+  ctx->in_h = in_h; ctx->in_w = in_w; ctx->in_c = in_c;
+  int H = in_h, W = in_w, C = in_c;
+  int flat = 0;            // >0 once flattened: current vector length
+  ctx->fc_first = -1;
+  for (int i = 0; i < n_layers; ++i) {
+    Layer L;
+    L.type = specs[i].type;
+    if (L.type == NNAL_LAYER_CONV) {
+      if (flat) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "conv layer after an fc layer");
+      if (specs[i].kh <= 0 || specs[i].kw <= 0 || !(specs[i].kh & 1) || !(specs[i].kw & 1) || specs[i].out <= 0)
+        NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv kernels must be odd-sized (SAME, stride 1)");
+      L.kh = specs[i].kh; L.kw = specs[i].kw;
+      L.in_h = H; L.in_w = W; L.in_c = C;
+      L.out_h = H; L.out_w = W; L.out_c = specs[i].out;
+      L.relu = 1;
+      C = L.out_c;
+    } else if (L.type == NNAL_LAYER_POOL) {
+      if (flat) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "pool layer after an fc layer");
+      if (specs[i].kh <= 0 || specs[i].kh != specs[i].kw) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "pool window must be square");
+      L.kh = L.kw = specs[i].kh;
+      L.in_h = H; L.in_w = W; L.in_c = C;
+      L.out_h = (H + L.kh - 1) / L.kh; L.out_w = (W + L.kw - 1) / L.kw; L.out_c = C;
+      H = L.out_h; W = L.out_w;
+    } else if (L.type == NNAL_LAYER_FC) {
+      if (specs[i].out <= 0) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "fc layer needs out > 0");
+      if (!flat) { flat = H * W * C; ctx->fc_first = i; L.in_h = H; L.in_w = W; L.in_c = C; }
+      L.in_dim = flat;
+      L.out_dim = specs[i].out;
+      L.relu = (i != n_layers - 1);
+      flat = L.out_dim;
+    } else {
+      NNAL_FAIL(ctx, NNAL_ERR_INVALID, "Layer's type should be either 'fc', 'conv' or 'pool'.");
+    }
+    ctx->layers.push_back(L);
+  }
+  if (ctx->layers.back().type != NNAL_LAYER_FC) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "last layer must be fc");
+  ctx->n_class = ctx->layers.back().out_dim;
+  if (feature_layer < 0) feature_layer = n_layers - 2;
+  ctx->feature_layer = feature_layer;
+  ctx->feat_dim = 0; ctx->prev_dim = 0;
+  if (feature_layer >= 0 && feature_layer < n_layers - 1 && ctx->layers[feature_layer].type == NNAL_LAYER_FC) {
+    ctx->feat_dim = ctx->layers[feature_layer].out_dim;
+    ctx->prev_dim = ctx->layers[feature_layer].in_dim;
+  }
+  return NNAL_OK;
+}
+
+extern "C" int nnal_model_info(nnal_ctx* ctx, int* n_class, int* feat_dim, int* prev_dim) {
+  if (!ctx || ctx->layers.empty()) return NNAL_ERR_STATE;
+  if (n_class) *n_class = ctx->n_class;
+  if (feat_dim) *feat_dim = ctx->feat_dim;
+  if (prev_dim) *prev_dim = ctx->prev_dim;
+  return NNAL_OK;
+}
+
+extern "C" int nnal_model_set_weights(nnal_ctx* ctx, int layer, const float* W, const float* b) {
+  if (!ctx || !W || !b) return NNAL_ERR_INVALID;
+  if (layer < 0 || layer >= (int)ctx->layers.size()) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "layer index out of range");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Layer& L = ctx->layers[layer];
+  size_t wn, bn;
+  if (L.type == NNAL_LAYER_CONV) { wn = (size_t)L.kh * L.kw * L.in_c * L.out_c; bn = L.out_c; }
+  else if (L.type == NNAL_LAYER_FC) { wn = (size_t)L.in_dim * L.out_dim; bn = L.out_dim; }
+  else NNAL_FAIL(ctx, NNAL_ERR_INVALID, "pool layers have no weights");
+  if (!L.W) CUDA_TRY(ctx, cudaMalloc(&L.W, wn * sizeof(float)));
+  if (!L.b) CUDA_TRY(ctx, cudaMalloc(&L.b, bn * sizeof(float)));
+  CUDA_TRY(ctx, cudaMemcpyAsync(L.b, b, bn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if (L.type == NNAL_LAYER_FC && layer == ctx->fc_first && L.in_h * L.in_w > 1) {
+    NNAL_TRY(devbuf_reserve(ctx, ctx->stage, wn * sizeof(float)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage.p, W, wn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    NNAL_TRY(nnal_k_permute_fc_weight(ctx, (const float*)ctx->stage.p, L.W, L.out_dim, L.in_c, L.in_h, L.in_w));
+  } else {
+    CUDA_TRY(ctx, cudaMemcpyAsync(L.W, W, wn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  L.has_weights = true;
+  NNAL_TRY(nnal_tc_prepare_layer(ctx, L));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// volumes
+// ---------------------------------------------------------------------------------------------
+extern "C" int nnal_volume_set(nnal_ctx* ctx, int subject, int m, const void* const* mods, int dtype, int64_t X, int64_t Y,
+                               int64_t Z, int64_t px, int64_t py, int64_t pz) {
+  if (!ctx || !mods || m <= 0 || subject < 0 || X <= 0 || Y <= 0 || Z <= 0 || px < 0 || py < 0 || pz < 0) return NNAL_ERR_INVALID;
+  if (dtype != NNAL_F32 && dtype != NNAL_F64) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "volume dtype must be NNAL_F32 or NNAL_F64");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((int)ctx->vols.size() <= subject) ctx->vols.resize(subject + 1);
+  Volume& v = ctx->vols[subject];
+  size_t esz = dtype == NNAL_F64 ? 8 : 4;
+  size_t in_elems = (size_t)X * Y * Z;
+  size_t out_bytes = (size_t)(X + 2 * px) * (Y + 2 * py) * (Z + 2 * pz) * m * esz;
+  NNAL_TRY(devbuf_reserve(ctx, ctx->stage, in_elems * m * esz));
+  for (int j = 0; j < m; ++j) {
+    if (!mods[j]) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "null modality pointer");
+    CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->stage.p + (size_t)j * in_elems * esz, mods[j], in_elems * esz,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (v.bytes < out_bytes) {
+    if (v.data) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CUDA_TRY(ctx, cudaFree(v.data)); v.data = nullptr; }
+    CUDA_TRY(ctx, cudaMalloc(&v.data, out_bytes));
+    v.bytes = out_bytes;
+  }
+  v.m = m; v.X = X + 2 * px; v.Y = Y + 2 * py; v.Z = Z + 2 * pz; v.dtype = dtype;
+  NNAL_TRY(nnal_k_relayout(ctx, ctx->stage.p, dtype, m, X, Y, Z, px, py, pz, v.data));
+  return NNAL_OK;
+}
+
+static int check_gather_args(nnal_ctx* ctx, int subject, int64_t n, int d1, int d2, int d3, const Volume** vout) {
+  if (subject < 0 || subject >= (int)ctx->vols.size() || !ctx->vols[subject].data)
+    NNAL_FAIL(ctx, NNAL_ERR_STATE, "subject volume not set");
+  const Volume& v = ctx->vols[subject];
+  if (n < 0 || d1 <= 0 || d2 <= 0 || d3 <= 0 || !(d1 & 1) || !(d2 & 1) || !(d3 & 1))
+    NNAL_FAIL(ctx, NNAL_ERR_INVALID, "patch shape must be odd and positive");
+  if (v.X - (d1 - 1) <= 0 || v.Y - (d2 - 1) <= 0 || v.Z - (d3 - 1) <= 0)
+    NNAL_FAIL(ctx, NNAL_ERR_INVALID, "patch larger than padded volume");
+  *vout = &v;
+  return NNAL_OK;
+}
+
+static int upload_stats(nnal_ctx* ctx, const double* stats, int m, int norm_mode, double** d_stats) {
+  *d_stats = nullptr;
+  if (norm_mode == NNAL_NORM_NONE) return NNAL_OK;
+  if (!stats) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "normalisation requested without stats");
+  // stats live at the tail of the index buffer allocation (small)
+  static_assert(sizeof(double) == 8, "");
+  NNAL_TRY(devbuf_reserve(ctx, ctx->logits, 4096));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->logits.p, stats, (size_t)m * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  *d_stats = (double*)ctx->logits.p;
+  return NNAL_OK;
+}
+
+extern "C" int nnal_gather(nnal_ctx* ctx, int subject, const int64_t* inds, int64_t n, int d1, int d2, int d3,
+                           const double* stats, int norm_mode, double* out) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const Volume* v;
+  NNAL_TRY(check_gather_args(ctx, subject, n, d1, d2, d3, &v));
+  if (n == 0) return NNAL_OK;
+  if (!inds || !out) return NNAL_ERR_INVALID;
+  if (v->m * 2 * 8 > 4096) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "too many modalities");
+  double* d_stats;
+  NNAL_TRY(upload_stats(ctx, stats, v->m, norm_mode, &d_stats));
+  const int64_t per = (int64_t)d1 * d2 * d3 * v->m;
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(1ll << 28) / (per * 8)));   // <= 256 MiB staging
+  NNAL_TRY(devbuf_reserve(ctx, ctx->inds, (size_t)chunk * 8));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->act[0], (size_t)chunk * per * 8));
+  for (int64_t o = 0; o < n; o += chunk) {
+    int64_t nb = std::min(chunk, n - o);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->inds.p, inds + o, (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    NNAL_TRY(nnal_k_gather_f64(ctx, *v, (const int64_t*)ctx->inds.p, nb, d1, d2, d3, d_stats, norm_mode, (double*)ctx->act[0].p));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out + o * per, ctx->act[0].p, (size_t)nb * per * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return NNAL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pool pass
+// ---------------------------------------------------------------------------------------------
+extern "C" int nnal_pool_begin(nnal_ctx* ctx, int64_t n_total, int keep) {
+  if (!ctx || n_total < 0 || keep < 0 || keep > 2) return NNAL_ERR_INVALID;
+  if (ctx->layers.empty()) NNAL_FAIL(ctx, NNAL_ERR_STATE, "model not set");
+  for (auto& L : ctx->layers)
+    if (L.type != NNAL_LAYER_POOL && !L.has_weights) NNAL_FAIL(ctx, NNAL_ERR_STATE, "weights not set for every layer");
+  if (keep > 0 && ctx->feat_dim == 0) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "feature layer must be an fc layer before the last");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  size_t n = (size_t)std::max<int64_t>(n_total, 1);
+  if (ctx->pool_post && ctx->pool_cap_n >= n && ctx->pool_cap_keep >= keep && ctx->pool_cap_class == ctx->n_class &&
+      ctx->pool_cap_feat == ctx->feat_dim && ctx->pool_cap_prev == ctx->prev_dim) {
+    ctx->pool_n = n_total;                     // re-use the arrays of the previous round
+    ctx->keep = keep;
+    return NNAL_OK;
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  free_pool(ctx);
+  ctx->pool_n = n_total;
+  ctx->keep = keep;
+  CUDA_TRY(ctx, cudaMalloc(&ctx->pool_post, n * ctx->n_class * sizeof(float)));
+  CUDA_TRY(ctx, cudaMalloc(&ctx->pool_score, n * sizeof(double)));
+  if (keep >= 1) CUDA_TRY(ctx, cudaMalloc(&ctx->pool_feat, n * ctx->feat_dim * sizeof(float)));
+  if (keep >= 2) CUDA_TRY(ctx, cudaMalloc(&ctx->pool_prev, n * ctx->prev_dim * sizeof(float)));
+  ctx->pool_cap_n = n; ctx->pool_cap_keep = keep; ctx->pool_cap_class = ctx->n_class;
+  ctx->pool_cap_feat = ctx->feat_dim; ctx->pool_cap_prev = ctx->prev_dim;
+  return NNAL_OK;
+}
+
+int nnal_tc_fc(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64_t n);
+
+// forward for nb samples whose normalised float32 NHWC input is in ctx->xin
+static int forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset) {
+  const int nl = (int)ctx->layers.size();
+  const float* cur = (const float*)ctx->xin.p;
+  int pp = 0;
+  for (int i = 0; i < nl; ++i) {
+    const Layer& L = ctx->layers[i];
+    prof_begin(ctx, i);
+    if (i == nl - 1) {
+      NNAL_TRY(nnal_k_head(ctx, L, cur, nb, ctx->pool_n, offset, ctx->pool_post, nullptr));
+      prof_end(ctx);
+      break;
+    }
+    float* out = (float*)ctx->act[pp].p;
+    if (L.type == NNAL_LAYER_FC) {
+      if (ctx->keep >= 1 && i == ctx->feature_layer) out = ctx->pool_feat + offset * (int64_t)ctx->feat_dim;
+      else if (ctx->keep >= 2 && i == ctx->feature_layer - 1 && L.out_dim == ctx->prev_dim) out = ctx->pool_prev + offset * (int64_t)ctx->prev_dim;
+    }
+    if (L.type == NNAL_LAYER_CONV) NNAL_TRY(nnal_k_conv_simt(ctx, L, cur, out, nb));
+    else if (L.type == NNAL_LAYER_POOL) NNAL_TRY(nnal_k_pool(ctx, L, cur, out, nb));
+    else {
+      if (ctx->use_tc && nnal_tc_fc_supported(ctx, L)) NNAL_TRY(nnal_tc_fc(ctx, L, cur, out, nb));
+      else NNAL_TRY(nnal_k_fc_simt(ctx, L, cur, out, nb));
+    }
+    prof_end(ctx);
+    if (out == (float*)ctx->act[pp].p) pp ^= 1;
+    cur = out;
+  }
+  return NNAL_OK;
+}
+
+static int reserve_forward(nnal_ctx* ctx, int64_t nb) {
+  size_t mx = (size_t)ctx->in_h * ctx->in_w * ctx->in_c;
+  for (auto& L : ctx->layers) {
+    size_t o = L.type == NNAL_LAYER_FC ? (size_t)L.out_dim : (size_t)L.out_h * L.out_w * L.out_c;
+    mx = std::max(mx, o);
+  }
+  NNAL_TRY(devbuf_reserve(ctx, ctx->act[0], (size_t)nb * mx * sizeof(float)));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->act[1], (size_t)nb * mx * sizeof(float)));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->xin, (size_t)nb * ctx->in_h * ctx->in_w * ctx->in_c * sizeof(float)));
+  return NNAL_OK;
+}
+
+static int pool_eval_impl(nnal_ctx* ctx, int subject, const int64_t* inds, bool inds_on_device, int64_t n, int64_t offset,
+                          int d1, int d2, int d3, const double* stats, int norm_mode) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->pool_post) NNAL_FAIL(ctx, NNAL_ERR_STATE, "nnal_pool_begin not called");
+  const Volume* v;
+  NNAL_TRY(check_gather_args(ctx, subject, n, d1, d2, d3, &v));
+  if (offset < 0 || offset + n > ctx->pool_n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "pool range out of bounds");
+  if (d1 != ctx->in_h || d2 != ctx->in_w || d3 * v->m != ctx->in_c)
+    NNAL_FAIL(ctx, NNAL_ERR_INVALID, "patch shape does not match the model input");
+  if (n == 0) return NNAL_OK;
+  if (!inds) return NNAL_ERR_INVALID;
+  double* d_stats;
+  NNAL_TRY(upload_stats(ctx, stats, v->m, norm_mode, &d_stats));
+  const int64_t chunk = std::min(chunk_size(), n);
+  NNAL_TRY(reserve_forward(ctx, chunk));
+  const int64_t* d_inds = inds;
+  if (!inds_on_device) {
+    NNAL_TRY(devbuf_reserve(ctx, ctx->inds, (size_t)n * 8));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->inds.p, inds, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    d_inds = (const int64_t*)ctx->inds.p;
+  }
+  for (int64_t o = 0; o < n; o += chunk) {
+    int64_t nb = std::min(chunk, n - o);
+    prof_begin(ctx, NNAL_PROF_GATHER);
+    NNAL_TRY(nnal_k_gather_norm_f32(ctx, *v, d_inds + o, nb, d1, d2, d3, d_stats, norm_mode, (float*)ctx->xin.p));
+    prof_end(ctx);
+    NNAL_TRY(forward_chunk(ctx, nb, offset + o));
+  }
+  return NNAL_OK;
+}
+
+extern "C" int nnal_pool_eval(nnal_ctx* ctx, int subject, const int64_t* inds, int64_t n, int64_t offset, int d1, int d2,
+                              int d3, const double* stats, int norm_mode) {
+  return pool_eval_impl(ctx, subject, inds, false, n, offset, d1, d2, d3, stats, norm_mode);
+}
+extern "C" int nnal_pool_eval_device_inds(nnal_ctx* ctx, int subject, const int64_t* d_inds, int64_t n, int64_t offset,
+                                          int d1, int d2, int d3, const double* stats, int norm_mode) {
+  return pool_eval_impl(ctx, subject, d_inds, true, n, offset, d1, d2, d3, stats, norm_mode);
+}
+
+extern "C" int nnal_pool_eval_images(nnal_ctx* ctx, const float* x, int64_t n, int64_t offset) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->pool_post) NNAL_FAIL(ctx, NNAL_ERR_STATE, "nnal_pool_begin not called");
+  if (n < 0 || offset < 0 || offset + n > ctx->pool_n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "pool range out of bounds");
+  if (n == 0) return NNAL_OK;
+  if (!x) return NNAL_ERR_INVALID;
+  const int64_t chunk = std::min(chunk_size(), n);
+  NNAL_TRY(reserve_forward(ctx, chunk));
+  const size_t per = (size_t)ctx->in_h * ctx->in_w * ctx->in_c;
+  for (int64_t o = 0; o < n; o += chunk) {
+    int64_t nb = std::min(chunk, n - o);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->xin.p, x + o * per, (size_t)nb * per * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    NNAL_TRY(forward_chunk(ctx, nb, offset + o));
+  }
+  return NNAL_OK;
+}
+
+extern "C" int nnal_pool_posteriors(nnal_ctx* ctx, float* out) {
+  if (!ctx || !out) return NNAL_ERR_INVALID;
+  if (!ctx->pool_post) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no pool pass");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->pool_post, (size_t)ctx->pool_n * ctx->n_class * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+__global__ void transpose_feat_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n, int d) {
+  __shared__ float t[32][33];
+  int64_t s0 = (int64_t)blockIdx.x * 32;
+  int f0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int64_t s = s0 + r; int f = f0 + threadIdx.x;
+    t[r][threadIdx.x] = (s < n && f < d) ? in[s * d + f] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int f = f0 + r; int64_t s = s0 + threadIdx.x;
+    if (s < n && f < d) out[(int64_t)f * n + s] = t[threadIdx.x][r];
+  }
+}
+
+extern "C" int nnal_pool_features(nnal_ctx* ctx, int64_t start, int64_t n, float* out) {
+  if (!ctx || !out) return NNAL_ERR_INVALID;
+  if (!ctx->pool_feat) NNAL_FAIL(ctx, NNAL_ERR_STATE, "pool pass did not keep features");
+  if (start < 0 || n < 0 || start + n > ctx->pool_n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "feature range out of bounds");
+  if (n == 0) return NNAL_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int d = ctx->feat_dim;
+  NNAL_TRY(devbuf_reserve(ctx, ctx->act[0], (size_t)n * d * sizeof(float)));
+  dim3 grid(cdiv(n, 32), cdiv(d, 32)), block(32, 8);
+  transpose_feat_kernel<<<grid, block, 0, ctx->stream>>>(ctx->pool_feat + start * d, (float*)ctx->act[0].p, n, d);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->act[0].p, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+extern "C" int nnal_pool_score(nnal_ctx* ctx, int kind, double eps) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  if (!ctx->pool_post) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no pool pass");
+  if (kind < 0 || kind > 2) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "unknown score kind");
+  if (kind == NNAL_SCORE_BINARY && ctx->n_class != 2) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "binary uncertainty needs a 2-class model");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  prof_begin(ctx, NNAL_PROF_SCORE);
+  int rc = nnal_k_scores_f32(ctx, ctx->pool_post, ctx->n_class, ctx->pool_n, kind, eps, ctx->pool_score);
+  prof_end(ctx);
+  return rc;
+}
+
+extern "C" int nnal_pool_scores_read(nnal_ctx* ctx, double* out) {
+  if (!ctx || !out) return NNAL_ERR_INVALID;
+  if (!ctx->pool_score) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no pool pass");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->pool_score, (size_t)ctx->pool_n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+static int topk_to_host(nnal_ctx* ctx, const double* d_score, int64_t n, int64_t k, int64_t* idx_out, double* score_out) {
+  if (k > n) k = n;
+  if (k <= 0) return NNAL_OK;
+  NNAL_TRY(devbuf_reserve(ctx, ctx->inds, (size_t)k * 16));
+  int64_t* d_idx = (int64_t*)ctx->inds.p;
+  double* d_sc = (double*)((char*)ctx->inds.p + (size_t)k * 8);
+  prof_begin(ctx, NNAL_PROF_TOPK);
+  NNAL_TRY(nnal_k_topk(ctx, d_score, n, k, d_idx, d_sc));
+  prof_end(ctx);
+  CUDA_TRY(ctx, cudaMemcpyAsync(idx_out, d_idx, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (score_out) CUDA_TRY(ctx, cudaMemcpyAsync(score_out, d_sc, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+extern "C" int nnal_pool_topk(nnal_ctx* ctx, int64_t k, int64_t* idx_out, double* score_out) {
+  if (!ctx || !idx_out || k < 0) return NNAL_ERR_INVALID;
+  if (!ctx->pool_score) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no pool pass");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return topk_to_host(ctx, ctx->pool_score, ctx->pool_n, k, idx_out, score_out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int nnal_entropy(nnal_ctx* ctx, const double* P, int c, int64_t n, int kind, double eps, double* out) {
+  if (!ctx || c <= 0 || n < 0) return NNAL_ERR_INVALID;
+  if (n == 0) return NNAL_OK;
+  if (!P || !out) return NNAL_ERR_INVALID;
+  if (kind == NNAL_SCORE_BINARY && c != 2) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "binary uncertainty needs c == 2");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->act[0], (size_t)n * c * 8));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->act[1], (size_t)n * 8));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->act[0].p, P, (size_t)n * c * 8, cudaMemcpyHostToDevice, ctx->stream));
+  NNAL_TRY(nnal_k_scores_f64(ctx, (const double*)ctx->act[0].p, c, n, kind, eps, (double*)ctx->act[1].p));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->act[1].p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+extern "C" int nnal_topk(nnal_ctx* ctx, const double* scores, int64_t n, int64_t k, int64_t* idx_out) {
+  if (!ctx || n < 0 || k < 0) return NNAL_ERR_INVALID;
+  if (n == 0 || k == 0) return NNAL_OK;
+  if (!scores || !idx_out) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->act[1], (size_t)n * 8));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->act[1].p, scores, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return topk_to_host(ctx, (const double*)ctx->act[1].p, n, k, idx_out, nullptr);
+}

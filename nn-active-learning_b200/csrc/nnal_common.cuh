@@ -1,0 +1,154 @@
+// Shared declarations of libnnal_b200 (sm_100a only).  See include/nnal_b200.h for the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define NNAL_OK 0
+#define NNAL_ERR_INVALID 1
+#define NNAL_ERR_CUDA 2
+#define NNAL_ERR_STATE 3
+#define NNAL_ERR_UNSUPPORTED 4
+#define NNAL_ERR_NO_DEVICE 5
+
+enum { NNAL_LAYER_CONV = 0, NNAL_LAYER_POOL = 1, NNAL_LAYER_FC = 2 };
+enum { NNAL_F32 = 0, NNAL_F64 = 1 };
+
+struct LayerSpec { int type, out, kh, kw; };
+
+struct Layer {
+  int type = 0;
+  int kh = 0, kw = 0;
+  int in_h = 0, in_w = 0, in_c = 0;      // conv/pool input geometry (NHWC)
+  int out_h = 0, out_w = 0, out_c = 0;   // conv/pool output geometry
+  int in_dim = 0, out_dim = 0;           // fc
+  int relu = 0;
+  bool has_weights = false;
+  float* W = nullptr;                    // conv: [kh][kw][cin][cout]; fc: [out][in_native]
+  float* b = nullptr;
+  // bf16 split planes for the tensor-core path (hi = bf16(x), lo = bf16(x - hi))
+  __nv_bfloat16* Wh = nullptr;
+  __nv_bfloat16* Wl = nullptr;
+  int k_pad = 0;                         // padded K of the split planes
+  int n_pad = 0;                         // padded N (rows) of the split planes
+};
+
+struct Volume {
+  int m = 0;                             // modalities
+  int64_t X = 0, Y = 0, Z = 0;           // padded extents (as the reference passes them)
+  int dtype = NNAL_F32;                  // device storage type
+  void* data = nullptr;                  // [Z][X][Y][m]
+  size_t bytes = 0;
+};
+
+struct ProfRec { int cls; cudaEvent_t a, b; };
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct nnal_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // model
+  std::vector<Layer> layers;
+  int in_h = 0, in_w = 0, in_c = 0, n_class = 0, feature_layer = -1, feat_dim = 0;
+  int fc_first = -1;                     // index of first fc layer
+  int use_tc = 1;                        // tensor-core (tcgen05) path for conv/fc where supported
+  // volumes
+  std::vector<Volume> vols;
+  DevBuf stage;                          // upload staging
+  // workspaces
+  DevBuf inds, act[2], xin, featbuf, prevbuf, logits;
+  DevBuf splitA[2];                      // bf16 hi/lo activation planes
+  // pool state
+  int64_t pool_n = 0;
+  int keep = 0;                          // 0: posteriors only, 1: + features (fc_{L-1} out), 2: + previous fc out
+  float* pool_post = nullptr;            // [c][pool_n]
+  double* pool_score = nullptr;           // [pool_n] float64 like the reference's ranking
+  float* pool_feat = nullptr;            // [pool_n][feat_dim]
+  float* pool_prev = nullptr;            // [pool_n][prev_dim]
+  int prev_dim = 0;
+  DevBuf topk_ws;
+  // FI state
+  DevBuf fi_ws;
+  // counters / per-kernel-class device timing (bench.py roofline leg)
+  long long launches = 0;
+  int profile = 0;
+  std::vector<ProfRec> prof;
+  size_t pool_cap_n = 0;                 // allocation capacities of the pool arrays (samples)
+  int pool_cap_keep = -1, pool_cap_class = 0, pool_cap_feat = 0, pool_cap_prev = 0;
+  void* tc_state = nullptr;              // tensor-map cache etc. (gemm_tc.cu)
+};
+
+#define CUDA_TRY(ctx, expr)                                                            \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+      return NNAL_ERR_CUDA;                                                            \
+    }                                                                                  \
+  } while (0)
+
+#define NNAL_FAIL(ctx, code, msg)                                                      \
+  do { (ctx)->err = (msg); return (code); } while (0)
+
+#define NNAL_TRY(expr)                                                                 \
+  do { int _r = (expr); if (_r != NNAL_OK) return _r; } while (0)
+
+static inline int devbuf_reserve(nnal_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (b.cap >= bytes) return NNAL_OK;
+  if (b.p) { CUDA_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+  size_t want = bytes + (bytes >> 3) + 256;
+  CUDA_TRY(ctx, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return NNAL_OK;
+}
+
+static inline void prof_begin(nnal_ctx* ctx, int cls) {
+  if (!ctx->profile) return;
+  ProfRec r; r.cls = cls;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, ctx->stream);
+  ctx->prof.push_back(r);
+}
+static inline void prof_end(nnal_ctx* ctx) {
+  if (!ctx->profile || ctx->prof.empty()) return;
+  cudaEventRecord(ctx->prof.back().b, ctx->stream);
+}
+#define NNAL_PROF_GATHER 100
+#define NNAL_PROF_SCORE 101
+#define NNAL_PROF_TOPK 102
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- kernels launchers (defined in the individual .cu files) -------------------------
+// volume.cu
+int nnal_k_relayout(nnal_ctx*, const void* stage, int dtype, int m, int64_t X, int64_t Y, int64_t Z,
+                    int64_t px, int64_t py, int64_t pz, void* out);
+int nnal_k_gather_f64(nnal_ctx*, const Volume&, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
+                      const double* d_stats, int norm_mode, double* d_out);
+int nnal_k_gather_norm_f32(nnal_ctx*, const Volume&, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
+                           const double* d_stats, int norm_mode, float* d_out);
+// forward_simt.cu
+int nnal_k_conv_simt(nnal_ctx*, const Layer&, const float* in, float* out, int64_t n);
+int nnal_k_pool(nnal_ctx*, const Layer&, const float* in, float* out, int64_t n);
+int nnal_k_fc_simt(nnal_ctx*, const Layer&, const float* in, float* out, int64_t n);
+int nnal_k_permute_fc_weight(nnal_ctx*, const float* Wtf, float* Wnative, int out, int C, int H, int W);
+// score.cu
+int nnal_k_head(nnal_ctx*, const Layer& fc_last, const float* feat, int64_t n, int64_t pool_n, int64_t offset,
+                float* post /*[c][pool_n]*/, float* logits_out /*[n][c] or null*/);
+int nnal_k_scores_f32(nnal_ctx*, const float* post, int c, int64_t n, int kind, double eps, double* score);
+int nnal_k_scores_f64(nnal_ctx*, const double* post, int c, int64_t n, int kind, double eps, double* score);
+int nnal_k_topk(nnal_ctx*, const double* score, int64_t n, int64_t k, int64_t* d_idx_out, double* d_score_out);
+// gemm_tc.cu / conv_tc.cu (tcgen05 path)
+int nnal_tc_prepare_layer(nnal_ctx*, Layer&);
+bool nnal_tc_fc_supported(const nnal_ctx*, const Layer&);
+int nnal_tc_release(nnal_ctx*);

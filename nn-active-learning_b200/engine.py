@@ -1,0 +1,280 @@
+"""Thin object wrapper over the C-ABI context: owns one ``nnal_ctx`` per process/GPU,
+uploads models and volumes, and exposes the pool pass to the reference-named shims."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine(object):
+    def __init__(self, device=None):
+        lib = L.load()
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', '0'))
+        h = C.c_void_p()
+        rc = lib.nnal_ctx_create(int(device), C.byref(h))
+        if rc == L.ERR_NO_DEVICE:
+            raise L.NnalError('no usable sm_100 (B200) CUDA device %d: nnal_b200 has no CPU fallback' % device)
+        if rc != 0:
+            raise L.NnalError('nnal_ctx_create failed with code %d' % rc)
+        self.lib = lib
+        self.h = h
+        self.device = device
+        self._model_key = None
+        self._vol_keys = {}
+        self._m = {}
+        self.volume_cache = os.environ.get('NNAL_VOLUME_CACHE', '1') != '0'
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # ------------------------------------------------------------------
+    def _chk(self, rc):
+        if rc != 0:
+            msg = self.lib.nnal_last_error(self.h)
+            msg = msg.decode() if msg else ''
+            if rc == L.ERR_INVALID:
+                raise ValueError(msg or 'invalid argument')
+            raise L.NnalError('libnnal_b200 error %d: %s' % (rc, msg))
+
+    def close(self):
+        if self.h:
+            self.lib.nnal_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._chk(self.lib.nnal_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.nnal_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.nnal_launch_count(self.h))
+
+    def profile(self, enable):
+        self._chk(self.lib.nnal_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self, cls):
+        t, c = C.c_double(), C.c_longlong()
+        self._chk(self.lib.nnal_profile_read(self.h, int(cls), C.byref(t), C.byref(c)))
+        return t.value, c.value
+
+    def layer_info(self, layer):
+        ty, macs, tc = C.c_int(), C.c_longlong(), C.c_int()
+        self._chk(self.lib.nnal_model_layer_info(self.h, int(layer), C.byref(ty), C.byref(macs), C.byref(tc)))
+        return ty.value, macs.value, tc.value
+
+    def pool_eval_device(self, subject, d_inds_ptr, n, offset, patch_shape, stats, norm_mode=L.NORM_BATCH_EVAL):
+        """Pool pass over indices already resident in device memory (int64 device pointer)."""
+        d1, d2, d3 = [int(p) for p in patch_shape]
+        st = None if stats is None else np.ascontiguousarray(stats, dtype=np.float64)
+        self._chk(self.lib.nnal_pool_eval_device_inds(self.h, int(subject), C.c_void_p(int(d_inds_ptr)), int(n),
+                                                      int(offset), d1, d2, d3,
+                                                      None if st is None else _ptr(st), int(norm_mode)))
+
+    def set_tensor_cores(self, enable):
+        self._chk(self.lib.nnal_set_tensor_cores(self.h, 1 if enable else 0))
+
+    # ------------------------------------------------------------------
+    # model
+    # ------------------------------------------------------------------
+    def set_model(self, model, sess=None):
+        """Uploads ``model`` (an ``nnal_b200.NN.CNN``, or any object exposing ``layer_dict``,
+        ``input_shape``, ``feature_layer_index`` and ``get_weights(sess)``) unless the same
+        weights are already resident."""
+        key = (id(model), getattr(model, '_version', 0))
+        if key == self._model_key:
+            return
+        layers = list(model.layer_dict.items()) if isinstance(model.layer_dict, dict) else list(model.layer_dict)
+        specs = (L.LayerSpec * len(layers))()
+        for i, (name, spec) in enumerate(layers):
+            if spec[1] == 'conv':
+                specs[i] = L.LayerSpec(L.LAYER_CONV, int(spec[0]), int(spec[2][0]), int(spec[2][1]))
+            elif spec[1] == 'pool':
+                specs[i] = L.LayerSpec(L.LAYER_POOL, 0, int(spec[0][0]), int(spec[0][1]))
+            elif spec[1] == 'fc':
+                specs[i] = L.LayerSpec(L.LAYER_FC, int(spec[0]), 0, 0)
+            else:
+                raise ValueError("Layer's type should be either 'fc', 'conv' or 'pool'.")
+        H, W, Cc = model.input_shape
+        fl = model.feature_layer_index if model.feature_layer_index is not None else -1
+        self._chk(self.lib.nnal_model_set(self.h, specs, len(layers), int(H), int(W), int(Cc), int(fl)))
+        weights = model.get_weights(sess)
+        for i, (name, spec) in enumerate(layers):
+            if spec[1] == 'pool':
+                continue
+            Wt, b = weights[name]
+            Wt = np.ascontiguousarray(Wt, dtype=np.float32)
+            b = np.ascontiguousarray(np.ravel(b), dtype=np.float32)
+            self.h2d_bytes += Wt.nbytes + b.nbytes
+            self._chk(self.lib.nnal_model_set_weights(self.h, i, _ptr(Wt), _ptr(b)))
+        nc, fd, pd = C.c_int(), C.c_int(), C.c_int()
+        self._chk(self.lib.nnal_model_info(self.h, C.byref(nc), C.byref(fd), C.byref(pd)))
+        self.n_class, self.feat_dim, self.prev_dim = nc.value, fd.value, pd.value
+        self._model_key = key
+
+    # ------------------------------------------------------------------
+    # volumes
+    # ------------------------------------------------------------------
+    @staticmethod
+    def _as_device_dtype(a):
+        a = np.asarray(a)
+        if a.dtype == np.float32 or a.dtype == np.float64:
+            return np.ascontiguousarray(a)
+        if a.dtype in (np.int8, np.uint8, np.int16, np.uint16):
+            return np.ascontiguousarray(a, dtype=np.float32)      # exact
+        return np.ascontiguousarray(a, dtype=np.float64)          # exact up to 2^53
+
+    def set_volume(self, subject, imgs, pads=(0, 0, 0)):
+        """``imgs``: list of m arrays (X,Y,Z) of one subject (already padded unless ``pads``)."""
+        arrs = [self._as_device_dtype(a) for a in imgs]
+        if any(a.ndim != 3 or a.shape != arrs[0].shape for a in arrs):
+            raise ValueError('all modalities must be 3-D arrays of one shape')
+        if any(a.dtype != arrs[0].dtype for a in arrs):
+            arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
+        key = tuple((a.__array_interface__['data'][0], a.shape, a.dtype.str) for a in arrs) + (tuple(pads),)
+        if self.volume_cache and self._vol_keys.get(subject) == key and all(
+                x is y for x, y in zip(arrs, imgs)):
+            return
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        X, Y, Z = arrs[0].shape
+        dt = L.F64 if arrs[0].dtype == np.float64 else L.F32
+        self.h2d_bytes += sum(a.nbytes for a in arrs)
+        self._chk(self.lib.nnal_volume_set(self.h, int(subject), len(arrs), ptrs, dt, X, Y, Z,
+                                           int(pads[0]), int(pads[1]), int(pads[2])))
+        self._vol_keys[subject] = key
+
+    def invalidate_volumes(self):
+        self._vol_keys = {}
+
+    # ------------------------------------------------------------------
+    # gather
+    # ------------------------------------------------------------------
+    @staticmethod
+    def _check_inds(inds, padded_shape, patch_shape, pads):
+        inds = np.ascontiguousarray(inds, dtype=np.int64).ravel()
+        orig = tuple(int(padded_shape[i] + 2 * pads[i] - (patch_shape[i] - 1)) for i in range(3))
+        nvox = int(np.prod(orig))
+        if inds.size and (inds.min() < 0 or inds.max() >= nvox):
+            # np.unravel_index raises ValueError (patch_utils.py:1144)
+            raise ValueError('index %d is out of bounds for array with size %d'
+                             % (int(inds.max() if inds.max() >= nvox else inds.min()), nvox))
+        return inds, orig
+
+    def gather(self, subject, inds, patch_shape, stats=None, norm_mode=L.NORM_NONE, shape=None, pads=(0, 0, 0)):
+        inds, _ = self._check_inds(inds, shape, patch_shape, pads)
+        d1, d2, d3 = [int(p) for p in patch_shape]
+        m = self._m[subject]
+        out = np.empty((inds.size, d1, d2, m * d3), dtype=np.float64)
+        st = None if stats is None else np.ascontiguousarray(stats, dtype=np.float64)
+        self.h2d_bytes += inds.nbytes
+        self.d2h_bytes += out.nbytes
+        self._chk(self.lib.nnal_gather(self.h, int(subject), _ptr(inds), inds.size, d1, d2, d3,
+                                       None if st is None else _ptr(st), int(norm_mode), _ptr(out)))
+        return out
+
+    def upload(self, subject, imgs, pads=(0, 0, 0)):
+        self.set_volume(subject, imgs, pads)
+        self._m[subject] = len(imgs)
+
+    # ------------------------------------------------------------------
+    # pool pass
+    # ------------------------------------------------------------------
+    def pool_begin(self, n, keep=0):
+        self._chk(self.lib.nnal_pool_begin(self.h, int(n), int(keep)))
+        self._pool_n = int(n)
+
+    def pool_eval(self, subject, inds, offset, patch_shape, stats, norm_mode=L.NORM_BATCH_EVAL, shape=None):
+        inds, _ = self._check_inds(inds, shape, patch_shape, (0, 0, 0))
+        d1, d2, d3 = [int(p) for p in patch_shape]
+        st = None if stats is None else np.ascontiguousarray(stats, dtype=np.float64)
+        self.h2d_bytes += inds.nbytes
+        self._chk(self.lib.nnal_pool_eval(self.h, int(subject), _ptr(inds), inds.size, int(offset), d1, d2, d3,
+                                          None if st is None else _ptr(st), int(norm_mode)))
+
+    def pool_eval_images(self, x, offset):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        self.h2d_bytes += x.nbytes
+        self._chk(self.lib.nnal_pool_eval_images(self.h, _ptr(x), x.shape[0], int(offset)))
+
+    def pool_posteriors(self):
+        out = np.empty((self.n_class, self._pool_n), dtype=np.float32)
+        self.d2h_bytes += out.nbytes
+        self._chk(self.lib.nnal_pool_posteriors(self.h, _ptr(out)))
+        return out
+
+    def pool_features(self, start=0, n=None):
+        n = self._pool_n - start if n is None else n
+        out = np.empty((self.feat_dim, n), dtype=np.float32)
+        self.d2h_bytes += out.nbytes
+        self._chk(self.lib.nnal_pool_features(self.h, int(start), int(n), _ptr(out)))
+        return out
+
+    def pool_score(self, kind, eps=0.0):
+        self._chk(self.lib.nnal_pool_score(self.h, int(kind), float(eps)))
+
+    def pool_scores(self):
+        out = np.empty(self._pool_n, dtype=np.float64)
+        self.d2h_bytes += out.nbytes
+        self._chk(self.lib.nnal_pool_scores_read(self.h, _ptr(out)))
+        return out
+
+    def pool_topk(self, k, with_scores=False):
+        k = int(min(max(k, 0), self._pool_n))
+        idx = np.empty(k, dtype=np.int64)
+        sc = np.empty(k, dtype=np.float64)
+        self.d2h_bytes += idx.nbytes + (sc.nbytes if with_scores else 0)
+        self._chk(self.lib.nnal_pool_topk(self.h, k, _ptr(idx), _ptr(sc) if with_scores else None))
+        return (idx, sc) if with_scores else idx
+
+    # ------------------------------------------------------------------
+    # stand-alone helpers
+    # ------------------------------------------------------------------
+    def entropy(self, P, kind=L.SCORE_ENTROPY, eps=10e-8):
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        c, n = P.shape
+        out = np.empty(n, dtype=np.float64)
+        self.h2d_bytes += P.nbytes
+        self.d2h_bytes += out.nbytes
+        self._chk(self.lib.nnal_entropy(self.h, _ptr(P), c, n, int(kind), float(eps), _ptr(out)))
+        return out
+
+    def topk(self, scores, k):
+        s = np.ascontiguousarray(scores, dtype=np.float64).ravel()
+        k = int(min(max(k, 0), s.size))
+        idx = np.empty(k, dtype=np.int64)
+        self.h2d_bytes += s.nbytes
+        self.d2h_bytes += idx.nbytes
+        self._chk(self.lib.nnal_topk(self.h, _ptr(s), s.size, k, _ptr(idx)))
+        return idx
+
+
+_engine = None
+
+
+def get_engine():
+    """Process-wide engine on the GPU named by LOCAL_RANK (one process per GPU)."""
+    global _engine
+    if _engine is None:
+        _engine = Engine()
+    return _engine
+
+
+def reset_engine():
+    global _engine
+    if _engine is not None:
+        _engine.close()
+    _engine = None
