@@ -151,6 +151,12 @@ int nnal_fi_winner_factors(nnal_ctx* ctx, int64_t cand, float* factors_out, int6
 int nnal_fi_step_apply(nnal_ctx* ctx, int64_t step, const float* winner_factors, int64_t n_floats, int owner_is_local,
                        int64_t cand_local);
 
+/* ---- test hook ---------------------------------------------------------------------------- */
+/* One FC layer out[M][N] = act(A[M][K] W[N][K]^T + b) on host buffers, on the tcgen05 GEMM
+ * (use_tc=1) or the FP32 CUDA-core GEMM (use_tc=0); lets tests check the kernels in isolation. */
+int nnal_debug_fc(nnal_ctx* ctx, const float* A, const float* W, const float* b, int64_t M, int N, int K, int relu,
+                  int use_tc, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -540,3 +540,45 @@ extern "C" int nnal_topk(nnal_ctx* ctx, const double* scores, int64_t n, int64_t
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->act[1].p, scores, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   return topk_to_host(ctx, (const double*)ctx->act[1].p, n, k, idx_out, nullptr);
 }
+
+// ---------------------------------------------------------------------------------------------
+// test hook: one FC layer out = act(A W^T + b) on host buffers (used by tests to compare the
+// tcgen05 GEMM with the FP32 CUDA-core GEMM and the oracle in isolation)
+// ---------------------------------------------------------------------------------------------
+extern "C" int nnal_debug_fc(nnal_ctx* ctx, const float* A, const float* W, const float* b, int64_t M, int N, int K,
+                             int relu, int use_tc, float* out) {
+  if (!ctx || !A || !W || !b || !out || M <= 0 || N <= 0 || K <= 0) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Layer L;
+  L.type = NNAL_LAYER_FC; L.in_dim = K; L.out_dim = N; L.relu = relu;
+  float *dA = nullptr, *dO = nullptr;
+  int rc = NNAL_OK;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    if (dA) cudaFree(dA); if (dO) cudaFree(dO);
+    if (L.W) cudaFree(L.W); if (L.b) cudaFree(L.b); if (L.Wh) cudaFree(L.Wh); if (L.Wl) cudaFree(L.Wl);
+  };
+  if (cudaMalloc(&dA, (size_t)M * K * 4) != cudaSuccess || cudaMalloc(&dO, (size_t)M * N * 4) != cudaSuccess ||
+      cudaMalloc(&L.W, (size_t)N * K * 4) != cudaSuccess || cudaMalloc(&L.b, (size_t)N * 4) != cudaSuccess) {
+    cleanup(); NNAL_FAIL(ctx, NNAL_ERR_CUDA, "debug_fc allocation failed");
+  }
+  cudaMemcpyAsync(dA, A, (size_t)M * K * 4, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(L.W, W, (size_t)N * K * 4, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(L.b, b, (size_t)N * 4, cudaMemcpyHostToDevice, ctx->stream);
+  L.has_weights = true;
+  if (use_tc) {
+    rc = nnal_tc_prepare_layer(ctx, L);
+    if (rc == NNAL_OK && !nnal_tc_fc_supported(ctx, L)) { ctx->err = "shape not supported by the tensor-core FC"; rc = NNAL_ERR_UNSUPPORTED; }
+    if (rc == NNAL_OK) rc = nnal_tc_fc(ctx, L, dA, dO, M);
+  } else {
+    rc = nnal_k_fc_simt(ctx, L, dA, dO, M);
+  }
+  if (rc == NNAL_OK) {
+    if (cudaMemcpyAsync(out, dO, (size_t)M * N * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      ctx->err = std::string("debug_fc: ") + cudaGetErrorString(cudaGetLastError()); rc = NNAL_ERR_CUDA;
+    }
+  }
+  cleanup();
+  return rc;
+}

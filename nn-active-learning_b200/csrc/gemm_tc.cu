@@ -1,6 +1,410 @@
-// tcgen05 FC GEMM -- placeholder
+// tcgen05 / TMEM / TMA GEMM for the fully-connected layers (sm_100a).
+//
+//   out[M][N] = act( A[M][K] . W[N][K]^T + b )          (sample-major restatement of W@x+b, NN.py:322-327)
+//
+// Precision: the north-star tolerance (posteriors within 1e-4 absolute of the float64 oracle) rules out
+// single-pass bf16 / fp16 / tf32 operands (measured: 2e-3 / 1.2e-4 / 1.1e-4 max posterior error on PW1,
+// DESIGN.md §precision).  Operands are therefore split into two bf16 terms x = hi + lo
+// (hi = bf16(x), lo = bf16(x - hi)) and each K-step issues three kind::f16 MMAs
+//   hi.hi + hi.lo + lo.hi      (lo.lo ~ 2^-18 relative is dropped)
+// into one FP32 TMEM accumulator: ~2^-16 relative operand error, 2e-6 max posterior error.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B) of A_hi, A_lo, W_hi, W_lo
+//   warp 1   : MMA issuer    -- one thread issues tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16
+//   warp 2   : TMEM allocator (512 columns = two 128x256 FP32 accumulators, double-buffered)
+//   warps 4-7: epilogue      -- tcgen05.ld 32x32b.x32 -> +bias, ReLU -> global (fp32)
+// smem ring: 2 stages x (2 x 16 KB A + 2 x 32 KB W) = 192 KB, mbarrier full/empty pairs.
 #include "nnal_common.cuh"
-int nnal_tc_prepare_layer(nnal_ctx*, Layer&) { return NNAL_OK; }
-bool nnal_tc_fc_supported(const nnal_ctx*, const Layer&) { return false; }
-int nnal_tc_fc(nnal_ctx* ctx, const Layer&, const float*, float*, int64_t) { NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "tc fc not built"); }
-int nnal_tc_release(nnal_ctx*) { return NNAL_OK; }
+#include <cuda.h>
+
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 2;
+constexpr int A_BYTES = BM * BK * 2;                  // 16 KB
+constexpr int B_BYTES = BN * BK * 2;                  // 32 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 0xfff) == 0xfff) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();     // ~2 s
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | base_offset [49,52) | layout [61,64)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;                  // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;        // SBO: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct FcParams {
+  const float* bias;
+  float* out;
+  __nv_bfloat16* out_hi;     // optional: bf16 split planes of the activated output (next layer's A operand)
+  __nv_bfloat16* out_lo;
+  int ld_split;              // row stride (elements) of the split planes
+  int M, N, num_kb, relu, ldo;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+             const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, FcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024-B alignment
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mblocks = (p.M + BM - 1) / BM, nblocks = (p.N + BN - 1) / BN;
+  const int ntiles = mblocks * nblocks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl));
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int n_blk = t % nblocks, m_blk = t / nblocks;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa = base + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
+          tma_load_2d(sa, &tmAh, full_bar(s), kb * BK, m_blk * BM);
+          tma_load_2d(sa + A_BYTES, &tmAl, full_bar(s), kb * BK, m_blk * BM);
+          tma_load_2d(sa + 2 * A_BYTES, &tmBh, full_bar(s), kb * BK, n_blk * BN);
+          tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmBl, full_bar(s), kb * BK, n_blk * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, BN);
+      uint32_t it = 0, tile_it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_it) {
+        const int acc = tile_it & 1;
+        const uint32_t acc_ph = (tile_it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * STAGE_BYTES;
+          const uint64_t dAh = make_desc_sw128(sa), dAl = make_desc_sw128(sa + A_BYTES);
+          const uint64_t dBh = make_desc_sw128(sa + 2 * A_BYTES), dBl = make_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);              // +32 B per K=16 step (start address >> 4)
+            umma_bf16(d_tmem, dAl + adv, dBh + adv, idesc, (kb | k) != 0);
+            umma_bf16(d_tmem, dAh + adv, dBl + adv, idesc, 1);
+            umma_bf16(d_tmem, dAh + adv, dBh + adv, idesc, 1);
+          }
+          umma_commit(empty_bar(s));                             // frees the smem stage when the MMAs retire
+        }
+        umma_commit(tfull_bar(acc));                             // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;                                      // TMEM lane quarter owned by this warp
+    uint32_t tile_it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_it) {
+      const int n_blk = t % nblocks, m_blk = t / nblocks;
+      const int acc = tile_it & 1;
+      const uint32_t acc_ph = (tile_it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+        const int col0 = n_blk * BN + c0;
+        if (row_ok && col0 < p.N) {
+          if (col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = v[j] + __ldg(p.bias + col0 + j);
+              v[j] = p.relu ? fmaxf(x, 0.f) : x;
+            }
+            if (p.out) {
+              float4* dst = reinterpret_cast<float4*>(p.out + (size_t)row * p.ldo + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (p.out_hi) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+                __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+                __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+                hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              uint4* dh = reinterpret_cast<uint4*>(p.out_hi + (size_t)row * p.ld_split + col0);
+              uint4* dl = reinterpret_cast<uint4*>(p.out_lo + (size_t)row * p.ld_split + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
+              float x = v[j] + __ldg(p.bias + col0 + j);
+              x = p.relu ? fmaxf(x, 0.f) : x;
+              if (p.out) p.out[(size_t)row * p.ldo + col0 + j] = x;
+              if (p.out_hi) {
+                __nv_bfloat16 h = __float2bfloat16_rn(x);
+                p.out_hi[(size_t)row * p.ld_split + col0 + j] = h;
+                p.out_lo[(size_t)row * p.ld_split + col0 + j] = __float2bfloat16_rn(x - __bfloat162float(h));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// fp32 [M][K] -> bf16 hi/lo planes [M][Kp] (zero padded columns)
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                                     __nv_bfloat16* __restrict__ lo, int64_t M, int K, int Kp) {
+  const int64_t total = M * (int64_t)(Kp / 2);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = e / (Kp / 2);
+    int c = (int)(e - r * (Kp / 2)) * 2;
+    float x0 = c < K ? in[r * K + c] : 0.f;
+    float x1 = c + 1 < K ? in[r * K + c + 1] : 0.f;
+    __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    __nv_bfloat162 hv, lv;
+    hv.x = h0; hv.y = h1;
+    lv.x = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+    lv.y = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+    *reinterpret_cast<__nv_bfloat162*>(hi + r * Kp + c) = hv;
+    *reinterpret_cast<__nv_bfloat162*>(lo + r * Kp + c) = lv;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcState {
+  EncodeTiledFn encode = nullptr;
+  bool attr_set = false;
+};
+
+static int get_state(nnal_ctx* ctx, TcState** out) {
+  if (!ctx->tc_state) {
+    TcState* st = new TcState();
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) { delete st; NNAL_FAIL(ctx, NNAL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available"); }
+    st->encode = (EncodeTiledFn)fn;
+    ctx->tc_state = st;
+  }
+  *out = (TcState*)ctx->tc_state;
+  return NNAL_OK;
+}
+
+// 2-D bf16 tensor [rows][ld] (ld elements per row, `cols` valid) with a {64, box_rows} SWIZZLE_128B box
+static int make_tmap(nnal_ctx* ctx, TcState* st, CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld,
+                     uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = st->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) NNAL_FAIL(ctx, NNAL_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return NNAL_OK;
+}
+
+}  // namespace tc
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+bool nnal_tc_fc_supported(const nnal_ctx*, const Layer& L) {
+  return L.type == NNAL_LAYER_FC && L.Wh != nullptr && L.out_dim >= 64 && L.in_dim >= 64 && (L.out_dim % 4) == 0;
+}
+
+// Builds the bf16 hi/lo planes of an FC weight (called from nnal_model_set_weights).
+int nnal_tc_prepare_layer(nnal_ctx* ctx, Layer& L) {
+  if (L.type != NNAL_LAYER_FC || L.out_dim < 64 || L.in_dim < 64) return NNAL_OK;
+  const int Kp = round_up(L.in_dim, tc::BK);
+  if (!L.Wh) {
+    CUDA_TRY(ctx, cudaMalloc(&L.Wh, (size_t)L.out_dim * Kp * 2));
+    CUDA_TRY(ctx, cudaMalloc(&L.Wl, (size_t)L.out_dim * Kp * 2));
+  }
+  L.k_pad = Kp;
+  L.n_pad = L.out_dim;
+  int64_t total = (int64_t)L.out_dim * (Kp / 2);
+  int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  tc::split_kernel<<<grid, 256, 0, ctx->stream>>>(L.W, L.Wh, L.Wl, L.out_dim, L.in_dim, Kp);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+// A operand given as fp32 [n][K]: split into planes, then GEMM.  out fp32 [n][N].
+int nnal_tc_fc(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64_t n) {
+  if (n == 0) return NNAL_OK;
+  tc::TcState* st;
+  NNAL_TRY(tc::get_state(ctx, &st));
+  const int K = L.in_dim, Kp = L.k_pad, N = L.out_dim;
+  const size_t plane = (size_t)n * Kp * 2;
+  NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[0], plane));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[1], plane));
+  __nv_bfloat16* Ah = (__nv_bfloat16*)ctx->splitA[0].p;
+  __nv_bfloat16* Al = (__nv_bfloat16*)ctx->splitA[1].p;
+  {
+    int64_t total = n * (int64_t)(Kp / 2);
+    int grid = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
+    tc::split_kernel<<<grid, 256, 0, ctx->stream>>>(in, Ah, Al, n, K, Kp);
+    ctx->launches++;
+  }
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  NNAL_TRY(tc::make_tmap(ctx, st, &tmAh, Ah, Kp, (uint64_t)n, Kp, tc::BM));
+  NNAL_TRY(tc::make_tmap(ctx, st, &tmAl, Al, Kp, (uint64_t)n, Kp, tc::BM));
+  NNAL_TRY(tc::make_tmap(ctx, st, &tmBh, L.Wh, Kp, (uint64_t)N, Kp, tc::BN));
+  NNAL_TRY(tc::make_tmap(ctx, st, &tmBl, L.Wl, Kp, (uint64_t)N, Kp, tc::BN));
+  if (!st->attr_set) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(tc::fc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    st->attr_set = true;
+  }
+  tc::FcParams p;
+  p.bias = L.b; p.out = out; p.out_hi = nullptr; p.out_lo = nullptr; p.ld_split = 0;
+  p.M = (int)n; p.N = N; p.num_kb = Kp / tc::BK; p.relu = L.relu; p.ldo = N;
+  const int ntiles = cdiv(n, tc::BM) * cdiv(N, tc::BN);
+  const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
+  tc::fc_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, ctx->stream>>>(tmAh, tmAl, tmBh, tmBl, p);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+int nnal_tc_release(nnal_ctx* ctx) {
+  if (ctx->tc_state) { delete (tc::TcState*)ctx->tc_state; ctx->tc_state = nullptr; }
+  return NNAL_OK;
+}

@@ -28,6 +28,7 @@ class Engine(object):
         self.device = device
         self._model_key = None
         self._vol_keys = {}
+        self._vol_refs = {}
         self._m = {}
         self.volume_cache = os.environ.get('NNAL_VOLUME_CACHE', '1') != '0'
         self.h2d_bytes = 0
@@ -84,6 +85,16 @@ class Engine(object):
         self._chk(self.lib.nnal_pool_eval_device_inds(self.h, int(subject), C.c_void_p(int(d_inds_ptr)), int(n),
                                                       int(offset), d1, d2, d3,
                                                       None if st is None else _ptr(st), int(norm_mode)))
+
+    def debug_fc(self, A, W, b, relu, use_tc):
+        A = np.ascontiguousarray(A, dtype=np.float32)
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32).ravel()
+        M, K = A.shape
+        N = W.shape[0]
+        out = np.empty((M, N), dtype=np.float32)
+        self._chk(self.lib.nnal_debug_fc(self.h, _ptr(A), _ptr(W), _ptr(b), M, N, K, int(relu), int(use_tc), _ptr(out)))
+        return out
 
     def set_tensor_cores(self, enable):
         self._chk(self.lib.nnal_set_tensor_cores(self.h, 1 if enable else 0))
@@ -145,9 +156,14 @@ class Engine(object):
             raise ValueError('all modalities must be 3-D arrays of one shape')
         if any(a.dtype != arrs[0].dtype for a in arrs):
             arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
-        key = tuple((a.__array_interface__['data'][0], a.shape, a.dtype.str) for a in arrs) + (tuple(pads),)
-        if self.volume_cache and self._vol_keys.get(subject) == key and all(
-                x is y for x, y in zip(arrs, imgs)):
+        # Cache: the reference passes the same (never modified) padded arrays on every query.  A
+        # subject is skipped only if the very same array OBJECTS (kept alive here, so their memory
+        # cannot be recycled) with an unchanged sampled checksum are passed again.
+        key = tuple((a.shape, a.dtype.str, float(a.ravel()[::max(1, a.size // 4096)].sum(dtype=np.float64)))
+                    for a in arrs) + (tuple(pads),)
+        cached = self._vol_refs.get(subject)
+        if (self.volume_cache and cached is not None and self._vol_keys.get(subject) == key and
+                len(cached) == len(imgs) and all(x is y for x, y in zip(cached, imgs))):
             return
         ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         X, Y, Z = arrs[0].shape
@@ -156,9 +172,11 @@ class Engine(object):
         self._chk(self.lib.nnal_volume_set(self.h, int(subject), len(arrs), ptrs, dt, X, Y, Z,
                                            int(pads[0]), int(pads[1]), int(pads[2])))
         self._vol_keys[subject] = key
+        self._vol_refs[subject] = list(imgs)
 
     def invalidate_volumes(self):
         self._vol_keys = {}
+        self._vol_refs = {}
 
     # ------------------------------------------------------------------
     # gather

@@ -215,3 +215,20 @@ def test_pw_entropy_query_multimg(nb):
     kth = np.sort(score)[39]
     assert np.all(score[got_global] <= kth + POST_TOL)
     assert np.all(np.isin(np.where(score < kth - POST_TOL)[0], got_global))
+
+
+# ------------------------------------------------------------------ tensor-core FC GEMM in isolation
+@pytest.mark.parametrize('M,N,K', [(128, 256, 64), (300, 256, 128), (1000, 320, 200), (777, 4096, 4704),
+                                   (8192, 512, 192), (50, 64, 4096)])
+def test_fc_tcgen05_vs_f64(nb, M, N, K):
+    rs = np.random.RandomState(M + N + K)
+    A = np.maximum(rs.randn(M, K), 0).astype(np.float32) * 3           # post-ReLU-like activations
+    W = (rs.randn(N, K) * np.sqrt(2. / K)).astype(np.float32)
+    b = (rs.randn(N) * .1).astype(np.float32)
+    ref = np.maximum(A.astype(np.float64) @ W.astype(np.float64).T + b, 0)
+    eng = nb.get_engine()
+    got_tc = eng.debug_fc(A, W, b, 1, 1)
+    got_simt = eng.debug_fc(A, W, b, 1, 0)
+    scale = np.abs(ref).max()
+    assert np.abs(got_simt - ref).max() < 2e-5 * scale
+    assert np.abs(got_tc - ref).max() < 2e-5 * scale, 'bf16x3 tcgen05 GEMM off by %g' % (np.abs(got_tc - ref).max() / scale)
