@@ -157,6 +157,11 @@ int nnal_fi_step_apply(nnal_ctx* ctx, int64_t step, const float* winner_factors,
 int nnal_debug_fc(nnal_ctx* ctx, const float* A, const float* W, const float* b, int64_t M, int N, int K, int relu,
                   int use_tc, float* out);
 
+/* One conv layer (SAME, stride 1, bias, ReLU; NN.py:285-290) on host NHWC buffers, tensor-core or
+ * CUDA-core kernel. */
+int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, const float* b, int64_t n, int H, int Wd, int Cin,
+                    int Cout, int ks, int use_tc, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,8 @@ SIGNATURES = {
     'nnal_entropy': (C.c_int, [c_vp, c_vp, C.c_int, C.c_int64, C.c_int, C.c_double, c_vp]),
     'nnal_topk': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, c_vp]),
     'nnal_debug_fc': (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
+    'nnal_debug_conv': (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, c_vp]),
     'nnal_fi_set_candidates': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int]),
     'nnal_fi_gram': (C.c_int, [c_vp, c_vp, c_vp]),
     'nnal_fi_gram_ptr': (c_vp, [c_vp, c_i64p]),

@@ -92,6 +92,8 @@ extern "C" int nnal_synchronize(nnal_ctx* ctx) {
   return NNAL_OK;
 }
 
+bool nnal_layer_on_tc(const nnal_ctx* ctx, int i);
+
 extern "C" int nnal_profile(nnal_ctx* ctx, int enable) {
   if (!ctx) return NNAL_ERR_INVALID;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -124,7 +126,7 @@ extern "C" int nnal_model_layer_info(nnal_ctx* ctx, int layer, int* type, long l
   if (L.type == NNAL_LAYER_CONV) macs = (long long)L.out_h * L.out_w * L.out_c * L.kh * L.kw * L.in_c;
   else if (L.type == NNAL_LAYER_FC) macs = (long long)L.in_dim * L.out_dim;
   if (macs_per_sample) *macs_per_sample = macs;
-  if (uses_tc) *uses_tc = (ctx->use_tc && L.type == NNAL_LAYER_FC && layer != (int)ctx->layers.size() - 1 && nnal_tc_fc_supported(ctx, L)) ? 1 : 0;
+  if (uses_tc) *uses_tc = nnal_layer_on_tc(ctx, layer) ? 1 : 0;
   return NNAL_OK;
 }
 
@@ -325,39 +327,6 @@ extern "C" int nnal_pool_begin(nnal_ctx* ctx, int64_t n_total, int keep) {
   return NNAL_OK;
 }
 
-int nnal_tc_fc(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64_t n);
-
-// forward for nb samples whose normalised float32 NHWC input is in ctx->xin
-static int forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset) {
-  const int nl = (int)ctx->layers.size();
-  const float* cur = (const float*)ctx->xin.p;
-  int pp = 0;
-  for (int i = 0; i < nl; ++i) {
-    const Layer& L = ctx->layers[i];
-    prof_begin(ctx, i);
-    if (i == nl - 1) {
-      NNAL_TRY(nnal_k_head(ctx, L, cur, nb, ctx->pool_n, offset, ctx->pool_post, nullptr));
-      prof_end(ctx);
-      break;
-    }
-    float* out = (float*)ctx->act[pp].p;
-    if (L.type == NNAL_LAYER_FC) {
-      if (ctx->keep >= 1 && i == ctx->feature_layer) out = ctx->pool_feat + offset * (int64_t)ctx->feat_dim;
-      else if (ctx->keep >= 2 && i == ctx->feature_layer - 1 && L.out_dim == ctx->prev_dim) out = ctx->pool_prev + offset * (int64_t)ctx->prev_dim;
-    }
-    if (L.type == NNAL_LAYER_CONV) NNAL_TRY(nnal_k_conv_simt(ctx, L, cur, out, nb));
-    else if (L.type == NNAL_LAYER_POOL) NNAL_TRY(nnal_k_pool(ctx, L, cur, out, nb));
-    else {
-      if (ctx->use_tc && nnal_tc_fc_supported(ctx, L)) NNAL_TRY(nnal_tc_fc(ctx, L, cur, out, nb));
-      else NNAL_TRY(nnal_k_fc_simt(ctx, L, cur, out, nb));
-    }
-    prof_end(ctx);
-    if (out == (float*)ctx->act[pp].p) pp ^= 1;
-    cur = out;
-  }
-  return NNAL_OK;
-}
-
 static int reserve_forward(nnal_ctx* ctx, int64_t nb) {
   size_t mx = (size_t)ctx->in_h * ctx->in_w * ctx->in_c;
   for (auto& L : ctx->layers) {
@@ -397,7 +366,7 @@ static int pool_eval_impl(nnal_ctx* ctx, int subject, const int64_t* inds, bool 
     prof_begin(ctx, NNAL_PROF_GATHER);
     NNAL_TRY(nnal_k_gather_norm_f32(ctx, *v, d_inds + o, nb, d1, d2, d3, d_stats, norm_mode, (float*)ctx->xin.p));
     prof_end(ctx);
-    NNAL_TRY(forward_chunk(ctx, nb, offset + o));
+    NNAL_TRY(nnal_forward_chunk(ctx, nb, offset + o));
   }
   return NNAL_OK;
 }
@@ -424,7 +393,7 @@ extern "C" int nnal_pool_eval_images(nnal_ctx* ctx, const float* x, int64_t n, i
   for (int64_t o = 0; o < n; o += chunk) {
     int64_t nb = std::min(chunk, n - o);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->xin.p, x + o * per, (size_t)nb * per * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    NNAL_TRY(forward_chunk(ctx, nb, offset + o));
+    NNAL_TRY(nnal_forward_chunk(ctx, nb, offset + o));
   }
   return NNAL_OK;
 }
@@ -577,6 +546,50 @@ extern "C" int nnal_debug_fc(nnal_ctx* ctx, const float* A, const float* W, cons
     if (cudaMemcpyAsync(out, dO, (size_t)M * N * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
         cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
       ctx->err = std::string("debug_fc: ") + cudaGetErrorString(cudaGetLastError()); rc = NNAL_ERR_CUDA;
+    }
+  }
+  cleanup();
+  return rc;
+}
+
+// test hook: one conv layer (SAME, stride 1, bias, ReLU) on host NHWC buffers
+extern "C" int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, const float* b, int64_t n, int H, int Wd,
+                               int Cin, int Cout, int ks, int use_tc, float* out) {
+  if (!ctx || !x || !W || !b || !out || n <= 0) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Layer L;
+  L.type = NNAL_LAYER_CONV; L.kh = L.kw = ks; L.in_h = L.out_h = H; L.in_w = L.out_w = Wd; L.in_c = Cin; L.out_c = Cout; L.relu = 1;
+  const size_t ie = (size_t)n * H * Wd * Cin, oe = (size_t)n * H * Wd * Cout;
+  float *dX = nullptr, *dO = nullptr;
+  __nv_bfloat16 *ih = nullptr, *oh = nullptr;
+  int rc = NNAL_OK;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    if (dX) cudaFree(dX); if (dO) cudaFree(dO); if (ih) cudaFree(ih); if (oh) cudaFree(oh);
+    if (L.W) cudaFree(L.W); if (L.b) cudaFree(L.b); if (L.Wh) cudaFree(L.Wh); if (L.Wl) cudaFree(L.Wl);
+  };
+  if (cudaMalloc(&dX, ie * 4) != cudaSuccess || cudaMalloc(&dO, oe * 4) != cudaSuccess || cudaMalloc(&ih, ie * 4) != cudaSuccess ||
+      cudaMalloc(&oh, oe * 4) != cudaSuccess || cudaMalloc(&L.W, (size_t)ks * ks * Cin * Cout * 4) != cudaSuccess ||
+      cudaMalloc(&L.b, (size_t)Cout * 4) != cudaSuccess) {
+    cleanup(); NNAL_FAIL(ctx, NNAL_ERR_CUDA, "debug_conv allocation failed");
+  }
+  cudaMemcpyAsync(dX, x, ie * 4, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(L.W, W, (size_t)ks * ks * Cin * Cout * 4, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(L.b, b, (size_t)Cout * 4, cudaMemcpyHostToDevice, ctx->stream);
+  L.has_weights = true;
+  if (use_tc) {
+    rc = nnal_tc_prepare_layer(ctx, L);
+    if (rc == NNAL_OK && !nnal_tc_conv_supported(ctx, L)) { ctx->err = "shape not supported by the tensor-core conv"; rc = NNAL_ERR_UNSUPPORTED; }
+    if (rc == NNAL_OK) rc = nnal_k_split_flat(ctx, dX, ih, ih + ie, (int64_t)ie);
+    if (rc == NNAL_OK) rc = nnal_tc_conv(ctx, L, ih, ih + ie, oh, oh + oe, n);
+    if (rc == NNAL_OK) rc = nnal_k_merge_flat(ctx, oh, oh + oe, dO, (int64_t)oe);
+  } else {
+    rc = nnal_k_conv_simt(ctx, L, dX, dO, n);
+  }
+  if (rc == NNAL_OK) {
+    if (cudaMemcpyAsync(out, dO, oe * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      ctx->err = std::string("debug_conv: ") + cudaGetErrorString(cudaGetLastError()); rc = NNAL_ERR_CUDA;
     }
   }
   cleanup();

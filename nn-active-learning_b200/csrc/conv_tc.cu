@@ -1,0 +1,455 @@
+// tcgen05 implicit-GEMM convolution (SAME, stride 1, bias, ReLU) for the patch CNN (sm_100a).
+//
+// Replaces tf.nn.conv2d + bias + relu of NN.CNN.add_conv (NN.py:258-301) for layers whose input has
+// a multiple of 8 channels (conv2/conv3/conv4 of PW1).  Precision: 3-term bf16 split as in gemm_tc.cu.
+//
+// "Shift" implicit GEMM -- no im2col is ever materialised:
+//   * A group of G samples is TMA-loaded ONCE into shared memory as zero-padded rasters (TMA
+//     out-of-bounds zero fill reproduces SAME padding), in the no-swizzle K-major UMMA layout built
+//     from 16-byte "chunks": plane q holds channels 8q..8q+7 of every padded position,
+//     addr = q*PLANE + pos*16.  Eight consecutive positions form one 128-byte UMMA core matrix.
+//   * The GEMM rows are padded-raster positions (M tile = 128 consecutive positions); for filter tap
+//     (dy,dx) the A operand is the SAME buffer shifted by (dy*Wp+dx) positions, i.e. only the
+//     descriptor start address changes.  Columns x >= W / rows y >= H of the raster produce garbage
+//     that the epilogue discards.
+//   * One K=16 MMA consumes two chunks (tap,q) whose addresses may be unrelated: the descriptor's
+//     leading-byte-offset is set per instruction, so K = (#taps * Cin/8) chunks is only padded to an
+//     even count (75 -> 76 for conv2), not per tap.
+//   * Weights are pre-arranged per K-step as [2 chunks][Cout][8] bf16 (hi and lo) and streamed through
+//     a 3-stage ring with cp.async.bulk.
+// Warp roles: warp 0 input TMA, warp 3 weight producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue (TMEM -> +bias, ReLU -> bf16 hi/lo NHWC in global memory).
+#include "nnal_common.cuh"
+#include <cuda.h>
+
+namespace ctc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 0xfff) == 0xfff) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();     // protocol bug -> CUDA error, never a hung GPU
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// no-swizzle K-major descriptor: start>>4 | LBO>>4 at [16,30) | SBO>>4 at [32,46) | version 1 | layout 0
+__device__ __forceinline__ uint64_t make_desc_none(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Compile-time geometry of one conv layer
+template <int H_, int W_, int CIN_, int COUT_, int KS_, int G_, int KPS_, int NBUF_, int NACC_>
+struct Cfg {
+  static constexpr int H = H_, W = W_, CIN = CIN_, COUT = COUT_, KS = KS_, G = G_;
+  static constexpr int KPS = KPS_;                       // K-steps per weight stage
+  static constexpr int NBUF = NBUF_, NACC = NACC_;
+  static constexpr int PH = KS / 2;
+  static constexpr int HP = H + KS - 1, WP = W + KS - 1;
+  static constexpr int Q = CIN / 8;
+  static constexpr int NTAPS = KS * KS;
+  static constexpr int NCH = NTAPS * Q;                  // 16-byte chunks along K
+  static constexpr int NK = (NCH + 1) / 2;               // K=16 MMA steps
+  static constexpr int NSTAGE_W = (NK + KPS - 1) / KPS;  // weight stages per group
+  static constexpr int RASTER = G * HP * WP;
+  static constexpr int LAST_VALID = (G - 1) * HP * WP + (H - 1) * WP + (W - 1);
+  static constexpr int T = LAST_VALID / 128 + 1;         // M tiles per group
+  static constexpr int MAX_OFF = (KS - 1) * WP + (KS - 1);
+  static constexpr int PLANE = ((RASTER * 16 + 127) / 128) * 128;                 // bytes
+  static constexpr int OVERRUN = (T * 128 + MAX_OFF + 8 - RASTER) > 0 ? (T * 128 + MAX_OFF + 8 - RASTER) : 0;
+  static constexpr int IN_BYTES = ((2 * Q * PLANE + OVERRUN * 16 + 1023) / 1024) * 1024;   // hi planes then lo planes
+  static constexpr int W_KSTEP_BYTES = 2 * COUT * 16;    // one K-step of one (hi|lo) plane: [2][COUT][8] bf16
+  static constexpr int W_STAGE_BYTES = 2 * KPS * W_KSTEP_BYTES;                   // hi block then lo block
+  static constexpr int WSTAGES = 3;
+  static constexpr int SMEM = NBUF * IN_BYTES + WSTAGES * W_STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS_USED = NACC * T * COUT;
+  static_assert(CIN % 8 == 0, "input channels must be a multiple of 8");
+  static_assert(COUT % 16 == 0 && COUT <= 256, "UMMA N");
+  static_assert(TMEM_COLS_USED <= 512, "TMEM budget");
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+struct ConvParams {
+  const uint8_t* wpack;      // [NSTAGE_W][hi|lo][KPS][2][COUT][8] bf16
+  const float* bias;
+  __nv_bfloat16* out_hi;     // [n][H][W][COUT]
+  __nv_bfloat16* out_lo;
+  int n;
+};
+
+template <class C>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t in_base = base;
+  const uint32_t w_base = base + C::NBUF * C::IN_BYTES;
+  const uint32_t bar0 = w_base + C::WSTAGES * C::W_STAGE_BYTES;
+  // barrier map
+  auto in_full = [&](int b) { return bar0 + 8u * b; };
+  auto in_empty = [&](int b) { return bar0 + 8u * (2 + b); };
+  auto w_full = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto w_empty = [&](int s) { return bar0 + 8u * (7 + s); };
+  auto acc_full = [&](int a) { return bar0 + 8u * (10 + a); };
+  auto acc_empty = [&](int a) { return bar0 + 8u * (12 + a); };
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + C::NBUF * C::IN_BYTES + C::WSTAGES * C::W_STAGE_BYTES + 8 * 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ngroups = (p.n + C::G - 1) / C::G;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmHi));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmLo));
+  }
+  if (warp == 1 && lane == 0) {
+    for (int b = 0; b < 2; ++b) { mbar_init(in_full(b), 1); mbar_init(in_empty(b), 1); }
+    for (int s = 0; s < 3; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== input producer: Q 4-D TMA boxes {8ch, WP, HP, G} per (hi|lo), zero-filled borders =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+        const int b = it % C::NBUF;
+        const uint32_t ph = (it / C::NBUF) & 1;
+        mbar_wait(in_empty(b), ph ^ 1);
+        const uint32_t dst = in_base + b * C::IN_BYTES;
+        mbar_arrive_expect_tx(in_full(b), 2 * C::Q * C::RASTER * 16);
+#pragma unroll 1
+        for (int q = 0; q < C::Q; ++q) {
+          tma_load_4d(dst + q * C::PLANE, &tmHi, in_full(b), q * 8, -C::PH, -C::PH, g * C::G);
+          tma_load_4d(dst + (C::Q + q) * C::PLANE, &tmLo, in_full(b), q * 8, -C::PH, -C::PH, g * C::G);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===== weight producer: one contiguous bulk copy per stage =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        for (int ws = 0; ws < C::NSTAGE_W; ++ws, ++it) {
+          const int s = it % C::WSTAGES;
+          const uint32_t ph = (it / C::WSTAGES) & 1;
+          mbar_wait(w_empty(s), ph ^ 1);
+          mbar_arrive_expect_tx(w_full(s), C::W_STAGE_BYTES);
+          bulk_load(w_base + s * C::W_STAGE_BYTES, p.wpack + (size_t)ws * C::W_STAGE_BYTES, C::W_STAGE_BYTES, w_full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, C::COUT);
+      uint32_t it_in = 0, it_w = 0;
+      for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it_in) {
+        const int b = it_in % C::NBUF;
+        const uint32_t ph_in = (it_in / C::NBUF) & 1;
+        const int a = it_in % C::NACC;
+        const uint32_t ph_acc = (it_in / C::NACC) & 1;
+        mbar_wait(acc_empty(a), ph_acc ^ 1);
+        mbar_wait(in_full(b), ph_in);
+        tc_fence_after();
+        const uint32_t a_hi = in_base + b * C::IN_BYTES;
+        const uint32_t a_lo = a_hi + C::Q * C::PLANE;
+        const uint32_t d_base = tmem_base + a * C::T * C::COUT;
+        for (int ws = 0; ws < C::NSTAGE_W; ++ws, ++it_w) {
+          const int s = it_w % C::WSTAGES;
+          const uint32_t ph = (it_w / C::WSTAGES) & 1;
+          mbar_wait(w_full(s), ph);
+          tc_fence_after();
+          const uint32_t wb_hi = w_base + s * C::W_STAGE_BYTES;
+          const uint32_t wb_lo = wb_hi + C::KPS * C::W_KSTEP_BYTES;
+#pragma unroll 1
+          for (int j = 0; j < C::KPS; ++j) {
+            const int ks = ws * C::KPS + j;
+            if (ks >= C::NK) break;
+            // chunk c -> (q = c / NTAPS, tap = c % NTAPS): q-major order keeps every LBO positive
+            const int c0 = 2 * ks, c1 = 2 * ks + 1;
+            const int q0 = c0 / C::NTAPS, t0 = c0 % C::NTAPS;
+            const uint32_t off0 = q0 * C::PLANE + ((t0 / C::KS) * C::WP + (t0 % C::KS)) * 16;
+            uint32_t lbo = 16;                                    // dummy second chunk (zero weights) stays in-plane
+            if (c1 < C::NCH) {
+              const int q1 = c1 / C::NTAPS, t1 = c1 % C::NTAPS;
+              const uint32_t off1 = q1 * C::PLANE + ((t1 / C::KS) * C::WP + (t1 % C::KS)) * 16;
+              lbo = off1 - off0;
+            }
+            const uint64_t dBh = make_desc_none(wb_hi + j * C::W_KSTEP_BYTES, C::COUT * 16, 128);
+            const uint64_t dBl = make_desc_none(wb_lo + j * C::W_KSTEP_BYTES, C::COUT * 16, 128);
+#pragma unroll 1
+            for (int t = 0; t < C::T; ++t) {
+              const uint32_t rowoff = t * 128 * 16;
+              const uint64_t dAh = make_desc_none(a_hi + off0 + rowoff, lbo, 128);
+              const uint64_t dAl = make_desc_none(a_lo + off0 + rowoff, lbo, 128);
+              const uint32_t d = d_base + t * C::COUT;
+              umma_bf16(d, dAl, dBh, idesc, ks != 0);
+              umma_bf16(d, dAh, dBl, idesc, 1);
+              umma_bf16(d, dAh, dBh, idesc, 1);
+            }
+          }
+          umma_commit(w_empty(s));
+        }
+        umma_commit(in_empty(b));
+        umma_commit(acc_full(a));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int qd = warp & 3;
+    uint32_t it = 0;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+      const int a = it % C::NACC;
+      const uint32_t ph_acc = (it / C::NACC) & 1;
+      mbar_wait(acc_full(a), ph_acc);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < C::T; ++t) {
+        const int pos = t * 128 + qd * 32 + lane;              // padded-raster position of this thread's row
+        const int gs = pos / (C::HP * C::WP);
+        const int rem = pos - gs * (C::HP * C::WP);
+        const int y = rem / C::WP, x = rem - y * C::WP;
+        const int sample = g * C::G + gs;
+        const bool valid = gs < C::G && y < C::H && x < C::W && sample < p.n;
+        const size_t obase = (((size_t)sample * C::H + y) * C::W + x) * C::COUT;
+#pragma unroll 1
+        for (int c0 = 0; c0 < C::COUT; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((a * C::T + t) * C::COUT + c0), v);
+          if (valid) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x0 = fmaxf(v[2 * j] + __ldg(p.bias + c0 + 2 * j), 0.f);
+              float x1 = fmaxf(v[2 * j + 1] + __ldg(p.bias + c0 + 2 * j + 1), 0.f);
+              __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+              __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+              __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+              hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
+            dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(a));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// W fp32 [kh][kw][cin][cout] -> packed bf16 [NSTAGE_W][hi|lo][KPS][2][COUT][8]
+__global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int KS, int CIN, int COUT,
+                                         int KPS, int NK, int NSTAGE) {
+  const int NTAPS = KS * KS, Q = CIN / 8, NCH = NTAPS * Q;
+  const int64_t total = (int64_t)NSTAGE * KPS * 2 * COUT * 8;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int k8 = e % 8;
+    int64_t t = e / 8;
+    int co = t % COUT; t /= COUT;
+    int half = t % 2; t /= 2;
+    int j = t % KPS;
+    int ws = (int)(t / KPS);
+    int ks = ws * KPS + j;
+    int c = 2 * ks + half;
+    float w = 0.f;
+    if (ks < NK && c < NCH) {
+      int q = c / NTAPS, tap = c % NTAPS;
+      int ci = q * 8 + k8;
+      w = W[((int64_t)tap * CIN + ci) * COUT + co];
+    }
+    __nv_bfloat16 h = __float2bfloat16_rn(w);
+    __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+    const int64_t stage_elems = (int64_t)2 * KPS * 2 * COUT * 8;            // hi block + lo block
+    const int64_t in_block = (((int64_t)j * 2 + half) * COUT + co) * 8 + k8;
+    o[ws * stage_elems + in_block] = h;
+    o[ws * stage_elems + (int64_t)KPS * 2 * COUT * 8 + in_block] = l;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+
+// activation tensor [n][H][W][C] bf16 viewed as 4-D (c, x, y, sample) with box {8, WP, HP, G}
+static int make_act_tmap(nnal_ctx* ctx, CUtensorMap* tm, const void* ptr, int n, int H, int W, int C, int WP, int HP, int G) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) NNAL_FAIL(ctx, NNAL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {8, (cuuint32_t)WP, (cuuint32_t)HP, (cuuint32_t)G};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) NNAL_FAIL(ctx, NNAL_ERR_CUDA, "cuTensorMapEncodeTiled (conv activations) failed");
+  return NNAL_OK;
+}
+
+//                 H   W  CIN COUT KS G KPS NBUF NACC
+typedef Cfg<25, 25, 24, 32, 5, 1, 8, 2, 2> CfgConv2;      // PW1 conv2
+typedef Cfg<13, 13, 32, 48, 3, 2, 6, 2, 2> CfgConv3;      // PW1 conv3
+typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2> CfgConv4;      // PW1 conv4
+
+template <class C>
+static bool matches(const Layer& L) {
+  return L.in_h == C::H && L.in_w == C::W && L.in_c == C::CIN && L.out_c == C::COUT && L.kh == C::KS && L.kw == C::KS;
+}
+
+template <class C>
+static int pack(nnal_ctx* ctx, Layer& L) {
+  size_t bytes = (size_t)C::NSTAGE_W * C::W_STAGE_BYTES;
+  if (!L.Wh) CUDA_TRY(ctx, cudaMalloc(&L.Wh, bytes));
+  int64_t total = (int64_t)C::NSTAGE_W * C::KPS * 2 * C::COUT * 8;
+  int grid = (int)((total + 255) / 256);
+  pack_conv_weights_kernel<<<grid, 256, 0, ctx->stream>>>(L.W, (uint8_t*)L.Wh, C::KS, C::CIN, C::COUT, C::KPS, C::NK, C::NSTAGE_W);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+template <class C>
+static int launch(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, __nv_bfloat16* out_hi,
+                  __nv_bfloat16* out_lo, int64_t n) {
+  CUtensorMap tmHi, tmLo;
+  NNAL_TRY(make_act_tmap(ctx, &tmHi, in_hi, (int)n, C::H, C::W, C::CIN, C::WP, C::HP, C::G));
+  NNAL_TRY(make_act_tmap(ctx, &tmLo, in_lo, (int)n, C::H, C::W, C::CIN, C::WP, C::HP, C::G));
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr = true;
+  }
+  ConvParams p;
+  p.wpack = (const uint8_t*)L.Wh; p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.n = (int)n;
+  const int ngroups = (int)((n + C::G - 1) / C::G);
+  const int grid = ngroups < ctx->sm_count ? ngroups : ctx->sm_count;
+  conv_tc_kernel<C><<<grid, 256, C::SMEM, ctx->stream>>>(tmHi, tmLo, p);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+}  // namespace ctc
+
+bool nnal_tc_conv_supported(const nnal_ctx*, const Layer& L) {
+  if (L.type != NNAL_LAYER_CONV || !L.Wh) return false;
+  return ctc::matches<ctc::CfgConv2>(L) || ctc::matches<ctc::CfgConv3>(L) || ctc::matches<ctc::CfgConv4>(L);
+}
+
+int nnal_tc_prepare_conv(nnal_ctx* ctx, Layer& L) {
+  if (L.type != NNAL_LAYER_CONV) return NNAL_OK;
+  if (ctc::matches<ctc::CfgConv2>(L)) return ctc::pack<ctc::CfgConv2>(ctx, L);
+  if (ctc::matches<ctc::CfgConv3>(L)) return ctc::pack<ctc::CfgConv3>(ctx, L);
+  if (ctc::matches<ctc::CfgConv4>(L)) return ctc::pack<ctc::CfgConv4>(ctx, L);
+  return NNAL_OK;
+}
+
+int nnal_tc_conv(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, __nv_bfloat16* out_hi,
+                 __nv_bfloat16* out_lo, int64_t n) {
+  if (n == 0) return NNAL_OK;
+  if (ctc::matches<ctc::CfgConv2>(L)) return ctc::launch<ctc::CfgConv2>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
+  if (ctc::matches<ctc::CfgConv3>(L)) return ctc::launch<ctc::CfgConv3>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
+  if (ctc::matches<ctc::CfgConv4>(L)) return ctc::launch<ctc::CfgConv4>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
+  NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv shape not covered by the tensor-core kernel");
+}

@@ -1,0 +1,125 @@
+// Forward driver: walks the layer list for one chunk of samples and picks, per layer, the tensor-core
+// kernel (bf16 hi/lo operand planes) or the FP32 CUDA-core kernel, converting the activation format
+// only where two neighbouring layers disagree.  Replaces one sess.run(model.posteriors / feature_layer)
+// of PW_NN.batch_eval (PW_NN.py:522-524).
+#include "nnal_common.cuh"
+
+namespace {
+
+struct Act {
+  float* f32 = nullptr;
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  bool split = false;
+  int64_t elems = 0;        // per sample
+};
+
+bool layer_on_tc(const nnal_ctx* ctx, int i) {
+  if (!ctx->use_tc) return false;
+  const int nl = (int)ctx->layers.size();
+  if (i < 0 || i >= nl - 1) return false;               // the last FC runs in the fused head kernel
+  const Layer& L = ctx->layers[i];
+  if (L.type == NNAL_LAYER_CONV) return nnal_tc_conv_supported(ctx, L);
+  if (L.type == NNAL_LAYER_FC) return nnal_tc_fc_supported(ctx, L);
+  return false;
+}
+
+// does the consumer of layer i's output (skipping pools) want bf16 hi/lo planes?
+bool consumer_wants_split(const nnal_ctx* ctx, int i) {
+  const int nl = (int)ctx->layers.size();
+  int j = i + 1;
+  while (j < nl && ctx->layers[j].type == NNAL_LAYER_POOL) ++j;
+  return layer_on_tc(ctx, j);
+}
+
+}  // namespace
+
+bool nnal_layer_on_tc(const nnal_ctx* ctx, int i) { return layer_on_tc(ctx, i); }
+
+int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset) {
+  const int nl = (int)ctx->layers.size();
+  Act cur;
+  cur.f32 = (float*)ctx->xin.p;
+  cur.elems = (int64_t)ctx->in_h * ctx->in_w * ctx->in_c;
+  int pp = 0;
+  auto next_buf = [&](int64_t elems, Act& o) {
+    // both formats occupy 4 bytes per element: fp32, or a bf16 hi plane followed by a bf16 lo plane
+    o.f32 = (float*)ctx->act[pp].p;
+    o.hi = (__nv_bfloat16*)ctx->act[pp].p;
+    o.lo = o.hi + nb * elems;
+    o.elems = elems;
+    pp ^= 1;
+  };
+  auto to_split = [&](Act& a) -> int {
+    if (a.split) return NNAL_OK;
+    Act o; next_buf(a.elems, o);
+    NNAL_TRY(nnal_k_split_flat(ctx, a.f32, o.hi, o.lo, nb * a.elems));
+    o.split = true; a = o;
+    return NNAL_OK;
+  };
+  auto to_f32 = [&](Act& a) -> int {
+    if (!a.split) return NNAL_OK;
+    Act o; next_buf(a.elems, o);
+    NNAL_TRY(nnal_k_merge_flat(ctx, a.hi, a.lo, o.f32, nb * a.elems));
+    o.split = false; a = o;
+    return NNAL_OK;
+  };
+
+  for (int i = 0; i < nl; ++i) {
+    const Layer& L = ctx->layers[i];
+    prof_begin(ctx, i);
+    if (i == nl - 1) {
+      NNAL_TRY(to_f32(cur));
+      NNAL_TRY(nnal_k_head(ctx, L, cur.f32, nb, ctx->pool_n, offset, ctx->pool_post, nullptr));
+      prof_end(ctx);
+      break;
+    }
+    const bool want_split = consumer_wants_split(ctx, i);
+    if (L.type == NNAL_LAYER_CONV) {
+      const int64_t oe = (int64_t)L.out_h * L.out_w * L.out_c;
+      if (layer_on_tc(ctx, i)) {
+        NNAL_TRY(to_split(cur));
+        Act o; next_buf(oe, o);
+        NNAL_TRY(nnal_tc_conv(ctx, L, cur.hi, cur.lo, o.hi, o.lo, nb));
+        o.split = true; cur = o;
+      } else {
+        NNAL_TRY(to_f32(cur));
+        Act o; next_buf(oe, o);
+        if (want_split) { NNAL_TRY(nnal_k_conv_simt_split(ctx, L, cur.f32, o.hi, o.lo, nb)); o.split = true; }
+        else { NNAL_TRY(nnal_k_conv_simt(ctx, L, cur.f32, o.f32, nb)); o.split = false; }
+        cur = o;
+      }
+    } else if (L.type == NNAL_LAYER_POOL) {
+      const int64_t oe = (int64_t)L.out_h * L.out_w * L.out_c;
+      Act o; next_buf(oe, o);
+      if (cur.split) { NNAL_TRY(nnal_k_pool_split(ctx, L, cur.hi, cur.lo, o.hi, o.lo, nb)); o.split = true; }
+      else { NNAL_TRY(nnal_k_pool(ctx, L, cur.f32, o.f32, nb)); o.split = false; }
+      cur = o;
+    } else {
+      // FC (not the last).  fp32 copies wanted by the pool state go straight to their final place.
+      float* keep_dst = nullptr;
+      if (ctx->keep >= 1 && i == ctx->feature_layer) keep_dst = ctx->pool_feat + offset * (int64_t)ctx->feat_dim;
+      else if (ctx->keep >= 2 && i == ctx->feature_layer - 1 && L.out_dim == ctx->prev_dim)
+        keep_dst = ctx->pool_prev + offset * (int64_t)ctx->prev_dim;
+      if (layer_on_tc(ctx, i)) {
+        NNAL_TRY(to_split(cur));
+        Act o; next_buf(L.out_dim, o);
+        float* f32_dst = keep_dst ? keep_dst : (want_split ? nullptr : o.f32);
+        NNAL_TRY(nnal_tc_fc_planes(ctx, L, cur.hi, cur.lo, L.in_dim, f32_dst, want_split ? o.hi : nullptr,
+                                   want_split ? o.lo : nullptr, nb));
+        if (want_split) { o.split = true; }
+        else { o.split = false; if (keep_dst) o.f32 = keep_dst; }
+        cur = o;
+      } else {
+        NNAL_TRY(to_f32(cur));
+        Act o; next_buf(L.out_dim, o);
+        float* dst = keep_dst ? keep_dst : o.f32;
+        NNAL_TRY(nnal_k_fc_simt(ctx, L, cur.f32, dst, nb));
+        o.f32 = dst; o.split = false;
+        cur = o;
+      }
+    }
+    prof_end(ctx);
+  }
+  return NNAL_OK;
+}

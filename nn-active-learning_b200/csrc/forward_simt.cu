@@ -12,6 +12,7 @@
 template <int TP, int TC>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict__ in, const float* __restrict__ Wt,
                                                          const float* __restrict__ bias, float* __restrict__ out,
+                                                         __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
                                                          int64_t n, int H, int Wd, int Cin, int Cout, int kh, int kw) {
   extern __shared__ float s_in[];
   const int ph = kh / 2, pw = kw / 2;
@@ -71,8 +72,16 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict_
           if (p < HW) {
 #pragma unroll
             for (int c = 0; c < TC; ++c)
-              if (co0 + c < Cout)
-                out[(s * HW + p) * (int64_t)Cout + co0 + c] = fmaxf(acc[t][c] + bias[co0 + c], 0.f);
+              if (co0 + c < Cout) {
+                const float v = fmaxf(acc[t][c] + bias[co0 + c], 0.f);
+                const int64_t o = (s * HW + p) * (int64_t)Cout + co0 + c;
+                if (out) out[o] = v;
+                if (out_hi) {
+                  __nv_bfloat16 h = __float2bfloat16_rn(v);
+                  out_hi[o] = h;
+                  out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+                }
+              }
           }
         }
       }
@@ -81,7 +90,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict_
   }
 }
 
-int nnal_k_conv_simt(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64_t n) {
+static int conv_simt_launch(nnal_ctx* ctx, const Layer& L, const float* in, float* out, __nv_bfloat16* out_hi,
+                            __nv_bfloat16* out_lo, int64_t n) {
   if (n == 0) return NNAL_OK;
   size_t smem = (size_t)(L.in_h + L.kh - 1) * (L.in_w + L.kw - 1) * L.in_c * sizeof(float);
   if (smem > 200 * 1024) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv input tile exceeds shared memory");
@@ -89,15 +99,23 @@ int nnal_k_conv_simt(nnal_ctx* ctx, const Layer& L, const float* in, float* out,
   if (L.out_c % 4 == 0) {
     auto k = conv_simt_kernel<8, 4>;
     CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, ctx->stream>>>(in, L.W, L.b, out, n, L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw);
+    k<<<grid, 256, smem, ctx->stream>>>(in, L.W, L.b, out, out_hi, out_lo, n, L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw);
   } else {
     auto k = conv_simt_kernel<8, 1>;
     CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, ctx->stream>>>(in, L.W, L.b, out, n, L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw);
+    k<<<grid, 256, smem, ctx->stream>>>(in, L.W, L.b, out, out_hi, out_lo, n, L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw);
   }
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
+}
+
+int nnal_k_conv_simt(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64_t n) {
+  return conv_simt_launch(ctx, L, in, out, nullptr, nullptr, n);
+}
+// same kernel, output written as bf16 hi/lo planes (operand format of the tensor-core layers)
+int nnal_k_conv_simt_split(nnal_ctx* ctx, const Layer& L, const float* in, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int64_t n) {
+  return conv_simt_launch(ctx, L, in, nullptr, out_hi, out_lo, n);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -123,6 +141,46 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ in,
     }
     out[e] = m;
   }
+}
+
+// max-pool on bf16 hi/lo planes: the max of x = hi + lo is the pair whose sum is largest (exact)
+__global__ void __launch_bounds__(256) pool_split_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                                                          __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                                          int64_t total, int H, int Wd, int C, int Ho, int Wo, int s) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int c = e % C;
+    int64_t t = e / C;
+    int xo = t % Wo; t /= Wo;
+    int yo = t % Ho;
+    int64_t smp = t / Ho;
+    float m = -INFINITY;
+    __nv_bfloat16 bh = __float2bfloat16_rn(0.f), bl = bh;
+    for (int dy = 0; dy < s; ++dy) {
+      int y = yo * s + dy;
+      if (y >= H) break;
+      for (int dx = 0; dx < s; ++dx) {
+        int x = xo * s + dx;
+        if (x >= Wd) break;
+        int64_t idx = ((smp * H + y) * Wd + x) * (int64_t)C + c;
+        __nv_bfloat16 h = in_hi[idx], l = in_lo[idx];
+        float v = __bfloat162float(h) + __bfloat162float(l);
+        if (v > m) { m = v; bh = h; bl = l; }
+      }
+    }
+    out_hi[e] = bh;
+    out_lo[e] = bl;
+  }
+}
+
+int nnal_k_pool_split(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, __nv_bfloat16* out_hi,
+                      __nv_bfloat16* out_lo, int64_t n) {
+  int64_t total = n * L.out_h * L.out_w * L.out_c;
+  if (total == 0) return NNAL_OK;
+  int grid = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
+  pool_split_kernel<<<grid, 256, 0, ctx->stream>>>(in_hi, in_lo, out_hi, out_lo, total, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w, L.kh);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
 }
 
 int nnal_k_pool(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64_t n) {

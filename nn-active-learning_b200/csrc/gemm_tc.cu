@@ -346,11 +346,14 @@ static int make_tmap(nnal_ctx* ctx, TcState* st, CUtensorMap* tm, const void* pt
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 bool nnal_tc_fc_supported(const nnal_ctx*, const Layer& L) {
-  return L.type == NNAL_LAYER_FC && L.Wh != nullptr && L.out_dim >= 64 && L.in_dim >= 64 && (L.out_dim % 4) == 0;
+  return L.type == NNAL_LAYER_FC && L.Wh != nullptr && L.out_dim >= 64 && L.in_dim >= 64 && (L.out_dim % 8) == 0 &&
+         (L.in_dim % 8) == 0;
 }
 
 // Builds the bf16 hi/lo planes of an FC weight (called from nnal_model_set_weights).
+int nnal_tc_prepare_conv(nnal_ctx* ctx, Layer& L);
 int nnal_tc_prepare_layer(nnal_ctx* ctx, Layer& L) {
+  if (L.type == NNAL_LAYER_CONV) return nnal_tc_prepare_conv(ctx, L);
   if (L.type != NNAL_LAYER_FC || L.out_dim < 64 || L.in_dim < 64) return NNAL_OK;
   const int Kp = round_up(L.in_dim, tc::BK);
   if (!L.Wh) {
@@ -367,26 +370,18 @@ int nnal_tc_prepare_layer(nnal_ctx* ctx, Layer& L) {
   return NNAL_OK;
 }
 
-// A operand given as fp32 [n][K]: split into planes, then GEMM.  out fp32 [n][N].
-int nnal_tc_fc(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64_t n) {
+// A operand given as bf16 hi/lo planes [n][lda] (lda >= K, K % 8 == 0; the K tail of the last 64-wide
+// block is zero-filled by TMA).  Outputs: fp32 [n][N] (out, may be null) and/or bf16 hi/lo planes
+// [n][N] of the activated result (the next tensor-core layer's A operand).
+int nnal_tc_fc_planes(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* Ah, const __nv_bfloat16* Al, int lda, float* out,
+                      __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int64_t n) {
   if (n == 0) return NNAL_OK;
   tc::TcState* st;
   NNAL_TRY(tc::get_state(ctx, &st));
   const int K = L.in_dim, Kp = L.k_pad, N = L.out_dim;
-  const size_t plane = (size_t)n * Kp * 2;
-  NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[0], plane));
-  NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[1], plane));
-  __nv_bfloat16* Ah = (__nv_bfloat16*)ctx->splitA[0].p;
-  __nv_bfloat16* Al = (__nv_bfloat16*)ctx->splitA[1].p;
-  {
-    int64_t total = n * (int64_t)(Kp / 2);
-    int grid = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
-    tc::split_kernel<<<grid, 256, 0, ctx->stream>>>(in, Ah, Al, n, K, Kp);
-    ctx->launches++;
-  }
   CUtensorMap tmAh, tmAl, tmBh, tmBl;
-  NNAL_TRY(tc::make_tmap(ctx, st, &tmAh, Ah, Kp, (uint64_t)n, Kp, tc::BM));
-  NNAL_TRY(tc::make_tmap(ctx, st, &tmAl, Al, Kp, (uint64_t)n, Kp, tc::BM));
+  NNAL_TRY(tc::make_tmap(ctx, st, &tmAh, Ah, K, (uint64_t)n, lda, tc::BM));
+  NNAL_TRY(tc::make_tmap(ctx, st, &tmAl, Al, K, (uint64_t)n, lda, tc::BM));
   NNAL_TRY(tc::make_tmap(ctx, st, &tmBh, L.Wh, Kp, (uint64_t)N, Kp, tc::BN));
   NNAL_TRY(tc::make_tmap(ctx, st, &tmBl, L.Wl, Kp, (uint64_t)N, Kp, tc::BN));
   if (!st->attr_set) {
@@ -394,11 +389,59 @@ int nnal_tc_fc(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64
     st->attr_set = true;
   }
   tc::FcParams p;
-  p.bias = L.b; p.out = out; p.out_hi = nullptr; p.out_lo = nullptr; p.ld_split = 0;
+  p.bias = L.b; p.out = out; p.out_hi = out_hi; p.out_lo = out_lo; p.ld_split = N;
   p.M = (int)n; p.N = N; p.num_kb = Kp / tc::BK; p.relu = L.relu; p.ldo = N;
   const int ntiles = cdiv(n, tc::BM) * cdiv(N, tc::BN);
   const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
   tc::fc_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, ctx->stream>>>(tmAh, tmAl, tmBh, tmBl, p);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+// fp32 A operand [n][K]: split into planes first (used by the isolated test hook and mixed pipelines)
+int nnal_tc_fc(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64_t n) {
+  if (n == 0) return NNAL_OK;
+  const int K = L.in_dim, Kp = L.k_pad;
+  const size_t plane = (size_t)n * Kp * 2;
+  NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[0], plane));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[1], plane));
+  __nv_bfloat16* Ah = (__nv_bfloat16*)ctx->splitA[0].p;
+  __nv_bfloat16* Al = (__nv_bfloat16*)ctx->splitA[1].p;
+  int64_t total = n * (int64_t)(Kp / 2);
+  int grid = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
+  tc::split_kernel<<<grid, 256, 0, ctx->stream>>>(in, Ah, Al, n, K, Kp);
+  ctx->launches++;
+  return nnal_tc_fc_planes(ctx, L, Ah, Al, Kp, out, nullptr, nullptr, n);
+}
+
+// flat fp32 <-> bf16 hi/lo conversions (format changes between CUDA-core and tensor-core layers)
+__global__ void __launch_bounds__(256) split_flat_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                                          __nv_bfloat16* __restrict__ lo, int64_t count) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+    float x = in[e];
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[e] = h;
+    lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+__global__ void __launch_bounds__(256) merge_flat_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                                          float* __restrict__ out, int64_t count) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = __bfloat162float(hi[e]) + __bfloat162float(lo[e]);
+}
+int nnal_k_split_flat(nnal_ctx* ctx, const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t count) {
+  if (count == 0) return NNAL_OK;
+  int grid = (int)((count + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (count + 255) / 256 : (int64_t)ctx->sm_count * 16);
+  split_flat_kernel<<<grid, 256, 0, ctx->stream>>>(in, hi, lo, count);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+int nnal_k_merge_flat(nnal_ctx* ctx, const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, int64_t count) {
+  if (count == 0) return NNAL_OK;
+  int grid = (int)((count + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (count + 255) / 256 : (int64_t)ctx->sm_count * 16);
+  merge_flat_kernel<<<grid, 256, 0, ctx->stream>>>(hi, lo, out, count);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;

@@ -96,6 +96,17 @@ class Engine(object):
         self._chk(self.lib.nnal_debug_fc(self.h, _ptr(A), _ptr(W), _ptr(b), M, N, K, int(relu), int(use_tc), _ptr(out)))
         return out
 
+    def debug_conv(self, x, W, b, use_tc):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32).ravel()
+        n, H, Wd, Cin = x.shape
+        ks, _, _, Cout = W.shape
+        out = np.empty((n, H, Wd, Cout), dtype=np.float32)
+        self._chk(self.lib.nnal_debug_conv(self.h, _ptr(x), _ptr(W), _ptr(b), n, H, Wd, Cin, Cout, ks, int(use_tc),
+                                           _ptr(out)))
+        return out
+
     def set_tensor_cores(self, enable):
         self._chk(self.lib.nnal_set_tensor_cores(self.h, 1 if enable else 0))
 

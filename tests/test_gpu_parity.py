@@ -232,3 +232,21 @@ def test_fc_tcgen05_vs_f64(nb, M, N, K):
     scale = np.abs(ref).max()
     assert np.abs(got_simt - ref).max() < 2e-5 * scale
     assert np.abs(got_tc - ref).max() < 2e-5 * scale, 'bf16x3 tcgen05 GEMM off by %g' % (np.abs(got_tc - ref).max() / scale)
+
+
+@pytest.mark.parametrize('H,Cin,Cout,ks', [(25, 24, 32, 5), (13, 32, 48, 3), (13, 48, 96, 3)])
+@pytest.mark.parametrize('n', [1, 5, 300])
+def test_conv_tcgen05_vs_f64(nb, H, Cin, Cout, ks, n):
+    """tcgen05 shift-implicit-GEMM conv (PW1 conv2/conv3/conv4 shapes) vs the float64 oracle."""
+    rs = np.random.RandomState(H + Cin + n)
+    x = np.maximum(rs.randn(n, H, H, Cin), 0).astype(np.float32)
+    W = (rs.randn(ks, ks, Cin, Cout) * np.sqrt(2. / (ks * ks * Cin))).astype(np.float32)
+    b = (rs.randn(Cout) * .1).astype(np.float32)
+    ref = np.maximum(O.conv2d_same(x.astype(np.float64), W.astype(np.float64), b.astype(np.float64)), 0)
+    eng = nb.get_engine()
+    got_simt = eng.debug_conv(x, W, b, 0)
+    scale = np.abs(ref).max()
+    assert np.abs(got_simt - ref).max() < 2e-5 * scale
+    got_tc = eng.debug_conv(x, W, b, 1)
+    err = np.abs(got_tc - ref).max() / scale
+    assert err < 3e-5, 'tcgen05 conv off by %g (relative to max)' % err
