@@ -179,6 +179,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  // Zero the input buffers once: the slack after each plane and after the last plane is never written
+  // by TMA but IS read (second chunk of an odd K tail, overrun rows of the last tile).  Those reads
+  // only ever meet zero weights or discarded rows, but NaN bit patterns in stale shared memory would
+  // still poison valid rows (NaN x 0 = NaN).
+  {
+    uint4* z = reinterpret_cast<uint4*>(base_ptr);
+    for (int i = threadIdx.x; i < C::NBUF * C::IN_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
