@@ -328,7 +328,7 @@ extern "C" int nnal_pool_begin(nnal_ctx* ctx, int64_t n_total, int keep) {
 }
 
 static int reserve_forward(nnal_ctx* ctx, int64_t nb) {
-  size_t mx = (size_t)ctx->in_h * ctx->in_w * ctx->in_c;
+  size_t mx = (size_t)ctx->in_h * ctx->in_w * ((ctx->in_c + 7) / 8 * 8);
   for (auto& L : ctx->layers) {
     size_t o = L.type == NNAL_LAYER_FC ? (size_t)L.out_dim : (size_t)L.out_h * L.out_w * L.out_c;
     mx = std::max(mx, o);
@@ -580,8 +580,11 @@ extern "C" int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, co
   if (use_tc) {
     rc = nnal_tc_prepare_layer(ctx, L);
     if (rc == NNAL_OK && !nnal_tc_conv_supported(ctx, L)) { ctx->err = "shape not supported by the tensor-core conv"; rc = NNAL_ERR_UNSUPPORTED; }
-    if (rc == NNAL_OK) rc = nnal_k_split_flat(ctx, dX, ih, ih + ie, (int64_t)ie);
-    if (rc == NNAL_OK) rc = nnal_tc_conv(ctx, L, ih, ih + ie, oh, oh + oe, n);
+    const int cp = (Cin + 7) / 8 * 8;
+    const size_t iep = (size_t)n * H * Wd * cp;
+    if (cp != Cin) { cudaFree(ih); ih = nullptr; if (cudaMalloc(&ih, iep * 4) != cudaSuccess) { cleanup(); NNAL_FAIL(ctx, NNAL_ERR_CUDA, "debug_conv allocation failed"); } }
+    if (rc == NNAL_OK) rc = nnal_k_split_pad(ctx, dX, ih, ih + iep, (int64_t)n * H * Wd, Cin, cp);
+    if (rc == NNAL_OK) rc = nnal_tc_conv(ctx, L, ih, ih + iep, oh, oh + oe, n);
     if (rc == NNAL_OK) rc = nnal_k_merge_flat(ctx, oh, oh + oe, dO, (int64_t)oe);
   } else {
     rc = nnal_k_conv_simt(ctx, L, dX, dO, n);

@@ -104,9 +104,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // Compile-time geometry of one conv layer
-template <int H_, int W_, int CIN_, int COUT_, int KS_, int G_, int KPS_, int NBUF_, int NACC_>
+template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int NACC_>
 struct Cfg {
-  static constexpr int H = H_, W = W_, CIN = CIN_, COUT = COUT_, KS = KS_, G = G_;
+  // CIN / COUT are the padded operand extents (multiples of 8 / 16); the *_REAL values are the layer's
+  static constexpr int CIN_REAL = CIN_REAL_, COUT_REAL = COUT_REAL_;
+  static constexpr int CIN = (CIN_REAL + 7) / 8 * 8, COUT = (COUT_REAL + 15) / 16 * 16;
+  static constexpr int H = H_, W = W_, KS = KS_, G = G_;
   static constexpr int KPS = KPS_;                       // K-steps per weight stage
   static constexpr int NBUF = NBUF_, NACC = NACC_;
   static constexpr int PH = KS / 2;
@@ -188,6 +191,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     for (int i = threadIdx.x; i < C::NBUF * C::IN_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  // K-step table: chunk c -> (q = c / NTAPS, tap = c % NTAPS); q-major order keeps every LBO positive
+  __shared__ uint2 ktab[C::NK];
+  for (int ks = threadIdx.x; ks < C::NK; ks += blockDim.x) {
+    const int c0 = 2 * ks, c1 = 2 * ks + 1;
+    const int q0 = c0 / C::NTAPS, t0 = c0 % C::NTAPS;
+    const uint32_t off0 = q0 * C::PLANE + ((t0 / C::KS) * C::WP + (t0 % C::KS)) * 16;
+    uint32_t lbo = 16;                    // dummy second chunk of an odd K tail (zero weights) stays in-plane
+    if (c1 < C::NCH) {
+      const int q1 = c1 / C::NTAPS, t1 = c1 % C::NTAPS;
+      lbo = q1 * C::PLANE + ((t1 / C::KS) * C::WP + (t1 % C::KS)) * 16 - off0;
+    }
+    ktab[ks] = make_uint2(off0 >> 4, ((lbo >> 4) & 0x3fffu) << 16);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -226,8 +242,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    // One thread issues every tcgen05.mma; with N as small as 32 an MMA retires in 16-32 clocks, so the
+    // issue loop is kept to a few instructions per MMA: per-K-step descriptor words come from the
+    // table built above, per-tile descriptors differ by a compile-time constant.
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, C::COUT);
+      constexpr uint32_t DESC_HI = 8u /*SBO 128 B*/ | (1u << 14) /*version*/;
+      constexpr uint32_t B_LBO = (uint32_t)C::COUT << 16;       // (COUT*16 B) >> 4 in the LBO field
       uint32_t it_in = 0, it_w = 0;
       for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it_in) {
         const int b = it_in % C::NBUF;
@@ -237,41 +258,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         mbar_wait(acc_empty(a), ph_acc ^ 1);
         mbar_wait(in_full(b), ph_in);
         tc_fence_after();
-        const uint32_t a_hi = in_base + b * C::IN_BYTES;
-        const uint32_t a_lo = a_hi + C::Q * C::PLANE;
+        const uint32_t a_hi16 = (in_base + b * C::IN_BYTES) >> 4;
         const uint32_t d_base = tmem_base + a * C::T * C::COUT;
         for (int ws = 0; ws < C::NSTAGE_W; ++ws, ++it_w) {
           const int s = it_w % C::WSTAGES;
           const uint32_t ph = (it_w / C::WSTAGES) & 1;
           mbar_wait(w_full(s), ph);
           tc_fence_after();
-          const uint32_t wb_hi = w_base + s * C::W_STAGE_BYTES;
-          const uint32_t wb_lo = wb_hi + C::KPS * C::W_KSTEP_BYTES;
-#pragma unroll 1
+          const uint32_t wb16 = (w_base + s * C::W_STAGE_BYTES) >> 4;
+#pragma unroll
           for (int j = 0; j < C::KPS; ++j) {
             const int ks = ws * C::KPS + j;
-            if (ks >= C::NK) break;
-            // chunk c -> (q = c / NTAPS, tap = c % NTAPS): q-major order keeps every LBO positive
-            const int c0 = 2 * ks, c1 = 2 * ks + 1;
-            const int q0 = c0 / C::NTAPS, t0 = c0 % C::NTAPS;
-            const uint32_t off0 = q0 * C::PLANE + ((t0 / C::KS) * C::WP + (t0 % C::KS)) * 16;
-            uint32_t lbo = 16;                                    // dummy second chunk (zero weights) stays in-plane
-            if (c1 < C::NCH) {
-              const int q1 = c1 / C::NTAPS, t1 = c1 % C::NTAPS;
-              const uint32_t off1 = q1 * C::PLANE + ((t1 / C::KS) * C::WP + (t1 % C::KS)) * 16;
-              lbo = off1 - off0;
-            }
-            const uint64_t dBh = make_desc_none(wb_hi + j * C::W_KSTEP_BYTES, C::COUT * 16, 128);
-            const uint64_t dBl = make_desc_none(wb_lo + j * C::W_KSTEP_BYTES, C::COUT * 16, 128);
-#pragma unroll 1
-            for (int t = 0; t < C::T; ++t) {
-              const uint32_t rowoff = t * 128 * 16;
-              const uint64_t dAh = make_desc_none(a_hi + off0 + rowoff, lbo, 128);
-              const uint64_t dAl = make_desc_none(a_lo + off0 + rowoff, lbo, 128);
-              const uint32_t d = d_base + t * C::COUT;
-              umma_bf16(d, dAl, dBh, idesc, ks != 0);
-              umma_bf16(d, dAh, dBl, idesc, 1);
-              umma_bf16(d, dAh, dBh, idesc, 1);
+            if (ks < C::NK) {
+              const uint2 e = ktab[ks];                           // {start offset >> 4, LBO field}
+              const uint32_t ah = (a_hi16 + e.x) | e.y;
+              const uint32_t al = ah + ((C::Q * C::PLANE) >> 4);
+              const uint32_t bh = (wb16 + j * (C::W_KSTEP_BYTES >> 4)) | B_LBO;
+              const uint32_t bl = bh + ((C::KPS * C::W_KSTEP_BYTES) >> 4);
+              const uint64_t dBh = ((uint64_t)DESC_HI << 32) | bh, dBl = ((uint64_t)DESC_HI << 32) | bl;
+              const uint32_t acc0 = ks != 0;
+#pragma unroll
+              for (int t = 0; t < C::T; ++t) {
+                const uint64_t dAh = ((uint64_t)DESC_HI << 32) | (ah + t * 128);
+                const uint64_t dAl = ((uint64_t)DESC_HI << 32) | (al + t * 128);
+                const uint32_t d = d_base + t * C::COUT;
+                umma_bf16(d, dAl, dBh, idesc, acc0);
+                umma_bf16(d, dAh, dBl, idesc, 1);
+                umma_bf16(d, dAh, dBh, idesc, 1);
+              }
             }
           }
           umma_commit(w_empty(s));
@@ -297,17 +311,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         const int y = rem / C::WP, x = rem - y * C::WP;
         const int sample = g * C::G + gs;
         const bool valid = gs < C::G && y < C::H && x < C::W && sample < p.n;
-        const size_t obase = (((size_t)sample * C::H + y) * C::W + x) * C::COUT;
+        const size_t obase = (((size_t)sample * C::H + y) * C::W + x) * C::COUT_REAL;
 #pragma unroll 1
-        for (int c0 = 0; c0 < C::COUT; c0 += 16) {
+        for (int c0 = 0; c0 < C::COUT_REAL; c0 += 16) {
           float v[16];
           tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((a * C::T + t) * C::COUT + c0), v);
           if (valid) {
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float x0 = fmaxf(v[2 * j] + __ldg(p.bias + c0 + 2 * j), 0.f);
-              float x1 = fmaxf(v[2 * j + 1] + __ldg(p.bias + c0 + 2 * j + 1), 0.f);
+              const int ca = c0 + 2 * j < C::COUT_REAL ? c0 + 2 * j : 0, cb = c0 + 2 * j + 1 < C::COUT_REAL ? c0 + 2 * j + 1 : 0;
+              float x0 = fmaxf(v[2 * j] + __ldg(p.bias + ca), 0.f);
+              float x1 = fmaxf(v[2 * j + 1] + __ldg(p.bias + cb), 0.f);
               __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
               __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
               __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
@@ -317,9 +332,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
             uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
             dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
             dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            if (c0 + 8 < C::COUT_REAL) {                     // COUT_REAL is a multiple of 8
+              dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
           }
         }
       }
@@ -339,7 +356,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
 
 // W fp32 [kh][kw][cin][cout] -> packed bf16 [NSTAGE_W][hi|lo][KPS][2][COUT][8]
 __global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int KS, int CIN, int COUT,
-                                         int KPS, int NK, int NSTAGE) {
+                                         int CIN_REAL, int COUT_REAL, int KPS, int NK, int NSTAGE) {
   const int NTAPS = KS * KS, Q = CIN / 8, NCH = NTAPS * Q;
   const int64_t total = (int64_t)NSTAGE * KPS * 2 * COUT * 8;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
@@ -356,7 +373,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* _
     if (ks < NK && c < NCH) {
       int q = c / NTAPS, tap = c % NTAPS;
       int ci = q * 8 + k8;
-      w = W[((int64_t)tap * CIN + ci) * COUT + co];
+      if (ci < CIN_REAL && co < COUT_REAL) w = W[((int64_t)tap * CIN_REAL + ci) * COUT_REAL + co];
     }
     __nv_bfloat16 h = __float2bfloat16_rn(w);
     __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
@@ -397,13 +414,14 @@ static int make_act_tmap(nnal_ctx* ctx, CUtensorMap* tm, const void* ptr, int n,
 }
 
 //                 H   W  CIN COUT KS G KPS NBUF NACC
+typedef Cfg<25, 25, 3, 24, 5, 1, 7, 2, 2> CfgConv1;       // PW1 conv1: 3 input channels zero-padded to one 8-channel chunk
 typedef Cfg<25, 25, 24, 32, 5, 1, 8, 2, 2> CfgConv2;      // PW1 conv2
 typedef Cfg<13, 13, 32, 48, 3, 2, 6, 2, 2> CfgConv3;      // PW1 conv3
 typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2> CfgConv4;      // PW1 conv4
 
 template <class C>
 static bool matches(const Layer& L) {
-  return L.in_h == C::H && L.in_w == C::W && L.in_c == C::CIN && L.out_c == C::COUT && L.kh == C::KS && L.kw == C::KS;
+  return L.in_h == C::H && L.in_w == C::W && L.in_c == C::CIN_REAL && L.out_c == C::COUT_REAL && L.kh == C::KS && L.kw == C::KS;
 }
 
 template <class C>
@@ -412,7 +430,8 @@ static int pack(nnal_ctx* ctx, Layer& L) {
   if (!L.Wh) CUDA_TRY(ctx, cudaMalloc(&L.Wh, bytes));
   int64_t total = (int64_t)C::NSTAGE_W * C::KPS * 2 * C::COUT * 8;
   int grid = (int)((total + 255) / 256);
-  pack_conv_weights_kernel<<<grid, 256, 0, ctx->stream>>>(L.W, (uint8_t*)L.Wh, C::KS, C::CIN, C::COUT, C::KPS, C::NK, C::NSTAGE_W);
+  pack_conv_weights_kernel<<<grid, 256, 0, ctx->stream>>>(L.W, (uint8_t*)L.Wh, C::KS, C::CIN, C::COUT, C::CIN_REAL, C::COUT_REAL, C::KPS, C::NK,
+                                                          C::NSTAGE_W);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
@@ -443,11 +462,13 @@ static int launch(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* in_hi, con
 
 bool nnal_tc_conv_supported(const nnal_ctx*, const Layer& L) {
   if (L.type != NNAL_LAYER_CONV || !L.Wh) return false;
-  return ctc::matches<ctc::CfgConv2>(L) || ctc::matches<ctc::CfgConv3>(L) || ctc::matches<ctc::CfgConv4>(L);
+  return ctc::matches<ctc::CfgConv1>(L) || ctc::matches<ctc::CfgConv2>(L) || ctc::matches<ctc::CfgConv3>(L) ||
+         ctc::matches<ctc::CfgConv4>(L);
 }
 
 int nnal_tc_prepare_conv(nnal_ctx* ctx, Layer& L) {
   if (L.type != NNAL_LAYER_CONV) return NNAL_OK;
+  if (ctc::matches<ctc::CfgConv1>(L)) return ctc::pack<ctc::CfgConv1>(ctx, L);
   if (ctc::matches<ctc::CfgConv2>(L)) return ctc::pack<ctc::CfgConv2>(ctx, L);
   if (ctc::matches<ctc::CfgConv3>(L)) return ctc::pack<ctc::CfgConv3>(ctx, L);
   if (ctc::matches<ctc::CfgConv4>(L)) return ctc::pack<ctc::CfgConv4>(ctx, L);
@@ -457,6 +478,7 @@ int nnal_tc_prepare_conv(nnal_ctx* ctx, Layer& L) {
 int nnal_tc_conv(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, __nv_bfloat16* out_hi,
                  __nv_bfloat16* out_lo, int64_t n) {
   if (n == 0) return NNAL_OK;
+  if (ctc::matches<ctc::CfgConv1>(L)) return ctc::launch<ctc::CfgConv1>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
   if (ctc::matches<ctc::CfgConv2>(L)) return ctc::launch<ctc::CfgConv2>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
   if (ctc::matches<ctc::CfgConv3>(L)) return ctc::launch<ctc::CfgConv3>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
   if (ctc::matches<ctc::CfgConv4>(L)) return ctc::launch<ctc::CfgConv4>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);

@@ -78,7 +78,16 @@ int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset) {
     if (L.type == NNAL_LAYER_CONV) {
       const int64_t oe = (int64_t)L.out_h * L.out_w * L.out_c;
       if (layer_on_tc(ctx, i)) {
-        NNAL_TRY(to_split(cur));
+        if (L.in_c % 8 != 0) {
+          // the tensor-core conv consumes whole 8-channel chunks: zero-pad the channels while splitting
+          NNAL_TRY(to_f32(cur));
+          const int cp = (L.in_c + 7) / 8 * 8;
+          Act o2; next_buf((int64_t)L.in_h * L.in_w * cp, o2);
+          NNAL_TRY(nnal_k_split_pad(ctx, cur.f32, o2.hi, o2.lo, nb * L.in_h * L.in_w, L.in_c, cp));
+          o2.split = true; cur = o2;
+        } else {
+          NNAL_TRY(to_split(cur));
+        }
         Act o; next_buf(oe, o);
         NNAL_TRY(nnal_tc_conv(ctx, L, cur.hi, cur.lo, o.hi, o.lo, nb));
         o.split = true; cur = o;

@@ -143,10 +143,53 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ in,
   }
 }
 
-// max-pool on bf16 hi/lo planes: the max of x = hi + lo is the pair whose sum is largest (exact)
+// max-pool on bf16 hi/lo planes: the max of x = hi + lo is the pair whose sum is largest (exact).
+// One thread pools 8 channels (one 16-byte vector of each plane) of one output position.
+__device__ __forceinline__ void pool8_update(const uint4& h, const uint4& l, float* m, uint32_t* bh, uint32_t* bl) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t hb = (hw[k >> 1] >> ((k & 1) * 16)) & 0xffffu, lb = (lw[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+    const float v = __uint_as_float(hb << 16) + __uint_as_float(lb << 16);
+    if (v > m[k]) { m[k] = v; bh[k] = hb; bl[k] = lb; }
+  }
+}
 __global__ void __launch_bounds__(256) pool_split_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
                                                           __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                                                          int64_t total, int H, int Wd, int C, int Ho, int Wo, int s) {
+                                                          int64_t total8, int H, int Wd, int C, int Ho, int Wo, int s) {
+  const int C8 = C / 8;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total8; e += (int64_t)gridDim.x * blockDim.x) {
+    int c8 = e % C8;
+    int64_t t = e / C8;
+    int xo = t % Wo; t /= Wo;
+    int yo = t % Ho;
+    int64_t smp = t / Ho;
+    float m[8];
+    uint32_t bh[8], bl[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { m[k] = -INFINITY; bh[k] = 0; bl[k] = 0; }
+    for (int dy = 0; dy < s; ++dy) {
+      int y = yo * s + dy;
+      if (y >= H) break;
+      for (int dx = 0; dx < s; ++dx) {
+        int x = xo * s + dx;
+        if (x >= Wd) break;
+        int64_t idx = ((smp * H + y) * Wd + x) * (int64_t)C + c8 * 8;
+        uint4 h = *reinterpret_cast<const uint4*>(in_hi + idx);
+        uint4 l = *reinterpret_cast<const uint4*>(in_lo + idx);
+        pool8_update(h, l, m, bh, bl);
+      }
+    }
+    uint4 oh = make_uint4(bh[0] | (bh[1] << 16), bh[2] | (bh[3] << 16), bh[4] | (bh[5] << 16), bh[6] | (bh[7] << 16));
+    uint4 ol = make_uint4(bl[0] | (bl[1] << 16), bl[2] | (bl[3] << 16), bl[4] | (bl[5] << 16), bl[6] | (bl[7] << 16));
+    *reinterpret_cast<uint4*>(out_hi + e * 8) = oh;
+    *reinterpret_cast<uint4*>(out_lo + e * 8) = ol;
+  }
+}
+// scalar variant for channel counts that are not a multiple of 8
+__global__ void __launch_bounds__(256) pool_split_scalar_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                                                                 __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                                                 int64_t total, int H, int Wd, int C, int Ho, int Wo, int s) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int c = e % C;
     int64_t t = e / C;
@@ -176,8 +219,14 @@ int nnal_k_pool_split(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* in_hi,
                       __nv_bfloat16* out_lo, int64_t n) {
   int64_t total = n * L.out_h * L.out_w * L.out_c;
   if (total == 0) return NNAL_OK;
-  int grid = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
-  pool_split_kernel<<<grid, 256, 0, ctx->stream>>>(in_hi, in_lo, out_hi, out_lo, total, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w, L.kh);
+  if (L.out_c % 8 == 0) {
+    int64_t total8 = total / 8;
+    int grid = (int)((total8 + 255) / 256 < (int64_t)ctx->sm_count * 32 ? (total8 + 255) / 256 : (int64_t)ctx->sm_count * 32);
+    pool_split_kernel<<<grid, 256, 0, ctx->stream>>>(in_hi, in_lo, out_hi, out_lo, total8, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w, L.kh);
+  } else {
+    int grid = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
+    pool_split_scalar_kernel<<<grid, 256, 0, ctx->stream>>>(in_hi, in_lo, out_hi, out_lo, total, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w, L.kh);
+  }
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;

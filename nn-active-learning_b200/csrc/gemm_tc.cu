@@ -430,6 +430,29 @@ __global__ void __launch_bounds__(256) merge_flat_kernel(const __nv_bfloat16* __
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
     out[e] = __bfloat162float(hi[e]) + __bfloat162float(lo[e]);
 }
+// fp32 [rows][C] -> bf16 hi/lo [rows][Cp] with zero-padded channels (conv1: 3 -> 8, one UMMA chunk per pixel)
+__global__ void __launch_bounds__(256) split_pad_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo, int64_t rows, int C, int Cp) {
+  const int64_t total = rows * Cp;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / Cp;
+    const int c = (int)(e - r * Cp);
+    const float x = c < C ? in[r * C + c] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[e] = h;
+    lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+int nnal_k_split_pad(nnal_ctx* ctx, const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t rows, int C, int Cp) {
+  const int64_t total = rows * Cp;
+  if (total == 0) return NNAL_OK;
+  int grid = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
+  split_pad_kernel<<<grid, 256, 0, ctx->stream>>>(in, hi, lo, rows, C, Cp);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
 int nnal_k_split_flat(nnal_ctx* ctx, const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t count) {
   if (count == 0) return NNAL_OK;
   int grid = (int)((count + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (count + 255) / 256 : (int64_t)ctx->sm_count * 16);

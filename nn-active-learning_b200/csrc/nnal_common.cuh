@@ -156,6 +156,7 @@ int nnal_tc_fc(nnal_ctx*, const Layer&, const float* in, float* out, int64_t n);
 int nnal_tc_fc_planes(nnal_ctx*, const Layer&, const __nv_bfloat16* Ah, const __nv_bfloat16* Al, int lda, float* out,
                       __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int64_t n);
 int nnal_k_split_flat(nnal_ctx*, const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t count);
+int nnal_k_split_pad(nnal_ctx*, const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t rows, int C, int Cp);
 int nnal_k_merge_flat(nnal_ctx*, const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, int64_t count);
 bool nnal_tc_conv_supported(const nnal_ctx*, const Layer&);
 int nnal_tc_conv(nnal_ctx*, const Layer&, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, __nv_bfloat16* out_hi,

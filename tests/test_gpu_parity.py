@@ -234,7 +234,7 @@ def test_fc_tcgen05_vs_f64(nb, M, N, K):
     assert np.abs(got_tc - ref).max() < 2e-5 * scale, 'bf16x3 tcgen05 GEMM off by %g' % (np.abs(got_tc - ref).max() / scale)
 
 
-@pytest.mark.parametrize('H,Cin,Cout,ks', [(25, 24, 32, 5), (13, 32, 48, 3), (13, 48, 96, 3)])
+@pytest.mark.parametrize('H,Cin,Cout,ks', [(25, 3, 24, 5), (25, 24, 32, 5), (13, 32, 48, 3), (13, 48, 96, 3)])
 @pytest.mark.parametrize('n', [1, 5, 300])
 def test_conv_tcgen05_vs_f64(nb, H, Cin, Cout, ks, n):
     """tcgen05 shift-implicit-GEMM conv (PW1 conv2/conv3/conv4 shapes) vs the float64 oracle."""
