@@ -87,6 +87,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// one elected lane of a converged warp (lets ptxas issue tcgen05/TMA ops without per-thread retry loops)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -245,7 +255,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     // One thread issues every tcgen05.mma; with N as small as 32 an MMA retires in 16-32 clocks, so the
     // issue loop is kept to a few instructions per MMA: per-K-step descriptor words come from the
     // table built above, per-tile descriptors differ by a compile-time constant.
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_bf16(128, C::COUT);
       constexpr uint32_t DESC_HI = 8u /*SBO 128 B*/ | (1u << 14) /*version*/;
       constexpr uint32_t B_LBO = (uint32_t)C::COUT << 16;       // (COUT*16 B) >> 4 in the LBO field
@@ -266,32 +276,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
           mbar_wait(w_full(s), ph);
           tc_fence_after();
           const uint32_t wb16 = (w_base + s * C::W_STAGE_BYTES) >> 4;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int j = 0; j < C::KPS; ++j) {
-            const int ks = ws * C::KPS + j;
-            if (ks < C::NK) {
-              const uint2 e = ktab[ks];                           // {start offset >> 4, LBO field}
-              const uint32_t ah = (a_hi16 + e.x) | e.y;
-              const uint32_t al = ah + ((C::Q * C::PLANE) >> 4);
-              const uint32_t bh = (wb16 + j * (C::W_KSTEP_BYTES >> 4)) | B_LBO;
-              const uint32_t bl = bh + ((C::KPS * C::W_KSTEP_BYTES) >> 4);
-              const uint64_t dBh = ((uint64_t)DESC_HI << 32) | bh, dBl = ((uint64_t)DESC_HI << 32) | bl;
-              const uint32_t acc0 = ks != 0;
+            for (int j = 0; j < C::KPS; ++j) {
+              const int ks = ws * C::KPS + j;
+              if (ks < C::NK) {
+                const uint2 e = ktab[ks];                           // {start offset >> 4, LBO field}
+                const uint32_t ah = (a_hi16 + e.x) | e.y;
+                const uint32_t al = ah + ((C::Q * C::PLANE) >> 4);
+                const uint32_t bh = (wb16 + j * (C::W_KSTEP_BYTES >> 4)) | B_LBO;
+                const uint32_t bl = bh + ((C::KPS * C::W_KSTEP_BYTES) >> 4);
+                const uint64_t dBh = ((uint64_t)DESC_HI << 32) | bh, dBl = ((uint64_t)DESC_HI << 32) | bl;
+                const uint32_t acc0 = ks != 0;
 #pragma unroll
-              for (int t = 0; t < C::T; ++t) {
-                const uint64_t dAh = ((uint64_t)DESC_HI << 32) | (ah + t * 128);
-                const uint64_t dAl = ((uint64_t)DESC_HI << 32) | (al + t * 128);
-                const uint32_t d = d_base + t * C::COUT;
-                umma_bf16(d, dAl, dBh, idesc, acc0);
-                umma_bf16(d, dAh, dBl, idesc, 1);
-                umma_bf16(d, dAh, dBh, idesc, 1);
+                for (int t = 0; t < C::T; ++t) {
+                  const uint64_t dAh = ((uint64_t)DESC_HI << 32) | (ah + t * 128);
+                  const uint64_t dAl = ((uint64_t)DESC_HI << 32) | (al + t * 128);
+                  const uint32_t d = d_base + t * C::COUT;
+                  umma_bf16(d, dAl, dBh, idesc, acc0);
+                  umma_bf16(d, dAh, dBl, idesc, 1);
+                  umma_bf16(d, dAh, dBh, idesc, 1);
+                }
               }
             }
+            umma_commit(w_empty(s));
           }
-          umma_commit(w_empty(s));
+          __syncwarp();
         }
-        umma_commit(in_empty(b));
-        umma_commit(acc_full(a));
+        if (elect_one_sync()) {
+          umma_commit(in_empty(b));
+          umma_commit(acc_full(a));
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

@@ -94,6 +94,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -180,21 +189,21 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, BN);
-      uint32_t it = 0, tile_it = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_it) {
-        const int acc = tile_it & 1;
-        const uint32_t acc_ph = (tile_it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+    // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
+    const uint32_t idesc = make_idesc_bf16(BM, BN);
+    uint32_t it = 0, tile_it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_it) {
+      const int acc = tile_it & 1;
+      const uint32_t acc_ph = (tile_it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t sa = base + s * STAGE_BYTES;
           const uint64_t dAh = make_desc_sw128(sa), dAl = make_desc_sw128(sa + A_BYTES);
           const uint64_t dBh = make_desc_sw128(sa + 2 * A_BYTES), dBl = make_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
@@ -206,8 +215,9 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
             umma_bf16(d_tmem, dAh + adv, dBh + adv, idesc, 1);
           }
           umma_commit(empty_bar(s));                             // frees the smem stage when the MMAs retire
+          if (kb == p.num_kb - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         }
-        umma_commit(tfull_bar(acc));                             // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
