@@ -2,6 +2,7 @@
 #include "nnal_common.cuh"
 #include "../../include/nnal_b200.h"
 #include <cstdlib>
+#include <cmath>
 #include <algorithm>
 
 static const int NNAL_VERSION = 100;
@@ -194,6 +195,19 @@ extern "C" int nnal_model_info(nnal_ctx* ctx, int* n_class, int* feat_dim, int* 
   return NNAL_OK;
 }
 
+// power-of-two scale that lifts max|W| to [2^13, 2^14): fp16 hi terms stay far from overflow and the
+// lo terms (2^-11 of hi) stay out of the subnormal range for all but negligible weights
+static void nnal_set_weight_scale(Layer& L, const float* W, size_t n) {
+  float mx = 0.f;
+  for (size_t i = 0; i < n; ++i) { float a = fabsf(W[i]); if (a > mx && a < 3.0e38f) mx = a; }
+  int e = 0;
+  if (mx > 0.f) { int ex; frexpf(mx, &ex); e = 14 - ex; }       // mx = f * 2^ex, f in [0.5,1)
+  if (e > 24) e = 24;
+  if (e < -24) e = -24;
+  L.w_scale = ldexpf(1.f, e);
+  L.w_scale_inv = ldexpf(1.f, -e);
+}
+
 extern "C" int nnal_model_set_weights(nnal_ctx* ctx, int layer, const float* W, const float* b) {
   if (!ctx || !W || !b) return NNAL_ERR_INVALID;
   if (layer < 0 || layer >= (int)ctx->layers.size()) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "layer index out of range");
@@ -214,6 +228,7 @@ extern "C" int nnal_model_set_weights(nnal_ctx* ctx, int layer, const float* W, 
     CUDA_TRY(ctx, cudaMemcpyAsync(L.W, W, wn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   }
   L.has_weights = true;
+  nnal_set_weight_scale(L, W, wn);
   NNAL_TRY(nnal_tc_prepare_layer(ctx, L));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return NNAL_OK;
@@ -535,6 +550,7 @@ extern "C" int nnal_debug_fc(nnal_ctx* ctx, const float* A, const float* W, cons
   cudaMemcpyAsync(L.W, W, (size_t)N * K * 4, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(L.b, b, (size_t)N * 4, cudaMemcpyHostToDevice, ctx->stream);
   L.has_weights = true;
+  nnal_set_weight_scale(L, W, (size_t)N * K);
   if (use_tc) {
     rc = nnal_tc_prepare_layer(ctx, L);
     if (rc == NNAL_OK && !nnal_tc_fc_supported(ctx, L)) { ctx->err = "shape not supported by the tensor-core FC"; rc = NNAL_ERR_UNSUPPORTED; }
@@ -561,7 +577,7 @@ extern "C" int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, co
   L.type = NNAL_LAYER_CONV; L.kh = L.kw = ks; L.in_h = L.out_h = H; L.in_w = L.out_w = Wd; L.in_c = Cin; L.out_c = Cout; L.relu = 1;
   const size_t ie = (size_t)n * H * Wd * Cin, oe = (size_t)n * H * Wd * Cout;
   float *dX = nullptr, *dO = nullptr;
-  __nv_bfloat16 *ih = nullptr, *oh = nullptr;
+  nnal_h *ih = nullptr, *oh = nullptr;
   int rc = NNAL_OK;
   auto cleanup = [&]() {
     cudaStreamSynchronize(ctx->stream);
@@ -577,6 +593,7 @@ extern "C" int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, co
   cudaMemcpyAsync(L.W, W, (size_t)ks * ks * Cin * Cout * 4, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(L.b, b, (size_t)Cout * 4, cudaMemcpyHostToDevice, ctx->stream);
   L.has_weights = true;
+  nnal_set_weight_scale(L, W, (size_t)ks * ks * Cin * Cout);
   if (use_tc) {
     rc = nnal_tc_prepare_layer(ctx, L);
     if (rc == NNAL_OK && !nnal_tc_conv_supported(ctx, L)) { ctx->err = "shape not supported by the tensor-core conv"; rc = NNAL_ERR_UNSUPPORTED; }

@@ -73,8 +73,8 @@ __device__ __forceinline__ uint64_t make_desc_none(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;
   return d;
 }
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {       // A/B format 0 = F16
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -150,9 +150,10 @@ struct Cfg {
 struct ConvParams {
   const uint8_t* wpack;      // [NSTAGE_W][hi|lo][KPS][2][COUT][8] bf16
   const float* bias;
-  __nv_bfloat16* out_hi;     // [n][H][W][COUT]
-  __nv_bfloat16* out_lo;
+  nnal_h* out_hi;     // [n][H][W][COUT]
+  nnal_h* out_lo;
   int n;
+  float w_scale_inv;
 };
 
 template <class C>
@@ -337,13 +338,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int ca = c0 + 2 * j < C::COUT_REAL ? c0 + 2 * j : 0, cb = c0 + 2 * j + 1 < C::COUT_REAL ? c0 + 2 * j + 1 : 0;
-              float x0 = fmaxf(v[2 * j] + __ldg(p.bias + ca), 0.f);
-              float x1 = fmaxf(v[2 * j + 1] + __ldg(p.bias + cb), 0.f);
-              __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-              __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-              __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-              hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              float x0 = fmaxf(v[2 * j] * p.w_scale_inv + __ldg(p.bias + ca), 0.f);
+              float x1 = fmaxf(v[2 * j + 1] * p.w_scale_inv + __ldg(p.bias + cb), 0.f);
+              nnal_h h0, h1, l0, l1;
+              nnal_split(x0, h0, l0);
+              nnal_split(x1, h1, l1);
+              hi[j] = nnal_pack2(h0, h1);
+              lo[j] = nnal_pack2(l0, l1);
             }
             uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
             uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
@@ -372,10 +373,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
 
 // W fp32 [kh][kw][cin][cout] -> packed bf16 [NSTAGE_W][hi|lo][KPS][2][COUT][8]
 __global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int KS, int CIN, int COUT,
-                                         int CIN_REAL, int COUT_REAL, int KPS, int NK, int NSTAGE) {
+                                         int CIN_REAL, int COUT_REAL, int KPS, int NK, int NSTAGE, float scale) {
   const int NTAPS = KS * KS, Q = CIN / 8, NCH = NTAPS * Q;
   const int64_t total = (int64_t)NSTAGE * KPS * 2 * COUT * 8;
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  nnal_h* o = reinterpret_cast<nnal_h*>(out);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int k8 = e % 8;
     int64_t t = e / 8;
@@ -389,10 +390,10 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* _
     if (ks < NK && c < NCH) {
       int q = c / NTAPS, tap = c % NTAPS;
       int ci = q * 8 + k8;
-      if (ci < CIN_REAL && co < COUT_REAL) w = W[((int64_t)tap * CIN_REAL + ci) * COUT_REAL + co];
+      if (ci < CIN_REAL && co < COUT_REAL) w = W[((int64_t)tap * CIN_REAL + ci) * COUT_REAL + co] * scale;
     }
-    __nv_bfloat16 h = __float2bfloat16_rn(w);
-    __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+    nnal_h h, l;
+    nnal_split(w, h, l);
     const int64_t stage_elems = (int64_t)2 * KPS * 2 * COUT * 8;            // hi block + lo block
     const int64_t in_block = (((int64_t)j * 2 + half) * COUT + co) * 8 + k8;
     o[ws * stage_elems + in_block] = h;
@@ -422,7 +423,7 @@ static int make_act_tmap(nnal_ctx* ctx, CUtensorMap* tm, const void* ptr, int n,
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {8, (cuuint32_t)WP, (cuuint32_t)HP, (cuuint32_t)G};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) NNAL_FAIL(ctx, NNAL_ERR_CUDA, "cuTensorMapEncodeTiled (conv activations) failed");
@@ -447,15 +448,15 @@ static int pack(nnal_ctx* ctx, Layer& L) {
   int64_t total = (int64_t)C::NSTAGE_W * C::KPS * 2 * C::COUT * 8;
   int grid = (int)((total + 255) / 256);
   pack_conv_weights_kernel<<<grid, 256, 0, ctx->stream>>>(L.W, (uint8_t*)L.Wh, C::KS, C::CIN, C::COUT, C::CIN_REAL, C::COUT_REAL, C::KPS, C::NK,
-                                                          C::NSTAGE_W);
+                                                          C::NSTAGE_W, L.w_scale);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
 }
 
 template <class C>
-static int launch(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, __nv_bfloat16* out_hi,
-                  __nv_bfloat16* out_lo, int64_t n) {
+static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
+                  nnal_h* out_lo, int64_t n) {
   CUtensorMap tmHi, tmLo;
   NNAL_TRY(make_act_tmap(ctx, &tmHi, in_hi, (int)n, C::H, C::W, C::CIN, C::WP, C::HP, C::G));
   NNAL_TRY(make_act_tmap(ctx, &tmLo, in_lo, (int)n, C::H, C::W, C::CIN, C::WP, C::HP, C::G));
@@ -465,7 +466,7 @@ static int launch(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* in_hi, con
     attr = true;
   }
   ConvParams p;
-  p.wpack = (const uint8_t*)L.Wh; p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.n = (int)n;
+  p.wpack = (const uint8_t*)L.Wh; p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.n = (int)n; p.w_scale_inv = L.w_scale_inv;
   const int ngroups = (int)((n + C::G - 1) / C::G);
   const int grid = ngroups < ctx->sm_count ? ngroups : ctx->sm_count;
   conv_tc_kernel<C><<<grid, 256, C::SMEM, ctx->stream>>>(tmHi, tmLo, p);
@@ -491,8 +492,8 @@ int nnal_tc_prepare_conv(nnal_ctx* ctx, Layer& L) {
   return NNAL_OK;
 }
 
-int nnal_tc_conv(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, __nv_bfloat16* out_hi,
-                 __nv_bfloat16* out_lo, int64_t n) {
+int nnal_tc_conv(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
+                 nnal_h* out_lo, int64_t n) {
   if (n == 0) return NNAL_OK;
   if (ctc::matches<ctc::CfgConv1>(L)) return ctc::launch<ctc::CfgConv1>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
   if (ctc::matches<ctc::CfgConv2>(L)) return ctc::launch<ctc::CfgConv2>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);

@@ -8,8 +8,8 @@ namespace {
 
 struct Act {
   float* f32 = nullptr;
-  __nv_bfloat16* hi = nullptr;
-  __nv_bfloat16* lo = nullptr;
+  nnal_h* hi = nullptr;
+  nnal_h* lo = nullptr;
   bool split = false;
   int64_t elems = 0;        // per sample
 };
@@ -45,7 +45,7 @@ int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset) {
   auto next_buf = [&](int64_t elems, Act& o) {
     // both formats occupy 4 bytes per element: fp32, or a bf16 hi plane followed by a bf16 lo plane
     o.f32 = (float*)ctx->act[pp].p;
-    o.hi = (__nv_bfloat16*)ctx->act[pp].p;
+    o.hi = (nnal_h*)ctx->act[pp].p;
     o.lo = o.hi + nb * elems;
     o.elems = elems;
     pp ^= 1;

@@ -12,7 +12,7 @@
 template <int TP, int TC>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict__ in, const float* __restrict__ Wt,
                                                          const float* __restrict__ bias, float* __restrict__ out,
-                                                         __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                                         nnal_h* __restrict__ out_hi, nnal_h* __restrict__ out_lo,
                                                          int64_t n, int H, int Wd, int Cin, int Cout, int kh, int kw) {
   extern __shared__ float s_in[];
   const int ph = kh / 2, pw = kw / 2;
@@ -77,9 +77,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict_
                 const int64_t o = (s * HW + p) * (int64_t)Cout + co0 + c;
                 if (out) out[o] = v;
                 if (out_hi) {
-                  __nv_bfloat16 h = __float2bfloat16_rn(v);
+                  nnal_h h, l;
+                  nnal_split(v, h, l);
                   out_hi[o] = h;
-                  out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+                  out_lo[o] = l;
                 }
               }
           }
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict_
   }
 }
 
-static int conv_simt_launch(nnal_ctx* ctx, const Layer& L, const float* in, float* out, __nv_bfloat16* out_hi,
-                            __nv_bfloat16* out_lo, int64_t n) {
+static int conv_simt_launch(nnal_ctx* ctx, const Layer& L, const float* in, float* out, nnal_h* out_hi,
+                            nnal_h* out_lo, int64_t n) {
   if (n == 0) return NNAL_OK;
   size_t smem = (size_t)(L.in_h + L.kh - 1) * (L.in_w + L.kw - 1) * L.in_c * sizeof(float);
   if (smem > 200 * 1024) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv input tile exceeds shared memory");
@@ -114,7 +115,7 @@ int nnal_k_conv_simt(nnal_ctx* ctx, const Layer& L, const float* in, float* out,
   return conv_simt_launch(ctx, L, in, out, nullptr, nullptr, n);
 }
 // same kernel, output written as bf16 hi/lo planes (operand format of the tensor-core layers)
-int nnal_k_conv_simt_split(nnal_ctx* ctx, const Layer& L, const float* in, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int64_t n) {
+int nnal_k_conv_simt_split(nnal_ctx* ctx, const Layer& L, const float* in, nnal_h* out_hi, nnal_h* out_lo, int64_t n) {
   return conv_simt_launch(ctx, L, in, nullptr, out_hi, out_lo, n);
 }
 
@@ -150,12 +151,12 @@ __device__ __forceinline__ void pool8_update(const uint4& h, const uint4& l, flo
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const uint32_t hb = (hw[k >> 1] >> ((k & 1) * 16)) & 0xffffu, lb = (lw[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-    const float v = __uint_as_float(hb << 16) + __uint_as_float(lb << 16);
+    const float v = __half2float(__ushort_as_half((unsigned short)hb)) + __half2float(__ushort_as_half((unsigned short)lb));
     if (v > m[k]) { m[k] = v; bh[k] = hb; bl[k] = lb; }
   }
 }
-__global__ void __launch_bounds__(256) pool_split_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
-                                                          __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+__global__ void __launch_bounds__(256) pool_split_kernel(const nnal_h* __restrict__ in_hi, const nnal_h* __restrict__ in_lo,
+                                                          nnal_h* __restrict__ out_hi, nnal_h* __restrict__ out_lo,
                                                           int64_t total8, int H, int Wd, int C, int Ho, int Wo, int s) {
   const int C8 = C / 8;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total8; e += (int64_t)gridDim.x * blockDim.x) {
@@ -187,8 +188,8 @@ __global__ void __launch_bounds__(256) pool_split_kernel(const __nv_bfloat16* __
   }
 }
 // scalar variant for channel counts that are not a multiple of 8
-__global__ void __launch_bounds__(256) pool_split_scalar_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
-                                                                 __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+__global__ void __launch_bounds__(256) pool_split_scalar_kernel(const nnal_h* __restrict__ in_hi, const nnal_h* __restrict__ in_lo,
+                                                                 nnal_h* __restrict__ out_hi, nnal_h* __restrict__ out_lo,
                                                                  int64_t total, int H, int Wd, int C, int Ho, int Wo, int s) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int c = e % C;
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(256) pool_split_scalar_kernel(const __nv_bfloa
     int yo = t % Ho;
     int64_t smp = t / Ho;
     float m = -INFINITY;
-    __nv_bfloat16 bh = __float2bfloat16_rn(0.f), bl = bh;
+    nnal_h bh = __float2half_rn(0.f), bl = bh;
     for (int dy = 0; dy < s; ++dy) {
       int y = yo * s + dy;
       if (y >= H) break;
@@ -205,8 +206,8 @@ __global__ void __launch_bounds__(256) pool_split_scalar_kernel(const __nv_bfloa
         int x = xo * s + dx;
         if (x >= Wd) break;
         int64_t idx = ((smp * H + y) * Wd + x) * (int64_t)C + c;
-        __nv_bfloat16 h = in_hi[idx], l = in_lo[idx];
-        float v = __bfloat162float(h) + __bfloat162float(l);
+        nnal_h h = in_hi[idx], l = in_lo[idx];
+        float v = nnal_merge(h, l);
         if (v > m) { m = v; bh = h; bl = l; }
       }
     }
@@ -215,8 +216,8 @@ __global__ void __launch_bounds__(256) pool_split_scalar_kernel(const __nv_bfloa
   }
 }
 
-int nnal_k_pool_split(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, __nv_bfloat16* out_hi,
-                      __nv_bfloat16* out_lo, int64_t n) {
+int nnal_k_pool_split(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
+                      nnal_h* out_lo, int64_t n) {
   int64_t total = n * L.out_h * L.out_w * L.out_c;
   if (total == 0) return NNAL_OK;
   if (L.out_c % 8 == 0) {

@@ -79,8 +79,9 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 }
 
 // kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+// (A/B format field 0 = F16; 1 would be BF16)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -125,10 +126,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 struct FcParams {
   const float* bias;
   float* out;
-  __nv_bfloat16* out_hi;     // optional: bf16 split planes of the activated output (next layer's A operand)
-  __nv_bfloat16* out_lo;
+  nnal_h* out_hi;     // optional: bf16 split planes of the activated output (next layer's A operand)
+  nnal_h* out_lo;
   int ld_split;              // row stride (elements) of the split planes
   int M, N, num_kb, relu, ldo;
+  float w_scale_inv;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -241,7 +243,7 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
           if (col0 + 32 <= p.N) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float x = v[j] + __ldg(p.bias + col0 + j);
+              float x = v[j] * p.w_scale_inv + __ldg(p.bias + col0 + j);
               v[j] = p.relu ? fmaxf(x, 0.f) : x;
             }
             if (p.out) {
@@ -253,11 +255,11 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
               uint32_t hi[16], lo[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-                __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-                __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-                hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                nnal_h h0, h1, l0, l1;
+                nnal_split(v[2 * j], h0, l0);
+                nnal_split(v[2 * j + 1], h1, l1);
+                hi[j] = nnal_pack2(h0, h1);
+                lo[j] = nnal_pack2(l0, l1);
               }
               uint4* dh = reinterpret_cast<uint4*>(p.out_hi + (size_t)row * p.ld_split + col0);
               uint4* dl = reinterpret_cast<uint4*>(p.out_lo + (size_t)row * p.ld_split + col0);
@@ -269,13 +271,14 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
             }
           } else {
             for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
-              float x = v[j] + __ldg(p.bias + col0 + j);
+              float x = v[j] * p.w_scale_inv + __ldg(p.bias + col0 + j);
               x = p.relu ? fmaxf(x, 0.f) : x;
               if (p.out) p.out[(size_t)row * p.ldo + col0 + j] = x;
               if (p.out_hi) {
-                __nv_bfloat16 h = __float2bfloat16_rn(x);
+                nnal_h h, l;
+                nnal_split(x, h, l);
                 p.out_hi[(size_t)row * p.ld_split + col0 + j] = h;
-                p.out_lo[(size_t)row * p.ld_split + col0 + j] = __float2bfloat16_rn(x - __bfloat162float(h));
+                p.out_lo[(size_t)row * p.ld_split + col0 + j] = l;
               }
             }
           }
@@ -296,21 +299,19 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
 }
 
 // fp32 [M][K] -> bf16 hi/lo planes [M][Kp] (zero padded columns)
-__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
-                                                     __nv_bfloat16* __restrict__ lo, int64_t M, int K, int Kp) {
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ in, nnal_h* __restrict__ hi,
+                                                     nnal_h* __restrict__ lo, int64_t M, int K, int Kp, float scale) {
   const int64_t total = M * (int64_t)(Kp / 2);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = e / (Kp / 2);
     int c = (int)(e - r * (Kp / 2)) * 2;
-    float x0 = c < K ? in[r * K + c] : 0.f;
-    float x1 = c + 1 < K ? in[r * K + c + 1] : 0.f;
-    __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    __nv_bfloat162 hv, lv;
-    hv.x = h0; hv.y = h1;
-    lv.x = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-    lv.y = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-    *reinterpret_cast<__nv_bfloat162*>(hi + r * Kp + c) = hv;
-    *reinterpret_cast<__nv_bfloat162*>(lo + r * Kp + c) = lv;
+    float x0 = c < K ? in[r * K + c] * scale : 0.f;
+    float x1 = c + 1 < K ? in[r * K + c + 1] * scale : 0.f;
+    nnal_h h0, h1, l0, l1;
+    nnal_split(x0, h0, l0);
+    nnal_split(x1, h1, l1);
+    *reinterpret_cast<uint32_t*>(hi + r * Kp + c) = nnal_pack2(h0, h1);
+    *reinterpret_cast<uint32_t*>(lo + r * Kp + c) = nnal_pack2(l0, l1);
   }
 }
 
@@ -344,7 +345,7 @@ static int make_tmap(nnal_ctx* ctx, TcState* st, CUtensorMap* tm, const void* pt
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = st->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = st->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) NNAL_FAIL(ctx, NNAL_ERR_CUDA, "cuTensorMapEncodeTiled failed");
@@ -374,7 +375,7 @@ int nnal_tc_prepare_layer(nnal_ctx* ctx, Layer& L) {
   L.n_pad = L.out_dim;
   int64_t total = (int64_t)L.out_dim * (Kp / 2);
   int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  tc::split_kernel<<<grid, 256, 0, ctx->stream>>>(L.W, L.Wh, L.Wl, L.out_dim, L.in_dim, Kp);
+  tc::split_kernel<<<grid, 256, 0, ctx->stream>>>(L.W, L.Wh, L.Wl, L.out_dim, L.in_dim, Kp, L.w_scale);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
@@ -383,8 +384,8 @@ int nnal_tc_prepare_layer(nnal_ctx* ctx, Layer& L) {
 // A operand given as bf16 hi/lo planes [n][lda] (lda >= K, K % 8 == 0; the K tail of the last 64-wide
 // block is zero-filled by TMA).  Outputs: fp32 [n][N] (out, may be null) and/or bf16 hi/lo planes
 // [n][N] of the activated result (the next tensor-core layer's A operand).
-int nnal_tc_fc_planes(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* Ah, const __nv_bfloat16* Al, int lda, float* out,
-                      __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int64_t n) {
+int nnal_tc_fc_planes(nnal_ctx* ctx, const Layer& L, const nnal_h* Ah, const nnal_h* Al, int lda, float* out,
+                      nnal_h* out_hi, nnal_h* out_lo, int64_t n) {
   if (n == 0) return NNAL_OK;
   tc::TcState* st;
   NNAL_TRY(tc::get_state(ctx, &st));
@@ -400,7 +401,7 @@ int nnal_tc_fc_planes(nnal_ctx* ctx, const Layer& L, const __nv_bfloat16* Ah, co
   }
   tc::FcParams p;
   p.bias = L.b; p.out = out; p.out_hi = out_hi; p.out_lo = out_lo; p.ld_split = N;
-  p.M = (int)n; p.N = N; p.num_kb = Kp / tc::BK; p.relu = L.relu; p.ldo = N;
+  p.M = (int)n; p.N = N; p.num_kb = Kp / tc::BK; p.relu = L.relu; p.ldo = N; p.w_scale_inv = L.w_scale_inv;
   const int ntiles = cdiv(n, tc::BM) * cdiv(N, tc::BN);
   const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
   tc::fc_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, ctx->stream>>>(tmAh, tmAl, tmBh, tmBl, p);
@@ -416,44 +417,45 @@ int nnal_tc_fc(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64
   const size_t plane = (size_t)n * Kp * 2;
   NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[0], plane));
   NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[1], plane));
-  __nv_bfloat16* Ah = (__nv_bfloat16*)ctx->splitA[0].p;
-  __nv_bfloat16* Al = (__nv_bfloat16*)ctx->splitA[1].p;
+  nnal_h* Ah = (nnal_h*)ctx->splitA[0].p;
+  nnal_h* Al = (nnal_h*)ctx->splitA[1].p;
   int64_t total = n * (int64_t)(Kp / 2);
   int grid = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
-  tc::split_kernel<<<grid, 256, 0, ctx->stream>>>(in, Ah, Al, n, K, Kp);
+  tc::split_kernel<<<grid, 256, 0, ctx->stream>>>(in, Ah, Al, n, K, Kp, 1.f);
   ctx->launches++;
   return nnal_tc_fc_planes(ctx, L, Ah, Al, Kp, out, nullptr, nullptr, n);
 }
 
 // flat fp32 <-> bf16 hi/lo conversions (format changes between CUDA-core and tensor-core layers)
-__global__ void __launch_bounds__(256) split_flat_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
-                                                          __nv_bfloat16* __restrict__ lo, int64_t count) {
+__global__ void __launch_bounds__(256) split_flat_kernel(const float* __restrict__ in, nnal_h* __restrict__ hi,
+                                                          nnal_h* __restrict__ lo, int64_t count) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
-    float x = in[e];
-    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    nnal_h h, l;
+    nnal_split(in[e], h, l);
     hi[e] = h;
-    lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
+    lo[e] = l;
   }
 }
-__global__ void __launch_bounds__(256) merge_flat_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+__global__ void __launch_bounds__(256) merge_flat_kernel(const nnal_h* __restrict__ hi, const nnal_h* __restrict__ lo,
                                                           float* __restrict__ out, int64_t count) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
-    out[e] = __bfloat162float(hi[e]) + __bfloat162float(lo[e]);
+    out[e] = nnal_merge(hi[e], lo[e]);
 }
 // fp32 [rows][C] -> bf16 hi/lo [rows][Cp] with zero-padded channels (conv1: 3 -> 8, one UMMA chunk per pixel)
-__global__ void __launch_bounds__(256) split_pad_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
-                                                         __nv_bfloat16* __restrict__ lo, int64_t rows, int C, int Cp) {
+__global__ void __launch_bounds__(256) split_pad_kernel(const float* __restrict__ in, nnal_h* __restrict__ hi,
+                                                         nnal_h* __restrict__ lo, int64_t rows, int C, int Cp) {
   const int64_t total = rows * Cp;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / Cp;
     const int c = (int)(e - r * Cp);
     const float x = c < C ? in[r * C + c] : 0.f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    nnal_h h, l;
+    nnal_split(x, h, l);
     hi[e] = h;
-    lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
+    lo[e] = l;
   }
 }
-int nnal_k_split_pad(nnal_ctx* ctx, const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t rows, int C, int Cp) {
+int nnal_k_split_pad(nnal_ctx* ctx, const float* in, nnal_h* hi, nnal_h* lo, int64_t rows, int C, int Cp) {
   const int64_t total = rows * Cp;
   if (total == 0) return NNAL_OK;
   int grid = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
@@ -463,7 +465,7 @@ int nnal_k_split_pad(nnal_ctx* ctx, const float* in, __nv_bfloat16* hi, __nv_bfl
   return NNAL_OK;
 }
 
-int nnal_k_split_flat(nnal_ctx* ctx, const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t count) {
+int nnal_k_split_flat(nnal_ctx* ctx, const float* in, nnal_h* hi, nnal_h* lo, int64_t count) {
   if (count == 0) return NNAL_OK;
   int grid = (int)((count + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (count + 255) / 256 : (int64_t)ctx->sm_count * 16);
   split_flat_kernel<<<grid, 256, 0, ctx->stream>>>(in, hi, lo, count);
@@ -471,7 +473,7 @@ int nnal_k_split_flat(nnal_ctx* ctx, const float* in, __nv_bfloat16* hi, __nv_bf
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
 }
-int nnal_k_merge_flat(nnal_ctx* ctx, const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, int64_t count) {
+int nnal_k_merge_flat(nnal_ctx* ctx, const nnal_h* hi, const nnal_h* lo, float* out, int64_t count) {
   if (count == 0) return NNAL_OK;
   int grid = (int)((count + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (count + 255) / 256 : (int64_t)ctx->sm_count * 16);
   merge_flat_kernel<<<grid, 256, 0, ctx->stream>>>(hi, lo, out, count);

@@ -1,7 +1,7 @@
 // Shared declarations of libnnal_b200 (sm_100a only).  See include/nnal_b200.h for the C ABI.
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -18,6 +18,24 @@
 enum { NNAL_LAYER_CONV = 0, NNAL_LAYER_POOL = 1, NNAL_LAYER_FC = 2 };
 enum { NNAL_F32 = 0, NNAL_F64 = 1 };
 
+// Operand element type of the tensor-core path.  Every fp32 value x is carried as two fp16 terms
+// x ~= hi + lo (hi = fp16(x), lo = fp16(x - hi)): 22 significant bits, products hi.hi + hi.lo + lo.hi.
+// (bf16 terms were measured first: 2^-18 relative operand error, too coarse for the 1e-4 posterior
+// tolerance at 1e5-sample pools; fp16 terms have the same MMA rate.)  Weights are pre-scaled by a
+// power of two so that their lo terms stay in fp16's normal range; epilogues undo the scale.
+typedef __half nnal_h;
+#ifdef __CUDACC__
+__device__ __forceinline__ void nnal_split(float x, nnal_h& h, nnal_h& l) {
+  x = fminf(fmaxf(x, -65504.f), 65504.f);
+  h = __float2half_rn(x);
+  l = __float2half_rn(x - __half2float(h));
+}
+__device__ __forceinline__ float nnal_merge(nnal_h h, nnal_h l) { return __half2float(h) + __half2float(l); }
+__device__ __forceinline__ uint32_t nnal_pack2(nnal_h a, nnal_h b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+#endif
+
 struct LayerSpec { int type, out, kh, kw; };
 
 struct Layer {
@@ -31,10 +49,11 @@ struct Layer {
   float* W = nullptr;                    // conv: [kh][kw][cin][cout]; fc: [out][in_native]
   float* b = nullptr;
   // bf16 split planes for the tensor-core path (hi = bf16(x), lo = bf16(x - hi))
-  __nv_bfloat16* Wh = nullptr;
-  __nv_bfloat16* Wl = nullptr;
+  nnal_h* Wh = nullptr;
+  nnal_h* Wl = nullptr;
   int k_pad = 0;                         // padded K of the split planes
   int n_pad = 0;                         // padded N (rows) of the split planes
+  float w_scale = 1.f, w_scale_inv = 1.f; // power-of-two scale applied to the fp16 weight planes
 };
 
 struct Volume {
@@ -153,15 +172,15 @@ int nnal_tc_prepare_layer(nnal_ctx*, Layer&);
 bool nnal_tc_fc_supported(const nnal_ctx*, const Layer&);
 int nnal_tc_release(nnal_ctx*);
 int nnal_tc_fc(nnal_ctx*, const Layer&, const float* in, float* out, int64_t n);
-int nnal_tc_fc_planes(nnal_ctx*, const Layer&, const __nv_bfloat16* Ah, const __nv_bfloat16* Al, int lda, float* out,
-                      __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int64_t n);
-int nnal_k_split_flat(nnal_ctx*, const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t count);
-int nnal_k_split_pad(nnal_ctx*, const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t rows, int C, int Cp);
-int nnal_k_merge_flat(nnal_ctx*, const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, int64_t count);
+int nnal_tc_fc_planes(nnal_ctx*, const Layer&, const nnal_h* Ah, const nnal_h* Al, int lda, float* out,
+                      nnal_h* out_hi, nnal_h* out_lo, int64_t n);
+int nnal_k_split_flat(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t count);
+int nnal_k_split_pad(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t rows, int C, int Cp);
+int nnal_k_merge_flat(nnal_ctx*, const nnal_h* hi, const nnal_h* lo, float* out, int64_t count);
 bool nnal_tc_conv_supported(const nnal_ctx*, const Layer&);
-int nnal_tc_conv(nnal_ctx*, const Layer&, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, __nv_bfloat16* out_hi,
-                 __nv_bfloat16* out_lo, int64_t n);
-int nnal_k_conv_simt_split(nnal_ctx*, const Layer&, const float* in, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int64_t n);
-int nnal_k_pool_split(nnal_ctx*, const Layer&, const __nv_bfloat16* in_hi, const __nv_bfloat16* in_lo, __nv_bfloat16* out_hi,
-                      __nv_bfloat16* out_lo, int64_t n);
+int nnal_tc_conv(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
+                 nnal_h* out_lo, int64_t n);
+int nnal_k_conv_simt_split(nnal_ctx*, const Layer&, const float* in, nnal_h* out_hi, nnal_h* out_lo, int64_t n);
+int nnal_k_pool_split(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
+                      nnal_h* out_lo, int64_t n);
 int nnal_forward_chunk(nnal_ctx*, int64_t nb, int64_t offset);
