@@ -9,12 +9,18 @@
 //   hi.hi + hi.lo + lo.hi      (lo.lo ~ 2^-18 relative is dropped)
 // into one FP32 TMEM accumulator: ~2^-16 relative operand error, 2e-6 max posterior error.
 //
-// Structure (one persistent CTA per SM, 256 threads):
-//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B) of A_hi, A_lo, W_hi, W_lo
-//   warp 1   : MMA issuer    -- one thread issues tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16
-//   warp 2   : TMEM allocator (512 columns = two 128x256 FP32 accumulators, double-buffered)
-//   warps 4-7: epilogue      -- tcgen05.ld 32x32b.x32 -> +bias, ReLU -> global (fp32)
+// Structure (one persistent CTA per SM, 384 threads):
+//   warp 0    : TMA producer  -- cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B) of A_hi, A_lo, W_hi, W_lo
+//   warp 1    : MMA issuer    -- one elected lane issues tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16
+//   warp 2    : TMEM allocator (512 columns = two 128x256 FP32 accumulators)
+//   warps 4-11: epilogue      -- tcgen05.ld -> FP32 register sums -> +bias, ReLU -> global (fp32 / fp16 hi,lo)
 // smem ring: 2 stages x (2 x 16 KB A + 2 x 32 KB W) = 192 KB, mbarrier full/empty pairs.
+//
+// Chunked accumulation.  The tensor core adds into its FP32 accumulator with round-toward-zero
+// (measured on B200: signed bias -1.1e-5 of the output rms at K=4704, shrinking linearly with the
+// number of accumulations -- profiles/r1_precision.md).  The K loop is therefore cut into chunks of
+// CHUNK_KB k-blocks; each chunk accumulates from zero into one of the two TMEM buffers while the
+// epilogue warps drain the other one and add it to per-thread FP32 sums with round-to-nearest.
 #include "nnal_common.cuh"
 #include <cuda.h>
 
@@ -25,7 +31,8 @@ constexpr int A_BYTES = BM * BK * 2;                  // 16 KB
 constexpr int B_BYTES = BN * BK * 2;                  // 32 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
+constexpr int CHUNK_KB = 8;                           // k-blocks (of 64) accumulated inside the tensor core
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -123,6 +130,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 struct FcParams {
   const float* bias;
   float* out;
@@ -159,7 +179,7 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -193,68 +213,87 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
     const uint32_t idesc = make_idesc_bf16(BM, BN);
-    uint32_t it = 0, tile_it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_it) {
-      const int acc = tile_it & 1;
-      const uint32_t acc_ph = (tile_it >> 1) & 1;
-      mbar_wait(tempty_bar(acc), acc_ph ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
+    uint32_t it = 0, cc = 0;                                     // smem-stage counter, accumulation-chunk counter
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int kb0 = 0; kb0 < p.num_kb; kb0 += CHUNK_KB, ++cc) {
+        const int acc = cc & 1;
+        const uint32_t acc_ph = (cc >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1);
         tc_fence_after();
-        if (elect_one_sync()) {
-          const uint32_t sa = base + s * STAGE_BYTES;
-          const uint64_t dAh = make_desc_sw128(sa), dAl = make_desc_sw128(sa + A_BYTES);
-          const uint64_t dBh = make_desc_sw128(sa + 2 * A_BYTES), dBl = make_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const int kb1 = kb0 + CHUNK_KB < p.num_kb ? kb0 + CHUNK_KB : p.num_kb;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t sa = base + s * STAGE_BYTES;
+            const uint64_t dAh = make_desc_sw128(sa), dAl = make_desc_sw128(sa + A_BYTES);
+            const uint64_t dBh = make_desc_sw128(sa + 2 * A_BYTES), dBl = make_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2);              // +32 B per K=16 step (start address >> 4)
-            umma_bf16(d_tmem, dAl + adv, dBh + adv, idesc, (kb | k) != 0);
-            umma_bf16(d_tmem, dAh + adv, dBl + adv, idesc, 1);
-            umma_bf16(d_tmem, dAh + adv, dBh + adv, idesc, 1);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);            // +32 B per K=16 step (start address >> 4)
+              umma_bf16(d_tmem, dAl + adv, dBh + adv, idesc, ((kb - kb0) | k) != 0);
+              umma_bf16(d_tmem, dAh + adv, dBl + adv, idesc, 1);
+              umma_bf16(d_tmem, dAh + adv, dBh + adv, idesc, 1);
+            }
+            umma_commit(empty_bar(s));                           // frees the smem stage when the MMAs retire
+            if (kb == kb1 - 1) umma_commit(tfull_bar(acc));      // chunk complete -> epilogue
           }
-          umma_commit(empty_bar(s));                             // frees the smem stage when the MMAs retire
-          if (kb == p.num_kb - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: drain each chunk from TMEM into FP32 register sums (round-to-nearest adds) =====
     const int q = warp & 3;                                      // TMEM lane quarter owned by this warp
-    uint32_t tile_it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_it) {
+    const int half = (warp - 4) >> 2;                            // which 128 of the 256 accumulator columns
+    uint32_t cc = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int n_blk = t % nblocks, m_blk = t / nblocks;
-      const int acc = tile_it & 1;
-      const uint32_t acc_ph = (tile_it >> 1) & 1;
-      mbar_wait(tfull_bar(acc), acc_ph);
-      tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-        const int col0 = n_blk * BN + c0;
-        if (row_ok && col0 < p.N) {
-          if (col0 + 32 <= p.N) {
+      float sum[128];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = v[j] * p.w_scale_inv + __ldg(p.bias + col0 + j);
+      for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+      for (int kb0 = 0; kb0 < p.num_kb; kb0 += CHUNK_KB, ++cc) {
+        const int acc = cc & 1;
+        const uint32_t acc_ph = (cc >> 1) & 1;
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+#pragma unroll
+        for (int c = 0; c < 128; c += 16) {
+          float v[16];
+          tmem_ld16(taddr + c, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum[c + j] += v[j];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      const int row = m_blk * BM + q * 32 + lane;
+      if (row < p.M) {
+#pragma unroll
+        for (int c = 0; c < 128; c += 16) {
+          const int col0 = n_blk * BN + half * 128 + c;
+          if (col0 >= p.N) continue;
+          float v[16];
+          if (col0 + 16 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = sum[c + j] * p.w_scale_inv + __ldg(p.bias + col0 + j);
               v[j] = p.relu ? fmaxf(x, 0.f) : x;
             }
             if (p.out) {
               float4* dst = reinterpret_cast<float4*>(p.out + (size_t)row * p.ldo + col0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             if (p.out_hi) {
-              uint32_t hi[16], lo[16];
+              uint32_t hi[8], lo[8];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
+              for (int j = 0; j < 8; ++j) {
                 nnal_h h0, h1, l0, l1;
                 nnal_split(v[2 * j], h0, l0);
                 nnal_split(v[2 * j + 1], h1, l1);
@@ -263,30 +302,29 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
               }
               uint4* dh = reinterpret_cast<uint4*>(p.out_hi + (size_t)row * p.ld_split + col0);
               uint4* dl = reinterpret_cast<uint4*>(p.out_lo + (size_t)row * p.ld_split + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-              }
+              dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
             }
           } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
-              float x = v[j] * p.w_scale_inv + __ldg(p.bias + col0 + j);
-              x = p.relu ? fmaxf(x, 0.f) : x;
-              if (p.out) p.out[(size_t)row * p.ldo + col0 + j] = x;
-              if (p.out_hi) {
-                nnal_h h, l;
-                nnal_split(x, h, l);
-                p.out_hi[(size_t)row * p.ld_split + col0 + j] = h;
-                p.out_lo[(size_t)row * p.ld_split + col0 + j] = l;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (col0 + j < p.N) {
+                float x = sum[c + j] * p.w_scale_inv + __ldg(p.bias + col0 + j);
+                x = p.relu ? fmaxf(x, 0.f) : x;
+                if (p.out) p.out[(size_t)row * p.ldo + col0 + j] = x;
+                if (p.out_hi) {
+                  nnal_h h, l;
+                  nnal_split(x, h, l);
+                  p.out_hi[(size_t)row * p.ld_split + col0 + j] = h;
+                  p.out_lo[(size_t)row * p.ld_split + col0 + j] = l;
+                }
               }
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
 
