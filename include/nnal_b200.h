@@ -47,6 +47,8 @@ typedef struct { int32_t type, out, kh, kw; } nnal_layer_spec;
 #define NNAL_SCORE_BINARY 0     /* |P(class1) - 0.5|          (PW_NNAL.py:64,109-110,724-730) */
 #define NNAL_SCORE_NEG_ENTROPY 1 /* sum_c p log p = -H        (NNAL.py:309-310, NNAL_tools.py:32-34) */
 #define NNAL_SCORE_ENTROPY 2    /* H                          (NNAL_tools.py:71-85) */
+#define NNAL_SCORE_NEG_FI_TRACE 3 /* -(1-|pi|^2)(|u|^2+1): minus the trace of the last-layer FI (NNAL.py:121-139);
+                                     needs a pool pass that kept the feature layer */
 
 /* ---- context ------------------------------------------------------------------------------- */
 int nnal_version(void);
@@ -129,25 +131,44 @@ int nnal_entropy(nnal_ctx* ctx, const double* P, int c, int64_t n, int kind, dou
 /* np.argsort(scores)[:k] */
 int nnal_topk(nnal_ctx* ctx, const double* scores, int64_t n, int64_t k, int64_t* idx_out);
 
-/* ---- Fisher-information scoring (PW_NNAL.py:547-627, 738-816; NN.py:874-955) ---------------- */
-/* Select the FI candidate set: pool positions (ascending argsort order irrelevant) whose factored
- * scores take part in the greedy selection.  cand: n_cand pool positions. */
+/* ---- Fisher-information scoring (PW_NNAL.py:89-163, 547-627, 738-816; NN.py:874-955) ---------- */
+/* The conditional FI of a sample over the parameters of the last 1 or 2 FC layers is kept in FACTORED
+ * form (NN.LLFC_grads NN.py:905-955, NNAL_tools.FC_gradnorms_batch NNAL_tools.py:725-775): for the
+ * binary model Abar_i = w_i gbar_i gbar_i^T, w_i = p_i(1-p_i), <gbar_i,gbar_j> = 2(u_i.u_j+1) +
+ * (delta2_i.delta2_j)(a_i.a_j+1).  Selection is the deterministic greedy restatement of the reference's
+ * SDP objective tr((sum_i q_i A_i)^-1) (NNAL_tools.py:576-659) at q = uniform(S); see DESIGN.md.
+ *
+ * Candidate set from the current pool pass (nnal_pool_begin keep >= n_layers): cand = n_cand pool
+ * positions, or NULL for every pool sample.  Candidate indices used below are positions in this list. */
 int nnal_fi_set_candidates(nnal_ctx* ctx, const int64_t* cand, int64_t n_cand, int n_layers /*1 or 2*/);
-/* Weighted penultimate-feature Gram  H = sum_i wq_i [u_i;1][u_i;1]^T over the candidates
- * ((d+1)x(d+1) float32, row-major) -- the last-layer FI block of NN.LLFC_hess (NN.py:891-901).
- * wq: per-candidate weight q_i p_i (1-p_i) is formed on the device from q (host, n_cand) or
- * uniform if q == NULL.  The result stays on the device (for NCCL all-reduce by the host layer,
- * see nnal_fi_gram_ptr) and is copied to H_out if non-NULL. */
+/* Candidate set from host factors: p1[n] = P(class 1), U[n][d] = feature-layer activations (input of the
+ * last FC), A_prev[n][d_prev] = input of the feature layer's FC and w_last[2][d] = last FC weights (both
+ * NULL for last-layer-only FI). */
+int nnal_fi_set_factors(nnal_ctx* ctx, int64_t n, int d, int d_prev, const double* p1, const float* U,
+                        const float* A_prev, const float* w_last);
+/* n candidates, layers covered, widths and the parameter count D = 2(d+1) [+ d(d_prev+1)] */
+int nnal_fi_info(nnal_ctx* ctx, int64_t* n_cand, int* n_layers, int* d, int* d_prev, double* param_dim);
+/* Weighted penultimate-feature Gram  H = sum_i wq_i [u_i;1][u_i;1]^T over the candidates ((d+1)x(d+1)
+ * float32, row-major) on tensor cores -- the last-layer FI of NN.LLFC_hess (NN.py:891-901) is
+ * (v v^T) (x) H, never formed.  wq_i = q_i p_i(1-p_i), q from the host (n_cand) or uniform 1/n_cand if
+ * NULL.  The result stays on the device (nnal_fi_gram_ptr: base pointer, rows = d+1, row stride ld, for
+ * the NCCL all-reduce of per-GPU partials by the host layer) and is copied to H_out if non-NULL. */
 int nnal_fi_gram(nnal_ctx* ctx, const double* q, float* H_out);
-void* nnal_fi_gram_ptr(nnal_ctx* ctx, int64_t* n_elems);
-/* Greedy FI selection: k candidates minimising tr(((1/|S|) sum Abar_i + delta I)^-1)
- * step by step; sel_out: positions into the candidate list, obj_out: objective after each step,
- * red_out: its kernel-dependent part tr((delta I + K_SS/s)^-1). */
+void* nnal_fi_gram_ptr(nnal_ctx* ctx, int64_t* rows, int64_t* ld);
+int nnal_fi_gram_read(nnal_ctx* ctx, float* H_out);
+/* Greedy FI selection: k candidates minimising f(S) = tr(((1/|S|) sum_{i in S} Abar_i + delta I)^-1) step
+ * by step (ties: lowest candidate index).  sel_out[k]: candidate indices in selection order; obj_out[k]:
+ * f(S_t) after each step; red_out[k]: its kernel-dependent part tr((delta I + K_SS/s)^-1).  Any of
+ * obj_out / red_out may be NULL.  Fewer than k candidates: only n_cand entries are written. */
 int nnal_fi_greedy(nnal_ctx* ctx, int64_t k, double delta, int64_t* sel_out, double* obj_out, double* red_out);
-/* Multi-GPU greedy: one step split in two so the host layer can combine ranks with NCCL:
- * (1) local best candidate, (2) apply the globally chosen winner's factors. */
-int nnal_fi_step_local_best(nnal_ctx* ctx, int64_t step, double delta, double* loss_out, int64_t* cand_out);
-int nnal_fi_winner_factors(nnal_ctx* ctx, int64_t cand, float* factors_out, int64_t* n_floats);
+/* Multi-GPU greedy, one step split so that the host layer can combine ranks (NCCL): nnal_fi_begin once;
+ * per step (1) local best candidate: loss, local candidate index (-1 if none) and tr C of the shared
+ * winners' system (objective after the step = (D-s)/delta + s (trC + global loss), s = step+1);
+ * (2) the owner exports its winner's factors [u (d) | a (d_prev) | sqrt(w) as one double];
+ * (3) every rank applies the global winner. */
+int nnal_fi_begin(nnal_ctx* ctx, int64_t k, double delta);
+int nnal_fi_step_local_best(nnal_ctx* ctx, int64_t step, double* loss_out, int64_t* cand_out, double* trC_out);
+int nnal_fi_winner_factors(nnal_ctx* ctx, int64_t cand, float* factors_out /*NULL: size query*/, int64_t* n_floats);
 int nnal_fi_step_apply(nnal_ctx* ctx, int64_t step, const float* winner_factors, int64_t n_floats, int owner_is_local,
                        int64_t cand_local);
 

@@ -62,13 +62,9 @@ def CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, method_name):
     raise NotImplementedError('query method %r is not part of the replaced path' % method_name)
 
 
-def bin_uncertainty_filter_multimg(expr, model, sess, all_padded_imgs, pool_inds, B, x_feed_dict={},
-                                   keep=0):
-    """PW_NNAL.bin_uncertainty_filter_multimg (PW_NNAL.py:684-736): posteriors of every
-    subject's pool, rank |p - 0.5| over the CONCATENATED pool, keep B, split back with
-    global2local_inds.  Returns ``(sel_inds, sel_posts)`` lists per subject."""
-    if len(x_feed_dict) > 0:
-        raise NotImplementedError('x_feed_dict (MC-dropout) is not part of the replaced path yet')
+def _bin_filter_core(expr, model, sess, all_padded_imgs, pool_inds, B, keep=0):
+    """Pool pass over (this rank's block of) the concatenated multi-subject pool + global top-B by
+    |p - 0.5|.  Returns (sorted global positions, their posteriors, lo, hi, per-subject sizes)."""
     eng = get_engine()
     eng.set_model(model, sess)
     s = len(pool_inds)
@@ -105,6 +101,17 @@ def bin_uncertainty_filter_multimg(expr, model, sess, all_padded_imgs, pool_inds
         t = torch.from_numpy(sel_p).to(dist._device())
         dist.allreduce_sum_(t)
         sel_p = t.cpu().numpy()
+    return sorted_inds, sel_p, lo, hi, img_ind_sizes
+
+
+def bin_uncertainty_filter_multimg(expr, model, sess, all_padded_imgs, pool_inds, B, x_feed_dict={}):
+    """PW_NNAL.bin_uncertainty_filter_multimg (PW_NNAL.py:684-736): posteriors of every
+    subject's pool, rank |p - 0.5| over the CONCATENATED pool, keep B, split back with
+    global2local_inds.  Returns ``(sel_inds, sel_posts)`` lists per subject."""
+    if len(x_feed_dict) > 0:
+        raise NotImplementedError('x_feed_dict (MC-dropout) is not part of the replaced path yet')
+    sorted_inds, sel_p, _, _, img_ind_sizes = _bin_filter_core(expr, model, sess, all_padded_imgs, pool_inds, B)
+    s = len(pool_inds)
     sel_inds = patch_utils.global2local_inds(sorted_inds, img_ind_sizes)
     cum = np.append(-1, np.cumsum(img_ind_sizes) - 1)
     set_of = cum.searchsorted(sorted_inds) - 1

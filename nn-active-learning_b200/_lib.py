@@ -52,10 +52,14 @@ SIGNATURES = {
     'nnal_debug_conv': (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, c_vp]),
     'nnal_fi_set_candidates': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int]),
+    'nnal_fi_set_factors': (C.c_int, [c_vp, C.c_int64, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]),
+    'nnal_fi_info': (C.c_int, [c_vp, c_i64p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_f64p]),
     'nnal_fi_gram': (C.c_int, [c_vp, c_vp, c_vp]),
-    'nnal_fi_gram_ptr': (c_vp, [c_vp, c_i64p]),
+    'nnal_fi_gram_ptr': (c_vp, [c_vp, c_i64p, c_i64p]),
+    'nnal_fi_gram_read': (C.c_int, [c_vp, c_vp]),
     'nnal_fi_greedy': (C.c_int, [c_vp, C.c_int64, C.c_double, c_vp, c_vp, c_vp]),
-    'nnal_fi_step_local_best': (C.c_int, [c_vp, C.c_int64, C.c_double, c_f64p, c_i64p]),
+    'nnal_fi_begin': (C.c_int, [c_vp, C.c_int64, C.c_double]),
+    'nnal_fi_step_local_best': (C.c_int, [c_vp, C.c_int64, c_f64p, c_i64p, c_f64p]),
     'nnal_fi_winner_factors': (C.c_int, [c_vp, C.c_int64, c_vp, c_i64p]),
     'nnal_fi_step_apply': (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int64, C.c_int, C.c_int64]),
 }
@@ -64,7 +68,7 @@ NNAL_OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, 1
 LAYER_CONV, LAYER_POOL, LAYER_FC = 0, 1, 2
 F32, F64 = 0, 1
 NORM_NONE, NORM_BATCH_EVAL, NORM_MULTIMG = 0, 1, 2
-SCORE_BINARY, SCORE_NEG_ENTROPY, SCORE_ENTROPY = 0, 1, 2
+SCORE_BINARY, SCORE_NEG_ENTROPY, SCORE_ENTROPY, SCORE_NEG_FI_TRACE = 0, 1, 2, 3
 
 _lib = None
 

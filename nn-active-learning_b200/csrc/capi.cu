@@ -457,11 +457,15 @@ extern "C" int nnal_pool_features(nnal_ctx* ctx, int64_t start, int64_t n, float
 extern "C" int nnal_pool_score(nnal_ctx* ctx, int kind, double eps) {
   if (!ctx) return NNAL_ERR_INVALID;
   if (!ctx->pool_post) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no pool pass");
-  if (kind < 0 || kind > 2) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "unknown score kind");
+  if (kind < 0 || kind > 3) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "unknown score kind");
   if (kind == NNAL_SCORE_BINARY && ctx->n_class != 2) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "binary uncertainty needs a 2-class model");
+  if (kind == NNAL_SCORE_NEG_FI_TRACE && (!ctx->pool_feat || ctx->keep < 1))
+    NNAL_FAIL(ctx, NNAL_ERR_STATE, "the FI trace score needs a pool pass that kept the feature layer");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   prof_begin(ctx, NNAL_PROF_SCORE);
-  int rc = nnal_k_scores_f32(ctx, ctx->pool_post, ctx->n_class, ctx->pool_n, kind, eps, ctx->pool_score);
+  int rc = kind == NNAL_SCORE_NEG_FI_TRACE
+               ? nnal_k_fi_trace_scores(ctx, ctx->pool_post, ctx->n_class, ctx->pool_n, ctx->pool_feat, ctx->feat_dim, ctx->pool_score)
+               : nnal_k_scores_f32(ctx, ctx->pool_post, ctx->n_class, ctx->pool_n, kind, eps, ctx->pool_score);
   prof_end(ctx);
   return rc;
 }

@@ -1,12 +1,879 @@
-// Fisher-information scoring kernels -- placeholder until fi.cu lands (entry points fail loudly).
+// Fisher-information (FI) scoring and greedy selection (sm_100a).
+//
+// Reference behaviour replaced (all file:line in jsourati/nn-active-learning):
+//   * per-sample last-layer score factors  grad log p_y = [(e_y - pi) (x) u ; (e_y - pi)]   NN.LLFC_grads (NN.py:905-955)
+//   * last-layer FI  (diag pi - pi pi^T) (x) [u;1][u;1]^T                                    NN.LLFC_hess  (NN.py:874-903)
+//   * back-propagation of the score through the previous FC layer with ReLU masks          NNAL_tools.FC_gradnorms_batch
+//                                                                                          (NNAL_tools.py:725-775)
+//   * conditional FI matrices A_i and the objective tr((sum_i q_i A_i)^-1)                 PW_NNAL.gen_A_matrices
+//                                                                (PW_NNAL.py:738-816), NNAL_tools.py:576-659
+//   * closed-form trace score (1 - ||pi||^2)(||u||^2 + 1)                                   NNAL.py:121-139
+//
+// Nothing of size (d+1)c is ever formed.  For the binary model the conditional FI of sample i over the
+// parameters of the last one or two FC layers is RANK ONE:  Abar_i = w_i gbar_i gbar_i^T with
+// w_i = p_i (1 - p_i) and gbar_i = [ v (x) [u_i;1] ; delta2_i (x) [a_i;1] ],  v = (1,-1),
+// delta2_i = (W_last^T v) . 1[u_i > 0].  Inner products factor:
+//     <gbar_i, gbar_j> = 2 (u_i.u_j + 1) + (delta2_i.delta2_j)(a_i.a_j + 1),
+// so the greedy selection of oracle/fi_oracle.py:greedy_fi_rank1 (objective = the reference's SDP objective
+// at q = uniform(S)) needs one kernel COLUMN per selected sample (a memory-bound GEMV over the candidates'
+// factor rows, float64 accumulation), a t x t inverse per step and an O(t^2) quadratic form per candidate,
+// followed by a block-level arg-min.  The primal form of the same objective goes through the weighted
+// penultimate-feature Gram  H = sum_i wq_i [u_i;1][u_i;1]^T  ((d+1)^2, tensor cores: fp16 hi/lo split planes
+// through the tcgen05 GEMM of gemm_tc.cu).
 #include "nnal_common.cuh"
 #include "../../include/nnal_b200.h"
-int nnal_fi_release(nnal_ctx*) { return NNAL_OK; }
-#define FI_STUB(ctx) do { if (!(ctx)) return NNAL_ERR_INVALID; (ctx)->err = "FI path not built yet"; return NNAL_ERR_UNSUPPORTED; } while (0)
-extern "C" int nnal_fi_set_candidates(nnal_ctx* ctx, const int64_t*, int64_t, int) { FI_STUB(ctx); }
-extern "C" int nnal_fi_gram(nnal_ctx* ctx, const double*, float*) { FI_STUB(ctx); }
-extern "C" void* nnal_fi_gram_ptr(nnal_ctx*, int64_t* n) { if (n) *n = 0; return nullptr; }
-extern "C" int nnal_fi_greedy(nnal_ctx* ctx, int64_t, double, int64_t*, double*, double*) { FI_STUB(ctx); }
-extern "C" int nnal_fi_step_local_best(nnal_ctx* ctx, int64_t, double, double*, int64_t*) { FI_STUB(ctx); }
-extern "C" int nnal_fi_winner_factors(nnal_ctx* ctx, int64_t, float*, int64_t*) { FI_STUB(ctx); }
-extern "C" int nnal_fi_step_apply(nnal_ctx* ctx, int64_t, const float*, int64_t, int, int64_t) { FI_STUB(ctx); }
+#include <algorithm>
+#include <cmath>
+
+namespace fi {
+
+constexpr int T_SMEM = 152;          // largest t whose t x t float64 system fits one CTA's shared memory
+
+struct DevScalars {
+  double best_loss;
+  long long best_idx;
+  double trC;
+  unsigned int gmax_bits;
+  unsigned int pad;
+};
+
+struct State {
+  int64_t n = 0;
+  int nl = 1, d = 0, dp = 0;
+  int64_t kcap = 0, kcols_n = 0;
+  double delta = 0;
+  // factor sources: row of candidate i is rows ? rows[i] : i
+  const float* U = nullptr;
+  const float* A = nullptr;
+  int64_t* rows = nullptr;
+  bool use_rows = false;
+  const int64_t* R() const { return use_rows ? rows : nullptr; }
+  float *ownU = nullptr, *ownA = nullptr;
+  int64_t own_cap_u = 0, own_cap_a = 0;
+  double *w = nullptr, *sw = nullptr, *diag = nullptr;
+  unsigned char* avail = nullptr;
+  int64_t cand_cap = 0;
+  float* beta2 = nullptr;
+  int beta_cap = 0;
+  // greedy state
+  double *kcols = nullptr, *kss = nullptr, *C = nullptr, *inv_ws = nullptr, *red = nullptr, *win_sw = nullptr;
+  float *win_u = nullptr, *win_a = nullptr;
+  int win_d = 0, win_dp = 0;
+  long long* sel = nullptr;
+  double* blk_loss = nullptr;
+  long long* blk_idx = nullptr;
+  int blk_cap = 0;
+  DevScalars* sc = nullptr;
+  // Gram
+  float* H = nullptr;
+  int Hd = 0, Hld = 0;
+  nnal_h *Xh = nullptr, *Xl = nullptr;
+  size_t plane_cap = 0;
+  double* wq = nullptr;
+  int64_t wq_cap = 0;
+};
+
+static State* get(nnal_ctx* ctx) {
+  if (!ctx->fi_state) ctx->fi_state = new State();
+  return (State*)ctx->fi_state;
+}
+
+template <typename T>
+static int ensure(nnal_ctx* ctx, T*& p, size_t have, size_t want) {
+  if (p && have >= want) return NNAL_OK;
+  if (p) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CUDA_TRY(ctx, cudaFree(p)); p = nullptr; }
+  CUDA_TRY(ctx, cudaMalloc(&p, std::max<size_t>(want, 1) * sizeof(T)));
+  return NNAL_OK;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// The three inner products of a (candidate, winner) pair, float64 accumulation of exact float32 products in
+// a FIXED order (lane-strided, then butterfly), so that every kernel that needs <gbar_i, gbar_j> gets the
+// same bits:  uu = u.x,  aa = a.y,  mm = sum_k beta2_k 1[u_k > 0] 1[x_k > 0].
+__device__ __forceinline__ void pair_dots(const float* __restrict__ u, const float* __restrict__ a,
+                                          const float* __restrict__ x, const float* __restrict__ y,
+                                          const float* __restrict__ beta2, int d, int dp, int nl, int lane, double& uu,
+                                          double& aa, double& mm) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  if ((d & 3) == 0) {
+    for (int k = lane * 4; k < d; k += 128) {
+      const float4 p = *reinterpret_cast<const float4*>(u + k);
+      const float4 q = *reinterpret_cast<const float4*>(x + k);
+      s0 = fma((double)p.x, (double)q.x, s0);
+      s0 = fma((double)p.y, (double)q.y, s0);
+      s0 = fma((double)p.z, (double)q.z, s0);
+      s0 = fma((double)p.w, (double)q.w, s0);
+      if (nl == 2) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta2 + k));
+        if (p.x > 0.f && q.x > 0.f) s2 += (double)b.x;
+        if (p.y > 0.f && q.y > 0.f) s2 += (double)b.y;
+        if (p.z > 0.f && q.z > 0.f) s2 += (double)b.z;
+        if (p.w > 0.f && q.w > 0.f) s2 += (double)b.w;
+      }
+    }
+  } else {
+    for (int k = lane; k < d; k += 32) {
+      const float p = u[k], q = x[k];
+      s0 = fma((double)p, (double)q, s0);
+      if (nl == 2 && p > 0.f && q > 0.f) s2 += (double)__ldg(beta2 + k);
+    }
+  }
+  if (nl == 2) {
+    if ((dp & 3) == 0) {
+      for (int k = lane * 4; k < dp; k += 128) {
+        const float4 p = *reinterpret_cast<const float4*>(a + k);
+        const float4 q = *reinterpret_cast<const float4*>(y + k);
+        s1 = fma((double)p.x, (double)q.x, s1);
+        s1 = fma((double)p.y, (double)q.y, s1);
+        s1 = fma((double)p.z, (double)q.z, s1);
+        s1 = fma((double)p.w, (double)q.w, s1);
+      }
+    } else {
+      for (int k = lane; k < dp; k += 32) s1 = fma((double)a[k], (double)y[k], s1);
+    }
+  }
+  uu = warp_sum(s0);
+  aa = warp_sum(s1);
+  mm = warp_sum(s2);
+}
+
+__device__ __forceinline__ double pair_kernel(double uu, double aa, double mm, int nl) {
+  double k = 2.0 * (uu + 1.0);
+  if (nl == 2) k += mm * (aa + 1.0);
+  return k;
+}
+
+// beta2_k = (W_last[0][k] - W_last[1][k])^2   (delta2 = (W_last^T v) . mask, v = (1,-1); only products of two
+// delta2 vectors are ever needed)
+__global__ void beta2_kernel(const float* __restrict__ Wlast, int d, float* __restrict__ beta2) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < d; k += gridDim.x * blockDim.x) {
+    const float b = Wlast[k] - Wlast[d + k];
+    beta2[k] = b * b;
+  }
+}
+
+// per candidate: w = p(1-p), sqrt(w), Kt_ii, avail = 1.   One warp per candidate.
+__global__ void __launch_bounds__(256) setup_kernel(const float* __restrict__ U, const float* __restrict__ A,
+                                                     const int64_t* __restrict__ rows, const float* __restrict__ post1,
+                                                     const double* __restrict__ p1_given, const float* __restrict__ beta2,
+                                                     int64_t n, int d, int dp, int nl, double* __restrict__ w,
+                                                     double* __restrict__ sw, double* __restrict__ diag,
+                                                     unsigned char* __restrict__ avail) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t r = rows ? rows[i] : i;
+    const float* u = U + r * d;
+    const float* a = A ? A + r * dp : nullptr;
+    double uu, aa, mm;
+    pair_dots(u, a, u, a, beta2, d, dp, nl, lane, uu, aa, mm);
+    if (lane == 0) {
+      const double p = p1_given ? p1_given[i] : (double)post1[r];
+      const double wi = p * (1.0 - p);
+      w[i] = wi;
+      sw[i] = sqrt(wi);
+      diag[i] = wi * pair_kernel(uu, aa, mm, nl);
+      avail[i] = 1;
+    }
+  }
+}
+
+// kernel column of the step-t winner against every local candidate:
+//   kcols[t][i] = sqrt(w_i) sqrt(w_win) <gbar_i, gbar_win>
+__global__ void __launch_bounds__(256) column_kernel(const float* __restrict__ U, const float* __restrict__ A,
+                                                      const int64_t* __restrict__ rows, const double* __restrict__ sw,
+                                                      const float* __restrict__ beta2, const float* __restrict__ wu,
+                                                      const float* __restrict__ wa, const double* __restrict__ wsw,
+                                                      int64_t n, int d, int dp, int nl, double* __restrict__ kcol) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const double s_w = *wsw;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t r = rows ? rows[i] : i;
+    double uu, aa, mm;
+    pair_dots(U + r * d, A ? A + r * dp : nullptr, wu, wa, beta2, d, dp, nl, lane, uu, aa, mm);
+    if (lane == 0) kcol[i] = sw[i] * s_w * pair_kernel(uu, aa, mm, nl);
+  }
+}
+
+// row/column t of the winners' kernel K_SS (from the stored winner factors: identical on every rank)
+__global__ void __launch_bounds__(256) kss_row_kernel(const float* __restrict__ win_u, const float* __restrict__ win_a,
+                                                       const double* __restrict__ win_sw, const float* __restrict__ beta2,
+                                                       int t, int d, int dp, int nl, int64_t ld, double* __restrict__ kss) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int a = warp; a <= t; a += nwarps) {
+    double uu, aa, mm;
+    pair_dots(win_u + (int64_t)a * d, win_a ? win_a + (int64_t)a * dp : nullptr, win_u + (int64_t)t * d,
+              win_a ? win_a + (int64_t)t * dp : nullptr, beta2, d, dp, nl, lane, uu, aa, mm);
+    if (lane == 0) {
+      const double v = win_sw[a] * win_sw[t] * pair_kernel(uu, aa, mm, nl);
+      kss[(int64_t)t * ld + a] = v;
+      kss[(int64_t)a * ld + t] = v;
+    }
+  }
+}
+
+// copies the factors of local candidate *idx_ptr into winner slot t
+__global__ void copy_winner_kernel(const float* __restrict__ U, const float* __restrict__ A, const int64_t* __restrict__ rows,
+                                   const double* __restrict__ sw, const long long* __restrict__ idx_ptr, int t, int d, int dp,
+                                   float* __restrict__ win_u, float* __restrict__ win_a, double* __restrict__ win_sw) {
+  const long long i = *idx_ptr;
+  if (i < 0) return;
+  const int64_t r = rows ? rows[i] : i;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int k = tid; k < d; k += nt) win_u[(int64_t)t * d + k] = U[r * d + k];
+  if (A)
+    for (int k = tid; k < dp; k += nt) win_a[(int64_t)t * dp + k] = A[r * dp + k];
+  if (tid == 0) win_sw[t] = sw[i];
+}
+
+// C = (alpha I + K_SS[0:t,0:t])^-1 by in-place Gauss-Jordan (SPD: no pivoting), one CTA, float64.
+// The working matrix lives in shared memory when it fits, else in the global workspace `gws`.
+__global__ void __launch_bounds__(1024) invert_kernel(const double* __restrict__ kss, int64_t kss_ld, int t, double alpha,
+                                                       double* __restrict__ Cout, int ldc, double* __restrict__ gws,
+                                                       int use_smem, DevScalars* sc) {
+  extern __shared__ double sm_d[];
+  const int ld = t | 1;
+  double* M = use_smem ? sm_d : gws;
+  double* col = M + (size_t)t * ld;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int e = tid; e < t * t; e += nt) {
+    const int i = e / t, j = e - i * t;
+    M[(size_t)i * ld + j] = kss[(int64_t)i * kss_ld + j] + (i == j ? alpha : 0.0);
+  }
+  __syncthreads();
+  for (int p = 0; p < t; ++p) {
+    const double inv = 1.0 / M[(size_t)p * ld + p];
+    for (int i = tid; i < t; i += nt) col[i] = M[(size_t)i * ld + p];
+    __syncthreads();
+    for (int j = tid; j < t; j += nt) M[(size_t)p * ld + j] = (j == p ? 1.0 : M[(size_t)p * ld + j]) * inv;
+    __syncthreads();
+    for (int e = tid; e < t * t; e += nt) {
+      const int i = e / t, j = e - i * t;
+      if (i != p) {
+        const double base = (j == p) ? 0.0 : M[(size_t)i * ld + j];
+        M[(size_t)i * ld + j] = fma(-col[i], M[(size_t)p * ld + j], base);
+      }
+    }
+    __syncthreads();
+  }
+  // symmetrise, pad the row stride with zeros, trace
+  for (int e = tid; e < t * ldc; e += nt) {
+    const int i = e / ldc, j = e - i * ldc;
+    Cout[(size_t)i * ldc + j] = j < t ? 0.5 * (M[(size_t)i * ld + j] + M[(size_t)j * ld + i]) : 0.0;
+  }
+  __shared__ double red[32];
+  double tr = 0.0;
+  for (int i = tid; i < t; i += nt) tr += M[(size_t)i * ld + i];
+  tr = warp_sum(tr);
+  if ((tid & 31) == 0) red[tid >> 5] = tr;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (nt + 31) / 32; ++i) s += red[i];
+    sc->trC = s;
+  }
+}
+
+// Candidate evaluation at step t (|S| = t, alpha = (t+1) delta, C = (alpha I + K_SS)^-1):
+//   y = C k_j,  r_j = Kt_jj - k_j.y,  e_j = |y|^2,  loss_j = (1 + e_j)/(alpha + r_j)    (f(S+j) = const + (t+1) loss_j)
+// followed by a block-level arg-min (ties: lowest candidate index).
+template <bool SMEM_C>
+__global__ void __launch_bounds__(128) eval_kernel(const double* __restrict__ kcols, int64_t kn, const double* __restrict__ diag,
+                                                    const unsigned char* __restrict__ avail, const double* __restrict__ Cg, int t,
+                                                    int ldc, int64_t n, double alpha, double* __restrict__ blk_loss,
+                                                    long long* __restrict__ blk_idx) {
+  extern __shared__ double sm_d[];
+  const double* Cs = Cg;
+  if (SMEM_C) {
+    for (int e = threadIdx.x; e < t * ldc; e += blockDim.x) sm_d[e] = Cg[e];
+    __syncthreads();
+    Cs = sm_d;
+  }
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double loss = INFINITY;
+  if (j < n && avail[j]) {
+    double r = diag[j], e = 0.0;
+    for (int a0 = 0; a0 < t; a0 += 8) {
+      double acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+      for (int b = 0; b < t; ++b) {
+        const double kb = kcols[(int64_t)b * kn + j];
+        const double2* c2 = reinterpret_cast<const double2*>(Cs + (size_t)b * ldc + a0);   // C[b][a0..a0+7] (symmetric)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double2 c = c2[q];
+          acc[2 * q] = fma(c.x, kb, acc[2 * q]);
+          acc[2 * q + 1] = fma(c.y, kb, acc[2 * q + 1]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (a0 + q < t) {
+          const double ka = kcols[(int64_t)(a0 + q) * kn + j];
+          r = fma(-ka, acc[q], r);
+          e = fma(acc[q], acc[q], e);
+        }
+      }
+    }
+    loss = (1.0 + e) / (alpha + r);
+    if (!(loss == loss)) loss = INFINITY;
+  }
+  // block arg-min
+  long long idx = (j < n) ? (long long)j : 0x7fffffffffffffffll;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ol = __shfl_xor_sync(0xffffffffu, loss, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ol < loss || (ol == loss && oi < idx)) { loss = ol; idx = oi; }
+  }
+  __shared__ double wl[4];
+  __shared__ long long wi[4];
+  if ((threadIdx.x & 31) == 0) { wl[threadIdx.x >> 5] = loss; wi[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 4; ++q)
+      if (wl[q] < loss || (wl[q] == loss && wi[q] < idx)) { loss = wl[q]; idx = wi[q]; }
+    blk_loss[blockIdx.x] = loss;
+    blk_idx[blockIdx.x] = idx;
+  }
+}
+
+// final arg-min over the block results; commit = 1 also removes the winner from the candidate set and
+// records the selection and the reduced objective  red_t = (t+1) (tr C + loss*)
+__global__ void __launch_bounds__(256) pick_kernel(const double* __restrict__ blk_loss, const long long* __restrict__ blk_idx,
+                                                    int nblk, int t, DevScalars* sc, int commit, unsigned char* __restrict__ avail,
+                                                    long long* __restrict__ sel, double* __restrict__ red) {
+  double loss = INFINITY;
+  long long idx = 0x7fffffffffffffffll;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+    const double ol = blk_loss[b];
+    const long long oi = blk_idx[b];
+    if (ol < loss || (ol == loss && oi < idx)) { loss = ol; idx = oi; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ol = __shfl_xor_sync(0xffffffffu, loss, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ol < loss || (ol == loss && oi < idx)) { loss = ol; idx = oi; }
+  }
+  __shared__ double wl[8];
+  __shared__ long long wi[8];
+  if ((threadIdx.x & 31) == 0) { wl[threadIdx.x >> 5] = loss; wi[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q)
+      if (wl[q] < loss || (wl[q] == loss && wi[q] < idx)) { loss = wl[q]; idx = wi[q]; }
+    const bool found = loss < INFINITY;
+    if (!found) idx = -1;
+    sc->best_loss = loss;
+    sc->best_idx = idx;
+    if (t == 0) sc->trC = 0.0;
+    if (commit) {
+      if (found) avail[idx] = 0;
+      sel[t] = idx;
+      red[t] = (double)(t + 1) * (sc->trC + loss);
+    }
+  }
+}
+
+__global__ void mark_taken_kernel(unsigned char* avail, long long idx) { avail[idx] = 0; }
+
+// ---- closed-form trace score  -(1 - |pi|^2)(|u|^2 + 1)  (NNAL.py:124-139; negated: top-k takes the smallest)
+__global__ void __launch_bounds__(256) trace_score_kernel(const float* __restrict__ post, int c, int64_t n,
+                                                           const float* __restrict__ feat, int d, double* __restrict__ score) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    double s = 0.0;
+    for (int k = lane; k < d; k += 32) { const double u = (double)feat[i * d + k]; s = fma(u, u, s); }
+    s = warp_sum(s);
+    if (lane == 0) {
+      double pp = 0.0;
+      for (int j = 0; j < c; ++j) { const double p = (double)post[(int64_t)j * n + i]; pp = fma(p, p, pp); }
+      score[i] = -((1.0 - pp) * (s + 1.0)) + 0.0;
+    }
+  }
+}
+
+// ---- weighted Gram ------------------------------------------------------------------------------------
+__global__ void wq_kernel(const double* __restrict__ w, const double* __restrict__ q, int64_t n, double* __restrict__ wq) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    wq[i] = (q ? q[i] : 1.0 / (double)n) * w[i];
+}
+
+// max over candidates of sqrt(wq_i) max(1, max_k |u_ik|)  (power-of-two operand scaling for the fp16 planes)
+__global__ void __launch_bounds__(256) gram_max_kernel(const float* __restrict__ U, const int64_t* __restrict__ rows,
+                                                        const double* __restrict__ wq, int64_t n, int d, DevScalars* sc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float best = 0.f;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t r = rows ? rows[i] : i;
+    float m = 1.f;
+    for (int k = lane; k < d; k += 32) m = fmaxf(m, fabsf(U[r * d + k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    best = fmaxf(best, m * (float)sqrt(wq[i]));
+  }
+  if (lane == 0 && best > 0.f) atomicMax(&sc->gmax_bits, __float_as_uint(best));
+}
+
+// X^T planes:  Xh/Xl[f][c] = split( scale * sqrt(wq_i) * ut_i[f] ),  i = i0 + c,  ut = [u;1]   (feature-major,
+// K = candidates contiguous: both GEMM operands of H = X^T X are K-major)
+__global__ void __launch_bounds__(256) gram_planes_kernel(const float* __restrict__ U, const int64_t* __restrict__ rows,
+                                                           const double* __restrict__ wq, int64_t i0, int64_t nc, int64_t ld,
+                                                           int d, float scale, nnal_h* __restrict__ Xh, nnal_h* __restrict__ Xl) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32;
+  const int f0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int64_t c = c0 + r;
+    const int f = f0 + threadIdx.x;
+    float v = 0.f;
+    if (c < nc && f <= d) {
+      const int64_t i = i0 + c;
+      const int64_t row = rows ? rows[i] : i;
+      const float s = (float)sqrt(wq[i]) * scale;
+      v = (f < d ? U[row * d + f] : 1.f) * s;
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int f = f0 + r;
+    const int64_t c = c0 + threadIdx.x;
+    if (f <= d && c < ld) {
+      nnal_h h, l;
+      nnal_split(tile[threadIdx.x][r], h, l);
+      Xh[(int64_t)f * ld + c] = h;
+      Xl[(int64_t)f * ld + c] = l;
+    }
+  }
+}
+
+static int warp_grid(nnal_ctx* ctx, int64_t n) {
+  int64_t blocks = (n + 7) / 8;
+  int64_t cap = (int64_t)ctx->sm_count * 16;
+  return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+static int alloc_candidates(nnal_ctx* ctx, State* s, int64_t n) {
+  if (s->cand_cap < n) {
+    NNAL_TRY(ensure(ctx, s->w, 0, (size_t)n));
+    NNAL_TRY(ensure(ctx, s->sw, 0, (size_t)n));
+    NNAL_TRY(ensure(ctx, s->diag, 0, (size_t)n));
+    NNAL_TRY(ensure(ctx, s->avail, 0, (size_t)n));
+    NNAL_TRY(ensure(ctx, s->rows, 0, (size_t)n));
+    s->cand_cap = n;
+  }
+  if (!s->sc) {
+    CUDA_TRY(ctx, cudaMalloc(&s->sc, sizeof(DevScalars)));
+    CUDA_TRY(ctx, cudaMemsetAsync(s->sc, 0, sizeof(DevScalars), ctx->stream));
+  }
+  return NNAL_OK;
+}
+
+static int run_setup(nnal_ctx* ctx, State* s, const float* post1, const double* p1_given) {
+  if (s->n == 0) return NNAL_OK;
+  setup_kernel<<<warp_grid(ctx, s->n), 256, 0, ctx->stream>>>(s->U, s->A, s->R(), post1, p1_given, s->beta2, s->n, s->d,
+                                                             s->dp, s->nl, s->w, s->sw, s->diag, s->avail);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+
+static int alloc_greedy(nnal_ctx* ctx, State* s, int64_t k) {
+  if (s->kcap < k || s->kcols_n < s->n || s->win_d < s->d || s->win_dp < s->dp) {
+    const int64_t kc = std::max<int64_t>(k, s->kcap);
+    const int64_t nn = std::max<int64_t>(s->n, s->kcols_n);
+    NNAL_TRY(ensure(ctx, s->kcols, 0, (size_t)kc * nn));
+    NNAL_TRY(ensure(ctx, s->kss, 0, (size_t)kc * kc));
+    NNAL_TRY(ensure(ctx, s->C, 0, (size_t)kc * (kc + 8)));
+    NNAL_TRY(ensure(ctx, s->inv_ws, 0, (size_t)(kc + 2) * (kc + 2)));
+    NNAL_TRY(ensure(ctx, s->red, 0, (size_t)kc));
+    NNAL_TRY(ensure(ctx, s->win_sw, 0, (size_t)kc));
+    NNAL_TRY(ensure(ctx, s->sel, 0, (size_t)kc));
+    NNAL_TRY(ensure(ctx, s->win_u, 0, (size_t)kc * s->d));
+    NNAL_TRY(ensure(ctx, s->win_a, 0, (size_t)kc * std::max(s->dp, 1)));
+    s->kcap = kc;
+    s->kcols_n = nn;
+    s->win_d = s->d;
+    s->win_dp = s->dp;
+  }
+  const int nblk = cdiv(std::max<int64_t>(s->n, 1), 128);
+  if (s->blk_cap < nblk) {
+    NNAL_TRY(ensure(ctx, s->blk_loss, 0, (size_t)nblk));
+    NNAL_TRY(ensure(ctx, s->blk_idx, 0, (size_t)nblk));
+    s->blk_cap = nblk;
+  }
+  return NNAL_OK;
+}
+
+// steps 1-3 of greedy step t: inverse, candidate evaluation, arg-min
+static int step_select(nnal_ctx* ctx, State* s, int t, int commit) {
+  const double alpha = (double)(t + 1) * s->delta;
+  const int ldc = (t + 7) / 8 * 8;
+  static bool attr_inv = false, attr_eval = false;
+  if (t > 0) {
+    const int use_smem = t <= T_SMEM ? 1 : 0;
+    const size_t smem = use_smem ? ((size_t)t * (t | 1) + t) * sizeof(double) : 0;
+    if (!attr_inv) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(((size_t)T_SMEM * (T_SMEM | 1) + T_SMEM) * sizeof(double))));
+      attr_inv = true;
+    }
+    invert_kernel<<<1, 1024, smem, ctx->stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->inv_ws, use_smem, s->sc);
+    ctx->launches++;
+  }
+  const int nblk = cdiv(s->n, 128);
+  if (t <= T_SMEM) {
+    if (!attr_eval) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)T_SMEM * ((T_SMEM + 7) / 8 * 8) * sizeof(double))));
+      attr_eval = true;
+    }
+    eval_kernel<true><<<nblk, 128, (size_t)t * ldc * sizeof(double), ctx->stream>>>(s->kcols, s->kcols_n, s->diag, s->avail, s->C, t,
+                                                                                   ldc, s->n, alpha, s->blk_loss, s->blk_idx);
+  } else {
+    eval_kernel<false><<<nblk, 128, 0, ctx->stream>>>(s->kcols, s->kcols_n, s->diag, s->avail, s->C, t, ldc, s->n, alpha,
+                                                     s->blk_loss, s->blk_idx);
+  }
+  pick_kernel<<<1, 256, 0, ctx->stream>>>(s->blk_loss, s->blk_idx, nblk, t, s->sc, commit, s->avail, s->sel, s->red);
+  ctx->launches += 2;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+// steps 5-6: winner slot t is filled; extend K_SS and compute the new kernel column
+static int step_extend(nnal_ctx* ctx, State* s, int t) {
+  const float* wa = s->nl == 2 ? s->win_a : nullptr;
+  kss_row_kernel<<<cdiv(t + 1, 8), 256, 0, ctx->stream>>>(s->win_u, wa, s->win_sw, s->beta2, t, s->d, s->dp, s->nl, s->kcap, s->kss);
+  ctx->launches++;
+  if (s->n > 0) {
+    column_kernel<<<warp_grid(ctx, s->n), 256, 0, ctx->stream>>>(s->U, s->A, s->R(), s->sw, s->beta2, s->win_u + (int64_t)t * s->d,
+                                                                wa ? wa + (int64_t)t * s->dp : nullptr, s->win_sw + t, s->n,
+                                                                s->d, s->dp, s->nl, s->kcols + (int64_t)t * s->kcols_n);
+    ctx->launches++;
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+static double param_dim(const State* s) {
+  double D = 2.0 * (s->d + 1.0);
+  if (s->nl == 2) D += (double)s->d * (s->dp + 1.0);
+  return D;
+}
+
+}  // namespace fi
+
+using fi::State;
+
+int nnal_fi_release(nnal_ctx* ctx) {
+  if (!ctx->fi_state) return NNAL_OK;
+  State* s = (State*)ctx->fi_state;
+  void* ptrs[] = {s->rows, s->ownU, s->ownA, s->w, s->sw, s->diag, s->avail, s->beta2, s->kcols, s->kss, s->C, s->inv_ws,
+                  s->red, s->win_sw, s->win_u, s->win_a, s->sel, s->blk_loss, s->blk_idx, s->sc, s->H, s->Xh, s->Xl, s->wq};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete s;
+  ctx->fi_state = nullptr;
+  return NNAL_OK;
+}
+
+int nnal_k_fi_trace_scores(nnal_ctx* ctx, const float* post, int c, int64_t n, const float* feat, int d, double* score) {
+  if (n == 0) return NNAL_OK;
+  fi::trace_score_kernel<<<fi::warp_grid(ctx, n), 256, 0, ctx->stream>>>(post, c, n, feat, d, score);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_set_candidates(nnal_ctx* ctx, const int64_t* cand, int64_t n_cand, int n_layers) {
+  if (!ctx || n_cand < 0) return NNAL_ERR_INVALID;
+  if (n_layers != 1 && n_layers != 2) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "FI covers the last 1 or 2 fully-connected layers");
+  if (!ctx->pool_post || !ctx->pool_feat || ctx->keep < 1) NNAL_FAIL(ctx, NNAL_ERR_STATE, "pool pass did not keep the feature layer");
+  if (n_layers == 2 && (!ctx->pool_prev || ctx->keep < 2)) NNAL_FAIL(ctx, NNAL_ERR_STATE, "pool pass did not keep the previous FC output");
+  if (ctx->n_class != 2) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "factored greedy FI is implemented for the binary model");
+  if (ctx->feature_layer != (int)ctx->layers.size() - 2) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "feature layer must feed the last FC layer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  State* s = fi::get(ctx);
+  const int64_t n = cand ? n_cand : ctx->pool_n;
+  if (cand)
+    for (int64_t i = 0; i < n; ++i)
+      if (cand[i] < 0 || cand[i] >= ctx->pool_n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "candidate position outside the pool");
+  s->n = n; s->nl = n_layers; s->d = ctx->feat_dim; s->dp = n_layers == 2 ? ctx->prev_dim : 0;
+  s->U = ctx->pool_feat; s->A = n_layers == 2 ? ctx->pool_prev : nullptr;
+  NNAL_TRY(fi::alloc_candidates(ctx, s, n));
+  s->use_rows = cand != nullptr;
+  if (cand && n) CUDA_TRY(ctx, cudaMemcpyAsync(s->rows, cand, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (s->beta_cap < s->d) { NNAL_TRY(fi::ensure(ctx, s->beta2, 0, (size_t)s->d)); s->beta_cap = s->d; }
+  prof_begin(ctx, NNAL_PROF_FI_SETUP);
+  fi::beta2_kernel<<<cdiv(s->d, 256), 256, 0, ctx->stream>>>(ctx->layers.back().W, s->d, s->beta2);
+  ctx->launches++;
+  int rc = fi::run_setup(ctx, s, ctx->pool_post + ctx->pool_n, nullptr);
+  prof_end(ctx);
+  NNAL_TRY(rc);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // `cand` is caller-owned host memory
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_set_factors(nnal_ctx* ctx, int64_t n, int d, int d_prev, const double* p1, const float* U,
+                                   const float* A_prev, const float* w_last) {
+  if (!ctx || n < 0 || d <= 0 || !p1 || !U) return NNAL_ERR_INVALID;
+  if ((A_prev != nullptr) != (w_last != nullptr) || (A_prev && d_prev <= 0))
+    NNAL_FAIL(ctx, NNAL_ERR_INVALID, "two-layer FI needs both the previous activations and the last-layer weights");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  State* s = fi::get(ctx);
+  s->n = n; s->nl = A_prev ? 2 : 1; s->d = d; s->dp = A_prev ? d_prev : 0;
+  NNAL_TRY(fi::alloc_candidates(ctx, s, n));
+  s->use_rows = false;
+  if (s->own_cap_u < n * d) { NNAL_TRY(fi::ensure(ctx, s->ownU, 0, (size_t)n * d)); s->own_cap_u = n * d; }
+  if (A_prev && s->own_cap_a < n * d_prev) { NNAL_TRY(fi::ensure(ctx, s->ownA, 0, (size_t)n * d_prev)); s->own_cap_a = n * d_prev; }
+  if (s->beta_cap < d) { NNAL_TRY(fi::ensure(ctx, s->beta2, 0, (size_t)d)); s->beta_cap = d; }
+  double* d_p1 = nullptr;
+  NNAL_TRY(devbuf_reserve(ctx, ctx->fi_ws, (size_t)n * 8 + (size_t)2 * d * 4 + 64));
+  d_p1 = (double*)ctx->fi_ws.p;
+  float* d_wl = (float*)((char*)ctx->fi_ws.p + (size_t)n * 8);
+  if (n) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(s->ownU, U, (size_t)n * d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (A_prev) CUDA_TRY(ctx, cudaMemcpyAsync(s->ownA, A_prev, (size_t)n * d_prev * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_p1, p1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  s->U = s->ownU; s->A = A_prev ? s->ownA : nullptr;
+  if (w_last) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_wl, w_last, (size_t)2 * d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    fi::beta2_kernel<<<cdiv(d, 256), 256, 0, ctx->stream>>>(d_wl, d, s->beta2);
+    ctx->launches++;
+  }
+  NNAL_TRY(fi::run_setup(ctx, s, nullptr, d_p1));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_info(nnal_ctx* ctx, int64_t* n_cand, int* n_layers, int* d, int* d_prev, double* param_dim) {
+  if (!ctx || !ctx->fi_state) return NNAL_ERR_STATE;
+  State* s = (State*)ctx->fi_state;
+  if (n_cand) *n_cand = s->n;
+  if (n_layers) *n_layers = s->nl;
+  if (d) *d = s->d;
+  if (d_prev) *d_prev = s->dp;
+  if (param_dim) *param_dim = fi::param_dim(s);
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_begin(nnal_ctx* ctx, int64_t k, double delta) {
+  if (!ctx || k < 0 || !(delta > 0)) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  if (k > 4096) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "greedy FI selection supports k <= 4096");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  State* s = (State*)ctx->fi_state;
+  s->delta = delta;
+  NNAL_TRY(fi::alloc_greedy(ctx, s, std::max<int64_t>(k, 1)));
+  if (s->n) CUDA_TRY(ctx, cudaMemsetAsync(s->avail, 1, (size_t)s->n, ctx->stream));
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_greedy(nnal_ctx* ctx, int64_t k, double delta, int64_t* sel_out, double* obj_out, double* red_out) {
+  if (!ctx || !sel_out || k < 0) return NNAL_ERR_INVALID;
+  NNAL_TRY(nnal_fi_begin(ctx, k, delta));
+  State* s = (State*)ctx->fi_state;
+  if (k > s->n) k = s->n;
+  if (k == 0) return NNAL_OK;
+  prof_begin(ctx, NNAL_PROF_FI_GREEDY);
+  for (int t = 0; t < (int)k; ++t) {
+    NNAL_TRY(fi::step_select(ctx, s, t, 1));
+    fi::copy_winner_kernel<<<8, 256, 0, ctx->stream>>>(s->U, s->A, s->R(), s->sw, &s->sc->best_idx, t, s->d, s->dp, s->win_u,
+                                                      s->win_a, s->win_sw);
+    ctx->launches++;
+    NNAL_TRY(fi::step_extend(ctx, s, t));
+  }
+  prof_end(ctx);
+  std::vector<double> red((size_t)k);
+  static_assert(sizeof(long long) == sizeof(int64_t), "");
+  CUDA_TRY(ctx, cudaMemcpyAsync(sel_out, s->sel, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(red.data(), s->red, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const double D = fi::param_dim(s);
+  for (int64_t t = 0; t < k; ++t) {
+    if (red_out) red_out[t] = red[t];
+    if (obj_out) obj_out[t] = (D - (double)(t + 1)) / delta + red[t];
+  }
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_step_local_best(nnal_ctx* ctx, int64_t step, double* loss_out, int64_t* cand_out, double* trC_out) {
+  if (!ctx || !loss_out || !cand_out || step < 0) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  State* s = (State*)ctx->fi_state;
+  if (step >= s->kcap) NNAL_FAIL(ctx, NNAL_ERR_STATE, "nnal_fi_begin not called with a large enough k");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (s->n > 0) {
+    NNAL_TRY(fi::step_select(ctx, s, (int)step, 0));
+  } else {
+    // a rank without candidates still needs tr C of the shared winners' system
+    if (step > 0) {
+      const int t = (int)step;
+      const int use_smem = t <= fi::T_SMEM ? 1 : 0;
+      const size_t smem = use_smem ? ((size_t)t * (t | 1) + t) * sizeof(double) : 0;
+      CUDA_TRY(ctx, cudaFuncSetAttribute(fi::invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(((size_t)fi::T_SMEM * (fi::T_SMEM | 1) + fi::T_SMEM) * sizeof(double))));
+      fi::invert_kernel<<<1, 1024, smem, ctx->stream>>>(s->kss, s->kcap, t, (double)(t + 1) * s->delta, s->C, (t + 7) / 8 * 8,
+                                                       s->inv_ws, use_smem, s->sc);
+      ctx->launches++;
+    }
+  }
+  fi::DevScalars h;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&h, s->sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (s->n > 0) { *loss_out = h.best_loss; *cand_out = h.best_idx; }
+  else { *loss_out = INFINITY; *cand_out = -1; }
+  if (trC_out) *trC_out = step > 0 ? h.trC : 0.0;
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_winner_factors(nnal_ctx* ctx, int64_t cand, float* factors_out, int64_t* n_floats) {
+  if (!ctx || !n_floats) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  State* s = (State*)ctx->fi_state;
+  const int64_t nf = (int64_t)s->d + s->dp + 2;
+  *n_floats = nf;
+  if (!factors_out) return NNAL_OK;                       // size query
+  if (cand < 0 || cand >= s->n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "candidate index out of range");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int64_t row = cand;
+  if (s->use_rows) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(&row, s->rows + cand, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(factors_out, s->U + row * s->d, (size_t)s->d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (s->nl == 2)
+    CUDA_TRY(ctx, cudaMemcpyAsync(factors_out + s->d, s->A + row * s->dp, (size_t)s->dp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(factors_out + s->d + s->dp, s->sw + cand, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_step_apply(nnal_ctx* ctx, int64_t step, const float* winner_factors, int64_t n_floats, int owner_is_local,
+                                  int64_t cand_local) {
+  if (!ctx || !winner_factors || step < 0) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  State* s = (State*)ctx->fi_state;
+  if (step >= s->kcap) NNAL_FAIL(ctx, NNAL_ERR_STATE, "nnal_fi_begin not called with a large enough k");
+  if (n_floats != (int64_t)s->d + s->dp + 2) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "winner factor vector has the wrong length");
+  if (owner_is_local && (cand_local < 0 || cand_local >= s->n)) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "candidate index out of range");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int t = (int)step;
+  CUDA_TRY(ctx, cudaMemcpyAsync(s->win_u + (int64_t)t * s->d, winner_factors, (size_t)s->d * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (s->nl == 2)
+    CUDA_TRY(ctx, cudaMemcpyAsync(s->win_a + (int64_t)t * s->dp, winner_factors + s->d, (size_t)s->dp * 4, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(s->win_sw + t, winner_factors + s->d + s->dp, 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (owner_is_local) {
+    fi::mark_taken_kernel<<<1, 1, 0, ctx->stream>>>(s->avail, (long long)cand_local);
+    ctx->launches++;
+  }
+  NNAL_TRY(fi::step_extend(ctx, s, t));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // winner_factors is caller-owned host memory
+  return NNAL_OK;
+}
+
+// ---- weighted Gram on tensor cores -----------------------------------------------------------------------
+extern "C" int nnal_fi_gram(nnal_ctx* ctx, const double* q, float* H_out) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  State* s = (State*)ctx->fi_state;
+  const int Dg = s->d + 1;
+  const int ld = (Dg + 7) / 8 * 8;
+  if (s->Hd != Dg) {
+    NNAL_TRY(fi::ensure(ctx, s->H, 0, (size_t)Dg * ld));
+    s->Hd = Dg; s->Hld = ld;
+  }
+  CUDA_TRY(ctx, cudaMemsetAsync(s->H, 0, (size_t)Dg * ld * 4, ctx->stream));
+  if (s->n > 0) {
+    if (s->wq_cap < s->n) { NNAL_TRY(fi::ensure(ctx, s->wq, 0, (size_t)s->n)); s->wq_cap = s->n; }
+    const double* d_q = nullptr;
+    if (q) {
+      NNAL_TRY(devbuf_reserve(ctx, ctx->fi_ws, (size_t)s->n * 8));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->fi_ws.p, q, (size_t)s->n * 8, cudaMemcpyHostToDevice, ctx->stream));
+      d_q = (const double*)ctx->fi_ws.p;
+    }
+    prof_begin(ctx, NNAL_PROF_FI_SETUP);
+    fi::wq_kernel<<<std::min(cdiv(s->n, 256), ctx->sm_count * 8), 256, 0, ctx->stream>>>(s->w, d_q, s->n, s->wq);
+    CUDA_TRY(ctx, cudaMemsetAsync(&s->sc->gmax_bits, 0, 4, ctx->stream));
+    fi::gram_max_kernel<<<fi::warp_grid(ctx, s->n), 256, 0, ctx->stream>>>(s->U, s->R(), s->wq, s->n, s->d, s->sc);
+    ctx->launches += 2;
+    prof_end(ctx);
+    fi::DevScalars h;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&h, s->sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float gmax;
+    memcpy(&gmax, &h.gmax_bits, 4);
+    if (gmax > 0.f && gmax < 3.0e38f) {
+      int ex;
+      frexpf(gmax, &ex);
+      int e = 13 - ex;                                    // scaled operands below 2^13: the K-sum of squares stays finite in fp32
+      e = std::max(-60, std::min(60, e));
+      const float scale = ldexpf(1.f, e), inv2 = ldexpf(1.f, -2 * e);
+      const int64_t CH = 65536;
+      const int64_t ldp = std::min<int64_t>(CH, (s->n + 7) / 8 * 8);
+      const size_t plane = (size_t)Dg * ldp;
+      if (s->plane_cap < plane) {
+        NNAL_TRY(fi::ensure(ctx, s->Xh, 0, plane));
+        NNAL_TRY(fi::ensure(ctx, s->Xl, 0, plane));
+        s->plane_cap = plane;
+      }
+      for (int64_t i0 = 0; i0 < s->n; i0 += CH) {
+        const int64_t nc = std::min(CH, s->n - i0);
+        prof_begin(ctx, NNAL_PROF_FI_SETUP);
+        dim3 grid(cdiv(ldp, 32), cdiv(Dg, 32)), block(32, 8);
+        fi::gram_planes_kernel<<<grid, block, 0, ctx->stream>>>(s->U, s->R(), s->wq, i0, nc, ldp, s->d, scale, s->Xh, s->Xl);
+        ctx->launches++;
+        prof_end(ctx);
+        prof_begin(ctx, NNAL_PROF_FI_GRAM);
+        int rc = nnal_tc_gemm_planes(ctx, s->Xh, s->Xl, ldp, Dg, s->Xh, s->Xl, ldp, Dg, nc, nullptr, inv2, 0, i0 > 0 ? 1 : 0, s->H,
+                                     ld, nullptr, nullptr, 0);
+        prof_end(ctx);
+        NNAL_TRY(rc);
+      }
+    }
+  }
+  if (H_out) {
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(H_out, (size_t)Dg * 4, s->H, (size_t)ld * 4, (size_t)Dg * 4, Dg, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+extern "C" void* nnal_fi_gram_ptr(nnal_ctx* ctx, int64_t* rows, int64_t* ld) {
+  if (!ctx || !ctx->fi_state) return nullptr;
+  State* s = (State*)ctx->fi_state;
+  if (rows) *rows = s->Hd;
+  if (ld) *ld = s->Hld;
+  return s->H;
+}
+
+extern "C" int nnal_fi_gram_read(nnal_ctx* ctx, float* H_out) {
+  if (!ctx || !H_out) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state || !((State*)ctx->fi_state)->H) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no Gram computed");
+  State* s = (State*)ctx->fi_state;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaMemcpy2DAsync(H_out, (size_t)s->Hd * 4, s->H, (size_t)s->Hld * 4, (size_t)s->Hd * 4, s->Hd, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}

@@ -151,6 +151,7 @@ struct FcParams {
   int ld_split;              // row stride (elements) of the split planes
   int M, N, num_kb, relu, ldo;
   float w_scale_inv;
+  int accum;                 // out += result (Gram partial sums over sample chunks)
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -282,11 +283,18 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
           if (col0 + 16 <= p.N) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float x = sum[c + j] * p.w_scale_inv + __ldg(p.bias + col0 + j);
+              float x = sum[c + j] * p.w_scale_inv + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
               v[j] = p.relu ? fmaxf(x, 0.f) : x;
             }
             if (p.out) {
               float4* dst = reinterpret_cast<float4*>(p.out + (size_t)row * p.ldo + col0);
+              if (p.accum) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 o = dst[j];
+                  v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+                }
+              }
 #pragma unroll
               for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
@@ -311,8 +319,9 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               if (col0 + j < p.N) {
-                float x = sum[c + j] * p.w_scale_inv + __ldg(p.bias + col0 + j);
+                float x = sum[c + j] * p.w_scale_inv + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
                 x = p.relu ? fmaxf(x, 0.f) : x;
+                if (p.out && p.accum) x += p.out[(size_t)row * p.ldo + col0 + j];
                 if (p.out) p.out[(size_t)row * p.ldo + col0 + j] = x;
                 if (p.out_hi) {
                   nnal_h h, l;
@@ -419,33 +428,43 @@ int nnal_tc_prepare_layer(nnal_ctx* ctx, Layer& L) {
   return NNAL_OK;
 }
 
-// A operand given as bf16 hi/lo planes [n][lda] (lda >= K, K % 8 == 0; the K tail of the last 64-wide
-// block is zero-filled by TMA).  Outputs: fp32 [n][N] (out, may be null) and/or bf16 hi/lo planes
-// [n][N] of the activated result (the next tensor-core layer's A operand).
-int nnal_tc_fc_planes(nnal_ctx* ctx, const Layer& L, const nnal_h* Ah, const nnal_h* Al, int lda, float* out,
-                      nnal_h* out_hi, nnal_h* out_lo, int64_t n) {
-  if (n == 0) return NNAL_OK;
+// Generic split-plane GEMM  out[M][N] (+)= scale * A[M][K] . B[N][K]^T (+ bias, ReLU): both operands are
+// fp16 hi/lo planes, K-major, row strides lda/ldb elements (multiples of 8); the K tail of the last
+// 64-wide block and rows beyond M/N are zero-filled by TMA.
+int nnal_tc_gemm_planes(nnal_ctx* ctx, const nnal_h* Ah, const nnal_h* Al, int64_t lda, int64_t M, const nnal_h* Bh,
+                        const nnal_h* Bl, int64_t ldb, int N, int64_t K, const float* bias, float scale, int relu,
+                        int accum, float* out, int ldo, nnal_h* out_hi, nnal_h* out_lo, int ld_split) {
+  if (M == 0 || N == 0) return NNAL_OK;
   tc::TcState* st;
   NNAL_TRY(tc::get_state(ctx, &st));
-  const int K = L.in_dim, Kp = L.k_pad, N = L.out_dim;
   CUtensorMap tmAh, tmAl, tmBh, tmBl;
-  NNAL_TRY(tc::make_tmap(ctx, st, &tmAh, Ah, K, (uint64_t)n, lda, tc::BM));
-  NNAL_TRY(tc::make_tmap(ctx, st, &tmAl, Al, K, (uint64_t)n, lda, tc::BM));
-  NNAL_TRY(tc::make_tmap(ctx, st, &tmBh, L.Wh, Kp, (uint64_t)N, Kp, tc::BN));
-  NNAL_TRY(tc::make_tmap(ctx, st, &tmBl, L.Wl, Kp, (uint64_t)N, Kp, tc::BN));
+  NNAL_TRY(tc::make_tmap(ctx, st, &tmAh, Ah, (uint64_t)K, (uint64_t)M, (uint64_t)lda, tc::BM));
+  NNAL_TRY(tc::make_tmap(ctx, st, &tmAl, Al, (uint64_t)K, (uint64_t)M, (uint64_t)lda, tc::BM));
+  NNAL_TRY(tc::make_tmap(ctx, st, &tmBh, Bh, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, tc::BN));
+  NNAL_TRY(tc::make_tmap(ctx, st, &tmBl, Bl, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, tc::BN));
   if (!st->attr_set) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(tc::fc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     st->attr_set = true;
   }
   tc::FcParams p;
-  p.bias = L.b; p.out = out; p.out_hi = out_hi; p.out_lo = out_lo; p.ld_split = N;
-  p.M = (int)n; p.N = N; p.num_kb = Kp / tc::BK; p.relu = L.relu; p.ldo = N; p.w_scale_inv = L.w_scale_inv;
-  const int ntiles = cdiv(n, tc::BM) * cdiv(N, tc::BN);
+  p.bias = bias; p.out = out; p.out_hi = out_hi; p.out_lo = out_lo; p.ld_split = ld_split;
+  p.M = (int)M; p.N = N; p.num_kb = (int)((K + tc::BK - 1) / tc::BK); p.relu = relu; p.ldo = ldo; p.w_scale_inv = scale;
+  p.accum = accum;
+  const int ntiles = cdiv(M, tc::BM) * cdiv(N, tc::BN);
   const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
   tc::fc_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, ctx->stream>>>(tmAh, tmAl, tmBh, tmBl, p);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
+}
+
+// A operand given as fp16 hi/lo planes [n][lda] (lda >= K, K % 8 == 0; the K tail of the last 64-wide
+// block is zero-filled by TMA).  Outputs: fp32 [n][N] (out, may be null) and/or fp16 hi/lo planes
+// [n][N] of the activated result (the next tensor-core layer's A operand).
+int nnal_tc_fc_planes(nnal_ctx* ctx, const Layer& L, const nnal_h* Ah, const nnal_h* Al, int lda, float* out,
+                      nnal_h* out_hi, nnal_h* out_lo, int64_t n) {
+  return nnal_tc_gemm_planes(ctx, Ah, Al, lda, n, L.Wh, L.Wl, L.k_pad, L.out_dim, L.in_dim, L.b, L.w_scale_inv, L.relu, 0,
+                             out, L.out_dim, out_hi, out_lo, L.out_dim);
 }
 
 // fp32 A operand [n][K]: split into planes first (used by the isolated test hook and mixed pipelines)

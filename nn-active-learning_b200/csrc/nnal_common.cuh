@@ -105,6 +105,7 @@ struct nnal_ctx {
   size_t pool_cap_n = 0;                 // allocation capacities of the pool arrays (samples)
   int pool_cap_keep = -1, pool_cap_class = 0, pool_cap_feat = 0, pool_cap_prev = 0;
   void* tc_state = nullptr;              // tensor-map cache etc. (gemm_tc.cu)
+  void* fi_state = nullptr;              // Fisher-information candidate set / greedy state (fi.cu)
 };
 
 #define CUDA_TRY(ctx, expr)                                                            \
@@ -145,6 +146,9 @@ static inline void prof_end(nnal_ctx* ctx) {
 #define NNAL_PROF_GATHER 100
 #define NNAL_PROF_SCORE 101
 #define NNAL_PROF_TOPK 102
+#define NNAL_PROF_FI_SETUP 110
+#define NNAL_PROF_FI_GRAM 111
+#define NNAL_PROF_FI_GREEDY 112
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -174,6 +178,9 @@ int nnal_tc_release(nnal_ctx*);
 int nnal_tc_fc(nnal_ctx*, const Layer&, const float* in, float* out, int64_t n);
 int nnal_tc_fc_planes(nnal_ctx*, const Layer&, const nnal_h* Ah, const nnal_h* Al, int lda, float* out,
                       nnal_h* out_hi, nnal_h* out_lo, int64_t n);
+int nnal_tc_gemm_planes(nnal_ctx*, const nnal_h* Ah, const nnal_h* Al, int64_t lda, int64_t M, const nnal_h* Bh,
+                        const nnal_h* Bl, int64_t ldb, int N, int64_t K, const float* bias, float scale, int relu,
+                        int accum, float* out, int ldo, nnal_h* out_hi, nnal_h* out_lo, int ld_split);
 int nnal_k_split_flat(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t count);
 int nnal_k_split_pad(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t rows, int C, int Cp);
 int nnal_k_merge_flat(nnal_ctx*, const nnal_h* hi, const nnal_h* lo, float* out, int64_t count);
@@ -184,3 +191,5 @@ int nnal_k_conv_simt_split(nnal_ctx*, const Layer&, const float* in, nnal_h* out
 int nnal_k_pool_split(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
                       nnal_h* out_lo, int64_t n);
 int nnal_forward_chunk(nnal_ctx*, int64_t nb, int64_t offset);
+// fi.cu
+int nnal_k_fi_trace_scores(nnal_ctx*, const float* post, int c, int64_t n, const float* feat, int d, double* score);

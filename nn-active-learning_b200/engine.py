@@ -270,6 +270,104 @@ class Engine(object):
         return (idx, sc) if with_scores else idx
 
     # ------------------------------------------------------------------
+    # Fisher information
+    # ------------------------------------------------------------------
+    def fi_set_candidates(self, cand=None, n_layers=2):
+        """Candidates = pool positions ``cand`` (None: every pool sample) of the current pool pass."""
+        if cand is None:
+            self._chk(self.lib.nnal_fi_set_candidates(self.h, None, 0, int(n_layers)))
+        else:
+            cand = np.ascontiguousarray(cand, dtype=np.int64).ravel()
+            self.h2d_bytes += cand.nbytes
+            self._chk(self.lib.nnal_fi_set_candidates(self.h, _ptr(cand), cand.size, int(n_layers)))
+
+    def fi_set_factors(self, p1, U, A_prev=None, w_last=None):
+        """Candidates from host factors: ``p1`` [n], ``U`` [n,d], ``A_prev`` [n,d_prev], ``w_last`` [2,d]."""
+        p1 = np.ascontiguousarray(p1, dtype=np.float64).ravel()
+        U = np.ascontiguousarray(U, dtype=np.float32)
+        n, d = U.shape
+        if p1.size != n:
+            raise ValueError('p1 and U disagree on the number of candidates')
+        if A_prev is not None:
+            A_prev = np.ascontiguousarray(A_prev, dtype=np.float32)
+            w_last = np.ascontiguousarray(w_last, dtype=np.float32)
+            if A_prev.shape[0] != n or w_last.shape != (2, d):
+                raise ValueError('A_prev must be [n,d_prev] and w_last [2,d]')
+        self.h2d_bytes += p1.nbytes + U.nbytes + (A_prev.nbytes + w_last.nbytes if A_prev is not None else 0)
+        self._chk(self.lib.nnal_fi_set_factors(self.h, n, d, 0 if A_prev is None else A_prev.shape[1], _ptr(p1), _ptr(U),
+                                               None if A_prev is None else _ptr(A_prev),
+                                               None if A_prev is None else _ptr(w_last)))
+
+    def fi_info(self):
+        n, nl, d, dp, D = C.c_int64(), C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        self._chk(self.lib.nnal_fi_info(self.h, C.byref(n), C.byref(nl), C.byref(d), C.byref(dp), C.byref(D)))
+        return {'n': n.value, 'n_layers': nl.value, 'd': d.value, 'd_prev': dp.value, 'D': D.value}
+
+    def fi_gram(self, q=None, read=True):
+        """Weighted Gram ``sum_i q_i p_i(1-p_i) [u_i;1][u_i;1]^T`` ((d+1)x(d+1) float32)."""
+        info = self.fi_info()
+        if q is not None:
+            q = np.ascontiguousarray(q, dtype=np.float64).ravel()
+            if q.size != info['n']:
+                raise ValueError('q must have one weight per candidate')
+            self.h2d_bytes += q.nbytes
+        out = np.empty((info['d'] + 1, info['d'] + 1), dtype=np.float32) if read else None
+        if read:
+            self.d2h_bytes += out.nbytes
+        self._chk(self.lib.nnal_fi_gram(self.h, None if q is None else _ptr(q), None if out is None else _ptr(out)))
+        return out
+
+    def fi_gram_device(self):
+        """(device pointer, rows, row stride) of the Gram left on the device by ``fi_gram``."""
+        rows, ld = C.c_int64(), C.c_int64()
+        p = self.lib.nnal_fi_gram_ptr(self.h, C.byref(rows), C.byref(ld))
+        return p, rows.value, ld.value
+
+    def fi_gram_read(self):
+        info = self.fi_info()
+        out = np.empty((info['d'] + 1, info['d'] + 1), dtype=np.float32)
+        self.d2h_bytes += out.nbytes
+        self._chk(self.lib.nnal_fi_gram_read(self.h, _ptr(out)))
+        return out
+
+    def fi_greedy(self, k, delta):
+        """Returns (candidate indices in selection order, objective per step, reduced objective)."""
+        k = int(min(k, self.fi_info()['n']))
+        sel = np.empty(k, dtype=np.int64)
+        obj = np.empty(k, dtype=np.float64)
+        red = np.empty(k, dtype=np.float64)
+        self.d2h_bytes += sel.nbytes + obj.nbytes
+        self._chk(self.lib.nnal_fi_greedy(self.h, k, float(delta), _ptr(sel), _ptr(obj), _ptr(red)))
+        return sel, obj, red
+
+    def fi_begin(self, k, delta):
+        self._chk(self.lib.nnal_fi_begin(self.h, int(k), float(delta)))
+
+    def fi_step_local_best(self, step):
+        loss, cand, trc = C.c_double(), C.c_int64(), C.c_double()
+        self._chk(self.lib.nnal_fi_step_local_best(self.h, int(step), C.byref(loss), C.byref(cand), C.byref(trc)))
+        return loss.value, cand.value, trc.value
+
+    def fi_winner_factors(self, cand):
+        nf = C.c_int64()
+        self._chk(self.lib.nnal_fi_winner_factors(self.h, 0, None, C.byref(nf)))
+        out = np.empty(nf.value, dtype=np.float32)
+        self._chk(self.lib.nnal_fi_winner_factors(self.h, int(cand), _ptr(out), C.byref(nf)))
+        self.d2h_bytes += out.nbytes
+        return out
+
+    def fi_factor_len(self):
+        nf = C.c_int64()
+        self._chk(self.lib.nnal_fi_winner_factors(self.h, 0, None, C.byref(nf)))
+        return nf.value
+
+    def fi_step_apply(self, step, factors, owner_is_local, cand_local):
+        factors = np.ascontiguousarray(factors, dtype=np.float32)
+        self.h2d_bytes += factors.nbytes
+        self._chk(self.lib.nnal_fi_step_apply(self.h, int(step), _ptr(factors), factors.size, 1 if owner_is_local else 0,
+                                              int(cand_local)))
+
+    # ------------------------------------------------------------------
     # stand-alone helpers
     # ------------------------------------------------------------------
     def entropy(self, P, kind=L.SCORE_ENTROPY, eps=10e-8):

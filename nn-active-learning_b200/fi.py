@@ -1,0 +1,162 @@
+"""Fisher-information (FI) queries: the ``'fi'`` branches of ``PW_NNAL.CNN_query``
+(PW_NNAL.py:89-163), ``PW_NNAL.query_multimg`` (:547-627) and ``NNAL.CNN_query`` (NNAL.py:312-464).
+
+The reference builds one tau x tau conditional FI per pre-filtered sample from 2B single-sample
+``sess.run(tf.gradients)`` calls, solves an SDP for a query distribution and SAMPLES k indices from it
+with the unseeded global RNG.  The drop-in keeps the reference's pipeline shape -- uncertainty
+pre-filter to B (:108-115, 549-551), conditional FIs of the B candidates, selection of k -- but
+
+* keeps the FI of the last ``fi_layers`` (default 2) fully-connected layers in factored form
+  (NN.LLFC_grads NN.py:905-955, NNAL_tools.FC_gradnorms_batch NNAL_tools.py:725-775), and
+* replaces SDP + sampling by the deterministic greedy minimisation of the SAME objective
+  ``tr((sum_i q_i A_i)^-1)`` (NNAL_tools.py:589-602) at ``q = uniform(S)`` (FI section).
+
+``expr.pars`` keys read: ``k``, ``B`` (reference keys) and the optional ``fi_layers`` (1 or 2) and
+``fi_diag_load`` (the reference's ``diag_load``: 1e-5 single-volume PW_NNAL.py:738-745, 1e-3 multi-volume
+:573-578)."""
+import numpy as np
+
+from . import _lib as L
+from . import dist, patch_utils
+from .engine import get_engine
+
+
+def greedy_select(eng, k, delta, gids=None):
+    """Greedy FI selection over the engine's current candidate set.
+
+    Single process: one device-side loop (``nnal_fi_greedy``).  Several ranks: every step combines the
+    ranks' local best candidates (all-gather of one (loss, id) pair), the owner broadcasts its winner's
+    factor vector and every rank applies the same rank-one update.  ``gids``: global candidate ids of
+    this rank's candidates (ascending), used for the result and for tie-breaking (lowest id).
+    Returns (selected global ids in selection order, objective after each step)."""
+    n_local = eng.fi_info()['n']
+    if gids is None:
+        gids = np.arange(n_local, dtype=np.int64)
+    if not dist.is_dist():
+        sel, obj, _ = eng.fi_greedy(k, delta)
+        return gids[sel], obj
+    import torch
+    rank, world = dist.rank_world()
+    n_total = int(dist.allreduce_sum_(torch.tensor([n_local], dtype=torch.int64, device=dist._device())).item())
+    k = min(int(k), n_total)
+    D = eng.fi_info()['D']
+    nf = eng.fi_factor_len()
+    eng.fi_begin(max(k, 1), delta)
+    sel, obj = [], []
+    none = float(np.iinfo(np.int64).max >> 12)
+    for t in range(k):
+        loss, cand, trc = eng.fi_step_local_best(t)
+        gid = float(gids[cand]) if cand >= 0 else none
+        val, payload, owner = dist.allreduce_argmin(loss, gid)
+        mine = (owner == rank)
+        f = eng.fi_winner_factors(cand) if mine else np.zeros(nf, dtype=np.float32)
+        f = dist.broadcast_array(f, owner)
+        eng.fi_step_apply(t, f, mine, cand if mine else 0)
+        sel.append(int(payload))
+        obj.append((D - (t + 1)) / delta + (t + 1) * (trc + val))
+    return np.array(sel, dtype=np.int64), np.array(obj)
+
+
+def _pars(expr, default_delta):
+    nl = int(expr.pars.get('fi_layers', 2))
+    delta = float(expr.pars.get('fi_diag_load', default_delta))
+    return nl, delta
+
+
+def query_single(expr, model, sess, padded_imgs, pool_inds, return_objective=False):
+    """``PW_NNAL.CNN_query(..., 'fi')``: positions into ``pool_inds`` (greedy selection order)."""
+    from .PW_NNAL import _score_pool_single, _stats_list
+    k, B = int(expr.pars['k']), int(expr.pars['B'])
+    nl, delta = _pars(expr, 1e-5)
+    pool_inds = np.asarray(pool_inds)
+    n = len(pool_inds)
+    if B < n:
+        eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=0)
+        eng.pool_score(L.SCORE_BINARY)
+        idx, sc = eng.pool_topk(B, with_scores=True)
+        sel_inds, _ = dist.allgather_topk(sc, idx + lo, B)
+        own = (sel_inds >= lo) & (sel_inds < hi)
+        mine = sel_inds[own]
+        # second pass over this rank's candidates, keeping the factors of the last FC layers
+        eng.pool_begin(len(mine), nl)
+        if len(mine):
+            imgs = list(padded_imgs)
+            eng.pool_eval(0, pool_inds[mine], 0, expr.pars['patch_shape'], _stats_list(expr.pars['stats'], len(imgs)),
+                          L.NORM_BATCH_EVAL, shape=imgs[0].shape)
+    else:
+        eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=nl)
+        sel_inds = np.arange(n, dtype=np.int64)
+        own = (sel_inds >= lo) & (sel_inds < hi)
+    eng.fi_set_candidates(None, nl)
+    gids = np.nonzero(own)[0].astype(np.int64)
+    chosen, obj = greedy_select(eng, min(k, len(sel_inds)), delta, gids)
+    q = sel_inds[chosen]
+    return (q, obj) if return_objective else q
+
+
+def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, return_objective=False):
+    """``PW_NNAL.query_multimg(..., 'fi')``: list of S arrays of local positions into ``pool_inds[s]``.
+    Candidate order = the reference's: subject-major, uncertainty order inside a subject
+    (``A += gen_A_matrices(...)`` per subject, PW_NNAL.py:566-578)."""
+    from .PW_NNAL import _bin_filter_core
+    k, B = int(expr.pars['k']), int(expr.pars['B'])
+    nl, delta = _pars(expr, 1e-3)
+    eng = get_engine()
+    sorted_inds, _, lo, hi, sizes = _bin_filter_core(expr, model, sess, all_padded_imgs, pool_inds, B)
+    s = len(pool_inds)
+    m = len(all_padded_imgs[0]) - 1
+    cum = np.append(-1, np.cumsum(sizes) - 1)
+    set_of = cum.searchsorted(sorted_inds) - 1
+    order = np.argsort(set_of, kind='stable')
+    G = sorted_inds[order]                       # global positions, subject-major candidate order
+    G_set = set_of[order]
+    own = (G >= lo) & (G < hi)
+    eng.pool_begin(int(own.sum()), nl)
+    off = 0
+    for i in range(s):
+        sel = own & (G_set == i)
+        ni = int(sel.sum())
+        if ni == 0:
+            continue
+        local = G[sel] - (cum[i] + 1)
+        imgs = list(all_padded_imgs[i][:-1])
+        eng.upload(i, imgs)
+        stats = np.array([[expr.train_stats[i, 2 * j], expr.train_stats[i, 2 * j + 1]] for j in range(m)],
+                         dtype=np.float64)
+        eng.pool_eval(i, np.asarray(pool_inds[i])[local], off, expr.pars['patch_shape'], stats, L.NORM_BATCH_EVAL,
+                      shape=imgs[0].shape)
+        off += ni
+    eng.fi_set_candidates(None, nl)
+    gids = np.nonzero(own)[0].astype(np.int64)
+    chosen, obj = greedy_select(eng, min(k, len(G)), delta, gids)
+    Q = patch_utils.global2local_inds(G[chosen], sizes)
+    return (Q, obj) if return_objective else Q
+
+
+def query_whole(model, expr, pool_inds, session):
+    """``NNAL.CNN_query(..., 'fi')`` (NNAL.py:312-464).  Binary models: uncertainty pre-filter to B
+    (entropy, NNAL_tools.uncertainty_filtering) + last-layer factored greedy.  c > 2: the k pool
+    samples with the largest last-layer FI trace ``(1-|pi|^2)(|u|^2+1)``, the closed form the
+    reference itself uses in its self-contained FI scorer (NNAL.py:121-139)."""
+    from .NNAL import _posteriors_on_device
+    k, B = int(expr.pars['k']), int(expr.pars['B'])
+    nl, delta = _pars(expr, 1e-5)
+    pool_inds = np.asarray(pool_inds)
+    n = len(pool_inds)
+    eng, lo, hi = _posteriors_on_device(model, expr, pool_inds, session, keep=1)
+    if eng.n_class != 2:
+        eng.pool_score(L.SCORE_NEG_FI_TRACE)
+        idx, sc = eng.pool_topk(k, with_scores=True)
+        q, _ = dist.allgather_topk(sc, idx + lo, min(k, n))
+        return q
+    if B < n:
+        eng.pool_score(L.SCORE_NEG_ENTROPY, 1e-8)
+        idx, sc = eng.pool_topk(B, with_scores=True)
+        sel_inds, _ = dist.allgather_topk(sc, idx + lo, B)
+    else:
+        sel_inds = np.arange(n, dtype=np.int64)
+    own = (sel_inds >= lo) & (sel_inds < hi)
+    eng.fi_set_candidates(sel_inds[own] - lo, 1)
+    gids = np.nonzero(own)[0].astype(np.int64)
+    chosen, _ = greedy_select(eng, min(k, len(sel_inds)), delta, gids)
+    return sel_inds[chosen]

@@ -18,7 +18,7 @@ which is exactly the SDP objective of NNAL_tools.py:589-602 evaluated at
 q = uniform(S).
 """
 import numpy as np
-from .nnal_oracle import forward, stable_topk
+from .nnal_oracle import forward, stable_topk, batch_eval, get_patches, normalize_batch_eval
 
 __all__ = [
     'class_score_factors', 'explicit_class_gradients', 'shrink_gradient',
@@ -27,7 +27,8 @@ __all__ = [
     'mnist_fi_score', 'sdp_objective', 'fi_objective_direct', 'greedy_fi_direct',
     'fi_objective_dual', 'greedy_fi_dual_bruteforce', 'greedy_fi_rank1',
     'last_layers_kernel', 'last_layers_dim', 'weighted_gram', 'fi_objective_from_gram',
-    'sample_query_dstr', 'append_zero',
+    'sample_query_dstr', 'append_zero', 'last_layers_factors', 'greedy_fi_replay', 'query_fi_single',
+    'query_fi_multimg',
 ]
 
 
@@ -481,3 +482,105 @@ def append_zero(A):
     d = A.shape[0]
     A = np.insert(A, d, 0, axis=1)
     return np.insert(A, d, 0, axis=0)
+
+
+# --------------------------------------------------------------------------
+# the adopted FI query (FI section): reference pipeline shape
+# (pre-filter to B, conditional FIs of the B candidates, pick k) with the
+# factored last-layer FI and the deterministic greedy selection
+# --------------------------------------------------------------------------
+def last_layers_factors(layers, weights, x):
+    """Factors of the last two FC layers for a batch ``x`` [N,H,W,C]: P(class 1) [N],
+    U [d,N] (input of the last FC = model.feature_layer for PW1, NN.py:1346),
+    A_prev [d_prev,N] (input of the FC before it) and W_last [c,d]."""
+    fwd = forward(layers, weights, x, keep_acts=True)
+    acts = fwd['acts']
+    return (fwd['posteriors'][1], acts[-1]['in'], acts[-2]['in'],
+            weights[layers[-1][0]][0].astype(np.float64))
+
+
+def greedy_fi_replay(Kt, D, delta, S):
+    """Replays a given selection sequence ``S`` through the greedy criterion of
+    ``greedy_fi_rank1``: for every step returns (loss of S[t], best available loss,
+    objective after taking S[t]).  Used to accept selections that differ from the
+    oracle's only at ties within tolerance."""
+    n = Kt.shape[0]
+    diag = np.diag(Kt).copy()
+    avail = np.ones(n, dtype=bool)
+    out = []
+    for t in range(len(S)):
+        alpha = (t + 1) * delta
+        prev = list(S[:t])
+        if t == 0:
+            r, e, trC = diag.copy(), np.zeros(n), 0.
+        else:
+            C = np.linalg.inv(alpha * np.eye(t) + Kt[np.ix_(prev, prev)])
+            kjs = Kt[:, prev]
+            Y = kjs @ C
+            r = diag - np.sum(Y * kjs, axis=1)
+            e = np.sum(Y * Y, axis=1)
+            trC = np.trace(C)
+        loss = (1. + e) / (alpha + r)
+        loss[~avail] = np.inf
+        j = int(S[t])
+        assert avail[j], 'selection repeats a candidate'
+        s = t + 1
+        obj = (D - s) / delta + s * (trC + loss[j])
+        out.append((loss[j], loss.min(), obj))
+        avail[j] = False
+    return np.array(out)
+
+
+def _fi_select(p1, U, A_prev, W_last, k, n_layers, delta):
+    two = n_layers == 2
+    Kt = last_layers_kernel(p1, U, A_prev if two else None, W_last if two else None)
+    D = last_layers_dim(2, U.shape[0], A_prev.shape[0] if two else None)
+    S, obj = greedy_fi_rank1(Kt, D, delta, k)
+    return S, obj, Kt, D
+
+
+def query_fi_single(layers, weights, padded_imgs, pool_inds, patch_shape, ntb, stats, k, B,
+                    n_layers=2, delta=1e-5):
+    """PW_NNAL.CNN_query 'fi' (PW_NNAL.py:89-163) with the adopted selection:
+    posteriors -> uncertainty pre-filter to B (:108-115) -> re-gather + normalise the B
+    patches (:122-130) -> factored FIs -> greedy k.  Returns (positions into
+    ``pool_inds`` in selection order, objective per step, details)."""
+    pool_inds = np.asarray(pool_inds)
+    posts = batch_eval(layers, weights, padded_imgs, pool_inds, patch_shape, ntb, stats, 'posteriors')[0]
+    if B < len(pool_inds):
+        sel = stable_topk(np.abs(posts - .5), B)
+    else:
+        sel = np.arange(len(pool_inds))
+    x = normalize_batch_eval(get_patches(padded_imgs, pool_inds[sel], patch_shape), stats).astype(np.float32)
+    p1, U, A_prev, W_last = last_layers_factors(layers, weights, x)
+    S, obj, Kt, D = _fi_select(p1, U, A_prev, W_last, k, n_layers, delta)
+    return sel[S], obj, {'sel': sel, 'Kt': Kt, 'D': D, 'p1': p1, 'U': U, 'A_prev': A_prev, 'W_last': W_last,
+                         'posts': posts, 'S': S}
+
+
+def query_fi_multimg(layers, weights, all_padded_imgs, pool_inds, patch_shape, ntb, train_stats, k, B,
+                     n_layers=2, delta=1e-3):
+    """PW_NNAL.query_multimg 'fi' (PW_NNAL.py:547-627) with the adopted selection;
+    candidate order subject-major as the reference's ``A +=`` loop (:566-578).
+    Returns (list of per-subject local positions, objective per step, details)."""
+    from .nnal_oracle import bin_uncertainty_filter_multimg, global2local_inds
+    s = len(pool_inds)
+    m = len(all_padded_imgs[0]) - 1
+    sel_inds, sel_posts = bin_uncertainty_filter_multimg(layers, weights, all_padded_imgs, pool_inds,
+                                                         patch_shape, ntb, train_stats, B)
+    P, Us, As = [], [], []
+    W_last = None
+    for i in range(s):
+        if len(sel_inds[i]) == 0:
+            continue
+        stats = [[train_stats[i, 2 * j], train_stats[i, 2 * j + 1]] for j in range(m)]
+        vox = np.asarray(pool_inds[i])[sel_inds[i]]
+        x = normalize_batch_eval(get_patches(all_padded_imgs[i][:m], vox, patch_shape), stats).astype(np.float32)
+        p1, U, A_prev, W_last = last_layers_factors(layers, weights, x)
+        P.append(p1); Us.append(U); As.append(A_prev)
+    p1, U, A_prev = np.concatenate(P), np.concatenate(Us, axis=1), np.concatenate(As, axis=1)
+    S, obj, Kt, D = _fi_select(p1, U, A_prev, W_last, k, n_layers, delta)
+    sizes = [len(sel_inds[i]) for i in range(s)]
+    local = global2local_inds(S, sizes)
+    Q = [np.array(sel_inds[i])[local[i]] for i in range(s)]
+    return Q, obj, {'Kt': Kt, 'D': D, 'S': S, 'sel_inds': sel_inds}

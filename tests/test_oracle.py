@@ -243,3 +243,27 @@ def test_gen_A_matrices_rank_one_identity():
         assert np.allclose(A[i] - 1e-3 * np.eye(3), p[i] * (1 - p[i]) * np.outer(gbar[i], gbar[i]))
     assert np.allclose(A[1] - 1e-3 * np.eye(3), np.outer(g0[1], g0[1]))     # clamped p=0
     assert np.allclose(A[2] - 1e-3 * np.eye(3), np.outer(g1[2], g1[2]))     # clamped p=1
+
+
+def test_greedy_replay_matches_rank1():
+    """greedy_fi_replay (the tolerance-aware checker used by the GPU tests) follows greedy_fi_rank1."""
+    rs = np.random.RandomState(3)
+    n, d, dp = 60, 12, 10
+    U = np.maximum(rs.randn(d, n), 0)
+    A = np.maximum(rs.randn(dp, n), 0)
+    Wl = rs.randn(2, d)
+    p1 = rs.rand(n)
+    for two in (False, True):
+        Kt = O.last_layers_kernel(p1, U, A if two else None, Wl if two else None)
+        D = O.last_layers_dim(2, d, dp if two else None)
+        S, obj = O.greedy_fi_rank1(Kt, D, 1e-3, 15)
+        rep = O.greedy_fi_replay(Kt, D, 1e-3, S)
+        assert np.allclose(rep[:, 0], rep[:, 1], rtol=1e-12)
+        assert np.allclose(rep[:, 2], obj, rtol=1e-9)
+        # definition: f(S) through explicit conditional FIs
+        G = np.concatenate([np.kron(np.array([1., -1.])[:, None], np.concatenate([U, np.ones((1, n))])),
+                            ] + ([np.stack([np.kron((Wl.T @ np.array([1., -1.])) * (U[:, i] > 0),
+                                                    np.append(A[:, i], 1.)) for i in range(n)], axis=1)] if two else []),
+                           axis=0) * np.sqrt(p1 * (1 - p1))[None, :]
+        Abar = [np.outer(G[:, i], G[:, i]) for i in range(n)]
+        assert np.isclose(O.fi_objective_direct(Abar, list(S[:6]), 1e-3), obj[5], rtol=1e-8)
