@@ -258,6 +258,11 @@ def run_ours(args, rank, world):
         dev_ms = float(tms.item())
     value = pool_total * args.steps / (dev_ms * 1e-3)
 
+    # ---------------- FI round (extra keys; the headline workload stays the entropy round) ----------------
+    fi = None
+    if args.fi_B > 0:
+        fi = run_fi_round(args, eng, model, padded, stats, pool, lo, hi, d_inds, st, k, peaks, barrier, rank, world)
+
     # ---------------- end-to-end leg through the reference-facing API ----------------
     expr = Expr()
     expr.pars = dict(k=k, B=k, lambda_=0., patch_shape=PATCH, ntb=10000, stats=stats)
@@ -325,8 +330,76 @@ def run_ours(args, rank, world):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': 1e3 * e2e_s / args.steps,
                     'api': 'nnal_b200.PW_NNAL.CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, "entropy")'},
-            'roofline': roofline, 'stage_ms_per_step': stage_ms, 'cpu_baseline': cpu}
+            'roofline': roofline, 'stage_ms_per_step': stage_ms, 'cpu_baseline': cpu, 'fi_round': fi}
     print(json.dumps(line))
+
+
+def run_fi_round(args, eng, model, padded, stats, pool, lo, hi, d_inds, st, k, peaks, barrier, rank, world):
+    """One FI query round on the same pool (reference pipeline shape, PW_NNAL.py:89-163): pool pass ->
+    uncertainty pre-filter to B -> second pass over the B candidates keeping the factors of the last two FC
+    layers -> greedy k.  Also times the weighted Gram of the candidates (tensor cores).  Device timing per stage."""
+    import torch
+    import nnal_b200
+    from nnal_b200 import _lib as L
+    from nnal_b200 import dist, fi as fimod
+    n_local = hi - lo
+    B = min(args.fi_B, len(pool))
+    delta = 1e-5
+    stream = torch.cuda.ExternalStream(eng.stream)
+
+    def fi_step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record(stream)
+        eng.pool_begin(n_local, 0)
+        eng.pool_eval_device(0, d_inds.data_ptr(), n_local, 0, PATCH, st)
+        eng.pool_score(L.SCORE_BINARY)
+        idx, sc = eng.pool_topk(B, with_scores=True)
+        sel, _ = dist.allgather_topk(sc, idx + lo, B)
+        ev[1].record(stream)
+        own = (sel >= lo) & (sel < hi)
+        mine = sel[own]
+        eng.pool_begin(len(mine), 2)
+        if len(mine):
+            eng.pool_eval(0, pool[mine], 0, PATCH, st, shape=padded[0].shape)
+        eng.fi_set_candidates(None, 2)
+        ev[2].record(stream)
+        chosen, obj = fimod.greedy_select(eng, k, delta, np.nonzero(own)[0].astype(np.int64))
+        ev[3].record(stream)
+        eng.fi_gram(None, read=False)
+        ev[4].record(stream)
+        ev[4].synchronize()
+        return [ev[i].elapsed_time(ev[i + 1]) for i in range(4)], sel[chosen], obj, len(mine)
+
+    for _ in range(max(1, args.warmup // 2)):
+        fi_step()
+    barrier()
+    eng.profile(True)
+    acc = np.zeros(4)
+    steps = max(1, min(args.steps, 3))
+    for _ in range(steps):
+        t, q, obj, n_mine = fi_step()
+        acc += np.array(t)
+    gram_ms, gram_n = eng.profile_read(111)
+    eng.profile(False)
+    acc /= steps
+    d = eng.fi_info()['d']
+    gram_flops = 2.0 * n_mine * (d + 1) ** 2
+    gram_ms_per = gram_ms / max(1, steps)
+    if world > 1:
+        tm = torch.tensor(list(acc), dtype=torch.float64, device='cuda')
+        torch.distributed.all_reduce(tm, op=torch.distributed.ReduceOp.MAX)
+        acc = tm.cpu().numpy()
+    total = float(acc[:3].sum())
+    return {'B': int(B), 'k': int(k), 'fi_layers': 2, 'delta': delta,
+            'ms_per_round': total, 'samples_per_s': len(pool) / (total * 1e-3),
+            'stage_ms': {'pool_pass+prefilter': float(acc[0]), 'candidate_pass+factors': float(acc[1]),
+                         'greedy': float(acc[2]), 'gram(extra)': float(acc[3])},
+            'greedy_us_per_step': 1e3 * float(acc[2]) / max(1, k),
+            'gram': {'candidates_this_rank': int(n_mine), 'ms': gram_ms_per,
+                     'tflops_algorithmic': gram_flops / max(gram_ms_per, 1e-9) / 1e9,
+                     'frac_of_bf16_peak': gram_flops / max(gram_ms_per, 1e-9) / 1e9 / peaks['bf16_sustained'],
+                     'note': 'full symmetric (d+1)^2 output, fp16 hi/lo split: 3 MMAs per product'},
+            'objective_final': float(obj[-1]) if len(obj) else None}
 
 
 def main():
@@ -338,6 +411,7 @@ def main():
     ap.add_argument('--pool', type=int, default=100000, help='pool samples per GPU')
     ap.add_argument('--cpu-sample', type=int, default=5000)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--fi-B', type=int, default=10000, help='FI pre-filter size of the extra FI round (0: skip)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
