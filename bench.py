@@ -358,10 +358,20 @@ def run_fi_round(args, eng, model, padded, stats, pool, lo, hi, d_inds, st, k, p
         ev[1].record(stream)
         own = (sel >= lo) & (sel < hi)
         mine = sel[own]
+        dbg = os.environ.get('NNAL_BENCH_DEBUG')
+        t0 = time.perf_counter()
         eng.pool_begin(len(mine), 2)
+        t1 = time.perf_counter()
         if len(mine):
             eng.pool_eval(0, pool[mine], 0, PATCH, st, shape=padded[0].shape)
+        if dbg:
+            eng.synchronize()
+        t2 = time.perf_counter()
         eng.fi_set_candidates(None, 2)
+        t3 = time.perf_counter()
+        if dbg:
+            sys.stderr.write('fi candidate pass: pool_begin %.2f ms, pool_eval %.2f ms, set_candidates %.2f ms\n'
+                             % (1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)))
         ev[2].record(stream)
         chosen, obj = fimod.greedy_select(eng, k, delta, np.nonzero(own)[0].astype(np.int64))
         ev[3].record(stream)

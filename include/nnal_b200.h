@@ -164,11 +164,12 @@ int nnal_fi_greedy(nnal_ctx* ctx, int64_t k, double delta, int64_t* sel_out, dou
 /* Multi-GPU greedy, one step split so that the host layer can combine ranks (NCCL): nnal_fi_begin once;
  * per step (1) local best candidate: loss, local candidate index (-1 if none) and tr C of the shared
  * winners' system (objective after the step = (D-s)/delta + s (trC + global loss), s = step+1);
- * (2) the owner exports its winner's factors [u (d) | a (d_prev) | sqrt(w) as one double];
- * (3) every rank applies the global winner. */
+ * (2) the owner exports its winner's message [u (d) | a (d_prev) | sqrt(w) as one double | row `step` of the
+ * winners' kernel K_SS as step+1 doubles]; (3) every rank applies the global winner. */
 int nnal_fi_begin(nnal_ctx* ctx, int64_t k, double delta);
 int nnal_fi_step_local_best(nnal_ctx* ctx, int64_t step, double* loss_out, int64_t* cand_out, double* trC_out);
-int nnal_fi_winner_factors(nnal_ctx* ctx, int64_t cand, float* factors_out /*NULL: size query*/, int64_t* n_floats);
+int nnal_fi_winner_factors(nnal_ctx* ctx, int64_t step, int64_t cand, float* factors_out /*NULL: size query*/,
+                           int64_t* n_floats);
 int nnal_fi_step_apply(nnal_ctx* ctx, int64_t step, const float* winner_factors, int64_t n_floats, int owner_is_local,
                        int64_t cand_local);
 

@@ -51,7 +51,7 @@ static void free_pool(nnal_ctx* ctx) {
   if (ctx->pool_feat) cudaFree(ctx->pool_feat);
   if (ctx->pool_prev) cudaFree(ctx->pool_prev);
   ctx->pool_post = nullptr; ctx->pool_score = nullptr; ctx->pool_feat = nullptr; ctx->pool_prev = nullptr;
-  ctx->pool_n = 0; ctx->pool_cap_n = 0; ctx->pool_cap_keep = -1;
+  ctx->pool_n = 0; ctx->pool_cap_n = 0; ctx->pool_cap_score = 0; ctx->pool_cap_nfeat = 0; ctx->pool_cap_nprev = 0;
 }
 
 extern "C" int nnal_volume_clear(nnal_ctx* ctx) {
@@ -322,23 +322,27 @@ extern "C" int nnal_pool_begin(nnal_ctx* ctx, int64_t n_total, int keep) {
     if (L.type != NNAL_LAYER_POOL && !L.has_weights) NNAL_FAIL(ctx, NNAL_ERR_STATE, "weights not set for every layer");
   if (keep > 0 && ctx->feat_dim == 0) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "feature layer must be an fc layer before the last");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  size_t n = (size_t)std::max<int64_t>(n_total, 1);
-  if (ctx->pool_post && ctx->pool_cap_n >= n && ctx->pool_cap_keep >= keep && ctx->pool_cap_class == ctx->n_class &&
-      ctx->pool_cap_feat == ctx->feat_dim && ctx->pool_cap_prev == ctx->prev_dim) {
-    ctx->pool_n = n_total;                     // re-use the arrays of the previous round
-    ctx->keep = keep;
-    return NNAL_OK;
+  // Every pool array has its own grow-only capacity, so alternating rounds of different shape (a large
+  // posterior-only pass, then a small candidate pass that keeps the FC factors) never re-allocate.
+  const size_t n = (size_t)std::max<int64_t>(n_total, 1);
+  if (ctx->pool_cap_class != ctx->n_class || ctx->pool_cap_feat != ctx->feat_dim || ctx->pool_cap_prev != ctx->prev_dim) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    free_pool(ctx);
+    ctx->pool_cap_class = ctx->n_class; ctx->pool_cap_feat = ctx->feat_dim; ctx->pool_cap_prev = ctx->prev_dim;
   }
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  free_pool(ctx);
+  auto grow = [&](void** p, size_t& cap, size_t elem_bytes) -> int {
+    if (*p && cap >= n) return NNAL_OK;
+    if (*p) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CUDA_TRY(ctx, cudaFree(*p)); *p = nullptr; cap = 0; }
+    CUDA_TRY(ctx, cudaMalloc(p, n * elem_bytes));
+    cap = n;
+    return NNAL_OK;
+  };
+  NNAL_TRY(grow((void**)&ctx->pool_post, ctx->pool_cap_n, (size_t)ctx->n_class * sizeof(float)));
+  NNAL_TRY(grow((void**)&ctx->pool_score, ctx->pool_cap_score, sizeof(double)));
+  if (keep >= 1) NNAL_TRY(grow((void**)&ctx->pool_feat, ctx->pool_cap_nfeat, (size_t)ctx->feat_dim * sizeof(float)));
+  if (keep >= 2) NNAL_TRY(grow((void**)&ctx->pool_prev, ctx->pool_cap_nprev, (size_t)ctx->prev_dim * sizeof(float)));
   ctx->pool_n = n_total;
   ctx->keep = keep;
-  CUDA_TRY(ctx, cudaMalloc(&ctx->pool_post, n * ctx->n_class * sizeof(float)));
-  CUDA_TRY(ctx, cudaMalloc(&ctx->pool_score, n * sizeof(double)));
-  if (keep >= 1) CUDA_TRY(ctx, cudaMalloc(&ctx->pool_feat, n * ctx->feat_dim * sizeof(float)));
-  if (keep >= 2) CUDA_TRY(ctx, cudaMalloc(&ctx->pool_prev, n * ctx->prev_dim * sizeof(float)));
-  ctx->pool_cap_n = n; ctx->pool_cap_keep = keep; ctx->pool_cap_class = ctx->n_class;
-  ctx->pool_cap_feat = ctx->feat_dim; ctx->pool_cap_prev = ctx->prev_dim;
   return NNAL_OK;
 }
 
@@ -439,7 +443,7 @@ __global__ void transpose_feat_kernel(const float* __restrict__ in, float* __res
 
 extern "C" int nnal_pool_features(nnal_ctx* ctx, int64_t start, int64_t n, float* out) {
   if (!ctx || !out) return NNAL_ERR_INVALID;
-  if (!ctx->pool_feat) NNAL_FAIL(ctx, NNAL_ERR_STATE, "pool pass did not keep features");
+  if (!ctx->pool_feat || ctx->keep < 1) NNAL_FAIL(ctx, NNAL_ERR_STATE, "pool pass did not keep features");
   if (start < 0 || n < 0 || start + n > ctx->pool_n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "feature range out of bounds");
   if (n == 0) return NNAL_OK;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));

@@ -93,50 +93,77 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // The three inner products of a (candidate, winner) pair, float64 accumulation of exact float32 products in
-// a FIXED order (lane-strided, then butterfly), so that every kernel that needs <gbar_i, gbar_j> gets the
-// same bits:  uu = u.x,  aa = a.y,  mm = sum_k beta2_k 1[u_k > 0] 1[x_k > 0].
-__device__ __forceinline__ void pair_dots(const float* __restrict__ u, const float* __restrict__ a,
-                                          const float* __restrict__ x, const float* __restrict__ y,
-                                          const float* __restrict__ beta2, int d, int dp, int nl, int lane, double& uu,
-                                          double& aa, double& mm) {
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+// a FIXED order (four independent chains per lane, lane-strided, then butterfly):
+//   uu = u.x,  aa = a.y,  mm = sum_k beta2_k 1[u_k > 0] 1[x_k > 0].
+// Inner products of float32 factor rows.  Every lane multiplies-and-adds SHORT float32 chains (four
+// independent chains of four FMAs: the product inside an FMA is exact, one rounding per add) and flushes
+// them into float64 sums, which are then reduced in float64: the result carries ~1e-8 relative error
+// (16-term float32 partials, random signs, averaged over d/16 partials) at one FMA per element -- a
+// cvt+DFMA loop is bound by the quarter-rate float32->float64 conversions, a compensated float32 dot
+// product by its 10 flops per element; this one stays on the HBM roofline.
+// Fixed order (lane-strided, then butterfly) => bit-reproducible.
+//   uu = u.x,  aa = a.y,  mm = sum_k beta2_k 1[u_k > 0] 1[x_k > 0]
+__device__ __forceinline__ void dot_um(const float* __restrict__ u, const float* __restrict__ x,
+                                       const float* __restrict__ beta2, int d, bool mask, int lane, double& uu, double& mm) {
+  double su = 0.0, sm = 0.0;
   if ((d & 3) == 0) {
-    for (int k = lane * 4; k < d; k += 128) {
+    int k = lane * 4;
+    for (; k + 3 * 128 < d; k += 4 * 128) {
+      float4 p[4], q[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        p[i] = *reinterpret_cast<const float4*>(u + k + i * 128);
+        q[i] = *reinterpret_cast<const float4*>(x + k + i * 128);
+      }
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f0 = fmaf(p[i].x, q[i].x, f0);
+        f1 = fmaf(p[i].y, q[i].y, f1);
+        f2 = fmaf(p[i].z, q[i].z, f2);
+        f3 = fmaf(p[i].w, q[i].w, f3);
+      }
+      su += ((double)f0 + (double)f1) + ((double)f2 + (double)f3);
+      if (mask) {
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(beta2 + k + i * 128));
+          g0 += (p[i].x > 0.f && q[i].x > 0.f) ? b.x : 0.f;
+          g1 += (p[i].y > 0.f && q[i].y > 0.f) ? b.y : 0.f;
+          g2 += (p[i].z > 0.f && q[i].z > 0.f) ? b.z : 0.f;
+          g3 += (p[i].w > 0.f && q[i].w > 0.f) ? b.w : 0.f;
+        }
+        sm += ((double)g0 + (double)g1) + ((double)g2 + (double)g3);
+      }
+    }
+    for (; k < d; k += 128) {
       const float4 p = *reinterpret_cast<const float4*>(u + k);
       const float4 q = *reinterpret_cast<const float4*>(x + k);
-      s0 = fma((double)p.x, (double)q.x, s0);
-      s0 = fma((double)p.y, (double)q.y, s0);
-      s0 = fma((double)p.z, (double)q.z, s0);
-      s0 = fma((double)p.w, (double)q.w, s0);
-      if (nl == 2) {
+      su += ((double)(p.x * q.x) + (double)(p.y * q.y)) + ((double)(p.z * q.z) + (double)(p.w * q.w));   // not reached for d % 512 == 0
+      if (mask) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(beta2 + k));
-        if (p.x > 0.f && q.x > 0.f) s2 += (double)b.x;
-        if (p.y > 0.f && q.y > 0.f) s2 += (double)b.y;
-        if (p.z > 0.f && q.z > 0.f) s2 += (double)b.z;
-        if (p.w > 0.f && q.w > 0.f) s2 += (double)b.w;
+        sm += (double)((p.x > 0.f && q.x > 0.f) ? b.x : 0.f) + (double)((p.y > 0.f && q.y > 0.f) ? b.y : 0.f) +
+              (double)((p.z > 0.f && q.z > 0.f) ? b.z : 0.f) + (double)((p.w > 0.f && q.w > 0.f) ? b.w : 0.f);
       }
     }
   } else {
     for (int k = lane; k < d; k += 32) {
-      const float p = u[k], q = x[k];
-      s0 = fma((double)p, (double)q, s0);
-      if (nl == 2 && p > 0.f && q > 0.f) s2 += (double)__ldg(beta2 + k);
+      su = fma((double)u[k], (double)x[k], su);
+      if (mask && u[k] > 0.f && x[k] > 0.f) sm += (double)__ldg(beta2 + k);
     }
   }
-  if (nl == 2) {
-    if ((dp & 3) == 0) {
-      for (int k = lane * 4; k < dp; k += 128) {
-        const float4 p = *reinterpret_cast<const float4*>(a + k);
-        const float4 q = *reinterpret_cast<const float4*>(y + k);
-        s1 = fma((double)p.x, (double)q.x, s1);
-        s1 = fma((double)p.y, (double)q.y, s1);
-        s1 = fma((double)p.z, (double)q.z, s1);
-        s1 = fma((double)p.w, (double)q.w, s1);
-      }
-    } else {
-      for (int k = lane; k < dp; k += 32) s1 = fma((double)a[k], (double)y[k], s1);
-    }
-  }
+  uu = su;
+  mm = sm;
+}
+
+__device__ __forceinline__ void pair_dots(const float* __restrict__ u, const float* __restrict__ a,
+                                          const float* __restrict__ x, const float* __restrict__ y,
+                                          const float* __restrict__ beta2, int d, int dp, int nl, int lane, double& uu,
+                                          double& aa, double& mm) {
+  double s0, s1 = 0.0, s2, dummy;
+  dot_um(u, x, beta2, d, nl == 2, lane, s0, s2);
+  if (nl == 2) dot_um(a, y, nullptr, dp, false, lane, s1, dummy);
   uu = warp_sum(s0);
   aa = warp_sum(s1);
   mm = warp_sum(s2);
@@ -203,37 +230,108 @@ __global__ void __launch_bounds__(256) column_kernel(const float* __restrict__ U
   }
 }
 
-// row/column t of the winners' kernel K_SS (from the stored winner factors: identical on every rank)
-__global__ void __launch_bounds__(256) kss_row_kernel(const float* __restrict__ win_u, const float* __restrict__ win_a,
-                                                       const double* __restrict__ win_sw, const float* __restrict__ beta2,
-                                                       int t, int d, int dp, int nl, int64_t ld, double* __restrict__ kss) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int a = warp; a <= t; a += nwarps) {
-    double uu, aa, mm;
-    pair_dots(win_u + (int64_t)a * d, win_a ? win_a + (int64_t)a * dp : nullptr, win_u + (int64_t)t * d,
-              win_a ? win_a + (int64_t)t * dp : nullptr, beta2, d, dp, nl, lane, uu, aa, mm);
-    if (lane == 0) {
-      const double v = win_sw[a] * win_sw[t] * pair_kernel(uu, aa, mm, nl);
-      kss[(int64_t)t * ld + a] = v;
-      kss[(int64_t)a * ld + t] = v;
-    }
-  }
-}
-
-// copies the factors of local candidate *idx_ptr into winner slot t
+// Step-t winner = local candidate *idx_ptr: copies its factors into the winner slot and extends the winners'
+// kernel K_SS by row/column t, read back from the kernel columns already computed:
+//   K_SS[t][a] = kcols[a][winner] (a < t),  K_SS[t][t] = Kt_winner,winner.
 __global__ void copy_winner_kernel(const float* __restrict__ U, const float* __restrict__ A, const int64_t* __restrict__ rows,
-                                   const double* __restrict__ sw, const long long* __restrict__ idx_ptr, int t, int d, int dp,
-                                   float* __restrict__ win_u, float* __restrict__ win_a, double* __restrict__ win_sw) {
+                                   const double* __restrict__ sw, const double* __restrict__ diag,
+                                   const double* __restrict__ kcols, int64_t kn, const long long* __restrict__ idx_ptr, int t,
+                                   int d, int dp, float* __restrict__ win_u, float* __restrict__ win_a,
+                                   double* __restrict__ win_sw, double* __restrict__ kss, int64_t kss_ld) {
   const long long i = *idx_ptr;
   if (i < 0) return;
   const int64_t r = rows ? rows[i] : i;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-  for (int k = tid; k < d; k += nt) win_u[(int64_t)t * d + k] = U[r * d + k];
+  for (int k = tid; k < d; k += nt) win_u[k] = U[r * d + k];
   if (A)
-    for (int k = tid; k < dp; k += nt) win_a[(int64_t)t * dp + k] = A[r * dp + k];
-  if (tid == 0) win_sw[t] = sw[i];
+    for (int k = tid; k < dp; k += nt) win_a[k] = A[r * dp + k];
+  for (int a = tid; a <= t; a += nt) {
+    const double v = a < t ? kcols[(int64_t)a * kn + i] : diag[i];
+    kss[(int64_t)t * kss_ld + a] = v;
+    kss[(int64_t)a * kss_ld + t] = v;
+  }
+  if (tid == 0) *win_sw = sw[i];
+}
+
+// Register-tiled Gauss-Jordan for t <= 32 RT: 1024 threads as a 32 x 32 grid, thread (ty,tx) owns the RT x RT
+// elements M[ty+32a][tx+32b]; per pivot the owners publish row p and column p through (double-buffered) shared
+// memory: one barrier per pivot.  Writes C (row stride ldc, zero padded) and tr C.
+template <int RT>
+__global__ void __launch_bounds__(1024) invert_reg_kernel(const double* __restrict__ kss, int64_t kss_ld, int t, double alpha,
+                                                           double* __restrict__ Cout, int ldc, DevScalars* sc) {
+  __shared__ double rowp[2][32 * RT], colp[2][32 * RT];
+  __shared__ double red[32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  double m[RT][RT];
+#pragma unroll
+  for (int a = 0; a < RT; ++a)
+#pragma unroll
+    for (int b = 0; b < RT; ++b) {
+      const int i = ty + 32 * a, j = tx + 32 * b;
+      m[a][b] = (i < t && j < t) ? kss[(int64_t)i * kss_ld + j] + (i == j ? alpha : 0.0) : (i == j ? 1.0 : 0.0);
+    }
+  // In-place Gauss-Jordan written so that the per-pivot update is ONE uniform FMA per element:
+  //   new M[i][j] = M'[i][j] - c[i] r[j],  r = (row p with M[p][p] := 1) / pivot,
+  //   c[i] = M[i][p] for i != p and -1 for i = p,  M' = M with row p and column p zeroed.
+  // (pq is warp-uniform, so the register-array row/column is picked by uniform branches, not selects.)
+  for (int p = 0; p < t; ++p) {
+    const int buf = p & 1, pr = p & 31, pq = p >> 5;
+    if (ty == pr) {                          // warp `pr` holds row p: pivot by shuffle, publish the scaled row, zero it
+      double rv[RT];
+#pragma unroll
+      for (int a = 0; a < RT; ++a)
+        if (a == pq) {
+#pragma unroll
+          for (int b = 0; b < RT; ++b) { rv[b] = m[a][b]; m[a][b] = 0.0; }
+        }
+      double piv = 0.0;
+#pragma unroll
+      for (int b = 0; b < RT; ++b)
+        if (b == pq) piv = __shfl_sync(0xffffffffu, rv[b], pr);
+      const double inv = 1.0 / piv;
+#pragma unroll
+      for (int b = 0; b < RT; ++b) rowp[buf][tx + 32 * b] = ((tx + 32 * b) == p ? 1.0 : rv[b]) * inv;
+    }
+    if (tx == pr) {                          // lane `pr` of every warp holds column p: publish it, zero it
+#pragma unroll
+      for (int b = 0; b < RT; ++b)
+        if (b == pq) {
+#pragma unroll
+          for (int a = 0; a < RT; ++a) {
+            const int i = ty + 32 * a;
+            colp[buf][i] = (i == p) ? -1.0 : m[a][b];     // (row p was zeroed above; its entry is replaced by -1)
+            m[a][b] = 0.0;
+          }
+        }
+    }
+    __syncthreads();
+    double nr[RT], cc[RT];
+#pragma unroll
+    for (int b = 0; b < RT; ++b) nr[b] = rowp[buf][tx + 32 * b];
+#pragma unroll
+    for (int a = 0; a < RT; ++a) cc[a] = colp[buf][ty + 32 * a];
+#pragma unroll
+    for (int a = 0; a < RT; ++a)
+#pragma unroll
+      for (int b = 0; b < RT; ++b) m[a][b] = fma(-cc[a], nr[b], m[a][b]);
+  }
+  double tr = 0.0;
+#pragma unroll
+  for (int a = 0; a < RT; ++a)
+#pragma unroll
+    for (int b = 0; b < RT; ++b) {
+      const int i = ty + 32 * a, j = tx + 32 * b;
+      if (i < t && j < ldc) Cout[(size_t)i * ldc + j] = j < t ? m[a][b] : 0.0;
+      if (i == j && i < t) tr += m[a][b];
+    }
+  tr = warp_sum(tr);
+  if (tx == 0) red[ty] = tr;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sacc = 0.0;
+    for (int q = 0; q < 32; ++q) sacc += red[q];
+    sc->trC = sacc;
+  }
 }
 
 // C = (alpha I + K_SS[0:t,0:t])^-1 by in-place Gauss-Jordan (SPD: no pivoting), one CTA, float64.
@@ -284,32 +382,58 @@ __global__ void __launch_bounds__(1024) invert_kernel(const double* __restrict__
   }
 }
 
+constexpr int EVAL_CAND = 32, EVAL_SUB = 8;      // candidates per CTA (= lanes), y-slices per candidate (= warps)
 // Candidate evaluation at step t (|S| = t, alpha = (t+1) delta, C = (alpha I + K_SS)^-1):
 //   y = C k_j,  r_j = Kt_jj - k_j.y,  e_j = |y|^2,  loss_j = (1 + e_j)/(alpha + r_j)    (f(S+j) = const + (t+1) loss_j)
 // followed by a block-level arg-min (ties: lowest candidate index).
-template <bool SMEM_C>
-__global__ void __launch_bounds__(128) eval_kernel(const double* __restrict__ kcols, int64_t kn, const double* __restrict__ diag,
+// Mapping: lane = candidate, warp w computes the slices a0 = 8w, 8(w+8), ... of y.  All lanes of a warp read
+// the SAME C elements (shared-memory broadcast: one wavefront per 16 bytes) and consecutive k values.
+// MODE 2: C and the CTA's 32 x t slice of the kernel columns staged in shared memory (t <= 128);
+// MODE 1: C in shared memory; MODE 0: everything from global memory (large t).
+template <int MODE>
+__global__ void __launch_bounds__(256) eval_kernel(const double* __restrict__ kcols, int64_t kn, const double* __restrict__ diag,
                                                     const unsigned char* __restrict__ avail, const double* __restrict__ Cg, int t,
                                                     int ldc, int64_t n, double alpha, double* __restrict__ blk_loss,
                                                     long long* __restrict__ blk_idx) {
   extern __shared__ double sm_d[];
+  __shared__ double part_r[EVAL_SUB][EVAL_CAND], part_e[EVAL_SUB][EVAL_CAND];
   const double* Cs = Cg;
-  if (SMEM_C) {
-    for (int e = threadIdx.x; e < t * ldc; e += blockDim.x) sm_d[e] = Cg[e];
-    __syncthreads();
+  const double* Kb = kcols;                 // element (b, candidate) at Kb[b * kstride + kj]
+  int64_t kstride = kn;
+  const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+  const int64_t j = (int64_t)blockIdx.x * EVAL_CAND + lane;
+  int64_t kj = j;
+  if (MODE >= 1) {
+    const double2* src = reinterpret_cast<const double2*>(Cg);
+    double2* dst = reinterpret_cast<double2*>(sm_d);
+#pragma unroll 8
+    for (int e = threadIdx.x; e < t * ldc / 2; e += 256) dst[e] = src[e];
     Cs = sm_d;
   }
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  double loss = INFINITY;
-  if (j < n && avail[j]) {
-    double r = diag[j], e = 0.0;
-    for (int a0 = 0; a0 < t; a0 += 8) {
+  if (MODE == 2) {
+    double* Ks = sm_d + (size_t)t * ldc;
+    const int64_t j0 = (int64_t)blockIdx.x * EVAL_CAND;
+#pragma unroll 8
+    for (int e = threadIdx.x; e < t * EVAL_CAND; e += 256) {
+      const int b = e / EVAL_CAND, c = e % EVAL_CAND;
+      Ks[e] = (j0 + c < n) ? kcols[(int64_t)b * kn + j0 + c] : 0.0;
+    }
+    Kb = Ks;
+    kstride = EVAL_CAND;
+    kj = lane;
+  }
+  if (MODE >= 1) __syncthreads();
+  const bool live = j < n && avail[j];
+  double r = 0.0, e = 0.0;
+  if (live || MODE == 2) {                  // (MODE 2 reads zero-filled shared memory for dead lanes: keeps warps converged)
+    for (int a0 = sub * 8; a0 < t; a0 += 8 * EVAL_SUB) {
       double acc[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+#pragma unroll 4
       for (int b = 0; b < t; ++b) {
-        const double kb = kcols[(int64_t)b * kn + j];
-        const double2* c2 = reinterpret_cast<const double2*>(Cs + (size_t)b * ldc + a0);   // C[b][a0..a0+7] (symmetric)
+        const double kb = Kb[(int64_t)b * kstride + kj];
+        const double2* c2 = reinterpret_cast<const double2*>(Cs + (size_t)b * ldc + a0);   // C[b][a0..a0+7] (C symmetric)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const double2 c = c2[q];
@@ -320,32 +444,32 @@ __global__ void __launch_bounds__(128) eval_kernel(const double* __restrict__ kc
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         if (a0 + q < t) {
-          const double ka = kcols[(int64_t)(a0 + q) * kn + j];
-          r = fma(-ka, acc[q], r);
+          const double ka = Kb[(int64_t)(a0 + q) * kstride + kj];
+          r = fma(ka, acc[q], r);
           e = fma(acc[q], acc[q], e);
         }
       }
     }
-    loss = (1.0 + e) / (alpha + r);
-    if (!(loss == loss)) loss = INFINITY;
   }
-  // block arg-min
-  long long idx = (j < n) ? (long long)j : 0x7fffffffffffffffll;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ol = __shfl_xor_sync(0xffffffffu, loss, o);
-    const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ol < loss || (ol == loss && oi < idx)) { loss = ol; idx = oi; }
-  }
-  __shared__ double wl[4];
-  __shared__ long long wi[4];
-  if ((threadIdx.x & 31) == 0) { wl[threadIdx.x >> 5] = loss; wi[threadIdx.x >> 5] = idx; }
+  part_r[sub][lane] = r;
+  part_e[sub][lane] = e;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int q = 1; q < 4; ++q)
-      if (wl[q] < loss || (wl[q] == loss && wi[q] < idx)) { loss = wl[q]; idx = wi[q]; }
-    blk_loss[blockIdx.x] = loss;
-    blk_idx[blockIdx.x] = idx;
+  if (sub == 0) {
+#pragma unroll
+    for (int w = 1; w < EVAL_SUB; ++w) { r += part_r[w][lane]; e += part_e[w][lane]; }
+    double loss = INFINITY;
+    if (live) {
+      loss = (1.0 + e) / (alpha + (diag[j] - r));
+      if (!(loss == loss)) loss = INFINITY;
+    }
+    long long idx = (j < n) ? (long long)j : 0x7fffffffffffffffll;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ol = __shfl_xor_sync(0xffffffffu, loss, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ol < loss || (ol == loss && oi < idx)) { loss = ol; idx = oi; }
+    }
+    if (lane == 0) { blk_loss[blockIdx.x] = loss; blk_idx[blockIdx.x] = idx; }
   }
 }
 
@@ -505,16 +629,16 @@ static int alloc_greedy(nnal_ctx* ctx, State* s, int64_t k) {
     NNAL_TRY(ensure(ctx, s->C, 0, (size_t)kc * (kc + 8)));
     NNAL_TRY(ensure(ctx, s->inv_ws, 0, (size_t)(kc + 2) * (kc + 2)));
     NNAL_TRY(ensure(ctx, s->red, 0, (size_t)kc));
-    NNAL_TRY(ensure(ctx, s->win_sw, 0, (size_t)kc));
+    NNAL_TRY(ensure(ctx, s->win_sw, 0, (size_t)1));
     NNAL_TRY(ensure(ctx, s->sel, 0, (size_t)kc));
-    NNAL_TRY(ensure(ctx, s->win_u, 0, (size_t)kc * s->d));
-    NNAL_TRY(ensure(ctx, s->win_a, 0, (size_t)kc * std::max(s->dp, 1)));
+    NNAL_TRY(ensure(ctx, s->win_u, 0, (size_t)s->d));
+    NNAL_TRY(ensure(ctx, s->win_a, 0, (size_t)std::max(s->dp, 1)));
     s->kcap = kc;
     s->kcols_n = nn;
     s->win_d = s->d;
     s->win_dp = s->dp;
   }
-  const int nblk = cdiv(std::max<int64_t>(s->n, 1), 128);
+  const int nblk = cdiv(std::max<int64_t>(s->n, 1), EVAL_CAND);
   if (s->blk_cap < nblk) {
     NNAL_TRY(ensure(ctx, s->blk_loss, 0, (size_t)nblk));
     NNAL_TRY(ensure(ctx, s->blk_idx, 0, (size_t)nblk));
@@ -523,12 +647,18 @@ static int alloc_greedy(nnal_ctx* ctx, State* s, int64_t k) {
   return NNAL_OK;
 }
 
-// steps 1-3 of greedy step t: inverse, candidate evaluation, arg-min
-static int step_select(nnal_ctx* ctx, State* s, int t, int commit) {
+// C = ((t+1) delta I + K_SS[0:t,0:t])^-1 and its trace (t >= 1)
+static int run_invert(nnal_ctx* ctx, State* s, int t) {
   const double alpha = (double)(t + 1) * s->delta;
   const int ldc = (t + 7) / 8 * 8;
-  static bool attr_inv = false, attr_eval = false;
-  if (t > 0) {
+  if (t <= 32) {
+    invert_reg_kernel<1><<<1, 1024, 0, ctx->stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->sc);
+  } else if (t <= 64) {
+    invert_reg_kernel<2><<<1, 1024, 0, ctx->stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->sc);
+  } else if (t <= 128) {
+    invert_reg_kernel<4><<<1, 1024, 0, ctx->stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->sc);
+  } else {
+    static bool attr_inv = false;
     const int use_smem = t <= T_SMEM ? 1 : 0;
     const size_t smem = use_smem ? ((size_t)t * (t | 1) + t) * sizeof(double) : 0;
     if (!attr_inv) {
@@ -537,20 +667,34 @@ static int step_select(nnal_ctx* ctx, State* s, int t, int commit) {
       attr_inv = true;
     }
     invert_kernel<<<1, 1024, smem, ctx->stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->inv_ws, use_smem, s->sc);
-    ctx->launches++;
   }
-  const int nblk = cdiv(s->n, 128);
-  if (t <= T_SMEM) {
-    if (!attr_eval) {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((size_t)T_SMEM * ((T_SMEM + 7) / 8 * 8) * sizeof(double))));
-      attr_eval = true;
-    }
-    eval_kernel<true><<<nblk, 128, (size_t)t * ldc * sizeof(double), ctx->stream>>>(s->kcols, s->kcols_n, s->diag, s->avail, s->C, t,
-                                                                                   ldc, s->n, alpha, s->blk_loss, s->blk_idx);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+// steps 1-3 of greedy step t: inverse, candidate evaluation, arg-min
+static int step_select(nnal_ctx* ctx, State* s, int t, int commit) {
+  const double alpha = (double)(t + 1) * s->delta;
+  const int ldc = (t + 7) / 8 * 8;
+  static bool attr_eval = false;
+  if (t > 0) NNAL_TRY(run_invert(ctx, s, t));
+  const int nblk = cdiv(s->n, EVAL_CAND);
+  if (!attr_eval) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(eval_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 * 128 + 128 * EVAL_CAND) * sizeof(double))));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(eval_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)((size_t)T_SMEM * ((T_SMEM + 7) / 8 * 8) * sizeof(double))));
+    attr_eval = true;
+  }
+  if (t <= 128) {
+    eval_kernel<2><<<nblk, 256, ((size_t)t * ldc + (size_t)t * EVAL_CAND) * sizeof(double), ctx->stream>>>(
+        s->kcols, s->kcols_n, s->diag, s->avail, s->C, t, ldc, s->n, alpha, s->blk_loss, s->blk_idx);
+  } else if (t <= T_SMEM) {
+    eval_kernel<1><<<nblk, 256, (size_t)t * ldc * sizeof(double), ctx->stream>>>(s->kcols, s->kcols_n, s->diag, s->avail, s->C, t,
+                                                                                ldc, s->n, alpha, s->blk_loss, s->blk_idx);
   } else {
-    eval_kernel<false><<<nblk, 128, 0, ctx->stream>>>(s->kcols, s->kcols_n, s->diag, s->avail, s->C, t, ldc, s->n, alpha,
-                                                     s->blk_loss, s->blk_idx);
+    eval_kernel<0><<<nblk, 256, 0, ctx->stream>>>(s->kcols, s->kcols_n, s->diag, s->avail, s->C, t, ldc, s->n, alpha, s->blk_loss,
+                                                 s->blk_idx);
   }
   pick_kernel<<<1, 256, 0, ctx->stream>>>(s->blk_loss, s->blk_idx, nblk, t, s->sc, commit, s->avail, s->sel, s->red);
   ctx->launches += 2;
@@ -558,15 +702,12 @@ static int step_select(nnal_ctx* ctx, State* s, int t, int commit) {
   return NNAL_OK;
 }
 
-// steps 5-6: winner slot t is filled; extend K_SS and compute the new kernel column
-static int step_extend(nnal_ctx* ctx, State* s, int t) {
-  const float* wa = s->nl == 2 ? s->win_a : nullptr;
-  kss_row_kernel<<<cdiv(t + 1, 8), 256, 0, ctx->stream>>>(s->win_u, wa, s->win_sw, s->beta2, t, s->d, s->dp, s->nl, s->kcap, s->kss);
-  ctx->launches++;
+// the winner slot is filled and K_SS extended: compute kernel column t over the local candidates
+static int step_column(nnal_ctx* ctx, State* s, int t) {
   if (s->n > 0) {
-    column_kernel<<<warp_grid(ctx, s->n), 256, 0, ctx->stream>>>(s->U, s->A, s->R(), s->sw, s->beta2, s->win_u + (int64_t)t * s->d,
-                                                                wa ? wa + (int64_t)t * s->dp : nullptr, s->win_sw + t, s->n,
-                                                                s->d, s->dp, s->nl, s->kcols + (int64_t)t * s->kcols_n);
+    column_kernel<<<warp_grid(ctx, s->n), 256, 0, ctx->stream>>>(s->U, s->A, s->R(), s->sw, s->beta2, s->win_u,
+                                                                s->nl == 2 ? s->win_a : nullptr, s->win_sw, s->n, s->d, s->dp,
+                                                                s->nl, s->kcols + (int64_t)t * s->kcols_n);
     ctx->launches++;
   }
   CUDA_TRY(ctx, cudaGetLastError());
@@ -696,10 +837,10 @@ extern "C" int nnal_fi_greedy(nnal_ctx* ctx, int64_t k, double delta, int64_t* s
   prof_begin(ctx, NNAL_PROF_FI_GREEDY);
   for (int t = 0; t < (int)k; ++t) {
     NNAL_TRY(fi::step_select(ctx, s, t, 1));
-    fi::copy_winner_kernel<<<8, 256, 0, ctx->stream>>>(s->U, s->A, s->R(), s->sw, &s->sc->best_idx, t, s->d, s->dp, s->win_u,
-                                                      s->win_a, s->win_sw);
+    fi::copy_winner_kernel<<<8, 256, 0, ctx->stream>>>(s->U, s->A, s->R(), s->sw, s->diag, s->kcols, s->kcols_n, &s->sc->best_idx, t,
+                                                      s->d, s->dp, s->win_u, s->win_a, s->win_sw, s->kss, s->kcap);
     ctx->launches++;
-    NNAL_TRY(fi::step_extend(ctx, s, t));
+    NNAL_TRY(fi::step_column(ctx, s, t));
   }
   prof_end(ctx);
   std::vector<double> red((size_t)k);
@@ -725,16 +866,7 @@ extern "C" int nnal_fi_step_local_best(nnal_ctx* ctx, int64_t step, double* loss
     NNAL_TRY(fi::step_select(ctx, s, (int)step, 0));
   } else {
     // a rank without candidates still needs tr C of the shared winners' system
-    if (step > 0) {
-      const int t = (int)step;
-      const int use_smem = t <= fi::T_SMEM ? 1 : 0;
-      const size_t smem = use_smem ? ((size_t)t * (t | 1) + t) * sizeof(double) : 0;
-      CUDA_TRY(ctx, cudaFuncSetAttribute(fi::invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(((size_t)fi::T_SMEM * (fi::T_SMEM | 1) + fi::T_SMEM) * sizeof(double))));
-      fi::invert_kernel<<<1, 1024, smem, ctx->stream>>>(s->kss, s->kcap, t, (double)(t + 1) * s->delta, s->C, (t + 7) / 8 * 8,
-                                                       s->inv_ws, use_smem, s->sc);
-      ctx->launches++;
-    }
+    if (step > 0) NNAL_TRY(fi::run_invert(ctx, s, (int)step));
   }
   fi::DevScalars h;
   CUDA_TRY(ctx, cudaMemcpyAsync(&h, s->sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
@@ -745,24 +877,32 @@ extern "C" int nnal_fi_step_local_best(nnal_ctx* ctx, int64_t step, double* loss
   return NNAL_OK;
 }
 
-extern "C" int nnal_fi_winner_factors(nnal_ctx* ctx, int64_t cand, float* factors_out, int64_t* n_floats) {
-  if (!ctx || !n_floats) return NNAL_ERR_INVALID;
+extern "C" int nnal_fi_winner_factors(nnal_ctx* ctx, int64_t step, int64_t cand, float* factors_out, int64_t* n_floats) {
+  if (!ctx || !n_floats || step < 0) return NNAL_ERR_INVALID;
   if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
   State* s = (State*)ctx->fi_state;
-  const int64_t nf = (int64_t)s->d + s->dp + 2;
+  const int64_t nf = (int64_t)s->d + s->dp + 2 + 2 * (step + 1);
   *n_floats = nf;
   if (!factors_out) return NNAL_OK;                       // size query
   if (cand < 0 || cand >= s->n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "candidate index out of range");
+  if (step >= s->kcap) NNAL_FAIL(ctx, NNAL_ERR_STATE, "nnal_fi_begin not called with a large enough k");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   int64_t row = cand;
   if (s->use_rows) {
     CUDA_TRY(ctx, cudaMemcpyAsync(&row, s->rows + cand, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
-  CUDA_TRY(ctx, cudaMemcpyAsync(factors_out, s->U + row * s->d, (size_t)s->d * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (s->nl == 2)
-    CUDA_TRY(ctx, cudaMemcpyAsync(factors_out + s->d, s->A + row * s->dp, (size_t)s->dp * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(factors_out + s->d + s->dp, s->sw + cand, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  float* o = factors_out;
+  CUDA_TRY(ctx, cudaMemcpyAsync(o, s->U + row * s->d, (size_t)s->d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  o += s->d;
+  if (s->nl == 2) CUDA_TRY(ctx, cudaMemcpyAsync(o, s->A + row * s->dp, (size_t)s->dp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  o += s->dp;
+  CUDA_TRY(ctx, cudaMemcpyAsync(o, s->sw + cand, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  o += 2;
+  // K_SS row: kcols[a][cand] for a < step (strided gather), then Kt_cand,cand
+  if (step > 0)
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(o, 8, s->kcols + cand, (size_t)s->kcols_n * 8, 8, (size_t)step, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(o + 2 * step, s->diag + cand, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return NNAL_OK;
 }
@@ -773,20 +913,25 @@ extern "C" int nnal_fi_step_apply(nnal_ctx* ctx, int64_t step, const float* winn
   if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
   State* s = (State*)ctx->fi_state;
   if (step >= s->kcap) NNAL_FAIL(ctx, NNAL_ERR_STATE, "nnal_fi_begin not called with a large enough k");
-  if (n_floats != (int64_t)s->d + s->dp + 2) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "winner factor vector has the wrong length");
+  if (n_floats != (int64_t)s->d + s->dp + 2 + 2 * (step + 1)) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "winner factor vector has the wrong length");
   if (owner_is_local && (cand_local < 0 || cand_local >= s->n)) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "candidate index out of range");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const int t = (int)step;
-  CUDA_TRY(ctx, cudaMemcpyAsync(s->win_u + (int64_t)t * s->d, winner_factors, (size_t)s->d * 4, cudaMemcpyHostToDevice, ctx->stream));
-  if (s->nl == 2)
-    CUDA_TRY(ctx, cudaMemcpyAsync(s->win_a + (int64_t)t * s->dp, winner_factors + s->d, (size_t)s->dp * 4, cudaMemcpyHostToDevice,
-                                  ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(s->win_sw + t, winner_factors + s->d + s->dp, 8, cudaMemcpyHostToDevice, ctx->stream));
+  const float* f = winner_factors;
+  CUDA_TRY(ctx, cudaMemcpyAsync(s->win_u, f, (size_t)s->d * 4, cudaMemcpyHostToDevice, ctx->stream));
+  f += s->d;
+  if (s->nl == 2) CUDA_TRY(ctx, cudaMemcpyAsync(s->win_a, f, (size_t)s->dp * 4, cudaMemcpyHostToDevice, ctx->stream));
+  f += s->dp;
+  CUDA_TRY(ctx, cudaMemcpyAsync(s->win_sw, f, 8, cudaMemcpyHostToDevice, ctx->stream));
+  f += 2;
+  // K_SS row t (contiguous) and column t (strided)
+  CUDA_TRY(ctx, cudaMemcpyAsync(s->kss + (int64_t)t * s->kcap, f, (size_t)(t + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpy2DAsync(s->kss + t, (size_t)s->kcap * 8, f, 8, 8, (size_t)(t + 1), cudaMemcpyHostToDevice, ctx->stream));
   if (owner_is_local) {
     fi::mark_taken_kernel<<<1, 1, 0, ctx->stream>>>(s->avail, (long long)cand_local);
     ctx->launches++;
   }
-  NNAL_TRY(fi::step_extend(ctx, s, t));
+  NNAL_TRY(fi::step_column(ctx, s, t));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // winner_factors is caller-owned host memory
   return NNAL_OK;
 }

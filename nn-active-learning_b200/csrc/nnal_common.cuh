@@ -102,8 +102,8 @@ struct nnal_ctx {
   long long launches = 0;
   int profile = 0;
   std::vector<ProfRec> prof;
-  size_t pool_cap_n = 0;                 // allocation capacities of the pool arrays (samples)
-  int pool_cap_keep = -1, pool_cap_class = 0, pool_cap_feat = 0, pool_cap_prev = 0;
+  size_t pool_cap_n = 0, pool_cap_score = 0, pool_cap_nfeat = 0, pool_cap_nprev = 0;   // per-array capacities (samples)
+  int pool_cap_class = 0, pool_cap_feat = 0, pool_cap_prev = 0;                        // widths they were sized for
   void* tc_state = nullptr;              // tensor-map cache etc. (gemm_tc.cu)
   void* fi_state = nullptr;              // Fisher-information candidate set / greedy state (fi.cu)
 };

@@ -348,17 +348,17 @@ class Engine(object):
         self._chk(self.lib.nnal_fi_step_local_best(self.h, int(step), C.byref(loss), C.byref(cand), C.byref(trc)))
         return loss.value, cand.value, trc.value
 
-    def fi_winner_factors(self, cand):
+    def fi_winner_factors(self, step, cand):
+        """Message of the step's winner (local candidate ``cand``): factors + its K_SS row."""
+        out = np.empty(self.fi_factor_len(step), dtype=np.float32)
         nf = C.c_int64()
-        self._chk(self.lib.nnal_fi_winner_factors(self.h, 0, None, C.byref(nf)))
-        out = np.empty(nf.value, dtype=np.float32)
-        self._chk(self.lib.nnal_fi_winner_factors(self.h, int(cand), _ptr(out), C.byref(nf)))
+        self._chk(self.lib.nnal_fi_winner_factors(self.h, int(step), int(cand), _ptr(out), C.byref(nf)))
         self.d2h_bytes += out.nbytes
         return out
 
-    def fi_factor_len(self):
+    def fi_factor_len(self, step):
         nf = C.c_int64()
-        self._chk(self.lib.nnal_fi_winner_factors(self.h, 0, None, C.byref(nf)))
+        self._chk(self.lib.nnal_fi_winner_factors(self.h, int(step), 0, None, C.byref(nf)))
         return nf.value
 
     def fi_step_apply(self, step, factors, owner_is_local, cand_local):

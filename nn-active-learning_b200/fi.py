@@ -40,7 +40,6 @@ def greedy_select(eng, k, delta, gids=None):
     n_total = int(dist.allreduce_sum_(torch.tensor([n_local], dtype=torch.int64, device=dist._device())).item())
     k = min(int(k), n_total)
     D = eng.fi_info()['D']
-    nf = eng.fi_factor_len()
     eng.fi_begin(max(k, 1), delta)
     sel, obj = [], []
     none = float(np.iinfo(np.int64).max >> 12)
@@ -49,7 +48,7 @@ def greedy_select(eng, k, delta, gids=None):
         gid = float(gids[cand]) if cand >= 0 else none
         val, payload, owner = dist.allreduce_argmin(loss, gid)
         mine = (owner == rank)
-        f = eng.fi_winner_factors(cand) if mine else np.zeros(nf, dtype=np.float32)
+        f = eng.fi_winner_factors(t, cand) if mine else np.zeros(eng.fi_factor_len(t), dtype=np.float32)
         f = dist.broadcast_array(f, owner)
         eng.fi_step_apply(t, f, mine, cand if mine else 0)
         sel.append(int(payload))
