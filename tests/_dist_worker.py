@@ -1,0 +1,91 @@
+"""Worker of tests/test_dist_cpu.py: one rank of a world_size-N gloo group running the reference-named
+query functions of nnal_b200 on a NumPy fake engine.  Writes its results to <out>/rank<r>.npz."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def make_case():
+    from collections import OrderedDict
+    import oracle as O
+    from tests.util import pad_imgs, synth_volume
+    ps = (5, 5, 1)
+    m, S = 2, 3
+    shape = (12, 11, 4)
+    layers = [('conv1', [4, 'conv', [3, 3]]), ('max1', [[2, 2], 'pool']), ('fc1', [16, 'fc']), ('fc2', [12, 'fc']),
+              ('fc3', [2, 'fc'])]
+    w = O.he_init_weights(layers, (5, 5, m), 7, bias_scale=0.1)
+    rs = np.random.RandomState(5)
+    allp, pools, st = [], [], np.zeros((S, 2 * m))
+    for s in range(S):
+        imgs = synth_volume(shape, m, 90 + s)
+        allp.append(pad_imgs(imgs, ps) + [(rs.rand(*shape) > .5).astype(np.int8)])
+        pools.append(list(rs.choice(int(np.prod(shape)), [70, 0, 95][s], replace=False)))
+        for j in range(m):
+            st[s, 2 * j], st[s, 2 * j + 1] = imgs[j].mean(), imgs[j].std()
+    return ps, m, layers, w, allp, pools, st, OrderedDict(layers)
+
+
+def run(rank, world, out):
+    import torch.distributed as td
+    if world > 1:
+        td.init_process_group('gloo', rank=rank, world_size=world)
+    import nnal_b200
+    from nnal_b200 import dist, engine
+    from tests.fake_engine import FakeEngine
+    engine._engine = FakeEngine()            # the host logic under test talks to this instead of libnnal_b200
+
+    class Expr(object):
+        pass
+
+    ps, m, layers, w, allp, pools, st, ld = make_case()
+    model = nnal_b200.NN.CNN((5, 5, m), ld, feature_layer=len(layers) - 2)
+    model.set_weights(w)
+    res = {}
+    # single-volume queries
+    expr = Expr()
+    stats0 = [[st[0, 2 * j], st[0, 2 * j + 1]] for j in range(m)]
+    expr.pars = dict(k=9, B=30, lambda_=0., patch_shape=ps, ntb=16, stats=stats0, fi_layers=2, fi_diag_load=1e-3)
+    pool0 = np.array(pools[0])
+    res['ent_single'] = nnal_b200.PW_NNAL.CNN_query(expr, model, None, allp[0][:m], pool0, None, 'entropy')
+    q, obj = nnal_b200.fi.query_single(expr, model, None, allp[0][:m], pool0, return_objective=True)
+    res['fi_single'], res['fi_single_obj'] = q, obj
+    expr.pars['B'] = 10 ** 6                 # no pre-filter: every rank's whole block is a candidate
+    q, obj = nnal_b200.fi.query_single(expr, model, None, allp[0][:m], pool0, return_objective=True)
+    res['fi_all'], res['fi_all_obj'] = q, obj
+    # multi-volume queries
+    expr = Expr()
+    expr.pars = dict(k=11, B=40, lambda_=0., patch_shape=ps, ntb=16, SDP_solver='CVXOPT', fi_layers=2)
+    expr.train_stats = st
+    Q = nnal_b200.PW_NNAL.query_multimg(expr, model, None, allp, pools, None, 'entropy')
+    for s in range(len(Q)):
+        res['ent_multi%d' % s] = np.asarray(Q[s])
+    sel_inds, sel_posts = nnal_b200.PW_NNAL.bin_uncertainty_filter_multimg(expr, model, None, allp, pools, 25)
+    for s in range(len(sel_inds)):
+        res['filt_inds%d' % s] = np.asarray(sel_inds[s])
+        res['filt_posts%d' % s] = np.asarray(sel_posts[s])
+    Q, obj = nnal_b200.fi.query_multimg(expr, model, None, allp, pools, return_objective=True)
+    for s in range(len(Q)):
+        res['fi_multi%d' % s] = np.asarray(Q[s])
+    res['fi_multi_obj'] = obj
+    # primitives
+    rs = np.random.RandomState(100 + rank)
+    sc = np.sort(rs.rand(6))
+    pos = rs.choice(50, 6, replace=False).astype(np.int64) + 100 * rank
+    res['merge_pos'], res['merge_sc'] = dist.allgather_topk(sc, pos, 8)
+    res['my_sc'], res['my_pos'] = sc, pos
+    res['argmin'] = np.array(dist.allreduce_argmin(float(rs.rand()), 5 + rank))
+    res['bcast'] = dist.broadcast_array(np.arange(4, dtype=np.float32) + rank, world - 1)
+    res['concat'] = dist.allgather_concat(np.arange(rank + 2, dtype=np.int64) + 10 * rank)
+    np.savez(os.path.join(out, 'rank%d.npz' % rank), **res)
+    if world > 1:
+        td.barrier()
+        td.destroy_process_group()
+
+
+if __name__ == '__main__':
+    run(int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), sys.argv[1])

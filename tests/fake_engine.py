@@ -1,0 +1,191 @@
+"""NumPy stand-in for ``nnal_b200.engine.Engine`` used by the CPU-only multi-rank tests (gloo,
+world_size 2): same method surface as the C-ABI wrapper, arithmetic through the float64 oracle.
+TEST INFRASTRUCTURE ONLY -- it lets the host-side logic (pool sharding, top-k merge, the FI greedy
+step protocol, index bookkeeping) run without a GPU; the product never imports it."""
+import numpy as np
+
+import oracle as O
+
+
+class FakeEngine(object):
+    def __init__(self):
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.vols = {}
+        self._m = {}
+
+    # -- model / volumes ---------------------------------------------------
+    def set_model(self, model, sess=None):
+        self.layers = [(k, v) for k, v in model.layer_dict.items()]
+        self.weights = model.get_weights(sess)
+        self.n_class = int(self.layers[-1][1][0])
+        self.feature_layer = model.feature_layer_index if model.feature_layer_index is not None else len(self.layers) - 2
+
+    def upload(self, subject, imgs, pads=(0, 0, 0)):
+        self.vols[subject] = [np.asarray(a) for a in imgs]
+        self._m[subject] = len(imgs)
+
+    # -- pool pass -----------------------------------------------------------
+    def pool_begin(self, n, keep=0):
+        self._pool_n = int(n)
+        self.keep = keep
+        self.post = np.zeros((self.n_class, n))
+        self.feat = None
+        self.prev = None
+        self.score = None
+
+    def _forward(self, x, offset):
+        r = O.forward(self.layers, self.weights, x, self.feature_layer, keep_acts=True)
+        n = x.shape[0]
+        self.post[:, offset:offset + n] = r['posteriors']
+        if self.keep >= 1:
+            if self.feat is None:
+                self.feat = np.zeros((self._pool_n, r['feature_layer'].shape[0]))
+            self.feat[offset:offset + n] = r['feature_layer'].T
+        if self.keep >= 2:
+            a = r['acts'][self.feature_layer]['in']
+            if self.prev is None:
+                self.prev = np.zeros((self._pool_n, a.shape[0]))
+            self.prev[offset:offset + n] = a.T
+
+    def pool_eval(self, subject, inds, offset, patch_shape, stats, norm_mode=1, shape=None):
+        inds = np.asarray(inds)
+        if len(inds) == 0:
+            return
+        x = O.get_patches(self.vols[subject], inds, patch_shape)
+        x = O.normalize_batch_eval(x, [list(s) for s in np.asarray(stats)]).astype(np.float32)
+        self._forward(x, offset)
+
+    def pool_eval_images(self, x, offset):
+        if len(x):
+            self._forward(np.asarray(x, dtype=np.float32), offset)
+
+    def pool_posteriors(self):
+        return self.post.astype(np.float32)
+
+    def pool_features(self, start=0, n=None):
+        n = self._pool_n - start if n is None else n
+        return self.feat[start:start + n].T.astype(np.float32)
+
+    def pool_score(self, kind, eps=0.0):
+        p = self.post
+        if kind == 0:
+            self.score = np.abs(p[1] - .5)
+        elif kind in (1, 2):
+            q = np.where(p == 0, eps, p)
+            h = np.sum(q * np.log(q), axis=0)
+            self.score = h if kind == 1 else -h
+        else:
+            self.score = -O.fi_trace_score(p, self.feat.T)
+
+    def pool_topk(self, k, with_scores=False):
+        k = int(min(max(k, 0), self._pool_n))
+        idx = O.stable_topk(self.score, k).astype(np.int64)
+        return (idx, self.score[idx]) if with_scores else idx
+
+    # -- Fisher information --------------------------------------------------
+    def fi_set_candidates(self, cand=None, n_layers=2):
+        rows = np.arange(self._pool_n) if cand is None else np.asarray(cand, dtype=np.int64)
+        self.fi_nl = n_layers
+        self.fi_p1 = self.post[1, rows]
+        f32 = lambda a: a.astype(np.float32).astype(np.float64)       # factors are float32 on the device
+        self.fi_U = f32(self.feat[rows]) if len(rows) else np.zeros((0, self._feat_dim()))
+        self.fi_A = (f32(self.prev[rows]) if len(rows) else np.zeros((0, self._prev_dim()))) if n_layers == 2 else None
+        self.fi_Wl = self.weights[self.layers[-1][0]][0].astype(np.float64)
+        self._fi_setup()
+
+    def _feat_dim(self):
+        return int(self.layers[self.feature_layer][1][0])
+
+    def _prev_dim(self):
+        return int(self.weights[self.layers[self.feature_layer][0]][0].shape[1])
+
+    def _fi_setup(self):
+        self.fi_w = self.fi_p1 * (1 - self.fi_p1)
+        self.fi_beta = self.fi_Wl[0] - self.fi_Wl[1]
+        n = len(self.fi_p1)
+        self.fi_diag = np.array([self._kern(i, self.fi_U[i], None if self.fi_A is None else self.fi_A[i],
+                                            np.sqrt(self.fi_w[i])) for i in range(n)]) if n else np.zeros(0)
+
+    def _kern(self, i, u, a, sw):
+        k = 2. * (self.fi_U[i] @ u + 1.)
+        if self.fi_nl == 2:
+            mk = ((self.fi_U[i] > 0) & (u > 0)) @ (self.fi_beta ** 2)
+            k += mk * (self.fi_A[i] @ a + 1.)
+        return np.sqrt(self.fi_w[i]) * sw * k
+
+    def fi_info(self):
+        d = self.fi_U.shape[1] if self.fi_U.ndim == 2 and self.fi_U.shape[1] else self._feat_dim()
+        dp = self._prev_dim() if self.fi_nl == 2 else 0
+        return {'n': len(self.fi_p1), 'n_layers': self.fi_nl, 'd': d, 'd_prev': dp,
+                'D': O.last_layers_dim(2, d, dp if self.fi_nl == 2 else None)}
+
+    def fi_begin(self, k, delta):
+        n = len(self.fi_p1)
+        self.fi_delta = delta
+        self.fi_avail = np.ones(n, dtype=bool)
+        self.fi_kcols = np.zeros((k, n))
+        self.fi_kss = np.zeros((k, k))
+
+    def fi_step_local_best(self, t):
+        n = len(self.fi_p1)
+        alpha = (t + 1) * self.fi_delta
+        trc = 0.
+        if t > 0:
+            C = np.linalg.inv(alpha * np.eye(t) + self.fi_kss[:t, :t])
+            trc = float(np.trace(C))
+        if n == 0:
+            return float('inf'), -1, trc
+        if t == 0:
+            r, e = self.fi_diag.copy(), np.zeros(n)
+        else:
+            kj = self.fi_kcols[:t].T
+            Y = kj @ C
+            r = self.fi_diag - np.sum(Y * kj, axis=1)
+            e = np.sum(Y * Y, axis=1)
+        loss = (1. + e) / (alpha + r)
+        loss[~self.fi_avail] = np.inf
+        j = int(np.argmin(loss))
+        if not np.isfinite(loss[j]):
+            return float('inf'), -1, trc
+        return float(loss[j]), j, trc
+
+    def fi_factor_len(self, step):
+        i = self.fi_info()
+        return i['d'] + i['d_prev'] + 2 + 2 * (step + 1)
+
+    def fi_winner_factors(self, step, cand):
+        row = np.append(self.fi_kcols[:step, cand], self.fi_diag[cand])
+        parts = [self.fi_U[cand].astype(np.float32)]
+        if self.fi_nl == 2:
+            parts.append(self.fi_A[cand].astype(np.float32))
+        parts.append(np.array([np.sqrt(self.fi_w[cand])], dtype=np.float64).view(np.float32))
+        parts.append(row.astype(np.float64).view(np.float32))
+        return np.concatenate(parts)
+
+    def fi_step_apply(self, t, f, owner_is_local, cand_local):
+        i = self.fi_info()
+        d, dp = i['d'], i['d_prev']
+        u = f[:d].astype(np.float64)
+        a = f[d:d + dp].astype(np.float64) if dp else None
+        sw = float(np.ascontiguousarray(f[d + dp:d + dp + 2]).view(np.float64)[0])
+        row = np.ascontiguousarray(f[d + dp + 2:]).view(np.float64)
+        self.fi_kss[t, :t + 1] = row
+        self.fi_kss[:t + 1, t] = row
+        if owner_is_local:
+            self.fi_avail[cand_local] = False
+        for j in range(len(self.fi_p1)):
+            self.fi_kcols[t, j] = self._kern(j, u, a, sw)
+
+    def fi_greedy(self, k, delta):
+        k = int(min(k, len(self.fi_p1)))
+        self.fi_begin(max(k, 1), delta)
+        D = self.fi_info()['D']
+        sel, obj, red = [], [], []
+        for t in range(k):
+            loss, cand, trc = self.fi_step_local_best(t)
+            self.fi_step_apply(t, self.fi_winner_factors(t, cand), True, cand)
+            sel.append(cand)
+            red.append((t + 1) * (trc + loss))
+            obj.append((D - (t + 1)) / delta + red[-1])
+        return np.array(sel, dtype=np.int64), np.array(obj), np.array(red)

@@ -1,0 +1,98 @@
+"""Multi-rank host logic on CPU: world_size-2 gloo groups run the reference-named query functions over a
+NumPy fake engine (tests/fake_engine.py); every rank must return what a single process returns, and
+that must agree with the float64 oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _launch(world, out, port):
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1',
+                   MASTER_PORT=str(port), OMP_NUM_THREADS='1')
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, 'tests', '_dist_worker.py'), out], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        o = p.communicate(timeout=600)[0].decode()
+        assert p.returncode == 0, o[-3000:]
+    return [np.load(os.path.join(out, 'rank%d.npz' % r)) for r in range(world)]
+
+
+@pytest.fixture(scope='module')
+def runs(tmp_path_factory):
+    d1 = str(tmp_path_factory.mktemp('w1'))
+    d2 = str(tmp_path_factory.mktemp('w2'))
+    d3 = str(tmp_path_factory.mktemp('w3'))
+    return _launch(1, d1, 29611)[0], _launch(2, d2, 29612), _launch(3, d3, 29613)
+
+
+def test_ranks_agree_with_single_process(runs):
+    one, two, three = runs
+    skip = ('merge_', 'my_', 'argmin', 'bcast', 'concat')
+    for multi in (two, three):
+        for r in multi:
+            for key in one.files:
+                if key.startswith(skip):
+                    continue
+                a, b = one[key], r[key]
+                if a.dtype.kind == 'f':
+                    assert np.allclose(a, b, rtol=1e-9, atol=0), key
+                else:
+                    assert np.array_equal(a, b), key
+
+
+def test_single_process_matches_oracle(runs):
+    one = runs[0]
+    sys.path.insert(0, ROOT)
+    from tests._dist_worker import make_case
+    ps, m, layers, w, allp, pools, st, _ = make_case()
+    stats0 = [[st[0, 2 * j], st[0, 2 * j + 1]] for j in range(m)]
+    pool0 = np.array(pools[0])
+    q, posts = O.query_entropy_single(layers, w, allp[0][:m], pool0, ps, 16, stats0, 9)
+    assert np.array_equal(one['ent_single'], q)
+    qf, obj, _ = O.query_fi_single(layers, w, allp[0][:m], pool0, ps, 16, stats0, 9, 30, 2, 1e-3)
+    assert np.array_equal(one['fi_single'], qf)
+    assert np.allclose(one['fi_single_obj'], obj, rtol=1e-6)
+    qf, obj, _ = O.query_fi_single(layers, w, allp[0][:m], pool0, ps, 16, stats0, 9, 10 ** 6, 2, 1e-3)
+    assert np.array_equal(one['fi_all'], qf)
+    Q = O.query_entropy_multimg(layers, w, allp, pools, ps, 16, st, 11)
+    for s in range(3):
+        assert np.array_equal(one['ent_multi%d' % s], Q[s])
+    si, sp = O.bin_uncertainty_filter_multimg(layers, w, allp, pools, ps, 16, st, 25)
+    for s in range(3):
+        assert np.array_equal(one['filt_inds%d' % s], si[s])
+        assert np.allclose(one['filt_posts%d' % s], sp[s], rtol=1e-6)      # float32 posteriors like the TF fetch
+    Qf, obj, _ = O.query_fi_multimg(layers, w, allp, pools, ps, 16, st, 11, 40, 2, 1e-3)
+    for s in range(3):
+        assert np.array_equal(one['fi_multi%d' % s], Qf[s])
+    assert np.allclose(one['fi_multi_obj'], obj, rtol=1e-6)
+
+
+def test_collective_primitives(runs):
+    for multi in runs[1:]:
+        world = len(multi)
+        sc = np.concatenate([r['my_sc'] for r in multi])
+        pos = np.concatenate([r['my_pos'] for r in multi])
+        order = np.lexsort((pos, sc))[:8]
+        for r in multi:
+            assert np.array_equal(r['merge_pos'], pos[order]) and np.array_equal(r['merge_sc'], sc[order])
+            assert np.array_equal(r['argmin'], multi[0]['argmin'])
+            assert np.array_equal(r['bcast'], np.arange(4, dtype=np.float32) + world - 1)
+            assert np.array_equal(r['concat'], np.concatenate([np.arange(q + 2) + 10 * q for q in range(world)]))
+
+
+def test_shard_bounds():
+    from nnal_b200 import dist
+    for n, w in [(0, 3), (5, 8), (100, 3), (17, 1)]:
+        b = dist.shard_bounds(n, w)
+        assert b[0] == 0 and b[-1] == n and len(b) == w + 1
+        sizes = np.diff(b)
+        assert sizes.max() - sizes.min() <= 1 and np.all(sizes >= 0)
