@@ -300,7 +300,7 @@ def run_ours(args, rank, world):
         roofline = {'kernel': top, 'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                     'frac': achieved / peak, 'traffic': None,
                     'note': 'algorithmic FLOPs (2*MACs) per launch / mean launch time; peak = %s sustained bf16; '
-                            '%s' % (peaks['source'], 'tcgen05 3-term bf16 split executes 3x these FLOPs'
+                            '%s' % (peaks['source'], 'tcgen05 fp16 hi/lo split executes 3x these FLOPs'
                                     if tinfo['tc'] else 'FP32 CUDA-core kernel (no tensor pipe)')}
     else:
         bytes_per = {'gather': 15008.0, 'score': 12.0, 'topk': 4.0}[top]
@@ -319,7 +319,7 @@ def run_ours(args, rank, world):
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'bf16x3 (3-term bf16 split, fp32 accumulate) + f32/f64 scoring',
+            'vs_baseline': None, 'dtype': 'f16x3 (fp16 hi/lo split operands, 3 tcgen05 MMAs per product, fp32 accumulate) + f32/f64 scoring',
             'data': 'synthetic',
             'config': {'workload': 'config2: PW1 2-class CNN, 3x 256x256x180 f32 volumes, 25x25x3 patches, '
                                    '%d-patch pool per GPU, entropy query k=100' % args.pool,
