@@ -15,8 +15,16 @@
 //   * One K=16 MMA consumes two chunks (tap,q) whose addresses may be unrelated: the descriptor's
 //     leading-byte-offset is set per instruction, so K = (#taps * Cin/8) chunks is only padded to an
 //     even count (75 -> 76 for conv2), not per tap.
-//   * Weights are pre-arranged per K-step as [2 chunks][Cout][8] bf16 (hi and lo) and streamed through
-//     a 3-stage ring with cp.async.bulk.
+//   * Weights are pre-arranged per K-step as [2 chunks][2*Cout][8] fp16 -- rows 0..Cout-1 the hi terms, rows
+//     Cout..2Cout-1 the lo terms -- and streamed through a 3-stage ring with cp.async.bulk.  The three
+//     products hi.hi + hi.lo + lo.hi take TWO MMAs per K-step: A_hi x [W_hi;W_lo] (N = 2 Cout: hi.hi lands in
+//     accumulator columns 0..Cout-1, hi.lo in Cout..2Cout-1) and A_lo x W_hi (N = Cout, first Cout rows of the
+//     same block, accumulated into columns 0..Cout-1); the epilogue adds the two column halves.  With N as
+//     small as 32 the MMA is bound by SHARED-MEMORY operand reads (4 KB of A per 16-cycle MMA at 128 B/clk),
+//     so reading A_hi once instead of twice is worth 27 % (profiles/).
+//   * The T M-tiles of a sample group are processed in NG groups of TG tiles (the weight ring is streamed
+//     once per tile group): 2 x TG x 2Cout accumulator columns fit TMEM, so the epilogue of one tile group
+//     overlaps the MMAs of the next.
 // Warp roles: warp 0 input TMA, warp 3 weight producer, warp 1 MMA issuer, warp 2 TMEM allocator,
 // warps 4-7 epilogue (TMEM -> +bias, ReLU -> bf16 hi/lo NHWC in global memory).
 #include "nnal_common.cuh"
@@ -114,14 +122,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // Compile-time geometry of one conv layer
-template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int NACC_>
+template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_>
 struct Cfg {
   // CIN / COUT are the padded operand extents (multiples of 8 / 16); the *_REAL values are the layer's
   static constexpr int CIN_REAL = CIN_REAL_, COUT_REAL = COUT_REAL_;
   static constexpr int CIN = (CIN_REAL + 7) / 8 * 8, COUT = (COUT_REAL + 15) / 16 * 16;
   static constexpr int H = H_, W = W_, KS = KS_, G = G_;
   static constexpr int KPS = KPS_;                       // K-steps per weight stage
-  static constexpr int NBUF = NBUF_, NACC = NACC_;
+  static constexpr int NBUF = NBUF_, NACC = 2, TG = TG_;  // TG: M tiles per accumulator (tile group)
+  static constexpr bool CAT = CAT_;                      // A_hi x [W_hi;W_lo] in one MMA (2 MMAs per K-step) or three separate MMAs
   static constexpr int PH = KS / 2;
   static constexpr int HP = H + KS - 1, WP = W + KS - 1;
   static constexpr int Q = CIN / 8;
@@ -131,24 +140,27 @@ struct Cfg {
   static constexpr int NSTAGE_W = (NK + KPS - 1) / KPS;  // weight stages per group
   static constexpr int RASTER = G * HP * WP;
   static constexpr int LAST_VALID = (G - 1) * HP * WP + (H - 1) * WP + (W - 1);
-  static constexpr int T = LAST_VALID / 128 + 1;         // M tiles per group
+  static constexpr int T = LAST_VALID / 128 + 1;         // M tiles per sample group
+  static constexpr int NG = (T + TG - 1) / TG;           // tile groups per sample group
+  static constexpr int TILE_COLS = CAT ? 2 * COUT : COUT; // TMEM columns of one M tile (CAT: hi.hi+lo.hi | hi.lo halves)
+  static constexpr int ACC_COLS = TG * TILE_COLS;        // TMEM columns of one accumulator
   static constexpr int MAX_OFF = (KS - 1) * WP + (KS - 1);
   static constexpr int PLANE = ((RASTER * 16 + 127) / 128) * 128;                 // bytes
   static constexpr int OVERRUN = (T * 128 + MAX_OFF + 8 - RASTER) > 0 ? (T * 128 + MAX_OFF + 8 - RASTER) : 0;
   static constexpr int IN_BYTES = ((2 * Q * PLANE + OVERRUN * 16 + 1023) / 1024) * 1024;   // hi planes then lo planes
-  static constexpr int W_KSTEP_BYTES = 2 * COUT * 16;    // one K-step of one (hi|lo) plane: [2][COUT][8] bf16
-  static constexpr int W_STAGE_BYTES = 2 * KPS * W_KSTEP_BYTES;                   // hi block then lo block
+  static constexpr int W_KSTEP_BYTES = 2 * (2 * COUT) * 16;   // one K-step: [2 chunks][hi rows | lo rows][8] fp16
+  static constexpr int W_STAGE_BYTES = KPS * W_KSTEP_BYTES;
   static constexpr int WSTAGES = 3;
   static constexpr int SMEM = NBUF * IN_BYTES + WSTAGES * W_STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS_USED = NACC * T * COUT;
+  static constexpr int TMEM_COLS_USED = NACC * ACC_COLS;
   static_assert(CIN % 8 == 0, "input channels must be a multiple of 8");
-  static_assert(COUT % 16 == 0 && COUT <= 256, "UMMA N");
+  static_assert(COUT % 16 == 0 && 2 * COUT <= 256, "UMMA N");
   static_assert(TMEM_COLS_USED <= 512, "TMEM budget");
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 struct ConvParams {
-  const uint8_t* wpack;      // [NSTAGE_W][hi|lo][KPS][2][COUT][8] bf16
+  const uint8_t* wpack;      // [NSTAGE_W][KPS][2 chunks][hi COUT | lo COUT][8] fp16
   const float* bias;
   nnal_h* out_hi;     // [n][H][W][COUT]
   nnal_h* out_lo;
@@ -242,12 +254,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     if (lane == 0) {
       uint32_t it = 0;
       for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        for (int ws = 0; ws < C::NSTAGE_W; ++ws, ++it) {
+        for (int ws = 0; ws < C::NG * C::NSTAGE_W; ++ws, ++it) {
           const int s = it % C::WSTAGES;
           const uint32_t ph = (it / C::WSTAGES) & 1;
           mbar_wait(w_empty(s), ph ^ 1);
           mbar_arrive_expect_tx(w_full(s), C::W_STAGE_BYTES);
-          bulk_load(w_base + s * C::W_STAGE_BYTES, p.wpack + (size_t)ws * C::W_STAGE_BYTES, C::W_STAGE_BYTES, w_full(s));
+          bulk_load(w_base + s * C::W_STAGE_BYTES, p.wpack + (size_t)(ws % C::NSTAGE_W) * C::W_STAGE_BYTES, C::W_STAGE_BYTES, w_full(s));
         }
       }
     }
@@ -257,109 +269,146 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     // issue loop is kept to a few instructions per MMA: per-K-step descriptor words come from the
     // table built above, per-tile descriptors differ by a compile-time constant.
     {
-      const uint32_t idesc = make_idesc_bf16(128, C::COUT);
+      const uint32_t idesc_cat = make_idesc_bf16(128, 2 * C::COUT);   // A_hi x [W_hi;W_lo]
+      const uint32_t idesc_hi = make_idesc_bf16(128, C::COUT);        // A_lo x W_hi
       constexpr uint32_t DESC_HI = 8u /*SBO 128 B*/ | (1u << 14) /*version*/;
-      constexpr uint32_t B_LBO = (uint32_t)C::COUT << 16;       // (COUT*16 B) >> 4 in the LBO field
-      uint32_t it_in = 0, it_w = 0;
+      constexpr uint32_t B_LBO = (uint32_t)(2 * C::COUT) << 16;      // chunk stride (2*COUT*16 B) >> 4 in the LBO field
+      uint32_t it_in = 0, it_w = 0, it_acc = 0;
       for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it_in) {
         const int b = it_in % C::NBUF;
         const uint32_t ph_in = (it_in / C::NBUF) & 1;
-        const int a = it_in % C::NACC;
-        const uint32_t ph_acc = (it_in / C::NACC) & 1;
-        mbar_wait(acc_empty(a), ph_acc ^ 1);
         mbar_wait(in_full(b), ph_in);
         tc_fence_after();
         const uint32_t a_hi16 = (in_base + b * C::IN_BYTES) >> 4;
-        const uint32_t d_base = tmem_base + a * C::T * C::COUT;
-        for (int ws = 0; ws < C::NSTAGE_W; ++ws, ++it_w) {
-          const int s = it_w % C::WSTAGES;
-          const uint32_t ph = (it_w / C::WSTAGES) & 1;
-          mbar_wait(w_full(s), ph);
+#pragma unroll 1
+        for (int tg = 0; tg < C::NG; ++tg, ++it_acc) {
+          const int a = it_acc % C::NACC;
+          const uint32_t ph_acc = (it_acc / C::NACC) & 1;
+          mbar_wait(acc_empty(a), ph_acc ^ 1);
           tc_fence_after();
-          const uint32_t wb16 = (w_base + s * C::W_STAGE_BYTES) >> 4;
-          if (elect_one_sync()) {
+          const uint32_t d_base = tmem_base + a * C::ACC_COLS;
+          const uint32_t tile0 = (uint32_t)(tg * C::TG) * 128u;       // first raster position of the tile group (>>4 units: x128 = 16 B x 128 / 16)
+          for (int ws = 0; ws < C::NSTAGE_W; ++ws, ++it_w) {
+            const int s = it_w % C::WSTAGES;
+            const uint32_t ph = (it_w / C::WSTAGES) & 1;
+            mbar_wait(w_full(s), ph);
+            tc_fence_after();
+            const uint32_t wb16 = (w_base + s * C::W_STAGE_BYTES) >> 4;
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int j = 0; j < C::KPS; ++j) {
-              const int ks = ws * C::KPS + j;
-              if (ks < C::NK) {
-                const uint2 e = ktab[ks];                           // {start offset >> 4, LBO field}
-                const uint32_t ah = (a_hi16 + e.x) | e.y;
-                const uint32_t al = ah + ((C::Q * C::PLANE) >> 4);
-                const uint32_t bh = (wb16 + j * (C::W_KSTEP_BYTES >> 4)) | B_LBO;
-                const uint32_t bl = bh + ((C::KPS * C::W_KSTEP_BYTES) >> 4);
-                const uint64_t dBh = ((uint64_t)DESC_HI << 32) | bh, dBl = ((uint64_t)DESC_HI << 32) | bl;
-                const uint32_t acc0 = ks != 0;
+              for (int j = 0; j < C::KPS; ++j) {
+                const int ks = ws * C::KPS + j;
+                if (ks < C::NK) {
+                  const uint2 e = ktab[ks];                           // {start offset >> 4, LBO field}
+                  const uint32_t ah = (a_hi16 + e.x + tile0) | e.y;
+                  const uint32_t al = ah + ((C::Q * C::PLANE) >> 4);
+                  const uint64_t dB = ((uint64_t)DESC_HI << 32) | ((wb16 + j * (C::W_KSTEP_BYTES >> 4)) | B_LBO);
+                  const uint32_t acc0 = ks != 0;
+                  if (C::CAT) {
+                    // the two MMAs of a tile accumulate into the same columns: issue them TG MMAs apart
 #pragma unroll
-                for (int t = 0; t < C::T; ++t) {
-                  const uint64_t dAh = ((uint64_t)DESC_HI << 32) | (ah + t * 128);
-                  const uint64_t dAl = ((uint64_t)DESC_HI << 32) | (al + t * 128);
-                  const uint32_t d = d_base + t * C::COUT;
-                  umma_bf16(d, dAl, dBh, idesc, acc0);
-                  umma_bf16(d, dAh, dBl, idesc, 1);
-                  umma_bf16(d, dAh, dBh, idesc, 1);
+                    for (int t = 0; t < C::TG; ++t) {
+                      if (tg * C::TG + t < C::T) {
+                        const uint64_t dAh = ((uint64_t)DESC_HI << 32) | (ah + t * 128);
+                        umma_bf16(d_base + t * C::TILE_COLS, dAh, dB, idesc_cat, acc0);   // cols [0,COUT): hi.hi  [COUT,2COUT): hi.lo
+                      }
+                    }
+#pragma unroll
+                    for (int t = 0; t < C::TG; ++t) {
+                      if (tg * C::TG + t < C::T) {
+                        const uint64_t dAl = ((uint64_t)DESC_HI << 32) | (al + t * 128);
+                        umma_bf16(d_base + t * C::TILE_COLS, dAl, dB, idesc_hi, 1);       // cols [0,COUT) += lo.hi
+                      }
+                    }
+                  } else {
+                    const uint64_t dBl = dB + (uint64_t)C::COUT;                          // lo rows start COUT*16 B further
+#pragma unroll
+                    for (int t = 0; t < C::TG; ++t) {
+                      if (tg * C::TG + t < C::T) {
+                        const uint64_t dAh = ((uint64_t)DESC_HI << 32) | (ah + t * 128);
+                        const uint64_t dAl = ((uint64_t)DESC_HI << 32) | (al + t * 128);
+                        const uint32_t d = d_base + t * C::TILE_COLS;
+                        umma_bf16(d, dAl, dB, idesc_hi, acc0);
+                        umma_bf16(d, dAh, dBl, idesc_hi, 1);
+                        umma_bf16(d, dAh, dB, idesc_hi, 1);
+                      }
+                    }
+                  }
                 }
               }
+              umma_commit(w_empty(s));
             }
-            umma_commit(w_empty(s));
+            __syncwarp();
+          }
+          if (elect_one_sync()) {
+            if (tg == C::NG - 1) umma_commit(in_empty(b));
+            umma_commit(acc_full(a));
           }
           __syncwarp();
         }
-        if (elect_one_sync()) {
-          umma_commit(in_empty(b));
-          umma_commit(acc_full(a));
-        }
-        __syncwarp();
       }
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
     const int qd = warp & 3;
     uint32_t it = 0;
-    for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
-      const int a = it % C::NACC;
-      const uint32_t ph_acc = (it / C::NACC) & 1;
-      mbar_wait(acc_full(a), ph_acc);
-      tc_fence_after();
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
 #pragma unroll 1
-      for (int t = 0; t < C::T; ++t) {
-        const int pos = t * 128 + qd * 32 + lane;              // padded-raster position of this thread's row
-        const int gs = pos / (C::HP * C::WP);
-        const int rem = pos - gs * (C::HP * C::WP);
-        const int y = rem / C::WP, x = rem - y * C::WP;
-        const int sample = g * C::G + gs;
-        const bool valid = gs < C::G && y < C::H && x < C::W && sample < p.n;
-        const size_t obase = (((size_t)sample * C::H + y) * C::W + x) * C::COUT_REAL;
+      for (int tg = 0; tg < C::NG; ++tg, ++it) {
+        const int a = it % C::NACC;
+        const uint32_t ph_acc = (it / C::NACC) & 1;
+        mbar_wait(acc_full(a), ph_acc);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < C::COUT_REAL; c0 += 16) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((a * C::T + t) * C::COUT + c0), v);
-          if (valid) {
-            uint32_t hi[8], lo[8];
+        for (int tl = 0; tl < C::TG; ++tl) {
+          const int t = tg * C::TG + tl;
+          if (t >= C::T) break;
+          const int pos = t * 128 + qd * 32 + lane;              // padded-raster position of this thread's row
+          const int gs = pos / (C::HP * C::WP);
+          const int rem = pos - gs * (C::HP * C::WP);
+          const int y = rem / C::WP, x = rem - y * C::WP;
+          const int sample = g * C::G + gs;
+          const bool valid = gs < C::G && y < C::H && x < C::W && sample < p.n;
+          const size_t obase = (((size_t)sample * C::H + y) * C::W + x) * C::COUT_REAL;
+          const uint32_t tcol = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * C::ACC_COLS + tl * C::TILE_COLS);
+#pragma unroll 1
+          for (int c0 = 0; c0 < C::COUT_REAL; c0 += 16) {
+            float v[16], w[16];
+            tmem_ld16(tcol + c0, v);                             // hi.hi + lo.hi (CAT) or the full sum
+            if (C::CAT) {
+              tmem_ld16(tcol + C::COUT + c0, w);                 // hi.lo
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int ca = c0 + 2 * j < C::COUT_REAL ? c0 + 2 * j : 0, cb = c0 + 2 * j + 1 < C::COUT_REAL ? c0 + 2 * j + 1 : 0;
-              float x0 = fmaxf(v[2 * j] * p.w_scale_inv + __ldg(p.bias + ca), 0.f);
-              float x1 = fmaxf(v[2 * j + 1] * p.w_scale_inv + __ldg(p.bias + cb), 0.f);
-              nnal_h h0, h1, l0, l1;
-              nnal_split(x0, h0, l0);
-              nnal_split(x1, h1, l1);
-              hi[j] = nnal_pack2(h0, h1);
-              lo[j] = nnal_pack2(l0, l1);
+              for (int j = 0; j < 16; ++j) w[j] = 0.f;
             }
-            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
-            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
-            dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            if (c0 + 8 < C::COUT_REAL) {                     // COUT_REAL is a multiple of 8
-              dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-              dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            if (valid) {
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int ca = c0 + 2 * j < C::COUT_REAL ? c0 + 2 * j : 0, cb = c0 + 2 * j + 1 < C::COUT_REAL ? c0 + 2 * j + 1 : 0;
+                float x0 = fmaxf((v[2 * j] + w[2 * j]) * p.w_scale_inv + __ldg(p.bias + ca), 0.f);
+                float x1 = fmaxf((v[2 * j + 1] + w[2 * j + 1]) * p.w_scale_inv + __ldg(p.bias + cb), 0.f);
+                nnal_h h0, h1, l0, l1;
+                nnal_split(x0, h0, l0);
+                nnal_split(x1, h1, l1);
+                hi[j] = nnal_pack2(h0, h1);
+                lo[j] = nnal_pack2(l0, l1);
+              }
+              uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
+              uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
+              dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              if (c0 + 8 < C::COUT_REAL) {                     // COUT_REAL is a multiple of 8
+                dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(a));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(a));
     }
   }
 
@@ -371,7 +420,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
   }
 }
 
-// W fp32 [kh][kw][cin][cout] -> packed bf16 [NSTAGE_W][hi|lo][KPS][2][COUT][8]
+// W fp32 [kh][kw][cin][cout] -> packed fp16 [NSTAGE_W][KPS][2 chunks][hi COUT rows | lo COUT rows][8]
 __global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int KS, int CIN, int COUT,
                                          int CIN_REAL, int COUT_REAL, int KPS, int NK, int NSTAGE, float scale) {
   const int NTAPS = KS * KS, Q = CIN / 8, NCH = NTAPS * Q;
@@ -382,9 +431,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* _
     int64_t t = e / 8;
     int co = t % COUT; t /= COUT;
     int half = t % 2; t /= 2;
-    int j = t % KPS;
-    int ws = (int)(t / KPS);
-    int ks = ws * KPS + j;
+    int ks = (int)t;                         // global K-step index (ws * KPS + j)
     int c = 2 * ks + half;
     float w = 0.f;
     if (ks < NK && c < NCH) {
@@ -394,10 +441,10 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* _
     }
     nnal_h h, l;
     nnal_split(w, h, l);
-    const int64_t stage_elems = (int64_t)2 * KPS * 2 * COUT * 8;            // hi block + lo block
-    const int64_t in_block = (((int64_t)j * 2 + half) * COUT + co) * 8 + k8;
-    o[ws * stage_elems + in_block] = h;
-    o[ws * stage_elems + (int64_t)KPS * 2 * COUT * 8 + in_block] = l;
+    const int64_t kstep_elems = (int64_t)2 * (2 * COUT) * 8;
+    const int64_t base = ks * kstep_elems + (int64_t)half * (2 * COUT) * 8;
+    o[base + (int64_t)co * 8 + k8] = h;
+    o[base + (int64_t)(COUT + co) * 8 + k8] = l;
   }
 }
 
@@ -430,11 +477,13 @@ static int make_act_tmap(nnal_ctx* ctx, CUtensorMap* tm, const void* ptr, int n,
   return NNAL_OK;
 }
 
-//                 H   W  CIN COUT KS G KPS NBUF NACC
-typedef Cfg<25, 25, 3, 24, 5, 1, 7, 2, 2> CfgConv1;       // PW1 conv1: 3 input channels zero-padded to one 8-channel chunk
-typedef Cfg<25, 25, 24, 32, 5, 1, 8, 2, 2> CfgConv2;      // PW1 conv2
-typedef Cfg<13, 13, 32, 48, 3, 2, 6, 2, 2> CfgConv3;      // PW1 conv3
-typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2> CfgConv4;      // PW1 conv4
+//                 H   W  CIN COUT KS G KPS NBUF TG CAT
+typedef Cfg<25, 25, 3, 24, 5, 1, 7, 2, 3, true> CfgConv1;     // PW1 conv1: 3 input channels zero-padded to one 8-channel chunk
+typedef Cfg<25, 25, 24, 32, 5, 1, 8, 2, 3, true> CfgConv2;    // PW1 conv2: 6 M tiles in 2 groups of 3
+// conv3/conv4: N is large enough that the concatenated form gains nothing and streaming the (larger) weight set
+// once per tile group would make conv4 L2-bound: one tile group, three MMAs per K-step
+typedef Cfg<13, 13, 32, 48, 3, 2, 6, 2, 4, false> CfgConv3;   // PW1 conv3: 2 samples, 4 M tiles
+typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2, false> CfgConv4;   // PW1 conv4: 2 M tiles
 
 template <class C>
 static bool matches(const Layer& L) {

@@ -27,6 +27,7 @@ class Engine(object):
         self.h = h
         self.device = device
         self._model_key = None
+        self._model_ref = None
         self._vol_keys = {}
         self._vol_refs = {}
         self._m = {}
@@ -117,8 +118,10 @@ class Engine(object):
         """Uploads ``model`` (an ``nnal_b200.NN.CNN``, or any object exposing ``layer_dict``,
         ``input_shape``, ``feature_layer_index`` and ``get_weights(sess)``) unless the same
         weights are already resident."""
-        key = (id(model), getattr(model, '_version', 0))
-        if key == self._model_key:
+        # the resident weights are reused only for the very same model OBJECT (a reference is kept, so its
+        # id cannot be recycled by a new object) at an unchanged weight version
+        key = getattr(model, '_version', 0)
+        if self._model_ref is model and key == self._model_key:
             return
         layers = list(model.layer_dict.items()) if isinstance(model.layer_dict, dict) else list(model.layer_dict)
         specs = (L.LayerSpec * len(layers))()
@@ -147,6 +150,7 @@ class Engine(object):
         self._chk(self.lib.nnal_model_info(self.h, C.byref(nc), C.byref(fd), C.byref(pd)))
         self.n_class, self.feat_dim, self.prev_dim = nc.value, fd.value, pd.value
         self._model_key = key
+        self._model_ref = model
 
     # ------------------------------------------------------------------
     # volumes
