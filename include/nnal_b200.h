@@ -100,6 +100,14 @@ int nnal_volume_clear(nnal_ctx* ctx);
 int nnal_gather(nnal_ctx* ctx, int subject, const int64_t* inds, int64_t n, int d1, int d2, int d3,
                 const double* stats, int norm_mode, double* out);
 
+/* Device-resident variants for the memory-bound full-volume path (PW_analyze_results.full_slice_eval
+ * PW_analyze_results.py:689-715 gathers every voxel of a slice; eval_utils.py:153-175 holds posteriors as
+ * [c,h,w,z]): d_inds / d_out / d_post are DEVICE pointers, float32 patches [n][d1][d2][m*d3] resp. a float32
+ * entropy map [n] from float32 posteriors [c][n] (zeros -> eps as compute_entropy). */
+int nnal_gather_device_f32(nnal_ctx* ctx, int subject, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
+                           const double* stats, int norm_mode, float* d_out);
+int nnal_entropy_device_f32(nnal_ctx* ctx, const float* d_post, int c, int64_t n, double eps, float* d_out);
+
 /* ---- pool pass: replaces PW_NN.batch_eval (PW_NN.py:357-539) + the TF forward --------------- */
 /* Declares a pool of n_total samples scored in this query round.  keep = 0: posteriors only; 1: also
  * model.feature_layer; 2: also the input of the feature layer's FC (needed for two-layer FI). */

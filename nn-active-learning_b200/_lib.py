@@ -36,6 +36,8 @@ SIGNATURES = {
                                   C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     'nnal_volume_clear': (C.c_int, [c_vp]),
     'nnal_gather': (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
+    'nnal_gather_device_f32': (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
+    'nnal_entropy_device_f32': (C.c_int, [c_vp, c_vp, C.c_int, C.c_int64, C.c_double, c_vp]),
     'nnal_pool_begin': (C.c_int, [c_vp, C.c_int64, C.c_int]),
     'nnal_pool_eval': (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, c_vp, C.c_int]),
     'nnal_pool_eval_images': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64]),

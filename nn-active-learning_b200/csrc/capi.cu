@@ -275,14 +275,27 @@ static int check_gather_args(nnal_ctx* ctx, int subject, int64_t n, int d1, int 
   return NNAL_OK;
 }
 
+// Uploads the per-modality normalisation table [m][3] = (mu, sigma, y): y = RN(1/sigma) drives the
+// correctly-rounded Markstein division of the gather kernels; y = NaN makes them fall back to a true division
+// (sigma zero / non-finite, or a significand of all ones, where the Markstein sequence is not proven).
 static int upload_stats(nnal_ctx* ctx, const double* stats, int m, int norm_mode, double** d_stats) {
   *d_stats = nullptr;
   if (norm_mode == NNAL_NORM_NONE) return NNAL_OK;
   if (!stats) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "normalisation requested without stats");
-  // stats live at the tail of the index buffer allocation (small)
-  static_assert(sizeof(double) == 8, "");
+  if ((size_t)m * 3 * sizeof(double) > 4096) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "too many modalities");
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // earlier async copies from stats_host must be done before it is rewritten
+  ctx->stats_host.resize((size_t)m * 3);
+  for (int j = 0; j < m; ++j) {
+    const double mu = stats[2 * j], sg = stats[2 * j + 1];
+    uint64_t bits;
+    memcpy(&bits, &sg, 8);
+    const bool ok = std::isfinite(sg) && sg != 0.0 && (bits & 0xfffffffffffffull) != 0xfffffffffffffull;
+    ctx->stats_host[3 * j] = mu;
+    ctx->stats_host[3 * j + 1] = sg;
+    ctx->stats_host[3 * j + 2] = ok ? 1.0 / sg : std::nan("");
+  }
   NNAL_TRY(devbuf_reserve(ctx, ctx->logits, 4096));
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->logits.p, stats, (size_t)m * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->logits.p, ctx->stats_host.data(), (size_t)m * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   *d_stats = (double*)ctx->logits.p;
   return NNAL_OK;
 }
@@ -295,7 +308,6 @@ extern "C" int nnal_gather(nnal_ctx* ctx, int subject, const int64_t* inds, int6
   NNAL_TRY(check_gather_args(ctx, subject, n, d1, d2, d3, &v));
   if (n == 0) return NNAL_OK;
   if (!inds || !out) return NNAL_ERR_INVALID;
-  if (v->m * 2 * 8 > 4096) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "too many modalities");
   double* d_stats;
   NNAL_TRY(upload_stats(ctx, stats, v->m, norm_mode, &d_stats));
   const int64_t per = (int64_t)d1 * d2 * d3 * v->m;
@@ -310,6 +322,34 @@ extern "C" int nnal_gather(nnal_ctx* ctx, int subject, const int64_t* inds, int6
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return NNAL_OK;
+}
+
+// device-resident variants (memory-bound path of config 4: full-volume patch gather, pixel-wise entropy map)
+extern "C" int nnal_gather_device_f32(nnal_ctx* ctx, int subject, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
+                                      const double* stats, int norm_mode, float* d_out) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const Volume* v;
+  NNAL_TRY(check_gather_args(ctx, subject, n, d1, d2, d3, &v));
+  if (n == 0) return NNAL_OK;
+  if (!d_inds || !d_out) return NNAL_ERR_INVALID;
+  double* d_stats;
+  NNAL_TRY(upload_stats(ctx, stats, v->m, norm_mode, &d_stats));
+  prof_begin(ctx, NNAL_PROF_GATHER);
+  int rc = nnal_k_gather_norm_f32(ctx, *v, d_inds, n, d1, d2, d3, d_stats, norm_mode, d_out);
+  prof_end(ctx);
+  return rc;
+}
+
+extern "C" int nnal_entropy_device_f32(nnal_ctx* ctx, const float* d_post, int c, int64_t n, double eps, float* d_out) {
+  if (!ctx || c <= 0 || n < 0) return NNAL_ERR_INVALID;
+  if (n == 0) return NNAL_OK;
+  if (!d_post || !d_out) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  prof_begin(ctx, NNAL_PROF_SCORE);
+  int rc = nnal_k_entropy_f32(ctx, d_post, c, n, (float)eps, d_out);
+  prof_end(ctx);
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,7 +394,8 @@ static int reserve_forward(nnal_ctx* ctx, int64_t nb) {
   }
   NNAL_TRY(devbuf_reserve(ctx, ctx->act[0], (size_t)nb * mx * sizeof(float)));
   NNAL_TRY(devbuf_reserve(ctx, ctx->act[1], (size_t)nb * mx * sizeof(float)));
-  NNAL_TRY(devbuf_reserve(ctx, ctx->xin, (size_t)nb * ctx->in_h * ctx->in_w * ctx->in_c * sizeof(float)));
+  // input staging: fp32 NHWC, or (fused gather) fp16 hi/lo planes padded to 8 channels
+  NNAL_TRY(devbuf_reserve(ctx, ctx->xin, (size_t)nb * ctx->in_h * ctx->in_w * std::max<size_t>((size_t)ctx->in_c * sizeof(float), 32)));
   return NNAL_OK;
 }
 
@@ -374,6 +415,8 @@ static int pool_eval_impl(nnal_ctx* ctx, int subject, const int64_t* inds, bool 
   NNAL_TRY(upload_stats(ctx, stats, v->m, norm_mode, &d_stats));
   const int64_t chunk = std::min(chunk_size(), n);
   NNAL_TRY(reserve_forward(ctx, chunk));
+  // gather straight into the first conv's tensor-core input planes when it takes them
+  const bool fused = nnal_first_layer_wants_split8(ctx) && nnal_k_gather_split_supported(*v, d3) && getenv("NNAL_NO_FUSED_GATHER") == nullptr;
   const int64_t* d_inds = inds;
   if (!inds_on_device) {
     NNAL_TRY(devbuf_reserve(ctx, ctx->inds, (size_t)n * 8));
@@ -383,9 +426,14 @@ static int pool_eval_impl(nnal_ctx* ctx, int subject, const int64_t* inds, bool 
   for (int64_t o = 0; o < n; o += chunk) {
     int64_t nb = std::min(chunk, n - o);
     prof_begin(ctx, NNAL_PROF_GATHER);
-    NNAL_TRY(nnal_k_gather_norm_f32(ctx, *v, d_inds + o, nb, d1, d2, d3, d_stats, norm_mode, (float*)ctx->xin.p));
+    if (fused) {
+      nnal_h* hi = (nnal_h*)ctx->xin.p;
+      NNAL_TRY(nnal_k_gather_split(ctx, *v, d_inds + o, nb, d1, d2, d3, stats, norm_mode, hi, hi + (size_t)nb * d1 * d2 * 8));
+    } else {
+      NNAL_TRY(nnal_k_gather_norm_f32(ctx, *v, d_inds + o, nb, d1, d2, d3, d_stats, norm_mode, (float*)ctx->xin.p));
+    }
     prof_end(ctx);
-    NNAL_TRY(nnal_forward_chunk(ctx, nb, offset + o));
+    NNAL_TRY(nnal_forward_chunk(ctx, nb, offset + o, fused));
   }
   return NNAL_OK;
 }

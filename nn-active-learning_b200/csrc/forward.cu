@@ -36,11 +36,23 @@ bool consumer_wants_split(const nnal_ctx* ctx, int i) {
 
 bool nnal_layer_on_tc(const nnal_ctx* ctx, int i) { return layer_on_tc(ctx, i); }
 
-int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset) {
+bool nnal_first_layer_wants_split8(const nnal_ctx* ctx) {
+  if (ctx->layers.empty()) return false;
+  const Layer& L = ctx->layers[0];
+  return L.type == NNAL_LAYER_CONV && L.in_c % 8 != 0 && L.in_c <= 8 && layer_on_tc(ctx, 0);
+}
+
+int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset, bool input_is_split8) {
   const int nl = (int)ctx->layers.size();
   Act cur;
   cur.f32 = (float*)ctx->xin.p;
   cur.elems = (int64_t)ctx->in_h * ctx->in_w * ctx->in_c;
+  if (input_is_split8) {                  // the fused gather already wrote the first conv's 8-channel hi/lo planes
+    cur.elems = (int64_t)ctx->in_h * ctx->in_w * 8;
+    cur.hi = (nnal_h*)ctx->xin.p;
+    cur.lo = cur.hi + nb * cur.elems;
+    cur.split = true;
+  }
   int pp = 0;
   auto next_buf = [&](int64_t elems, Act& o) {
     // both formats occupy 4 bytes per element: fp32, or a bf16 hi plane followed by a bf16 lo plane
@@ -78,7 +90,9 @@ int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset) {
     if (L.type == NNAL_LAYER_CONV) {
       const int64_t oe = (int64_t)L.out_h * L.out_w * L.out_c;
       if (layer_on_tc(ctx, i)) {
-        if (L.in_c % 8 != 0) {
+        if (i == 0 && input_is_split8) {
+          // nothing to do: planes come from the gather
+        } else if (L.in_c % 8 != 0) {
           // the tensor-core conv consumes whole 8-channel chunks: zero-pad the channels while splitting
           NNAL_TRY(to_f32(cur));
           const int cp = (L.in_c + 7) / 8 * 8;

@@ -84,6 +84,7 @@ struct nnal_ctx {
   // volumes
   std::vector<Volume> vols;
   DevBuf stage;                          // upload staging
+  std::vector<double> stats_host;        // normalisation table being uploaded (mu, sigma, 1/sigma per modality)
   // workspaces
   DevBuf inds, act[2], xin, featbuf, prevbuf, logits;
   DevBuf splitA[2];                      // bf16 hi/lo activation planes
@@ -160,6 +161,9 @@ int nnal_k_gather_f64(nnal_ctx*, const Volume&, const int64_t* d_inds, int64_t n
                       const double* d_stats, int norm_mode, double* d_out);
 int nnal_k_gather_norm_f32(nnal_ctx*, const Volume&, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
                            const double* d_stats, int norm_mode, float* d_out);
+bool nnal_k_gather_split_supported(const Volume&, int d3);
+int nnal_k_gather_split(nnal_ctx*, const Volume&, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
+                        const double* h_stats, int norm_mode, nnal_h* out_hi, nnal_h* out_lo);
 // forward_simt.cu
 int nnal_k_conv_simt(nnal_ctx*, const Layer&, const float* in, float* out, int64_t n);
 int nnal_k_pool(nnal_ctx*, const Layer&, const float* in, float* out, int64_t n);
@@ -170,6 +174,7 @@ int nnal_k_head(nnal_ctx*, const Layer& fc_last, const float* feat, int64_t n, i
                 float* post /*[c][pool_n]*/, float* logits_out /*[n][c] or null*/);
 int nnal_k_scores_f32(nnal_ctx*, const float* post, int c, int64_t n, int kind, double eps, double* score);
 int nnal_k_scores_f64(nnal_ctx*, const double* post, int c, int64_t n, int kind, double eps, double* score);
+int nnal_k_entropy_f32(nnal_ctx*, const float* post, int c, int64_t n, float eps, float* H);
 int nnal_k_topk(nnal_ctx*, const double* score, int64_t n, int64_t k, int64_t* d_idx_out, double* d_score_out);
 // gemm_tc.cu / conv_tc.cu (tcgen05 path)
 int nnal_tc_prepare_layer(nnal_ctx*, Layer&);
@@ -190,6 +195,7 @@ int nnal_tc_conv(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_
 int nnal_k_conv_simt_split(nnal_ctx*, const Layer&, const float* in, nnal_h* out_hi, nnal_h* out_lo, int64_t n);
 int nnal_k_pool_split(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
                       nnal_h* out_lo, int64_t n);
-int nnal_forward_chunk(nnal_ctx*, int64_t nb, int64_t offset);
+int nnal_forward_chunk(nnal_ctx*, int64_t nb, int64_t offset, bool input_is_split8 = false);
+bool nnal_first_layer_wants_split8(const nnal_ctx*);
 // fi.cu
 int nnal_k_fi_trace_scores(nnal_ctx*, const float* post, int c, int64_t n, const float* feat, int d, double* score);

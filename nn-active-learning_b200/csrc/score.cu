@@ -133,6 +133,51 @@ int nnal_k_scores_f64(nnal_ctx* ctx, const double* post, int c, int64_t n, int k
 }
 
 // ------------------------------------------------------------------------------------------
+// pixel-wise entropy map in float32 (config 4: posteriors [c][n] float32 -> H [n] float32, the shape of
+// eval_utils.full_slice_segment's [c,h,w,z] tensor): -sum_c p log p with the compute_entropy zero guard.
+// Memory-bound: (c+1)*4 B per sample; 4 samples per thread, 16-byte loads/stores when n % 4 == 0.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) entropy_f32_kernel(const float* __restrict__ post, int c, int64_t n, float eps,
+                                                           float* __restrict__ H) {
+  const int64_t nv = n >> 2;
+  const bool vec = (n & 3) == 0;
+  if (vec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < c; ++j) {
+        float4 p = __ldcs(reinterpret_cast<const float4*>(post + (int64_t)j * n) + i);
+        p.x = p.x == 0.f ? eps : p.x; p.y = p.y == 0.f ? eps : p.y; p.z = p.z == 0.f ? eps : p.z; p.w = p.w == 0.f ? eps : p.w;
+        h.x = fmaf(-p.x, logf(p.x), h.x); h.y = fmaf(-p.y, logf(p.y), h.y);
+        h.z = fmaf(-p.z, logf(p.z), h.z); h.w = fmaf(-p.w, logf(p.w), h.w);
+      }
+      __stcs(reinterpret_cast<float4*>(H) + i, h);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      float h = 0.f;
+      for (int j = 0; j < c; ++j) {
+        float p = post[(int64_t)j * n + i];
+        p = p == 0.f ? eps : p;
+        h = fmaf(-p, logf(p), h);
+      }
+      H[i] = h;
+    }
+  }
+}
+
+int nnal_k_entropy_f32(nnal_ctx* ctx, const float* post, int c, int64_t n, float eps, float* H) {
+  if (n == 0) return NNAL_OK;
+  // one 16-byte column group per thread: every load of the map is in flight at once
+  int64_t blocks = ((n + 3) / 4 + 255) / 256;
+  if ((n & 3) != 0) blocks = (n + 255) / 256;
+  int grid = (int)(blocks < (int64_t)0x7fffffff ? blocks : (int64_t)0x7fffffff);
+  entropy_f32_kernel<<<grid, 256, 0, ctx->stream>>>(post, c, n, eps, H);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // exact top-k (k smallest scores, ties -> lowest position): 8-pass MSB radix select on
 // order-preserving 64-bit keys, stable tie compaction, bitonic sort of the k survivors.
 // ------------------------------------------------------------------------------------------

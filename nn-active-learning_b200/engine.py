@@ -223,6 +223,18 @@ class Engine(object):
         self.set_volume(subject, imgs, pads)
         self._m[subject] = len(imgs)
 
+    def gather_device(self, subject, d_inds_ptr, n, patch_shape, stats, norm_mode, d_out_ptr):
+        """float32 patches of ``n`` voxels (int64 DEVICE indices) into a DEVICE buffer [n,d1,d2,m*d3]."""
+        d1, d2, d3 = [int(p) for p in patch_shape]
+        st = None if stats is None else np.ascontiguousarray(stats, dtype=np.float64)
+        self._chk(self.lib.nnal_gather_device_f32(self.h, int(subject), C.c_void_p(int(d_inds_ptr)), int(n), d1, d2, d3,
+                                                  None if st is None else _ptr(st), int(norm_mode), C.c_void_p(int(d_out_ptr))))
+
+    def entropy_device(self, d_post_ptr, c, n, eps, d_out_ptr):
+        """float32 entropy map [n] from float32 posteriors [c,n], both in device memory."""
+        self._chk(self.lib.nnal_entropy_device_f32(self.h, C.c_void_p(int(d_post_ptr)), int(c), int(n), float(eps),
+                                                   C.c_void_p(int(d_out_ptr))))
+
     # ------------------------------------------------------------------
     # pool pass
     # ------------------------------------------------------------------

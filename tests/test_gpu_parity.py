@@ -250,3 +250,66 @@ def test_conv_tcgen05_vs_f64(nb, H, Cin, Cout, ks, n):
     got_tc = eng.debug_conv(x, W, b, 1)
     err = np.abs(got_tc - ref).max() / scale
     assert err < 3e-5, 'tcgen05 conv off by %g (relative to max)' % err
+
+
+# ------------------------------------------------------------------ fused gather / device-resident paths
+def test_fused_gather_matches_unfused(nb):
+    """The gather that writes conv1's fp16 hi/lo planes directly must give the same posteriors as the
+    fp32 gather + split pass it replaces (bit-identical: same float64 normalisation, same split)."""
+    import os
+    ps, imgs, padded, stats, pool, layers, w = _pw_setup(300, 44)
+    model = nb.NN.create_PW1(2)
+    model.set_weights(w)
+    a = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
+    os.environ['NNAL_NO_FUSED_GATHER'] = '1'
+    try:
+        b = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
+    finally:
+        del os.environ['NNAL_NO_FUSED_GATHER']
+    assert np.array_equal(a, b)
+
+
+def test_device_gather_and_entropy_map(nb):
+    import torch
+    ps = (25, 25, 1)
+    imgs = synth_volume((30, 28, 5), 3, 3)
+    padded = pad_imgs(imgs, ps)
+    stats = vol_stats(imgs)
+    eng = nb.get_engine()
+    eng.upload(0, padded)
+    inds = np.random.RandomState(0).choice(30 * 28 * 5, 500, replace=False).astype(np.int64)
+    d_inds = torch.from_numpy(inds).cuda()
+    out = torch.empty((500, 25, 25, 3), dtype=torch.float32, device='cuda')
+    for norm in (0, 1):
+        eng.gather_device(0, d_inds.data_ptr(), 500, ps, np.array(stats), norm, out.data_ptr())
+        eng.synchronize()
+        ref = O.get_patches(padded, inds, ps)
+        if norm:
+            ref = O.normalize_batch_eval(ref, stats)
+        assert np.array_equal(out.cpu().numpy(), ref.astype(np.float32))      # float32(float64 arithmetic): bit-exact
+    for n in (1000, 1003):
+        rs = np.random.RandomState(n)
+        z = rs.randn(3, n)
+        p = (np.exp(z) / np.exp(z).sum(0)).astype(np.float32)
+        p[0, 5] = 0.
+        dp = torch.from_numpy(p).cuda()
+        H = torch.empty(n, dtype=torch.float32, device='cuda')
+        eng.entropy_device(dp.data_ptr(), 3, n, 10e-8, H.data_ptr())
+        eng.synchronize()
+        ref = O.compute_entropy(p.astype(np.float64).copy())
+        assert np.allclose(H.cpu().numpy(), ref, rtol=1e-3, atol=1e-7)        # north star: entropy within 1e-3 relative
+
+
+def test_normalisation_division_is_ieee(nb):
+    """Markstein's correctly-rounded division in the gather == numpy's float64 division, incl. awkward sigmas."""
+    rs = np.random.RandomState(9)
+    imgs = [(rs.rand(20, 18, 3) * 1000).astype(np.float32) for _ in range(3)]
+    padded = pad_imgs(imgs, (5, 5, 1))
+    S = np.zeros((1, 6))
+    for j, sg in enumerate([1. / 3., 30.000000000000004, np.nextafter(2.0, 0)]):       # last: all-ones significand
+        S[0, 2 * j], S[0, 2 * j + 1] = 100. / 7. * (j + 1), sg
+    allp = [padded + [np.zeros((20, 18, 3), np.int8)]]
+    inds = [list(rs.choice(20 * 18 * 3, 400, replace=False))]
+    got, _ = nb.patch_utils.get_patches_multimg(allp, inds, (5, 5, 1), S)
+    ref, _ = O.get_patches_multimg(allp, inds, (5, 5, 1), S)
+    assert np.array_equal(got[0], ref[0])
