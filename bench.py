@@ -83,6 +83,21 @@ def make_workload(pool_total, seed_pool=3, pinned=False):
     return padded, stats, pool
 
 
+def workload_config(args, world):
+    return {'workload': 'config2: PW1 2-class CNN, 3x 256x256x180 f32 volumes, 25x25x3 patches, '
+                        '%d-patch pool per GPU, entropy query k=100' % args.pool,
+            'pool_per_gpu': args.pool, 'k': 100, 'parallelism': 'pool sharded x%d' % world,
+            'l2': 'inputs larger than L2 (volumes 169 MB + >600 MB activations per chunk)',
+            'forward_gflop_per_step_per_gpu': PW1_MFLOP * args.pool / 1e3}
+
+
+def load_traffic():
+    """DRAM bytes per sample of each kernel class, from the committed ncu --set full capture
+    (profiles/r1_traffic.json, written by scripts/summarize_ncu.py traffic)."""
+    p = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def pw1_weights():
     import oracle as O
     layers = O.pw1_layers(2)
@@ -171,9 +186,7 @@ def run_reference(args, rank, world):
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'config2: PW1 2-class CNN, 3x 256x256x180 volumes, 25x25x3 patches, '
-                                   '%d-patch pool/GPU, entropy query k=100' % args.pool,
-                       'pool_per_gpu': args.pool, 'k': 100},
+            'config': workload_config(args, world),
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': desc},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -297,16 +310,21 @@ def run_ours(args, rank, world):
         flops = 2.0 * tinfo['macs_per_sample'] * samples_per_launch
         achieved = flops / (per_launch_ms * 1e-3) / 1e12
         peak = peaks['bf16_sustained']
+        tr = load_traffic().get(top)
         roofline = {'kernel': top, 'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                    'frac': achieved / peak, 'traffic': None,
+                    'frac': achieved / peak,
+                    'traffic': None if tr is None else tr['dram_bytes_per_sample'] * samples_per_launch,
                     'note': 'algorithmic FLOPs (2*MACs) per launch / mean launch time; peak = %s sustained bf16; '
                             '%s' % (peaks['source'], 'tcgen05 fp16 hi/lo split executes 3x these FLOPs'
                                     if tinfo['tc'] else 'FP32 CUDA-core kernel (no tensor pipe)')}
     else:
         bytes_per = {'gather': 15008.0, 'score': 12.0, 'topk': 4.0}[top]
         achieved = bytes_per * samples_per_launch / (per_launch_ms * 1e-3) / 1e9
+        tr = load_traffic().get(top)
         roofline = {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                    'frac': achieved / peaks['hbm_gbs'], 'traffic': None, 'note': 'peak = %s copy bandwidth' % peaks['source']}
+                    'frac': achieved / peaks['hbm_gbs'],
+                    'traffic': None if tr is None else tr['dram_bytes_per_sample'] * samples_per_launch,
+                    'note': 'peak = %s copy bandwidth' % peaks['source']}
     stage_ms = {kk: round(v['ms'] / args.steps, 4) for kk, v in classes.items()}
 
     # ---------------- CPU baseline (bounded sample, rank 0, N=1 only) ----------------
@@ -321,11 +339,7 @@ def run_ours(args, rank, world):
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f16x3 (fp16 hi/lo split operands, 3 tcgen05 MMAs per product, fp32 accumulate) + f32/f64 scoring',
             'data': 'synthetic',
-            'config': {'workload': 'config2: PW1 2-class CNN, 3x 256x256x180 f32 volumes, 25x25x3 patches, '
-                                   '%d-patch pool per GPU, entropy query k=100' % args.pool,
-                       'pool_per_gpu': args.pool, 'k': k, 'parallelism': 'pool sharded x%d' % world,
-                       'l2': 'inputs larger than L2 (volumes 169 MB + >600 MB activations per chunk)',
-                       'forward_gflop_per_step_per_gpu': PW1_MFLOP * args.pool / 1e3},
+            'config': workload_config(args, world),
             'clocks': clocks, 'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': 1e3 * e2e_s / args.steps,

@@ -181,6 +181,17 @@ int nnal_fi_winner_factors(nnal_ctx* ctx, int64_t step, int64_t cand, float* fac
 int nnal_fi_step_apply(nnal_ctx* ctx, int64_t step, const float* winner_factors, int64_t n_floats, int owner_is_local,
                        int64_t cand_local);
 
+/* Device-resident form of the same step (no host round trip inside the loop): every rank packs its local best
+ * into a fixed-size message in DEVICE memory (nnal_fi_msg_bytes), the host layer all-gathers the messages with
+ * NCCL on nnal_stream(), and every rank applies the global winner (min loss, ties -> lowest global id) from the
+ * gathered buffer [world][msg_bytes].  nnal_fi_set_gids gives the global ids of the local candidates (NULL:
+ * local index); nnal_fi_result reads the selected global ids and the reduced objective per step. */
+int nnal_fi_set_gids(nnal_ctx* ctx, const int64_t* gids, int64_t n);
+int nnal_fi_msg_bytes(nnal_ctx* ctx, int64_t* bytes);
+int nnal_fi_step_pack(nnal_ctx* ctx, int64_t step, void* d_msg);
+int nnal_fi_step_apply_gathered(nnal_ctx* ctx, int64_t step, const void* d_msgs, int world, int rank);
+int nnal_fi_result(nnal_ctx* ctx, int64_t k, int64_t* gids_out, double* red_out);
+
 /* ---- test hook ---------------------------------------------------------------------------- */
 /* One FC layer out[M][N] = act(A[M][K] W[N][K]^T + b) on host buffers, on the tcgen05 GEMM
  * (use_tc=1) or the FP32 CUDA-core GEMM (use_tc=0); lets tests check the kernels in isolation. */

@@ -63,6 +63,11 @@ SIGNATURES = {
     'nnal_fi_begin': (C.c_int, [c_vp, C.c_int64, C.c_double]),
     'nnal_fi_step_local_best': (C.c_int, [c_vp, C.c_int64, c_f64p, c_i64p, c_f64p]),
     'nnal_fi_winner_factors': (C.c_int, [c_vp, C.c_int64, C.c_int64, c_vp, c_i64p]),
+    'nnal_fi_set_gids': (C.c_int, [c_vp, c_vp, C.c_int64]),
+    'nnal_fi_msg_bytes': (C.c_int, [c_vp, c_i64p]),
+    'nnal_fi_step_pack': (C.c_int, [c_vp, C.c_int64, c_vp]),
+    'nnal_fi_step_apply_gathered': (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int, C.c_int]),
+    'nnal_fi_result': (C.c_int, [c_vp, C.c_int64, c_vp, c_vp]),
     'nnal_fi_step_apply': (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int64, C.c_int, C.c_int64]),
 }
 

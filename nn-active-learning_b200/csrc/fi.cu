@@ -47,6 +47,9 @@ struct State {
   const float* A = nullptr;
   int64_t* rows = nullptr;
   bool use_rows = false;
+  long long* gids = nullptr;             // global candidate ids of the local candidates (multi-rank); null = identity
+  int64_t gids_cap = 0;
+  bool use_gids = false;
   const int64_t* R() const { return use_rows ? rows : nullptr; }
   float *ownU = nullptr, *ownA = nullptr;
   int64_t own_cap_u = 0, own_cap_a = 0;
@@ -513,6 +516,74 @@ __global__ void __launch_bounds__(256) pick_kernel(const double* __restrict__ bl
 
 __global__ void mark_taken_kernel(unsigned char* avail, long long idx) { avail[idx] = 0; }
 
+// ---- device-resident multi-rank step: every rank packs its local best into a fixed-size message, the messages
+// of all ranks are all-gathered (NCCL, on this stream), and every rank applies the global winner -- no host
+// round trip inside the greedy loop.
+//   message = [ loss f64 | gid i64 | sqrt(w) f64 | reserved f64 | K_SS row: kcap f64 | u: d f32 | a: d_prev f32 ]
+struct MsgHeader { double loss; long long gid; double sw; double reserved; };
+
+__global__ void __launch_bounds__(256) pack_msg_kernel(const float* __restrict__ U, const float* __restrict__ A,
+                                                        const int64_t* __restrict__ rows, const long long* __restrict__ gids,
+                                                        const double* __restrict__ sw, const double* __restrict__ diag,
+                                                        const double* __restrict__ kcols, int64_t kn, const DevScalars* __restrict__ sc,
+                                                        int t, int kcap, int d, int dp, int have_cands, unsigned char* __restrict__ msg) {
+  MsgHeader* h = reinterpret_cast<MsgHeader*>(msg);
+  double* row = reinterpret_cast<double*>(msg + sizeof(MsgHeader));
+  float* fu = reinterpret_cast<float*>(msg + sizeof(MsgHeader) + (size_t)kcap * 8);
+  float* fa = fu + d;
+  const long long i = have_cands ? sc->best_idx : -1;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (i < 0) {
+    if (tid == 0) { h->loss = INFINITY; h->gid = 0x7fffffffffffffffll; h->sw = 0.0; h->reserved = 0.0; }
+    return;
+  }
+  const int64_t r = rows ? rows[i] : i;
+  for (int k = tid; k < d; k += nt) fu[k] = U[r * d + k];
+  if (A)
+    for (int k = tid; k < dp; k += nt) fa[k] = A[r * dp + k];
+  for (int a = tid; a <= t; a += nt) row[a] = a < t ? kcols[(int64_t)a * kn + i] : diag[i];
+  if (tid == 0) { h->loss = sc->best_loss; h->gid = gids ? gids[i] : i; h->sw = sw[i]; h->reserved = 0.0; }
+}
+
+// picks the global winner among `world` messages (min loss, ties -> lowest global id), fills the winner slot,
+// extends K_SS, records the selection; the owner removes the winner from its candidate set.
+__global__ void __launch_bounds__(256) apply_msgs_kernel(const unsigned char* __restrict__ msgs, size_t msg_bytes, int world, int rank,
+                                                          int t, int kcap, int d, int dp, DevScalars* sc,
+                                                          unsigned char* __restrict__ avail, float* __restrict__ win_u,
+                                                          float* __restrict__ win_a, double* __restrict__ win_sw,
+                                                          double* __restrict__ kss, long long* __restrict__ sel,
+                                                          double* __restrict__ red) {
+  int best = 0;
+  double bl = INFINITY;
+  long long bg = 0x7fffffffffffffffll;
+  for (int r = 0; r < world; ++r) {
+    const MsgHeader* h = reinterpret_cast<const MsgHeader*>(msgs + (size_t)r * msg_bytes);
+    const double l = h->loss;
+    const long long g = h->gid;
+    if (l < bl || (l == bl && g < bg)) { bl = l; bg = g; best = r; }
+  }
+  const unsigned char* m = msgs + (size_t)best * msg_bytes;
+  const MsgHeader* h = reinterpret_cast<const MsgHeader*>(m);
+  const double* row = reinterpret_cast<const double*>(m + sizeof(MsgHeader));
+  const float* fu = reinterpret_cast<const float*>(m + sizeof(MsgHeader) + (size_t)kcap * 8);
+  const float* fa = fu + d;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int k = tid; k < d; k += nt) win_u[k] = fu[k];
+  if (win_a)
+    for (int k = tid; k < dp; k += nt) win_a[k] = fa[k];
+  for (int a = tid; a <= t; a += nt) {
+    const double v = row[a];
+    kss[(int64_t)t * kcap + a] = v;
+    kss[(int64_t)a * kcap + t] = v;
+  }
+  if (tid == 0) {
+    *win_sw = h->sw;
+    sel[t] = bl < INFINITY ? bg : -1;
+    red[t] = (double)(t + 1) * ((t == 0 ? 0.0 : sc->trC) + bl);
+    if (best == rank && bl < INFINITY) avail[sc->best_idx] = 0;
+  }
+}
+
 // ---- closed-form trace score  -(1 - |pi|^2)(|u|^2 + 1)  (NNAL.py:124-139; negated: top-k takes the smallest)
 __global__ void __launch_bounds__(256) trace_score_kernel(const float* __restrict__ post, int c, int64_t n,
                                                            const float* __restrict__ feat, int d, double* __restrict__ score) {
@@ -727,7 +798,7 @@ using fi::State;
 int nnal_fi_release(nnal_ctx* ctx) {
   if (!ctx->fi_state) return NNAL_OK;
   State* s = (State*)ctx->fi_state;
-  void* ptrs[] = {s->rows, s->ownU, s->ownA, s->w, s->sw, s->diag, s->avail, s->beta2, s->kcols, s->kss, s->C, s->inv_ws,
+  void* ptrs[] = {s->gids, s->rows, s->ownU, s->ownA, s->w, s->sw, s->diag, s->avail, s->beta2, s->kcols, s->kss, s->C, s->inv_ws,
                   s->red, s->win_sw, s->win_u, s->win_a, s->sel, s->blk_loss, s->blk_idx, s->sc, s->H, s->Xh, s->Xl, s->wq};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete s;
@@ -933,6 +1004,78 @@ extern "C" int nnal_fi_step_apply(nnal_ctx* ctx, int64_t step, const float* winn
   }
   NNAL_TRY(fi::step_column(ctx, s, t));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // winner_factors is caller-owned host memory
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_set_gids(nnal_ctx* ctx, const int64_t* gids, int64_t n) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  State* s = (State*)ctx->fi_state;
+  if (n != s->n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "one global id per local candidate expected");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  s->use_gids = gids != nullptr;
+  if (gids && n) {
+    if (s->gids_cap < n) { NNAL_TRY(fi::ensure(ctx, s->gids, 0, (size_t)n)); s->gids_cap = n; }
+    CUDA_TRY(ctx, cudaMemcpyAsync(s->gids, gids, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_msg_bytes(nnal_ctx* ctx, int64_t* bytes) {
+  if (!ctx || !bytes) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  State* s = (State*)ctx->fi_state;
+  if (s->kcap <= 0) NNAL_FAIL(ctx, NNAL_ERR_STATE, "nnal_fi_begin not called");
+  size_t b = sizeof(fi::MsgHeader) + (size_t)s->kcap * 8 + ((size_t)s->d + s->dp) * 4;
+  *bytes = (int64_t)((b + 15) / 16 * 16);
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_step_pack(nnal_ctx* ctx, int64_t step, void* d_msg) {
+  if (!ctx || !d_msg || step < 0) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  State* s = (State*)ctx->fi_state;
+  if (step >= s->kcap) NNAL_FAIL(ctx, NNAL_ERR_STATE, "nnal_fi_begin not called with a large enough k");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int t = (int)step;
+  if (s->n > 0) NNAL_TRY(fi::step_select(ctx, s, t, 0));
+  else if (t > 0) NNAL_TRY(fi::run_invert(ctx, s, t));
+  fi::pack_msg_kernel<<<8, 256, 0, ctx->stream>>>(s->U, s->A, s->R(), s->use_gids ? s->gids : nullptr, s->sw, s->diag, s->kcols,
+                                                 s->kcols_n, s->sc, t, (int)s->kcap, s->d, s->dp, s->n > 0 ? 1 : 0,
+                                                 (unsigned char*)d_msg);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_step_apply_gathered(nnal_ctx* ctx, int64_t step, const void* d_msgs, int world, int rank) {
+  if (!ctx || !d_msgs || step < 0 || world <= 0 || rank < 0 || rank >= world) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  State* s = (State*)ctx->fi_state;
+  if (step >= s->kcap) NNAL_FAIL(ctx, NNAL_ERR_STATE, "nnal_fi_begin not called with a large enough k");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int64_t mb;
+  NNAL_TRY(nnal_fi_msg_bytes(ctx, &mb));
+  const int t = (int)step;
+  fi::apply_msgs_kernel<<<8, 256, 0, ctx->stream>>>((const unsigned char*)d_msgs, (size_t)mb, world, rank, t, (int)s->kcap, s->d, s->dp,
+                                                   s->sc, s->avail, s->win_u, s->nl == 2 ? s->win_a : nullptr, s->win_sw, s->kss,
+                                                   s->sel, s->red);
+  ctx->launches++;
+  NNAL_TRY(fi::step_column(ctx, s, t));
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_result(nnal_ctx* ctx, int64_t k, int64_t* gids_out, double* red_out) {
+  if (!ctx || k < 0 || !gids_out) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  State* s = (State*)ctx->fi_state;
+  if (k > s->kcap) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "more steps requested than were run");
+  if (k == 0) return NNAL_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaMemcpyAsync(gids_out, s->sel, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (red_out) CUDA_TRY(ctx, cudaMemcpyAsync(red_out, s->red, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return NNAL_OK;
 }
 

@@ -377,6 +377,32 @@ class Engine(object):
         self._chk(self.lib.nnal_fi_winner_factors(self.h, int(step), 0, None, C.byref(nf)))
         return nf.value
 
+    # device-resident multi-rank step (messages live in device memory; the caller all-gathers them)
+    def fi_set_gids(self, gids):
+        gids = np.ascontiguousarray(gids, dtype=np.int64).ravel()
+        self.h2d_bytes += gids.nbytes
+        self._chk(self.lib.nnal_fi_set_gids(self.h, _ptr(gids) if gids.size else None, gids.size))
+
+    def fi_msg_bytes(self):
+        b = C.c_int64()
+        self._chk(self.lib.nnal_fi_msg_bytes(self.h, C.byref(b)))
+        return b.value
+
+    def fi_step_pack(self, step, d_msg_ptr):
+        self._chk(self.lib.nnal_fi_step_pack(self.h, int(step), C.c_void_p(int(d_msg_ptr))))
+
+    def fi_step_apply_gathered(self, step, d_msgs_ptr, world, rank):
+        self._chk(self.lib.nnal_fi_step_apply_gathered(self.h, int(step), C.c_void_p(int(d_msgs_ptr)), int(world), int(rank)))
+
+    def fi_result(self, k):
+        sel = np.empty(int(k), dtype=np.int64)
+        red = np.empty(int(k), dtype=np.float64)
+        self.d2h_bytes += sel.nbytes + red.nbytes
+        self._chk(self.lib.nnal_fi_result(self.h, int(k), _ptr(sel), _ptr(red)))
+        return sel, red
+
+    message_device = 'cuda'
+
     def fi_step_apply(self, step, factors, owner_is_local, cand_local):
         factors = np.ascontiguousarray(factors, dtype=np.float32)
         self.h2d_bytes += factors.nbytes

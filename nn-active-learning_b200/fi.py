@@ -14,6 +14,8 @@ pre-filter to B (:108-115, 549-551), conditional FIs of the B candidates, select
 ``expr.pars`` keys read: ``k``, ``B`` (reference keys) and the optional ``fi_layers`` (1 or 2) and
 ``fi_diag_load`` (the reference's ``diag_load``: 1e-5 single-volume PW_NNAL.py:738-745, 1e-3 multi-volume
 :573-578)."""
+import contextlib
+
 import numpy as np
 
 from . import _lib as L
@@ -24,9 +26,9 @@ from .engine import get_engine
 def greedy_select(eng, k, delta, gids=None):
     """Greedy FI selection over the engine's current candidate set.
 
-    Single process: one device-side loop (``nnal_fi_greedy``).  Several ranks: every step combines the
-    ranks' local best candidates (all-gather of one (loss, id) pair), the owner broadcasts its winner's
-    factor vector and every rank applies the same rank-one update.  ``gids``: global candidate ids of
+    Single process: one device-side loop (``nnal_fi_greedy``).  Several ranks: every step all-gathers one
+    fixed-size message per rank (its local best: loss, id, factor rows, K_SS row) and every rank applies the
+    same global winner.  ``gids``: global candidate ids of
     this rank's candidates (ascending), used for the result and for tie-breaking (lowest id).
     Returns (selected global ids in selection order, objective after each step)."""
     n_local = eng.fi_info()['n']
@@ -36,24 +38,31 @@ def greedy_select(eng, k, delta, gids=None):
         sel, obj, _ = eng.fi_greedy(k, delta)
         return gids[sel], obj
     import torch
+    import torch.distributed as td
     rank, world = dist.rank_world()
     n_total = int(dist.allreduce_sum_(torch.tensor([n_local], dtype=torch.int64, device=dist._device())).item())
     k = min(int(k), n_total)
+    if k == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0)
     D = eng.fi_info()['D']
-    eng.fi_begin(max(k, 1), delta)
-    sel, obj = [], []
-    none = float(np.iinfo(np.int64).max >> 12)
-    for t in range(k):
-        loss, cand, trc = eng.fi_step_local_best(t)
-        gid = float(gids[cand]) if cand >= 0 else none
-        val, payload, owner = dist.allreduce_argmin(loss, gid)
-        mine = (owner == rank)
-        f = eng.fi_winner_factors(t, cand) if mine else np.zeros(eng.fi_factor_len(t), dtype=np.float32)
-        f = dist.broadcast_array(f, owner)
-        eng.fi_step_apply(t, f, mine, cand if mine else 0)
-        sel.append(int(payload))
-        obj.append((D - (t + 1)) / delta + (t + 1) * (trc + val))
-    return np.array(sel, dtype=np.int64), np.array(obj)
+    eng.fi_begin(k, delta)
+    eng.fi_set_gids(gids)
+    # Device-resident loop: per step every rank packs its local best (loss, id, factor rows, K_SS row) into a
+    # fixed-size message, the messages are all-gathered on the engine's stream and every rank applies the
+    # global winner -- the host only enqueues.
+    nbytes = eng.fi_msg_bytes()
+    dev = eng.message_device
+    send = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    recv = torch.zeros(world * nbytes, dtype=torch.uint8, device=dev)
+    ctx = torch.cuda.stream(torch.cuda.ExternalStream(eng.stream)) if dev == 'cuda' else contextlib.nullcontext()
+    with ctx:
+        for t in range(k):
+            eng.fi_step_pack(t, send.data_ptr())
+            td.all_gather_into_tensor(recv, send)
+            eng.fi_step_apply_gathered(t, recv.data_ptr(), world, rank)
+    sel, red = eng.fi_result(k)
+    s = np.arange(1, k + 1, dtype=np.float64)
+    return sel, (D - s) / delta + red
 
 
 def _pars(expr, default_delta):

@@ -67,8 +67,48 @@ def report(path, pattern=None):
         print()
 
 
+def traffic(path, samples_per_launch):
+    """DRAM bytes per sample of each forward kernel class (ncu --set full capture of one chunk) as JSON."""
+    import json
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                         text=True).stdout
+    rd = list(csv.reader(io.StringIO(out)))
+    hdr, units = rd[0], rd[1]
+    u = dict(zip(hdr, units))
+    scale = {'byte': 1., 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    res, nfc = {}, 0
+    for row in rd[2:]:
+        d = dict(zip(hdr, row))
+        name = d['Kernel Name']
+        cls = None
+        m = re.search(r'Cfg<\(int\)(\d+), \(int\)\d+, \(int\)(\d+), \(int\)(\d+)', name) or \
+            re.search(r'Cfg<(\d+), \d+, (\d+), (\d+)', name)
+        if 'conv_tc_kernel' in name and m:
+            cls = {('25', '3'): 'conv1', ('25', '24'): 'conv2', ('13', '32'): 'conv3', ('13', '48'): 'conv4'}.get((m.group(1), m.group(2)))
+        elif 'fc_tc_kernel' in name:
+            nfc += 1
+            cls = 'fc%d' % nfc if nfc <= 2 else None
+        elif 'gather_split_kernel' in name:
+            cls = 'gather'
+        elif 'pool_split_kernel' in name:
+            cls = 'max1' if 'max1' not in res else 'max2'
+        elif 'head_kernel' in name:
+            cls = 'fc3'
+        if cls is None or cls in res:
+            continue
+        rb = float(d['dram__bytes_read.sum']) * scale[u['dram__bytes_read.sum']]
+        wb = float(d['dram__bytes_write.sum']) * scale[u['dram__bytes_write.sum']]
+        res[cls] = {'dram_bytes_per_sample': (rb + wb) / samples_per_launch, 'dram_read_per_launch': rb,
+                    'dram_write_per_launch': wb, 'samples_per_launch': samples_per_launch,
+                    'duration_us': float(d['gpu__time_duration.sum']),
+                    'tensor_pipe_pct': float(d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'nan') or 'nan')}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == '__main__':
     if sys.argv[1] == 'launches':
         launches(sys.argv[2])
+    elif sys.argv[1] == 'traffic':
+        traffic(sys.argv[2], int(sys.argv[3]))
     else:
         report(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)

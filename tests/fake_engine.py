@@ -177,6 +177,76 @@ class FakeEngine(object):
         for j in range(len(self.fi_p1)):
             self.fi_kcols[t, j] = self._kern(j, u, a, sw)
 
+    # -- device-resident step protocol, emulated on host memory -----------------------------------
+    message_device = 'cpu'
+    stream = None
+
+    def fi_set_gids(self, gids):
+        self.fi_gids = np.asarray(gids, dtype=np.int64)
+
+    def fi_msg_bytes(self):
+        i = self.fi_info()
+        return (32 + 8 * self.fi_kcols.shape[0] + 4 * (i['d'] + i['d_prev']) + 15) // 16 * 16
+
+    @staticmethod
+    def _mem(ptr, nbytes):
+        import ctypes
+        return np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(ptr))
+
+    def fi_step_pack(self, t, ptr):
+        nb = self.fi_msg_bytes()
+        buf = self._mem(ptr, nb)
+        i = self.fi_info()
+        kcap = self.fi_kcols.shape[0]
+        loss, cand, trc = self.fi_step_local_best(t)
+        self._trc, self._cand = trc, cand
+        hdr = buf[:32].view(np.float64)
+        if cand < 0:
+            hdr[0] = np.inf
+            buf[8:16].view(np.int64)[0] = np.iinfo(np.int64).max
+            return
+        hdr[0] = loss
+        buf[8:16].view(np.int64)[0] = self.fi_gids[cand] if getattr(self, 'fi_gids', None) is not None and len(self.fi_gids) else cand
+        hdr[2] = np.sqrt(self.fi_w[cand])
+        row = buf[32:32 + 8 * kcap].view(np.float64)
+        row[:t] = self.fi_kcols[:t, cand]
+        row[t] = self.fi_diag[cand]
+        f = buf[32 + 8 * kcap:32 + 8 * kcap + 4 * (i['d'] + i['d_prev'])].view(np.float32)
+        f[:i['d']] = self.fi_U[cand]
+        if i['d_prev']:
+            f[i['d']:] = self.fi_A[cand]
+
+    def fi_step_apply_gathered(self, t, ptr, world, rank):
+        nb = self.fi_msg_bytes()
+        buf = self._mem(ptr, nb * world)
+        i = self.fi_info()
+        kcap = self.fi_kcols.shape[0]
+        best, bl, bg = 0, np.inf, np.iinfo(np.int64).max
+        for r in range(world):
+            m = buf[r * nb:(r + 1) * nb]
+            l, g = m[:8].view(np.float64)[0], m[8:16].view(np.int64)[0]
+            if l < bl or (l == bl and g < bg):
+                best, bl, bg = r, l, g
+        m = buf[best * nb:(best + 1) * nb]
+        sw = m[16:24].view(np.float64)[0]
+        row = m[32:32 + 8 * kcap].view(np.float64)[:t + 1].copy()
+        f = m[32 + 8 * kcap:32 + 8 * kcap + 4 * (i['d'] + i['d_prev'])].view(np.float32)
+        u = f[:i['d']].astype(np.float64)
+        a = f[i['d']:].astype(np.float64) if i['d_prev'] else None
+        self.fi_kss[t, :t + 1] = row
+        self.fi_kss[:t + 1, t] = row
+        if best == rank and np.isfinite(bl):
+            self.fi_avail[self._cand] = False
+        for j in range(len(self.fi_p1)):
+            self.fi_kcols[t, j] = self._kern(j, u, a, sw)
+        if not hasattr(self, '_sel') or t == 0:
+            self._sel, self._red = [], []
+        self._sel.append(int(bg) if np.isfinite(bl) else -1)
+        self._red.append((t + 1) * (self._trc + bl))
+
+    def fi_result(self, k):
+        return np.array(self._sel[:k], dtype=np.int64), np.array(self._red[:k])
+
     def fi_greedy(self, k, delta):
         k = int(min(k, len(self.fi_p1)))
         self.fi_begin(max(k, 1), delta)

@@ -257,3 +257,43 @@ def test_whole_image_fi_trace_score(nb):
     tol = 1e-3 * np.abs(score).max()
     assert len(q) == 20 and np.all(-score[q] <= kth + tol)
     assert np.all(np.isin(np.where(-score < kth - tol)[0], q))
+
+
+def test_fi_device_message_protocol_two_contexts(nb):
+    """Device-resident step protocol (pack -> all-gather -> apply) over two contexts that split the candidates,
+    the all-gather emulated by device copies, reproduces the single-context greedy."""
+    import torch
+    n, d, dp, k = 500, 128, 64, 40
+    p1, U, A, Wl = _factors(n, d, dp, 19)
+    delta = 1e-3
+    eng = nb.get_engine()
+    eng.fi_set_factors(p1, U, A, Wl)
+    ref_sel, ref_obj, ref_red = eng.fi_greedy(k, delta)
+    parts = [(0, 210), (210, 210), (210, n)]              # middle rank owns no candidates
+    engs = [nb.Engine(0) for _ in parts]
+    try:
+        for e, (a, b) in zip(engs, parts):
+            e.fi_set_factors(p1[a:b], U[a:b], A[a:b], Wl)
+            e.fi_begin(k, delta)
+            e.fi_set_gids(np.arange(a, b))
+        nbytes = engs[0].fi_msg_bytes()
+        world = len(engs)
+        send = [torch.zeros(nbytes, dtype=torch.uint8, device='cuda') for _ in engs]
+        recv = torch.zeros(world * nbytes, dtype=torch.uint8, device='cuda')
+        for t in range(k):
+            for r, e in enumerate(engs):
+                e.fi_step_pack(t, send[r].data_ptr())
+                e.synchronize()
+            for r in range(world):
+                recv[r * nbytes:(r + 1) * nbytes].copy_(send[r])
+            torch.cuda.synchronize()
+            for r, e in enumerate(engs):
+                e.fi_step_apply_gathered(t, recv.data_ptr(), world, r)
+                e.synchronize()
+        res = [e.fi_result(k) for e in engs]
+    finally:
+        for e in engs:
+            e.close()
+    for sel, red in res:
+        assert np.array_equal(sel, ref_sel)
+        assert np.allclose(red, ref_red, rtol=1e-12)
