@@ -100,7 +100,8 @@ def traffic(path, samples_per_launch):
         wb = float(d['dram__bytes_write.sum']) * scale[u['dram__bytes_write.sum']]
         res[cls] = {'dram_bytes_per_sample': (rb + wb) / samples_per_launch, 'dram_read_per_launch': rb,
                     'dram_write_per_launch': wb, 'samples_per_launch': samples_per_launch,
-                    'duration_us': float(d['gpu__time_duration.sum']),
+                    'duration_us': float(d['gpu__time_duration.sum']) * {'ns': 1e-3, 'us': 1., 'ms': 1e3, 's': 1e6}.get(
+                        u['gpu__time_duration.sum'], 1.),
                     'tensor_pipe_pct': float(d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'nan') or 'nan')}
     print(json.dumps(res, indent=1))
 
