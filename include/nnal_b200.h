@@ -192,6 +192,35 @@ int nnal_fi_step_pack(nnal_ctx* ctx, int64_t step, void* d_msg);
 int nnal_fi_step_apply_gathered(nnal_ctx* ctx, int64_t step, const void* d_msgs, int world, int rank);
 int nnal_fi_result(nnal_ctx* ctx, int64_t k, int64_t* gids_out, double* red_out);
 
+/* ---- representativeness queries over the feature layer ------------------------------- */
+/* Rows = the samples of the current pool pass (nnal_pool_begin keep >= 1; feature width multiple of 8).
+ * 'rep-entropy' (NNAL.py:466-523, PW_NNAL.py:284-351): cols [B][d] = feature rows of the B most uncertain samples
+ * (every rank passes the same array), excl_pos = pool positions of this rank that belong to them (they are not
+ * rows).  nnal_rep_set builds the cosine similarities [rows][B] on tensor cores; each greedy step is
+ * nnal_rep_step_scores (local partial sums sum_rows max(cur_row, sims[row][j]) into a DEVICE float64 [B] array
+ * that the host layer all-reduces) + nnal_rep_step_pick (arg-max, ties -> lowest column, update).
+ * nnal_rep_greedy runs k steps in one process.  nnal_sel_result reads the selected columns / global ids. */
+int nnal_rep_set(nnal_ctx* ctx, const float* cols, int64_t B, const int64_t* excl_pos, int64_t n_excl, int64_t k);
+int nnal_rep_step_scores(nnal_ctx* ctx, double* d_scores);
+int nnal_rep_step_pick(nnal_ctx* ctx, int64_t step, const double* d_scores);
+int nnal_rep_greedy(nnal_ctx* ctx, int64_t k, int64_t* sel_out, double* val_out);
+int nnal_sel_result(nnal_ctx* ctx, int64_t k, int64_t* sel_out, double* val_out);
+/* PW_NNAL.get_cross_sims (PW_NNAL.py:1093-1136): out[i] = max_j cos(pool row i, F2[j]) (float64 [n] on the host);
+ * the result also stays on the device as the starting point of a core-set selection (init = 2 below). */
+int nnal_cross_sims(nnal_ctx* ctx, const float* F2, int64_t n2, double* out);
+/* 'core-set' (PW_NNAL.py:353-451): k-center over the pool rows: q = argmin(sims) (ties -> lowest id),
+ * sims = max(sims, cos(f_q, F_u)), sims[q] = inf.  init 0: sims = -inf; 1: host array sims0[n]; 2: device result
+ * of the last nnal_cross_sims.  Multi-rank: per step nnal_cs_step_pack writes this rank's best (similarity, global
+ * id, feature row) into a DEVICE message, the messages are all-gathered, nnal_cs_step_apply_gathered applies the
+ * global winner.  nnal_cs_greedy runs k steps in one process. */
+int nnal_cs_begin(nnal_ctx* ctx, int init, const double* sims0, const int64_t* gids, int64_t k);
+int nnal_cs_msg_bytes(nnal_ctx* ctx, int64_t* bytes);
+int nnal_cs_step_pack(nnal_ctx* ctx, int64_t step, void* d_msg);
+int nnal_cs_step_apply_gathered(nnal_ctx* ctx, int64_t step, const void* d_msgs, int world, int rank);
+int nnal_cs_greedy(nnal_ctx* ctx, int64_t k, int64_t* sel_out, double* val_out);
+/* feature rows of the given pool positions as [n][d] float32 on the host (row-major) */
+int nnal_pool_feature_rows(nnal_ctx* ctx, const int64_t* pos, int64_t n, float* out);
+
 /* ---- test hook ---------------------------------------------------------------------------- */
 /* One FC layer out[M][N] = act(A[M][K] W[N][K]^T + b) on host buffers, on the tcgen05 GEMM
  * (use_tc=1) or the FP32 CUDA-core GEMM (use_tc=0); lets tests check the kernels in isolation. */

@@ -47,4 +47,7 @@ def CNN_query(model, expr, pool_inds, method_name, session, col=True, extra_feed
     if method_name == 'fi':
         from . import fi
         return fi.query_whole(model, expr, pool_inds, session)
+    if method_name == 'rep-entropy':
+        from . import rep
+        return rep.query_rep_entropy_whole(model, expr, pool_inds, session)
     raise NotImplementedError('query method %r is not part of the replaced path' % method_name)

@@ -137,4 +137,12 @@ def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, labeled_inds, m
         from . import fi
         return fi.query_multimg(expr, model, sess, all_padded_imgs, pool_inds)
 
+    if method_name == 'rep-entropy':
+        from . import rep
+        return rep.query_rep_entropy_multimg(expr, model, sess, all_padded_imgs, pool_inds)
+
+    if method_name == 'core-set':
+        from . import rep
+        return rep.query_core_set_multimg(expr, model, sess, all_padded_imgs, pool_inds, labeled_inds)
+
     raise NotImplementedError('query method %r is not part of the replaced path' % method_name)

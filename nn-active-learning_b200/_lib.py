@@ -53,6 +53,18 @@ SIGNATURES = {
     'nnal_debug_fc': (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
     'nnal_debug_conv': (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, c_vp]),
+    'nnal_rep_set': (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, C.c_int64, C.c_int64]),
+    'nnal_rep_step_scores': (C.c_int, [c_vp, c_vp]),
+    'nnal_rep_step_pick': (C.c_int, [c_vp, C.c_int64, c_vp]),
+    'nnal_rep_greedy': (C.c_int, [c_vp, C.c_int64, c_vp, c_vp]),
+    'nnal_sel_result': (C.c_int, [c_vp, C.c_int64, c_vp, c_vp]),
+    'nnal_cross_sims': (C.c_int, [c_vp, c_vp, C.c_int64, c_vp]),
+    'nnal_cs_begin': (C.c_int, [c_vp, C.c_int, c_vp, c_vp, C.c_int64]),
+    'nnal_cs_msg_bytes': (C.c_int, [c_vp, c_i64p]),
+    'nnal_cs_step_pack': (C.c_int, [c_vp, C.c_int64, c_vp]),
+    'nnal_cs_step_apply_gathered': (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int, C.c_int]),
+    'nnal_cs_greedy': (C.c_int, [c_vp, C.c_int64, c_vp, c_vp]),
+    'nnal_pool_feature_rows': (C.c_int, [c_vp, c_vp, C.c_int64, c_vp]),
     'nnal_fi_set_candidates': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int]),
     'nnal_fi_set_factors': (C.c_int, [c_vp, C.c_int64, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     'nnal_fi_info': (C.c_int, [c_vp, c_i64p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_f64p]),

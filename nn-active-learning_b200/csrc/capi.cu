@@ -64,6 +64,7 @@ extern "C" int nnal_volume_clear(nnal_ctx* ctx) {
 }
 
 int nnal_fi_release(nnal_ctx* ctx);
+int nnal_sims_release(nnal_ctx* ctx);
 
 extern "C" int nnal_ctx_destroy(nnal_ctx* ctx) {
   if (!ctx) return NNAL_OK;
@@ -73,6 +74,7 @@ extern "C" int nnal_ctx_destroy(nnal_ctx* ctx) {
   free_layers(ctx);
   free_pool(ctx);
   nnal_fi_release(ctx);
+  nnal_sims_release(ctx);
   nnal_tc_release(ctx);
   free_buf(ctx->stage); free_buf(ctx->inds); free_buf(ctx->act[0]); free_buf(ctx->act[1]); free_buf(ctx->xin);
   free_buf(ctx->featbuf); free_buf(ctx->prevbuf); free_buf(ctx->logits); free_buf(ctx->splitA[0]); free_buf(ctx->splitA[1]);
@@ -499,6 +501,35 @@ extern "C" int nnal_pool_features(nnal_ctx* ctx, int64_t start, int64_t n, float
   NNAL_TRY(devbuf_reserve(ctx, ctx->act[0], (size_t)n * d * sizeof(float)));
   dim3 grid(cdiv(n, 32), cdiv(d, 32)), block(32, 8);
   transpose_feat_kernel<<<grid, block, 0, ctx->stream>>>(ctx->pool_feat + start * d, (float*)ctx->act[0].p, n, d);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->act[0].p, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+__global__ void gather_rows_f32_kernel(const float* __restrict__ src, const int64_t* __restrict__ pos, int64_t n, int d,
+                                       float* __restrict__ out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * d; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / d;
+    out[e] = src[pos[r] * d + (e - r * d)];
+  }
+}
+
+extern "C" int nnal_pool_feature_rows(nnal_ctx* ctx, const int64_t* pos, int64_t n, float* out) {
+  if (!ctx || n < 0) return NNAL_ERR_INVALID;
+  if (!ctx->pool_feat || ctx->keep < 1) NNAL_FAIL(ctx, NNAL_ERR_STATE, "pool pass did not keep features");
+  if (n == 0) return NNAL_OK;
+  if (!pos || !out) return NNAL_ERR_INVALID;
+  for (int64_t i = 0; i < n; ++i)
+    if (pos[i] < 0 || pos[i] >= ctx->pool_n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "feature row position outside the pool");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int d = ctx->feat_dim;
+  NNAL_TRY(devbuf_reserve(ctx, ctx->act[0], (size_t)n * d * sizeof(float)));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->inds, (size_t)n * 8));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->inds.p, pos, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  gather_rows_f32_kernel<<<std::min(cdiv(n * d, 256), ctx->sm_count * 16), 256, 0, ctx->stream>>>(ctx->pool_feat, (const int64_t*)ctx->inds.p, n, d,
+                                                                                                 (float*)ctx->act[0].p);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->act[0].p, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));

@@ -21,6 +21,7 @@
 // penultimate-feature Gram  H = sum_i wq_i [u_i;1][u_i;1]^T  ((d+1)^2, tensor cores: fp16 hi/lo split planes
 // through the tcgen05 GEMM of gemm_tc.cu).
 #include "nnal_common.cuh"
+#include "dots.cuh"
 #include "../../include/nnal_b200.h"
 #include <algorithm>
 #include <cmath>
@@ -87,77 +88,6 @@ static int ensure(nnal_ctx* ctx, T*& p, size_t have, size_t want) {
   if (p) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CUDA_TRY(ctx, cudaFree(p)); p = nullptr; }
   CUDA_TRY(ctx, cudaMalloc(&p, std::max<size_t>(want, 1) * sizeof(T)));
   return NNAL_OK;
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// The three inner products of a (candidate, winner) pair, float64 accumulation of exact float32 products in
-// a FIXED order (four independent chains per lane, lane-strided, then butterfly):
-//   uu = u.x,  aa = a.y,  mm = sum_k beta2_k 1[u_k > 0] 1[x_k > 0].
-// Inner products of float32 factor rows.  Every lane multiplies-and-adds SHORT float32 chains (four
-// independent chains of four FMAs: the product inside an FMA is exact, one rounding per add) and flushes
-// them into float64 sums, which are then reduced in float64: the result carries ~1e-8 relative error
-// (16-term float32 partials, random signs, averaged over d/16 partials) at one FMA per element -- a
-// cvt+DFMA loop is bound by the quarter-rate float32->float64 conversions, a compensated float32 dot
-// product by its 10 flops per element; this one stays on the HBM roofline.
-// Fixed order (lane-strided, then butterfly) => bit-reproducible.
-//   uu = u.x,  aa = a.y,  mm = sum_k beta2_k 1[u_k > 0] 1[x_k > 0]
-__device__ __forceinline__ void dot_um(const float* __restrict__ u, const float* __restrict__ x,
-                                       const float* __restrict__ beta2, int d, bool mask, int lane, double& uu, double& mm) {
-  double su = 0.0, sm = 0.0;
-  if ((d & 3) == 0) {
-    int k = lane * 4;
-    for (; k + 3 * 128 < d; k += 4 * 128) {
-      float4 p[4], q[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        p[i] = *reinterpret_cast<const float4*>(u + k + i * 128);
-        q[i] = *reinterpret_cast<const float4*>(x + k + i * 128);
-      }
-      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        f0 = fmaf(p[i].x, q[i].x, f0);
-        f1 = fmaf(p[i].y, q[i].y, f1);
-        f2 = fmaf(p[i].z, q[i].z, f2);
-        f3 = fmaf(p[i].w, q[i].w, f3);
-      }
-      su += ((double)f0 + (double)f1) + ((double)f2 + (double)f3);
-      if (mask) {
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(beta2 + k + i * 128));
-          g0 += (p[i].x > 0.f && q[i].x > 0.f) ? b.x : 0.f;
-          g1 += (p[i].y > 0.f && q[i].y > 0.f) ? b.y : 0.f;
-          g2 += (p[i].z > 0.f && q[i].z > 0.f) ? b.z : 0.f;
-          g3 += (p[i].w > 0.f && q[i].w > 0.f) ? b.w : 0.f;
-        }
-        sm += ((double)g0 + (double)g1) + ((double)g2 + (double)g3);
-      }
-    }
-    for (; k < d; k += 128) {
-      const float4 p = *reinterpret_cast<const float4*>(u + k);
-      const float4 q = *reinterpret_cast<const float4*>(x + k);
-      su += ((double)(p.x * q.x) + (double)(p.y * q.y)) + ((double)(p.z * q.z) + (double)(p.w * q.w));   // not reached for d % 512 == 0
-      if (mask) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta2 + k));
-        sm += (double)((p.x > 0.f && q.x > 0.f) ? b.x : 0.f) + (double)((p.y > 0.f && q.y > 0.f) ? b.y : 0.f) +
-              (double)((p.z > 0.f && q.z > 0.f) ? b.z : 0.f) + (double)((p.w > 0.f && q.w > 0.f) ? b.w : 0.f);
-      }
-    }
-  } else {
-    for (int k = lane; k < d; k += 32) {
-      su = fma((double)u[k], (double)x[k], su);
-      if (mask && u[k] > 0.f && x[k] > 0.f) sm += (double)__ldg(beta2 + k);
-    }
-  }
-  uu = su;
-  mm = sm;
 }
 
 __device__ __forceinline__ void pair_dots(const float* __restrict__ u, const float* __restrict__ a,

@@ -106,6 +106,7 @@ struct nnal_ctx {
   size_t pool_cap_n = 0, pool_cap_score = 0, pool_cap_nfeat = 0, pool_cap_nprev = 0;   // per-array capacities (samples)
   int pool_cap_class = 0, pool_cap_feat = 0, pool_cap_prev = 0;                        // widths they were sized for
   void* tc_state = nullptr;              // tensor-map cache etc. (gemm_tc.cu)
+  void* sims_state = nullptr;            // representativeness queries (sims.cu)
   void* fi_state = nullptr;              // Fisher-information candidate set / greedy state (fi.cu)
 };
 

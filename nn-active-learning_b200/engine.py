@@ -410,6 +410,82 @@ class Engine(object):
                                               int(cand_local)))
 
     # ------------------------------------------------------------------
+    # representativeness queries (rep-entropy, core-set)
+    # ------------------------------------------------------------------
+    def pool_feature_rows(self, pos):
+        """Feature-layer rows of pool positions ``pos`` as ``[len(pos), d]`` float32."""
+        pos = np.ascontiguousarray(pos, dtype=np.int64).ravel()
+        out = np.empty((pos.size, self.feat_dim), dtype=np.float32)
+        self.h2d_bytes += pos.nbytes
+        self.d2h_bytes += out.nbytes
+        self._chk(self.lib.nnal_pool_feature_rows(self.h, _ptr(pos) if pos.size else None, pos.size,
+                                                  _ptr(out) if pos.size else None))
+        return out
+
+    def rep_set(self, cols, excl_pos, k):
+        cols = np.ascontiguousarray(cols, dtype=np.float32)
+        excl = np.ascontiguousarray(excl_pos, dtype=np.int64).ravel()
+        self.h2d_bytes += cols.nbytes + excl.nbytes
+        self._rep_B = cols.shape[0]
+        self._chk(self.lib.nnal_rep_set(self.h, _ptr(cols) if cols.size else None, cols.shape[0],
+                                        _ptr(excl) if excl.size else None, excl.size, int(k)))
+
+    def rep_step_scores(self, d_scores_ptr):
+        self._chk(self.lib.nnal_rep_step_scores(self.h, C.c_void_p(int(d_scores_ptr))))
+
+    def rep_step_pick(self, step, d_scores_ptr):
+        self._chk(self.lib.nnal_rep_step_pick(self.h, int(step), C.c_void_p(int(d_scores_ptr))))
+
+    def rep_greedy(self, k):
+        k = int(min(k, self._rep_B))
+        sel = np.empty(k, dtype=np.int64)
+        val = np.empty(k, dtype=np.float64)
+        self.d2h_bytes += sel.nbytes + val.nbytes
+        self._chk(self.lib.nnal_rep_greedy(self.h, k, _ptr(sel), _ptr(val)))
+        return sel, val
+
+    def sel_result(self, k):
+        sel = np.empty(int(k), dtype=np.int64)
+        val = np.empty(int(k), dtype=np.float64)
+        self.d2h_bytes += sel.nbytes + val.nbytes
+        self._chk(self.lib.nnal_sel_result(self.h, int(k), _ptr(sel), _ptr(val)))
+        return sel, val
+
+    def cross_sims(self, F2):
+        """max_j cos(pool row i, F2[j]) for every sample of the current pool pass (float64 [n])."""
+        F2 = np.ascontiguousarray(F2, dtype=np.float32)
+        out = np.empty(self._pool_n, dtype=np.float64)
+        self.h2d_bytes += F2.nbytes
+        self.d2h_bytes += out.nbytes
+        self._chk(self.lib.nnal_cross_sims(self.h, _ptr(F2), F2.shape[0], _ptr(out)))
+        return out
+
+    def cs_begin(self, init, sims0, gids, k):
+        s0 = None if sims0 is None else np.ascontiguousarray(sims0, dtype=np.float64)
+        g = None if gids is None else np.ascontiguousarray(gids, dtype=np.int64)
+        self._chk(self.lib.nnal_cs_begin(self.h, int(init), None if s0 is None else _ptr(s0),
+                                         None if g is None or g.size == 0 else _ptr(g), int(k)))
+
+    def cs_msg_bytes(self):
+        b = C.c_int64()
+        self._chk(self.lib.nnal_cs_msg_bytes(self.h, C.byref(b)))
+        return b.value
+
+    def cs_step_pack(self, step, d_msg_ptr):
+        self._chk(self.lib.nnal_cs_step_pack(self.h, int(step), C.c_void_p(int(d_msg_ptr))))
+
+    def cs_step_apply_gathered(self, step, d_msgs_ptr, world, rank):
+        self._chk(self.lib.nnal_cs_step_apply_gathered(self.h, int(step), C.c_void_p(int(d_msgs_ptr)), int(world), int(rank)))
+
+    def cs_greedy(self, k):
+        k = int(min(k, self._pool_n))
+        sel = np.empty(k, dtype=np.int64)
+        val = np.empty(k, dtype=np.float64)
+        self.d2h_bytes += sel.nbytes + val.nbytes
+        self._chk(self.lib.nnal_cs_greedy(self.h, k, _ptr(sel), _ptr(val)))
+        return sel, val
+
+    # ------------------------------------------------------------------
     # stand-alone helpers
     # ------------------------------------------------------------------
     def entropy(self, P, kind=L.SCORE_ENTROPY, eps=10e-8):

@@ -22,3 +22,4 @@ Parity status
 """
 from .nnal_oracle import *   # noqa: F401,F403
 from .fi_oracle import *     # noqa: F401,F403
+from .rep_oracle import *    # noqa: F401,F403

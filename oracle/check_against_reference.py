@@ -167,6 +167,40 @@ def main():
     assert np.array_equal(ref_tools.append_zero(A), O.append_zero(A))
     print('sample_query_dstr / append_zero: oracle == reference')
 
+    # ---- similarity helpers and the greedy loops of the representativeness queries
+    F1 = np.maximum(rs.randn(16, 40), 0)
+    F2 = np.maximum(rs.randn(16, 23), 0)
+    r_self, r_cross = ref_pw.get_self_sims(F1), ref_pw.get_cross_sims(F1, F2)
+    assert np.allclose(r_self, O.get_self_sims(F1), rtol=1e-13) and np.allclose(r_cross, O.get_cross_sims(F1, F2), rtol=1e-13)
+    gold['sims_F1'], gold['sims_F2'], gold['sims_self'], gold['sims_cross'] = F1, F2, r_self, r_cross
+    # the literal greedy facility-location loop of NNAL.py:506-521 / PW_NNAL.py:329-343 (copied control flow, run on
+    # the reference's arithmetic: np.sum(np.max(sims[:, cand_Q], axis=1)) / np.argmax / np.delete)
+    sims = O.cosine_sims(F1[:, :25], F1[:, 25:])
+    B, k = sims.shape[1], 6
+    Q_inds, nQ = [], np.arange(B)
+    for i in range(k):
+        rep = np.zeros(B - i)
+        for j in range(B - i):
+            rep[j] = np.sum(np.max(sims[:, Q_inds + [nQ[j]]], axis=1))
+        Q_inds += [nQ[np.argmax(rep)]]
+        nQ = np.delete(nQ, np.argmax(rep))
+    assert np.array_equal(Q_inds, O.greedy_facility_location(sims, k)[0])
+    gold['fl_sims'], gold['fl_Q'] = sims, np.array(Q_inds)
+    # the k-center loop of PW_NNAL.py:437-448
+    Fu = F1
+    norms_u = np.sqrt(np.sum(Fu ** 2, axis=0))
+    s0 = r_cross.copy()
+    sims1, Qk = s0.copy(), []
+    for t in range(5):
+        q_ind = np.argmin(sims1)
+        Qk += [q_ind]
+        s_ind = np.dot(Fu[:, q_ind].T, Fu) / (norms_u * norms_u[q_ind])
+        sims1 = np.maximum(sims1, s_ind)
+        sims1[q_ind] = np.inf
+    assert np.array_equal(Qk, O.kcenter_greedy(Fu, s0, 5)[0])
+    gold['kc_Q'] = np.array(Qk)
+    print('get_self_sims / get_cross_sims / facility-location / k-center loops: oracle == reference')
+
     np.savez_compressed(os.path.join(GOLD, 'reference_numpy_helpers.npz'), **gold)
     print('wrote', os.path.join(GOLD, 'reference_numpy_helpers.npz'))
 

@@ -72,6 +72,21 @@ def run(rank, world, out):
     for s in range(len(Q)):
         res['fi_multi%d' % s] = np.asarray(Q[s])
     res['fi_multi_obj'] = obj
+    # representativeness queries
+    expr.pars['B'] = 30
+    Q = nnal_b200.PW_NNAL.query_multimg(expr, model, None, allp, pools, None, 'rep-entropy')
+    for s in range(len(Q)):
+        res['rep_multi%d' % s] = np.asarray(Q[s])
+    rs2 = np.random.RandomState(17)
+    labeled = [list(rs2.choice(12 * 11 * 4, 9, replace=False)) for _ in range(3)]
+    expr.labeled_stats = st
+    Q = nnal_b200.PW_NNAL.query_multimg(expr, model, None, allp, pools, labeled, 'core-set')
+    for s in range(len(Q)):
+        res['cs_multi%d' % s] = np.asarray(Q[s])
+    wexpr = Expr()
+    wexpr.pars = dict(k=7, B=25, lambda_=0., batch_size=32)
+    wexpr.pool_images = np.random.RandomState(3).rand(90, 5, 5, m).astype(np.float32)
+    res['rep_whole'] = nnal_b200.NNAL.CNN_query(model, wexpr, np.arange(90), 'rep-entropy', None)
     # primitives
     rs = np.random.RandomState(100 + rank)
     sc = np.sort(rs.rand(6))

@@ -83,6 +83,129 @@ class FakeEngine(object):
         idx = O.stable_topk(self.score, k).astype(np.int64)
         return (idx, self.score[idx]) if with_scores else idx
 
+    # -- representativeness queries ------------------------------------------------
+    @property
+    def feat_dim(self):
+        return self._feat_dim()
+
+    def pool_feature_rows(self, pos):
+        pos = np.asarray(pos, dtype=np.int64)
+        if self.feat is None:
+            return np.zeros((0, self._feat_dim()), dtype=np.float32)
+        return self.feat[pos].astype(np.float32)
+
+    def _unit_rows(self):
+        F = (self.feat if self.feat is not None else np.zeros((0, self._feat_dim()))).astype(np.float32).astype(np.float64)
+        nr = np.sqrt(np.sum(F ** 2, axis=1))
+        self._inorm = np.where(nr > 0, 1. / np.where(nr > 0, nr, 1.), 0.)
+        return F * self._inorm[:, None]
+
+    def rep_set(self, cols, excl_pos, k):
+        U = self._unit_rows()
+        Cn = np.asarray(cols, dtype=np.float64)
+        cn = np.sqrt(np.sum(Cn ** 2, axis=1))
+        Cn = Cn * np.where(cn > 0, 1. / np.where(cn > 0, cn, 1.), 0.)[:, None]
+        self.rep_S = U @ Cn.T
+        self.rep_mask = self._inorm > 0
+        self.rep_mask[np.asarray(excl_pos, dtype=np.int64)] = False
+        self.rep_cur = np.full(len(U), -np.inf)
+        self.rep_taken = np.zeros(len(Cn), dtype=bool)
+        self._sel, self._val = [], []
+        self._rep_B = len(Cn)
+
+    def rep_step_scores(self, ptr):
+        B = self._rep_B
+        out = self._mem(ptr, 8 * max(B, 1)).view(np.float64)
+        sc = np.sum(np.maximum(self.rep_cur[self.rep_mask, None], self.rep_S[self.rep_mask]), axis=0) if B else np.zeros(0)
+        sc = np.where(self.rep_taken, -np.inf, sc)
+        out[:B] = sc
+
+    def rep_step_pick(self, t, ptr):
+        B = self._rep_B
+        sc = self._mem(ptr, 8 * max(B, 1)).view(np.float64)[:B].copy()
+        sc[self.rep_taken] = -np.inf
+        j = int(np.argmax(sc))
+        self._sel.append(j)
+        self._val.append(sc[j])
+        self.rep_taken[j] = True
+        self.rep_cur = np.maximum(self.rep_cur, self.rep_S[:, j])
+
+    def rep_greedy(self, k):
+        import ctypes
+        buf = np.zeros(max(self._rep_B, 1), dtype=np.float64)
+        for t in range(int(min(k, self._rep_B))):
+            self.rep_step_scores(buf.ctypes.data)
+            self.rep_step_pick(t, buf.ctypes.data)
+        return self.sel_result(len(self._sel))
+
+    def sel_result(self, k):
+        return np.array(self._sel[:k], dtype=np.int64), np.array(self._val[:k], dtype=np.float64)
+
+    def cross_sims(self, F2):
+        U = self._unit_rows()
+        T = np.asarray(F2, dtype=np.float64)
+        tn = np.sqrt(np.sum(T ** 2, axis=1))
+        T = T * np.where(tn > 0, 1. / np.where(tn > 0, tn, 1.), 0.)[:, None]
+        self.cs = np.where(self._inorm > 0, np.max(U @ T.T, axis=1), np.inf) if len(U) else np.zeros(0)
+        return self.cs.copy()
+
+    def cs_begin(self, init, sims0, gids, k):
+        U = self._unit_rows()
+        self.cs_U = U
+        if init == 0:
+            self.cs = np.where(self._inorm > 0, -np.inf, np.inf)
+        elif init == 1:
+            self.cs = np.where(self._inorm > 0, np.asarray(sims0, dtype=np.float64), np.inf)
+        self.cs_gids = np.arange(len(U)) if gids is None else np.asarray(gids, dtype=np.int64)
+        self._sel, self._val = [], []
+
+    def cs_msg_bytes(self):
+        return (32 + 4 * self._feat_dim() + 15) // 16 * 16
+
+    def cs_step_pack(self, t, ptr):
+        buf = self._mem(ptr, self.cs_msg_bytes())
+        hdr = buf[:32].view(np.float64)
+        if len(self.cs) == 0 or np.min(self.cs) == np.inf:
+            hdr[0] = np.inf
+            buf[8:16].view(np.int64)[0] = np.iinfo(np.int64).max
+            self._cand = -1
+            return
+        q = int(np.argmin(self.cs))
+        self._cand = q
+        hdr[0] = self.cs[q]
+        buf[8:16].view(np.int64)[0] = self.cs_gids[q]
+        hdr[2] = self._inorm[q]
+        buf[32:32 + 4 * self._feat_dim()].view(np.float32)[:] = self.feat[q].astype(np.float32)
+
+    def cs_step_apply_gathered(self, t, ptr, world, rank):
+        nb = self.cs_msg_bytes()
+        buf = self._mem(ptr, nb * world)
+        best, bv, bg = 0, np.inf, np.iinfo(np.int64).max
+        for r in range(world):
+            m = buf[r * nb:(r + 1) * nb]
+            v, g = m[:8].view(np.float64)[0], m[8:16].view(np.int64)[0]
+            if v < bv or (v == bv and g < bg):
+                best, bv, bg = r, v, g
+        m = buf[best * nb:(best + 1) * nb]
+        inorm = m[16:24].view(np.float64)[0]
+        f = m[32:32 + 4 * self._feat_dim()].view(np.float32).astype(np.float64)
+        if best == rank and np.isfinite(bv):
+            self.cs[self._cand] = np.inf
+        if len(self.cs):
+            raw = self.feat.astype(np.float32).astype(np.float64)
+            s_ind = (raw @ f) * self._inorm * inorm
+            live = self.cs < np.inf
+            self.cs[live] = np.maximum(self.cs[live], s_ind[live])
+        self._sel.append(int(bg) if np.isfinite(bv) else -1)
+        self._val.append(bv)
+
+    def cs_greedy(self, k):
+        buf = np.zeros(self.cs_msg_bytes(), dtype=np.uint8)
+        for t in range(int(min(k, len(self.cs)))):
+            self.cs_step_pack(t, buf.ctypes.data)
+            self.cs_step_apply_gathered(t, buf.ctypes.data, 1, 0)
+        return self.sel_result(len(self._sel))
+
     # -- Fisher information --------------------------------------------------
     def fi_set_candidates(self, cand=None, n_layers=2):
         rows = np.arange(self._pool_n) if cand is None else np.asarray(cand, dtype=np.int64)

@@ -74,6 +74,18 @@ def test_single_process_matches_oracle(runs):
     for s in range(3):
         assert np.array_equal(one['fi_multi%d' % s], Qf[s])
     assert np.allclose(one['fi_multi_obj'], obj, rtol=1e-6)
+    Qr, _ = O.query_rep_entropy_multimg(layers, w, allp, pools, ps, 16, st, 11, 30)
+    for s in range(3):
+        assert np.array_equal(one['rep_multi%d' % s], Qr[s])
+    labeled = [list(np.random.RandomState(17).choice(12 * 11 * 4, 9, replace=False)) for _ in range(1)]
+    rs2 = np.random.RandomState(17)
+    labeled = [list(rs2.choice(12 * 11 * 4, 9, replace=False)) for _ in range(3)]
+    Qc, _ = O.query_core_set_multimg(layers, w, allp, pools, labeled, ps, 16, st, st, 11)
+    for s in range(3):
+        assert np.array_equal(one['cs_multi%d' % s], Qc[s])
+    x = np.random.RandomState(3).rand(90, 5, 5, m).astype(np.float32)
+    qw, _ = O.query_rep_entropy_whole(layers, w, x, 7, 25)
+    assert np.array_equal(one['rep_whole'], qw)
 
 
 def test_collective_primitives(runs):

@@ -267,3 +267,16 @@ def test_greedy_replay_matches_rank1():
                            axis=0) * np.sqrt(p1 * (1 - p1))[None, :]
         Abar = [np.outer(G[:, i], G[:, i]) for i in range(n)]
         assert np.isclose(O.fi_objective_direct(Abar, list(S[:6]), 1e-3), obj[5], rtol=1e-8)
+
+
+def test_rep_oracle_golden(golden):
+    """Similarity helpers and greedy loops of the representativeness queries vs the reference's own outputs."""
+    F1, F2 = golden['sims_F1'], golden['sims_F2']
+    assert np.allclose(O.get_self_sims(F1), golden['sims_self'], rtol=1e-13)
+    assert np.allclose(O.get_cross_sims(F1, F2), golden['sims_cross'], rtol=1e-13)
+    assert np.array_equal(O.greedy_facility_location(golden['fl_sims'], 6)[0], golden['fl_Q'])
+    rep = O.facility_location_replay(golden['fl_sims'], golden['fl_Q'])
+    assert np.allclose(rep[:, 0], rep[:, 1])
+    assert np.array_equal(O.kcenter_greedy(F1, golden['sims_cross'], 5)[0], golden['kc_Q'])
+    rep = O.kcenter_replay(F1, golden['sims_cross'], golden['kc_Q'])
+    assert np.allclose(rep[:, 0], rep[:, 1])
