@@ -227,8 +227,9 @@ int nnal_pool_feature_rows(nnal_ctx* ctx, const int64_t* pos, int64_t n, float* 
 int nnal_debug_fc(nnal_ctx* ctx, const float* A, const float* W, const float* b, int64_t M, int N, int K, int relu,
                   int use_tc, float* out);
 
-/* One conv layer (SAME, stride 1, bias, ReLU; NN.py:285-290) on host NHWC buffers, tensor-core or
- * CUDA-core kernel. */
+/* One conv layer (SAME, stride 1, bias, ReLU; NN.py:285-290) on host NHWC buffers.  use_tc: 0 CUDA-core kernel,
+ * 1 tcgen05 kernel with positions on M (conv_tc.cu), 2 weight-stationary tcgen05 kernel (conv_wt.cu), 3 = 2 and 4 = 1 with
+ * the following 2x2/s2 SAME max-pool (NN.py:1473-1477) fused: out is then [n][ceil(H/2)][ceil(Wd/2)][Cout]. */
 int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, const float* b, int64_t n, int H, int Wd, int Cin,
                     int Cout, int ks, int use_tc, float* out);
 

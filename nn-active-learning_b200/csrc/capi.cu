@@ -31,6 +31,8 @@ extern "C" int nnal_ctx_create(int device, nnal_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return NNAL_ERR_CUDA; }
   const char* f = getenv("NNAL_FORCE_SIMT");
   ctx->use_tc = (f && atoi(f)) ? 0 : 1;
+  const char* fw = getenv("NNAL_CONV_WT");   // 0: conv_tc.cu only, 1: conv_wt.cu where faster, 2 (default): + pool fusion, 3: wherever supported
+  ctx->use_wt = fw ? atoi(fw) : 2;
   *out = ctx;
   return NNAL_OK;
 }
@@ -41,6 +43,7 @@ static void free_layers(nnal_ctx* ctx) {
     if (L.b) cudaFree(L.b);
     if (L.Wh) cudaFree(L.Wh);
     if (L.Wl) cudaFree(L.Wl);
+    if (L.Wt) cudaFree(L.Wt);
   }
   ctx->layers.clear();
 }
@@ -627,7 +630,7 @@ extern "C" int nnal_debug_fc(nnal_ctx* ctx, const float* A, const float* W, cons
   auto cleanup = [&]() {
     cudaStreamSynchronize(ctx->stream);
     if (dA) cudaFree(dA); if (dO) cudaFree(dO);
-    if (L.W) cudaFree(L.W); if (L.b) cudaFree(L.b); if (L.Wh) cudaFree(L.Wh); if (L.Wl) cudaFree(L.Wl);
+    if (L.W) cudaFree(L.W); if (L.b) cudaFree(L.b); if (L.Wh) cudaFree(L.Wh); if (L.Wl) cudaFree(L.Wl); if (L.Wt) cudaFree(L.Wt);
   };
   if (cudaMalloc(&dA, (size_t)M * K * 4) != cudaSuccess || cudaMalloc(&dO, (size_t)M * N * 4) != cudaSuccess ||
       cudaMalloc(&L.W, (size_t)N * K * 4) != cudaSuccess || cudaMalloc(&L.b, (size_t)N * 4) != cudaSuccess) {
@@ -663,13 +666,14 @@ extern "C" int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, co
   Layer L;
   L.type = NNAL_LAYER_CONV; L.kh = L.kw = ks; L.in_h = L.out_h = H; L.in_w = L.out_w = Wd; L.in_c = Cin; L.out_c = Cout; L.relu = 1;
   const size_t ie = (size_t)n * H * Wd * Cin, oe = (size_t)n * H * Wd * Cout;
+  size_t oe_out = oe;
   float *dX = nullptr, *dO = nullptr;
   nnal_h *ih = nullptr, *oh = nullptr;
   int rc = NNAL_OK;
   auto cleanup = [&]() {
     cudaStreamSynchronize(ctx->stream);
     if (dX) cudaFree(dX); if (dO) cudaFree(dO); if (ih) cudaFree(ih); if (oh) cudaFree(oh);
-    if (L.W) cudaFree(L.W); if (L.b) cudaFree(L.b); if (L.Wh) cudaFree(L.Wh); if (L.Wl) cudaFree(L.Wl);
+    if (L.W) cudaFree(L.W); if (L.b) cudaFree(L.b); if (L.Wh) cudaFree(L.Wh); if (L.Wl) cudaFree(L.Wl); if (L.Wt) cudaFree(L.Wt);
   };
   if (cudaMalloc(&dX, ie * 4) != cudaSuccess || cudaMalloc(&dO, oe * 4) != cudaSuccess || cudaMalloc(&ih, ie * 4) != cudaSuccess ||
       cudaMalloc(&oh, oe * 4) != cudaSuccess || cudaMalloc(&L.W, (size_t)ks * ks * Cin * Cout * 4) != cudaSuccess ||
@@ -688,13 +692,23 @@ extern "C" int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, co
     const size_t iep = (size_t)n * H * Wd * cp;
     if (cp != Cin) { cudaFree(ih); ih = nullptr; if (cudaMalloc(&ih, iep * 4) != cudaSuccess) { cleanup(); NNAL_FAIL(ctx, NNAL_ERR_CUDA, "debug_conv allocation failed"); } }
     if (rc == NNAL_OK) rc = nnal_k_split_pad(ctx, dX, ih, ih + iep, (int64_t)n * H * Wd, Cin, cp);
-    if (rc == NNAL_OK) rc = nnal_tc_conv(ctx, L, ih, ih + iep, oh, oh + oe, n);
-    if (rc == NNAL_OK) rc = nnal_k_merge_flat(ctx, oh, oh + oe, dO, (int64_t)oe);
+    if (rc == NNAL_OK && (use_tc == 2 || use_tc == 3) &&
+        !(use_tc == 3 ? nnal_wt_conv_pool_supported(ctx, L) : nnal_wt_conv_supported(ctx, L))) {
+      ctx->err = "shape not supported by the weight-stationary conv"; rc = NNAL_ERR_UNSUPPORTED;
+    }
+    if (rc == NNAL_OK && use_tc == 4 && !nnal_tc_conv_pool_supported(ctx, L)) {
+      ctx->err = "conv+pool shape not supported by the tensor-core conv"; rc = NNAL_ERR_UNSUPPORTED;
+    }
+    if (use_tc >= 3) oe_out = (size_t)n * ((H + 1) / 2) * ((Wd + 1) / 2) * Cout;      // fused 2x2/s2 SAME max-pool
+    if (rc == NNAL_OK) rc = use_tc == 4 ? nnal_tc_conv_pool(ctx, L, ih, ih + iep, oh, oh + oe_out, n)
+                          : use_tc >= 2 ? nnal_wt_conv(ctx, L, ih, ih + iep, oh, oh + oe_out, n, use_tc == 3)
+                                        : nnal_tc_conv(ctx, L, ih, ih + iep, oh, oh + oe, n);
+    if (rc == NNAL_OK) rc = nnal_k_merge_flat(ctx, oh, oh + oe_out, dO, (int64_t)oe_out);
   } else {
     rc = nnal_k_conv_simt(ctx, L, dX, dO, n);
   }
   if (rc == NNAL_OK) {
-    if (cudaMemcpyAsync(out, dO, oe * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+    if (cudaMemcpyAsync(out, dO, oe_out * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
         cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
       ctx->err = std::string("debug_conv: ") + cudaGetErrorString(cudaGetLastError()); rc = NNAL_ERR_CUDA;
     }

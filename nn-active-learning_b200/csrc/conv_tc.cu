@@ -122,8 +122,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // Compile-time geometry of one conv layer
-template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_>
+template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_, bool POOL_ = false>
 struct Cfg {
+  static constexpr bool POOL = POOL_;                     // fuse the following 2x2/s2 SAME max-pool into the epilogue
   // CIN / COUT are the padded operand extents (multiples of 8 / 16); the *_REAL values are the layer's
   static constexpr int CIN_REAL = CIN_REAL_, COUT_REAL = COUT_REAL_;
   static constexpr int CIN = (CIN_REAL + 7) / 8 * 8, COUT = (COUT_REAL + 15) / 16 * 16;
@@ -151,12 +152,16 @@ struct Cfg {
   static constexpr int W_KSTEP_BYTES = 2 * (2 * COUT) * 16;   // one K-step: [2 chunks][hi rows | lo rows][8] fp16
   static constexpr int W_STAGE_BYTES = KPS * W_KSTEP_BYTES;
   static constexpr int WSTAGES = 3;
-  static constexpr int SMEM = NBUF * IN_BYTES + WSTAGES * W_STAGE_BYTES + 1024 + 256;
+  static constexpr int PHO = (H + 1) / 2, PWO = (W + 1) / 2;
+  static constexpr int PSTRIDE = COUT_REAL | 1;           // pooled-cell stride in words: odd, so neighbouring cells hit different banks
+  static constexpr int POOL_BYTES = POOL ? (PHO * PWO * PSTRIDE * 4 + 15) / 16 * 16 : 0;
+  static constexpr int SMEM = NBUF * IN_BYTES + WSTAGES * W_STAGE_BYTES + 1024 + 256 + POOL_BYTES;
   static constexpr int TMEM_COLS_USED = NACC * ACC_COLS;
   static_assert(CIN % 8 == 0, "input channels must be a multiple of 8");
   static_assert(COUT % 16 == 0 && 2 * COUT <= 256, "UMMA N");
   static_assert(TMEM_COLS_USED <= 512, "TMEM budget");
   static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(!POOL || G == 1, "fused pooling works on single-sample groups");
 };
 
 struct ConvParams {
@@ -190,6 +195,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ngroups = (p.n + C::G - 1) / C::G;
+  uint32_t* pooled = reinterpret_cast<uint32_t*>(base_ptr + C::NBUF * C::IN_BYTES + C::WSTAGES * C::W_STAGE_BYTES + 256);
+  for (int i = threadIdx.x; i < C::POOL_BYTES / 4; i += blockDim.x) pooled[i] = 0u;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmHi));
@@ -381,7 +388,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 16; ++j) w[j] = 0.f;
             }
-            if (valid) {
+            if (valid && C::POOL) {
+              // post-ReLU values are >= +0, so their bit patterns order like unsigned integers
+              uint32_t* pc = pooled + ((y >> 1) * C::PWO + (x >> 1)) * C::PSTRIDE + c0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (c0 + j < C::COUT_REAL) {
+                  const float r = (v[j] + w[j]) * p.w_scale_inv + __ldg(p.bias + c0 + j);
+                  atomicMax(pc + j, __float_as_uint(r > 0.f ? fminf(r, 65504.f) : 0.f));
+                }
+              }
+            } else if (valid) {
               uint32_t hi[8], lo[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -408,6 +425,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty(a));
+        if (C::POOL && tg == C::NG - 1) {
+          // the sample's pooled raster is complete: write it out as fp16 hi/lo planes [n][PHO][PWO][COUT] and clear it
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          constexpr int OCT = C::COUT_REAL / 8;
+          for (int item = threadIdx.x - 128; item < C::PHO * C::PWO * OCT; item += 128) {
+            const int cell = item / OCT, oct = item % OCT;
+            uint32_t* pc = pooled + cell * C::PSTRIDE + 8 * oct;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float o0 = __uint_as_float(pc[2 * j]), o1 = __uint_as_float(pc[2 * j + 1]);
+              pc[2 * j] = 0u; pc[2 * j + 1] = 0u;
+              nnal_h h0, h1, l0, l1;
+              nnal_split(o0, h0, l0);
+              nnal_split(o1, h1, l1);
+              hi[j] = nnal_pack2(h0, h1);
+              lo[j] = nnal_pack2(l0, l1);
+            }
+            const size_t ob = ((size_t)g * C::PHO * C::PWO + cell) * C::COUT_REAL + 8 * oct;
+            *reinterpret_cast<uint4*>(p.out_hi + ob) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(p.out_lo + ob) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
       }
     }
   }
@@ -484,6 +525,7 @@ typedef Cfg<25, 25, 24, 32, 5, 1, 8, 2, 3, true> CfgConv2;    // PW1 conv2: 6 M 
 // once per tile group would make conv4 L2-bound: one tile group, three MMAs per K-step
 typedef Cfg<13, 13, 32, 48, 3, 2, 6, 2, 4, false> CfgConv3;   // PW1 conv3: 2 samples, 4 M tiles
 typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2, false> CfgConv4;   // PW1 conv4: 2 M tiles
+typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2, false, true> CfgConv4Pool;   // ... with the following 2x2 max-pool fused (shared-memory atomicMax raster)
 
 template <class C>
 static bool matches(const Layer& L) {
@@ -539,6 +581,17 @@ int nnal_tc_prepare_conv(nnal_ctx* ctx, Layer& L) {
   if (ctc::matches<ctc::CfgConv3>(L)) return ctc::pack<ctc::CfgConv3>(ctx, L);
   if (ctc::matches<ctc::CfgConv4>(L)) return ctc::pack<ctc::CfgConv4>(ctx, L);
   return NNAL_OK;
+}
+
+// conv + the following 2x2/s2 SAME max-pool in one kernel: output planes are [n][ceil(H/2)][ceil(W/2)][Cout]
+bool nnal_tc_conv_pool_supported(const nnal_ctx*, const Layer& L) {
+  return L.type == NNAL_LAYER_CONV && L.Wh && ctc::matches<ctc::CfgConv4Pool>(L);
+}
+int nnal_tc_conv_pool(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
+                      nnal_h* out_lo, int64_t n) {
+  if (n == 0) return NNAL_OK;
+  if (ctc::matches<ctc::CfgConv4Pool>(L)) return ctc::launch<ctc::CfgConv4Pool>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
+  NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv+pool shape not covered by the tensor-core kernel");
 }
 
 int nnal_tc_conv(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,

@@ -102,8 +102,25 @@ int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset, bool input_is_
         } else {
           NNAL_TRY(to_split(cur));
         }
+        // narrow layers: weight-stationary kernel; when a 2x2 max-pool follows it is fused into the epilogue
+        const bool wt = ctx->use_wt >= 3 ? nnal_wt_conv_supported(ctx, L) : ctx->use_wt >= 1 && nnal_wt_conv_preferred(ctx, L);
+        const bool fuse = wt && ctx->use_wt >= 2 && i + 1 < nl - 1 && ctx->layers[i + 1].type == NNAL_LAYER_POOL &&
+                          ctx->layers[i + 1].kh == 2 && ctx->layers[i + 1].kw == 2 && nnal_wt_conv_pool_supported(ctx, L);
+        const bool fuse_tc = !wt && ctx->use_wt >= 2 && i + 1 < nl - 1 && ctx->layers[i + 1].type == NNAL_LAYER_POOL &&
+                             ctx->layers[i + 1].kh == 2 && ctx->layers[i + 1].kw == 2 && nnal_tc_conv_pool_supported(ctx, L);
+        if (fuse || fuse_tc) {
+          const Layer& P = ctx->layers[i + 1];
+          Act o; next_buf((int64_t)P.out_h * P.out_w * P.out_c, o);
+          if (fuse) NNAL_TRY(nnal_wt_conv(ctx, L, cur.hi, cur.lo, o.hi, o.lo, nb, 1));
+          else NNAL_TRY(nnal_tc_conv_pool(ctx, L, cur.hi, cur.lo, o.hi, o.lo, nb));
+          o.split = true; cur = o;
+          prof_end(ctx);
+          ++i;                                  // the pool layer is done
+          continue;
+        }
         Act o; next_buf(oe, o);
-        NNAL_TRY(nnal_tc_conv(ctx, L, cur.hi, cur.lo, o.hi, o.lo, nb));
+        if (wt) NNAL_TRY(nnal_wt_conv(ctx, L, cur.hi, cur.lo, o.hi, o.lo, nb, 0));
+        else NNAL_TRY(nnal_tc_conv(ctx, L, cur.hi, cur.lo, o.hi, o.lo, nb));
         o.split = true; cur = o;
       } else {
         NNAL_TRY(to_f32(cur));

@@ -411,7 +411,10 @@ bool nnal_tc_fc_supported(const nnal_ctx*, const Layer& L) {
 // Builds the bf16 hi/lo planes of an FC weight (called from nnal_model_set_weights).
 int nnal_tc_prepare_conv(nnal_ctx* ctx, Layer& L);
 int nnal_tc_prepare_layer(nnal_ctx* ctx, Layer& L) {
-  if (L.type == NNAL_LAYER_CONV) return nnal_tc_prepare_conv(ctx, L);
+  if (L.type == NNAL_LAYER_CONV) {
+    NNAL_TRY(nnal_tc_prepare_conv(ctx, L));
+    return nnal_wt_prepare_conv(ctx, L);
+  }
   if (L.type != NNAL_LAYER_FC || L.out_dim < 64 || L.in_dim < 64) return NNAL_OK;
   const int Kp = round_up(L.in_dim, tc::BK);
   if (!L.Wh) {

@@ -51,6 +51,7 @@ struct Layer {
   // bf16 split planes for the tensor-core path (hi = bf16(x), lo = bf16(x - hi))
   nnal_h* Wh = nullptr;
   nnal_h* Wl = nullptr;
+  void* Wt = nullptr;                    // conv: weight blocks of the weight-stationary kernel (conv_wt.cu)
   int k_pad = 0;                         // padded K of the split planes
   int n_pad = 0;                         // padded N (rows) of the split planes
   float w_scale = 1.f, w_scale_inv = 1.f; // power-of-two scale applied to the fp16 weight planes
@@ -81,6 +82,7 @@ struct nnal_ctx {
   int in_h = 0, in_w = 0, in_c = 0, n_class = 0, feature_layer = -1, feat_dim = 0;
   int fc_first = -1;                     // index of first fc layer
   int use_tc = 1;                        // tensor-core (tcgen05) path for conv/fc where supported
+  int use_wt = 2;                        // conv_wt.cu: 0 never, 1 where it is the faster kernel, 2 (default) + fused max-pool, 3 wherever it covers the layer
   // volumes
   std::vector<Volume> vols;
   DevBuf stage;                          // upload staging
@@ -191,8 +193,18 @@ int nnal_k_split_flat(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_
 int nnal_k_split_pad(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t rows, int C, int Cp);
 int nnal_k_merge_flat(nnal_ctx*, const nnal_h* hi, const nnal_h* lo, float* out, int64_t count);
 bool nnal_tc_conv_supported(const nnal_ctx*, const Layer&);
+bool nnal_tc_conv_pool_supported(const nnal_ctx*, const Layer&);
+int nnal_tc_conv_pool(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi, nnal_h* out_lo,
+                      int64_t n);
 int nnal_tc_conv(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
                  nnal_h* out_lo, int64_t n);
+// conv_wt.cu (weight-stationary tcgen05 conv, optional fused 2x2 max-pool)
+bool nnal_wt_conv_supported(const nnal_ctx*, const Layer&);
+bool nnal_wt_conv_preferred(const nnal_ctx*, const Layer&);
+bool nnal_wt_conv_pool_supported(const nnal_ctx*, const Layer&);
+int nnal_wt_prepare_conv(nnal_ctx*, Layer&);
+int nnal_wt_conv(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi, nnal_h* out_lo,
+                 int64_t n, int fuse_pool);
 int nnal_k_conv_simt_split(nnal_ctx*, const Layer&, const float* in, nnal_h* out_hi, nnal_h* out_lo, int64_t n);
 int nnal_k_pool_split(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
                       nnal_h* out_lo, int64_t n);

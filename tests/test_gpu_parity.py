@@ -252,6 +252,40 @@ def test_conv_tcgen05_vs_f64(nb, H, Cin, Cout, ks, n):
     assert err < 3e-5, 'tcgen05 conv off by %g (relative to max)' % err
 
 
+@pytest.mark.parametrize('H,Cin,Cout,ks', [(25, 24, 32, 5), (25, 3, 24, 5), (13, 32, 48, 3)])
+@pytest.mark.parametrize('n', [1, 2, 5, 300])
+def test_conv_weight_stationary_vs_f64(nb, H, Cin, Cout, ks, n):
+    """Weight-stationary tcgen05 conv (conv_wt.cu: weights on M, 256 raster positions on N, tap pairs stacked
+    in the weight rows) vs the float64 oracle, PW1 conv1/conv2/conv3 shapes; odd sample counts exercise the
+    partly filled last group and the single-raster band hand-over."""
+    rs = np.random.RandomState(7 * H + Cin + n)
+    x = np.maximum(rs.randn(n, H, H, Cin), 0).astype(np.float32)
+    W = (rs.randn(ks, ks, Cin, Cout) * np.sqrt(2. / (ks * ks * Cin))).astype(np.float32)
+    b = (rs.randn(Cout) * .1).astype(np.float32)
+    ref = np.maximum(O.conv2d_same(x.astype(np.float64), W.astype(np.float64), b.astype(np.float64)), 0)
+    scale = np.abs(ref).max()
+    got = nb.get_engine().debug_conv(x, W, b, 2)
+    err = np.abs(got - ref).max() / scale
+    assert err < 3e-5, 'weight-stationary conv off by %g (relative to max)' % err
+
+
+@pytest.mark.parametrize('H,Cin,Cout,ks,mode', [(25, 24, 32, 5, 3), (13, 48, 96, 3, 4)])
+@pytest.mark.parametrize('n', [1, 3, 300])
+def test_conv_fused_pool(nb, H, Cin, Cout, ks, mode, n):
+    """conv + the following 2x2/s2 SAME max-pool in one kernel (shared-memory atomicMax raster; conv2 on the
+    weight-stationary kernel, conv4 on the positions-on-M kernel) vs oracle conv -> oracle max_pool_same
+    (ceil mode: the last pooled row/column covers a single input row/column)."""
+    rs = np.random.RandomState(11 + n)
+    x = np.maximum(rs.randn(n, H, H, Cin), 0).astype(np.float32)
+    W = (rs.randn(ks, ks, Cin, Cout) * np.sqrt(2. / (ks * ks * Cin))).astype(np.float32)
+    b = (rs.randn(Cout) * .1).astype(np.float32)
+    ref = O.max_pool_same(np.maximum(O.conv2d_same(x.astype(np.float64), W.astype(np.float64), b.astype(np.float64)), 0))
+    got = nb.get_engine().debug_conv(x, W, b, mode)
+    assert got.shape == ref.shape == (n, (H + 1) // 2, (H + 1) // 2, Cout)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 3e-5, 'fused conv+pool off by %g (relative to max)' % err
+
+
 # ------------------------------------------------------------------ fused gather / device-resident paths
 def test_fused_gather_matches_unfused(nb):
     """The gather that writes conv1's fp16 hi/lo planes directly must give the same posteriors as the
