@@ -26,7 +26,8 @@
 //     once per tile group): 2 x TG x 2Cout accumulator columns fit TMEM, so the epilogue of one tile group
 //     overlaps the MMAs of the next.
 // Warp roles: warp 0 input TMA, warp 3 weight producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-7 epilogue (TMEM -> +bias, ReLU -> bf16 hi/lo NHWC in global memory).
+// warps 4-11 epilogue (TMEM -> +bias, ReLU -> fp16 hi/lo NHWC in global memory, or the fused max-pool raster):
+// two warpgroups, one per accumulator.
 #include "nnal_common.cuh"
 #include <cuda.h>
 
@@ -154,14 +155,15 @@ struct Cfg {
   static constexpr int WSTAGES = 3;
   static constexpr int PHO = (H + 1) / 2, PWO = (W + 1) / 2;
   static constexpr int PSTRIDE = COUT_REAL | 1;           // pooled-cell stride in words: odd, so neighbouring cells hit different banks
-  static constexpr int POOL_BYTES = POOL ? (PHO * PWO * PSTRIDE * 4 + 15) / 16 * 16 : 0;
+  static constexpr int POOL_WORDS = (PHO * PWO * PSTRIDE + 3) / 4 * 4;    // one pooled raster per epilogue warpgroup
+  static constexpr int POOL_BYTES = POOL ? 2 * POOL_WORDS * 4 : 0;
   static constexpr int SMEM = NBUF * IN_BYTES + WSTAGES * W_STAGE_BYTES + 1024 + 256 + POOL_BYTES;
   static constexpr int TMEM_COLS_USED = NACC * ACC_COLS;
   static_assert(CIN % 8 == 0, "input channels must be a multiple of 8");
   static_assert(COUT % 16 == 0 && 2 * COUT <= 256, "UMMA N");
   static_assert(TMEM_COLS_USED <= 512, "TMEM budget");
   static_assert(SMEM <= 232448, "shared memory budget");
-  static_assert(!POOL || G == 1, "fused pooling works on single-sample groups");
+  static_assert(!POOL || (G == 1 && NG == 1), "fused pooling: one sample = one tile group = one epilogue warpgroup");
 };
 
 struct ConvParams {
@@ -174,7 +176,7 @@ struct ConvParams {
 };
 
 template <class C>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -356,12 +358,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue =====
+    // ===== epilogue: two warpgroups, warpgroup wg drains accumulator wg (every other tile group) =====
     const int qd = warp & 3;
+    const int wg = (warp - 4) >> 2;
+    uint32_t* my_pooled = pooled + wg * C::POOL_WORDS;
     uint32_t it = 0;
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
 #pragma unroll 1
       for (int tg = 0; tg < C::NG; ++tg, ++it) {
+        if ((int)(it % C::NACC) != wg) continue;
         const int a = it % C::NACC;
         const uint32_t ph_acc = (it / C::NACC) & 1;
         mbar_wait(acc_full(a), ph_acc);
@@ -390,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             }
             if (valid && C::POOL) {
               // post-ReLU values are >= +0, so their bit patterns order like unsigned integers
-              uint32_t* pc = pooled + ((y >> 1) * C::PWO + (x >> 1)) * C::PSTRIDE + c0;
+              uint32_t* pc = my_pooled + ((y >> 1) * C::PWO + (x >> 1)) * C::PSTRIDE + c0;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 if (c0 + j < C::COUT_REAL) {
@@ -427,11 +432,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         if (lane == 0) mbar_arrive(acc_empty(a));
         if (C::POOL && tg == C::NG - 1) {
           // the sample's pooled raster is complete: write it out as fp16 hi/lo planes [n][PHO][PWO][COUT] and clear it
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
           constexpr int OCT = C::COUT_REAL / 8;
-          for (int item = threadIdx.x - 128; item < C::PHO * C::PWO * OCT; item += 128) {
+          for (int item = (threadIdx.x - 128) & 127; item < C::PHO * C::PWO * OCT; item += 128) {
             const int cell = item / OCT, oct = item % OCT;
-            uint32_t* pc = pooled + cell * C::PSTRIDE + 8 * oct;
+            uint32_t* pc = my_pooled + cell * C::PSTRIDE + 8 * oct;
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -447,7 +452,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             *reinterpret_cast<uint4*>(p.out_hi + ob) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4*>(p.out_lo + ob) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
         }
       }
     }
@@ -560,7 +565,7 @@ static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal
   p.wpack = (const uint8_t*)L.Wh; p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.n = (int)n; p.w_scale_inv = L.w_scale_inv;
   const int ngroups = (int)((n + C::G - 1) / C::G);
   const int grid = ngroups < ctx->sm_count ? ngroups : ctx->sm_count;
-  conv_tc_kernel<C><<<grid, 256, C::SMEM, ctx->stream>>>(tmHi, tmLo, p);
+  conv_tc_kernel<C><<<grid, 384, C::SMEM, ctx->stream>>>(tmHi, tmLo, p);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;

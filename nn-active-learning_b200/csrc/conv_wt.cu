@@ -15,24 +15,26 @@
 //     same "shift = descriptor start address" trick as conv_tc.cu: no im2col), so one MMA runs 128 tensor-core
 //     cycles against 96 cycles of operand fetch (4 KB of weights + 8 KB of positions): math bound.
 //   * A operand = weights.  Cout is far below 128, so the 128 rows stack what would otherwise be separate MMAs:
-//     TAPS = 2:  rows = [W_hi(tap a) | W_lo(tap a) | W_hi(tap b) | W_lo(tap b)],  b = a + (0,1)   (conv1, conv2)
+//     TAPS = 2:  rows = [W_hi(tap a) | W_lo(tap a) | W_hi(tap b) | W_lo(tap b)],  b = a + (0,2)   (conv1, conv2)
 //     TAPS = 1:  rows = [W_hi(tap a) | W_lo(tap a)]                                             (conv3)
 //     One MMA with B = X_hi therefore yields hi.hi and hi.lo of two taps at once; a second MMA with the SAME A
 //     block and B = X_lo adds lo.hi (and the harmless 2^-22 lo.lo).  The partial sums of tap b belong to the
-//     output one position to the left: out[p] = D_a[p] + D_b[p + 1].  A shift along N is a TMEM *column* offset,
-//     i.e. free for tcgen05.ld; tiles advance by 255 positions so that column p + 1 always exists.
+//     output two positions to the left: out[p] = D_a[p] + D_b[p + 2].  A shift along N is a TMEM *column* offset,
+//     i.e. free for tcgen05.ld; tiles advance by 248 positions so that the shifted columns always exist.
+//     (A tcgen05.mma with M = 128 costs max(64, N/2) cycles whatever N is -- scripts/microbench/mma_rate.cu -- so
+//     any N below 128 wastes the tensor core; that, not operand fetch alone, is what bounds conv_tc.cu.)
 //   * All weight blocks of the layer (conv2: 23 x 4 KB) stay resident in shared memory for the life of the CTA:
 //     no weight streaming at all.  That leaves room for only ONE input raster (conv2: 81 KB), which is loaded in
 //     two row bands with separate full/empty barriers: the lower band of the next sample arrives while the last
 //     tile of the current sample is still being multiplied.
-//   * Epilogue (two warpgroups on alternate 32-column sub-blocks, each warp on its own TMEM lane quadrant): the
-//     partial sums of a channel (hi/lo weight rows, two tap groups) sit in different LANES of the same warp, so they
-//     are added with a shuffle transpose-reduce -- each exchange halves the columns a lane keeps -- and every lane
-//     ends up with 8 (16) consecutive positions of one channel: bias, ReLU, then either fp16 hi/lo planes in global
-//     memory, or (POOL) an atomicMax into a pooled raster in shared memory that is written out once per sample: the
-//     separate max-pool pass and the full-size activation round trip through HBM disappear.  No shared-memory
-//     staging and no barriers between epilogue warps: the first version staged through shared memory and lost 30 %
-//     of the MMA rate to the bandwidth it took from the operand fetch (profiles/).
+//   * Epilogue (NEW warpgroups on alternate 32-column sub-blocks, each warp on its own TMEM lane quadrant): the
+//     partial sums of a channel (hi/lo weight rows, two tap groups) are stacked 8 rows apart, and
+//     tcgen05.ld.16x256b delivers rows r and r + 8 to the SAME thread, so they add up in registers -- no shuffles,
+//     no shared-memory staging, no barriers between epilogue warps.  Then bias, ReLU, and either fp16 hi/lo planes
+//     in global memory or (POOL) an atomicMax into a pooled raster in shared memory that is written out once per
+//     sample: the separate max-pool pass and the full-size activation round trip through HBM disappear.
+//     (History, profiles/r1_conv_wt.md: a shared-memory staged epilogue cost 30 % of the MMA rate through the
+//     bandwidth it took from the operand fetch; a shuffle transpose-reduce was instruction bound.)
 // Precision: fp16 hi/lo split operands, FP32 accumulation in TMEM, as conv_tc.cu / gemm_tc.cu.
 // Warp roles: warp 0 input TMA, warp 1 MMA issuer, warp 2 TMEM allocator + one-off weight load, warps 4.. epilogue
 // (the next sub-block's tcgen05.ld is in flight while the current one is stored).
@@ -54,11 +56,14 @@ struct Cfg {
   static constexpr int COUT_MAX = 16 * CBT;
   static constexpr int PH = KS / 2, HP = H + KS - 1, WP = W + KS - 1;
   static constexpr int RASTER1 = HP * WP, RASTER = G * RASTER1;
-  static constexpr int NSLOT_ROW = (KS + TAPS - 1) / TAPS;    // B shifts per filter row (tap pairs along dx)
+  // B shifts per filter row.  TAPS == 2 pairs the taps (dx, dx + 2): dx_a = 0, 1, 4, 5, 8, ... (the TMEM column offset
+  // of tcgen05.ld.16x256b must be even, so the pair distance is 2, not 1)
+  static constexpr int NSLOT_ROW = TAPS == 1 ? KS : (KS / 4) * 2 + (KS % 4 < 2 ? KS % 4 : 2);
+  __host__ __device__ static constexpr int dx_a(int pr) { return TAPS == 1 ? pr : 4 * (pr / 2) + pr % 2; }
   static constexpr int NSLOT = KS * NSLOT_ROW;
   static constexpr int NCS = NSLOT * Q;                   // (slot, 8-channel chunk) pairs = K / 8
   static constexpr int NBLK = (NCS + 1) / 2;              // K = 16 weight blocks (4 KB each)
-  static constexpr int TILE_N = 256, TILE_OUT = TILE_N - (TAPS - 1);
+  static constexpr int TILE_N = 256, TILE_OUT = TAPS == 2 ? TILE_N - 8 : TILE_N;   // TAPS == 2: tap group b is read 2 columns further; its last 8-column block is not
   static constexpr int LAST_VALID = (G - 1) * RASTER1 + (H - 1) * WP + (W - 1);
   static constexpr int T = LAST_VALID / TILE_OUT + 1;     // position tiles per sample group
   static constexpr int MAX_OFF = (KS - 1) * WP + (KS - 1);
@@ -69,7 +74,7 @@ struct Cfg {
   static constexpr int NBUF = SPLIT ? 1 : 2;
   static constexpr int W_BYTES = NBLK * 4096;
   static constexpr int PHO = (H + 1) / 2, PWO = (W + 1) / 2;
-  static constexpr int PSTRIDE = COUT_MAX + 2;             // pooled-cell stride (words): lanes 4 cells apart land in different banks
+  static constexpr int PSTRIDE = COUT_MAX + 8;             // pooled-cell stride (words), = 8 mod 32: the 4 cells a warp touches per atomic land in different banks
   static constexpr int POOL_BYTES = POOL ? (PHO * PWO * PSTRIDE * 4 + 15) / 16 * 16 : 0;
   static constexpr int SMEM = NBUF * IN_BYTES + W_BYTES + POOL_BYTES + 1024 + 256;
   static constexpr int BYTES_L = 2 * Q * (SPLIT ? RL : HP) * WP * 16 * G;        // TMA bytes of the first band / whole raster
@@ -93,6 +98,7 @@ struct Params {
   nnal_h* out_lo;
   int n;
   float w_scale_inv;
+  int flags;                // diagnostics (NNAL_WT_FLAGS): 1 = skip the output stores / pool atomics (timing experiments only)
 };
 
 template <class C>
@@ -151,7 +157,7 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmHiL, const __grid_constant_
   for (int blk = threadIdx.x; blk < C::NBLK; blk += blockDim.x) {
     auto off_of = [](int cs) {
       const int q = cs / C::NSLOT, s = cs % C::NSLOT;
-      const int dy = s / C::NSLOT_ROW, dx = (s % C::NSLOT_ROW) * C::TAPS;
+      const int dy = s / C::NSLOT_ROW, dx = C::dx_a(s % C::NSLOT_ROW);
       return (uint32_t)(q * C::PLANE + (dy * C::WP + dx) * 16);
     };
     const uint32_t off0 = off_of(2 * blk);
@@ -257,96 +263,94 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmHiL, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===== epilogue: NEW warpgroups, each takes every NEW-th 32-column sub-block of every tile; warps never meet =====
-    // A warp owns one TMEM lane quadrant = 32 stacked weight rows = PARTS partial sums of CPW channels:
-    //   TAPS == 2: lane = 8 * part + c,  part = 2 * tap_group + term   (hi a, lo a, hi b, lo b),  channel 8 w + c
-    //   TAPS == 1: lane = 16 * term + c                                 (hi a, lo a),              channel 16 w + c
-    // The partial sums are added with a shuffle "transpose-reduce": in every exchange step a lane keeps half of
-    // its columns and receives the partner's partial sums for exactly those, so after log2(PARTS) steps lane L
-    // holds the complete sums of 32 / PARTS consecutive positions of one channel -- no shared memory, no barriers.
+    // A warp owns one TMEM lane quadrant = 32 stacked weight rows, read as two 16-lane halves with tcgen05.ld.16x256b,
+    // which hands rows r and r + 8 of a half to the SAME thread (thread T: rows T/4, T/4 + 8; columns 2 (T%4) + {0,1} of
+    // every 8-column block).  The weight rows are ordered so that everything a thread receives belongs together:
+    //   TAPS == 2: half = tap group, rows 0-7 W_hi / rows 8-15 W_lo of channels 8 w + 0..7; tap group b is read two
+    //              columns further (out[p] = D_a[p] + D_b[p + 2]): 4 partial sums, 3 adds, no shuffles, no selects
+    //   TAPS == 1: half = channel block, rows 0-7 W_hi / rows 8-15 W_lo of channels 16 w + 8 half + 0..7
+    // so a thread ends up with 8 output positions of one channel (two channels for TAPS == 1).
     const int wgi = (warp - 4) >> 2;
     const int w = warp & 3;
-    constexpr int PARTS = 2 * C::TAPS, CPW = 32 / PARTS, NPOS = 32 / PARTS;
     constexpr int NSB = C::TILE_N / 32;
-    const int c = lane & (CPW - 1);
-    const int co = CPW * w + c;
-    const bool h1 = (lane & 16) != 0;             // TAPS == 2: tap group b (columns shifted by one); keeps columns 16..31
-    const bool h0 = (lane & 8) != 0;              // TAPS == 2: lo-term row; keeps the upper 8 of its 16 columns
-    const bool ch_ok = co < C::COUT_REAL;
-    const float bias = ch_ok ? __ldg(p.bias + co) : 0.f;
+    constexpr int NCH = C::TAPS == 2 ? 1 : 2;               // channels per thread
+    const int cq = lane >> 2, m = lane & 3;
+    int co[NCH];
+    float bias[NCH];
+    uint32_t chlim[NCH];
+#pragma unroll
+    for (int h = 0; h < NCH; ++h) {
+      co[h] = C::TAPS == 2 ? 8 * w + cq : 16 * w + 8 * h + cq;
+      bias[h] = co[h] < C::COUT_REAL ? __ldg(p.bias + co[h]) : 0.f;
+    }
     uint32_t it = 0;
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+      // outputs of this sample group: table offsets are relative to its first sample; a partly filled last group
+      // (or a channel beyond COUT_REAL) is cut off by the limit
+      constexpr int SAMPLE_ELEMS = C::H * C::W * C::COUT_REAL;
+      nnal_h* ghi = p.out_hi + (size_t)g * C::G * SAMPLE_ELEMS;
+      nnal_h* glo = p.out_lo + (size_t)g * C::G * SAMPLE_ELEMS;
+      const int left = p.n - g * C::G;
+#pragma unroll
+      for (int h = 0; h < NCH; ++h)
+        chlim[h] = co[h] >= C::COUT_REAL ? 0u : C::POOL ? 0x7fffffffu : (uint32_t)((left < C::G ? left : C::G) * SAMPLE_ELEMS);
 #pragma unroll 1
       for (int t = 0; t < C::T; ++t, ++it) {
         const int a = it & 1;
         const uint32_t ph_acc = (it >> 1) & 1;
         mbar_wait(acc_full(a), ph_acc);
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(a * C::TILE_N);
-        // outputs of this sample group: table offsets are relative to its first sample; a partly filled last group
-        // (or a channel beyond COUT_REAL) is cut off by the limit
-        constexpr int SAMPLE_ELEMS = C::H * C::W * C::COUT_REAL;
-        nnal_h* ghi = p.out_hi + (size_t)g * C::G * SAMPLE_ELEMS + co;
-        nnal_h* glo = p.out_lo + (size_t)g * C::G * SAMPLE_ELEMS + co;
-        const int left = p.n - g * C::G;
-        const uint32_t lim = !ch_ok ? 0u : C::POOL ? 0x7fffffffu : (uint32_t)((left < C::G ? left : C::G) * SAMPLE_ELEMS);
-        uint32_t r[32];
-        uint32_t rx = 0;                          // column sb * 32 + 32 (first column of the next sub-block) for tap group b
-        tmem_ld32_issue(trow + wgi * 32, r);
-        if (C::TAPS == 2 && wgi < NSB - 1) tmem_ld1_issue(trow + wgi * 32 + 32, rx);
+        const uint32_t trowA = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(a * C::TILE_N);
+        const uint32_t trowB = trowA + (16u << 16) + (C::TAPS == 2 ? 2u : 0u);
+        uint32_t ra[16], rb[16];
+        auto issue = [&](int sb) {
+          tmem_ld16x256_x4_issue(trowA + sb * 32, ra);
+          if (C::TAPS == 2 && sb == NSB - 1) {
+            // columns TILE_N, TILE_N + 1 do not exist: the last 8-column block of tap group b (outputs >= TILE_OUT) is skipped
+            tmem_ld16x256_x2_issue(trowB + sb * 32, rb);
+            tmem_ld16x256_x1_issue(trowB + sb * 32 + 16, rb + 8);
+            rb[12] = rb[13] = rb[14] = rb[15] = 0u;
+          } else {
+            tmem_ld16x256_x4_issue(trowB + sb * 32, rb);
+          }
+        };
+        issue(wgi);
 #pragma unroll 1
         for (int sb = wgi; sb < NSB; sb += C::NEW) {
-          tmem_ld32_wait(r, rx);
-          float z[NPOS];
-          if (C::TAPS == 2) {
-            float v[33];
+          tmem_ld_wait_2x16(ra, rb);
+          float z[NCH][8];                         // [channel][block i, column k]: position 8 i + 2 m + k of the sub-block
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            v[32] = __uint_as_float(rx);
-            float y[16];
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {          // tap groups: partner lane ^ 16
-              const float keep = h1 ? v[j + 17] : v[j];
-              const float send = h1 ? v[j + 1] : v[j + 16];
-              y[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            for (int k = 0; k < 2; ++k) {
+              const float sa = __uint_as_float(ra[4 * i + k]) + __uint_as_float(ra[4 * i + 2 + k]);
+              const float sb_ = __uint_as_float(rb[4 * i + k]) + __uint_as_float(rb[4 * i + 2 + k]);
+              if (C::TAPS == 2) z[0][2 * i + k] = sa + sb_;
+              else { z[0][2 * i + k] = sa; z[NCH - 1][2 * i + k] = sb_; }
             }
+          if (sb + C::NEW < NSB) issue(sb + C::NEW);                      // next sub-block in flight during the stores
+          // output offsets (or -1) of this thread's positions from the table
+          const int* ot = otab + t * C::TILE_N + sb * 32 + 2 * m;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {           // hi / lo weight rows: partner lane ^ 8
-              const float keep = h0 ? y[j + 8] : y[j];
-              const float send = h0 ? y[j] : y[j + 8];
-              z[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-          } else {
+          for (int i = 0; i < 4; ++i) {
+            const int2 o2 = *reinterpret_cast<const int2*>(ot + 8 * i);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {          // hi / lo weight rows: partner lane ^ 16
-              const float keep = __uint_as_float(h1 ? r[j + 16] : r[j]);
-              const float send = __uint_as_float(h1 ? r[j] : r[j + 16]);
-              z[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-          }
-          if (sb + C::NEW < NSB) {                                        // next sub-block in flight during the stores
-            tmem_ld32_issue(trow + (sb + C::NEW) * 32, r);
-            if (C::TAPS == 2 && sb + C::NEW < NSB - 1) tmem_ld1_issue(trow + (sb + C::NEW) * 32 + 32, rx);
-          }
-          // lane holds NPOS consecutive positions of channel co; their output offsets (or -1) come from the table
-          const int col0 = sb * 32 + NPOS * (lane / CPW);
-          int off[NPOS];
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t off = (uint32_t)(k ? o2.y : o2.x);
 #pragma unroll
-          for (int j = 0; j < NPOS; j += 4) {
-            const int4 o4 = *reinterpret_cast<const int4*>(otab + t * C::TILE_N + col0 + j);
-            off[j] = o4.x; off[j + 1] = o4.y; off[j + 2] = o4.z; off[j + 3] = o4.w;
-          }
-#pragma unroll
-          for (int j = 0; j < NPOS; ++j) {
-            if ((uint32_t)off[j] < lim) {                                 // -1 (padding / garbage column) fails too
-              const float rr = z[j] * p.w_scale_inv + bias;
-              const float o = rr > 0.f ? fminf(rr, 65504.f) : 0.f;
-              if (C::POOL) {
-                atomicMax(pooled + off[j] + co, __float_as_uint(o));      // o >= +0: uint order == float order
-              } else {
-                const nnal_h hh = __float2half_rn(o);
-                const nnal_h ll = __float2half_rn(o - __half2float(hh));
-                ghi[off[j]] = hh;
-                glo[off[j]] = ll;
+              for (int h = 0; h < NCH; ++h) {
+                if (off < chlim[h] && !(p.flags & 1)) {                   // -1 (padding / garbage column) fails too
+                  const float rr = z[h][2 * i + k] * p.w_scale_inv + bias[h];
+                  const float o = rr > 0.f ? fminf(rr, 65504.f) : 0.f;
+                  if (C::POOL) {
+                    atomicMax(pooled + off + co[h], __float_as_uint(o));  // o >= +0: uint order == float order
+                  } else {
+                    const nnal_h hh = __float2half_rn(o);
+                    const nnal_h ll = __float2half_rn(o - __half2float(hh));
+                    ghi[off + co[h]] = hh;
+                    glo[off + co[h]] = ll;
+                  }
+                }
               }
             }
           }
@@ -399,14 +403,15 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, nnal_h* __restr
     const int blk = e / (8 * 128 * 2);
     const int cs = 2 * blk + h;
     float w = 0.f;
-    // row = 32 w + lane;  TAPS == 2: lane = 8 * (2 * tg + term) + c, channel 8 w + c;  TAPS == 1: lane = 16 * term + c, channel 16 w + c
+    // row = 32 w + lane;  TAPS == 2: lane = 16 * tg + 8 * term + c, channel 8 w + c
+    //                     TAPS == 1: lane = 16 * half + 8 * term + c, channel 16 w + 8 * half + c
     const int wq = row / 32, ln = row % 32;
     const int tg = C::TAPS == 2 ? ln / 16 : 0;
-    const int term = C::TAPS == 2 ? (ln / 8) % 2 : ln / 16;
-    const int co = C::TAPS == 2 ? 8 * wq + ln % 8 : 16 * wq + ln % 16;
+    const int term = (ln / 8) % 2;
+    const int co = C::TAPS == 2 ? 8 * wq + ln % 8 : 16 * wq + 8 * (ln / 16) + ln % 8;
     if (cs < C::NCS) {
       const int q = cs / C::NSLOT, s = cs % C::NSLOT;
-      const int dy = s / C::NSLOT_ROW, dx = (s % C::NSLOT_ROW) * C::TAPS + tg;
+      const int dy = s / C::NSLOT_ROW, dx = C::dx_a(s % C::NSLOT_ROW) + 2 * tg;
       const int ci = q * 8 + k8;
       if (dx < C::KS && ci < C::CIN_REAL && co < C::COUT_REAL)
         w = W[(((size_t)dy * C::KS + dx) * C::CIN_REAL + ci) * C::COUT_REAL + co] * scale;
@@ -489,6 +494,7 @@ static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal
   }
   Params p;
   p.wpack = (const uint8_t*)L.Wt; p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.n = (int)n; p.w_scale_inv = L.w_scale_inv;
+  { const char* f = getenv("NNAL_WT_FLAGS"); p.flags = f ? atoi(f) : 0; }
   const int ngroups = (int)((n + C::G - 1) / C::G);
   const int grid = ngroups < ctx->sm_count ? ngroups : ctx->sm_count;
   conv_wt_kernel<C><<<grid, C::THREADS, C::SMEM, ctx->stream>>>(tmHiL, tmLoL, tmHiU, tmLoU, p);

@@ -1,0 +1,76 @@
+// Microbenchmark: cycles per tcgen05.mma (kind::f16, M = 128, K = 16, SS mode, no-swizzle K-major operands) as a
+// function of N and of the number of TMEM accumulators the instruction stream rotates over.  Answers the question
+// "what does a narrow MMA really cost" that decides the tiling of the conv kernels.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_rate mma_rate.cu && ./mma_rate
+#include "../../nn-active-learning_b200/csrc/tc_ptx.cuh"
+#include <cstdio>
+using namespace tcx;
+
+__global__ void __launch_bounds__(128, 1) k(int N, int nacc, int iters, int a_stride16, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* bp = smem_raw + (base - raw);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(bp)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 0) {
+    long long t0 = 0, t1 = 0;
+    if (elect_one_sync()) {
+      const uint32_t idesc = make_idesc_bf16(128, N);
+      constexpr uint32_t DESC_HI = 8u | (1u << 14);
+      const uint32_t a16 = base >> 4, b16 = (base + 64 * 1024) >> 4;
+      const uint32_t A_LBO = (2048u >> 4) << 16, B_LBO = ((uint32_t)(N * 16) >> 4) << 16;
+      const int stride = 512 / nacc;
+      t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        const uint64_t dA = ((uint64_t)DESC_HI << 32) | ((a16 + (uint32_t)(i & 7) * a_stride16) | A_LBO);
+        const uint64_t dB = ((uint64_t)DESC_HI << 32) | ((b16 + (uint32_t)(i & 3) * 512u) | B_LBO);
+        umma_bf16(tmem + (i % nacc) * stride, dA, dB, idesc, 1);
+      }
+      umma_commit(smem_u32(&bar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = t1 - t0; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512)); }
+}
+
+int main() {
+  long long* d; cudaMalloc(&d, 8);
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int iters = 4096;
+  printf("cycles per MMA (M=128, K=16, f16, SS, no-swizzle), one CTA per SM on all 148 SMs; A operand: 8 different 4 KB blocks\n");
+  printf("%6s | %8s %8s %8s %8s %8s | floor N/2, fetch (4KB + N*32B)/128\n", "N", "acc=1", "acc=2", "acc=4", "acc=8", "same A");
+  int Ns[] = {16, 24, 32, 48, 64, 96, 128, 192, 256};
+  for (int N : Ns) {
+    printf("%6d |", N);
+    for (int v = 0; v < 5; ++v) {
+      int nacc = v < 4 ? (1 << v) : 4;
+      if (512 / nacc < N) { printf(" %8s", "-"); continue; }
+      int a_stride16 = v < 4 ? 256 : 0;
+      k<<<148, 128, 200 * 1024>>>(N, nacc, iters, a_stride16, d);
+      long long h = 0;
+      cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) { printf(" err:%s", cudaGetErrorString(e)); return 1; }
+      printf(" %8.1f", (double)h / iters);
+    }
+    printf(" | %5.0f %5.1f\n", N / 2.0, (4096 + N * 32) / 128.0);
+  }
+  return 0;
+}
