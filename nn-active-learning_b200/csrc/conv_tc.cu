@@ -153,6 +153,7 @@ struct Cfg {
   static constexpr int W_KSTEP_BYTES = 2 * (2 * COUT) * 16;   // one K-step: [2 chunks][hi rows | lo rows][8] fp16
   static constexpr int W_STAGE_BYTES = KPS * W_KSTEP_BYTES;
   static constexpr int WSTAGES = 3;
+  static constexpr bool WRES = NSTAGE_W <= WSTAGES;       // the whole weight set fits the ring: load it once, keep it resident
   static constexpr int PHO = (H + 1) / 2, PWO = (W + 1) / 2;
   static constexpr int PSTRIDE = COUT_REAL | 1;           // pooled-cell stride in words: odd, so neighbouring cells hit different banks
   static constexpr int POOL_WORDS = (PHO * PWO * PSTRIDE + 3) / 4 * 4;    // one pooled raster per epilogue warpgroup
@@ -260,7 +261,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     }
   } else if (warp == 3) {
     // ===== weight producer: one contiguous bulk copy per stage =====
-    if (lane == 0) {
+    if (lane == 0 && C::WRES) {
+      for (int ws = 0; ws < C::NSTAGE_W; ++ws) {
+        mbar_arrive_expect_tx(w_full(ws), C::W_STAGE_BYTES);
+        bulk_load(w_base + ws * C::W_STAGE_BYTES, p.wpack + (size_t)ws * C::W_STAGE_BYTES, C::W_STAGE_BYTES, w_full(ws));
+      }
+    } else if (lane == 0) {
       uint32_t it = 0;
       for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
         for (int ws = 0; ws < C::NG * C::NSTAGE_W; ++ws, ++it) {
@@ -298,8 +304,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
           const uint32_t d_base = tmem_base + a * C::ACC_COLS;
           const uint32_t tile0 = (uint32_t)(tg * C::TG) * 128u;       // first raster position of the tile group (>>4 units: x128 = 16 B x 128 / 16)
           for (int ws = 0; ws < C::NSTAGE_W; ++ws, ++it_w) {
-            const int s = it_w % C::WSTAGES;
-            const uint32_t ph = (it_w / C::WSTAGES) & 1;
+            const int s = C::WRES ? ws : it_w % C::WSTAGES;
+            const uint32_t ph = C::WRES ? 0u : (it_w / C::WSTAGES) & 1;      // resident: phase 0 completes once and stays complete
             mbar_wait(w_full(s), ph);
             tc_fence_after();
             const uint32_t wb16 = (w_base + s * C::W_STAGE_BYTES) >> 4;
@@ -345,7 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                   }
                 }
               }
-              umma_commit(w_empty(s));
+              if (!C::WRES) umma_commit(w_empty(s));
             }
             __syncwarp();
           }
@@ -526,8 +532,10 @@ static int make_act_tmap(nnal_ctx* ctx, CUtensorMap* tm, const void* ptr, int n,
 //                 H   W  CIN COUT KS G KPS NBUF TG CAT
 typedef Cfg<25, 25, 3, 24, 5, 1, 7, 2, 3, true> CfgConv1;     // PW1 conv1: 3 input channels zero-padded to one 8-channel chunk
 typedef Cfg<25, 25, 24, 32, 5, 1, 8, 2, 3, true> CfgConv2;    // PW1 conv2: 6 M tiles in 2 groups of 3
-// conv3/conv4: N is large enough that the concatenated form gains nothing and streaming the (larger) weight set
-// once per tile group would make conv4 L2-bound: one tile group, three MMAs per K-step
+// conv3/conv4: the concatenated form was measured for conv3 (TG = 2, N = 96 + 48): 2.63 ms vs 2.61 ms per 100k samples
+// -- with only two accumulators in rotation the MMAs wait on each other (scripts/microbench/mma_rate.cu: 129 cycles
+// per K-step and tile at TG = 2 against 100 at TG = 4), and four tiles of 96 columns do not fit TMEM twice.  conv4
+// would need 2 x 192 columns per tile and its 166 KB weight set streamed once per tile (L2-bound).
 typedef Cfg<13, 13, 32, 48, 3, 2, 6, 2, 4, false> CfgConv3;   // PW1 conv3: 2 samples, 4 M tiles
 typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2, false> CfgConv4;   // PW1 conv4: 2 M tiles
 typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2, false, true> CfgConv4Pool;   // ... with the following 2x2 max-pool fused (shared-memory atomicMax raster)

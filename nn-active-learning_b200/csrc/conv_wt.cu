@@ -21,8 +21,8 @@
 //     block and B = X_lo adds lo.hi (and the harmless 2^-22 lo.lo).  The partial sums of tap b belong to the
 //     output two positions to the left: out[p] = D_a[p] + D_b[p + 2].  A shift along N is a TMEM *column* offset,
 //     i.e. free for tcgen05.ld; tiles advance by 248 positions so that the shifted columns always exist.
-//     (A tcgen05.mma with M = 128 costs max(64, N/2) cycles whatever N is -- scripts/microbench/mma_rate.cu -- so
-//     any N below 128 wastes the tensor core; that, not operand fetch alone, is what bounds conv_tc.cu.)
+//     (scripts/microbench/mma_rate.cu: an M = 128, K = 16 MMA costs max(N/2, (4 KB + 32 N) / 128 B/clk) cycles, so below
+//     N = 128 the 4 KB A read dominates and the tensor core idles: N = 32 runs at 40 % of the math rate at best.)
 //   * All weight blocks of the layer (conv2: 23 x 4 KB) stay resident in shared memory for the life of the CTA:
 //     no weight streaming at all.  That leaves room for only ONE input raster (conv2: 81 KB), which is loaded in
 //     two row bands with separate full/empty barriers: the lower band of the next sample arrives while the last

@@ -34,10 +34,62 @@ __global__ void __launch_bounds__(128, 1) k(int N, int nacc, int iters, int a_st
       const uint32_t A_LBO = (2048u >> 4) << 16, B_LBO = ((uint32_t)(N * 16) >> 4) << 16;
       const int stride = 512 / nacc;
       t0 = clock64();
+      int acc = 0;                              // no division in the issue loop: it must not be the bottleneck
       for (int i = 0; i < iters; ++i) {
         const uint64_t dA = ((uint64_t)DESC_HI << 32) | ((a16 + (uint32_t)(i & 7) * a_stride16) | A_LBO);
         const uint64_t dB = ((uint64_t)DESC_HI << 32) | ((b16 + (uint32_t)(i & 3) * 512u) | B_LBO);
-        umma_bf16(tmem + (i % nacc) * stride, dA, dB, idesc, 1);
+        umma_bf16(tmem + acc, dA, dB, idesc, 1);
+        acc += stride;
+        if (acc >= 512) acc = 0;
+      }
+      umma_commit(smem_u32(&bar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = t1 - t0; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512)); }
+}
+
+
+// conv_tc.cu issue pattern: for every K-step, TG MMAs (N1) into TG accumulators, then TG MMAs (N2) into the same ones
+__global__ void __launch_bounds__(128, 1) kcat(int N1, int N2, int TG, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* bp = smem_raw + (base - raw);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(bp)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 0) {
+    long long t0 = 0, t1 = 0;
+    if (elect_one_sync()) {
+      const uint32_t id1 = make_idesc_bf16(128, N1), id2 = make_idesc_bf16(128, N2);
+      constexpr uint32_t DESC_HI = 8u | (1u << 14);
+      const uint32_t a16 = base >> 4, b16 = (base + 64 * 1024) >> 4;
+      const uint32_t A_LBO = (2048u >> 4) << 16, B_LBO = ((uint32_t)(N1 * 16) >> 4) << 16;
+      t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        const uint64_t dB = ((uint64_t)DESC_HI << 32) | ((b16 + (uint32_t)(i & 3) * 512u) | B_LBO);
+        for (int t = 0; t < TG; ++t)
+          umma_bf16(tmem + t * N1, ((uint64_t)DESC_HI << 32) | ((a16 + (uint32_t)t * 128u) | A_LBO), dB, id1, 1);
+        if (N2 > 0)
+          for (int t = 0; t < TG; ++t)
+            umma_bf16(tmem + t * N1, ((uint64_t)DESC_HI << 32) | ((a16 + 2048u + (uint32_t)t * 128u) | A_LBO), dB, id2, 1);
       }
       umma_commit(smem_u32(&bar));
     }
@@ -71,6 +123,16 @@ int main() {
       printf(" %8.1f", (double)h / iters);
     }
     printf(" | %5.0f %5.1f\n", N / 2.0, (4096 + N * 32) / 128.0);
+  }
+  cudaFuncSetAttribute(kcat, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  printf("\nconv_tc.cu issue pattern: per K-step TG x MMA(N1) then TG x MMA(N2) into the same TG accumulators; cycles per K-step per tile\n");
+  int pats[][3] = {{64, 32, 3}, {48, 24, 3}, {96, 48, 2}, {96, 48, 4}, {96, 0, 2}, {48, 0, 4}, {192, 96, 1}, {192, 96, 2}, {256, 128, 2}, {128, 64, 2}};
+  for (auto& pt : pats) {
+    kcat<<<148, 128, 200 * 1024>>>(pt[0], pt[1], pt[2], 1024, d);
+    long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { printf(" err:%s\n", cudaGetErrorString(e)); return 1; }
+    printf("N1 %3d N2 %3d TG %d : %7.1f cycles per K-step per tile (%d MMAs)\n", pt[0], pt[1], pt[2], (double)h / 1024 / pt[2], pt[1] > 0 ? 2 : 1);
   }
   return 0;
 }
