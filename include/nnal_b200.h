@@ -50,6 +50,10 @@ typedef struct { int32_t type, out, kh, kw; } nnal_layer_spec;
 #define NNAL_SCORE_NEG_FI_TRACE 3 /* -(1-|pi|^2)(|u|^2+1): minus the trace of the last-layer FI (NNAL.py:121-139);
                                      needs a pool pass that kept the feature layer */
 
+#define NNAL_SCORE_MC_BINARY 10 /* |mean_t P_t(class1) - 0.5| over the MC-dropout passes (PW_NNAL.py:67-87, 232-244) */
+#define NNAL_SCORE_NEG_BALD 11  /* -(H(mean_t P_t) - mean_t H(P_t)), zeros bumped by 1e-6 (PW_NNAL.py:247-282): ascending
+                                   top-k of it = np.argsort(-scores)[:k] */
+
 /* ---- context ------------------------------------------------------------------------------- */
 int nnal_version(void);
 /* Creates a context on CUDA device `device`.  Fails with NNAL_ERR_NO_DEVICE when there is no
@@ -122,6 +126,22 @@ int nnal_pool_eval_images(nnal_ctx* ctx, const float* x, int64_t n, int64_t offs
 /* Same, for samples resident in device memory (d_inds int64 device pointer) */
 int nnal_pool_eval_device_inds(nnal_ctx* ctx, int subject, const int64_t* d_inds, int64_t n, int64_t offset, int d1,
                                int d2, int d3, const double* stats, int norm_mode);
+/* MC-dropout (replaces feeding x_feed_dict = {model.keep_prob: model.dropout_rate} to PW_NN.batch_eval T times,
+ * PW_NNAL.py:67-87, 232-282).  Configure BEFORE nnal_pool_begin; the following nnal_pool_eval* calls evaluate the conv
+ * trunk once per chunk and the FC tail T times with tf.nn.dropout semantics (x / keep_prob where kept, NN.py:167-171)
+ * on the outputs of `layers` (model.dropout_layers: FC layers only), keeping float64 running means of P(class 1) and of
+ * the per-pass binary entropies for every pool sample.  Masks are Philox4x32-10 words keyed by `seed`, counter
+ * {unit/4, pos0 + pool position, first_pass + t, layer}: independent of chunking and of how the pool is sharded.
+ * T = 0 switches MC mode off.  Binary models only. */
+int nnal_pool_mc_config(nnal_ctx* ctx, int T, double keep_prob, unsigned long long seed, unsigned int first_pass,
+                        long long pos0, const int* layers, int n_layers);
+/* Committee scorers 'ensemble' / 'QBC-JS' (PW_NNAL.py:453-545): fold member t's deterministic pool pass (the current
+ * posteriors) into the same running means, av = (x + t av) / (t + 1).  t = 0 opens the accumulation,
+ * nnal_pool_ensemble_end closes it; every member scores the same pool.  Scores: NNAL_SCORE_MC_BINARY / _NEG_BALD. */
+int nnal_pool_ensemble_accumulate(nnal_ctx* ctx, int t);
+int nnal_pool_ensemble_end(nnal_ctx* ctx);
+/* running means after the pool pass: av_post [n_total], av_ent [n_total] (either may be NULL) */
+int nnal_pool_mc_read(nnal_ctx* ctx, double* av_post, double* av_ent);
 /* posteriors [c][n_total] float32 (layout of model.posteriors, NN.py:184-188) */
 int nnal_pool_posteriors(nnal_ctx* ctx, float* out);
 /* model.feature_layer as [feat_dim][n] columns start..start+n (PW_NN.py:530-531 layout) */

@@ -7,6 +7,17 @@ from collections import OrderedDict
 import numpy as np
 
 
+class _Placeholder(object):
+    """Stands in for a TensorFlow placeholder (``model.keep_prob``, NN.py:33-35): only ever used as a key of the
+    reference's ``x_feed_dict = {model.keep_prob: model.dropout_rate}`` (PW_NNAL.py:68-69, 234-235)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return '<placeholder %s>' % self.name
+
+
 class CNN(object):
     """``layer_dict``: ordered {name: [out,'conv',[kh,kw]] | [[p,p],'pool'] | [out,'fc']}
     (NN.py:98-108).  ``input_shape`` = (H, W, C) of the NHWC placeholder (NN.py:1339-1345)."""
@@ -22,6 +33,7 @@ class CNN(object):
         else:
             self.dropout_layers, self.dropout_rate = [], 1.
         self.probes = list(probes)
+        self.keep_prob = _Placeholder('keep_prob')
         self.var_dict = {}
         self.grad_layers = []
         self._version = 0
@@ -92,6 +104,20 @@ class CNN(object):
         z = np.load(file_path)
         self.set_weights({name: (z[name + '/Weight'], z[name + '/Bias']) for name in self.weight_shapes()})
 
+    def perform_assign_ops(self, file_path, sess=None):
+        """NN.CNN.perform_assign_ops (NN.py:397-419): load the weights saved at ``file_path`` into the model.
+        NPZ files written by ``save_weights`` (same ``<layer>/Weight``, ``<layer>/Bias`` keys as the reference's
+        HDF5 groups); HDF5 itself is read when h5py is importable."""
+        if str(file_path).endswith(('.h5', '.hdf5')):
+            try:
+                import h5py
+            except ImportError:
+                raise NotImplementedError('h5py is not available here: convert the weight file to NPZ (save_weights)')
+            with h5py.File(file_path, 'r') as f:
+                self.set_weights({name: (np.array(f[name]['Weight']), np.array(f[name]['Bias'])) for name in self.weight_shapes()})
+        else:
+            self.load_weights(file_path)
+
     def get_gradients(self, grad_layers=[]):
         """Records which layers the FI score factors cover (NN.py:621-645)."""
         self.grad_layers = list(grad_layers)
@@ -108,6 +134,8 @@ class ReferenceModelAdapter(object):
         self.input_shape = tuple(input_shape)
         self.feature_layer_index = feature_layer
         self.dropout_rate = getattr(ref_model, 'dropout_rate', 1.)
+        self.dropout_layers = list(getattr(ref_model, 'dropout_layers', []))
+        self.keep_prob = getattr(ref_model, 'keep_prob', _Placeholder('keep_prob'))
         self._version = 0
 
     def refresh(self):

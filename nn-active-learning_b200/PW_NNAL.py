@@ -12,9 +12,10 @@ def _stats_list(stats, m):
     return np.array([[stats[j][0], stats[j][1]] for j in range(m)], dtype=np.float64)
 
 
-def _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=0):
+def _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=0, mc=None):
     """Gather + forward for (this rank's block of) a single-volume pool; leaves posteriors on
-    the device.  Returns (engine, lo, hi) with [lo,hi) the block of pool positions scored here."""
+    the device.  Returns (engine, lo, hi) with [lo,hi) the block of pool positions scored here.
+    ``mc = (T, keep_prob)``: T MC-dropout passes of the FC tail, running means kept on the device."""
     eng = get_engine()
     eng.set_model(model, sess)
     imgs = list(padded_imgs)
@@ -24,9 +25,15 @@ def _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=0):
     rank, world = dist.rank_world()
     b = dist.shard_bounds(n, world)
     lo, hi = int(b[rank]), int(b[rank + 1])
-    eng.pool_begin(hi - lo, keep)
-    eng.pool_eval(0, pool_inds[lo:hi], 0, expr.pars['patch_shape'],
-                  _stats_list(expr.pars['stats'], len(imgs)), L.NORM_BATCH_EVAL, shape=imgs[0].shape)
+    if mc is not None:
+        eng.pool_mc_config(mc[0], mc[1], model.dropout_layers, pos0=lo)
+    try:
+        eng.pool_begin(hi - lo, keep)
+        eng.pool_eval(0, pool_inds[lo:hi], 0, expr.pars['patch_shape'],
+                      _stats_list(expr.pars['stats'], len(imgs)), L.NORM_BATCH_EVAL, shape=imgs[0].shape)
+    finally:
+        if mc is not None:
+            eng.pool_mc_config(0, 1., [])
     return eng, lo, hi
 
 
@@ -55,6 +62,16 @@ def CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, method_name):
         q, _ = dist.allgather_topk(sc, idx + lo, min(k, len(pool_inds)))
         return q
 
+    if method_name == 'MC-entropy':
+        # PW_NNAL.py:67-87: running mean of P(class 1) over MC_iters dropout passes, k smallest |mean - 0.5|
+        k = expr.pars['k']
+        eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds,
+                                         mc=(int(expr.pars['MC_iters']), float(model.dropout_rate)))
+        eng.pool_score(L.SCORE_MC_BINARY)
+        idx, sc = eng.pool_topk(k, with_scores=True)
+        q, _ = dist.allgather_topk(sc, idx + lo, min(k, len(pool_inds)))
+        return q
+
     if method_name == 'fi':
         from . import fi
         return fi.query_single(expr, model, sess, padded_imgs, pool_inds)
@@ -62,9 +79,9 @@ def CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, method_name):
     raise NotImplementedError('query method %r is not part of the replaced path' % method_name)
 
 
-def _bin_filter_core(expr, model, sess, all_padded_imgs, pool_inds, B, keep=0):
-    """Pool pass over (this rank's block of) the concatenated multi-subject pool + global top-B by
-    |p - 0.5|.  Returns (sorted global positions, their posteriors, lo, hi, per-subject sizes)."""
+def _pool_pass_multimg(expr, model, sess, all_padded_imgs, pool_inds, keep=0, mc=None):
+    """Pool pass over (this rank's block of) the concatenated multi-subject pool.  ``mc = (T, keep_prob)`` runs T
+    MC-dropout passes of the FC tail per chunk.  Returns (engine, lo, hi, per-subject sizes, n)."""
     eng = get_engine()
     eng.set_model(model, sess)
     s = len(pool_inds)
@@ -74,20 +91,33 @@ def _bin_filter_core(expr, model, sess, all_padded_imgs, pool_inds, B, keep=0):
     rank, world = dist.rank_world()
     b = dist.shard_bounds(n, world)
     lo, hi = int(b[rank]), int(b[rank + 1])
-    eng.pool_begin(hi - lo, keep)
-    start = 0
-    for i in range(s):
-        ni = img_ind_sizes[i]
-        a, e = max(start, lo), min(start + ni, hi)
-        if e > a:
-            imgs = list(all_padded_imgs[i][:-1])
-            eng.upload(i, imgs)
-            stats = np.array([[expr.train_stats[i, 2 * j], expr.train_stats[i, 2 * j + 1]] for j in range(m)],
-                             dtype=np.float64)
-            inds_i = np.asarray(pool_inds[i])[a - start:e - start]
-            eng.pool_eval(i, inds_i, a - lo, expr.pars['patch_shape'], stats, L.NORM_BATCH_EVAL,
-                          shape=imgs[0].shape)
-        start += ni
+    if mc is not None:
+        eng.pool_mc_config(mc[0], mc[1], model.dropout_layers, pos0=lo)
+    try:
+        eng.pool_begin(hi - lo, keep)
+        start = 0
+        for i in range(s):
+            ni = img_ind_sizes[i]
+            a, e = max(start, lo), min(start + ni, hi)
+            if e > a:
+                imgs = list(all_padded_imgs[i][:-1])
+                eng.upload(i, imgs)
+                stats = np.array([[expr.train_stats[i, 2 * j], expr.train_stats[i, 2 * j + 1]] for j in range(m)],
+                                 dtype=np.float64)
+                inds_i = np.asarray(pool_inds[i])[a - start:e - start]
+                eng.pool_eval(i, inds_i, a - lo, expr.pars['patch_shape'], stats, L.NORM_BATCH_EVAL,
+                              shape=imgs[0].shape)
+            start += ni
+    finally:
+        if mc is not None:
+            eng.pool_mc_config(0, 1., [])
+    return eng, lo, hi, img_ind_sizes, n
+
+
+def _bin_filter_core(expr, model, sess, all_padded_imgs, pool_inds, B, keep=0):
+    """Pool pass over (this rank's block of) the concatenated multi-subject pool + global top-B by
+    |p - 0.5|.  Returns (sorted global positions, their posteriors, lo, hi, per-subject sizes)."""
+    eng, lo, hi, img_ind_sizes, n = _pool_pass_multimg(expr, model, sess, all_padded_imgs, pool_inds, keep)
     eng.pool_score(L.SCORE_BINARY)
     idx, sc = eng.pool_topk(B, with_scores=True)
     post_local = eng.pool_posteriors()[1, :].astype(np.float64)
@@ -109,7 +139,12 @@ def bin_uncertainty_filter_multimg(expr, model, sess, all_padded_imgs, pool_inds
     subject's pool, rank |p - 0.5| over the CONCATENATED pool, keep B, split back with
     global2local_inds.  Returns ``(sel_inds, sel_posts)`` lists per subject."""
     if len(x_feed_dict) > 0:
-        raise NotImplementedError('x_feed_dict (MC-dropout) is not part of the replaced path yet')
+        # PW_NNAL.py:725-726: with a feed the reference returns the raw concatenated posteriors of this
+        # (stochastic) pass instead of a selection
+        from .PW_NN import keep_prob_from_feed
+        keep_prob = keep_prob_from_feed(model, x_feed_dict)
+        eng, lo, hi, _, n = _pool_pass_multimg(expr, model, sess, all_padded_imgs, pool_inds, mc=(1, keep_prob))
+        return dist.allgather_concat(eng.pool_posteriors()[1, :].astype(np.float64))
     sorted_inds, sel_p, _, _, img_ind_sizes = _bin_filter_core(expr, model, sess, all_padded_imgs, pool_inds, B)
     s = len(pool_inds)
     sel_inds = patch_utils.global2local_inds(sorted_inds, img_ind_sizes)
@@ -132,6 +167,39 @@ def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, labeled_inds, m
 
     if method_name == 'entropy':
         return bin_uncertainty_filter_multimg(expr, model, sess, all_padded_imgs, pool_inds, k)[0]
+
+    if method_name in ('MC-entropy', 'BALD'):
+        # PW_NNAL.py:232-244 (MC-entropy): k smallest |mean_t P_t - 0.5|;  :247-282 (BALD): k largest
+        # H(mean_t P_t) - mean_t H(P_t).  The T passes share one evaluation of the conv trunk per chunk.
+        eng, lo, hi, _, n = _pool_pass_multimg(expr, model, sess, all_padded_imgs, pool_inds,
+                                               mc=(int(expr.pars['MC_iters']), float(model.dropout_rate)))
+        eng.pool_score(L.SCORE_MC_BINARY if method_name == 'MC-entropy' else L.SCORE_NEG_BALD)
+        idx, sc = eng.pool_topk(k, with_scores=True)
+        inds, _ = dist.allgather_topk(sc, idx + lo, min(k, n))
+        return patch_utils.global2local_inds(inds, img_ind_sizes)
+
+    if method_name in ('ensemble', 'QBC-JS'):
+        # PW_NNAL.py:453-490 (ensemble): k smallest |mean_i P_i - 0.5| over the committee;  :492-545 (QBC-JS): k largest
+        # H(mean_i P_i) - mean_i H(P_i).  With no labels yet the committee is expr.pretrained_paths loaded into
+        # expr.model_holder (:463-466); with labels the reference fine-tunes the previous model once per member
+        # (:467-476) -- training, which stays in the reference.
+        n_labels = np.sum([len(labeled_inds[i]) for i in range(len(labeled_inds))]) if labeled_inds is not None else 0
+        if n_labels > 0:
+            raise NotImplementedError('committee members are fine-tuned by the reference (PW_AL.finetune_multimg); '
+                                      'load their weights into expr.pretrained_paths to score them here')
+        eng = None
+        try:
+            for i in range(len(expr.pretrained_paths)):
+                expr.model_holder.perform_assign_ops(expr.pretrained_paths[i], sess)
+                eng, lo, hi, _, n = _pool_pass_multimg(expr, expr.model_holder, sess, all_padded_imgs, pool_inds)
+                eng.pool_ensemble_accumulate(i)
+        finally:
+            if eng is not None:
+                eng.pool_ensemble_end()
+        eng.pool_score(L.SCORE_MC_BINARY if method_name == 'ensemble' else L.SCORE_NEG_BALD)
+        idx, sc = eng.pool_topk(k, with_scores=True)
+        inds, _ = dist.allgather_topk(sc, idx + lo, min(k, n))
+        return patch_utils.global2local_inds(inds, img_ind_sizes)
 
     if method_name == 'fi':
         from . import fi

@@ -51,6 +51,9 @@ static void free_buf(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap =
 static void free_pool(nnal_ctx* ctx) {
   if (ctx->pool_post) cudaFree(ctx->pool_post);
   if (ctx->pool_score) cudaFree(ctx->pool_score);
+  if (ctx->pool_mc_post) cudaFree(ctx->pool_mc_post);
+  if (ctx->pool_mc_ent) cudaFree(ctx->pool_mc_ent);
+  ctx->pool_mc_post = ctx->pool_mc_ent = nullptr; ctx->pool_cap_mc = 0;
   if (ctx->pool_feat) cudaFree(ctx->pool_feat);
   if (ctx->pool_prev) cudaFree(ctx->pool_prev);
   ctx->pool_post = nullptr; ctx->pool_score = nullptr; ctx->pool_feat = nullptr; ctx->pool_prev = nullptr;
@@ -386,8 +389,86 @@ extern "C" int nnal_pool_begin(nnal_ctx* ctx, int64_t n_total, int keep) {
   NNAL_TRY(grow((void**)&ctx->pool_score, ctx->pool_cap_score, sizeof(double)));
   if (keep >= 1) NNAL_TRY(grow((void**)&ctx->pool_feat, ctx->pool_cap_nfeat, (size_t)ctx->feat_dim * sizeof(float)));
   if (keep >= 2) NNAL_TRY(grow((void**)&ctx->pool_prev, ctx->pool_cap_nprev, (size_t)ctx->prev_dim * sizeof(float)));
+  if (ctx->mc_T > 0) {
+    if (keep != 0) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "MC-dropout passes do not keep features");
+    if (ctx->n_class != 2) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "MC-dropout scores are defined for the binary patch model");
+    if ((size_t)n_total > ctx->pool_cap_mc) {
+      if (ctx->pool_mc_post) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->pool_mc_post); cudaFree(ctx->pool_mc_ent); }
+      ctx->pool_mc_post = ctx->pool_mc_ent = nullptr;
+      CUDA_TRY(ctx, cudaMalloc(&ctx->pool_mc_post, (size_t)n_total * sizeof(double)));
+      CUDA_TRY(ctx, cudaMalloc(&ctx->pool_mc_ent, (size_t)n_total * sizeof(double)));
+      ctx->pool_cap_mc = (size_t)n_total;
+    }
+  }
+  if (!ctx->ens_open) ctx->mc_have = ctx->mc_T > 0;
   ctx->pool_n = n_total;
   ctx->keep = keep;
+  return NNAL_OK;
+}
+
+// MC-dropout configuration for the following nnal_pool_begin / nnal_pool_eval* calls (T = 0 switches it off).
+// layers: indices of the layers whose output is dropped out (model.dropout_layers); they must be FC layers.
+extern "C" int nnal_pool_mc_config(nnal_ctx* ctx, int T, double keep_prob, unsigned long long seed, unsigned int first_pass,
+                                   long long pos0, const int* layers, int n_layers) {
+  if (!ctx || T < 0) return NNAL_ERR_INVALID;
+  ctx->mc_T = 0;
+  if (T == 0) return NNAL_OK;
+  if (!(keep_prob > 0.0 && keep_prob <= 1.0) || n_layers < 0 || (n_layers > 0 && !layers)) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "keep_prob must be in (0, 1]");
+  if (ctx->fc_first < 0) NNAL_FAIL(ctx, NNAL_ERR_STATE, "model not set");
+  ctx->mc_sites.clear();
+  for (int i = 0; i < n_layers; ++i) {
+    if (layers[i] < ctx->fc_first || layers[i] >= (int)ctx->layers.size())
+      NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "dropout sites must be FC layers (the conv trunk is evaluated once)");
+    ctx->mc_sites.push_back(layers[i]);
+  }
+  DropSpec d;
+  d.keep = (float)keep_prob;
+  // keep_prob == 1: tf.nn.dropout is the identity; thresh 0 = off
+  d.thresh = keep_prob >= 1.0 ? 0u : (uint32_t)(keep_prob * 4294967296.0);
+  d.k0 = (uint32_t)(seed & 0xffffffffull);
+  d.k1 = (uint32_t)(seed >> 32);
+  d.pass = first_pass;
+  d.row0 = pos0;
+  ctx->mc_drop = d;
+  ctx->mc_T = T;
+  return NNAL_OK;
+}
+
+// Committee scorers ('ensemble', 'QBC-JS'; PW_NNAL.py:453-545): member t's DETERMINISTIC pool pass (current posteriors)
+// is folded into the same float64 running means the MC-dropout passes use:  av = (x + t * av) / (t + 1).
+// t = 0 opens the accumulation, nnal_pool_ensemble_end closes it; every member must score the same pool.
+extern "C" int nnal_pool_ensemble_accumulate(nnal_ctx* ctx, int t) {
+  if (!ctx || t < 0) return NNAL_ERR_INVALID;
+  if (!ctx->pool_post || ctx->pool_n <= 0) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no pool pass");
+  if (ctx->n_class != 2) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "committee scores are defined for the binary patch model");
+  if (t > 0 && !ctx->ens_open) NNAL_FAIL(ctx, NNAL_ERR_STATE, "committee accumulation starts with member 0");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((size_t)ctx->pool_n > ctx->pool_cap_mc) {
+    if (t > 0) NNAL_FAIL(ctx, NNAL_ERR_STATE, "committee members must score the same pool");
+    if (ctx->pool_mc_post) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->pool_mc_post); cudaFree(ctx->pool_mc_ent); }
+    ctx->pool_mc_post = ctx->pool_mc_ent = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->pool_mc_post, (size_t)ctx->pool_n * sizeof(double)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->pool_mc_ent, (size_t)ctx->pool_n * sizeof(double)));
+    ctx->pool_cap_mc = (size_t)ctx->pool_n;
+  }
+  NNAL_TRY(nnal_k_mc_accumulate(ctx, ctx->pool_post, ctx->pool_n, 0, ctx->pool_n, t, ctx->pool_mc_post, ctx->pool_mc_ent));
+  ctx->ens_open = 1;
+  ctx->mc_have = 1;
+  return NNAL_OK;
+}
+extern "C" int nnal_pool_ensemble_end(nnal_ctx* ctx) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  ctx->ens_open = 0;
+  return NNAL_OK;
+}
+
+extern "C" int nnal_pool_mc_read(nnal_ctx* ctx, double* av_post, double* av_ent) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  if (!ctx->pool_mc_post || !ctx->mc_have) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no MC-dropout pass has run");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (av_post) CUDA_TRY(ctx, cudaMemcpyAsync(av_post, ctx->pool_mc_post, (size_t)ctx->pool_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (av_ent) CUDA_TRY(ctx, cudaMemcpyAsync(av_ent, ctx->pool_mc_ent, (size_t)ctx->pool_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return NNAL_OK;
 }
 
@@ -543,6 +624,14 @@ extern "C" int nnal_pool_feature_rows(nnal_ctx* ctx, const int64_t* pos, int64_t
 extern "C" int nnal_pool_score(nnal_ctx* ctx, int kind, double eps) {
   if (!ctx) return NNAL_ERR_INVALID;
   if (!ctx->pool_post) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no pool pass");
+  if (kind == NNAL_SCORE_MC_BINARY || kind == NNAL_SCORE_NEG_BALD) {
+    if (!ctx->pool_mc_post || !ctx->mc_have) NNAL_FAIL(ctx, NNAL_ERR_STATE, "MC scores need an MC-dropout pool pass");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    prof_begin(ctx, NNAL_PROF_SCORE);
+    int rc = nnal_k_scores_mc(ctx, ctx->pool_mc_post, ctx->pool_mc_ent, ctx->pool_n, kind, ctx->pool_score);
+    prof_end(ctx);
+    return rc;
+  }
   if (kind < 0 || kind > 3) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "unknown score kind");
   if (kind == NNAL_SCORE_BINARY && ctx->n_class != 2) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "binary uncertainty needs a 2-class model");
   if (kind == NNAL_SCORE_NEG_FI_TRACE && (!ctx->pool_feat || ctx->keep < 1))

@@ -3,6 +3,7 @@
 // only where two neighbouring layers disagree.  Replaces one sess.run(model.posteriors / feature_layer)
 // of PW_NN.batch_eval (PW_NN.py:522-524).
 #include "nnal_common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -79,6 +80,48 @@ int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset, bool input_is_
 
   for (int i = 0; i < nl; ++i) {
     const Layer& L = ctx->layers[i];
+    if (ctx->mc_T > 0 && i == ctx->fc_first) {
+      // MC-dropout: the conv trunk is deterministic (PW1 drops out the FC outputs only, NN.py:1338) and was computed
+      // once; the FC tail runs T times with fresh masks.  The tail ping-pongs between the activation buffer that does
+      // not hold the trunk output and a third buffer.
+      if (!cur.split) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "MC-dropout needs the tensor-core path (trunk output in split planes)");
+      size_t maxfc = 0;
+      for (int j = i; j < nl; ++j) maxfc = std::max(maxfc, (size_t)ctx->layers[j].out_dim);
+      NNAL_TRY(devbuf_reserve(ctx, ctx->act_mc, (size_t)nb * maxfc * sizeof(float)));
+      void* bufs[2] = {ctx->act[pp].p, ctx->act_mc.p};
+      for (int t = 0; t < ctx->mc_T; ++t) {
+        Act h = cur;
+        int q = 0;
+        for (int j = i; j < nl; ++j) {
+          const Layer& F = ctx->layers[j];
+          DropSpec d = ctx->mc_drop;
+          d.pass += (uint32_t)t;
+          d.site = (uint32_t)j;
+          bool site = false;
+          for (int sj : ctx->mc_sites) site |= (sj == j);
+          prof_begin(ctx, j);
+          if (j == nl - 1) {
+            if (h.split) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "MC-dropout: the head expects fp32 features");
+            NNAL_TRY(nnal_k_head(ctx, F, h.f32, nb, ctx->pool_n, offset, ctx->pool_post, nullptr, site ? &d : nullptr));
+          } else {
+            if (F.type != NNAL_LAYER_FC || !layer_on_tc(ctx, j) || !h.split)
+              NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "MC-dropout: FC tail must run on the tensor-core path");
+            Act o;
+            o.f32 = (float*)bufs[q]; o.hi = (nnal_h*)bufs[q]; o.lo = o.hi + nb * F.out_dim; o.elems = F.out_dim;
+            q ^= 1;
+            const bool ws = consumer_wants_split(ctx, j);
+            d.row0 += offset;                    // FC rows are chunk-relative; the head adds the offset itself
+            NNAL_TRY(nnal_tc_fc_planes(ctx, F, h.hi, h.lo, F.in_dim, ws ? nullptr : o.f32, ws ? o.hi : nullptr,
+                                       ws ? o.lo : nullptr, nb, site ? &d : nullptr));
+            o.split = ws;
+            h = o;
+          }
+          prof_end(ctx);
+        }
+        NNAL_TRY(nnal_k_mc_accumulate(ctx, ctx->pool_post, ctx->pool_n, offset, nb, t, ctx->pool_mc_post, ctx->pool_mc_ent));
+      }
+      return NNAL_OK;
+    }
     prof_begin(ctx, i);
     if (i == nl - 1) {
       NNAL_TRY(to_f32(cur));

@@ -152,6 +152,7 @@ struct FcParams {
   int M, N, num_kb, relu, ldo;
   float w_scale_inv;
   int accum;                 // out += result (Gram partial sums over sample chunks)
+  DropSpec drop;             // tf.nn.dropout on the activated output (thresh == 0: off)
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -286,6 +287,16 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
               float x = sum[c + j] * p.w_scale_inv + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
               v[j] = p.relu ? fmaxf(x, 0.f) : x;
             }
+            if (p.drop.thresh) {                                   // NN.py:169-171: dropout on the layer's output
+              const uint32_t pos = (uint32_t)(p.drop.row0 + row);
+#pragma unroll
+              for (int jb = 0; jb < 4; ++jb) {
+                uint32_t r4[4];
+                philox4x32_10((uint32_t)(col0 + 4 * jb) >> 2, pos, p.drop.pass, p.drop.site, p.drop.k0, p.drop.k1, r4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[4 * jb + k] = r4[k] < p.drop.thresh ? v[4 * jb + k] / p.drop.keep : 0.f;
+              }
+            }
             if (p.out) {
               float4* dst = reinterpret_cast<float4*>(p.out + (size_t)row * p.ldo + col0);
               if (p.accum) {
@@ -321,6 +332,12 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
               if (col0 + j < p.N) {
                 float x = sum[c + j] * p.w_scale_inv + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
                 x = p.relu ? fmaxf(x, 0.f) : x;
+                if (p.drop.thresh) {
+                  uint32_t r4[4];
+                  philox4x32_10((uint32_t)(col0 + j) >> 2, (uint32_t)(p.drop.row0 + row), p.drop.pass, p.drop.site, p.drop.k0,
+                                p.drop.k1, r4);
+                  x = r4[(col0 + j) & 3] < p.drop.thresh ? x / p.drop.keep : 0.f;
+                }
                 if (p.out && p.accum) x += p.out[(size_t)row * p.ldo + col0 + j];
                 if (p.out) p.out[(size_t)row * p.ldo + col0 + j] = x;
                 if (p.out_hi) {
@@ -436,7 +453,8 @@ int nnal_tc_prepare_layer(nnal_ctx* ctx, Layer& L) {
 // 64-wide block and rows beyond M/N are zero-filled by TMA.
 int nnal_tc_gemm_planes(nnal_ctx* ctx, const nnal_h* Ah, const nnal_h* Al, int64_t lda, int64_t M, const nnal_h* Bh,
                         const nnal_h* Bl, int64_t ldb, int N, int64_t K, const float* bias, float scale, int relu,
-                        int accum, float* out, int ldo, nnal_h* out_hi, nnal_h* out_lo, int ld_split) {
+                        int accum, float* out, int ldo, nnal_h* out_hi, nnal_h* out_lo, int ld_split,
+                        const DropSpec* drop) {
   if (M == 0 || N == 0) return NNAL_OK;
   tc::TcState* st;
   NNAL_TRY(tc::get_state(ctx, &st));
@@ -453,6 +471,7 @@ int nnal_tc_gemm_planes(nnal_ctx* ctx, const nnal_h* Ah, const nnal_h* Al, int64
   p.bias = bias; p.out = out; p.out_hi = out_hi; p.out_lo = out_lo; p.ld_split = ld_split;
   p.M = (int)M; p.N = N; p.num_kb = (int)((K + tc::BK - 1) / tc::BK); p.relu = relu; p.ldo = ldo; p.w_scale_inv = scale;
   p.accum = accum;
+  p.drop = drop ? *drop : DropSpec();
   const int ntiles = cdiv(M, tc::BM) * cdiv(N, tc::BN);
   const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
   tc::fc_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, ctx->stream>>>(tmAh, tmAl, tmBh, tmBl, p);
@@ -465,9 +484,9 @@ int nnal_tc_gemm_planes(nnal_ctx* ctx, const nnal_h* Ah, const nnal_h* Al, int64
 // block is zero-filled by TMA).  Outputs: fp32 [n][N] (out, may be null) and/or fp16 hi/lo planes
 // [n][N] of the activated result (the next tensor-core layer's A operand).
 int nnal_tc_fc_planes(nnal_ctx* ctx, const Layer& L, const nnal_h* Ah, const nnal_h* Al, int lda, float* out,
-                      nnal_h* out_hi, nnal_h* out_lo, int64_t n) {
+                      nnal_h* out_hi, nnal_h* out_lo, int64_t n, const DropSpec* drop) {
   return nnal_tc_gemm_planes(ctx, Ah, Al, lda, n, L.Wh, L.Wl, L.k_pad, L.out_dim, L.in_dim, L.b, L.w_scale_inv, L.relu, 0,
-                             out, L.out_dim, out_hi, out_lo, L.out_dim);
+                             out, L.out_dim, out_hi, out_lo, L.out_dim, drop);
 }
 
 // fp32 A operand [n][K]: split into planes first (used by the isolated test hook and mixed pipelines)

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
+#include "philox.cuh"
 #include <cstring>
 #include <string>
 #include <vector>
@@ -110,6 +111,16 @@ struct nnal_ctx {
   void* tc_state = nullptr;              // tensor-map cache etc. (gemm_tc.cu)
   void* sims_state = nullptr;            // representativeness queries (sims.cu)
   void* fi_state = nullptr;              // Fisher-information candidate set / greedy state (fi.cu)
+  // MC-dropout (MC-entropy / BALD): T stochastic passes of the FC tail per chunk, running means per pool sample
+  int mc_T = 0;                          // 0: deterministic forward
+  int mc_have = 0;                       // the current pool pass ran in MC mode: running means are valid
+  int ens_open = 0;                      // committee accumulation in progress: pool passes of the members keep the running means
+  DropSpec mc_drop;                      // keep, threshold, seed, first pass id, global position of pool offset 0
+  std::vector<int> mc_sites;             // layer indices whose OUTPUT is dropped out (NN.py:167-171)
+  double* pool_mc_post = nullptr;        // [pool_n] running mean of P(class 1) over the passes (float64, PW_NNAL.py:80)
+  double* pool_mc_ent = nullptr;         // [pool_n] running mean of the per-pass binary entropies (PW_NNAL.py:262-268)
+  size_t pool_cap_mc = 0;
+  DevBuf act_mc;                         // third activation buffer: the conv trunk's output must survive the T tail passes
 };
 
 #define CUDA_TRY(ctx, expr)                                                            \
@@ -174,7 +185,10 @@ int nnal_k_fc_simt(nnal_ctx*, const Layer&, const float* in, float* out, int64_t
 int nnal_k_permute_fc_weight(nnal_ctx*, const float* Wtf, float* Wnative, int out, int C, int H, int W);
 // score.cu
 int nnal_k_head(nnal_ctx*, const Layer& fc_last, const float* feat, int64_t n, int64_t pool_n, int64_t offset,
-                float* post /*[c][pool_n]*/, float* logits_out /*[n][c] or null*/);
+                float* post /*[c][pool_n]*/, float* logits_out /*[n][c] or null*/, const DropSpec* drop = nullptr);
+int nnal_k_mc_accumulate(nnal_ctx*, const float* post, int64_t pool_n, int64_t offset, int64_t n, int t,
+                         double* av_post, double* av_ent);
+int nnal_k_scores_mc(nnal_ctx*, const double* av_post, const double* av_ent, int64_t n, int kind, double* score);
 int nnal_k_scores_f32(nnal_ctx*, const float* post, int c, int64_t n, int kind, double eps, double* score);
 int nnal_k_scores_f64(nnal_ctx*, const double* post, int c, int64_t n, int kind, double eps, double* score);
 int nnal_k_entropy_f32(nnal_ctx*, const float* post, int c, int64_t n, float eps, float* H);
@@ -185,10 +199,11 @@ bool nnal_tc_fc_supported(const nnal_ctx*, const Layer&);
 int nnal_tc_release(nnal_ctx*);
 int nnal_tc_fc(nnal_ctx*, const Layer&, const float* in, float* out, int64_t n);
 int nnal_tc_fc_planes(nnal_ctx*, const Layer&, const nnal_h* Ah, const nnal_h* Al, int lda, float* out,
-                      nnal_h* out_hi, nnal_h* out_lo, int64_t n);
+                      nnal_h* out_hi, nnal_h* out_lo, int64_t n, const DropSpec* drop = nullptr);
 int nnal_tc_gemm_planes(nnal_ctx*, const nnal_h* Ah, const nnal_h* Al, int64_t lda, int64_t M, const nnal_h* Bh,
                         const nnal_h* Bl, int64_t ldb, int N, int64_t K, const float* bias, float scale, int relu,
-                        int accum, float* out, int ldo, nnal_h* out_hi, nnal_h* out_lo, int ld_split);
+                        int accum, float* out, int ldo, nnal_h* out_hi, nnal_h* out_lo, int ld_split,
+                        const DropSpec* drop = nullptr);
 int nnal_k_split_flat(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t count);
 int nnal_k_split_pad(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t rows, int C, int Cp);
 int nnal_k_merge_flat(nnal_ctx*, const nnal_h* hi, const nnal_h* lo, float* out, int64_t count);

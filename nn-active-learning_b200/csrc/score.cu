@@ -15,7 +15,7 @@ template <int CMAX>
 __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ feat, const float* __restrict__ Wt,
                                                     const float* __restrict__ bias, int64_t n, int d, int c,
                                                     int64_t pool_n, int64_t offset, float* __restrict__ post,
-                                                    float* __restrict__ logits_out) {
+                                                    float* __restrict__ logits_out, DropSpec drop) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -51,7 +51,15 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ fea
     float zmax = -INFINITY;
 #pragma unroll
     for (int j = 0; j < CMAX; ++j)
-      if (j < c) { acc[j] += bias[j]; zmax = fmaxf(zmax, acc[j]); }
+      if (j < c) {
+        acc[j] += bias[j];
+        if (drop.thresh) {             // PW1 drops out the logits too (dropout layer 8 = fc3, NN.py:1338)
+          uint32_t r4[4];
+          philox4x32_10((uint32_t)j >> 2, (uint32_t)(drop.row0 + offset + s), drop.pass, drop.site, drop.k0, drop.k1, r4);
+          acc[j] = r4[j & 3] < drop.thresh ? acc[j] / drop.keep : 0.f;
+        }
+        zmax = fmaxf(zmax, acc[j]);
+      }
     float sum = 0.f;
     float mine = 0.f, myz = 0.f;
 #pragma unroll
@@ -69,17 +77,18 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ fea
 }
 
 int nnal_k_head(nnal_ctx* ctx, const Layer& L, const float* feat, int64_t n, int64_t pool_n, int64_t offset,
-                float* post, float* logits_out) {
+                float* post, float* logits_out, const DropSpec* dropp) {
   if (n == 0) return NNAL_OK;
+  const DropSpec drop = dropp ? *dropp : DropSpec();
   int c = L.out_dim, d = L.in_dim;
   int64_t blocks = (n * 32 + 255) / 256;
   int grid = (int)(blocks < (int64_t)ctx->sm_count * 8 ? blocks : (int64_t)ctx->sm_count * 8);
   if (c <= 2)
-    head_kernel<2><<<grid, 256, 0, ctx->stream>>>(feat, L.W, L.b, n, d, c, pool_n, offset, post, logits_out);
+    head_kernel<2><<<grid, 256, 0, ctx->stream>>>(feat, L.W, L.b, n, d, c, pool_n, offset, post, logits_out, drop);
   else if (c <= 16)
-    head_kernel<16><<<grid, 256, 0, ctx->stream>>>(feat, L.W, L.b, n, d, c, pool_n, offset, post, logits_out);
+    head_kernel<16><<<grid, 256, 0, ctx->stream>>>(feat, L.W, L.b, n, d, c, pool_n, offset, post, logits_out, drop);
   else if (c <= 32)
-    head_kernel<32><<<grid, 256, 0, ctx->stream>>>(feat, L.W, L.b, n, d, c, pool_n, offset, post, logits_out);
+    head_kernel<32><<<grid, 256, 0, ctx->stream>>>(feat, L.W, L.b, n, d, c, pool_n, offset, post, logits_out, drop);
   else
     NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "more than 32 classes not supported by the fused head");
   ctx->launches++;
@@ -130,6 +139,62 @@ int nnal_k_scores_f32(nnal_ctx* ctx, const float* post, int c, int64_t n, int ki
 }
 int nnal_k_scores_f64(nnal_ctx* ctx, const double* post, int c, int64_t n, int kind, double eps, double* score) {
   return launch_scores<double>(ctx, post, c, n, kind, eps, score);
+}
+
+// ------------------------------------------------------------------------------------------
+// MC-dropout running means (PW_NNAL.py:67-87 MC-entropy, :232-282 BALD), float64 like the reference:
+//   av_posts = (posts + i * av_posts) / (i + 1)
+//   ents = -p log p - (1-p) log(1-p) with zeros bumped by 1e-6;  av_ents = (ents + i * av_ents) / (i + 1)
+// posts = P(class 1) of pass i (float32 from the head kernel, promoted as batch_eval does, PW_NN.py:526-529)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mc_accum_kernel(const float* __restrict__ post1, int64_t n, int t,
+                                                        double* __restrict__ av_post, double* __restrict__ av_ent) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double p = (double)post1[i];
+    av_post[i] = t == 0 ? p : (p + t * av_post[i]) / (t + 1);
+    double q = 1.0 - p;
+    if (p == 0.0) p += 1e-6;
+    if (q == 0.0) q += 1e-6;
+    const double e = -p * log(p) - q * log(q);
+    av_ent[i] = t == 0 ? e : (e + t * av_ent[i]) / (t + 1);
+  }
+}
+int nnal_k_mc_accumulate(nnal_ctx* ctx, const float* post, int64_t pool_n, int64_t offset, int64_t n, int t,
+                         double* av_post, double* av_ent) {
+  if (n == 0) return NNAL_OK;
+  int64_t blocks = (n + 255) / 256;
+  int grid = (int)(blocks < (int64_t)ctx->sm_count * 16 ? blocks : (int64_t)ctx->sm_count * 16);
+  mc_accum_kernel<<<grid, 256, 0, ctx->stream>>>(post + pool_n + offset, n, t, av_post + offset, av_ent + offset);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+//   kind 10 (MC-entropy): |av_posts - 0.5|                                           (PW_NNAL.py:84-85, 241)
+//   kind 11 (BALD):       -(H(av_posts) - av_ents), H with the same 1e-6 zero bumps   (PW_NNAL.py:270-278; ascending
+//                         top-k of the negated score = argsort(-scores)[:k])
+__global__ void __launch_bounds__(256) mc_score_kernel(const double* __restrict__ av_post, const double* __restrict__ av_ent,
+                                                        int64_t n, int kind, double* __restrict__ score) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double p = av_post[i], v;
+    if (kind == 10) {
+      v = fabs(p - 0.5);
+    } else {
+      double q = 1.0 - p;
+      if (p == 0.0) p += 1e-6;
+      if (q == 0.0) q += 1e-6;
+      v = -((-p * log(p) - q * log(q)) - av_ent[i]);
+    }
+    score[i] = v + 0.0;
+  }
+}
+int nnal_k_scores_mc(nnal_ctx* ctx, const double* av_post, const double* av_ent, int64_t n, int kind, double* score) {
+  if (n == 0) return NNAL_OK;
+  int64_t blocks = (n + 255) / 256;
+  int grid = (int)(blocks < (int64_t)ctx->sm_count * 16 ? blocks : (int64_t)ctx->sm_count * 16);
+  mc_score_kernel<<<grid, 256, 0, ctx->stream>>>(av_post, av_ent, n, kind, score);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -269,6 +269,40 @@ class Engine(object):
         self._chk(self.lib.nnal_pool_features(self.h, int(start), int(n), _ptr(out)))
         return out
 
+    # ------------------------------------------------------------------
+    # MC-dropout
+    # ------------------------------------------------------------------
+    dropout_seed = 0          # masks are a pure function of (seed, pass counter, layer, pool position, unit)
+    dropout_pass = 0          # advances by T with every stochastic pool pass, like TF's stateful generator would
+
+    def set_dropout_seed(self, seed, first_pass=0):
+        self.dropout_seed = int(seed) & 0xffffffffffffffff
+        self.dropout_pass = int(first_pass)
+
+    def pool_mc_config(self, T, keep_prob, layers, pos0=0):
+        """MC mode for the following pool_begin / pool_eval calls (T = 0: off).  Returns the id of the first pass."""
+        lay = np.ascontiguousarray(layers, dtype=np.int32)
+        first = self.dropout_pass
+        self._chk(self.lib.nnal_pool_mc_config(self.h, int(T), float(keep_prob), self.dropout_seed, first & 0xffffffff,
+                                               int(pos0), _ptr(lay) if lay.size else None, int(lay.size)))
+        if T > 0:
+            self.dropout_pass += int(T)
+        return first
+
+    def pool_ensemble_accumulate(self, t):
+        """Fold committee member t's deterministic pool pass into the running means (t = 0 opens)."""
+        self._chk(self.lib.nnal_pool_ensemble_accumulate(self.h, int(t)))
+
+    def pool_ensemble_end(self):
+        self._chk(self.lib.nnal_pool_ensemble_end(self.h))
+
+    def pool_mc_means(self):
+        av_post = np.empty(self._pool_n, dtype=np.float64)
+        av_ent = np.empty(self._pool_n, dtype=np.float64)
+        self.d2h_bytes += av_post.nbytes + av_ent.nbytes
+        self._chk(self.lib.nnal_pool_mc_read(self.h, _ptr(av_post), _ptr(av_ent)))
+        return av_post, av_ent
+
     def pool_score(self, kind, eps=0.0):
         self._chk(self.lib.nnal_pool_score(self.h, int(kind), float(eps)))
 

@@ -23,3 +23,4 @@ Parity status
 from .nnal_oracle import *   # noqa: F401,F403
 from .fi_oracle import *     # noqa: F401,F403
 from .rep_oracle import *    # noqa: F401,F403
+from .mc_oracle import *     # noqa: F401,F403
