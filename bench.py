@@ -276,6 +276,10 @@ def run_ours(args, rank, world):
     if args.fi_B > 0:
         fi = run_fi_round(args, eng, model, padded, stats, pool, lo, hi, d_inds, st, k, peaks, barrier, rank, world)
 
+    mc = None
+    if args.mc_T > 0:
+        mc = run_mc_round(args, eng, model, lo, hi, d_inds, st, k)
+
     # ---------------- end-to-end leg through the reference-facing API ----------------
     expr = Expr()
     expr.pars = dict(k=k, B=k, lambda_=0., patch_shape=PATCH, ntb=10000, stats=stats)
@@ -344,8 +348,41 @@ def run_ours(args, rank, world):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': 1e3 * e2e_s / args.steps,
                     'api': 'nnal_b200.PW_NNAL.CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, "entropy")'},
-            'roofline': roofline, 'stage_ms_per_step': stage_ms, 'cpu_baseline': cpu, 'fi_round': fi}
+            'roofline': roofline, 'stage_ms_per_step': stage_ms, 'cpu_baseline': cpu, 'fi_round': fi, 'mc_round': mc}
     print(json.dumps(line))
+
+
+def run_mc_round(args, eng, model, lo, hi, d_inds, st, k):
+    """One MC-entropy round (PW_NNAL.py:67-87) on the same pool: T dropout passes.  The conv trunk runs once per chunk,
+    only the FC tail T times; the reference runs T complete batch_eval passes."""
+    import torch
+    from nnal_b200 import _lib as L
+    n_local = hi - lo
+    T = args.mc_T
+    stream = torch.cuda.ExternalStream(eng.stream)
+    eng.set_dropout_seed(5)
+
+    def mc_step():
+        eng.pool_mc_config(T, 0.5, model.dropout_layers, pos0=lo)
+        try:
+            eng.pool_begin(n_local, 0)
+            eng.pool_eval_device(0, d_inds.data_ptr(), n_local, 0, PATCH, st)
+        finally:
+            eng.pool_mc_config(0, 1., [])
+        eng.pool_score(L.SCORE_MC_BINARY)
+        return eng.pool_topk(k)
+    mc_step()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2
+    ev0.record(stream)
+    for _ in range(reps):
+        mc_step()
+    ev1.record(stream)
+    ev1.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    return {'method': 'MC-entropy', 'T': T, 'keep_prob': 0.5, 'ms_per_round': ms,
+            'stochastic_passes_per_s': n_local * T / (ms * 1e-3),
+            'note': 'conv trunk once per chunk + T FC-tail passes with Philox dropout fused into the FC epilogue / head'}
 
 
 def run_fi_round(args, eng, model, padded, stats, pool, lo, hi, d_inds, st, k, peaks, barrier, rank, world):
@@ -436,6 +473,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=5000)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--fi-B', type=int, default=10000, help='FI pre-filter size of the extra FI round (0: skip)')
+    ap.add_argument('--mc-T', type=int, default=10, help='MC-dropout passes of the extra MC-entropy round (0: skip)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
