@@ -291,9 +291,9 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmHiL, const __grid_constant_
       nnal_h* ghi = p.out_hi + (size_t)g * C::G * SAMPLE_ELEMS;
       nnal_h* glo = p.out_lo + (size_t)g * C::G * SAMPLE_ELEMS;
       const int left = p.n - g * C::G;
+      const uint32_t glim = (uint32_t)((left < C::G ? left : C::G) * SAMPLE_ELEMS);   // a partly filled last group ends here
 #pragma unroll
-      for (int h = 0; h < NCH; ++h)
-        chlim[h] = co[h] >= C::COUT_REAL ? 0u : C::POOL ? 0x7fffffffu : (uint32_t)((left < C::G ? left : C::G) * SAMPLE_ELEMS);
+      for (int h = 0; h < NCH; ++h) chlim[h] = co[h] >= C::COUT_REAL ? 0u : C::POOL ? 0x7fffffffu : glim;
 #pragma unroll 1
       for (int t = 0; t < C::T; ++t, ++it) {
         const int a = it & 1;
@@ -329,28 +329,61 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmHiL, const __grid_constant_
               else { z[0][2 * i + k] = sa; z[NCH - 1][2 * i + k] = sb_; }
             }
           if (sb + C::NEW < NSB) issue(sb + C::NEW);                      // next sub-block in flight during the stores
-          // output offsets (or -1) of this thread's positions from the table
-          const int* ot = otab + t * C::TILE_N + sb * 32 + 2 * m;
+          if (C::POOL) {
+            // output offsets (or -1) of this thread's positions from the table; one shared-memory atomicMax per output
+            const int* ot = otab + t * C::TILE_N + sb * 32 + 2 * m;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int2 o2 = *reinterpret_cast<const int2*>(ot + 8 * i);
+            for (int i = 0; i < 4; ++i) {
+              const int2 o2 = *reinterpret_cast<const int2*>(ot + 8 * i);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint32_t off = (uint32_t)(k ? o2.y : o2.x);
+              for (int k = 0; k < 2; ++k) {
+                const uint32_t off = (uint32_t)(k ? o2.y : o2.x);
 #pragma unroll
-              for (int h = 0; h < NCH; ++h) {
-                if (off < chlim[h] && !(p.flags & 1)) {                   // -1 (padding / garbage column) fails too
-                  const float rr = z[h][2 * i + k] * p.w_scale_inv + bias[h];
-                  const float o = rr > 0.f ? fminf(rr, 65504.f) : 0.f;
-                  if (C::POOL) {
+                for (int h = 0; h < NCH; ++h) {
+                  if (off < chlim[h] && !(p.flags & 1)) {                 // -1 (padding / garbage column) fails too
+                    const float rr = z[h][2 * i + k] * p.w_scale_inv + bias[h];
+                    const float o = rr > 0.f ? fminf(rr, 65504.f) : 0.f;
                     atomicMax(pooled + off + co[h], __float_as_uint(o));  // o >= +0: uint order == float order
-                  } else {
-                    const nnal_h hh = __float2half_rn(o);
-                    const nnal_h ll = __float2half_rn(o - __half2float(hh));
-                    ghi[off + co[h]] = hh;
-                    glo[off + co[h]] = ll;
                   }
                 }
+              }
+            }
+          } else {
+            // fp16 hi/lo planes in global memory.  A thread holds 8 positions of ONE channel (2-byte scattered stores:
+            // measured store bound); an 8x8 register transpose among the 8 lanes that share m (lane ^ 4, ^ 8, ^ 16)
+            // turns that into ONE position with 8 consecutive channels: a 16-byte store per plane.
+#pragma unroll
+            for (int h = 0; h < NCH; ++h) {
+              uint32_t P[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float rr = z[h][j] * p.w_scale_inv + bias[h];
+                const float o = rr > 0.f ? fminf(rr, 65504.f) : 0.f;
+                const nnal_h hh = __float2half_rn(o);
+                P[j] = nnal_pack2(hh, __float2half_rn(o - __half2float(hh)));
+              }
+#pragma unroll
+              for (int sft = 1; sft < 8; sft <<= 1) {
+                const bool up = (cq & sft) != 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (j & sft) continue;
+                  const uint32_t recv = __shfl_xor_sync(0xffffffffu, up ? P[j] : P[j ^ sft], 4 * sft);
+                  if (up) P[j] = recv; else P[j ^ sft] = recv;
+                }
+              }
+              // now P[c'] = channel (base + c') of position index cq of this m group
+              const int col = sb * 32 + 8 * (cq >> 1) + 2 * m + (cq & 1);
+              const uint32_t off = (uint32_t)otab[t * C::TILE_N + col];
+              const int chbase = C::TAPS == 2 ? 8 * w : 16 * w + 8 * h;
+              if (off < glim && chbase < C::COUT_REAL && !(p.flags & 1)) {
+                uint4 vh, vl;
+                vh.x = __byte_perm(P[0], P[1], 0x5410); vl.x = __byte_perm(P[0], P[1], 0x7632);
+                vh.y = __byte_perm(P[2], P[3], 0x5410); vl.y = __byte_perm(P[2], P[3], 0x7632);
+                vh.z = __byte_perm(P[4], P[5], 0x5410); vl.z = __byte_perm(P[4], P[5], 0x7632);
+                vh.w = __byte_perm(P[6], P[7], 0x5410); vl.w = __byte_perm(P[6], P[7], 0x7632);
+                *reinterpret_cast<uint4*>(ghi + off + chbase) = vh;
+                if (!(p.flags & 2)) *reinterpret_cast<uint4*>(glo + off + chbase) = vl;
               }
             }
           }
