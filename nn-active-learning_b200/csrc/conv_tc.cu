@@ -25,7 +25,7 @@
 //   * The T M-tiles of a sample group are processed in NG groups of TG tiles (the weight ring is streamed
 //     once per tile group): 2 x TG x 2Cout accumulator columns fit TMEM, so the epilogue of one tile group
 //     overlaps the MMAs of the next.
-// Warp roles: warp 0 input TMA, warp 3 weight producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// Warp roles: warp 0 input TMA, warp 3 weight producer, warps 1 and 12 MMA issuers, warp 2 TMEM allocator,
 // warps 4-11 epilogue (TMEM -> +bias, ReLU -> fp16 hi/lo NHWC in global memory, or the fused max-pool raster):
 // two warpgroups, one per accumulator.
 #include "nnal_common.cuh"
@@ -123,8 +123,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // Compile-time geometry of one conv layer
-template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_, bool POOL_ = false>
+template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_, bool POOL_ = false, bool DUAL_ = false>
 struct Cfg {
+  static constexpr int NISSUE = DUAL_ ? 2 : 1;            // MMA-issuing threads (tiles of a group alternate between them)
   static constexpr bool POOL = POOL_;                     // fuse the following 2x2/s2 SAME max-pool into the epilogue
   // CIN / COUT are the padded operand extents (multiples of 8 / 16); the *_REAL values are the layer's
   static constexpr int CIN_REAL = CIN_REAL_, COUT_REAL = COUT_REAL_;
@@ -177,7 +178,7 @@ struct ConvParams {
 };
 
 template <class C>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(416, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -206,9 +207,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmLo));
   }
   if (warp == 1 && lane == 0) {
-    for (int b = 0; b < 2; ++b) { mbar_init(in_full(b), 1); mbar_init(in_empty(b), 1); }
-    for (int s = 0; s < 3; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 4); }
+    // two MMA-issuing threads (see below): every "MMAs retired" barrier collects one commit from each
+    for (int b = 0; b < 2; ++b) { mbar_init(in_full(b), 1); mbar_init(in_empty(b), C::NISSUE); }
+    for (int s = 0; s < 3; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), C::NISSUE); }
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), C::NISSUE); mbar_init(acc_empty(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -278,11 +280,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    // One thread issues every tcgen05.mma; with N as small as 32 an MMA retires in 16-32 clocks, so the
-    // issue loop is kept to a few instructions per MMA: per-K-step descriptor words come from the
-    // table built above, per-tile descriptors differ by a compile-time constant.
+  } else if (warp == 1 || (warp == 12 && C::NISSUE == 2)) {
+    // ===== MMA issuers =====
+    // tcgen05.mma does not run ahead of the tensor pipe: the issuing thread is held until the instruction is accepted,
+    // and every cycle it spends on anything else (descriptor arithmetic, barrier waits, commits) is a cycle the pipe
+    // idles (scripts/microbench/mma_rate.cu: a gap of g cycles between bursts costs g cycles; clock64 probes put
+    // these gaps at 20-30 % of conv1/conv3/conv4).  With NISSUE == 2 two threads issue concurrently, each for every
+    // other tile of the tile group (independent accumulator columns, same operands): one thread's gaps are filled by
+    // the other's MMAs -- conv4 5.3 -> 4.6 ms per 100k patches.  The concatenated configurations keep one issuer:
+    // halving the tiles per thread halves the distance between two MMAs on the same accumulator, and that costs more
+    // than the filled gaps gain (conv1 4.4 -> 6.3 ms).  Per-K-step descriptor words come from the table built above,
+    // per-tile descriptors differ by a compile-time constant.
+    const int mi = warp == 1 ? 0 : 1;
     {
       const uint32_t idesc_cat = make_idesc_bf16(128, 2 * C::COUT);   // A_hi x [W_hi;W_lo]
       const uint32_t idesc_hi = make_idesc_bf16(128, C::COUT);        // A_lo x W_hi
@@ -323,14 +332,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     // the two MMAs of a tile accumulate into the same columns: issue them TG MMAs apart
 #pragma unroll
                     for (int t = 0; t < C::TG; ++t) {
-                      if (tg * C::TG + t < C::T) {
+                      if ((t % C::NISSUE) == mi && tg * C::TG + t < C::T) {
                         const uint64_t dAh = ((uint64_t)DESC_HI << 32) | (ah + t * 128);
                         umma_bf16(d_base + t * C::TILE_COLS, dAh, dB, idesc_cat, acc0);   // cols [0,COUT): hi.hi  [COUT,2COUT): hi.lo
                       }
                     }
 #pragma unroll
                     for (int t = 0; t < C::TG; ++t) {
-                      if (tg * C::TG + t < C::T) {
+                      if ((t % C::NISSUE) == mi && tg * C::TG + t < C::T) {
                         const uint64_t dAl = ((uint64_t)DESC_HI << 32) | (al + t * 128);
                         umma_bf16(d_base + t * C::TILE_COLS, dAl, dB, idesc_hi, 1);       // cols [0,COUT) += lo.hi
                       }
@@ -339,7 +348,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     const uint64_t dBl = dB + (uint64_t)C::COUT;                          // lo rows start COUT*16 B further
 #pragma unroll
                     for (int t = 0; t < C::TG; ++t) {
-                      if (tg * C::TG + t < C::T) {
+                      if ((t % C::NISSUE) == mi && tg * C::TG + t < C::T) {
                         const uint64_t dAh = ((uint64_t)DESC_HI << 32) | (ah + t * 128);
                         const uint64_t dAl = ((uint64_t)DESC_HI << 32) | (al + t * 128);
                         const uint32_t d = d_base + t * C::TILE_COLS;
@@ -363,7 +372,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ===== epilogue: two warpgroups, warpgroup wg drains accumulator wg (every other tile group) =====
     const int qd = warp & 3;
     const int wg = (warp - 4) >> 2;
@@ -537,8 +546,8 @@ typedef Cfg<25, 25, 24, 32, 5, 1, 8, 2, 3, true> CfgConv2;    // PW1 conv2: 6 M 
 // per K-step and tile at TG = 2 against 100 at TG = 4), and four tiles of 96 columns do not fit TMEM twice.  conv4
 // would need 2 x 192 columns per tile and its 166 KB weight set streamed once per tile (L2-bound).
 typedef Cfg<13, 13, 32, 48, 3, 2, 6, 2, 4, false> CfgConv3;   // PW1 conv3: 2 samples, 4 M tiles
-typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2, false> CfgConv4;   // PW1 conv4: 2 M tiles
-typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2, false, true> CfgConv4Pool;   // ... with the following 2x2 max-pool fused (shared-memory atomicMax raster)
+typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2, false, false, true> CfgConv4;   // PW1 conv4: 2 M tiles, one per issuing thread
+typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2, false, true, true> CfgConv4Pool;   // ... with the following 2x2 max-pool fused (shared-memory atomicMax raster)
 
 template <class C>
 static bool matches(const Layer& L) {
@@ -573,7 +582,7 @@ static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal
   p.wpack = (const uint8_t*)L.Wh; p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.n = (int)n; p.w_scale_inv = L.w_scale_inv;
   const int ngroups = (int)((n + C::G - 1) / C::G);
   const int grid = ngroups < ctx->sm_count ? ngroups : ctx->sm_count;
-  conv_tc_kernel<C><<<grid, 384, C::SMEM, ctx->stream>>>(tmHi, tmLo, p);
+  conv_tc_kernel<C><<<grid, 416, C::SMEM, ctx->stream>>>(tmHi, tmLo, p);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
