@@ -318,6 +318,8 @@ def run_ours(args, rank, world):
         roofline = {'kernel': top, 'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                     'frac': achieved / peak,
                     'traffic': None if tr is None else tr['dram_bytes_per_sample'] * samples_per_launch,
+                    'executed': None if not tinfo['tc'] else {'achieved': 3 * achieved, 'frac': 3 * achieved / peak,
+                                                             'what': 'tensor-pipe FLOPs actually issued: 3 MMAs per product'},
                     'note': 'algorithmic FLOPs (2*MACs) per launch / mean launch time; peak = %s sustained bf16; '
                             '%s' % (peaks['source'], 'tcgen05 fp16 hi/lo split executes 3x these FLOPs'
                                     if tinfo['tc'] else 'FP32 CUDA-core kernel (no tensor pipe)')}
