@@ -319,7 +319,7 @@ def run_ours(args, rank, world):
                     'frac': achieved / peak,
                     'traffic': None if tr is None else tr['dram_bytes_per_sample'] * samples_per_launch,
                     'executed': None if not tinfo['tc'] else {'achieved': 3 * achieved, 'frac': 3 * achieved / peak,
-                                                             'what': 'tensor-pipe FLOPs actually issued: 3 MMAs per product'},
+                                                             'what': 'useful tensor FLOPs of the split-precision scheme: hi.hi + hi.lo + lo.hi per product'},
                     'note': 'algorithmic FLOPs (2*MACs) per launch / mean launch time; peak = %s sustained bf16; '
                             '%s' % (peaks['source'], 'tcgen05 fp16 hi/lo split executes 3x these FLOPs'
                                     if tinfo['tc'] else 'FP32 CUDA-core kernel (no tensor pipe)')}
