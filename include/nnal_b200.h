@@ -249,7 +249,8 @@ int nnal_debug_fc(nnal_ctx* ctx, const float* A, const float* W, const float* b,
 
 /* One conv layer (SAME, stride 1, bias, ReLU; NN.py:285-290) on host NHWC buffers.  use_tc: 0 CUDA-core kernel,
  * 1 tcgen05 kernel with positions on M (conv_tc.cu), 2 weight-stationary tcgen05 kernel (conv_wt.cu), 3 = 2 and 4 = 1 with
- * the following 2x2/s2 SAME max-pool (NN.py:1473-1477) fused: out is then [n][ceil(H/2)][ceil(Wd/2)][Cout]. */
+ * the following 2x2/s2 SAME max-pool (NN.py:1473-1477) fused: out is then [n][ceil(H/2)][ceil(Wd/2)][Cout];
+ * 5 = PW1 conv1 with the 5 filter columns folded into the channel axis (x-im2col'd input, conv_tc.cu CfgConv1X). */
 int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, const float* b, int64_t n, int H, int Wd, int Cin,
                     int Cout, int ks, int use_tc, float* out);
 

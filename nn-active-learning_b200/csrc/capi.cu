@@ -33,6 +33,8 @@ extern "C" int nnal_ctx_create(int device, nnal_ctx** out) {
   ctx->use_tc = (f && atoi(f)) ? 0 : 1;
   const char* fw = getenv("NNAL_CONV_WT");   // 0: conv_tc.cu only, 1: conv_wt.cu where faster, 2 (default): + pool fusion, 3: wherever supported
   ctx->use_wt = fw ? atoi(fw) : 2;
+  const char* fx = getenv("NNAL_CONV_X16");
+  ctx->use_x16 = fx ? atoi(fx) : 0;      // measured: conv1 4.2 -> 3.2 ms but the gather writes twice the bytes (0.84 -> 1.6 ms): off by default
   *out = ctx;
   return NNAL_OK;
 }
@@ -44,6 +46,7 @@ static void free_layers(nnal_ctx* ctx) {
     if (L.Wh) cudaFree(L.Wh);
     if (L.Wl) cudaFree(L.Wl);
     if (L.Wt) cudaFree(L.Wt);
+    if (L.Wx) cudaFree(L.Wx);
   }
   ctx->layers.clear();
 }
@@ -473,7 +476,7 @@ extern "C" int nnal_pool_mc_read(nnal_ctx* ctx, double* av_post, double* av_ent)
 }
 
 static int reserve_forward(nnal_ctx* ctx, int64_t nb) {
-  size_t mx = (size_t)ctx->in_h * ctx->in_w * ((ctx->in_c + 7) / 8 * 8);
+  size_t mx = (size_t)ctx->in_h * ctx->in_w * std::max(16, (ctx->in_c + 7) / 8 * 8);   // padded / x-im2col'd input planes
   for (auto& L : ctx->layers) {
     size_t o = L.type == NNAL_LAYER_FC ? (size_t)L.out_dim : (size_t)L.out_h * L.out_w * L.out_c;
     mx = std::max(mx, o);
@@ -481,7 +484,7 @@ static int reserve_forward(nnal_ctx* ctx, int64_t nb) {
   NNAL_TRY(devbuf_reserve(ctx, ctx->act[0], (size_t)nb * mx * sizeof(float)));
   NNAL_TRY(devbuf_reserve(ctx, ctx->act[1], (size_t)nb * mx * sizeof(float)));
   // input staging: fp32 NHWC, or (fused gather) fp16 hi/lo planes padded to 8 channels
-  NNAL_TRY(devbuf_reserve(ctx, ctx->xin, (size_t)nb * ctx->in_h * ctx->in_w * std::max<size_t>((size_t)ctx->in_c * sizeof(float), 32)));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->xin, (size_t)nb * ctx->in_h * ctx->in_w * std::max<size_t>((size_t)ctx->in_c * sizeof(float), 64)));
   return NNAL_OK;
 }
 
@@ -502,7 +505,9 @@ static int pool_eval_impl(nnal_ctx* ctx, int subject, const int64_t* inds, bool 
   const int64_t chunk = std::min(chunk_size(), n);
   NNAL_TRY(reserve_forward(ctx, chunk));
   // gather straight into the first conv's tensor-core input planes when it takes them
-  const bool fused = nnal_first_layer_wants_split8(ctx) && nnal_k_gather_split_supported(*v, d3) && getenv("NNAL_NO_FUSED_GATHER") == nullptr;
+  const bool fused_ok = getenv("NNAL_NO_FUSED_GATHER") == nullptr;
+  const bool fused16 = fused_ok && nnal_first_layer_wants_x16(ctx) && nnal_k_gather_x16_supported(*v, d1, d2, d3);
+  const bool fused = fused_ok && !fused16 && nnal_first_layer_wants_split8(ctx) && nnal_k_gather_split_supported(*v, d3);
   const int64_t* d_inds = inds;
   if (!inds_on_device) {
     NNAL_TRY(devbuf_reserve(ctx, ctx->inds, (size_t)n * 8));
@@ -512,14 +517,17 @@ static int pool_eval_impl(nnal_ctx* ctx, int subject, const int64_t* inds, bool 
   for (int64_t o = 0; o < n; o += chunk) {
     int64_t nb = std::min(chunk, n - o);
     prof_begin(ctx, NNAL_PROF_GATHER);
-    if (fused) {
+    if (fused16) {
+      nnal_h* hi = (nnal_h*)ctx->xin.p;
+      NNAL_TRY(nnal_k_gather_x16(ctx, *v, d_inds + o, nb, d1, d2, d3, stats, norm_mode, hi, hi + (size_t)nb * d1 * d2 * 16));
+    } else if (fused) {
       nnal_h* hi = (nnal_h*)ctx->xin.p;
       NNAL_TRY(nnal_k_gather_split(ctx, *v, d_inds + o, nb, d1, d2, d3, stats, norm_mode, hi, hi + (size_t)nb * d1 * d2 * 8));
     } else {
       NNAL_TRY(nnal_k_gather_norm_f32(ctx, *v, d_inds + o, nb, d1, d2, d3, d_stats, norm_mode, (float*)ctx->xin.p));
     }
     prof_end(ctx);
-    NNAL_TRY(nnal_forward_chunk(ctx, nb, offset + o, fused));
+    NNAL_TRY(nnal_forward_chunk(ctx, nb, offset + o, fused16 ? 2 : fused ? 1 : 0));
   }
   return NNAL_OK;
 }
@@ -719,7 +727,7 @@ extern "C" int nnal_debug_fc(nnal_ctx* ctx, const float* A, const float* W, cons
   auto cleanup = [&]() {
     cudaStreamSynchronize(ctx->stream);
     if (dA) cudaFree(dA); if (dO) cudaFree(dO);
-    if (L.W) cudaFree(L.W); if (L.b) cudaFree(L.b); if (L.Wh) cudaFree(L.Wh); if (L.Wl) cudaFree(L.Wl); if (L.Wt) cudaFree(L.Wt);
+    if (L.W) cudaFree(L.W); if (L.b) cudaFree(L.b); if (L.Wh) cudaFree(L.Wh); if (L.Wl) cudaFree(L.Wl); if (L.Wt) cudaFree(L.Wt); if (L.Wx) cudaFree(L.Wx);
   };
   if (cudaMalloc(&dA, (size_t)M * K * 4) != cudaSuccess || cudaMalloc(&dO, (size_t)M * N * 4) != cudaSuccess ||
       cudaMalloc(&L.W, (size_t)N * K * 4) != cudaSuccess || cudaMalloc(&L.b, (size_t)N * 4) != cudaSuccess) {
@@ -762,7 +770,7 @@ extern "C" int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, co
   auto cleanup = [&]() {
     cudaStreamSynchronize(ctx->stream);
     if (dX) cudaFree(dX); if (dO) cudaFree(dO); if (ih) cudaFree(ih); if (oh) cudaFree(oh);
-    if (L.W) cudaFree(L.W); if (L.b) cudaFree(L.b); if (L.Wh) cudaFree(L.Wh); if (L.Wl) cudaFree(L.Wl); if (L.Wt) cudaFree(L.Wt);
+    if (L.W) cudaFree(L.W); if (L.b) cudaFree(L.b); if (L.Wh) cudaFree(L.Wh); if (L.Wl) cudaFree(L.Wl); if (L.Wt) cudaFree(L.Wt); if (L.Wx) cudaFree(L.Wx);
   };
   if (cudaMalloc(&dX, ie * 4) != cudaSuccess || cudaMalloc(&dO, oe * 4) != cudaSuccess || cudaMalloc(&ih, ie * 4) != cudaSuccess ||
       cudaMalloc(&oh, oe * 4) != cudaSuccess || cudaMalloc(&L.W, (size_t)ks * ks * Cin * Cout * 4) != cudaSuccess ||
@@ -777,10 +785,24 @@ extern "C" int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, co
   if (use_tc) {
     rc = nnal_tc_prepare_layer(ctx, L);
     if (rc == NNAL_OK && !nnal_tc_conv_supported(ctx, L)) { ctx->err = "shape not supported by the tensor-core conv"; rc = NNAL_ERR_UNSUPPORTED; }
+    bool x16done = false;
+    if (rc == NNAL_OK && use_tc == 5) {
+      // conv1 on the x-im2col'd input: fp32 -> [n][H][W][16] hi/lo planes -> CfgConv1X
+      if (!nnal_tc_conv_x16_supported(ctx, L)) { ctx->err = "shape not supported by the x-im2col'd conv"; rc = NNAL_ERR_UNSUPPORTED; }
+      const size_t iex = (size_t)n * H * Wd * 16;
+      nnal_h* ix = nullptr;
+      if (rc == NNAL_OK && cudaMalloc(&ix, iex * 4) != cudaSuccess) { cleanup(); NNAL_FAIL(ctx, NNAL_ERR_CUDA, "debug_conv allocation failed"); }
+      if (rc == NNAL_OK) rc = nnal_k_split_x16(ctx, dX, ix, ix + iex, (int64_t)n * H * Wd, Wd, Cin, ks);
+      if (rc == NNAL_OK) rc = nnal_tc_conv_x16(ctx, L, ix, ix + iex, oh, oh + oe, n);
+      if (rc == NNAL_OK) rc = nnal_k_merge_flat(ctx, oh, oh + oe, dO, (int64_t)oe);
+      cudaStreamSynchronize(ctx->stream);
+      if (ix) cudaFree(ix);
+      x16done = true;
+    }
     const int cp = (Cin + 7) / 8 * 8;
     const size_t iep = (size_t)n * H * Wd * cp;
     if (cp != Cin) { cudaFree(ih); ih = nullptr; if (cudaMalloc(&ih, iep * 4) != cudaSuccess) { cleanup(); NNAL_FAIL(ctx, NNAL_ERR_CUDA, "debug_conv allocation failed"); } }
-    if (rc == NNAL_OK) rc = nnal_k_split_pad(ctx, dX, ih, ih + iep, (int64_t)n * H * Wd, Cin, cp);
+    if (rc == NNAL_OK && !x16done) rc = nnal_k_split_pad(ctx, dX, ih, ih + iep, (int64_t)n * H * Wd, Cin, cp);
     if (rc == NNAL_OK && (use_tc == 2 || use_tc == 3) &&
         !(use_tc == 3 ? nnal_wt_conv_pool_supported(ctx, L) : nnal_wt_conv_supported(ctx, L))) {
       ctx->err = "shape not supported by the weight-stationary conv"; rc = NNAL_ERR_UNSUPPORTED;
@@ -788,11 +810,12 @@ extern "C" int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, co
     if (rc == NNAL_OK && use_tc == 4 && !nnal_tc_conv_pool_supported(ctx, L)) {
       ctx->err = "conv+pool shape not supported by the tensor-core conv"; rc = NNAL_ERR_UNSUPPORTED;
     }
-    if (use_tc >= 3) oe_out = (size_t)n * ((H + 1) / 2) * ((Wd + 1) / 2) * Cout;      // fused 2x2/s2 SAME max-pool
-    if (rc == NNAL_OK) rc = use_tc == 4 ? nnal_tc_conv_pool(ctx, L, ih, ih + iep, oh, oh + oe_out, n)
-                          : use_tc >= 2 ? nnal_wt_conv(ctx, L, ih, ih + iep, oh, oh + oe_out, n, use_tc == 3)
-                                        : nnal_tc_conv(ctx, L, ih, ih + iep, oh, oh + oe, n);
-    if (rc == NNAL_OK) rc = nnal_k_merge_flat(ctx, oh, oh + oe_out, dO, (int64_t)oe_out);
+    if (use_tc == 3 || use_tc == 4) oe_out = (size_t)n * ((H + 1) / 2) * ((Wd + 1) / 2) * Cout;      // fused 2x2/s2 SAME max-pool
+    if (rc == NNAL_OK && !x16done)
+      rc = use_tc == 4 ? nnal_tc_conv_pool(ctx, L, ih, ih + iep, oh, oh + oe_out, n)
+         : use_tc >= 2 ? nnal_wt_conv(ctx, L, ih, ih + iep, oh, oh + oe_out, n, use_tc == 3)
+                       : nnal_tc_conv(ctx, L, ih, ih + iep, oh, oh + oe, n);
+    if (rc == NNAL_OK && !x16done) rc = nnal_k_merge_flat(ctx, oh, oh + oe_out, dO, (int64_t)oe_out);
   } else {
     rc = nnal_k_conv_simt(ctx, L, dX, dO, n);
   }

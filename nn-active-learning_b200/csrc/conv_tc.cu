@@ -122,9 +122,31 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// waits for every outstanding tcgen05.ld of the thread; both register sets are in/out operands so that their uses stay below
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t* a, uint32_t* b) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+                 "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(b[0]),
+                 "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]),
+                 "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+               :
+               : "memory");
+}
+
 // Compile-time geometry of one conv layer
-template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_, bool POOL_ = false, bool DUAL_ = false>
+template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_, bool POOL_ = false, bool DUAL_ = false, int KW_ = 0, int NWG_ = 2>
 struct Cfg {
+  static constexpr int NWG = 2;                           // epilogue warpgroups, one per accumulator: warpgroup wg drains every other tile group
+  static_assert(NWG_ == 2, "tile-level splits over more warpgroups were measured slower: extra warps on the issuing warp's scheduler delay the MMAs");
+  static constexpr int THREADS = 32 * (4 + 4 * NWG_ + 1); // 4 service warps, 4 * NWG epilogue warps, the second MMA issuer
   static constexpr int NISSUE = DUAL_ ? 2 : 1;            // MMA-issuing threads (tiles of a group alternate between them)
   static constexpr bool POOL = POOL_;                     // fuse the following 2x2/s2 SAME max-pool into the epilogue
   // CIN / COUT are the padded operand extents (multiples of 8 / 16); the *_REAL values are the layer's
@@ -134,10 +156,11 @@ struct Cfg {
   static constexpr int KPS = KPS_;                       // K-steps per weight stage
   static constexpr int NBUF = NBUF_, NACC = 2, TG = TG_;  // TG: M tiles per accumulator (tile group)
   static constexpr bool CAT = CAT_;                      // A_hi x [W_hi;W_lo] in one MMA (2 MMAs per K-step) or three separate MMAs
-  static constexpr int PH = KS / 2;
-  static constexpr int HP = H + KS - 1, WP = W + KS - 1;
+  static constexpr int KH = KS_, KW = KW_ > 0 ? KW_ : KS_;   // KW_ = 1: filter columns folded into the channels by an x-im2col'd input
+  static constexpr int PH = KH / 2, PW = KW / 2;
+  static constexpr int HP = H + KH - 1, WP = W + KW - 1;
   static constexpr int Q = CIN / 8;
-  static constexpr int NTAPS = KS * KS;
+  static constexpr int NTAPS = KH * KW;
   static constexpr int NCH = NTAPS * Q;                  // 16-byte chunks along K
   static constexpr int NK = (NCH + 1) / 2;               // K=16 MMA steps
   static constexpr int NSTAGE_W = (NK + KPS - 1) / KPS;  // weight stages per group
@@ -147,7 +170,7 @@ struct Cfg {
   static constexpr int NG = (T + TG - 1) / TG;           // tile groups per sample group
   static constexpr int TILE_COLS = CAT ? 2 * COUT : COUT; // TMEM columns of one M tile (CAT: hi.hi+lo.hi | hi.lo halves)
   static constexpr int ACC_COLS = TG * TILE_COLS;        // TMEM columns of one accumulator
-  static constexpr int MAX_OFF = (KS - 1) * WP + (KS - 1);
+  static constexpr int MAX_OFF = (KH - 1) * WP + (KW - 1);
   static constexpr int PLANE = ((RASTER * 16 + 127) / 128) * 128;                 // bytes
   static constexpr int OVERRUN = (T * 128 + MAX_OFF + 8 - RASTER) > 0 ? (T * 128 + MAX_OFF + 8 - RASTER) : 0;
   static constexpr int IN_BYTES = ((2 * Q * PLANE + OVERRUN * 16 + 1023) / 1024) * 1024;   // hi planes then lo planes
@@ -178,7 +201,7 @@ struct ConvParams {
 };
 
 template <class C>
-__global__ void __launch_bounds__(416, 1)
+__global__ void __launch_bounds__(C::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -201,6 +224,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
   const int ngroups = (p.n + C::G - 1) / C::G;
   uint32_t* pooled = reinterpret_cast<uint32_t*>(base_ptr + C::NBUF * C::IN_BYTES + C::WSTAGES * C::W_STAGE_BYTES + 256);
   for (int i = threadIdx.x; i < C::POOL_BYTES / 4; i += blockDim.x) pooled[i] = 0u;
+  __shared__ __align__(16) float sbias[(C::COUT + 15) / 16 * 16];
+  for (int i = threadIdx.x; i < (C::COUT + 15) / 16 * 16; i += blockDim.x) sbias[i] = i < C::COUT_REAL ? p.bias[i] : 0.f;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmHi));
@@ -231,11 +256,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
   for (int ks = threadIdx.x; ks < C::NK; ks += blockDim.x) {
     const int c0 = 2 * ks, c1 = 2 * ks + 1;
     const int q0 = c0 / C::NTAPS, t0 = c0 % C::NTAPS;
-    const uint32_t off0 = q0 * C::PLANE + ((t0 / C::KS) * C::WP + (t0 % C::KS)) * 16;
+    const uint32_t off0 = q0 * C::PLANE + ((t0 / C::KW) * C::WP + (t0 % C::KW)) * 16;
     uint32_t lbo = 16;                    // dummy second chunk of an odd K tail (zero weights) stays in-plane
     if (c1 < C::NCH) {
       const int q1 = c1 / C::NTAPS, t1 = c1 % C::NTAPS;
-      lbo = q1 * C::PLANE + ((t1 / C::KS) * C::WP + (t1 % C::KS)) * 16 - off0;
+      lbo = q1 * C::PLANE + ((t1 / C::KW) * C::WP + (t1 % C::KW)) * 16 - off0;
     }
     ktab[ks] = make_uint2(off0 >> 4, ((lbo >> 4) & 0x3fffu) << 16);
   }
@@ -256,8 +281,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         mbar_arrive_expect_tx(in_full(b), 2 * C::Q * C::RASTER * 16);
 #pragma unroll 1
         for (int q = 0; q < C::Q; ++q) {
-          tma_load_4d(dst + q * C::PLANE, &tmHi, in_full(b), q * 8, -C::PH, -C::PH, g * C::G);
-          tma_load_4d(dst + (C::Q + q) * C::PLANE, &tmLo, in_full(b), q * 8, -C::PH, -C::PH, g * C::G);
+          tma_load_4d(dst + q * C::PLANE, &tmHi, in_full(b), q * 8, -C::PW, -C::PH, g * C::G);
+          tma_load_4d(dst + (C::Q + q) * C::PLANE, &tmLo, in_full(b), q * 8, -C::PW, -C::PH, g * C::G);
         }
       }
     }
@@ -280,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1 || (warp == 12 && C::NISSUE == 2)) {
+  } else if (warp == 1 || (warp == 4 + 4 * C::NWG && C::NISSUE == 2)) {
     // ===== MMA issuers =====
     // tcgen05.mma does not run ahead of the tensor pipe: the issuing thread is held until the instruction is accepted,
     // and every cycle it spends on anything else (descriptor arithmetic, barrier waits, commits) is a cycle the pipe
@@ -372,17 +397,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         }
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4 && warp < 4 + 4 * C::NWG) {
     // ===== epilogue: two warpgroups, warpgroup wg drains accumulator wg (every other tile group) =====
     const int qd = warp & 3;
     const int wg = (warp - 4) >> 2;
-    uint32_t* my_pooled = pooled + wg * C::POOL_WORDS;
     uint32_t it = 0;
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
 #pragma unroll 1
       for (int tg = 0; tg < C::NG; ++tg, ++it) {
         if ((int)(it % C::NACC) != wg) continue;
         const int a = it % C::NACC;
+        uint32_t* my_pooled = pooled + a * C::POOL_WORDS;           // one pooled raster per accumulator (= per sample in flight)
         const uint32_t ph_acc = (it / C::NACC) & 1;
         mbar_wait(acc_full(a), ph_acc);
         tc_fence_after();
@@ -400,13 +425,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
           const uint32_t tcol = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * C::ACC_COLS + tl * C::TILE_COLS);
 #pragma unroll 1
           for (int c0 = 0; c0 < C::COUT_REAL; c0 += 16) {
-            float v[16], w[16];
-            tmem_ld16(tcol + c0, v);                             // hi.hi + lo.hi (CAT) or the full sum
-            if (C::CAT) {
-              tmem_ld16(tcol + C::COUT + c0, w);                 // hi.lo
-            } else {
+            // The epilogue is instruction bound (4 warps per accumulator, ~1 instruction per 5 cycles each): one wait for
+            // both TMEM loads, the bias from shared memory as 4 broadcast 16-byte loads, packed fp16 conversions.
+            float v[16];
+            {
+              uint32_t rv[16], rw[16];
+              tmem_ld16_issue(tcol + c0, rv);                    // hi.hi + lo.hi (CAT) or the full sum
+              if (C::CAT) tmem_ld16_issue(tcol + C::COUT + c0, rw);   // hi.lo
+              tmem_ld16_wait(rv, rw);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) w[j] = 0.f;
+              for (int j = 0; j < 16; ++j) v[j] = C::CAT ? __uint_as_float(rv[j]) + __uint_as_float(rw[j]) : __uint_as_float(rv[j]);
+            }
+            float bb[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+              bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
             }
             if (valid && C::POOL) {
               // post-ReLU values are >= +0, so their bit patterns order like unsigned integers
@@ -414,7 +448,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 if (c0 + j < C::COUT_REAL) {
-                  const float r = (v[j] + w[j]) * p.w_scale_inv + __ldg(p.bias + c0 + j);
+                  const float r = v[j] * p.w_scale_inv + bb[j];
                   atomicMax(pc + j, __float_as_uint(r > 0.f ? fminf(r, 65504.f) : 0.f));
                 }
               }
@@ -422,14 +456,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
               uint32_t hi[8], lo[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const int ca = c0 + 2 * j < C::COUT_REAL ? c0 + 2 * j : 0, cb = c0 + 2 * j + 1 < C::COUT_REAL ? c0 + 2 * j + 1 : 0;
-                float x0 = fmaxf((v[2 * j] + w[2 * j]) * p.w_scale_inv + __ldg(p.bias + ca), 0.f);
-                float x1 = fmaxf((v[2 * j + 1] + w[2 * j + 1]) * p.w_scale_inv + __ldg(p.bias + cb), 0.f);
-                nnal_h h0, h1, l0, l1;
-                nnal_split(x0, h0, l0);
-                nnal_split(x1, h1, l1);
-                hi[j] = nnal_pack2(h0, h1);
-                lo[j] = nnal_pack2(l0, l1);
+                const float x0 = fminf(fmaxf(v[2 * j] * p.w_scale_inv + bb[2 * j], 0.f), 65504.f);
+                const float x1 = fminf(fmaxf(v[2 * j + 1] * p.w_scale_inv + bb[2 * j + 1], 0.f), 65504.f);
+                const __half2 h = __floats2half2_rn(x0, x1);              // .x (low half) = x0
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+                lo[j] = *reinterpret_cast<const uint32_t*>(&l);
               }
               uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
               uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
@@ -482,9 +515,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
 }
 
 // W fp32 [kh][kw][cin][cout] -> packed fp16 [NSTAGE_W][KPS][2 chunks][hi COUT rows | lo COUT rows][8]
-__global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int KS, int CIN, int COUT,
+__global__ void pack_conv_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int NTAPS, int CIN, int COUT,
                                          int CIN_REAL, int COUT_REAL, int KPS, int NK, int NSTAGE, float scale) {
-  const int NTAPS = KS * KS, Q = CIN / 8, NCH = NTAPS * Q;
+  const int Q = CIN / 8, NCH = NTAPS * Q;
   const int64_t total = (int64_t)NSTAGE * KPS * 2 * COUT * 8;
   nnal_h* o = reinterpret_cast<nnal_h*>(out);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -540,6 +573,11 @@ static int make_act_tmap(nnal_ctx* ctx, CUtensorMap* tm, const void* ptr, int n,
 
 //                 H   W  CIN COUT KS G KPS NBUF TG CAT
 typedef Cfg<25, 25, 3, 24, 5, 1, 7, 2, 3, true> CfgConv1;     // PW1 conv1: 3 input channels zero-padded to one 8-channel chunk
+// conv1 with the filter COLUMNS folded into the channel axis: the input is x-im2col'd to 16 "channels"
+// (element dx * 3 + ch of position (y, x) = in[y][x + dx - 2][ch], zero outside the patch, element 15 = 0), the filter
+// becomes 5 x 1 over 16 channels: K = 5 taps x 16 = 80 instead of 25 taps x 8 (3 real) = 200, no x padding (5 M tiles
+// instead of 6): 50 MMAs per sample instead of 156
+typedef Cfg<25, 25, 16, 24, 5, 1, 5, 2, 3, true, false, false, 1> CfgConv1X;
 typedef Cfg<25, 25, 24, 32, 5, 1, 8, 2, 3, true> CfgConv2;    // PW1 conv2: 6 M tiles in 2 groups of 3
 // conv3/conv4: the concatenated form was measured for conv3 (TG = 2, N = 96 + 48): 2.63 ms vs 2.61 ms per 100k samples
 // -- with only two accumulators in rotation the MMAs wait on each other (scripts/microbench/mma_rate.cu: 129 cycles
@@ -555,21 +593,23 @@ static bool matches(const Layer& L) {
 }
 
 template <class C>
-static int pack(nnal_ctx* ctx, Layer& L) {
+static int pack_from(nnal_ctx* ctx, const float* W, void** dst, float w_scale) {
   size_t bytes = (size_t)C::NSTAGE_W * C::W_STAGE_BYTES;
-  if (!L.Wh) CUDA_TRY(ctx, cudaMalloc(&L.Wh, bytes));
+  if (!*dst) CUDA_TRY(ctx, cudaMalloc(dst, bytes));
   int64_t total = (int64_t)C::NSTAGE_W * C::KPS * 2 * C::COUT * 8;
   int grid = (int)((total + 255) / 256);
-  pack_conv_weights_kernel<<<grid, 256, 0, ctx->stream>>>(L.W, (uint8_t*)L.Wh, C::KS, C::CIN, C::COUT, C::CIN_REAL, C::COUT_REAL, C::KPS, C::NK,
-                                                          C::NSTAGE_W, L.w_scale);
+  pack_conv_weights_kernel<<<grid, 256, 0, ctx->stream>>>(W, (uint8_t*)*dst, C::NTAPS, C::CIN, C::COUT, C::CIN_REAL, C::COUT_REAL, C::KPS, C::NK,
+                                                          C::NSTAGE_W, w_scale);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
 }
+template <class C>
+static int pack(nnal_ctx* ctx, Layer& L) { return pack_from<C>(ctx, L.W, (void**)&L.Wh, L.w_scale); }
 
 template <class C>
 static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
-                  nnal_h* out_lo, int64_t n) {
+                  nnal_h* out_lo, int64_t n, const void* wpack = nullptr) {
   CUtensorMap tmHi, tmLo;
   NNAL_TRY(make_act_tmap(ctx, &tmHi, in_hi, (int)n, C::H, C::W, C::CIN, C::WP, C::HP, C::G));
   NNAL_TRY(make_act_tmap(ctx, &tmLo, in_lo, (int)n, C::H, C::W, C::CIN, C::WP, C::HP, C::G));
@@ -579,10 +619,10 @@ static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal
     attr = true;
   }
   ConvParams p;
-  p.wpack = (const uint8_t*)L.Wh; p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.n = (int)n; p.w_scale_inv = L.w_scale_inv;
+  p.wpack = (const uint8_t*)(wpack ? wpack : L.Wh); p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.n = (int)n; p.w_scale_inv = L.w_scale_inv;
   const int ngroups = (int)((n + C::G - 1) / C::G);
   const int grid = ngroups < ctx->sm_count ? ngroups : ctx->sm_count;
-  conv_tc_kernel<C><<<grid, 416, C::SMEM, ctx->stream>>>(tmHi, tmLo, p);
+  conv_tc_kernel<C><<<grid, C::THREADS, C::SMEM, ctx->stream>>>(tmHi, tmLo, p);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
@@ -605,6 +645,65 @@ int nnal_tc_prepare_conv(nnal_ctx* ctx, Layer& L) {
   return NNAL_OK;
 }
 
+// ---- conv1 on x-im2col'd input ("x16") -------------------------------------------------------------------------
+namespace ctc {
+// W fp32 [5][5][C][cout] -> W' fp32 [5][1][16][cout]:  W'[dy][0][dx * C + ch][co] = W[dy][dx][ch][co], rest 0
+__global__ void rearrange_x16_kernel(const float* __restrict__ W, float* __restrict__ Wx, int KH, int KW, int C, int COUT) {
+  const int total = KH * 16 * COUT;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int co = e % COUT, j = (e / COUT) % 16, dy = e / (COUT * 16);
+    const int dx = j / C, ch = j % C;
+    Wx[e] = (dx < KW) ? W[(((size_t)dy * KW + dx) * C + ch) * COUT + co] : 0.f;
+  }
+}
+// fp32 NHWC [n][H][W][C] -> x-im2col'd fp16 hi/lo planes [n][H][W][16] (inputs that do not come from the fused gather)
+__global__ void __launch_bounds__(256) split_x16_kernel(const float* __restrict__ in, nnal_h* __restrict__ hi,
+                                                         nnal_h* __restrict__ lo, int64_t rows, int W, int C, int KW) {
+  const int64_t total = rows * 16;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / 16;
+    const int j = (int)(e - r * 16);
+    const int dx = j / C, ch = j % C;
+    const int x = (int)(r % W) + dx - KW / 2;
+    const float v = (dx < KW && x >= 0 && x < W) ? in[(r + dx - KW / 2) * C + ch] : 0.f;
+    nnal_h h, l;
+    nnal_split(v, h, l);
+    hi[e] = h;
+    lo[e] = l;
+  }
+}
+}  // namespace ctc
+
+bool nnal_tc_conv_x16_supported(const nnal_ctx*, const Layer& L) {
+  return L.type == NNAL_LAYER_CONV && L.Wx && L.in_h == 25 && L.in_w == 25 && L.in_c == 3 && L.out_c == 24 && L.kh == 5 && L.kw == 5;
+}
+int nnal_tc_prepare_conv_x16(nnal_ctx* ctx, Layer& L) {
+  if (!(L.type == NNAL_LAYER_CONV && L.in_h == 25 && L.in_w == 25 && L.in_c == 3 && L.out_c == 24 && L.kh == 5 && L.kw == 5)) return NNAL_OK;
+  float* Wx = nullptr;
+  const int total = 5 * 16 * 24;
+  CUDA_TRY(ctx, cudaMalloc(&Wx, total * sizeof(float)));
+  ctc::rearrange_x16_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(L.W, Wx, 5, 5, 3, 24);
+  ctx->launches++;
+  int rc = ctc::pack_from<ctc::CfgConv1X>(ctx, Wx, &L.Wx, L.w_scale);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(Wx);
+  return rc;
+}
+int nnal_k_split_x16(nnal_ctx* ctx, const float* in, nnal_h* hi, nnal_h* lo, int64_t rows, int W, int C, int KW) {
+  const int64_t total = rows * 16;
+  if (total == 0) return NNAL_OK;
+  int grid = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256 : (int64_t)ctx->sm_count * 16);
+  ctc::split_x16_kernel<<<grid, 256, 0, ctx->stream>>>(in, hi, lo, rows, W, C, KW);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+// in_hi / in_lo: x-im2col'd planes [n][25][25][16]
+int nnal_tc_conv_x16(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi, nnal_h* out_lo,
+                     int64_t n) {
+  if (n == 0) return NNAL_OK;
+  return ctc::launch<ctc::CfgConv1X>(ctx, L, in_hi, in_lo, out_hi, out_lo, n, L.Wx);
+}
 // conv + the following 2x2/s2 SAME max-pool in one kernel: output planes are [n][ceil(H/2)][ceil(W/2)][Cout]
 bool nnal_tc_conv_pool_supported(const nnal_ctx*, const Layer& L) {
   return L.type == NNAL_LAYER_CONV && L.Wh && ctc::matches<ctc::CfgConv4Pool>(L);

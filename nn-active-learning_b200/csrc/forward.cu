@@ -43,13 +43,29 @@ bool nnal_first_layer_wants_split8(const nnal_ctx* ctx) {
   return L.type == NNAL_LAYER_CONV && L.in_c % 8 != 0 && L.in_c <= 8 && layer_on_tc(ctx, 0);
 }
 
-int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset, bool input_is_split8) {
+// conv1 on the x-im2col'd input (conv_tc.cu CfgConv1X): 3x fewer MMAs (conv1 4.2 -> 3.2 ms per 100k patches), but the
+// gather then writes 40 KB instead of 20 KB per patch (0.84 -> 1.6 ms) and conv1 becomes bound by its 16-byte-row TMA
+// loads and its epilogue: a net 0.3 ms.  Kept behind NNAL_CONV_X16=1 (tests cover it), off by default.
+bool nnal_first_layer_wants_x16(const nnal_ctx* ctx) {
+  if (ctx->layers.empty() || !ctx->use_x16) return false;
+  return layer_on_tc(ctx, 0) && nnal_tc_conv_x16_supported(ctx, ctx->layers[0]);
+}
+
+int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset, int input_format) {
+  const bool input_is_split8 = input_format == 1;
+  bool input_is_x16 = input_format == 2;
   const int nl = (int)ctx->layers.size();
   Act cur;
   cur.f32 = (float*)ctx->xin.p;
   cur.elems = (int64_t)ctx->in_h * ctx->in_w * ctx->in_c;
   if (input_is_split8) {                  // the fused gather already wrote the first conv's 8-channel hi/lo planes
     cur.elems = (int64_t)ctx->in_h * ctx->in_w * 8;
+    cur.hi = (nnal_h*)ctx->xin.p;
+    cur.lo = cur.hi + nb * cur.elems;
+    cur.split = true;
+  }
+  if (input_is_x16) {                     // the fused gather wrote conv1's x-im2col'd hi/lo planes
+    cur.elems = (int64_t)ctx->in_h * ctx->in_w * 16;
     cur.hi = (nnal_h*)ctx->xin.p;
     cur.lo = cur.hi + nb * cur.elems;
     cur.split = true;
@@ -133,6 +149,21 @@ int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset, bool input_is_
     if (L.type == NNAL_LAYER_CONV) {
       const int64_t oe = (int64_t)L.out_h * L.out_w * L.out_c;
       if (layer_on_tc(ctx, i)) {
+        if (i == 0 && !input_is_split8 && !input_is_x16 && nnal_first_layer_wants_x16(ctx)) {
+          // fp32 input (images, unfused gather): x-im2col + split in one pass
+          NNAL_TRY(to_f32(cur));
+          Act o2; next_buf((int64_t)L.in_h * L.in_w * 16, o2);
+          NNAL_TRY(nnal_k_split_x16(ctx, cur.f32, o2.hi, o2.lo, nb * L.in_h * L.in_w, L.in_w, L.in_c, L.kw));
+          o2.split = true; cur = o2;
+          input_is_x16 = true;
+        }
+        if (i == 0 && input_is_x16) {
+          Act o; next_buf(oe, o);
+          NNAL_TRY(nnal_tc_conv_x16(ctx, L, cur.hi, cur.lo, o.hi, o.lo, nb));
+          o.split = true; cur = o;
+          prof_end(ctx);
+          continue;
+        }
         if (i == 0 && input_is_split8) {
           // nothing to do: planes come from the gather
         } else if (L.in_c % 8 != 0) {

@@ -430,6 +430,7 @@ int nnal_tc_prepare_conv(nnal_ctx* ctx, Layer& L);
 int nnal_tc_prepare_layer(nnal_ctx* ctx, Layer& L) {
   if (L.type == NNAL_LAYER_CONV) {
     NNAL_TRY(nnal_tc_prepare_conv(ctx, L));
+    NNAL_TRY(nnal_tc_prepare_conv_x16(ctx, L));
     return nnal_wt_prepare_conv(ctx, L);
   }
   if (L.type != NNAL_LAYER_FC || L.out_dim < 64 || L.in_dim < 64) return NNAL_OK;

@@ -53,6 +53,7 @@ struct Layer {
   nnal_h* Wh = nullptr;
   nnal_h* Wl = nullptr;
   void* Wt = nullptr;                    // conv: weight blocks of the weight-stationary kernel (conv_wt.cu)
+  void* Wx = nullptr;                    // conv1: packed weights of the x-im2col'd form (conv_tc.cu, CfgConv1X)
   int k_pad = 0;                         // padded K of the split planes
   int n_pad = 0;                         // padded N (rows) of the split planes
   float w_scale = 1.f, w_scale_inv = 1.f; // power-of-two scale applied to the fp16 weight planes
@@ -83,6 +84,7 @@ struct nnal_ctx {
   int in_h = 0, in_w = 0, in_c = 0, n_class = 0, feature_layer = -1, feat_dim = 0;
   int fc_first = -1;                     // index of first fc layer
   int use_tc = 1;                        // tensor-core (tcgen05) path for conv/fc where supported
+  int use_x16 = 0;                       // conv1 on x-im2col'd input (3 channels x 5 filter columns folded into 16 channels); NNAL_CONV_X16=1
   int use_wt = 2;                        // conv_wt.cu: 0 never, 1 where it is the faster kernel, 2 (default) + fused max-pool, 3 wherever it covers the layer
   // volumes
   std::vector<Volume> vols;
@@ -208,6 +210,13 @@ int nnal_k_split_flat(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_
 int nnal_k_split_pad(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t rows, int C, int Cp);
 int nnal_k_merge_flat(nnal_ctx*, const nnal_h* hi, const nnal_h* lo, float* out, int64_t count);
 bool nnal_tc_conv_supported(const nnal_ctx*, const Layer&);
+bool nnal_tc_conv_x16_supported(const nnal_ctx*, const Layer&);
+int nnal_tc_prepare_conv_x16(nnal_ctx*, Layer&);
+int nnal_tc_conv_x16(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi, nnal_h* out_lo, int64_t n);
+int nnal_k_split_x16(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t rows, int W, int C, int KW);
+bool nnal_k_gather_x16_supported(const Volume&, int d1, int d2, int d3);
+int nnal_k_gather_x16(nnal_ctx*, const Volume&, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
+                      const double* h_stats, int norm_mode, nnal_h* out_hi, nnal_h* out_lo);
 bool nnal_tc_conv_pool_supported(const nnal_ctx*, const Layer&);
 int nnal_tc_conv_pool(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi, nnal_h* out_lo,
                       int64_t n);
@@ -223,7 +232,9 @@ int nnal_wt_conv(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_
 int nnal_k_conv_simt_split(nnal_ctx*, const Layer&, const float* in, nnal_h* out_hi, nnal_h* out_lo, int64_t n);
 int nnal_k_pool_split(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
                       nnal_h* out_lo, int64_t n);
-int nnal_forward_chunk(nnal_ctx*, int64_t nb, int64_t offset, bool input_is_split8 = false);
+// input_format: 0 fp32 NHWC in xin, 1 fp16 hi/lo planes padded to 8 channels, 2 x-im2col'd fp16 hi/lo planes (16 per position)
+int nnal_forward_chunk(nnal_ctx*, int64_t nb, int64_t offset, int input_format = 0);
 bool nnal_first_layer_wants_split8(const nnal_ctx*);
+bool nnal_first_layer_wants_x16(const nnal_ctx*);
 // fi.cu
 int nnal_k_fi_trace_scores(nnal_ctx*, const float* post, int c, int64_t n, const float* feat, int d, double* score);

@@ -242,12 +242,93 @@ int nnal_k_gather_norm_f32(nnal_ctx* ctx, const Volume& v, const int64_t* d_inds
   return launch_gather<float>(ctx, v, d_inds, n, d1, d2, d3, d_stats, norm_mode, d_out);
 }
 
+// Fused gather -> conv1's x-im2col'd tensor-core input (conv_tc.cu CfgConv1X): fp16 hi/lo planes [n][d1][d2][16] where
+// element dx * C + ch of position (i, k) is the normalised patch value at (i, k + dx - 2, ch) (zero outside the patch,
+// element 15 zero): the 5 filter columns are folded into the channel axis, so conv1 needs 5 K-steps instead of 13.
+// One patch per block iteration: every value is read, normalised (float64, as get_patches_multimg / batch_eval) and
+// split ONCE into shared memory, then each thread assembles the 16-element rows of its positions (64 B per position).
+__global__ void __launch_bounds__(256) gather_x16_kernel(const float* __restrict__ vol, int m, int64_t Xp, int64_t Yp,
+                                                          int64_t Zp, const int64_t* __restrict__ inds, int64_t n, int d1,
+                                                          int d2, NormTab tab, nnal_h* __restrict__ out_hi,
+                                                          nnal_h* __restrict__ out_lo) {
+  extern __shared__ uint32_t sv[];                       // [d1][d2][m] packed (hi | lo << 16)
+  const int C = m, KW = 5;
+  const int npos = d1 * d2, row = d2 * C;
+  const int64_t Y0 = Yp - (d2 - 1), Z0 = Zp;
+  for (int64_t p = blockIdx.x; p < n; p += gridDim.x) {
+    const int64_t ind = inds[p];
+    const int64_t z = ind % Z0;
+    const int64_t t = ind / Z0;
+    const int64_t y = t % Y0;
+    const int64_t x = t / Y0;
+    const float* pbase = vol + ((z * Xp + x) * Yp + y) * m;
+    for (int e = threadIdx.x; e < npos * C; e += blockDim.x) {
+      const int i = e / row, r = e - i * row;            // r = k * C + ch: contiguous in the [Z][X][Y][m] volume
+      const int ch = r % C;
+      double v = (double)pbase[(int64_t)i * Yp * m + r];
+      if (tab.on[ch]) v = norm_apply(v, tab.mu[ch], tab.sg[ch], tab.rs[ch]);
+      nnal_h h, l;
+      nnal_split((float)v, h, l);
+      sv[e] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+    }
+    __syncthreads();
+    for (int pos = threadIdx.x; pos < npos; pos += blockDim.x) {
+      const int i = pos / d2, k = pos - i * d2;
+      uint32_t hw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 15; ++j) {
+        const int dx = j / 3, ch = j - dx * 3;
+        const int kk = k + dx - KW / 2;
+        if (ch < C && kk >= 0 && kk < d2) {
+          const uint32_t w = sv[(i * d2 + kk) * C + ch];
+          hw[j >> 1] |= (w & 0xffffu) << ((j & 1) * 16);
+          lw[j >> 1] |= (w >> 16) << ((j & 1) * 16);
+        }
+      }
+      const int64_t o = (p * npos + pos) * 16;
+      uint4* dh = reinterpret_cast<uint4*>(out_hi + o);
+      uint4* dl = reinterpret_cast<uint4*>(out_lo + o);
+      dh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); dh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+      dl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); dl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+    }
+    __syncthreads();
+  }
+}
+
+bool nnal_k_gather_x16_supported(const Volume& v, int d1, int d2, int d3) {
+  return v.dtype == NNAL_F32 && d3 == 1 && v.m == 3 && d1 == 25 && d2 == 25;
+}
+
 // host copy of the stats ([m][2]) is needed to build the per-output-channel table passed by value
 bool nnal_k_gather_split_supported(const Volume& v, int d3) { return v.dtype == NNAL_F32 && v.m * d3 <= 8; }
+
+static NormTab make_norm_tab(const Volume& v, int d3, const double* h_stats, int norm_mode);
+
+int nnal_k_gather_x16(nnal_ctx* ctx, const Volume& v, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
+                      const double* h_stats, int norm_mode, nnal_h* out_hi, nnal_h* out_lo) {
+  if (n == 0) return NNAL_OK;
+  const NormTab tab = make_norm_tab(v, d3, h_stats, norm_mode);
+  int grid = (int)(n < (int64_t)ctx->sm_count * 16 ? n : (int64_t)ctx->sm_count * 16);
+  gather_x16_kernel<<<grid, 256, (size_t)d1 * d2 * v.m * sizeof(uint32_t), ctx->stream>>>((const float*)v.data, v.m, v.X, v.Y, v.Z, d_inds, n,
+                                                                                          d1, d2, tab, out_hi, out_lo);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
 
 int nnal_k_gather_split(nnal_ctx* ctx, const Volume& v, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
                         const double* h_stats, int norm_mode, nnal_h* out_hi, nnal_h* out_lo) {
   if (n == 0) return NNAL_OK;
+  const NormTab tab = make_norm_tab(v, d3, h_stats, norm_mode);
+  int grid = (int)(n < (int64_t)ctx->sm_count * 32 ? n : (int64_t)ctx->sm_count * 32);
+  gather_split_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)v.data, v.m, v.X, v.Y, v.Z, d_inds, n, d1, d2, d3, tab, out_hi,
+                                                     out_lo);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+static NormTab make_norm_tab(const Volume& v, int d3, const double* h_stats, int norm_mode) {
   NormTab tab;
   const int C = v.m * d3;
   for (int ch = 0; ch < 8; ++ch) {
@@ -264,10 +345,5 @@ int nnal_k_gather_split(nnal_ctx* ctx, const Volume& v, const int64_t* d_inds, i
       tab.rs[ch] = ok ? 1.0 / sg : std::nan("");
     }
   }
-  int grid = (int)(n < (int64_t)ctx->sm_count * 32 ? n : (int64_t)ctx->sm_count * 32);
-  gather_split_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)v.data, v.m, v.X, v.Y, v.Z, d_inds, n, d1, d2, d3, tab, out_hi,
-                                                     out_lo);
-  ctx->launches++;
-  CUDA_TRY(ctx, cudaGetLastError());
-  return NNAL_OK;
+  return tab;
 }

@@ -103,8 +103,8 @@ class Engine(object):
         b = np.ascontiguousarray(b, dtype=np.float32).ravel()
         n, H, Wd, Cin = x.shape
         ks, _, _, Cout = W.shape
-        # use_tc: 0 CUDA cores, 1 tcgen05 (positions on M), 2 weight-stationary tcgen05, 3 = 2 + fused 2x2 max-pool, 4 = 1 + fused pool
-        out = np.empty((n, (H + 1) // 2, (Wd + 1) // 2, Cout) if int(use_tc) >= 3 else (n, H, Wd, Cout), dtype=np.float32)
+        # use_tc: 0 CUDA cores, 1 tcgen05 (positions on M), 2 weight-stationary tcgen05, 3 = 2 + fused 2x2 max-pool, 4 = 1 + fused pool, 5 = conv1 on the x-im2col'd input
+        out = np.empty((n, (H + 1) // 2, (Wd + 1) // 2, Cout) if int(use_tc) in (3, 4) else (n, H, Wd, Cout), dtype=np.float32)
         self._chk(self.lib.nnal_debug_conv(self.h, _ptr(x), _ptr(W), _ptr(b), n, H, Wd, Cin, Cout, ks, int(use_tc),
                                            _ptr(out)))
         return out

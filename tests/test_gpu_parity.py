@@ -269,6 +269,21 @@ def test_conv_weight_stationary_vs_f64(nb, H, Cin, Cout, ks, n):
     assert err < 3e-5, 'weight-stationary conv off by %g (relative to max)' % err
 
 
+@pytest.mark.parametrize('n', [1, 4, 300])
+def test_conv1_x_im2col_vs_f64(nb, n):
+    """PW1 conv1 with the 5 filter columns folded into the channel axis (input x-im2col'd to 16 elements per position,
+    5 x 1 filter over 16 channels: 5 K-steps instead of 13) vs the float64 oracle conv."""
+    H, Cin, Cout, ks = 25, 3, 24, 5
+    rs = np.random.RandomState(100 + n)
+    x = rs.randn(n, H, H, Cin).astype(np.float32)                     # conv1 sees signed (normalised) inputs
+    W = (rs.randn(ks, ks, Cin, Cout) * np.sqrt(2. / (ks * ks * Cin))).astype(np.float32)
+    b = (rs.randn(Cout) * .1).astype(np.float32)
+    ref = np.maximum(O.conv2d_same(x.astype(np.float64), W.astype(np.float64), b.astype(np.float64)), 0)
+    got = nb.get_engine().debug_conv(x, W, b, 5)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 3e-5, 'x-im2col conv1 off by %g (relative to max)' % err
+
+
 @pytest.mark.parametrize('H,Cin,Cout,ks,mode', [(25, 24, 32, 5, 3), (13, 48, 96, 3, 4)])
 @pytest.mark.parametrize('n', [1, 3, 300])
 def test_conv_fused_pool(nb, H, Cin, Cout, ks, mode, n):
@@ -301,6 +316,35 @@ def test_fused_gather_matches_unfused(nb):
     finally:
         del os.environ['NNAL_NO_FUSED_GATHER']
     assert np.array_equal(a, b)
+
+
+def test_x_im2col_gather_path_matches(nb):
+    """NNAL_CONV_X16=1: the gather writes conv1's x-im2col'd planes (16 elements per position) and conv1 runs as a 5 x 1
+    filter over 16 channels.  Same posteriors as the default path within accumulation-order noise, and the fused and
+    unfused (fp32 gather + x-im2col split) variants of it agree bit for bit."""
+    import os
+    ps, imgs, padded, stats, pool, layers, w = _pw_setup(300, 45)
+    model = nb.NN.create_PW1(2)
+    model.set_weights(w)
+    ref = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
+    os.environ['NNAL_CONV_X16'] = '1'
+    try:
+        nb.reset_engine()
+        model2 = nb.NN.create_PW1(2)
+        model2.set_weights(w)
+        a = nb.PW_NN.batch_eval(model2, None, padded, pool, ps, 100, stats, 'posteriors')[0]
+        os.environ['NNAL_NO_FUSED_GATHER'] = '1'
+        try:
+            b = nb.PW_NN.batch_eval(model2, None, padded, pool, ps, 100, stats, 'posteriors')[0]
+        finally:
+            del os.environ['NNAL_NO_FUSED_GATHER']
+    finally:
+        del os.environ['NNAL_CONV_X16']
+        nb.reset_engine()
+    assert np.array_equal(a, b)
+    assert np.abs(a - ref).max() < 2e-5
+    want = O.batch_eval(layers, w, padded, pool, ps, 100, stats, 'posteriors')[0]
+    assert np.abs(a - want).max() < POST_TOL
 
 
 def test_device_gather_and_entropy_map(nb):
