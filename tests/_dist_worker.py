@@ -72,6 +72,35 @@ def run(rank, world, out):
     for s in range(len(Q)):
         res['fi_multi%d' % s] = np.asarray(Q[s])
     res['fi_multi_obj'] = obj
+    # MC-dropout and committee queries (masks keyed by GLOBAL pool position: identical for every world size)
+    mcm = nnal_b200.NN.CNN((5, 5, m), ld, feature_layer=len(layers) - 2, dropout=[[2, 3, 4], 0.6])
+    mcm.set_weights(w)
+    expr.pars['MC_iters'] = 4
+    engine._engine.set_dropout_seed(77, first_pass=3)
+    res['mc_single'] = nnal_b200.PW_NNAL.CNN_query(
+        type('E', (), {'pars': dict(k=9, patch_shape=ps, ntb=16, stats=stats0, MC_iters=4)})(), mcm, None, allp[0][:m], pool0, None,
+        'MC-entropy')
+    for meth, key in (('MC-entropy', 'mc_multi'), ('BALD', 'bald_multi')):
+        engine._engine.set_dropout_seed(77, first_pass=3)
+        Q = nnal_b200.PW_NNAL.query_multimg(expr, mcm, None, allp, pools, None, meth)
+        for s in range(len(Q)):
+            res['%s%d' % (key, s)] = np.asarray(Q[s])
+    engine._engine.set_dropout_seed(77, first_pass=3)
+    res['mc_onepass'] = nnal_b200.PW_NNAL.bin_uncertainty_filter_multimg(expr, mcm, None, allp, pools, 5, {mcm.keep_prob: 0.6})
+    import tempfile
+    holder = nnal_b200.NN.CNN((5, 5, m), ld, feature_layer=len(layers) - 2)
+    paths = []
+    tmpd = tempfile.mkdtemp()
+    for i in range(3):
+        import oracle as O2
+        holder.set_weights(O2.he_init_weights(layers, (5, 5, m), 20 + i, bias_scale=0.1))
+        paths.append(os.path.join(tmpd, 'member%d_rank%d.npz' % (i, rank)))
+        holder.save_weights(paths[-1])
+    expr.model_holder, expr.pretrained_paths = holder, paths
+    for meth, key in (('ensemble', 'ens_multi'), ('QBC-JS', 'qbc_multi')):
+        Q = nnal_b200.PW_NNAL.query_multimg(expr, None, None, allp, pools, [[], [], []], meth)
+        for s in range(len(Q)):
+            res['%s%d' % (key, s)] = np.asarray(Q[s])
     # representativeness queries
     expr.pars['B'] = 30
     Q = nnal_b200.PW_NNAL.query_multimg(expr, model, None, allp, pools, None, 'rep-entropy')

@@ -30,11 +30,60 @@ class FakeEngine(object):
         self._pool_n = int(n)
         self.keep = keep
         self.post = np.zeros((self.n_class, n))
+        if self._mc is not None:
+            self.av_post, self.av_ent = np.zeros(n), np.zeros(n)
         self.feat = None
         self.prev = None
         self.score = None
 
+    # -- MC-dropout / committee (same surface as Engine) ------------------------
+    dropout_seed = 0
+    dropout_pass = 0
+    _mc = None                # (T, keep, layers, pos0, first_pass) while MC mode is on
+
+    def set_dropout_seed(self, seed, first_pass=0):
+        self.dropout_seed = int(seed)
+        self.dropout_pass = int(first_pass)
+
+    def pool_mc_config(self, T, keep_prob, layers, pos0=0):
+        first = self.dropout_pass
+        if T > 0:
+            self._mc = (int(T), float(keep_prob), list(layers), int(pos0), first)
+            self.dropout_pass += int(T)
+        else:
+            self._mc = None
+        return first
+
+    def pool_mc_means(self):
+        return self.av_post.copy(), self.av_ent.copy()
+
+    def pool_ensemble_accumulate(self, t):
+        from oracle import mc_oracle as M
+        p = self.post[1].astype(np.float32).astype(np.float64)
+        if t == 0:
+            self.av_post, self.av_ent = np.zeros(self._pool_n), np.zeros(self._pool_n)
+        self.av_post = (p + t * self.av_post) / (t + 1)
+        self.av_ent = (M.binary_entropy_bumped(p) + t * self.av_ent) / (t + 1)
+
+    def pool_ensemble_end(self):
+        pass
+
+    def _forward_mc(self, x, offset):
+        from oracle import mc_oracle as M
+        T, keep, layers, pos0, first = self._mc
+        n = x.shape[0]
+        pos = pos0 + offset + np.arange(n)
+        passes = [M.forward_dropout(self.layers, self.weights, x, pos, keep, layers, self.dropout_seed, first + t)[0]
+                  .astype(np.float32).astype(np.float64) for t in range(T)]
+        av_p, av_e = M.mc_running_means(passes)
+        self.av_post[offset:offset + n] = av_p
+        self.av_ent[offset:offset + n] = av_e
+        self.post[1, offset:offset + n] = passes[-1]
+        self.post[0, offset:offset + n] = 1 - passes[-1]
+
     def _forward(self, x, offset):
+        if self._mc is not None:
+            return self._forward_mc(x, offset)
         r = O.forward(self.layers, self.weights, x, self.feature_layer, keep_acts=True)
         n = x.shape[0]
         self.post[:, offset:offset + n] = r['posteriors']
@@ -69,7 +118,10 @@ class FakeEngine(object):
 
     def pool_score(self, kind, eps=0.0):
         p = self.post
-        if kind == 0:
+        if kind in (10, 11):
+            from oracle import mc_oracle as M
+            self.score = M.mc_entropy_scores(self.av_post) if kind == 10 else -M.bald_scores(self.av_post, self.av_ent)
+        elif kind == 0:
             self.score = np.abs(p[1] - .5)
         elif kind in (1, 2):
             q = np.where(p == 0, eps, p)

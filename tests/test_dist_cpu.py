@@ -74,6 +74,20 @@ def test_single_process_matches_oracle(runs):
     for s in range(3):
         assert np.array_equal(one['fi_multi%d' % s], Qf[s])
     assert np.allclose(one['fi_multi_obj'], obj, rtol=1e-6)
+    from oracle import mc_oracle as M
+    q, _ = M.query_mc_single(layers, w, allp[0][:m], pool0, ps, stats0, 9, 4, 0.6, [2, 3, 4], 77, first_pass=3)
+    assert np.array_equal(one['mc_single'], q)
+    for meth, key in (('MC-entropy', 'mc_multi'), ('BALD', 'bald_multi')):
+        Qm = M.query_mc_multimg(layers, w, allp, pools, ps, st, 11, 4, 0.6, [2, 3, 4], 77, meth, first_pass=3)[0]
+        for s in range(3):
+            assert np.array_equal(one['%s%d' % (key, s)], Qm[s]), key
+    first = M.query_mc_multimg(layers, w, allp, pools, ps, st, 11, 1, 0.6, [2, 3, 4], 77, 'MC-entropy', first_pass=3)[1]
+    assert np.allclose(one['mc_onepass'], first, atol=1e-6)
+    wsets = [O.he_init_weights(layers, (5, 5, m), 20 + i, bias_scale=0.1) for i in range(3)]
+    for meth, key in (('ensemble', 'ens_multi'), ('QBC-JS', 'qbc_multi')):
+        Qc = M.query_committee_multimg(layers, wsets, allp, pools, ps, 16, st, 11, meth)[0]
+        for s in range(3):
+            assert np.array_equal(one['%s%d' % (key, s)], Qc[s]), key
     Qr, _ = O.query_rep_entropy_multimg(layers, w, allp, pools, ps, 16, st, 11, 30)
     for s in range(3):
         assert np.array_equal(one['rep_multi%d' % s], Qr[s])
