@@ -10,6 +10,6 @@ compute call raises if ``libnnal_b200.so`` is missing or no B200 is present.
 """
 from . import _lib            # noqa: F401
 from .engine import Engine, get_engine, reset_engine      # noqa: F401
-from . import NN, patch_utils, PW_NN, NNAL_tools, PW_NNAL, NNAL, dist, fi, rep   # noqa: F401
+from . import NN, patch_utils, PW_NN, NNAL_tools, PW_NNAL, NNAL, PW_AL, dist, fi, rep   # noqa: F401
 
 __version__ = '0.1.0'
