@@ -403,11 +403,15 @@ def run_fi_round(args, eng, model, padded, stats, pool, lo, hi, d_inds, st, k, p
     def fi_step():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record(stream)
-        eng.pool_begin(n_local, 0)
-        eng.pool_eval_device(0, d_inds.data_ptr(), n_local, 0, PATCH, st)
-        eng.pool_score(L.SCORE_BINARY)
-        idx, sc = eng.pool_topk(B, with_scores=True)
-        sel, _ = dist.allgather_topk(sc, idx + lo, B)
+        if B < len(pool):
+            eng.pool_begin(n_local, 0)
+            eng.pool_eval_device(0, d_inds.data_ptr(), n_local, 0, PATCH, st)
+            eng.pool_score(L.SCORE_BINARY)
+            idx, sc = eng.pool_topk(B, with_scores=True)
+            sel, _ = dist.allgather_topk(sc, idx + lo, B)
+        else:
+            # B >= n: no pre-filter, every pool sample is a candidate (PW_NNAL.py:98-115 keeps all posteriors then)
+            sel = np.arange(len(pool), dtype=np.int64)
         ev[1].record(stream)
         own = (sel >= lo) & (sel < hi)
         mine = sel[own]
