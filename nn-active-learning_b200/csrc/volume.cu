@@ -126,36 +126,39 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const TV* __restrict__
                                                            const int64_t* __restrict__ inds, int64_t n, int d1, int d2,
                                                            int64_t Y0, int64_t Z0, const double* __restrict__ stats,
                                                            TO* __restrict__ out) {
-  __shared__ double s_mu[16], s_sg[16], s_rs[16];
-  if (NORM) {
-    if (threadIdx.x < m) {
-      s_mu[threadIdx.x] = stats[3 * threadIdx.x];
-      s_sg[threadIdx.x] = stats[3 * threadIdx.x + 1];
-      s_rs[threadIdx.x] = stats[3 * threadIdx.x + 2];
-    }
-    __syncthreads();
-  }
+  // Thread t owns column r = t % rowlen of the patch rows i = t / rowlen, + R, + 2R, ... (R = rows covered by the block):
+  // source and destination advance by constants, the channel (r % m) never changes, so the normalisation constants
+  // live in registers and an element costs a load, a store and two pointer increments.  (The first version carried
+  // (row, column, channel) indices through a flat sweep: 42 instructions per element, 71 % issue-slot utilisation
+  // for a copy kernel -- ncu, profiles/r1_config4.json history.)
   const int rowlen = d2 * m;
   const int per_patch = d1 * rowlen;
+  const int R = blockDim.x / rowlen;                     // launch_gather guarantees rowlen <= blockDim.x
+  const int i0 = threadIdx.x / rowlen, r = threadIdx.x - i0 * rowlen;
+  const bool active = i0 < R;
   const int64_t rowstride = Yp * m;
-  const int qi = blockDim.x / rowlen, qr = blockDim.x - qi * rowlen, qc = qr % m;
-  const int i0 = threadIdx.x / rowlen, r0 = threadIdx.x - i0 * rowlen, c0 = r0 % m;
+  double f_mu = 0., f_sg = 1., f_rs = 1.;
+  if (NORM) { const int ch = r % m; f_mu = stats[3 * ch]; f_sg = stats[3 * ch + 1]; f_rs = stats[3 * ch + 2]; }
   for (int64_t p = blockIdx.x; p < n; p += gridDim.x) {
     const int64_t ind = inds[p];
     const int64_t z = ind % Z0;
     const int64_t t = ind / Z0;
     const int64_t y = t % Y0;
     const int64_t x = t / Y0;
-    const TV* base = vol + ((z * Xp + x) * Yp + y) * m;
-    TO* dst = out + p * (int64_t)per_patch;
-    int i = i0, r = r0, ch = c0;
-    for (int e = threadIdx.x; e < per_patch; e += blockDim.x) {
-      const TV raw = base[i * rowstride + r];
-      if (NORM) dst[e] = (TO)norm_apply((double)raw, s_mu[ch], s_sg[ch], s_rs[ch]);
-      else dst[e] = (TO)raw;
-      i += qi; r += qr; ch += qc;
-      if (ch >= m) ch -= m;
-      if (r >= rowlen) { r -= rowlen; ++i; }
+    if (!active) continue;
+    const TV* src = vol + ((z * Xp + x + i0) * Yp + y) * m + r;
+    TO* dst = out + p * (int64_t)per_patch + i0 * rowlen + r;
+    // four independent loads in flight per thread
+#pragma unroll 4
+    for (int i = i0; i < d1; i += R) {
+      const TV raw = *src;
+      // (measured and dropped: skipping the two correction FMAs unless q0 is within a few ulps of a float32 rounding
+      //  midpoint -- 47.7 vs 46.9 ms -- and assembling the float64 bits with integer instructions -- 51.1 ms: the
+      //  kernel is not bound by the float64 pipe)
+      if (NORM) *dst = (TO)norm_apply((double)raw, f_mu, f_sg, f_rs);
+      else *dst = (TO)raw;
+      src += R * rowstride;
+      dst += R * rowlen;
     }
   }
 }
@@ -213,11 +216,12 @@ static int launch_gather(nnal_ctx* ctx, const Volume& v, const int64_t* d_inds, 
     // (norm modes 1 and 2 coincide for d3 == 1: every output channel is one modality)
     const int64_t Y0 = v.Y - (d2 - 1), Z0 = v.Z;
     const bool norm = norm_mode != 0;
+    const int blk = 256;                                   // >= d2 * m (checked above): whole patch rows per sweep
     if (v.dtype == NNAL_F64) {
-      if (norm) gather_rows_kernel<double, TO, true><<<grid, 256, 0, ctx->stream>>>((const double*)v.data, v.m, v.X, v.Y, d_inds, n, d1, d2, Y0, Z0, d_stats, d_out);
+      if (norm) gather_rows_kernel<double, TO, true><<<grid, blk, 0, ctx->stream>>>((const double*)v.data, v.m, v.X, v.Y, d_inds, n, d1, d2, Y0, Z0, d_stats, d_out);
       else gather_rows_kernel<double, TO, false><<<grid, 256, 0, ctx->stream>>>((const double*)v.data, v.m, v.X, v.Y, d_inds, n, d1, d2, Y0, Z0, d_stats, d_out);
     } else {
-      if (norm) gather_rows_kernel<float, TO, true><<<grid, 256, 0, ctx->stream>>>((const float*)v.data, v.m, v.X, v.Y, d_inds, n, d1, d2, Y0, Z0, d_stats, d_out);
+      if (norm) gather_rows_kernel<float, TO, true><<<grid, blk, 0, ctx->stream>>>((const float*)v.data, v.m, v.X, v.Y, d_inds, n, d1, d2, Y0, Z0, d_stats, d_out);
       else gather_rows_kernel<float, TO, false><<<grid, 256, 0, ctx->stream>>>((const float*)v.data, v.m, v.X, v.Y, d_inds, n, d1, d2, Y0, Z0, d_stats, d_out);
     }
   } else if (v.dtype == NNAL_F64)
