@@ -212,6 +212,29 @@ int nnal_fi_step_pack(nnal_ctx* ctx, int64_t step, void* d_msg);
 int nnal_fi_step_apply_gathered(nnal_ctx* ctx, int64_t step, const void* d_msgs, int world, int rank);
 int nnal_fi_result(nnal_ctx* ctx, int64_t k, int64_t* gids_out, double* red_out);
 
+/* ---- the reference's own FI coordinates: shrunk class-score gradients + SDP query distribution ------------------ */
+/* Replaces the 2B single-sample sess.run(model.grad_posts[y]) calls of PW_NNAL.gen_A_matrices (PW_NNAL.py:773-807;
+ * graph built by NN.get_gradients NN.py:621-645, all trainable layers) followed by NNAL_tools.shrink_gradient(grad,'sum')
+ * (NNAL_tools.py:784-796): g_out[y][i][t] = (sum dlog p_y(x_i)/dW_t + sum dlog p_y(x_i)/db_t) / (size W_t + size b_t) for
+ * every class y, sample i and parameterised layer t (creation order; tau of them), float64 [c][n][tau]; post_out (may be
+ * NULL) = posteriors [c][n] float32.  One batched data-gradient backward pass, no parameter gradient is formed.
+ * _images: samples as float32 NHWC [n][in_h][in_w][in_c] on the host (the normalised sel_patches of PW_NNAL.py:121-131);
+ * _voxels: gathered and normalised on the device like nnal_pool_eval. */
+int nnal_fi_shrunk_tau(nnal_ctx* ctx, int* tau);
+int nnal_fi_shrunk_images(nnal_ctx* ctx, const float* x, int64_t n, float* post_out, double* g_out);
+int nnal_fi_shrunk_voxels(nnal_ctx* ctx, int subject, const int64_t* inds, int64_t n, int d1, int d2, int d3,
+                          const double* stats, int norm_mode, float* post_out, double* g_out);
+/* Replaces NNAL_tools.SDP_query_distribution with lambda_ = 0 (NNAL_tools.py:612-659; solve_FIAL_SDP :576-610):
+ * minimise sum_j t_j s.t. [[sum_i q_i A_i, e_j],[e_j^T, t_j]] >= 0, q >= 0, sum q = 1, i.e. tr((sum_i q_i A_i)^-1) over the
+ * simplex.  A: n symmetric positive-definite tau x tau matrices (float64 [n][tau][tau], tau <= 16).  First-order
+ * multiplicative algorithm on the device, q_i <- q_i (d_i/phi)^gamma (gamma in (0,1], 0.5 is monotone), stopped at the
+ * duality certificate max_i tr(M^-1 A_i M^-1) / tr(M^-1) - 1 <= tol or after max_iter iterations.  q_out [n];
+ * t_out [tau] = diag((sum q_i A_i)^-1) (the SDP's t); *obj_out = sum_j t_j; *gap_out = the certificate of the returned q
+ * (objective within gap, relative, of the optimum); any of t_out/obj_out/gap_out/iters_out may be NULL. */
+int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64_t n, int tau, double tol, int64_t max_iter,
+                                double gamma, double* q_out, double* t_out, double* obj_out, double* gap_out,
+                                int64_t* iters_out);
+
 /* ---- representativeness queries over the feature layer ------------------------------- */
 /* Rows = the samples of the current pool pass (nnal_pool_begin keep >= 1; feature width multiple of 8).
  * 'rep-entropy' (NNAL.py:466-523, PW_NNAL.py:284-351): cols [B][d] = feature rows of the B most uncertain samples

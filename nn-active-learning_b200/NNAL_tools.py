@@ -36,6 +36,23 @@ def shrink_gradient(grad, method, args=None):
     return np.ravel(shrunk)
 
 
+def SDP_query_distribution(A, lambda_, X_pool, k, tol=1e-4, max_iter=200000):
+    """NNAL_tools.SDP_query_distribution (NNAL_tools.py:612-659) for ``lambda_ == 0``: the query distribution
+    minimising ``tr((sum_i q_i A_i)^-1)`` over the simplex.  ``A`` is the list of tau x tau conditional FIs of
+    ``gen_A_matrices``.  Returns a dict shaped like cvxopt's ``solvers.sdp`` solution: ``soln['x']`` =
+    ``[q_1..q_n, t_1..t_tau]`` (callers slice ``soln['x'][:n]``, PW_NNAL.py:157), ``soln['status']`` = 'optimal' when
+    the duality certificate ``max_i tr(M^-1 A_i M^-1)/tr(M^-1) - 1`` of the returned q is below ``tol`` (so the
+    objective is within ``tol`` of the SDP optimum), else 'unknown'; plus 'primal objective', 'gap', 'iterations'.
+    The regularised variant (``lambda_ > 0``: ``-lambda sum q_i |f_i|^2`` with ``F q = 0``, :625-644) is not
+    part of the replaced path."""
+    if lambda_ > 0:
+        raise NotImplementedError('lambda_ > 0 (feature-regularised SDP, NNAL_tools.py:625-644) stays in the reference')
+    A = np.asarray(A, dtype=np.float64)
+    r = get_engine().sdp_query_distribution(A, tol=tol, max_iter=max_iter)
+    return {'x': np.concatenate([r['q'], r['t']]), 'status': 'optimal' if r['gap'] <= 2 * tol else 'unknown',
+            'primal objective': r['objective'], 'gap': r['gap'], 'iterations': r['iterations']}
+
+
 def sample_query_dstr(q_dstr, k, replacement=True):
     """NNAL_tools.sample_query_dstr, replacement=True branch (NNAL_tools.py:844-872)."""
     if q_dstr.min() < -.01:

@@ -49,7 +49,9 @@ def CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, method_name):
     ``entropy``: k pool samples with the smallest |P(class 1) - 0.5| (:51-65), ascending.
     ``fi``: uncertainty pre-filter to B (:98-115), conditional FI of the last FC layers in
     factored form, deterministic greedy selection of k instead of the
-    reference's SDP + random sampling (:146-163); returns ``sel_inds[Q]``."""
+    reference's SDP + random sampling (:146-163); returns ``sel_inds[Q]``.
+    ``expr.pars['fi_mode'] = 'sdp'`` runs the reference's own pipeline instead: shrunk-coordinate
+    A-matrices (:133-137), SDP query distribution (:154-157), ``sample_query_dstr`` (:160-163)."""
     if method_name == 'random':
         n = len(pool_inds)
         return np.random.permutation(n)[:expr.pars['k']]
@@ -74,9 +76,40 @@ def CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, method_name):
 
     if method_name == 'fi':
         from . import fi
+        if expr.pars.get('fi_mode', 'greedy') == 'sdp':
+            return fi.query_single_sdp(expr, model, sess, padded_imgs, pool_inds)
         return fi.query_single(expr, model, sess, padded_imgs, pool_inds)
 
     raise NotImplementedError('query method %r is not part of the replaced path' % method_name)
+
+
+def _A_from_shrunk(g, sel_posts, diag_load):
+    """The A-matrix assembly of PW_NNAL.gen_A_matrices (PW_NNAL.py:766-814) from shrunk gradients ``g`` [2,B,tau]:
+    p < 1e-6 -> p = 0 and only g0 (:770-780), p > 1-1e-6 -> p = 1 and only g1 (:782-793),
+    ``A_i = (1-p) g0 g0^T + p g1 g1^T + diag_load I`` (:810-814).  Vectorised over the B samples with the
+    reference's order of operations (bit-identical to the per-sample loop)."""
+    tau = g.shape[2]
+    p = np.array(sel_posts, dtype=np.float64)
+    lo, hi = p < 1e-6, p > 1 - 1e-6
+    p[lo], p[hi] = 0., 1.
+    g0 = np.where(hi[:, None], 0., g[0])
+    g1 = np.where(lo[:, None], 0., g[1])
+    A = (1. - p)[:, None, None] * (g0[:, :, None] * g0[:, None, :]) + p[:, None, None] * (g1[:, :, None] * g1[:, None, :])
+    A = A + np.eye(tau) * diag_load
+    return list(A)
+
+
+def gen_A_matrices(expr, model, sess, sel_patches, sel_posts, diag_load=1e-5):
+    """PW_NNAL.gen_A_matrices (PW_NNAL.py:738-816): conditional FIs of the (already normalised) ``sel_patches``
+    [B,d1,d2,m*d3] in the reference's shrunk coordinates, ``A_i = (1-p) g0 g0^T + p g1 g1^T + diag_load I`` with
+    ``g_y = shrink_gradient(d log p_y / d theta, 'sum')`` over all trainable layers.  The 2B single-sample
+    ``sess.run(model.grad_posts[y])`` calls are one batched backward pass on the device (csrc/shrunk.cu)."""
+    eng = get_engine()
+    eng.set_model(model, sess)
+    if eng.n_class != 2:
+        raise NotImplementedError('gen_A_matrices assumes binary classification (PW_NNAL.py:765)')
+    _, g = eng.fi_shrunk_images(np.asarray(sel_patches))
+    return _A_from_shrunk(g, np.asarray(sel_posts, dtype=np.float64), diag_load)
 
 
 def _pool_pass_multimg(expr, model, sess, all_padded_imgs, pool_inds, keep=0, mc=None):
@@ -203,6 +236,8 @@ def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, labeled_inds, m
 
     if method_name == 'fi':
         from . import fi
+        if expr.pars.get('fi_mode', 'greedy') == 'sdp':
+            return fi.query_multimg_sdp(expr, model, sess, all_padded_imgs, pool_inds)
         return fi.query_multimg(expr, model, sess, all_padded_imgs, pool_inds)
 
     if method_name == 'rep-entropy':

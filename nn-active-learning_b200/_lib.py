@@ -85,6 +85,12 @@ SIGNATURES = {
     'nnal_fi_step_apply_gathered': (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int, C.c_int]),
     'nnal_fi_result': (C.c_int, [c_vp, C.c_int64, c_vp, c_vp]),
     'nnal_fi_step_apply': (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int64, C.c_int, C.c_int64]),
+    'nnal_fi_shrunk_tau': (C.c_int, [c_vp, C.POINTER(C.c_int)]),
+    'nnal_fi_shrunk_images': (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),
+    'nnal_fi_shrunk_voxels': (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp,
+                                        c_vp]),
+    'nnal_sdp_query_distribution': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, C.c_double, C.c_int64, C.c_double, c_vp,
+                                              c_vp, c_f64p, c_f64p, c_i64p]),
 }
 
 NNAL_OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, 1, 2, 3, 4, 5

@@ -84,6 +84,8 @@ extern "C" int nnal_ctx_destroy(nnal_ctx* ctx) {
   free_pool(ctx);
   nnal_fi_release(ctx);
   nnal_sims_release(ctx);
+  nnal_bw_release(ctx);
+  nnal_sdp_release(ctx);
   nnal_tc_release(ctx);
   free_buf(ctx->stage); free_buf(ctx->inds); free_buf(ctx->act[0]); free_buf(ctx->act[1]); free_buf(ctx->xin);
   free_buf(ctx->featbuf); free_buf(ctx->prevbuf); free_buf(ctx->logits); free_buf(ctx->splitA[0]); free_buf(ctx->splitA[1]);
@@ -309,6 +311,13 @@ static int upload_stats(nnal_ctx* ctx, const double* stats, int m, int norm_mode
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->logits.p, ctx->stats_host.data(), (size_t)m * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   *d_stats = (double*)ctx->logits.p;
   return NNAL_OK;
+}
+
+int nnal_upload_stats(nnal_ctx* ctx, const double* stats, int m, int norm_mode, double** d_stats) {
+  return upload_stats(ctx, stats, m, norm_mode, d_stats);
+}
+int nnal_check_gather_args(nnal_ctx* ctx, int subject, int64_t n, int d1, int d2, int d3, const Volume** vout) {
+  return check_gather_args(ctx, subject, n, d1, d2, d3, vout);
 }
 
 extern "C" int nnal_gather(nnal_ctx* ctx, int subject, const int64_t* inds, int64_t n, int d1, int d2, int d3,

@@ -113,6 +113,8 @@ struct nnal_ctx {
   void* tc_state = nullptr;              // tensor-map cache etc. (gemm_tc.cu)
   void* sims_state = nullptr;            // representativeness queries (sims.cu)
   void* fi_state = nullptr;              // Fisher-information candidate set / greedy state (fi.cu)
+  void* bw_state = nullptr;              // shrunk class-score gradients: kept activations and gradient buffers (shrunk.cu)
+  void* sdp_state = nullptr;             // query-distribution solver workspaces (sdp.cu)
   // MC-dropout (MC-entropy / BALD): T stochastic passes of the FC tail per chunk, running means per pool sample
   int mc_T = 0;                          // 0: deterministic forward
   int mc_have = 0;                       // the current pool pass ran in MC mode: running means are valid
@@ -236,5 +238,10 @@ int nnal_k_pool_split(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h
 int nnal_forward_chunk(nnal_ctx*, int64_t nb, int64_t offset, int input_format = 0);
 bool nnal_first_layer_wants_split8(const nnal_ctx*);
 bool nnal_first_layer_wants_x16(const nnal_ctx*);
+// shrunk.cu / sdp.cu
+int nnal_bw_release(nnal_ctx*);
+int nnal_sdp_release(nnal_ctx*);
+int nnal_upload_stats(nnal_ctx*, const double* stats, int m, int norm_mode, double** d_stats);
+int nnal_check_gather_args(nnal_ctx*, int subject, int64_t n, int d1, int d2, int d3, const Volume** vout);
 // fi.cu
 int nnal_k_fi_trace_scores(nnal_ctx*, const float* post, int c, int64_t n, const float* feat, int d, double* score);

@@ -1,0 +1,279 @@
+// Query distribution of the reference's FI query.
+//
+// NNAL_tools.SDP_query_distribution (NNAL_tools.py:612-659, constraints built by inequality_cvx_matrix :661-720; the cvxpy
+// twin solve_FIAL_SDP :576-610) hands cvxopt the SDP
+//     minimise sum_j t_j   s.t.  [[sum_i q_i A_i, e_j], [e_j^T, t_j]] >= 0 for all j,   q >= 0,  sum_i q_i = 1
+// whose Schur complements make t_j = ((sum_i q_i A_i)^-1)_jj at the optimum: it minimises phi(q) = tr(M(q)^-1),
+// M(q) = sum_i q_i A_i, over the simplex (A-optimal design).  tau is 7 for PW1, n = B is thousands: an interior-point
+// method factors an n x n positivity block per iteration, while phi's gradient needs only the tau x tau inverse:
+//     d_i = -d phi / d q_i = tr(M^-1 A_i M^-1) = <M^-2, A_i>,      sum_i q_i d_i = phi.
+// Solved here on the device by the multiplicative algorithm for A-optimality  q_i <- q_i (d_i / phi)^gamma / Z
+// (gamma = 1/2 decreases phi monotonically for positive semi-definite A_i).  Convexity gives the certificate
+//     phi(q) - phi* <= max_i d_i - phi(q),
+// so the loop stops when max_i d_i / phi - 1 <= tol: the objective is then within tol (relative) of the SDP optimum.
+// One kernel per iteration; every CTA rebuilds M from the previous iteration's per-CTA partial sums (fixed order:
+// deterministic), inverts it in shared memory, updates its samples and writes the next partial sums.  All float64.
+#include "nnal_common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int SDP_MAX_TAU = 16;
+constexpr int SDP_T2 = SDP_MAX_TAU * SDP_MAX_TAU;
+constexpr int SDP_THREADS = 256;
+constexpr int SDP_MAX_GRID = 128;
+
+struct SdpState {
+  DevBuf At, stage, qu, part[2], out;
+};
+
+SdpState* sdp_state(nnal_ctx* ctx) {
+  if (!ctx->sdp_state) ctx->sdp_state = new SdpState();
+  return (SdpState*)ctx->sdp_state;
+}
+
+// layout of one set of per-CTA partial sums: [G][T2] sums of q_i A_i, then [G] sums of q_i, then [G] max_i d_i / phi
+struct Parts {
+  double* M;
+  double* Z;
+  double* R;
+};
+__host__ __device__ inline Parts parts_of(double* base, int G, int T2) {
+  Parts p;
+  p.M = base;
+  p.Z = base + (size_t)G * T2;
+  p.R = p.Z + G;
+  return p;
+}
+
+__global__ void sdp_transpose_kernel(const double* __restrict__ A, double* __restrict__ At, int64_t n, int T2) {
+  const int64_t total = n * T2;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / T2;
+    const int ab = (int)(e - i * T2);
+    At[(int64_t)ab * n + i] = A[e];
+  }
+}
+
+__global__ void sdp_fill_kernel(double* __restrict__ q, int64_t n, double v) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) q[e] = v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// M = (sum of the partial sums) / Z; in-place Gauss-Jordan inverse (M is positive definite: no pivoting); P = Minv^2.
+// All threads of the CTA call this; returns phi = tr(Minv) and Z to every thread.
+__device__ void sdp_build(const Parts in, int G, int tau, double* s_M, double* s_P, double& phi, double& Z) {
+  const int T2 = tau * tau, tid = threadIdx.x;
+  double z = 0.0;
+  for (int g = 0; g < G; ++g) z += in.Z[g];
+  Z = z;
+  if (tid < T2) {
+    double m = 0.0;
+    for (int g = 0; g < G; ++g) m += in.M[(size_t)g * T2 + tid];
+    s_M[tid] = m / z;
+  }
+  __syncthreads();
+  const int a = tid / tau, b = tid % tau;
+  for (int k = 0; k < tau; ++k) {
+    double v = 0.0;
+    if (tid < T2) {
+      const double piv = 1.0 / s_M[k * tau + k];
+      if (a == k && b == k) v = piv;
+      else if (a == k) v = s_M[k * tau + b] * piv;
+      else if (b == k) v = -s_M[a * tau + k] * piv;
+      else v = s_M[a * tau + b] - s_M[a * tau + k] * s_M[k * tau + b] * piv;
+    }
+    __syncthreads();
+    if (tid < T2) s_M[tid] = v;
+    __syncthreads();
+  }
+  if (tid < T2) {
+    double v = 0.0;
+    for (int k = 0; k < tau; ++k) v += s_M[a * tau + k] * s_M[k * tau + b];
+    s_P[tid] = v;
+  }
+  __syncthreads();
+  double t = 0.0;
+  for (int k = 0; k < tau; ++k) t += s_M[k * tau + k];
+  phi = t;
+}
+
+// per-CTA partial sums of q_i A_i, q_i and the CTA's largest ratio
+__device__ void sdp_accumulate(const double* __restrict__ At, const double* __restrict__ qu, int64_t n, int T2, double rmax,
+                               Parts out, double (*s_w)[SDP_T2], double* s_r) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, j0 = (int64_t)blockIdx.x * blockDim.x + tid;
+  for (int ab = 0; ab < T2; ++ab) {
+    double v = 0.0;
+    for (int64_t j = j0; j < n; j += stride) v += qu[j] * At[(int64_t)ab * n + j];
+    v = warp_sum(v);
+    if (lane == 0) s_w[w][ab] = v;
+  }
+  double z = 0.0;
+  for (int64_t j = j0; j < n; j += stride) z += qu[j];
+  z = warp_sum(z);
+  rmax = warp_max(rmax);
+  if (lane == 0) { s_r[w] = z; s_r[8 + w] = rmax; }
+  __syncthreads();
+  if (tid < T2) {
+    double v = 0.0;
+    for (int k = 0; k < SDP_THREADS / 32; ++k) v += s_w[k][tid];
+    out.M[(size_t)blockIdx.x * T2 + tid] = v;
+  }
+  if (tid == 0) {
+    double zz = 0.0, rr = 0.0;
+    for (int k = 0; k < SDP_THREADS / 32; ++k) { zz += s_r[k]; rr = fmax(rr, s_r[8 + k]); }
+    out.Z[blockIdx.x] = zz;
+    out.R[blockIdx.x] = rr;
+  }
+}
+
+__global__ void __launch_bounds__(SDP_THREADS) sdp_init_kernel(const double* __restrict__ At, const double* __restrict__ qu,
+                                                                int64_t n, int tau, double* part_out) {
+  __shared__ double s_w[SDP_THREADS / 32][SDP_T2];
+  __shared__ double s_r[16];
+  sdp_accumulate(At, qu, n, tau * tau, 0.0, parts_of(part_out, gridDim.x, tau * tau), s_w, s_r);
+}
+
+__global__ void __launch_bounds__(SDP_THREADS) sdp_iter_kernel(const double* __restrict__ At, double* __restrict__ qu,
+                                                                int64_t n, int tau, double gamma, double* part_in,
+                                                                double* part_out, double* __restrict__ hist) {
+  __shared__ double s_M[SDP_T2], s_P[SDP_T2];
+  __shared__ double s_w[SDP_THREADS / 32][SDP_T2];
+  __shared__ double s_r[16];
+  const int T2 = tau * tau, G = gridDim.x;
+  const Parts in = parts_of(part_in, G, T2);
+  double phi, Z;
+  sdp_build(in, G, tau, s_M, s_P, phi, Z);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double r = 0.0;
+    for (int g = 0; g < G; ++g) r = fmax(r, in.R[g]);
+    hist[0] = phi;            // phi(q_it)
+    hist[1] = r;              // max_i d_i / phi of the PREVIOUS iterate (0 before the first update)
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double rmax = 0.0;
+  const double inv_phi = 1.0 / phi, inv_Z = 1.0 / Z;
+  for (int64_t j = j0; j < n; j += stride) {
+    double d = 0.0;
+    for (int ab = 0; ab < T2; ++ab) d += s_P[ab] * At[(int64_t)ab * n + j];
+    const double r = d * inv_phi;
+    const double q = qu[j] * inv_Z;
+    rmax = fmax(rmax, r);          // over ALL i: the optimality condition also binds where q_i has underflowed to 0
+    qu[j] = q * (gamma == 0.5 ? sqrt(r) : pow(r, gamma));
+  }
+  sdp_accumulate(At, qu, n, T2, rmax, parts_of(part_out, G, T2), s_w, s_r);
+}
+
+// single CTA: normalised q, t_j = (M^-1)_jj, phi and the certificate max_i d_i / phi - 1 of the RETURNED q
+__global__ void __launch_bounds__(SDP_THREADS) sdp_final_kernel(const double* __restrict__ At, const double* __restrict__ qu,
+                                                                 int64_t n, int tau, int G, double* part_in,
+                                                                 double* __restrict__ q_out, double* __restrict__ res) {
+  __shared__ double s_M[SDP_T2], s_P[SDP_T2];
+  __shared__ double s_r[8];
+  const int T2 = tau * tau;
+  double phi, Z;
+  sdp_build(parts_of(part_in, G, T2), G, tau, s_M, s_P, phi, Z);
+  double rmax = 0.0;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+    double d = 0.0;
+    for (int ab = 0; ab < T2; ++ab) d += s_P[ab] * At[(int64_t)ab * n + j];
+    rmax = fmax(rmax, d / phi);           // over ALL i: the optimality condition also binds where q_i = 0
+    q_out[j] = qu[j] / Z;
+  }
+  rmax = warp_max(rmax);
+  if ((threadIdx.x & 31) == 0) s_r[threadIdx.x >> 5] = rmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+    for (int k = 0; k < SDP_THREADS / 32; ++k) r = fmax(r, s_r[k]);
+    res[0] = phi;
+    res[1] = r - 1.0;
+  }
+  if (threadIdx.x < tau) res[2 + threadIdx.x] = s_M[threadIdx.x * tau + threadIdx.x];
+}
+
+}  // namespace
+
+int nnal_sdp_release(nnal_ctx* ctx) {
+  if (!ctx->sdp_state) return NNAL_OK;
+  SdpState* st = (SdpState*)ctx->sdp_state;
+  DevBuf* bufs[] = {&st->At, &st->stage, &st->qu, &st->part[0], &st->part[1], &st->out};
+  for (DevBuf* b : bufs) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+  delete st;
+  ctx->sdp_state = nullptr;
+  return NNAL_OK;
+}
+
+extern "C" int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64_t n, int tau, double tol, int64_t max_iter,
+                                           double gamma, double* q_out, double* t_out, double* obj_out, double* gap_out,
+                                           int64_t* iters_out) {
+  if (!ctx || !A || !q_out || n <= 0 || tau <= 0) return NNAL_ERR_INVALID;
+  if (tau > SDP_MAX_TAU) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "SDP: more than 16 shrunk coordinates");
+  if (!(gamma > 0.0 && gamma <= 1.0)) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "SDP: gamma must be in (0, 1]");
+  if (!(tol > 0.0)) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "SDP: tol must be positive");
+  if (max_iter < 1) max_iter = 1;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  SdpState* st = sdp_state(ctx);
+  const int T2 = tau * tau;
+  const int G = (int)std::min<int64_t>((n + SDP_THREADS - 1) / SDP_THREADS, SDP_MAX_GRID);
+  const size_t part_doubles = (size_t)G * T2 + 2 * (size_t)G;
+  NNAL_TRY(devbuf_reserve(ctx, st->stage, (size_t)n * T2 * 8));
+  NNAL_TRY(devbuf_reserve(ctx, st->At, (size_t)n * T2 * 8));
+  NNAL_TRY(devbuf_reserve(ctx, st->qu, (size_t)n * 8 * 2));           // unnormalised weights, then the normalised result
+  NNAL_TRY(devbuf_reserve(ctx, st->part[0], part_doubles * 8));
+  NNAL_TRY(devbuf_reserve(ctx, st->part[1], part_doubles * 8));
+  NNAL_TRY(devbuf_reserve(ctx, st->out, (size_t)(4 + SDP_MAX_TAU) * 8));
+  double* At = (double*)st->At.p;
+  double* qu = (double*)st->qu.p;
+  double* qn = qu + n;
+  double* hist = (double*)st->out.p;         // [0..1] per-iteration record, [2..] result of the final kernel
+  double* res = hist + 2;
+  CUDA_TRY(ctx, cudaMemcpyAsync(st->stage.p, A, (size_t)n * T2 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const int tg = (int)std::min<int64_t>((n * T2 + 255) / 256, (int64_t)ctx->sm_count * 8);
+  sdp_transpose_kernel<<<tg, 256, 0, ctx->stream>>>((const double*)st->stage.p, At, n, T2);
+  sdp_fill_kernel<<<G, 256, 0, ctx->stream>>>(qu, n, 1.0);
+  int cur = 0;
+  sdp_init_kernel<<<G, SDP_THREADS, 0, ctx->stream>>>(At, qu, n, tau, (double*)st->part[cur].p);
+  ctx->launches += 3;
+  CUDA_TRY(ctx, cudaGetLastError());
+  const int64_t check_every = 32;
+  int64_t it = 0;
+  while (it < max_iter) {
+    const int64_t stop = std::min(max_iter, it + check_every);
+    for (; it < stop; ++it) {
+      sdp_iter_kernel<<<G, SDP_THREADS, 0, ctx->stream>>>(At, qu, n, tau, gamma, (double*)st->part[cur].p,
+                                                          (double*)st->part[cur ^ 1].p, hist);
+      cur ^= 1;
+      ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    double h[2];
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, hist, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!(h[0] == h[0]) || h[0] <= 0.0) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "SDP: sum_i q_i A_i is not positive definite");
+    if (it > 1 && h[1] - 1.0 <= tol) break;
+  }
+  sdp_final_kernel<<<1, SDP_THREADS, 0, ctx->stream>>>(At, qu, n, tau, G, (double*)st->part[cur].p, qn, res);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  double hres[2 + SDP_MAX_TAU];
+  CUDA_TRY(ctx, cudaMemcpyAsync(hres, res, sizeof(hres), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(q_out, qn, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (obj_out) *obj_out = hres[0];
+  if (gap_out) *gap_out = hres[1];
+  if (t_out) for (int j = 0; j < tau; ++j) t_out[j] = hres[2 + j];
+  if (iters_out) *iters_out = it;
+  return NNAL_OK;
+}

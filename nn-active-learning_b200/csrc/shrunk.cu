@@ -1,0 +1,543 @@
+// Shrunk class-score gradients (the reference's FI coordinates).
+//
+// The reference's `fi` query calls, for each of the B pre-filtered samples and each class y, sess.run(model.grad_posts[y])
+// = tf.gradients(log posteriors[y,0], all trainable variables) (NN.get_gradients NN.py:621-645, PW_NNAL.gen_A_matrices
+// PW_NNAL.py:773-807) -- 2B single-sample backprops over 36 M parameters -- and then keeps ONE number per parameterised
+// layer: NNAL_tools.shrink_gradient(grad,'sum') = (sum gW_t + sum gb_t) / (size W_t + size b_t) (NNAL_tools.py:784-796).
+// The per-layer sums factor through the pre-activation gradients dz_t, so no parameter gradient is ever formed:
+//   fc   : sum gW = (sum_o dz_o)(sum_i a_i),            sum gb = sum_o dz_o
+//   conv : sum gW = sum_p (sum_co dz[p,co]) box[p],     sum gb = sum_p sum_co dz[p,co],
+//          box[p] = sum over the kh x kw window at p of sum_ci x_padded[.,ci]
+// What remains is a batched DATA-gradient backward pass: fp32 forward keeping every activation, then dz walks back
+// through fc (dz W), ReLU masks, max-pool (gradient to the first maximum of each window, as tf.nn.max_pool's gradient)
+// and conv (correlation of dz with the flipped filter).  For the binary model both class gradients are multiples of one
+// pass, d log p_0 = p_1 h, d log p_1 = -p_0 h with h = d(z_0 - z_1), and shrink_gradient is linear, so one pass serves both.
+#include "nnal_common.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+bool nnal_layer_on_tc(const nnal_ctx* ctx, int i);
+
+namespace {
+
+struct BwState {
+  DevBuf acts, g[2], post, gout, sred;
+};
+
+BwState* bw_state(nnal_ctx* ctx) {
+  if (!ctx->bw_state) ctx->bw_state = new BwState();
+  return (BwState*)ctx->bw_state;
+}
+
+int64_t bw_chunk() {
+  const char* e = getenv("NNAL_BW_CHUNK");
+  if (e) { long v = atol(e); if (v > 0) return v; }
+  return 2048;
+}
+
+inline int grid_for(const nnal_ctx* ctx, int64_t total, int per_sm) {
+  int64_t b = (total + 255) / 256, cap = (int64_t)ctx->sm_count * per_sm;
+  return (int)std::max<int64_t>(1, std::min(b, cap));
+}
+
+// ---- dz at the logits: e_y - pi (tf.gradients of log softmax), or h = e_0 - e_1 for the binary single pass ----------
+__global__ void dlogits_kernel(const float* __restrict__ post, float* __restrict__ dz, int64_t n, int c, int y) {
+  const int64_t total = n * c;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = e / c;
+    const int j = (int)(e - s * c);
+    dz[e] = y < 0 ? (j == 0 ? 1.f : -1.f) : ((j == y ? 1.f : 0.f) - post[(int64_t)j * n + s]);
+  }
+}
+
+// ---- ReLU: dz = d where the layer's output is positive (tf.nn.relu's gradient) -------------------------------------
+__global__ void relu_mask_kernel(float* __restrict__ d, const float* __restrict__ a, int64_t count) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
+    if (!(a[e] > 0.f)) d[e] = 0.f;
+}
+
+// ---- max-pool SAME, window == stride: every input cell asks whether it is the FIRST maximum of its window ----------
+__global__ void pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ in, float* __restrict__ d_in,
+                                int64_t total_in, int H, int Wd, int C, int Ho, int Wo, int s) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total_in; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    int64_t t = e / C;
+    const int x = (int)(t % Wd); t /= Wd;
+    const int y = (int)(t % H);
+    const int64_t smp = t / H;
+    const int yo = y / s, xo = x / s;
+    float m = -INFINITY;
+    int wy = -1, wx = -1;
+    for (int dy = 0; dy < s; ++dy) {
+      const int y2 = yo * s + dy;
+      if (y2 >= H) break;
+      for (int dx = 0; dx < s; ++dx) {
+        const int x2 = xo * s + dx;
+        if (x2 >= Wd) break;
+        const float v = in[((smp * H + y2) * Wd + x2) * (int64_t)C + c];
+        if (v > m) { m = v; wy = y2; wx = x2; }
+      }
+    }
+    d_in[e] = (wy == y && wx == x) ? d_out[((smp * Ho + yo) * Wo + xo) * (int64_t)C + c] : 0.f;
+  }
+}
+
+// ---- conv data gradient: d_in[y][x][ci] = sum_{dy,dx,co} dz[y-dy+ph][x-dx+pw][co] W[dy][dx][ci][co] ------------------
+// One CTA per sample; dz is staged zero-padded in shared memory so that the flipped tap (dy',dx') = (kh-1-dy, kw-1-dx)
+// reads padded position (y+dy', x+dx').  A thread owns TC input channels x TP positions and walks co four at a time.
+template <int TP, int TC>
+__global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restrict__ dz, const float* __restrict__ Wt,
+                                                             float* __restrict__ d_in, int64_t n, int H, int Wd, int Cin,
+                                                             int Cout, int kh, int kw) {
+  extern __shared__ float s_dz[];
+  const int Hp = H + kh - 1, Wp = Wd + kw - 1;
+  const int ph = kh / 2, pw = kw / 2;
+  const int ci_groups = (Cin + TC - 1) / TC;
+  const int PG = blockDim.x / ci_groups;
+  const int tid = threadIdx.x;
+  const int cg = tid % ci_groups, pg = tid / ci_groups;
+  const bool active = pg < PG;
+  const int ci0 = cg * TC;
+  const int HW = H * Wd;
+  const bool vec = (Cout % 4) == 0;
+  for (int64_t s = blockIdx.x; s < n; s += gridDim.x) {
+    const float* src = dz + s * (int64_t)HW * Cout;
+    for (int e = tid; e < Hp * Wp * Cout; e += blockDim.x) {
+      const int co = e % Cout;
+      const int t = e / Cout;
+      const int xx = t % Wp - pw, yy = t / Wp - ph;
+      s_dz[e] = (xx >= 0 && xx < Wd && yy >= 0 && yy < H) ? src[((int64_t)yy * Wd + xx) * Cout + co] : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      for (int p0 = 0; p0 < HW; p0 += PG * TP) {
+        float acc[TP][TC];
+        int off[TP];
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+          const int p = p0 + pg + t * PG;
+          const int pc = p < HW ? p : 0;
+          off[t] = ((pc / Wd) * Wp + (pc % Wd)) * Cout;
+#pragma unroll
+          for (int c = 0; c < TC; ++c) acc[t][c] = 0.f;
+        }
+        for (int fy = 0; fy < kh; ++fy)
+          for (int fx = 0; fx < kw; ++fx) {
+            const int toff = (fy * Wp + fx) * Cout;
+            const int tap = (kh - 1 - fy) * kw + (kw - 1 - fx);
+            const float* wtap = Wt + (int64_t)tap * Cin * Cout;
+            if (vec) {
+              for (int co = 0; co < Cout; co += 4) {
+                float4 w[TC];
+#pragma unroll
+                for (int c = 0; c < TC; ++c)
+                  w[c] = (ci0 + c < Cin) ? __ldg(reinterpret_cast<const float4*>(wtap + (int64_t)(ci0 + c) * Cout + co))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < TP; ++t) {
+                  const float4 a = *reinterpret_cast<const float4*>(&s_dz[off[t] + toff + co]);
+#pragma unroll
+                  for (int c = 0; c < TC; ++c) {
+                    acc[t][c] = fmaf(a.x, w[c].x, acc[t][c]);
+                    acc[t][c] = fmaf(a.y, w[c].y, acc[t][c]);
+                    acc[t][c] = fmaf(a.z, w[c].z, acc[t][c]);
+                    acc[t][c] = fmaf(a.w, w[c].w, acc[t][c]);
+                  }
+                }
+              }
+            } else {
+              for (int co = 0; co < Cout; ++co) {
+                float w[TC];
+#pragma unroll
+                for (int c = 0; c < TC; ++c) w[c] = (ci0 + c < Cin) ? __ldg(wtap + (int64_t)(ci0 + c) * Cout + co) : 0.f;
+#pragma unroll
+                for (int t = 0; t < TP; ++t) {
+                  const float a = s_dz[off[t] + toff + co];
+#pragma unroll
+                  for (int c = 0; c < TC; ++c) acc[t][c] = fmaf(a, w[c], acc[t][c]);
+                }
+              }
+            }
+          }
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+          const int p = p0 + pg + t * PG;
+          if (p < HW) {
+#pragma unroll
+            for (int c = 0; c < TC; ++c)
+              if (ci0 + c < Cin) d_in[(s * HW + p) * (int64_t)Cin + ci0 + c] = acc[t][c];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int conv_bwd_data(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int64_t n) {
+  if (n == 0) return NNAL_OK;
+  const size_t smem = (size_t)(L.in_h + L.kh - 1) * (L.in_w + L.kw - 1) * L.out_c * sizeof(float);
+  if (smem > 200 * 1024) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient tile exceeds shared memory");
+  const int grid = (int)std::min<int64_t>(n, (int64_t)ctx->sm_count * 8);
+  if (L.in_c % 4 == 0 && L.in_c / 4 <= 256) {
+    auto k = conv_bwd_data_kernel<4, 4>;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, ctx->stream>>>(dz, L.W, d_in, n, L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw);
+  } else {
+    if (L.in_c > 256) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient: more than 256 input channels");
+    auto k = conv_bwd_data_kernel<4, 1>;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, ctx->stream>>>(dz, L.W, d_in, n, L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw);
+  }
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+// ---- fc data gradient: d[M][N] = dz[M][K] . W[K][N]  (W = the layer's [out][in] weight, read as stored) -------------
+// 128x128x16 tiles, 256 threads, 8x8 register micro-tiles; fp32 throughout (gradients span too many binades for the
+// fp16 hi/lo operand planes of the forward GEMM).
+#define BW_BM 128
+#define BW_BN 128
+#define BW_BK 16
+__global__ void __launch_bounds__(256) fc_bwd_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                      float* __restrict__ C, int64_t M, int N, int K) {
+  __shared__ float As[BW_BK][BW_BM + 4];
+  __shared__ float Bs[BW_BK][BW_BN + 4];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.y * BW_BM;
+  const int n0 = blockIdx.x * BW_BN;
+  const int tx = tid % 16, ty = tid / 16;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const bool vecA = (K % 4) == 0, vecB = (N % 4) == 0;
+  for (int k0 = 0; k0 < K; k0 += BW_BK) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      // A tile: 128 rows x 16 k, a thread loads 4 consecutive k of one row
+      const int row = tid / 4 + 64 * i, kq = (tid % 4) * 4;
+      float va[4] = {0.f, 0.f, 0.f, 0.f};
+      const int64_t gm = m0 + row;
+      if (gm < M) {
+        if (vecA && k0 + kq + 3 < K) {
+          const float4 t = *reinterpret_cast<const float4*>(A + gm * K + k0 + kq);
+          va[0] = t.x; va[1] = t.y; va[2] = t.z; va[3] = t.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (k0 + kq + c < K) va[c] = A[gm * K + k0 + kq + c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) As[kq + c][row] = va[c];
+      // B tile: 16 k x 128 columns, a thread loads 4 consecutive columns of one k
+      const int kr = tid / 32 + 8 * i, cq = (tid % 32) * 4;
+      float vb[4] = {0.f, 0.f, 0.f, 0.f};
+      if (k0 + kr < K) {
+        const float* bp = B + (int64_t)(k0 + kr) * N + n0 + cq;
+        if (vecB && n0 + cq + 3 < N) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(bp));
+          vb[0] = t.x; vb[1] = t.y; vb[2] = t.z; vb[3] = t.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (n0 + cq + c < N) vb[c] = __ldg(bp + c);
+        }
+      }
+      *reinterpret_cast<float4*>(&Bs[kr][cq]) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BW_BK; ++k) {
+      float a[8], b[8];
+      float4 t;
+      t = *reinterpret_cast<const float4*>(&As[k][ty * 4]);       a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+      t = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);  a[4] = t.x; a[5] = t.y; a[6] = t.z; a[7] = t.w;
+      t = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);       b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
+      t = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);  b[4] = t.x; b[5] = t.y; b[6] = t.z; b[7] = t.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (gn < N) C[gm * N + gn] = acc[i][j];
+    }
+  }
+}
+
+int fc_bwd_data(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int64_t n) {
+  if (n == 0) return NNAL_OK;
+  dim3 grid(cdiv(L.in_dim, BW_BN), cdiv(n, BW_BM));
+  fc_bwd_kernel<<<grid, 256, 0, ctx->stream>>>(dz, L.W, d_in, n, L.in_dim, L.out_dim);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+// ---- block reduction in float64 ----------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ double block_sum(double v, double* s_red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();                      // s_red may still be read from the previous call
+  if (lane == 0) s_red[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = lane < (int)(blockDim.x >> 5) ? s_red[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;                             // valid in thread 0
+}
+
+// ---- shrink_gradient(.,'sum') of an fc layer: (sum dz)(sum a + 1) / (in*out + out) --------------------------------
+__global__ void __launch_bounds__(256) shrink_fc_kernel(const float* __restrict__ dz, const float* __restrict__ a,
+                                                         int out_dim, int in_dim, double inv_size, double* __restrict__ g,
+                                                         int tau, int t) {
+  __shared__ double s_red[8];
+  const int64_t s = blockIdx.x;
+  double sd = 0.0, sa = 0.0;
+  for (int j = threadIdx.x; j < out_dim; j += blockDim.x) sd += (double)dz[s * out_dim + j];
+  for (int j = threadIdx.x; j < in_dim; j += blockDim.x) sa += (double)a[s * (int64_t)in_dim + j];
+  sd = block_sum(sd, s_red);
+  sa = block_sum(sa, s_red);
+  if (threadIdx.x == 0) g[s * tau + t] = (sd * sa + sd) * inv_size;
+}
+
+// ---- shrink_gradient(.,'sum') of a conv layer: sum_p D[p] (box[p] + 1) / (kh*kw*cin*cout + cout) -------------------
+__global__ void __launch_bounds__(256) shrink_conv_kernel(const float* __restrict__ dz, const float* __restrict__ in, int H,
+                                                           int Wd, int Cin, int Cout, int kh, int kw, double inv_size,
+                                                           double* __restrict__ g, int tau, int t) {
+  extern __shared__ double s_xs[];      // [Hp][Wp] channel sums of the zero-padded input
+  __shared__ double s_red[8];
+  const int Hp = H + kh - 1, Wp = Wd + kw - 1, ph = kh / 2, pw = kw / 2;
+  const int64_t s = blockIdx.x;
+  const float* xin = in + s * (int64_t)H * Wd * Cin;
+  const float* dzs = dz + s * (int64_t)H * Wd * Cout;
+  for (int e = threadIdx.x; e < Hp * Wp; e += blockDim.x) {
+    const int xx = e % Wp - pw, yy = e / Wp - ph;
+    double v = 0.0;
+    if (xx >= 0 && xx < Wd && yy >= 0 && yy < H) {
+      const float* p = xin + ((int64_t)yy * Wd + xx) * Cin;
+      for (int c = 0; c < Cin; ++c) v += (double)p[c];
+    }
+    s_xs[e] = v;
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int p = threadIdx.x; p < H * Wd; p += blockDim.x) {
+    const int y = p / Wd, x = p % Wd;
+    const float* q = dzs + (int64_t)p * Cout;
+    double D = 0.0;
+    for (int c = 0; c < Cout; ++c) D += (double)q[c];
+    double box = 0.0;
+    for (int dy = 0; dy < kh; ++dy)
+      for (int dx = 0; dx < kw; ++dx) box += s_xs[(y + dy) * Wp + x + dx];
+    acc += D * (box + 1.0);
+  }
+  acc = block_sum(acc, s_red);
+  if (threadIdx.x == 0) g[s * tau + t] = acc * inv_size;
+}
+
+// ---- binary model: both class gradients from the single pass  g0 = p1 S, g1 = -p0 S ---------------------------------
+__global__ void binary_scale_kernel(const double* __restrict__ S, const float* __restrict__ post, int64_t n, int tau,
+                                    double* __restrict__ G) {
+  const int64_t total = n * tau;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = e / tau;
+    const double p0 = (double)post[s], p1 = (double)post[n + s];
+    G[e] = p1 * S[e];
+    G[total + e] = -p0 * S[e];
+  }
+}
+
+int count_tau(const nnal_ctx* ctx) {
+  int tau = 0;
+  for (auto& L : ctx->layers) tau += (L.type != NNAL_LAYER_POOL);
+  return tau;
+}
+
+// one chunk: inputs are fp32 NHWC in ctx->xin
+int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_t o, float* post_out, double* g_out) {
+  const int nl = (int)ctx->layers.size();
+  const int c = ctx->n_class, tau = count_tau(ctx);
+  // ---- forward, keeping every layer output ----
+  std::vector<int64_t> elems(nl), offs(nl);
+  int64_t tot = 0, mx = (int64_t)ctx->in_h * ctx->in_w * ctx->in_c;
+  for (int i = 0; i < nl; ++i) {
+    const Layer& L = ctx->layers[i];
+    elems[i] = L.type == NNAL_LAYER_FC ? L.out_dim : (int64_t)L.out_h * L.out_w * L.out_c;
+    offs[i] = tot;
+    tot += (elems[i] * nb + 63) / 64 * 64;          // 256-byte aligned blocks: the fc kernels read rows as float4
+    mx = std::max(mx, elems[i]);
+  }
+  NNAL_TRY(devbuf_reserve(ctx, st->acts, (size_t)tot * sizeof(float)));
+  NNAL_TRY(devbuf_reserve(ctx, st->g[0], (size_t)mx * nb * sizeof(float)));
+  NNAL_TRY(devbuf_reserve(ctx, st->g[1], (size_t)mx * nb * sizeof(float)));
+  NNAL_TRY(devbuf_reserve(ctx, st->post, (size_t)c * nb * sizeof(float)));
+  NNAL_TRY(devbuf_reserve(ctx, st->gout, (size_t)c * nb * tau * sizeof(double)));
+  NNAL_TRY(devbuf_reserve(ctx, st->sred, (size_t)nb * tau * sizeof(double)));
+  float* acts = (float*)st->acts.p;
+  auto in_of = [&](int i) -> const float* { return i == 0 ? (const float*)ctx->xin.p : acts + offs[i - 1]; };
+  for (int i = 0; i < nl; ++i) {
+    const Layer& L = ctx->layers[i];
+    if (!L.has_weights && L.type != NNAL_LAYER_POOL) NNAL_FAIL(ctx, NNAL_ERR_STATE, "layer weights not set");
+    float* out = acts + offs[i];
+    if (i == nl - 1) {
+      NNAL_TRY(nnal_k_head(ctx, L, in_of(i), nb, nb, 0, (float*)st->post.p, nullptr));
+    } else if (L.type == NNAL_LAYER_CONV) {
+      NNAL_TRY(nnal_k_conv_simt(ctx, L, in_of(i), out, nb));
+    } else if (L.type == NNAL_LAYER_POOL) {
+      NNAL_TRY(nnal_k_pool(ctx, L, in_of(i), out, nb));
+    } else if (nnal_layer_on_tc(ctx, i)) {
+      NNAL_TRY(nnal_tc_fc(ctx, L, in_of(i), out, nb));
+    } else {
+      NNAL_TRY(nnal_k_fc_simt(ctx, L, in_of(i), out, nb));
+    }
+  }
+  // ---- backward: one pass of h = e_0 - e_1 (binary) or one pass per class ----
+  const bool binary = c == 2;
+  const int passes = binary ? 1 : c;
+  double* G = (double*)st->gout.p;
+  for (int y = 0; y < passes; ++y) {
+    double* S = binary ? (double*)st->sred.p : G + (int64_t)y * nb * tau;
+    int pp = 0;
+    float* d = (float*)st->g[pp].p;
+    dlogits_kernel<<<grid_for(ctx, nb * c, 8), 256, 0, ctx->stream>>>((const float*)st->post.p, d, nb, c, binary ? -1 : y);
+    ctx->launches++;
+    int t = tau - 1;
+    for (int i = nl - 1; i >= 0; --i) {
+      const Layer& L = ctx->layers[i];
+      float* other = (float*)st->g[pp ^ 1].p;
+      if (L.type == NNAL_LAYER_POOL) {
+        const int64_t total_in = nb * L.in_h * L.in_w * L.in_c;
+        pool_bwd_kernel<<<grid_for(ctx, total_in, 16), 256, 0, ctx->stream>>>(d, in_of(i), other, total_in, L.in_h, L.in_w,
+                                                                                L.in_c, L.out_h, L.out_w, L.kh);
+        ctx->launches++;
+        d = other; pp ^= 1;
+        continue;
+      }
+      if (i != nl - 1) {                 // the last fc has no activation (NN.py:231-241)
+        const int64_t cnt = nb * elems[i];
+        relu_mask_kernel<<<grid_for(ctx, cnt, 16), 256, 0, ctx->stream>>>(d, acts + offs[i], cnt);
+        ctx->launches++;
+      }
+      if (L.type == NNAL_LAYER_FC) {
+        const double inv = 1.0 / ((double)L.in_dim * L.out_dim + L.out_dim);
+        shrink_fc_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(d, in_of(i), L.out_dim, L.in_dim, inv, S, tau, t);
+        ctx->launches++;
+        if (i > 0) { NNAL_TRY(fc_bwd_data(ctx, L, d, other, nb)); d = other; pp ^= 1; }
+      } else {
+        const double inv = 1.0 / ((double)L.kh * L.kw * L.in_c * L.out_c + L.out_c);
+        const size_t sm = (size_t)(L.in_h + L.kh - 1) * (L.in_w + L.kw - 1) * sizeof(double);
+        if (sm > 40 * 1024) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv input plane exceeds shared memory");
+        shrink_conv_kernel<<<(unsigned)nb, 256, sm, ctx->stream>>>(d, in_of(i), L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw,
+                                                                   inv, S, tau, t);
+        ctx->launches++;
+        if (i > 0) { NNAL_TRY(conv_bwd_data(ctx, L, d, other, nb)); d = other; pp ^= 1; }
+      }
+      --t;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
+  if (binary) {
+    binary_scale_kernel<<<grid_for(ctx, nb * tau, 8), 256, 0, ctx->stream>>>((const double*)st->sred.p,
+                                                                             (const float*)st->post.p, nb, tau, G);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
+  for (int y = 0; y < c; ++y) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(g_out + ((size_t)y * n_total + o) * tau, G + (size_t)y * nb * tau,
+                                  (size_t)nb * tau * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (post_out)
+      CUDA_TRY(ctx, cudaMemcpyAsync(post_out + (size_t)y * n_total + o, (const float*)st->post.p + (size_t)y * nb,
+                                    (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));     // the workspaces are reused by the next chunk
+  return NNAL_OK;
+}
+
+int check_model(nnal_ctx* ctx) {
+  if (ctx->layers.empty()) NNAL_FAIL(ctx, NNAL_ERR_STATE, "model not set");
+  if (ctx->n_class < 2) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "shrunk gradients need at least two classes");
+  return NNAL_OK;
+}
+
+}  // namespace
+
+int nnal_bw_release(nnal_ctx* ctx) {
+  if (!ctx->bw_state) return NNAL_OK;
+  BwState* st = (BwState*)ctx->bw_state;
+  DevBuf* bufs[] = {&st->acts, &st->g[0], &st->g[1], &st->post, &st->gout, &st->sred};
+  for (DevBuf* b : bufs) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+  delete st;
+  ctx->bw_state = nullptr;
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_shrunk_tau(nnal_ctx* ctx, int* tau) {
+  if (!ctx || !tau) return NNAL_ERR_INVALID;
+  NNAL_TRY(check_model(ctx));
+  *tau = count_tau(ctx);
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_shrunk_images(nnal_ctx* ctx, const float* x, int64_t n, float* post_out, double* g_out) {
+  if (!ctx || n < 0 || (n > 0 && (!x || !g_out))) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  NNAL_TRY(check_model(ctx));
+  if (n == 0) return NNAL_OK;
+  BwState* st = bw_state(ctx);
+  const int64_t chunk = std::min(bw_chunk(), n);
+  const size_t per = (size_t)ctx->in_h * ctx->in_w * ctx->in_c;
+  NNAL_TRY(devbuf_reserve(ctx, ctx->xin, (size_t)chunk * per * sizeof(float)));
+  for (int64_t o = 0; o < n; o += chunk) {
+    const int64_t nb = std::min(chunk, n - o);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->xin.p, x + o * per, (size_t)nb * per * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    NNAL_TRY(shrunk_chunk(ctx, st, nb, n, o, post_out, g_out));
+  }
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_shrunk_voxels(nnal_ctx* ctx, int subject, const int64_t* inds, int64_t n, int d1, int d2, int d3,
+                                     const double* stats, int norm_mode, float* post_out, double* g_out) {
+  if (!ctx || n < 0 || (n > 0 && (!inds || !g_out))) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  NNAL_TRY(check_model(ctx));
+  const Volume* v;
+  NNAL_TRY(nnal_check_gather_args(ctx, subject, n, d1, d2, d3, &v));
+  if (d1 != ctx->in_h || d2 != ctx->in_w || d3 * v->m != ctx->in_c)
+    NNAL_FAIL(ctx, NNAL_ERR_INVALID, "patch shape does not match the model input");
+  if (n == 0) return NNAL_OK;
+  double* d_stats;
+  NNAL_TRY(nnal_upload_stats(ctx, stats, v->m, norm_mode, &d_stats));
+  BwState* st = bw_state(ctx);
+  const int64_t chunk = std::min(bw_chunk(), n);
+  const size_t per = (size_t)ctx->in_h * ctx->in_w * ctx->in_c;
+  NNAL_TRY(devbuf_reserve(ctx, ctx->xin, (size_t)chunk * per * sizeof(float)));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->inds, (size_t)n * 8));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->inds.p, inds, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const int64_t* d_inds = (const int64_t*)ctx->inds.p;
+  for (int64_t o = 0; o < n; o += chunk) {
+    const int64_t nb = std::min(chunk, n - o);
+    NNAL_TRY(nnal_k_gather_norm_f32(ctx, *v, d_inds + o, nb, d1, d2, d3, d_stats, norm_mode, (float*)ctx->xin.p));
+    NNAL_TRY(shrunk_chunk(ctx, st, nb, n, o, post_out, g_out));
+  }
+  return NNAL_OK;
+}

@@ -391,6 +391,54 @@ class Engine(object):
         self._chk(self.lib.nnal_fi_greedy(self.h, k, float(delta), _ptr(sel), _ptr(obj), _ptr(red)))
         return sel, obj, red
 
+    # ------------------------------------------------------------------
+    # the reference's shrunk FI coordinates + SDP query distribution
+    # ------------------------------------------------------------------
+    def fi_shrunk_tau(self):
+        tau = C.c_int()
+        self._chk(self.lib.nnal_fi_shrunk_tau(self.h, C.byref(tau)))
+        return tau.value
+
+    def fi_shrunk_images(self, x):
+        """Shrunk class-score gradients of host samples ``x`` [n,H,W,C]: (posteriors [c,n] float32, g [c,n,tau] float64)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[0]
+        post = np.empty((self.n_class, n), dtype=np.float32)
+        g = np.empty((self.n_class, n, self.fi_shrunk_tau()), dtype=np.float64)
+        self.h2d_bytes += x.nbytes
+        self.d2h_bytes += post.nbytes + g.nbytes
+        self._chk(self.lib.nnal_fi_shrunk_images(self.h, _ptr(x), n, _ptr(post), _ptr(g)))
+        return post, g
+
+    def fi_shrunk_voxels(self, subject, inds, patch_shape, stats, norm_mode=L.NORM_BATCH_EVAL, shape=None):
+        """Same, for voxels of an uploaded subject (gathered and normalised on the device)."""
+        inds, _ = self._check_inds(inds, shape, patch_shape, (0, 0, 0))
+        d1, d2, d3 = [int(p) for p in patch_shape]
+        st = None if stats is None else np.ascontiguousarray(stats, dtype=np.float64)
+        post = np.empty((self.n_class, inds.size), dtype=np.float32)
+        g = np.empty((self.n_class, inds.size, self.fi_shrunk_tau()), dtype=np.float64)
+        self.h2d_bytes += inds.nbytes
+        self.d2h_bytes += post.nbytes + g.nbytes
+        self._chk(self.lib.nnal_fi_shrunk_voxels(self.h, int(subject), _ptr(inds), inds.size, d1, d2, d3,
+                                                 None if st is None else _ptr(st), int(norm_mode), _ptr(post), _ptr(g)))
+        return post, g
+
+    def sdp_query_distribution(self, A, tol=1e-4, max_iter=200000, gamma=0.5):
+        """min tr((sum_i q_i A_i)^-1) over the simplex; ``A`` [n,tau,tau] float64.
+        Returns dict(q, t, objective, gap, iterations)."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        if A.ndim != 3 or A.shape[1] != A.shape[2]:
+            raise ValueError('A must be [n, tau, tau]')
+        n, tau = A.shape[0], A.shape[1]
+        q = np.empty(n, dtype=np.float64)
+        t = np.empty(tau, dtype=np.float64)
+        obj, gap, it = C.c_double(), C.c_double(), C.c_int64()
+        self.h2d_bytes += A.nbytes
+        self.d2h_bytes += q.nbytes
+        self._chk(self.lib.nnal_sdp_query_distribution(self.h, _ptr(A), n, tau, float(tol), int(max_iter), float(gamma),
+                                                       _ptr(q), _ptr(t), C.byref(obj), C.byref(gap), C.byref(it)))
+        return {'q': q, 't': t, 'objective': obj.value, 'gap': gap.value, 'iterations': it.value}
+
     def fi_begin(self, k, delta):
         self._chk(self.lib.nnal_fi_begin(self.h, int(k), float(delta)))
 

@@ -141,6 +141,83 @@ def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, return_objectiv
     return (Q, obj) if return_objective else Q
 
 
+def _sdp_sample(A, expr, return_solution):
+    """SDP query distribution + the reference's sampler (PW_NNAL.py:154-163).  The draw uses NumPy's global
+    generator like the reference; with several ranks, rank 0's draw is broadcast."""
+    from . import NNAL_tools
+    k = int(expr.pars['k'])
+    soln = NNAL_tools.SDP_query_distribution(A, expr.pars.get('lambda_', 0), None, k,
+                                             tol=float(expr.pars.get('sdp_tol', 1e-4)))
+    q_opt = np.array(soln['x'][:len(A)])
+    Q_inds = NNAL_tools.sample_query_dstr(q_opt.copy(), k, replacement=True)
+    if dist.is_dist():
+        buf = np.full(k + 1, -1, dtype=np.int64)
+        buf[0] = len(Q_inds)
+        buf[1:1 + len(Q_inds)] = Q_inds
+        buf = dist.broadcast_array(buf, 0)
+        Q_inds = buf[1:1 + int(buf[0])]
+    return (Q_inds, soln) if return_solution else (Q_inds, None)
+
+
+def query_single_sdp(expr, model, sess, padded_imgs, pool_inds, return_solution=False):
+    """``PW_NNAL.CNN_query(..., 'fi')`` as the reference runs it (PW_NNAL.py:89-163): posteriors -> the B most
+    uncertain samples (:107-115) -> conditional FIs in shrunk coordinates (gen_A_matrices, diag_load 1e-5) -> SDP
+    query distribution -> ``sample_query_dstr`` (<= k unique positions, sorted).  Positions into ``pool_inds``.
+    The candidates' patches are gathered on the device; every rank evaluates the same B candidates."""
+    from .PW_NNAL import _score_pool_single, _stats_list, _A_from_shrunk
+    B = int(expr.pars['B'])
+    pool_inds = np.asarray(pool_inds)
+    n = len(pool_inds)
+    eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=0)
+    if B < n:
+        eng.pool_score(L.SCORE_BINARY)
+        idx, sc = eng.pool_topk(B, with_scores=True)
+        sel_inds, _ = dist.allgather_topk(sc, idx + lo, B)
+    else:
+        sel_inds = np.arange(n, dtype=np.int64)
+    imgs = list(padded_imgs)
+    post, g = eng.fi_shrunk_voxels(0, pool_inds[sel_inds], expr.pars['patch_shape'],
+                                   _stats_list(expr.pars['stats'], len(imgs)), L.NORM_BATCH_EVAL, shape=imgs[0].shape)
+    A = _A_from_shrunk(g, post[1].astype(np.float64), float(expr.pars.get('fi_diag_load', 1e-5)))
+    Q_inds, soln = _sdp_sample(A, expr, return_solution)
+    q = sel_inds[Q_inds]
+    return (q, soln, sel_inds) if return_solution else q
+
+
+def query_multimg_sdp(expr, model, sess, all_padded_imgs, pool_inds, return_solution=False):
+    """``PW_NNAL.query_multimg(..., 'fi')`` as the reference runs it (PW_NNAL.py:547-627): B most uncertain samples of
+    the concatenated pool, per-subject A-matrices with diag_load 1e-3 (:566-578) in subject-major order, SDP,
+    sampling, ``global2local_inds`` of the sampled candidates' pool positions."""
+    from .PW_NNAL import _bin_filter_core, _A_from_shrunk
+    B = int(expr.pars['B'])
+    eng = get_engine()
+    sorted_inds, _, lo, hi, sizes = _bin_filter_core(expr, model, sess, all_padded_imgs, pool_inds, B)
+    s = len(pool_inds)
+    m = len(all_padded_imgs[0]) - 1
+    cum = np.append(-1, np.cumsum(sizes) - 1)
+    set_of = cum.searchsorted(sorted_inds) - 1
+    order = np.argsort(set_of, kind='stable')
+    G = sorted_inds[order]                       # global positions, subject-major candidate order
+    G_set = set_of[order]
+    A = []
+    delta = float(expr.pars.get('fi_diag_load', 1e-3))
+    for i in range(s):
+        sel = G_set == i
+        if not sel.any():
+            continue
+        local = G[sel] - (cum[i] + 1)
+        imgs = list(all_padded_imgs[i][:-1])
+        eng.upload(i, imgs)
+        stats = np.array([[expr.train_stats[i, 2 * j], expr.train_stats[i, 2 * j + 1]] for j in range(m)],
+                         dtype=np.float64)
+        post, g = eng.fi_shrunk_voxels(i, np.asarray(pool_inds[i])[local], expr.pars['patch_shape'], stats,
+                                       L.NORM_BATCH_EVAL, shape=imgs[0].shape)
+        A += _A_from_shrunk(g, post[1].astype(np.float64), delta)
+    Q_inds, soln = _sdp_sample(A, expr, return_solution)
+    Q = patch_utils.global2local_inds(G[Q_inds], sizes)
+    return (Q, soln, G) if return_solution else Q
+
+
 def query_whole(model, expr, pool_inds, session):
     """``NNAL.CNN_query(..., 'fi')`` (NNAL.py:312-464).  Binary models: uncertainty pre-filter to B
     (entropy, NNAL_tools.uncertainty_filtering) + last-layer factored greedy.  c > 2: the k pool

@@ -28,7 +28,7 @@ __all__ = [
     'fi_objective_dual', 'greedy_fi_dual_bruteforce', 'greedy_fi_rank1',
     'last_layers_kernel', 'last_layers_dim', 'weighted_gram', 'fi_objective_from_gram',
     'sample_query_dstr', 'append_zero', 'last_layers_factors', 'greedy_fi_replay', 'query_fi_single',
-    'query_fi_multimg',
+    'query_fi_multimg', 'sdp_certificate', 'sdp_solve', 'sdp_solve_slsqp', 'query_fi_sdp_single',
 ]
 
 
@@ -319,6 +319,88 @@ def sdp_objective(A, q):
     NNAL_tools.py:589-602 / 612-659 minimises at its optimum for a given q."""
     Iq = sum(q[i] * A[i] for i in range(len(A)))
     return np.trace(np.linalg.inv(Iq))
+
+
+def sdp_certificate(A, q):
+    """(phi, gap) for a feasible q: phi = tr(M^-1), M = sum_i q_i A_i, and the duality
+    certificate gap = max_i tr(M^-1 A_i M^-1) / phi - 1.  phi is convex in q with
+    d phi / d q_i = -tr(M^-1 A_i M^-1) and sum_i q_i tr(M^-1 A_i M^-1) = phi, so
+    phi* >= phi - (max_i d_i - phi): the SDP optimum of NNAL_tools.py:612-659 lies within
+    ``gap`` (relative) of phi."""
+    A = np.asarray(A, dtype=np.float64)
+    q = np.asarray(q, dtype=np.float64)
+    M = np.tensordot(q, A, axes=(0, 0))
+    Mi = np.linalg.inv(M)
+    P = Mi @ Mi
+    d = np.tensordot(A, P, axes=([1, 2], [0, 1]))
+    phi = np.trace(Mi)
+    return phi, d.max() / phi - 1.
+
+
+def sdp_solve(A, tol=1e-4, max_iter=200000, gamma=0.5):
+    """Float64 restatement of the query-distribution problem the reference gives cvxopt
+    (NNAL_tools.SDP_query_distribution NNAL_tools.py:612-659 with lambda_ = 0: minimise
+    sum_j t_j s.t. [[sum q_i A_i, e_j],[e_j^T, t_j]] >= 0, q >= 0, sum q = 1  <=>
+    minimise tr((sum_i q_i A_i)^-1) over the simplex), solved by the multiplicative
+    algorithm q_i <- q_i (d_i / phi)^gamma until the certificate of ``sdp_certificate``
+    drops below ``tol``.  Returns (q, t = diag(M^-1), phi, gap, iterations)."""
+    A = np.asarray(A, dtype=np.float64)
+    n, tau, _ = A.shape
+    Af = A.reshape(n, -1)
+    q = np.ones(n) / n
+    it = 0
+    while True:
+        Mi = np.linalg.inv((q @ Af).reshape(tau, tau))
+        d = Af @ (Mi @ Mi).ravel()
+        phi = np.trace(Mi)
+        gap = d.max() / phi - 1.
+        if gap <= tol or it >= max_iter:
+            return q, np.diag(Mi).copy(), phi, gap, it
+        q = q * (d / phi) ** gamma
+        q /= q.sum()
+        it += 1
+
+
+def sdp_solve_slsqp(A, q0=None):
+    """Independent check of ``sdp_solve`` for SMALL n: the same convex programme handed to
+    scipy's SLSQP (equality sum q = 1, bounds q >= 0, analytic gradient).  Returns (q, phi)."""
+    from scipy.optimize import minimize
+    A = np.asarray(A, dtype=np.float64)
+    n, tau, _ = A.shape
+    Af = A.reshape(n, -1)
+
+    def f(q):
+        Mi = np.linalg.inv((q @ Af).reshape(tau, tau))
+        return np.trace(Mi), -(Af @ (Mi @ Mi).ravel())
+    scale = f(np.ones(n) / n)[0]
+    res = minimize(lambda q: tuple(v / scale for v in f(q)), np.ones(n) / n if q0 is None else q0, jac=True,
+                   method='SLSQP', bounds=[(0., 1.)] * n,
+                   constraints=[{'type': 'eq', 'fun': lambda q: q.sum() - 1., 'jac': lambda q: np.ones(n)}],
+                   options={'maxiter': 2000, 'ftol': 1e-14})
+    q = np.clip(res.x, 0., None)
+    q /= q.sum()
+    return q, f(q)[0]
+
+
+def query_fi_sdp_single(layers, weights, padded_imgs, pool_inds, patch_shape, ntb, stats, k, B, u,
+                        diag_load=1e-5, tol=1e-4):
+    """PW_NNAL.CNN_query 'fi' as the reference runs it (PW_NNAL.py:89-163) with lambda_ = 0:
+    posteriors -> the B most uncertain (:107-115) -> re-gather + normalise (:122-131) ->
+    gen_A_matrices in shrunk coordinates (:133-137) -> SDP query distribution (:154-157) ->
+    sample_query_dstr with the k uniform draws ``u`` (:160-163).  Returns (positions into
+    ``pool_inds``, details)."""
+    pool_inds = np.asarray(pool_inds)
+    posts = batch_eval(layers, weights, padded_imgs, pool_inds, patch_shape, ntb, stats, 'posteriors')[0]
+    if B < len(pool_inds):
+        sel = stable_topk(np.abs(posts - .5), B)
+    else:
+        sel = np.arange(len(pool_inds))
+    x = normalize_batch_eval(get_patches(padded_imgs, pool_inds[sel], patch_shape), stats).astype(np.float32)
+    post, g = shrunk_class_gradients(layers, weights, x)
+    A = gen_A_matrices(g[0], g[1], posts[sel], diag_load)
+    q, t, phi, gap, it = sdp_solve(A, tol)
+    Q = sample_query_dstr(q.copy(), k, u)
+    return sel[Q], {'sel': sel, 'A': A, 'q': q, 't': t, 'phi': phi, 'gap': gap, 'g': g, 'post': post, 'x': x}
 
 
 def fi_objective_direct(Abar, S, delta):

@@ -1,0 +1,233 @@
+"""GPU parity tests of the reference's literal FI pipeline (``pytest -m gpu`` on the B200 box): shrunk class-score
+gradients (NN.get_gradients + NNAL_tools.shrink_gradient), gen_A_matrices (row 10), the SDP query
+distribution (row 12) and the 'fi' query with ``fi_mode='sdp'`` -- through the C ABI, against oracle/fi_oracle.py."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+import oracle as O
+from tests.test_gpu_fi import Expr, _pw_setup
+from tests.test_gpu_parity import SMALL
+
+pytestmark = pytest.mark.gpu
+
+OBJ_RTOL = 1e-3      # north_star: FI objectives within 1e-3 relative
+G_RTOL = 2e-4        # shrunk gradients: fp32 forward/backward vs the float64 oracle, relative to the layer's largest entry
+
+SMALL2 = [('conv1', [8, 'conv', [3, 3]]), ('max1', [[2, 2], 'pool']), ('conv2', [12, 'conv', [5, 3]]),
+          ('fc1', [72, 'fc']), ('fc2', [64, 'fc']), ('fc3', [2, 'fc'])]
+
+
+@pytest.fixture(scope='module')
+def nb():
+    import nnal_b200
+    return nnal_b200
+
+
+def _assert_shrunk_close(g, go, rtol=G_RTOL):
+    assert g.shape == go.shape
+    floor = 1e-3 * np.abs(go).max()      # the last layer's entry is identically 0 (sum_y dz_y = 0): round-off only
+    for t in range(go.shape[2]):
+        scale = max(np.abs(go[:, :, t]).max(), floor)
+        assert np.abs(g[:, :, t] - go[:, :, t]).max() <= rtol * scale, \
+            'layer %d: %g vs scale %g' % (t, np.abs(g[:, :, t] - go[:, :, t]).max(), scale)
+
+
+@pytest.mark.parametrize('layers,in_shape,seed', [(SMALL, (9, 7, 2), 3), (SMALL2, (11, 8, 3), 4)])
+@pytest.mark.parametrize('tc', [1, 0])
+def test_shrunk_gradients_small_nets(nb, layers, in_shape, seed, tc):
+    """Generic layer dictionaries (odd sizes, non-square filters, c = 3 -> one backward pass per class; c = 2 -> the
+    single-pass shortcut) == shrink_gradient(tf.gradients(log p_y), 'sum') of the float64 oracle."""
+    rs = np.random.RandomState(seed)
+    x = rs.randn(150, *in_shape).astype(np.float32)
+    w = O.he_init_weights(layers, in_shape, seed, bias_scale=0.1)
+    model = nb.NN.CNN(in_shape, OrderedDict(layers), feature_layer=len(layers) - 2)
+    model.set_weights(w)
+    eng = nb.get_engine()
+    eng.set_model(model, None)
+    eng.set_tensor_cores(tc)
+    try:
+        post, g = eng.fi_shrunk_images(x)
+    finally:
+        eng.set_tensor_cores(1)
+    po, go = O.shrunk_class_gradients(layers, w, x)
+    assert eng.fi_shrunk_tau() == go.shape[2]
+    assert np.abs(post - po).max() < 1e-4
+    _assert_shrunk_close(g, go)
+
+
+def test_shrunk_gradients_chunking(nb, monkeypatch):
+    """Results do not depend on the chunk size of the backward pass."""
+    rs = np.random.RandomState(8)
+    x = rs.randn(70, 9, 7, 2).astype(np.float32)
+    w = O.he_init_weights(SMALL, (9, 7, 2), 9, bias_scale=0.1)
+    model = nb.NN.CNN((9, 7, 2), OrderedDict(SMALL), feature_layer=len(SMALL) - 2)
+    model.set_weights(w)
+    eng = nb.get_engine()
+    eng.set_model(model, None)
+    p1, g1 = eng.fi_shrunk_images(x)
+    monkeypatch.setenv('NNAL_BW_CHUNK', '16')
+    p2, g2 = eng.fi_shrunk_images(x)
+    assert np.array_equal(g1, g2) and np.array_equal(p1, p2)
+    p3, g3 = eng.fi_shrunk_images(x[:0])
+    assert g3.shape == (3, 0, 6)
+
+
+def test_shrunk_gradients_pw1_and_A_matrices(nb):
+    """PW1 on gathered voxels: shrunk gradients, then PW_NNAL.gen_A_matrices == the oracle's A_i (rows 8-10)."""
+    ps, imgs, padded, stats, pool, layers, w = _pw_setup(48, 90)
+    model = nb.NN.create_PW1(2)
+    model.set_weights(w)
+    eng = nb.get_engine()
+    eng.set_model(model, None)
+    eng.upload(0, padded)
+    st = np.array(stats, dtype=np.float64)
+    post, g = eng.fi_shrunk_voxels(0, pool, ps, st, shape=padded[0].shape)
+    x = O.normalize_batch_eval(O.get_patches(padded, pool, ps), stats).astype(np.float32)
+    po, go = O.shrunk_class_gradients(layers, w, x)
+    assert go.shape == (2, 48, 7)
+    assert np.abs(post - po).max() < 1e-4
+    _assert_shrunk_close(g, go)
+    # host-patch entry point (the reference hands gen_A_matrices the normalised patches, PW_NNAL.py:121-137)
+    sel_posts = po[1].copy()
+    sel_posts[0], sel_posts[1] = 1e-9, 1 - 1e-9          # the two clamped branches (:770-793)
+    expr = Expr(k=5, B=48, lambda_=0., patch_shape=ps, ntb=128, stats=stats)
+    A = nb.PW_NNAL.gen_A_matrices(expr, model, None, x, sel_posts, 1e-5)
+    Ao = O.gen_A_matrices(go[0], go[1], sel_posts, 1e-5)
+    assert len(A) == 48
+    for a, b in zip(A, Ao):
+        assert np.abs(a - b).max() <= 5e-4 * np.abs(b - 1e-5 * np.eye(7)).max() + 1e-20
+    # objective of the uniform design in both sets of matrices
+    q = np.ones(48) / 48
+    assert abs(O.sdp_objective(A, q) / O.sdp_objective(Ao, q) - 1) < OBJ_RTOL
+
+
+def _rand_A(n, tau, delta, seed, scale):
+    rs = np.random.RandomState(seed)
+    s = rs.randn(n, tau) * scale * np.exp(rs.randn(1, tau))
+    p = rs.rand(n)
+    g = np.stack([p[:, None] * s, -(1 - p)[:, None] * s])
+    return O.gen_A_matrices(g[0], g[1], p, delta)
+
+
+@pytest.mark.parametrize('n,tau,delta,scale', [(500, 7, 1e-5, 1e-2), (2000, 7, 1e-3, 1e-2), (300, 7, 1e-5, 1e-4),
+                                              (40000, 3, 1e-3, 1e-1), (64, 16, 1e-2, 1.), (10, 1, 1e-3, 1.), (1, 4, 1e-3, 1.)])
+def test_sdp_query_distribution(nb, n, tau, delta, scale):
+    """Device solver == float64 restatement of the SDP: objective within 1e-3 (in fact within the certified tol), the
+    certificate of the RETURNED q recomputed in float64, t = diag(M^-1), q on the simplex."""
+    A = np.array(_rand_A(n, tau, delta, n + tau, scale))
+    tol = 1e-4
+    r = nb.get_engine().sdp_query_distribution(A, tol=tol)
+    q = r['q']
+    assert q.shape == (n,) and np.all(q >= 0) and abs(q.sum() - 1) < 1e-12
+    phi, gap = O.sdp_certificate(A, q)
+    assert abs(r['objective'] / phi - 1) < 1e-9 and abs(r['gap'] - gap) < 1e-6
+    assert gap <= 2 * tol
+    assert np.allclose(r['t'], np.diag(np.linalg.inv(np.tensordot(q, A, axes=(0, 0)))), rtol=1e-9)
+    qo, to, phio, gapo, ito = O.sdp_solve(A, tol)
+    assert abs(phi / phio - 1) < 3 * tol < OBJ_RTOL
+    # shim with the cvxopt-shaped solution
+    soln = nb.NNAL_tools.SDP_query_distribution(list(A), 0., None, 10)
+    assert soln['status'] == 'optimal' and len(soln['x']) == n + tau
+    assert np.allclose(np.array(soln['x'][:n]), q)
+    assert abs(np.sum(soln['x'][n:]) / phi - 1) < 1e-9
+    with pytest.raises(NotImplementedError):
+        nb.NNAL_tools.SDP_query_distribution(list(A), 0.1, None, 10)
+
+
+def test_sdp_matches_slsqp_small(nb):
+    """Independent solver (scipy SLSQP on the same programme) at small n."""
+    A = np.array(_rand_A(40, 4, 1e-3, 5, 0.05))
+    r = nb.get_engine().sdp_query_distribution(A, tol=1e-6)
+    q2, phi2 = O.sdp_solve_slsqp(A)
+    assert abs(r['objective'] / phi2 - 1) < 1e-5
+
+
+def test_sdp_errors(nb):
+    eng = nb.get_engine()
+    with pytest.raises(Exception):
+        eng.sdp_query_distribution(np.zeros((4, 17, 17)))
+    with pytest.raises(Exception):
+        eng.sdp_query_distribution(np.zeros((4, 3, 3)))           # singular: not positive definite
+
+
+@pytest.mark.parametrize('B', [40, 10 ** 6])
+def test_pw_fi_query_sdp_single(nb, B):
+    """PW_NNAL.CNN_query(..., 'fi') with fi_mode='sdp' = the reference's own pipeline (PW_NNAL.py:89-163): same
+    pre-filtered candidates, SDP objective within 1e-3 of the oracle's, and the sampled positions are exactly what
+    sample_query_dstr returns for the device's q with the same uniform draws."""
+    ps, imgs, padded, stats, pool, layers, w = _pw_setup(120, 95)
+    model = nb.NN.create_PW1(2)
+    model.set_weights(w)
+    k = 8
+    expr = Expr(k=k, B=B, lambda_=0., patch_shape=ps, ntb=128, stats=stats, fi_mode='sdp')
+    np.random.seed(123)
+    u = np.random.sample(k)
+    np.random.seed(123)
+    q, soln, sel = nb.fi.query_single_sdp(expr, model, None, padded, pool, return_solution=True)
+    np.random.seed(123)
+    q2 = nb.PW_NNAL.CNN_query(expr, model, None, padded, pool, None, 'fi')
+    assert np.array_equal(q, q2)
+    qo, det = O.query_fi_sdp_single(layers, w, padded, pool, ps, 128, stats, k, B, u)
+    assert set(sel.tolist()) == set(det['sel'].tolist())
+    assert soln['status'] == 'optimal'
+    assert abs(soln['primal objective'] / det['phi'] - 1) < OBJ_RTOL
+    nB = len(sel)
+    q_dev = np.array(soln['x'][:nB])
+    # the device's q is near-optimal for the ORACLE's matrices too (candidate order may differ at exact ties only)
+    pos = {int(v): i for i, v in enumerate(det['sel'])}
+    perm = np.array([pos[int(v)] for v in sel])
+    phi_o, gap_o = O.sdp_certificate(np.array(det['A'])[perm], q_dev)
+    assert abs(phi_o / det['phi'] - 1) < OBJ_RTOL
+    assert np.array_equal(q, sel[O.sample_query_dstr(q_dev.copy(), k, u)])
+    assert len(q) <= k and len(np.unique(q)) == len(q) and np.all(np.isin(q, sel))
+
+
+def test_pw_fi_query_sdp_multimg(nb):
+    ps = (25, 25, 1)
+    S, m = 3, 3
+    shape = (34, 30, 4)
+    allp, pools, st = [], [], np.zeros((S, 2 * m))
+    rs = np.random.RandomState(44)
+    for s in range(S):
+        imgs = [np.clip(rs.randn(*shape) * 30 + 100, 0, None).astype(np.float32) for _ in range(m)]
+        r = [(p - 1) // 2 for p in ps]
+        allp.append([np.pad(im, ((r[0], r[0]), (r[1], r[1]), (r[2], r[2])), 'constant') for im in imgs] +
+                    [(rs.rand(*shape) > .5).astype(np.int8)])
+        pools.append(list(rs.choice(int(np.prod(shape)), [50, 0, 70][s], replace=False)))
+        for j in range(m):
+            st[s, 2 * j], st[s, 2 * j + 1] = imgs[j].mean(), imgs[j].std()
+    layers = O.pw1_layers(2)
+    w = O.he_init_weights(layers, (25, 25, 3), 62, bias_scale=0.05)
+    model = nb.NN.create_PW1(2)
+    model.set_weights(w)
+    k, B = 6, 30
+    expr = Expr(k=k, B=B, lambda_=0., patch_shape=ps, ntb=128, fi_mode='sdp', SDP_solver='CVXOPT')
+    expr.train_stats = st
+    np.random.seed(5)
+    u = np.random.sample(k)
+    np.random.seed(5)
+    Q, soln, G = nb.fi.query_multimg_sdp(expr, model, None, allp, pools, return_solution=True)
+    np.random.seed(5)
+    Q2 = nb.PW_NNAL.query_multimg(expr, model, None, allp, pools, None, 'fi')
+    assert len(Q) == S and all(np.array_equal(a, b) for a, b in zip(Q, Q2))
+    assert len(Q[1]) == 0 and sum(len(a) for a in Q) <= k
+    assert soln['status'] == 'optimal' and len(G) == B
+    # the oracle's A-matrices of the same candidates (subject-major order, diag_load 1e-3, PW_NNAL.py:566-578)
+    sizes = [len(p) for p in pools]
+    local = O.global2local_inds(G, sizes)
+    A = []
+    for s in range(S):
+        if len(local[s]) == 0:
+            continue
+        stats = [[st[s, 2 * j], st[s, 2 * j + 1]] for j in range(m)]
+        x = O.normalize_batch_eval(O.get_patches(allp[s][:m], np.asarray(pools[s])[local[s]], ps), stats).astype(np.float32)
+        po, go = O.shrunk_class_gradients(layers, w, x)
+        A += O.gen_A_matrices(go[0], go[1], po[1], 1e-3)
+    qo, to, phio, gapo, ito = O.sdp_solve(A, 1e-4)
+    assert abs(soln['primal objective'] / phio - 1) < OBJ_RTOL
+    q_dev = np.array(soln['x'][:B])
+    draws = O.sample_query_dstr(q_dev.copy(), k, u)
+    want = O.global2local_inds(G[draws], sizes)
+    assert all(np.array_equal(np.sort(a), np.sort(b)) for a, b in zip(Q, want))
