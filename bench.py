@@ -403,9 +403,13 @@ def run_sdp_round(args, eng, padded, pool, st, k):
     cand = pool[:B]
     res = None
     for rep in range(2):                       # first repetition warms the workspaces up
+        eng.profile(True)
         t0 = time.perf_counter()
         post, g = eng.fi_shrunk_voxels(0, cand, PATCH, st, shape=padded[0].shape)
         t1 = time.perf_counter()
+        fwd_ms, _ = eng.profile_read(120)
+        bwd_ms, _ = eng.profile_read(121)
+        eng.profile(False)
         A = np.array(_A_from_shrunk(g, post[1].astype(np.float64), 1e-5))
         t2 = time.perf_counter()
         r = eng.sdp_query_distribution(A, tol=1e-4)
@@ -416,6 +420,7 @@ def run_sdp_round(args, eng, padded, pool, st, k):
                'stage_ms': {'shrunk_gradients(gather+forward+backward)': 1e3 * (t1 - t0), 'A_matrices(host)': 1e3 * (t2 - t1),
                             'sdp_solver': 1e3 * (t3 - t2), 'sampling(host)': 1e3 * (t4 - t3)},
                'ms_per_round': 1e3 * (t4 - t0),
+               'shrunk_device_ms': {'forward(all activations kept)': fwd_ms, 'backward(data gradients + layer sums)': bwd_ms},
                'backprops_per_s': 2.0 * B / (t1 - t0),
                'sdp': {'iterations': int(r['iterations']), 'objective': float(r['objective']), 'gap': float(r['gap']),
                        'us_per_iteration': 1e6 * (t3 - t2) / max(1, int(r['iterations'])),

@@ -168,6 +168,8 @@ static inline void prof_end(nnal_ctx* ctx) {
 #define NNAL_PROF_FI_SETUP 110
 #define NNAL_PROF_FI_GRAM 111
 #define NNAL_PROF_FI_GREEDY 112
+#define NNAL_PROF_BW_FORWARD 120
+#define NNAL_PROF_BW_BACKWARD 121
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

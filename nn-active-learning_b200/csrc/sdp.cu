@@ -14,7 +14,11 @@
 // One kernel per iteration; every CTA rebuilds M from the previous iteration's per-CTA partial sums (fixed order:
 // deterministic), inverts it in shared memory, updates its samples and writes the next partial sums.  All float64.
 #include "nnal_common.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -75,11 +79,11 @@ __device__ __forceinline__ double warp_max(double v) {
 __device__ void sdp_build(const Parts in, int G, int tau, double* s_M, double* s_P, double& phi, double& Z) {
   const int T2 = tau * tau, tid = threadIdx.x;
   double z = 0.0;
-  for (int g = 0; g < G; ++g) z += in.Z[g];
+  for (int g = 0; g < G; ++g) z += __ldcg(in.Z + g);       // written by other CTAs: read through L2
   Z = z;
   if (tid < T2) {
     double m = 0.0;
-    for (int g = 0; g < G; ++g) m += in.M[(size_t)g * T2 + tid];
+    for (int g = 0; g < G; ++g) m += __ldcg(in.M + (size_t)g * T2 + tid);
     s_M[tid] = m / z;
   }
   __syncthreads();
@@ -145,22 +149,16 @@ __global__ void __launch_bounds__(SDP_THREADS) sdp_init_kernel(const double* __r
   sdp_accumulate(At, qu, n, tau * tau, 0.0, parts_of(part_out, gridDim.x, tau * tau), s_w, s_r);
 }
 
-__global__ void __launch_bounds__(SDP_THREADS) sdp_iter_kernel(const double* __restrict__ At, double* __restrict__ qu,
-                                                                int64_t n, int tau, double gamma, double* part_in,
-                                                                double* part_out, double* __restrict__ hist) {
-  __shared__ double s_M[SDP_T2], s_P[SDP_T2];
-  __shared__ double s_w[SDP_THREADS / 32][SDP_T2];
-  __shared__ double s_r[16];
+// one multiplicative update; returns max_i d_i / phi of the PREVIOUS iterate (identical in every CTA)
+__device__ double sdp_iterate(const double* __restrict__ At, double* __restrict__ qu, int64_t n, int tau, double gamma,
+                              double* part_in, double* part_out, double* s_M, double* s_P, double (*s_w)[SDP_T2],
+                              double* s_r, double& phi_out) {
   const int T2 = tau * tau, G = gridDim.x;
   const Parts in = parts_of(part_in, G, T2);
   double phi, Z;
   sdp_build(in, G, tau, s_M, s_P, phi, Z);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double r = 0.0;
-    for (int g = 0; g < G; ++g) r = fmax(r, in.R[g]);
-    hist[0] = phi;            // phi(q_it)
-    hist[1] = r;              // max_i d_i / phi of the PREVIOUS iterate (0 before the first update)
-  }
+  double rprev = 0.0;
+  for (int g = 0; g < G; ++g) rprev = fmax(rprev, __ldcg(in.R + g));
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double rmax = 0.0;
   const double inv_phi = 1.0 / phi, inv_Z = 1.0 / Z;
@@ -173,6 +171,50 @@ __global__ void __launch_bounds__(SDP_THREADS) sdp_iter_kernel(const double* __r
     qu[j] = q * (gamma == 0.5 ? sqrt(r) : pow(r, gamma));
   }
   sdp_accumulate(At, qu, n, T2, rmax, parts_of(part_out, G, T2), s_w, s_r);
+  phi_out = phi;
+  return rprev;
+}
+
+__global__ void __launch_bounds__(SDP_THREADS) sdp_iter_kernel(const double* __restrict__ At, double* __restrict__ qu,
+                                                                int64_t n, int tau, double gamma, double* part_in,
+                                                                double* part_out, double* __restrict__ hist) {
+  __shared__ double s_M[SDP_T2], s_P[SDP_T2];
+  __shared__ double s_w[SDP_THREADS / 32][SDP_T2];
+  __shared__ double s_r[16];
+  double phi;
+  const double rprev = sdp_iterate(At, qu, n, tau, gamma, part_in, part_out, s_M, s_P, s_w, s_r, phi);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    hist[0] = phi;            // phi(q_it)
+    hist[1] = rprev;          // max_i d_i / phi of the PREVIOUS iterate (0 before the first update)
+  }
+}
+
+// The whole loop in ONE cooperative launch: a grid-wide barrier between iterations instead of a kernel boundary
+// (the loop is latency-bound: ~20 us per iteration as separate launches).  Every CTA sees the same partial sums, so
+// the stopping decision is uniform.  hist = {phi, previous ratio, iterations done}.
+__global__ void __launch_bounds__(SDP_THREADS) sdp_loop_kernel(const double* __restrict__ At, double* __restrict__ qu,
+                                                                int64_t n, int tau, double gamma, double tol,
+                                                                long long max_iter, double* part0, double* part1,
+                                                                double* __restrict__ hist) {
+  __shared__ double s_M[SDP_T2], s_P[SDP_T2];
+  __shared__ double s_w[SDP_THREADS / 32][SDP_T2];
+  __shared__ double s_r[16];
+  cg::grid_group grid = cg::this_grid();
+  long long it = 0;
+  double phi = 0.0, rprev = 0.0;
+  for (; it < max_iter; ++it) {
+    double* pin = (it & 1) ? part1 : part0;
+    double* pout = (it & 1) ? part0 : part1;
+    rprev = sdp_iterate(At, qu, n, tau, gamma, pin, pout, s_M, s_P, s_w, s_r, phi);
+    grid.sync();
+    if (!(phi == phi) || phi <= 0.0) { ++it; break; }              // not positive definite: reported by the host
+    if (it >= 1 && rprev - 1.0 <= tol) { ++it; break; }            // the iterate before this update was already certified
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    hist[0] = phi;
+    hist[1] = rprev;
+    hist[2] = (double)it;
+  }
 }
 
 // single CTA: normalised q, t_j = (M^-1)_jj, phi and the certificate max_i d_i / phi - 1 of the RETURNED q
@@ -233,12 +275,12 @@ extern "C" int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64
   NNAL_TRY(devbuf_reserve(ctx, st->qu, (size_t)n * 8 * 2));           // unnormalised weights, then the normalised result
   NNAL_TRY(devbuf_reserve(ctx, st->part[0], part_doubles * 8));
   NNAL_TRY(devbuf_reserve(ctx, st->part[1], part_doubles * 8));
-  NNAL_TRY(devbuf_reserve(ctx, st->out, (size_t)(4 + SDP_MAX_TAU) * 8));
+  NNAL_TRY(devbuf_reserve(ctx, st->out, (size_t)(8 + SDP_MAX_TAU) * 8));
   double* At = (double*)st->At.p;
   double* qu = (double*)st->qu.p;
   double* qn = qu + n;
-  double* hist = (double*)st->out.p;         // [0..1] per-iteration record, [2..] result of the final kernel
-  double* res = hist + 2;
+  double* hist = (double*)st->out.p;         // [0..2] loop record, [4..] result of the final kernel
+  double* res = hist + 4;
   CUDA_TRY(ctx, cudaMemcpyAsync(st->stage.p, A, (size_t)n * T2 * 8, cudaMemcpyHostToDevice, ctx->stream));
   const int tg = (int)std::min<int64_t>((n * T2 + 255) / 256, (int64_t)ctx->sm_count * 8);
   sdp_transpose_kernel<<<tg, 256, 0, ctx->stream>>>((const double*)st->stage.p, At, n, T2);
@@ -247,9 +289,38 @@ extern "C" int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64
   sdp_init_kernel<<<G, SDP_THREADS, 0, ctx->stream>>>(At, qu, n, tau, (double*)st->part[cur].p);
   ctx->launches += 3;
   CUDA_TRY(ctx, cudaGetLastError());
-  const int64_t check_every = 32;
   int64_t it = 0;
-  while (it < max_iter) {
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+  static const bool no_coop = getenv("NNAL_SDP_NO_COOP") != nullptr;
+  bool done = false;
+  if (coop && !no_coop) {
+    const double* a_At = At;
+    double* a_qu = qu;
+    int64_t a_n = n;
+    int a_tau = tau;
+    double a_gamma = gamma, a_tol = tol;
+    long long a_max = (long long)max_iter;
+    double* a_p0 = (double*)st->part[0].p;
+    double* a_p1 = (double*)st->part[1].p;
+    double* a_hist = hist;
+    void* args[] = {&a_At, &a_qu, &a_n, &a_tau, &a_gamma, &a_tol, &a_max, &a_p0, &a_p1, &a_hist};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)sdp_loop_kernel, dim3(G), dim3(SDP_THREADS), args, 0, ctx->stream);
+    if (e == cudaSuccess) {
+      ctx->launches++;
+      double h[3];
+      CUDA_TRY(ctx, cudaMemcpyAsync(h, hist, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      if (!(h[0] == h[0]) || h[0] <= 0.0) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "SDP: sum_i q_i A_i is not positive definite");
+      it = (int64_t)h[2];
+      cur = (int)(it & 1);
+      done = true;
+    } else {
+      cudaGetLastError();            // cooperative launch refused (grid not co-resident): one launch per iteration instead
+    }
+  }
+  const int64_t check_every = 32;
+  while (!done && it < max_iter) {
     const int64_t stop = std::min(max_iter, it + check_every);
     for (; it < stop; ++it) {
       sdp_iter_kernel<<<G, SDP_THREADS, 0, ctx->stream>>>(At, qu, n, tau, gamma, (double*)st->part[cur].p,

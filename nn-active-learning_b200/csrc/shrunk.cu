@@ -384,6 +384,7 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
     const Layer& L = ctx->layers[i];
     elems[i] = L.type == NNAL_LAYER_FC ? L.out_dim : (int64_t)L.out_h * L.out_w * L.out_c;
     offs[i] = tot;
+    if (L.type == NNAL_LAYER_CONV) mx = std::max(mx, (int64_t)L.in_h * L.in_w * ((L.in_c + 7) / 8 * 8));   // padded operand planes
     tot += (elems[i] * nb + 63) / 64 * 64;          // 256-byte aligned blocks: the fc kernels read rows as float4
     mx = std::max(mx, elems[i]);
   }
@@ -395,6 +396,8 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
   NNAL_TRY(devbuf_reserve(ctx, st->sred, (size_t)nb * tau * sizeof(double)));
   float* acts = (float*)st->acts.p;
   auto in_of = [&](int i) -> const float* { return i == 0 ? (const float*)ctx->xin.p : acts + offs[i - 1]; };
+  static const bool simt_fwd = getenv("NNAL_BW_SIMT_FWD") != nullptr;
+  prof_begin(ctx, NNAL_PROF_BW_FORWARD);
   for (int i = 0; i < nl; ++i) {
     const Layer& L = ctx->layers[i];
     if (!L.has_weights && L.type != NNAL_LAYER_POOL) NNAL_FAIL(ctx, NNAL_ERR_STATE, "layer weights not set");
@@ -402,7 +405,21 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
     if (i == nl - 1) {
       NNAL_TRY(nnal_k_head(ctx, L, in_of(i), nb, nb, 0, (float*)st->post.p, nullptr));
     } else if (L.type == NNAL_LAYER_CONV) {
-      NNAL_TRY(nnal_k_conv_simt(ctx, L, in_of(i), out, nb));
+      if (!simt_fwd && nnal_layer_on_tc(ctx, i)) {
+        // tcgen05 conv kernels (unfused: the pre-pool activations are needed by the backward pass); the gradient
+        // buffers are idle during the forward pass and hold the fp16 hi/lo operand planes
+        const int cp = (L.in_c + 7) / 8 * 8;
+        const int64_t iep = nb * (int64_t)L.in_h * L.in_w * cp, oe = nb * elems[i];
+        nnal_h* ih = (nnal_h*)st->g[0].p;
+        nnal_h* oh = (nnal_h*)st->g[1].p;
+        NNAL_TRY(nnal_k_split_pad(ctx, in_of(i), ih, ih + iep, nb * (int64_t)L.in_h * L.in_w, L.in_c, cp));
+        const bool wt = ctx->use_wt >= 3 ? nnal_wt_conv_supported(ctx, L) : ctx->use_wt >= 1 && nnal_wt_conv_preferred(ctx, L);
+        if (wt) NNAL_TRY(nnal_wt_conv(ctx, L, ih, ih + iep, oh, oh + oe, nb, 0));
+        else NNAL_TRY(nnal_tc_conv(ctx, L, ih, ih + iep, oh, oh + oe, nb));
+        NNAL_TRY(nnal_k_merge_flat(ctx, oh, oh + oe, out, oe));
+      } else {
+        NNAL_TRY(nnal_k_conv_simt(ctx, L, in_of(i), out, nb));
+      }
     } else if (L.type == NNAL_LAYER_POOL) {
       NNAL_TRY(nnal_k_pool(ctx, L, in_of(i), out, nb));
     } else if (nnal_layer_on_tc(ctx, i)) {
@@ -411,9 +428,11 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
       NNAL_TRY(nnal_k_fc_simt(ctx, L, in_of(i), out, nb));
     }
   }
+  prof_end(ctx);
   // ---- backward: one pass of h = e_0 - e_1 (binary) or one pass per class ----
   const bool binary = c == 2;
   const int passes = binary ? 1 : c;
+  prof_begin(ctx, NNAL_PROF_BW_BACKWARD);
   double* G = (double*)st->gout.p;
   for (int y = 0; y < passes; ++y) {
     double* S = binary ? (double*)st->sred.p : G + (int64_t)y * nb * tau;
@@ -456,6 +475,7 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
     }
     CUDA_TRY(ctx, cudaGetLastError());
   }
+  prof_end(ctx);
   if (binary) {
     binary_scale_kernel<<<grid_for(ctx, nb * tau, 8), 256, 0, ctx->stream>>>((const double*)st->sred.p,
                                                                              (const float*)st->post.p, nb, tau, G);
