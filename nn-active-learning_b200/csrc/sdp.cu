@@ -75,15 +75,42 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 // M = (sum of the partial sums) / Z; in-place Gauss-Jordan inverse (M is positive definite: no pivoting); P = Minv^2.
-// All threads of the CTA call this; returns phi = tr(Minv) and Z to every thread.
-__device__ void sdp_build(const Parts in, int G, int tau, double* s_M, double* s_P, double& phi, double& Z) {
+// All threads of the CTA call this; returns phi = tr(Minv), Z and the largest ratio of the previous iterate to every
+// thread.  The G x (T2 + 2) partial values live in L2 (written by other CTAs): the reads are spread over all threads
+// -- entry e of slice s sums the CTAs g = s, s + S, ... with four loads in flight -- because G dependent L2 round
+// trips per entry were the longest stretch of an iteration.  Fixed order: every CTA gets bit-identical sums.
+__device__ void sdp_build(const Parts in, int G, int tau, double* s_M, double* s_P, double* s_part, double& phi, double& Z,
+                          double& rprev) {
   const int T2 = tau * tau, tid = threadIdx.x;
-  double z = 0.0;
-  for (int g = 0; g < G; ++g) z += __ldcg(in.Z + g);       // written by other CTAs: read through L2
+  const int NE = T2 + 2;                                   // entries: M (T2), Z, R
+  const int S = NE <= SDP_THREADS ? SDP_THREADS / NE : 1;  // slices
+  for (int e = tid % NE, sl = tid / NE; sl < S && e < NE; e += SDP_THREADS) {   // (one trip unless NE > 256)
+    const double* base = e < T2 ? in.M + e : (e == T2 ? in.Z : in.R);
+    const size_t step = e < T2 ? (size_t)T2 : 1;
+    const bool is_max = e == T2 + 1;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int g = sl;
+    for (; g + 3 * S < G; g += 4 * S) {
+      const double v0 = __ldcg(base + (size_t)g * step), v1 = __ldcg(base + (size_t)(g + S) * step);
+      const double v2 = __ldcg(base + (size_t)(g + 2 * S) * step), v3 = __ldcg(base + (size_t)(g + 3 * S) * step);
+      if (is_max) { a0 = fmax(a0, v0); a1 = fmax(a1, v1); a2 = fmax(a2, v2); a3 = fmax(a3, v3); }
+      else { a0 += v0; a1 += v1; a2 += v2; a3 += v3; }
+    }
+    for (; g < G; g += S) {
+      const double v = __ldcg(base + (size_t)g * step);
+      if (is_max) a0 = fmax(a0, v); else a0 += v;
+    }
+    s_part[sl * NE + e] = is_max ? fmax(fmax(a0, a1), fmax(a2, a3)) : (a0 + a1) + (a2 + a3);
+    if (NE <= SDP_THREADS) break;
+  }
+  __syncthreads();
+  double z = 0.0, r = 0.0;
+  for (int sl = 0; sl < S; ++sl) { z += s_part[sl * NE + T2]; r = fmax(r, s_part[sl * NE + T2 + 1]); }
   Z = z;
+  rprev = r;
   if (tid < T2) {
     double m = 0.0;
-    for (int g = 0; g < G; ++g) m += __ldcg(in.M + (size_t)g * T2 + tid);
+    for (int sl = 0; sl < S; ++sl) m += s_part[sl * NE + tid];
     s_M[tid] = m / z;
   }
   __syncthreads();
@@ -117,11 +144,27 @@ __device__ void sdp_accumulate(const double* __restrict__ At, const double* __re
                                Parts out, double (*s_w)[SDP_T2], double* s_r) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, j0 = (int64_t)blockIdx.x * blockDim.x + tid;
-  for (int ab = 0; ab < T2; ++ab) {
-    double v = 0.0;
-    for (int64_t j = j0; j < n; j += stride) v += qu[j] * At[(int64_t)ab * n + j];
-    v = warp_sum(v);
-    if (lane == 0) s_w[w][ab] = v;
+  // eight entries at a time: their shuffle chains are independent, so the reduction is issue-bound, not latency-bound
+  for (int ab0 = 0; ab0 < T2; ab0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = 0.0;
+    for (int64_t j = j0; j < n; j += stride) {
+      const double q = qu[j];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (ab0 + u < T2) v[u] += q * At[(int64_t)(ab0 + u) * n + j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] += __shfl_down_sync(0xffffffffu, v[u], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (ab0 + u < T2) s_w[w][ab0 + u] = v[u];
+    }
   }
   double z = 0.0;
   for (int64_t j = j0; j < n; j += stride) z += qu[j];
@@ -155,15 +198,14 @@ __device__ double sdp_iterate(const double* __restrict__ At, double* __restrict_
                               double* s_r, double& phi_out) {
   const int T2 = tau * tau, G = gridDim.x;
   const Parts in = parts_of(part_in, G, T2);
-  double phi, Z;
-  sdp_build(in, G, tau, s_M, s_P, phi, Z);
-  double rprev = 0.0;
-  for (int g = 0; g < G; ++g) rprev = fmax(rprev, __ldcg(in.R + g));
+  double phi, Z, rprev;
+  sdp_build(in, G, tau, s_M, s_P, &s_w[0][0], phi, Z, rprev);      // s_w doubles as the scratch of the partial read
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double rmax = 0.0;
   const double inv_phi = 1.0 / phi, inv_Z = 1.0 / Z;
   for (int64_t j = j0; j < n; j += stride) {
     double d = 0.0;
+#pragma unroll 7
     for (int ab = 0; ab < T2; ++ab) d += s_P[ab] * At[(int64_t)ab * n + j];
     const double r = d * inv_phi;
     const double q = qu[j] * inv_Z;
@@ -221,11 +263,11 @@ __global__ void __launch_bounds__(SDP_THREADS) sdp_loop_kernel(const double* __r
 __global__ void __launch_bounds__(SDP_THREADS) sdp_final_kernel(const double* __restrict__ At, const double* __restrict__ qu,
                                                                  int64_t n, int tau, int G, double* part_in,
                                                                  double* __restrict__ q_out, double* __restrict__ res) {
-  __shared__ double s_M[SDP_T2], s_P[SDP_T2];
+  __shared__ double s_M[SDP_T2], s_P[SDP_T2], s_part[SDP_T2 + 2 + SDP_THREADS];
   __shared__ double s_r[8];
   const int T2 = tau * tau;
-  double phi, Z;
-  sdp_build(parts_of(part_in, G, T2), G, tau, s_M, s_P, phi, Z);
+  double phi, Z, rprev;
+  sdp_build(parts_of(part_in, G, T2), G, tau, s_M, s_P, s_part, phi, Z, rprev);
   double rmax = 0.0;
   for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
     double d = 0.0;

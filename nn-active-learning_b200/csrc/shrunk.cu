@@ -85,7 +85,8 @@ __global__ void pool_bwd_kernel(const float* __restrict__ d_out, const float* __
 // ---- conv data gradient: d_in[y][x][ci] = sum_{dy,dx,co} dz[y-dy+ph][x-dx+pw][co] W[dy][dx][ci][co] ------------------
 // One CTA per sample; dz is staged zero-padded in shared memory so that the flipped tap (dy',dx') = (kh-1-dy, kw-1-dx)
 // reads padded position (y+dy', x+dx').  A thread owns TC input channels x TP positions and walks co four at a time.
-template <int TP, int TC>
+// WS: the whole filter is staged in shared memory behind the tile (once per CTA); otherwise it is read through L2.
+template <int TP, int TC, bool WS>
 __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restrict__ dz, const float* __restrict__ Wt,
                                                              float* __restrict__ d_in, int64_t n, int H, int Wd, int Cin,
                                                              int Cout, int kh, int kw) {
@@ -100,6 +101,11 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restr
   const int ci0 = cg * TC;
   const int HW = H * Wd;
   const bool vec = (Cout % 4) == 0;
+  float* s_w = s_dz + (Hp * Wp * Cout + 3) / 4 * 4;
+  if (WS) {
+    for (int e = tid; e < kh * kw * Cin * Cout; e += blockDim.x) s_w[e] = Wt[e];
+  }
+  const float* wbase = WS ? s_w : Wt;
   for (int64_t s = blockIdx.x; s < n; s += gridDim.x) {
     const float* src = dz + s * (int64_t)HW * Cout;
     for (int e = tid; e < Hp * Wp * Cout; e += blockDim.x) {
@@ -125,14 +131,15 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restr
           for (int fx = 0; fx < kw; ++fx) {
             const int toff = (fy * Wp + fx) * Cout;
             const int tap = (kh - 1 - fy) * kw + (kw - 1 - fx);
-            const float* wtap = Wt + (int64_t)tap * Cin * Cout;
+            const float* wtap = wbase + (int64_t)tap * Cin * Cout;
             if (vec) {
               for (int co = 0; co < Cout; co += 4) {
                 float4 w[TC];
 #pragma unroll
                 for (int c = 0; c < TC; ++c)
-                  w[c] = (ci0 + c < Cin) ? __ldg(reinterpret_cast<const float4*>(wtap + (int64_t)(ci0 + c) * Cout + co))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                  w[c] = (ci0 + c >= Cin) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                         : WS   ? *reinterpret_cast<const float4*>(wtap + (ci0 + c) * Cout + co)
+                                : __ldg(reinterpret_cast<const float4*>(wtap + (int64_t)(ci0 + c) * Cout + co));
 #pragma unroll
                 for (int t = 0; t < TP; ++t) {
                   const float4 a = *reinterpret_cast<const float4*>(&s_dz[off[t] + toff + co]);
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restr
               for (int co = 0; co < Cout; ++co) {
                 float w[TC];
 #pragma unroll
-                for (int c = 0; c < TC; ++c) w[c] = (ci0 + c < Cin) ? __ldg(wtap + (int64_t)(ci0 + c) * Cout + co) : 0.f;
+                for (int c = 0; c < TC; ++c) w[c] = (ci0 + c >= Cin) ? 0.f : WS ? wtap[(ci0 + c) * Cout + co] : __ldg(wtap + (int64_t)(ci0 + c) * Cout + co);
 #pragma unroll
                 for (int t = 0; t < TP; ++t) {
                   const float a = s_dz[off[t] + toff + co];
@@ -174,24 +181,48 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restr
   }
 }
 
-int conv_bwd_data(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int64_t n) {
-  if (n == 0) return NNAL_OK;
-  const size_t smem = (size_t)(L.in_h + L.kh - 1) * (L.in_w + L.kw - 1) * L.out_c * sizeof(float);
-  if (smem > 200 * 1024) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient tile exceeds shared memory");
-  const int grid = (int)std::min<int64_t>(n, (int64_t)ctx->sm_count * 8);
-  if (L.in_c % 4 == 0 && L.in_c / 4 <= 256) {
-    auto k = conv_bwd_data_kernel<4, 4>;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, ctx->stream>>>(dz, L.W, d_in, n, L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw);
-  } else {
-    if (L.in_c > 256) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient: more than 256 input channels");
-    auto k = conv_bwd_data_kernel<4, 1>;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, ctx->stream>>>(dz, L.W, d_in, n, L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw);
-  }
+template <int TP, int TC, bool WS>
+int conv_bwd_launch(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int64_t n, size_t smem) {
+  auto k = conv_bwd_data_kernel<TP, TC, WS>;
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 256, smem));
+  // persistent CTAs: the staged filter (WS) is amortised over the CTA's samples
+  const int grid = (int)std::min<int64_t>(n, (int64_t)ctx->sm_count * std::max(1, per_sm));
+  k<<<grid, 256, smem, ctx->stream>>>(dz, L.W, d_in, n, L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
+}
+
+// Positions per thread (TP).  Filter in shared memory (conv2, conv3 of PW1): 4 / 6 / 8 positions, several passes over the
+// raster if needed.  Filter too large for shared memory next to the dz tile (conv4: 166 KB + 86 KB): it is read through
+// L2 once per TP x TC x 4 multiply-adds, so TP is as large as one pass over the raster allows, ceil(H*W / position
+// groups) -- conv4: 21 groups x 9 = 189 slots for 169 positions.
+template <int TC>
+int conv_bwd_pick(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int64_t n) {
+  const int groups = (L.in_c + TC - 1) / TC, PG = 256 / groups;
+  const int need = (L.in_h * L.in_w + PG - 1) / PG;
+  const size_t tile = ((size_t)(L.in_h + L.kh - 1) * (L.in_w + L.kw - 1) * L.out_c + 3) / 4 * 4 * sizeof(float);
+  const size_t wbytes = (size_t)L.kh * L.kw * L.in_c * L.out_c * sizeof(float);
+  if (tile > 200 * 1024) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient tile exceeds shared memory");
+  static const bool no_ws = getenv("NNAL_BW_NO_WS") != nullptr;
+  if (!no_ws && tile + wbytes <= 200 * 1024) {
+    if (need <= 4) return conv_bwd_launch<4, TC, true>(ctx, L, dz, d_in, n, tile + wbytes);
+    if (need <= 6) return conv_bwd_launch<6, TC, true>(ctx, L, dz, d_in, n, tile + wbytes);
+    return conv_bwd_launch<8, TC, true>(ctx, L, dz, d_in, n, tile + wbytes);
+  }
+  if (need <= 4) return conv_bwd_launch<4, TC, false>(ctx, L, dz, d_in, n, tile);
+  if (need <= 6) return conv_bwd_launch<6, TC, false>(ctx, L, dz, d_in, n, tile);
+  if (need <= 9) return conv_bwd_launch<9, TC, false>(ctx, L, dz, d_in, n, tile);
+  return conv_bwd_launch<12, TC, false>(ctx, L, dz, d_in, n, tile);
+}
+
+int conv_bwd_data(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int64_t n) {
+  if (n == 0) return NNAL_OK;
+  if (L.in_c > 256) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient: more than 256 input channels");
+  if (L.in_c % 4 == 0) return conv_bwd_pick<4>(ctx, L, dz, d_in, n);
+  return conv_bwd_pick<1>(ctx, L, dz, d_in, n);
 }
 
 // ---- fc data gradient: d[M][N] = dz[M][K] . W[K][N]  (W = the layer's [out][in] weight, read as stored) -------------

@@ -57,6 +57,11 @@ def run(rank, world, out):
     expr.pars['B'] = 10 ** 6                 # no pre-filter: every rank's whole block is a candidate
     q, obj = nnal_b200.fi.query_single(expr, model, None, allp[0][:m], pool0, return_objective=True)
     res['fi_all'], res['fi_all_obj'] = q, obj
+    # the reference's literal FI pipeline (shrunk A-matrices -> SDP -> sampling): every rank evaluates the same B
+    # candidates, rank 0's draw is broadcast
+    expr.pars.update(B=30, fi_mode='sdp', fi_diag_load=1e-3)
+    np.random.seed(1000 + rank)              # different generator states per rank: the broadcast must reconcile them
+    res['fi_sdp_single'] = nnal_b200.PW_NNAL.CNN_query(expr, model, None, allp[0][:m], pool0, None, 'fi')
     # multi-volume queries
     expr = Expr()
     expr.pars = dict(k=11, B=40, lambda_=0., patch_shape=ps, ntb=16, SDP_solver='CVXOPT', fi_layers=2)
@@ -72,6 +77,12 @@ def run(rank, world, out):
     for s in range(len(Q)):
         res['fi_multi%d' % s] = np.asarray(Q[s])
     res['fi_multi_obj'] = obj
+    expr.pars['fi_mode'] = 'sdp'
+    np.random.seed(2000 + rank)
+    Q = nnal_b200.PW_NNAL.query_multimg(expr, model, None, allp, pools, None, 'fi')
+    for s in range(len(Q)):
+        res['fi_sdp_multi%d' % s] = np.asarray(Q[s])
+    del expr.pars['fi_mode']
     # MC-dropout and committee queries (masks keyed by GLOBAL pool position: identical for every world size)
     mcm = nnal_b200.NN.CNN((5, 5, m), ld, feature_layer=len(layers) - 2, dropout=[[2, 3, 4], 0.6])
     mcm.set_weights(w)

@@ -422,6 +422,22 @@ class FakeEngine(object):
     def fi_result(self, k):
         return np.array(self._sel[:k], dtype=np.int64), np.array(self._red[:k])
 
+    # -- the reference's literal FI pipeline (shrunk gradients + SDP), through the float64 oracle ------------
+    def fi_shrunk_tau(self):
+        return sum(1 for _, sp in self.layers if sp[1] != 'pool')
+
+    def fi_shrunk_images(self, x):
+        post, g = O.shrunk_class_gradients(self.layers, self.weights, np.asarray(x, dtype=np.float32))
+        return post.astype(np.float32), g
+
+    def fi_shrunk_voxels(self, subject, inds, patch_shape, stats, norm_mode=1, shape=None):
+        x = O.normalize_batch_eval(O.get_patches(self.vols[subject], np.asarray(inds), patch_shape), stats)
+        return self.fi_shrunk_images(x.astype(np.float32))
+
+    def sdp_query_distribution(self, A, tol=1e-4, max_iter=200000, gamma=0.5):
+        q, t, phi, gap, it = O.sdp_solve(np.asarray(A), tol, max_iter, gamma)
+        return {'q': q, 't': t, 'objective': phi, 'gap': gap, 'iterations': it}
+
     def fi_greedy(self, k, delta):
         k = int(min(k, len(self.fi_p1)))
         self.fi_begin(max(k, 1), delta)
