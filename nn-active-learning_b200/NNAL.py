@@ -32,7 +32,8 @@ def CNN_query(model, expr, pool_inds, method_name, session, col=True, extra_feed
     """NNAL.CNN_query (NNAL.py:188-525): returns positions into ``pool_inds``.
 
     ``entropy``: posteriors ``[c,n]`` -> compute_entropy (zeros -> 1e-7) -> argsort(-H)[:k]
-    (NNAL.py:298-310).  ``fi``: see ``nnal_b200.fi.query_whole``."""
+    (NNAL.py:298-310).  ``fi``: see ``nnal_b200.fi.query_whole``; ``expr.pars['fi_mode'] = 'sdp'`` runs the reference's
+    own multiclass A-matrix + SDP + sampling pipeline (``nnal_b200.fi.query_whole_sdp``)."""
     k = expr.pars['k']
     if method_name == 'random':
         return np.random.permutation(len(pool_inds))[:k]
@@ -46,6 +47,8 @@ def CNN_query(model, expr, pool_inds, method_name, session, col=True, extra_feed
         return q
     if method_name == 'fi':
         from . import fi
+        if expr.pars.get('fi_mode', 'greedy') == 'sdp':
+            return fi.query_whole_sdp(model, expr, pool_inds, session)
         return fi.query_whole(model, expr, pool_inds, session)
     if method_name == 'rep-entropy':
         from . import rep

@@ -218,6 +218,57 @@ def query_multimg_sdp(expr, model, sess, all_padded_imgs, pool_inds, return_solu
     return (Q, soln, G) if return_solution else Q
 
 
+def _A_multiclass_from_shrunk(sel_posteriors, g):
+    """The multiclass A-matrix assembly inlined in NNAL.CNN_query (NNAL.py:354-414) from shrunk gradients ``g``
+    [c,B,tau]: posteriors < 1e-6 zeroed IN PLACE (:361-362), the rest renormalised, all classes if fewer than 10 are
+    non-zero else the 10 largest renormalised again (:379-400), ``A_i = sum_j [g_j g_j^T / p_j + 1e-5 I]`` -- the
+    diagonal load once PER CLASS, as written (:404-409)."""
+    c, B = sel_posteriors.shape
+    tau = g.shape[2]
+    A = []
+    for i in range(B):
+        x_posterior = sel_posteriors[:, i]
+        x_posterior[x_posterior < 1e-6] = 0.
+        nz_classes = np.where(x_posterior > 0.)[0]
+        nz_posts = x_posterior[nz_classes] / np.sum(x_posterior[nz_classes])
+        if len(nz_classes) < 10:
+            sel_classes, new_posts = nz_classes, nz_posts
+        else:
+            sel_nz = np.argsort(-nz_posts, kind='stable')[:10]
+            sel_classes = nz_classes[sel_nz]
+            new_posts = nz_posts[sel_nz]
+            new_posts = new_posts / np.sum(new_posts)
+        Ai = np.zeros((tau, tau))
+        for j in range(len(sel_classes)):
+            sg = g[sel_classes[j], i]
+            Ai += np.outer(sg, sg) / new_posts[j] + np.eye(tau) * 1e-5
+        A += [Ai]
+    return A
+
+
+def query_whole_sdp(model, expr, pool_inds, session, return_solution=False):
+    """``NNAL.CNN_query(..., 'fi')`` as the reference runs it (NNAL.py:312-464) with ``lambda_ = 0``: posteriors ->
+    ``uncertainty_filtering`` to B (:326-333) -> per-sample multiclass A-matrices in shrunk coordinates (:354-414; the
+    per-class ``session.run(model.grad_posts[y])`` calls are one batched backward pass per class on the device) -> SDP
+    query distribution (:456-459) -> ``sample_query_dstr`` (:462-464).  Positions into ``pool_inds``."""
+    from .NNAL import _pool_images, _posteriors_on_device
+    B = int(expr.pars['B'])
+    pool_inds = np.asarray(pool_inds)
+    n = len(pool_inds)
+    eng, lo, hi = _posteriors_on_device(model, expr, pool_inds, session, keep=0)
+    if B < n:
+        eng.pool_score(L.SCORE_NEG_ENTROPY, 1e-8)
+        idx, sc = eng.pool_topk(B, with_scores=True)
+        sel_inds, _ = dist.allgather_topk(sc, idx + lo, B)
+    else:
+        sel_inds = np.arange(n, dtype=np.int64)
+    post, g = eng.fi_shrunk_images(_pool_images(expr, pool_inds[sel_inds]))
+    A = _A_multiclass_from_shrunk(post.astype(np.float64), g)
+    Q_inds, soln = _sdp_sample(A, expr, return_solution)
+    q = sel_inds[Q_inds]
+    return (q, soln, sel_inds) if return_solution else q
+
+
 def query_whole(model, expr, pool_inds, session):
     """``NNAL.CNN_query(..., 'fi')`` (NNAL.py:312-464).  Binary models: uncertainty pre-filter to B
     (entropy, NNAL_tools.uncertainty_filtering) + last-layer factored greedy.  c > 2: the k pool

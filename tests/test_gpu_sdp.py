@@ -231,3 +231,35 @@ def test_pw_fi_query_sdp_multimg(nb):
     draws = O.sample_query_dstr(q_dev.copy(), k, u)
     want = O.global2local_inds(G[draws], sizes)
     assert all(np.array_equal(np.sort(a), np.sort(b)) for a, b in zip(Q, want))
+
+
+def test_whole_image_fi_query_sdp_multiclass(nb):
+    """NNAL.CNN_query(..., 'fi') with fi_mode='sdp' on a c = 3 net (config-1 shape of the path): multiclass A-matrices
+    (NNAL.py:354-414) from one backward pass per class, SDP, sampling."""
+    rs = np.random.RandomState(21)
+    x = rs.rand(300, 9, 7, 2).astype(np.float32)
+    w = O.he_init_weights(SMALL, (9, 7, 2), 6, bias_scale=0.1)
+    model = nb.NN.CNN((9, 7, 2), OrderedDict(SMALL), feature_layer=len(SMALL) - 2)
+    model.set_weights(w)
+    k, B = 10, 60
+    expr = Expr(k=k, B=B, lambda_=0., batch_size=128, fi_mode='sdp')
+    expr.pool_images = x
+    np.random.seed(9)
+    u = np.random.sample(k)
+    np.random.seed(9)
+    q, soln, sel = nb.fi.query_whole_sdp(model, expr, np.arange(300), None, return_solution=True)
+    np.random.seed(9)
+    q2 = nb.NNAL.CNN_query(model, expr, np.arange(300), 'fi', None)
+    assert np.array_equal(q, q2) and soln['status'] == 'optimal'
+    # oracle: same candidates (entropy pre-filter, NNAL_tools.uncertainty_filtering), A-matrices, SDP objective
+    r = O.forward(SMALL, w, x)
+    sel_o = O.uncertainty_filtering(r['posteriors'].copy(), B)
+    assert set(sel.tolist()) == set(sel_o.tolist())
+    po, go = O.shrunk_class_gradients(SMALL, w, x[sel])
+    A = O.gen_A_matrices_multiclass(po.copy(), go)
+    qo, to, phio, gapo, ito = O.sdp_solve(A, 1e-4)
+    assert abs(soln['primal objective'] / phio - 1) < OBJ_RTOL
+    q_dev = np.array(soln['x'][:B])
+    phi_c, gap_c = O.sdp_certificate(A, q_dev)
+    assert abs(phi_c / phio - 1) < OBJ_RTOL
+    assert np.array_equal(q, sel[O.sample_query_dstr(q_dev.copy(), k, u)])

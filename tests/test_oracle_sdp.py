@@ -73,3 +73,15 @@ def test_query_fi_sdp_single_small_pool():
     q, det = O.query_fi_sdp_single(layers, w, padded, pool, ps, 16, stats, 4, 10, u)
     assert len(q) <= 4 and len(np.unique(q)) == len(q) and np.all(np.isin(q, det['sel']))
     assert det['gap'] <= 1e-4 and len(det['A']) == 10 and det['A'][0].shape == (7, 7)
+
+
+def test_multiclass_A_assembly_matches_oracle():
+    from nnal_b200.fi import _A_multiclass_from_shrunk
+    rs = np.random.RandomState(6)
+    c, B, tau = 12, 25, 5
+    g = rs.randn(c, B, tau) * .01
+    post = rs.dirichlet(np.ones(c) * .3, B).T.copy()
+    post[:, 0] = 0.; post[3, 0] = 1.                     # one-hot posterior: a single class survives
+    Ao = O.gen_A_matrices_multiclass(post.copy(), g)
+    Ah = _A_multiclass_from_shrunk(post.copy(), g)
+    assert all(np.array_equal(a, b) for a, b in zip(Ah, Ao))
