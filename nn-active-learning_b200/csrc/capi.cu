@@ -153,6 +153,7 @@ extern "C" int nnal_model_set(nnal_ctx* ctx, const nnal_layer_spec* specs, int n
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   free_layers(ctx);
+  ctx->weights_version++;
   ctx->in_h = in_h; ctx->in_w = in_w; ctx->in_c = in_c;
   int H = in_h, W = in_w, C = in_c;
   int flat = 0;            // >0 once flattened: current vector length
@@ -241,6 +242,7 @@ extern "C" int nnal_model_set_weights(nnal_ctx* ctx, int layer, const float* W, 
     CUDA_TRY(ctx, cudaMemcpyAsync(L.W, W, wn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   }
   L.has_weights = true;
+  ctx->weights_version++;
   nnal_set_weight_scale(L, W, wn);
   NNAL_TRY(nnal_tc_prepare_layer(ctx, L));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

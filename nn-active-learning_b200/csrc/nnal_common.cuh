@@ -113,6 +113,7 @@ struct nnal_ctx {
   void* tc_state = nullptr;              // tensor-map cache etc. (gemm_tc.cu)
   void* sims_state = nullptr;            // representativeness queries (sims.cu)
   void* fi_state = nullptr;              // Fisher-information candidate set / greedy state (fi.cu)
+  unsigned long long weights_version = 0; // bumped by nnal_model_set / nnal_model_set_weights: derived weight copies (shrunk.cu) are rebuilt
   void* bw_state = nullptr;              // shrunk class-score gradients: kept activations and gradient buffers (shrunk.cu)
   void* sdp_state = nullptr;             // query-distribution solver workspaces (sdp.cu)
   // MC-dropout (MC-entropy / BALD): T stochastic passes of the FC tail per chunk, running means per pool sample

@@ -14,14 +14,26 @@
 // pass, d log p_0 = p_1 h, d log p_1 = -p_0 h with h = d(z_0 - z_1), and shrink_gradient is linear, so one pass serves both.
 #include "nnal_common.cuh"
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 bool nnal_layer_on_tc(const nnal_ctx* ctx, int i);
 
 namespace {
 
+// transposed fp16 hi/lo planes [in][Kp(out)] of an fc weight: the B operand of the tensor-core data-gradient GEMM
+struct TWeight {
+  nnal_h* h = nullptr;
+  nnal_h* l = nullptr;
+  int Kp = 0;
+};
+
 struct BwState {
-  DevBuf acts, g[2], post, gout, sred;
+  DevBuf acts, g[2], post, gout, sred, amax;
+  std::vector<TWeight> wt;
+  unsigned long long wt_version = ~0ull;
 };
 
 BwState* bw_state(nnal_ctx* ctx) {
@@ -317,6 +329,123 @@ int fc_bwd_data(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int
   return NNAL_OK;
 }
 
+// ---- fc data gradient on the tensor cores -----------------------------------------------------------------------
+// d = dz . W as the split-plane GEMM of the forward pass (gemm_tc.cu): A = dz in fp16 hi/lo planes, B = W^T planes
+// (built once per weight set).  Gradients are small and span many binades, so dz is first multiplied by the power of
+// two that lifts its largest magnitude to [2^13, 2^14): every entry then carries an absolute error below 2^-39 of the
+// largest one, and entries within 2^-17 of it keep 22 significant bits -- the same footing as the weights.
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t count, unsigned int* __restrict__ out) {
+  unsigned int m = 0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned int b = __float_as_uint(x[e]) & 0x7fffffffu;      // |x| as an order-preserving integer
+    if (b < 0x7f800000u && b > m) m = b;                              // finite values only
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// fp32 [rows][K] * scale -> fp16 hi/lo planes [rows][Kp] (zero-padded columns)
+__global__ void __launch_bounds__(256) bw_split_kernel(const float* __restrict__ in, nnal_h* __restrict__ hi,
+                                                        nnal_h* __restrict__ lo, int64_t rows, int K, int Kp, float scale) {
+  const int64_t total = rows * (int64_t)(Kp / 2);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / (Kp / 2);
+    const int c = (int)(e - r * (Kp / 2)) * 2;
+    const float x0 = c < K ? in[r * K + c] * scale : 0.f;
+    const float x1 = c + 1 < K ? in[r * K + c + 1] * scale : 0.f;
+    nnal_h h0, h1, l0, l1;
+    nnal_split(x0, h0, l0);
+    nnal_split(x1, h1, l1);
+    *reinterpret_cast<uint32_t*>(hi + r * Kp + c) = nnal_pack2(h0, h1);
+    *reinterpret_cast<uint32_t*>(lo + r * Kp + c) = nnal_pack2(l0, l1);
+  }
+}
+
+// W fp32 [out][in] * scale -> planes of W^T: [in][Kp], Kp >= out (one-off per weight set)
+__global__ void __launch_bounds__(256) bw_split_transposed_kernel(const float* __restrict__ W, nnal_h* __restrict__ hi,
+                                                                   nnal_h* __restrict__ lo, int out_dim, int in_dim, int Kp,
+                                                                   float scale) {
+  const int64_t total = (int64_t)in_dim * Kp;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / Kp;
+    const int o = (int)(e - i * Kp);
+    const float x = o < out_dim ? W[(int64_t)o * in_dim + i] * scale : 0.f;
+    nnal_h h, l;
+    nnal_split(x, h, l);
+    hi[e] = h;
+    lo[e] = l;
+  }
+}
+
+bool fc_bwd_tc_eligible(const nnal_ctx* ctx, const Layer& L) {
+  static const bool off = getenv("NNAL_BW_NO_TC") != nullptr;
+  return !off && ctx->use_tc && L.type == NNAL_LAYER_FC && L.out_dim >= 64 && L.in_dim >= 64 && L.out_dim % 8 == 0 &&
+         L.in_dim % 8 == 0;
+}
+
+void free_transposed(BwState* st) {
+  for (auto& t : st->wt) { if (t.h) cudaFree(t.h); if (t.l) cudaFree(t.l); }
+  st->wt.clear();
+}
+
+int ensure_transposed(nnal_ctx* ctx, BwState* st) {
+  if (st->wt_version == ctx->weights_version && st->wt.size() == ctx->layers.size()) return NNAL_OK;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  free_transposed(st);
+  st->wt.resize(ctx->layers.size());
+  for (size_t i = 1; i < ctx->layers.size(); ++i) {        // layer 0 needs no data gradient
+    const Layer& L = ctx->layers[i];
+    if (!fc_bwd_tc_eligible(ctx, L) || !L.has_weights) continue;
+    TWeight& t = st->wt[i];
+    t.Kp = (L.out_dim + 63) / 64 * 64;
+    const size_t bytes = (size_t)L.in_dim * t.Kp * sizeof(nnal_h);
+    CUDA_TRY(ctx, cudaMalloc(&t.h, bytes));
+    CUDA_TRY(ctx, cudaMalloc(&t.l, bytes));
+    const int64_t total = (int64_t)L.in_dim * t.Kp;
+    bw_split_transposed_kernel<<<grid_for(ctx, total, 16), 256, 0, ctx->stream>>>(L.W, t.h, t.l, L.out_dim, L.in_dim, t.Kp,
+                                                                                  L.w_scale);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
+  st->wt_version = ctx->weights_version;
+  return NNAL_OK;
+}
+
+int fc_bwd_data_tc(nnal_ctx* ctx, BwState* st, const Layer& L, const TWeight& t, const float* dz, float* d_in, int64_t n) {
+  NNAL_TRY(devbuf_reserve(ctx, st->amax, 256));
+  unsigned int* d_max = (unsigned int*)st->amax.p;
+  CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, 4, ctx->stream));
+  const int64_t cnt = n * L.out_dim;
+  absmax_kernel<<<grid_for(ctx, cnt, 8), 256, 0, ctx->stream>>>(dz, cnt, d_max);
+  ctx->launches++;
+  unsigned int bits = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&bits, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  float mx;
+  memcpy(&mx, &bits, 4);
+  if (!(mx > 0.f)) {                                        // all-zero gradient (every unit masked): so is the result
+    CUDA_TRY(ctx, cudaMemsetAsync(d_in, 0, (size_t)n * L.in_dim * sizeof(float), ctx->stream));
+    return NNAL_OK;
+  }
+  int ex;
+  frexpf(mx, &ex);                                          // mx = f 2^ex, f in [0.5, 1)
+  int e = 14 - ex;
+  e = std::max(-100, std::min(100, e));
+  const float s = ldexpf(1.f, e);
+  const size_t plane = (size_t)n * t.Kp * sizeof(nnal_h);
+  NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[0], plane));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[1], plane));
+  nnal_h* Ah = (nnal_h*)ctx->splitA[0].p;
+  nnal_h* Al = (nnal_h*)ctx->splitA[1].p;
+  bw_split_kernel<<<grid_for(ctx, n * (int64_t)(t.Kp / 2), 16), 256, 0, ctx->stream>>>(dz, Ah, Al, n, L.out_dim, t.Kp, s);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  // out[n][in] = (1 / (s w_scale)) A[n][out] . B[in][out]^T
+  return nnal_tc_gemm_planes(ctx, Ah, Al, t.Kp, n, t.h, t.l, t.Kp, L.in_dim, L.out_dim, nullptr,
+                             ldexpf(1.f, -e) * L.w_scale_inv, 0, 0, d_in, L.in_dim, nullptr, nullptr, 0);
+}
+
 // ---- block reduction in float64 ----------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -460,6 +589,7 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
     }
   }
   prof_end(ctx);
+  NNAL_TRY(ensure_transposed(ctx, st));
   // ---- backward: one pass of h = e_0 - e_1 (binary) or one pass per class ----
   const bool binary = c == 2;
   const int passes = binary ? 1 : c;
@@ -492,7 +622,11 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
         const double inv = 1.0 / ((double)L.in_dim * L.out_dim + L.out_dim);
         shrink_fc_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(d, in_of(i), L.out_dim, L.in_dim, inv, S, tau, t);
         ctx->launches++;
-        if (i > 0) { NNAL_TRY(fc_bwd_data(ctx, L, d, other, nb)); d = other; pp ^= 1; }
+        if (i > 0) {
+          if (st->wt[i].h) NNAL_TRY(fc_bwd_data_tc(ctx, st, L, st->wt[i], d, other, nb));
+          else NNAL_TRY(fc_bwd_data(ctx, L, d, other, nb));
+          d = other; pp ^= 1;
+        }
       } else {
         const double inv = 1.0 / ((double)L.kh * L.kw * L.in_c * L.out_c + L.out_c);
         const size_t sm = (size_t)(L.in_h + L.kh - 1) * (L.in_w + L.kw - 1) * sizeof(double);
@@ -535,8 +669,9 @@ int check_model(nnal_ctx* ctx) {
 int nnal_bw_release(nnal_ctx* ctx) {
   if (!ctx->bw_state) return NNAL_OK;
   BwState* st = (BwState*)ctx->bw_state;
-  DevBuf* bufs[] = {&st->acts, &st->g[0], &st->g[1], &st->post, &st->gout, &st->sred};
+  DevBuf* bufs[] = {&st->acts, &st->g[0], &st->g[1], &st->post, &st->gout, &st->sred, &st->amax};
   for (DevBuf* b : bufs) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+  free_transposed(st);
   delete st;
   ctx->bw_state = nullptr;
   return NNAL_OK;
