@@ -227,7 +227,8 @@ int nnal_fi_shrunk_voxels(nnal_ctx* ctx, int subject, const int64_t* inds, int64
 /* Replaces NNAL_tools.SDP_query_distribution with lambda_ = 0 (NNAL_tools.py:612-659; solve_FIAL_SDP :576-610):
  * minimise sum_j t_j s.t. [[sum_i q_i A_i, e_j],[e_j^T, t_j]] >= 0, q >= 0, sum q = 1, i.e. tr((sum_i q_i A_i)^-1) over the
  * simplex.  A: n symmetric positive-definite tau x tau matrices (float64 [n][tau][tau], tau <= 16).  First-order
- * multiplicative algorithm on the device, q_i <- q_i (d_i/phi)^gamma (gamma in (0,1], 0.5 is monotone), stopped at the
+ * multiplicative algorithm on the device, q_i <- q_i (d_i/phi)^gamma (gamma in (0,1]; 0.5 is monotone, a larger value is
+ * used until the objective increases once and 0.5 from then on), stopped at the
  * duality certificate max_i tr(M^-1 A_i M^-1) / tr(M^-1) - 1 <= tol or after max_iter iterations.  q_out [n];
  * t_out [tau] = diag((sum q_i A_i)^-1) (the SDP's t); *obj_out = sum_j t_j; *gap_out = the certificate of the returned q
  * (objective within gap, relative, of the optimum); any of t_out/obj_out/gap_out/iters_out may be NULL. */

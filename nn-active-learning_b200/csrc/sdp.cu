@@ -8,7 +8,8 @@
 // method factors an n x n positivity block per iteration, while phi's gradient needs only the tau x tau inverse:
 //     d_i = -d phi / d q_i = tr(M^-1 A_i M^-1) = <M^-2, A_i>,      sum_i q_i d_i = phi.
 // Solved here on the device by the multiplicative algorithm for A-optimality  q_i <- q_i (d_i / phi)^gamma / Z
-// (gamma = 1/2 decreases phi monotonically for positive semi-definite A_i).  Convexity gives the certificate
+// (gamma = 1/2 decreases phi monotonically for positive semi-definite A_i; gamma = 1 usually halves the iteration count
+// and is used until phi increases for the first time, then 1/2).  Convexity gives the certificate
 //     phi(q) - phi* <= max_i d_i - phi(q),
 // so the loop stops when max_i d_i / phi - 1 <= tol: the objective is then within tol (relative) of the SDP optimum.
 // One kernel per iteration; every CTA rebuilds M from the previous iteration's per-CTA partial sums (fixed order:
@@ -243,11 +244,15 @@ __global__ void __launch_bounds__(SDP_THREADS) sdp_loop_kernel(const double* __r
   __shared__ double s_r[16];
   cg::grid_group grid = cg::this_grid();
   long long it = 0;
-  double phi = 0.0, rprev = 0.0;
+  double phi = 0.0, rprev = 0.0, phi_prev = 1e300, g = gamma;
   for (; it < max_iter; ++it) {
     double* pin = (it & 1) ? part1 : part0;
     double* pout = (it & 1) ? part0 : part1;
-    rprev = sdp_iterate(At, qu, n, tau, gamma, pin, pout, s_M, s_P, s_w, s_r, phi);
+    rprev = sdp_iterate(At, qu, n, tau, g, pin, pout, s_M, s_P, s_w, s_r, phi);
+    // exponents above 1/2 are not guaranteed to decrease phi: the first increase switches to the monotone 1/2 for good
+    // (phi is bit-identical in every CTA, so the switch is uniform)
+    if (phi > phi_prev * (1.0 + 1e-13) && g > 0.5) g = 0.5;
+    phi_prev = phi;
     grid.sync();
     if (!(phi == phi) || phi <= 0.0) { ++it; break; }              // not positive definite: reported by the host
     if (it >= 1 && rprev - 1.0 <= tol) { ++it; break; }            // the iterate before this update was already certified
@@ -362,10 +367,11 @@ extern "C" int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64
     }
   }
   const int64_t check_every = 32;
+  double g_host = gamma, phi_last = 1e300;
   while (!done && it < max_iter) {
     const int64_t stop = std::min(max_iter, it + check_every);
     for (; it < stop; ++it) {
-      sdp_iter_kernel<<<G, SDP_THREADS, 0, ctx->stream>>>(At, qu, n, tau, gamma, (double*)st->part[cur].p,
+      sdp_iter_kernel<<<G, SDP_THREADS, 0, ctx->stream>>>(At, qu, n, tau, g_host, (double*)st->part[cur].p,
                                                           (double*)st->part[cur ^ 1].p, hist);
       cur ^= 1;
       ctx->launches++;
@@ -376,6 +382,8 @@ extern "C" int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (!(h[0] == h[0]) || h[0] <= 0.0) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "SDP: sum_i q_i A_i is not positive definite");
     if (it > 1 && h[1] - 1.0 <= tol) break;
+    if (h[0] > phi_last * (1.0 + 1e-13) && g_host > 0.5) g_host = 0.5;     // as in the cooperative loop, checked per batch
+    phi_last = h[0];
   }
   sdp_final_kernel<<<1, SDP_THREADS, 0, ctx->stream>>>(At, qu, n, tau, G, (double*)st->part[cur].p, qn, res);
   ctx->launches++;

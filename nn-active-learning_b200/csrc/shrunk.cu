@@ -98,6 +98,12 @@ __global__ void pool_bwd_kernel(const float* __restrict__ d_out, const float* __
 // One CTA per sample; dz is staged zero-padded in shared memory so that the flipped tap (dy',dx') = (kh-1-dy, kw-1-dx)
 // reads padded position (y+dy', x+dx').  A thread owns TC input channels x TP positions and walks co four at a time.
 // WS: the whole filter is staged in shared memory behind the tile (once per CTA); otherwise it is read through L2.
+// Shared-memory layout against bank conflicts (the first version spent 5x more cycles in the LSU than in the FMA pipe):
+//  * threads of a warp share the channel group and own CONSECUTIVE positions, so a filter load is one broadcast;
+//  * a tile position holds CP = Cout (+4 when Cout/4 is even) floats, so the eight 16-byte loads of a quarter-warp
+//    (consecutive positions) fall into eight different bank groups.
+__host__ __device__ inline int conv_bwd_cp(int Cout) { return (Cout % 4 == 0 && (Cout / 4) % 2 == 0) ? Cout + 4 : Cout; }
+
 template <int TP, int TC, bool WS>
 __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restrict__ dz, const float* __restrict__ Wt,
                                                              float* __restrict__ d_in, int64_t n, int H, int Wd, int Cin,
@@ -105,15 +111,16 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restr
   extern __shared__ float s_dz[];
   const int Hp = H + kh - 1, Wp = Wd + kw - 1;
   const int ph = kh / 2, pw = kw / 2;
+  const int CP = conv_bwd_cp(Cout);
   const int ci_groups = (Cin + TC - 1) / TC;
   const int PG = blockDim.x / ci_groups;
   const int tid = threadIdx.x;
-  const int cg = tid % ci_groups, pg = tid / ci_groups;
-  const bool active = pg < PG;
+  const int cg = tid / PG, pg = tid % PG;
+  const bool active = cg < ci_groups;
   const int ci0 = cg * TC;
   const int HW = H * Wd;
   const bool vec = (Cout % 4) == 0;
-  float* s_w = s_dz + (Hp * Wp * Cout + 3) / 4 * 4;
+  float* s_w = s_dz + (Hp * Wp * CP + 3) / 4 * 4;
   if (WS) {
     for (int e = tid; e < kh * kw * Cin * Cout; e += blockDim.x) s_w[e] = Wt[e];
   }
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restr
       const int co = e % Cout;
       const int t = e / Cout;
       const int xx = t % Wp - pw, yy = t / Wp - ph;
-      s_dz[e] = (xx >= 0 && xx < Wd && yy >= 0 && yy < H) ? src[((int64_t)yy * Wd + xx) * Cout + co] : 0.f;
+      s_dz[t * CP + co] = (xx >= 0 && xx < Wd && yy >= 0 && yy < H) ? src[((int64_t)yy * Wd + xx) * Cout + co] : 0.f;
     }
     __syncthreads();
     if (active) {
@@ -135,13 +142,13 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restr
         for (int t = 0; t < TP; ++t) {
           const int p = p0 + pg + t * PG;
           const int pc = p < HW ? p : 0;
-          off[t] = ((pc / Wd) * Wp + (pc % Wd)) * Cout;
+          off[t] = ((pc / Wd) * Wp + (pc % Wd)) * CP;
 #pragma unroll
           for (int c = 0; c < TC; ++c) acc[t][c] = 0.f;
         }
         for (int fy = 0; fy < kh; ++fy)
           for (int fx = 0; fx < kw; ++fx) {
-            const int toff = (fy * Wp + fx) * Cout;
+            const int toff = (fy * Wp + fx) * CP;
             const int tap = (kh - 1 - fy) * kw + (kw - 1 - fx);
             const float* wtap = wbase + (int64_t)tap * Cin * Cout;
             if (vec) {
@@ -207,32 +214,42 @@ int conv_bwd_launch(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in,
   return NNAL_OK;
 }
 
-// Positions per thread (TP).  Filter in shared memory (conv2, conv3 of PW1): 4 / 6 / 8 positions, several passes over the
-// raster if needed.  Filter too large for shared memory next to the dz tile (conv4: 166 KB + 86 KB): it is read through
-// L2 once per TP x TC x 4 multiply-adds, so TP is as large as one pass over the raster allows, ceil(H*W / position
-// groups) -- conv4: 21 groups x 9 = 189 slots for 169 positions.
+// Register tile: TC input channels x TP positions per thread; one step (tap, 4 output channels) issues TC + TP 16-byte
+// shared-memory loads for 4 TC TP multiply-adds.  Large rasters with Cin % 8 == 0 (PW1 conv2: 625 positions, 24
+// channels -> 3 groups x 85 position groups x 8 = 680 slots) take 8 x 8 (16 FMAs per load: FMA-bound); 13 x 13 rasters take
+// TC = 4 and the TP that covers the raster in one pass (conv3: 32 groups x 6 = 192 slots for 169 positions, filter in
+// shared memory; conv4: 21 x 9 = 189, filter 166 KB + tile 90 KB do not fit together: filter through L2, one
+// warp-uniform load per TP x 16 multiply-adds).
 template <int TC>
 int conv_bwd_pick(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int64_t n) {
   const int groups = (L.in_c + TC - 1) / TC, PG = 256 / groups;
   const int need = (L.in_h * L.in_w + PG - 1) / PG;
-  const size_t tile = ((size_t)(L.in_h + L.kh - 1) * (L.in_w + L.kw - 1) * L.out_c + 3) / 4 * 4 * sizeof(float);
+  const size_t tile = ((size_t)(L.in_h + L.kh - 1) * (L.in_w + L.kw - 1) * conv_bwd_cp(L.out_c) + 3) / 4 * 4 * sizeof(float);
   const size_t wbytes = (size_t)L.kh * L.kw * L.in_c * L.out_c * sizeof(float);
   if (tile > 200 * 1024) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient tile exceeds shared memory");
   static const bool no_ws = getenv("NNAL_BW_NO_WS") != nullptr;
-  if (!no_ws && tile + wbytes <= 200 * 1024) {
+  const bool ws = !no_ws && tile + wbytes <= 220 * 1024;
+  if constexpr (TC == 8) {
+    if (ws) return conv_bwd_launch<8, TC, true>(ctx, L, dz, d_in, n, tile + wbytes);
+    return conv_bwd_launch<8, TC, false>(ctx, L, dz, d_in, n, tile);
+  } else {
+  if (ws) {
     if (need <= 4) return conv_bwd_launch<4, TC, true>(ctx, L, dz, d_in, n, tile + wbytes);
     if (need <= 6) return conv_bwd_launch<6, TC, true>(ctx, L, dz, d_in, n, tile + wbytes);
-    return conv_bwd_launch<8, TC, true>(ctx, L, dz, d_in, n, tile + wbytes);
+    return conv_bwd_launch<9, TC, true>(ctx, L, dz, d_in, n, tile + wbytes);
   }
   if (need <= 4) return conv_bwd_launch<4, TC, false>(ctx, L, dz, d_in, n, tile);
   if (need <= 6) return conv_bwd_launch<6, TC, false>(ctx, L, dz, d_in, n, tile);
   if (need <= 9) return conv_bwd_launch<9, TC, false>(ctx, L, dz, d_in, n, tile);
   return conv_bwd_launch<12, TC, false>(ctx, L, dz, d_in, n, tile);
+  }
 }
 
 int conv_bwd_data(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int64_t n) {
   if (n == 0) return NNAL_OK;
   if (L.in_c > 256) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient: more than 256 input channels");
+  static const bool no_tc8 = getenv("NNAL_BW_NO_TC8") != nullptr;
+  if (!no_tc8 && L.in_c % 8 == 0 && L.in_h * L.in_w >= 400) return conv_bwd_pick<8>(ctx, L, dz, d_in, n);
   if (L.in_c % 4 == 0) return conv_bwd_pick<4>(ctx, L, dz, d_in, n);
   return conv_bwd_pick<1>(ctx, L, dz, d_in, n);
 }

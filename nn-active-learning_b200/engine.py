@@ -423,8 +423,9 @@ class Engine(object):
                                                  None if st is None else _ptr(st), int(norm_mode), _ptr(post), _ptr(g)))
         return post, g
 
-    def sdp_query_distribution(self, A, tol=1e-4, max_iter=200000, gamma=0.5):
-        """min tr((sum_i q_i A_i)^-1) over the simplex; ``A`` [n,tau,tau] float64.
+    def sdp_query_distribution(self, A, tol=1e-4, max_iter=200000, gamma=1.0):
+        """min tr((sum_i q_i A_i)^-1) over the simplex; ``A`` [n,tau,tau] float64.  ``gamma``: exponent of the
+        multiplicative update; above 0.5 it is used until the objective increases once, then 0.5 (monotone).
         Returns dict(q, t, objective, gap, iterations)."""
         A = np.ascontiguousarray(A, dtype=np.float64)
         if A.ndim != 3 or A.shape[1] != A.shape[2]:

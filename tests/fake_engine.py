@@ -434,8 +434,8 @@ class FakeEngine(object):
         x = O.normalize_batch_eval(O.get_patches(self.vols[subject], np.asarray(inds), patch_shape), stats)
         return self.fi_shrunk_images(x.astype(np.float32))
 
-    def sdp_query_distribution(self, A, tol=1e-4, max_iter=200000, gamma=0.5):
-        q, t, phi, gap, it = O.sdp_solve(np.asarray(A), tol, max_iter, gamma)
+    def sdp_query_distribution(self, A, tol=1e-4, max_iter=200000, gamma=1.0):
+        q, t, phi, gap, it = O.sdp_solve(np.asarray(A), tol, max_iter, 0.5)    # the monotone exponent; the device may start faster
         return {'q': q, 't': t, 'objective': phi, 'gap': gap, 'iterations': it}
 
     def fi_greedy(self, k, delta):
