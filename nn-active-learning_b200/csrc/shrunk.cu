@@ -71,13 +71,15 @@ __global__ void relu_mask_kernel(float* __restrict__ d, const float* __restrict_
 // ---- max-pool SAME, window == stride: every input cell asks whether it is the FIRST maximum of its window ----------
 __global__ void pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ in, float* __restrict__ d_in,
                                 int64_t total_in, int H, int Wd, int C, int Ho, int Wo, int s) {
+  const int per = H * Wd * C;                      // one sample: 32-bit index arithmetic below
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total_in; e += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(e % C);
-    int64_t t = e / C;
-    const int x = (int)(t % Wd); t /= Wd;
-    const int y = (int)(t % H);
-    const int64_t smp = t / H;
+    const int64_t smp = e / per;
+    const int r = (int)(e - smp * per);
+    const int c = r % C;
+    const int t = r / C;
+    const int x = t % Wd, y = t / Wd;
     const int yo = y / s, xo = x / s;
+    const float* base = in + smp * per;
     float m = -INFINITY;
     int wy = -1, wx = -1;
     for (int dy = 0; dy < s; ++dy) {
@@ -86,7 +88,7 @@ __global__ void pool_bwd_kernel(const float* __restrict__ d_out, const float* __
       for (int dx = 0; dx < s; ++dx) {
         const int x2 = xo * s + dx;
         if (x2 >= Wd) break;
-        const float v = in[((smp * H + y2) * Wd + x2) * (int64_t)C + c];
+        const float v = base[(y2 * Wd + x2) * C + c];
         if (v > m) { m = v; wy = y2; wx = x2; }
       }
     }
@@ -104,8 +106,8 @@ __global__ void pool_bwd_kernel(const float* __restrict__ d_out, const float* __
 //    (consecutive positions) fall into eight different bank groups.
 __host__ __device__ inline int conv_bwd_cp(int Cout) { return (Cout % 4 == 0 && (Cout / 4) % 2 == 0) ? Cout + 4 : Cout; }
 
-template <int TP, int TC, bool WS>
-__global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restrict__ dz, const float* __restrict__ Wt,
+template <int TP, int TC, bool WS, int NT>
+__global__ void __launch_bounds__(NT) conv_bwd_data_kernel(const float* __restrict__ dz, const float* __restrict__ Wt,
                                                              float* __restrict__ d_in, int64_t n, int H, int Wd, int Cin,
                                                              int Cout, int kh, int kw) {
   extern __shared__ float s_dz[];
@@ -127,11 +129,23 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restr
   const float* wbase = WS ? s_w : Wt;
   for (int64_t s = blockIdx.x; s < n; s += gridDim.x) {
     const float* src = dz + s * (int64_t)HW * Cout;
-    for (int e = tid; e < Hp * Wp * Cout; e += blockDim.x) {
-      const int co = e % Cout;
-      const int t = e / Cout;
-      const int xx = t % Wp - pw, yy = t / Wp - ph;
-      s_dz[t * CP + co] = (xx >= 0 && xx < Wd && yy >= 0 && yy < H) ? src[((int64_t)yy * Wd + xx) * Cout + co] : 0.f;
+    if (vec) {
+      const int C4 = Cout / 4;
+      for (int e = tid; e < Hp * Wp * C4; e += blockDim.x) {
+        const int c4 = e % C4;
+        const int t = e / C4;
+        const int xx = t % Wp - pw, yy = t / Wp - ph;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xx >= 0 && xx < Wd && yy >= 0 && yy < H) v = *reinterpret_cast<const float4*>(src + ((int64_t)yy * Wd + xx) * Cout + 4 * c4);
+        *reinterpret_cast<float4*>(&s_dz[t * CP + 4 * c4]) = v;
+      }
+    } else {
+      for (int e = tid; e < Hp * Wp * Cout; e += blockDim.x) {
+        const int co = e % Cout;
+        const int t = e / Cout;
+        const int xx = t % Wp - pw, yy = t / Wp - ph;
+        s_dz[t * CP + co] = (xx >= 0 && xx < Wd && yy >= 0 && yy < H) ? src[((int64_t)yy * Wd + xx) * Cout + co] : 0.f;
+      }
     }
     __syncthreads();
     if (active) {
@@ -200,15 +214,15 @@ __global__ void __launch_bounds__(256) conv_bwd_data_kernel(const float* __restr
   }
 }
 
-template <int TP, int TC, bool WS>
+template <int TP, int TC, bool WS, int NT = 256>
 int conv_bwd_launch(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int64_t n, size_t smem) {
-  auto k = conv_bwd_data_kernel<TP, TC, WS>;
+  auto k = conv_bwd_data_kernel<TP, TC, WS, NT>;
   CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
-  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 256, smem));
+  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, NT, smem));
   // persistent CTAs: the staged filter (WS) is amortised over the CTA's samples
   const int grid = (int)std::min<int64_t>(n, (int64_t)ctx->sm_count * std::max(1, per_sm));
-  k<<<grid, 256, smem, ctx->stream>>>(dz, L.W, d_in, n, L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw);
+  k<<<grid, NT, smem, ctx->stream>>>(dz, L.W, d_in, n, L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
@@ -216,22 +230,24 @@ int conv_bwd_launch(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in,
 
 // Register tile: TC input channels x TP positions per thread; one step (tap, 4 output channels) issues TC + TP 16-byte
 // shared-memory loads for 4 TC TP multiply-adds.  Large rasters with Cin % 8 == 0 (PW1 conv2: 625 positions, 24
-// channels -> 3 groups x 85 position groups x 8 = 680 slots) take 8 x 8 (16 FMAs per load: FMA-bound); 13 x 13 rasters take
+// channels; tile + filter = 198 KB, one CTA per SM) take 8 channels x 4 positions in a 512-thread CTA (3 groups x 170
+// position groups x 4 = 680 slots, 10.7 FMAs per load; the 8 x 8 tile in 256 threads left the schedulers idle 57 % of the
+// time with two warps each -- profiles/r1_conv_bwd_full.md); 13 x 13 rasters take
 // TC = 4 and the TP that covers the raster in one pass (conv3: 32 groups x 6 = 192 slots for 169 positions, filter in
 // shared memory; conv4: 21 x 9 = 189, filter 166 KB + tile 90 KB do not fit together: filter through L2, one
 // warp-uniform load per TP x 16 multiply-adds).
 template <int TC>
 int conv_bwd_pick(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int64_t n) {
   const int groups = (L.in_c + TC - 1) / TC, PG = 256 / groups;
-  const int need = (L.in_h * L.in_w + PG - 1) / PG;
+  const int need = (L.in_h * L.in_w + PG - 1) / PG;         // (TC = 8 runs 512 threads: twice the position groups)
   const size_t tile = ((size_t)(L.in_h + L.kh - 1) * (L.in_w + L.kw - 1) * conv_bwd_cp(L.out_c) + 3) / 4 * 4 * sizeof(float);
   const size_t wbytes = (size_t)L.kh * L.kw * L.in_c * L.out_c * sizeof(float);
   if (tile > 200 * 1024) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient tile exceeds shared memory");
   static const bool no_ws = getenv("NNAL_BW_NO_WS") != nullptr;
   const bool ws = !no_ws && tile + wbytes <= 220 * 1024;
   if constexpr (TC == 8) {
-    if (ws) return conv_bwd_launch<8, TC, true>(ctx, L, dz, d_in, n, tile + wbytes);
-    return conv_bwd_launch<8, TC, false>(ctx, L, dz, d_in, n, tile);
+    if (ws) return conv_bwd_launch<4, TC, true, 512>(ctx, L, dz, d_in, n, tile + wbytes);
+    return conv_bwd_launch<4, TC, false, 512>(ctx, L, dz, d_in, n, tile);
   } else {
   if (ws) {
     if (need <= 4) return conv_bwd_launch<4, TC, true>(ctx, L, dz, d_in, n, tile + wbytes);
