@@ -410,7 +410,7 @@ def run_sdp_round(args, eng, padded, pool, st, k):
         fwd_ms, _ = eng.profile_read(120)
         bwd_ms, _ = eng.profile_read(121)
         eng.profile(False)
-        A = np.array(_A_from_shrunk(g, post[1].astype(np.float64), 1e-5))
+        A = _A_from_shrunk(g, post[1].astype(np.float64), 1e-5, as_list=False)
         t2 = time.perf_counter()
         r = eng.sdp_query_distribution(A, tol=1e-4)
         t3 = time.perf_counter()

@@ -83,20 +83,27 @@ def CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, method_name):
     raise NotImplementedError('query method %r is not part of the replaced path' % method_name)
 
 
-def _A_from_shrunk(g, sel_posts, diag_load):
+def _A_from_shrunk(g, sel_posts, diag_load, as_list=True):
     """The A-matrix assembly of PW_NNAL.gen_A_matrices (PW_NNAL.py:766-814) from shrunk gradients ``g`` [2,B,tau]:
     p < 1e-6 -> p = 0 and only g0 (:770-780), p > 1-1e-6 -> p = 1 and only g1 (:782-793),
     ``A_i = (1-p) g0 g0^T + p g1 g1^T + diag_load I`` (:810-814).  Vectorised over the B samples with the
-    reference's order of operations (bit-identical to the per-sample loop)."""
+    reference's order of operations (bit-identical to the per-sample loop).  ``as_list=False`` keeps the [B,tau,tau]
+    array (the SDP entry point takes either; 10,000 array views cost more than the arithmetic)."""
     tau = g.shape[2]
     p = np.array(sel_posts, dtype=np.float64)
     lo, hi = p < 1e-6, p > 1 - 1e-6
     p[lo], p[hi] = 0., 1.
     g0 = np.where(hi[:, None], 0., g[0])
     g1 = np.where(lo[:, None], 0., g[1])
-    A = (1. - p)[:, None, None] * (g0[:, :, None] * g0[:, None, :]) + p[:, None, None] * (g1[:, :, None] * g1[:, None, :])
-    A = A + np.eye(tau) * diag_load
-    return list(A)
+    B = len(p)
+    A = np.einsum('bi,bj->bij', g0, g0).reshape(B, tau * tau)
+    A1 = np.einsum('bi,bj->bij', g1, g1).reshape(B, tau * tau)
+    A *= (1. - p)[:, None]
+    A1 *= p[:, None]
+    A += A1
+    A += (np.eye(tau) * diag_load).reshape(1, tau * tau)
+    A = A.reshape(B, tau, tau)
+    return list(A) if as_list else A
 
 
 def gen_A_matrices(expr, model, sess, sel_patches, sel_posts, diag_load=1e-5):

@@ -96,6 +96,45 @@ __global__ void pool_bwd_kernel(const float* __restrict__ d_out, const float* __
   }
 }
 
+// four channels per thread (C % 4 == 0): 16-byte loads, four independent comparisons in flight
+__global__ void pool_bwd_vec4_kernel(const float* __restrict__ d_out, const float* __restrict__ in, float* __restrict__ d_in,
+                                     int64_t total4, int H, int Wd, int C, int Ho, int Wo, int s) {
+  const int C4 = C / 4, per4 = H * Wd * C4;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t smp = e / per4;
+    const int r = (int)(e - smp * per4);
+    const int c4 = r % C4;
+    const int t = r / C4;
+    const int x = t % Wd, y = t / Wd;
+    const int yo = y / s, xo = x / s;
+    const float* base = in + smp * (int64_t)per4 * 4 + 4 * c4;
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int win[4] = {-1, -1, -1, -1};
+    for (int dy = 0; dy < s; ++dy) {
+      const int y2 = yo * s + dy;
+      if (y2 >= H) break;
+      for (int dx = 0; dx < s; ++dx) {
+        const int x2 = xo * s + dx;
+        if (x2 >= Wd) break;
+        const float4 v = *reinterpret_cast<const float4*>(base + (int64_t)(y2 * Wd + x2) * C);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        const int id = y2 * Wd + x2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (vv[k] > m[k]) { m[k] = vv[k]; win[k] = id; }
+      }
+    }
+    const float4 g = *reinterpret_cast<const float4*>(d_out + ((smp * Ho + yo) * Wo + xo) * (int64_t)C + 4 * c4);
+    const int me = y * Wd + x;
+    float4 o;
+    o.x = win[0] == me ? g.x : 0.f;
+    o.y = win[1] == me ? g.y : 0.f;
+    o.z = win[2] == me ? g.z : 0.f;
+    o.w = win[3] == me ? g.w : 0.f;
+    *reinterpret_cast<float4*>(d_in + e * 4) = o;
+  }
+}
+
 // ---- conv data gradient: d_in[y][x][ci] = sum_{dy,dx,co} dz[y-dy+ph][x-dx+pw][co] W[dy][dx][ci][co] ------------------
 // One CTA per sample; dz is staged zero-padded in shared memory so that the flipped tap (dy',dx') = (kh-1-dy, kw-1-dx)
 // reads padded position (y+dy', x+dx').  A thread owns TC input channels x TP positions and walks co four at a time.
@@ -528,7 +567,14 @@ __global__ void __launch_bounds__(256) shrink_conv_kernel(const float* __restric
     double v = 0.0;
     if (xx >= 0 && xx < Wd && yy >= 0 && yy < H) {
       const float* p = xin + ((int64_t)yy * Wd + xx) * Cin;
-      for (int c = 0; c < Cin; ++c) v += (double)p[c];
+      if (Cin % 4 == 0) {
+        for (int c = 0; c < Cin; c += 4) {
+          const float4 q4 = *reinterpret_cast<const float4*>(p + c);
+          v += ((double)q4.x + (double)q4.y) + ((double)q4.z + (double)q4.w);
+        }
+      } else {
+        for (int c = 0; c < Cin; ++c) v += (double)p[c];
+      }
     }
     s_xs[e] = v;
   }
@@ -538,7 +584,14 @@ __global__ void __launch_bounds__(256) shrink_conv_kernel(const float* __restric
     const int y = p / Wd, x = p % Wd;
     const float* q = dzs + (int64_t)p * Cout;
     double D = 0.0;
-    for (int c = 0; c < Cout; ++c) D += (double)q[c];
+    if (Cout % 4 == 0) {
+      for (int c = 0; c < Cout; c += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(q + c);
+        D += ((double)q4.x + (double)q4.y) + ((double)q4.z + (double)q4.w);
+      }
+    } else {
+      for (int c = 0; c < Cout; ++c) D += (double)q[c];
+    }
     double box = 0.0;
     for (int dy = 0; dy < kh; ++dy)
       for (int dx = 0; dx < kw; ++dx) box += s_xs[(y + dy) * Wp + x + dx];
@@ -640,7 +693,11 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
       float* other = (float*)st->g[pp ^ 1].p;
       if (L.type == NNAL_LAYER_POOL) {
         const int64_t total_in = nb * L.in_h * L.in_w * L.in_c;
-        pool_bwd_kernel<<<grid_for(ctx, total_in, 16), 256, 0, ctx->stream>>>(d, in_of(i), other, total_in, L.in_h, L.in_w,
+        if (L.in_c % 4 == 0)
+          pool_bwd_vec4_kernel<<<grid_for(ctx, total_in / 4, 16), 256, 0, ctx->stream>>>(d, in_of(i), other, total_in / 4, L.in_h,
+                                                                                         L.in_w, L.in_c, L.out_h, L.out_w, L.kh);
+        else
+          pool_bwd_kernel<<<grid_for(ctx, total_in, 16), 256, 0, ctx->stream>>>(d, in_of(i), other, total_in, L.in_h, L.in_w,
                                                                                 L.in_c, L.out_h, L.out_w, L.kh);
         ctx->launches++;
         d = other; pp ^= 1;

@@ -178,7 +178,7 @@ def query_single_sdp(expr, model, sess, padded_imgs, pool_inds, return_solution=
     imgs = list(padded_imgs)
     post, g = eng.fi_shrunk_voxels(0, pool_inds[sel_inds], expr.pars['patch_shape'],
                                    _stats_list(expr.pars['stats'], len(imgs)), L.NORM_BATCH_EVAL, shape=imgs[0].shape)
-    A = _A_from_shrunk(g, post[1].astype(np.float64), float(expr.pars.get('fi_diag_load', 1e-5)))
+    A = _A_from_shrunk(g, post[1].astype(np.float64), float(expr.pars.get('fi_diag_load', 1e-5)), as_list=False)
     Q_inds, soln = _sdp_sample(A, expr, return_solution)
     q = sel_inds[Q_inds]
     return (q, soln, sel_inds) if return_solution else q
@@ -212,7 +212,8 @@ def query_multimg_sdp(expr, model, sess, all_padded_imgs, pool_inds, return_solu
                          dtype=np.float64)
         post, g = eng.fi_shrunk_voxels(i, np.asarray(pool_inds[i])[local], expr.pars['patch_shape'], stats,
                                        L.NORM_BATCH_EVAL, shape=imgs[0].shape)
-        A += _A_from_shrunk(g, post[1].astype(np.float64), delta)
+        A.append(_A_from_shrunk(g, post[1].astype(np.float64), delta, as_list=False))
+    A = np.concatenate(A, axis=0)
     Q_inds, soln = _sdp_sample(A, expr, return_solution)
     Q = patch_utils.global2local_inds(G[Q_inds], sizes)
     return (Q, soln, G) if return_solution else Q
