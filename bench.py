@@ -428,6 +428,22 @@ def run_sdp_round(args, eng, padded, pool, st, k):
                'n_selected': int(len(Q)),
                'note': 'reference: 2B single-sample tf.gradients runs over 36 M parameters + cvxopt SDP with an n x n '
                        'positivity block; here one batched data-gradient pass + tau x tau first-order solver'}
+    if not args.no_cpu and res is not None:
+        # the same selection through the float64 oracle on a bounded sample of the candidates (reported baseline: the
+        # reference itself runs two TF sess.run(tf.gradients) calls per candidate, which cannot be installed here)
+        import oracle as O
+        ns = 48
+        x = O.normalize_batch_eval(O.get_patches(padded, cand[:ns], PATCH), st).astype(np.float32)
+        layers, w = pw1_weights()
+        t0 = time.perf_counter()
+        po, go = O.shrunk_class_gradients(layers, w, x)
+        t1 = time.perf_counter()
+        Ao = O.gen_A_matrices(go[0], go[1], po[1], 1e-5)
+        qo, to, phio, gapo, ito = O.sdp_solve(Ao, 1e-4)
+        t2 = time.perf_counter()
+        res['cpu_baseline'] = {'kind': 'port', 'cores': 1, 'sample': '%d candidates (NumPy float64 forward + one backward pass per '
+                               'class + shrink + multiplicative SDP)' % ns,
+                               'backprops_per_s': 2.0 * ns / (t1 - t0), 'sdp_ms': 1e3 * (t2 - t1), 'sdp_iterations': int(ito)}
     return res
 
 

@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(256) bw_split_transposed_kernel(const float* _
 
 bool fc_bwd_tc_eligible(const nnal_ctx* ctx, const Layer& L) {
   static const bool off = getenv("NNAL_BW_NO_TC") != nullptr;
-  return !off && ctx->use_tc && L.type == NNAL_LAYER_FC && L.out_dim >= 64 && L.in_dim >= 64 && L.out_dim % 8 == 0 &&
+  return !off && L.type == NNAL_LAYER_FC && L.out_dim >= 64 && L.in_dim >= 64 && L.out_dim % 8 == 0 &&
          L.in_dim % 8 == 0;
 }
 
@@ -713,7 +713,7 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
         shrink_fc_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(d, in_of(i), L.out_dim, L.in_dim, inv, S, tau, t);
         ctx->launches++;
         if (i > 0) {
-          if (st->wt[i].h) NNAL_TRY(fc_bwd_data_tc(ctx, st, L, st->wt[i], d, other, nb));
+          if (ctx->use_tc && st->wt[i].h) NNAL_TRY(fc_bwd_data_tc(ctx, st, L, st->wt[i], d, other, nb));
           else NNAL_TRY(fc_bwd_data(ctx, L, d, other, nb));
           d = other; pp ^= 1;
         }

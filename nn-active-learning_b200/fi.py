@@ -141,6 +141,23 @@ def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, return_objectiv
     return (Q, obj) if return_objective else Q
 
 
+def _gather_shrunk(post, g):
+    """All-gather of per-rank shrunk-gradient slices (candidates are block-partitioned over the ranks in candidate
+    order): ``post`` [c,m_r], ``g`` [c,m_r,tau] -> [c,B], [c,B,tau] on every rank.  No-op in a single process."""
+    if not dist.is_dist():
+        return post, g
+    c, tau = g.shape[0], g.shape[2]
+    P = dist.allgather_concat(np.ascontiguousarray(post.T, dtype=np.float32).ravel()).reshape(-1, c).T
+    G = dist.allgather_concat(np.ascontiguousarray(np.transpose(g, (1, 0, 2)), dtype=np.float64).ravel())
+    return np.ascontiguousarray(P), np.ascontiguousarray(np.transpose(G.reshape(-1, c, tau), (1, 0, 2)))
+
+
+def _my_slice(n):
+    rank, world = dist.rank_world()
+    b = dist.shard_bounds(n, world)
+    return int(b[rank]), int(b[rank + 1])
+
+
 def _sdp_sample(A, expr, return_solution):
     """SDP query distribution + the reference's sampler (PW_NNAL.py:154-163).  The draw uses NumPy's global
     generator like the reference; with several ranks, rank 0's draw is broadcast."""
@@ -163,7 +180,8 @@ def query_single_sdp(expr, model, sess, padded_imgs, pool_inds, return_solution=
     """``PW_NNAL.CNN_query(..., 'fi')`` as the reference runs it (PW_NNAL.py:89-163): posteriors -> the B most
     uncertain samples (:107-115) -> conditional FIs in shrunk coordinates (gen_A_matrices, diag_load 1e-5) -> SDP
     query distribution -> ``sample_query_dstr`` (<= k unique positions, sorted).  Positions into ``pool_inds``.
-    The candidates' patches are gathered on the device; every rank evaluates the same B candidates."""
+    The candidates' patches are gathered on the device; with several ranks each one back-propagates its block of the B
+    candidates, the shrunk gradients (B x 2 x tau numbers) are all-gathered and every rank solves the same SDP."""
     from .PW_NNAL import _score_pool_single, _stats_list, _A_from_shrunk
     B = int(expr.pars['B'])
     pool_inds = np.asarray(pool_inds)
@@ -176,8 +194,10 @@ def query_single_sdp(expr, model, sess, padded_imgs, pool_inds, return_solution=
     else:
         sel_inds = np.arange(n, dtype=np.int64)
     imgs = list(padded_imgs)
-    post, g = eng.fi_shrunk_voxels(0, pool_inds[sel_inds], expr.pars['patch_shape'],
+    a, e = _my_slice(len(sel_inds))              # the backward pass is sharded over the ranks, the tiny SDP is replicated
+    post, g = eng.fi_shrunk_voxels(0, pool_inds[sel_inds[a:e]], expr.pars['patch_shape'],
                                    _stats_list(expr.pars['stats'], len(imgs)), L.NORM_BATCH_EVAL, shape=imgs[0].shape)
+    post, g = _gather_shrunk(post, g)
     A = _A_from_shrunk(g, post[1].astype(np.float64), float(expr.pars.get('fi_diag_load', 1e-5)), as_list=False)
     Q_inds, soln = _sdp_sample(A, expr, return_solution)
     q = sel_inds[Q_inds]
@@ -199,10 +219,13 @@ def query_multimg_sdp(expr, model, sess, all_padded_imgs, pool_inds, return_solu
     order = np.argsort(set_of, kind='stable')
     G = sorted_inds[order]                       # global positions, subject-major candidate order
     G_set = set_of[order]
-    A = []
     delta = float(expr.pars.get('fi_diag_load', 1e-3))
+    a, e = _my_slice(len(G))                     # this rank's block of the candidate list
+    mine = np.zeros(len(G), dtype=bool)
+    mine[a:e] = True
+    posts, gs = [], []
     for i in range(s):
-        sel = G_set == i
+        sel = mine & (G_set == i)
         if not sel.any():
             continue
         local = G[sel] - (cum[i] + 1)
@@ -212,8 +235,13 @@ def query_multimg_sdp(expr, model, sess, all_padded_imgs, pool_inds, return_solu
                          dtype=np.float64)
         post, g = eng.fi_shrunk_voxels(i, np.asarray(pool_inds[i])[local], expr.pars['patch_shape'], stats,
                                        L.NORM_BATCH_EVAL, shape=imgs[0].shape)
-        A.append(_A_from_shrunk(g, post[1].astype(np.float64), delta, as_list=False))
-    A = np.concatenate(A, axis=0)
+        posts.append(post)
+        gs.append(g)
+    tau = eng.fi_shrunk_tau()
+    post = np.concatenate(posts, axis=1) if posts else np.zeros((2, 0), dtype=np.float32)
+    g = np.concatenate(gs, axis=1) if gs else np.zeros((2, 0, tau))
+    post, g = _gather_shrunk(post, g)
+    A = _A_from_shrunk(g, post[1].astype(np.float64), delta, as_list=False)
     Q_inds, soln = _sdp_sample(A, expr, return_solution)
     Q = patch_utils.global2local_inds(G[Q_inds], sizes)
     return (Q, soln, G) if return_solution else Q
@@ -263,7 +291,9 @@ def query_whole_sdp(model, expr, pool_inds, session, return_solution=False):
         sel_inds, _ = dist.allgather_topk(sc, idx + lo, B)
     else:
         sel_inds = np.arange(n, dtype=np.int64)
-    post, g = eng.fi_shrunk_images(_pool_images(expr, pool_inds[sel_inds]))
+    a, e = _my_slice(len(sel_inds))
+    post, g = eng.fi_shrunk_images(_pool_images(expr, pool_inds[sel_inds[a:e]]))
+    post, g = _gather_shrunk(post, g)
     A = _A_multiclass_from_shrunk(post.astype(np.float64), g)
     Q_inds, soln = _sdp_sample(A, expr, return_solution)
     q = sel_inds[Q_inds]

@@ -127,6 +127,9 @@ def run(rank, world, out):
     wexpr.pars = dict(k=7, B=25, lambda_=0., batch_size=32)
     wexpr.pool_images = np.random.RandomState(3).rand(90, 5, 5, m).astype(np.float32)
     res['rep_whole'] = nnal_b200.NNAL.CNN_query(model, wexpr, np.arange(90), 'rep-entropy', None)
+    wexpr.pars.update(fi_mode='sdp', B=20)
+    np.random.seed(3000 + rank)
+    res['fi_sdp_whole'] = nnal_b200.NNAL.CNN_query(model, wexpr, np.arange(90), 'fi', None)
     # primitives
     rs = np.random.RandomState(100 + rank)
     sc = np.sort(rs.rand(6))

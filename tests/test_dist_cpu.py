@@ -105,6 +105,13 @@ def test_single_process_matches_oracle(runs):
     x = np.random.RandomState(3).rand(90, 5, 5, m).astype(np.float32)
     qw, _ = O.query_rep_entropy_whole(layers, w, x, 7, 25)
     assert np.array_equal(one['rep_whole'], qw)
+    # whole-image literal FI pipeline (binary net here: the multiclass assembly of NNAL.py:354-414 with c = 2)
+    r = O.forward(layers, w, x)
+    sel = O.uncertainty_filtering(r['posteriors'].copy(), 20)
+    po, go = O.shrunk_class_gradients(layers, w, x[sel])
+    qo, _, _, _, _ = O.sdp_solve(O.gen_A_matrices_multiclass(po.copy(), go), 1e-4)
+    draws = O.sample_query_dstr(qo.copy(), 7, np.random.RandomState(3000).random_sample(7))
+    assert np.array_equal(one['fi_sdp_whole'], sel[draws])
 
 
 def test_collective_primitives(runs):

@@ -263,3 +263,31 @@ def test_whole_image_fi_query_sdp_multiclass(nb):
     phi_c, gap_c = O.sdp_certificate(A, q_dev)
     assert abs(phi_c / phio - 1) < OBJ_RTOL
     assert np.array_equal(q, sel[O.sample_query_dstr(q_dev.copy(), k, u)])
+
+
+def test_shrunk_error_paths(nb):
+    """Argument checks of the shrunk-gradient entry points: wrong patch shape -> ValueError (the reference's feed would
+    fail on the placeholder shape), out-of-range voxel ids -> ValueError as np.unravel_index (patch_utils.py:1144)."""
+    ps, imgs, padded, stats, pool, layers, w = _pw_setup(8, 97)
+    model = nb.NN.create_PW1(2)
+    model.set_weights(w)
+    eng = nb.get_engine()
+    eng.set_model(model, None)
+    eng.upload(0, padded)
+    st = np.array(stats, dtype=np.float64)
+    with pytest.raises(ValueError):
+        eng.fi_shrunk_voxels(0, pool, (23, 23, 1), st, shape=padded[0].shape)
+    with pytest.raises(ValueError):
+        eng.fi_shrunk_voxels(0, np.array([10 ** 9]), ps, st, shape=padded[0].shape)
+    post, g = eng.fi_shrunk_voxels(0, pool[:0], ps, st, shape=padded[0].shape)
+    assert post.shape == (2, 0) and g.shape == (2, 0, 7)
+    # weights replaced -> the transposed fc planes of the backward pass are rebuilt (no stale gradients)
+    p1, g1 = eng.fi_shrunk_voxels(0, pool, ps, st, shape=padded[0].shape)
+    w2 = O.he_init_weights(layers, (25, 25, 3), 123, bias_scale=0.05)
+    model.set_weights(w2)
+    eng.set_model(model, None)
+    p2, g2 = eng.fi_shrunk_voxels(0, pool, ps, st, shape=padded[0].shape)
+    x = O.normalize_batch_eval(O.get_patches(padded, pool, ps), stats).astype(np.float32)
+    po, go = O.shrunk_class_gradients(layers, w2, x)
+    _assert_shrunk_close(g2, go)
+    assert np.abs(g1 - g2).max() > 0
