@@ -53,6 +53,12 @@ def SDP_query_distribution(A, lambda_, X_pool, k, tol=1e-4, max_iter=200000):
             'primal objective': r['objective'], 'gap': r['gap'], 'iterations': r['iterations']}
 
 
+def solve_FIAL_SDP(A):
+    """NNAL_tools.solve_FIAL_SDP (NNAL_tools.py:576-610): the same programme stated with cvxpy/MOSEK upstream
+    (``expr.pars['SDP_solver'] == 'MOSEK'``, PW_NNAL.py:608-611); returns the query distribution ``q``."""
+    return np.array(SDP_query_distribution(A, 0., None, None)['x'][:len(A)])
+
+
 def sample_query_dstr(q_dstr, k, replacement=True):
     """NNAL_tools.sample_query_dstr, replacement=True branch (NNAL_tools.py:844-872)."""
     if q_dstr.min() < -.01:

@@ -291,3 +291,24 @@ def test_shrunk_error_paths(nb):
     po, go = O.shrunk_class_gradients(layers, w2, x)
     _assert_shrunk_close(g2, go)
     assert np.abs(g1 - g2).max() > 0
+
+
+@pytest.mark.parametrize('env', [
+    {},
+    {'NNAL_BW_SIMT_FWD': '1', 'NNAL_BW_NO_TC': '1', 'NNAL_BW_NO_WS': '1', 'NNAL_BW_NO_TC8': '1', 'NNAL_SDP_NO_COOP': '1'},
+    {'NNAL_BW_NO_WS': '1', 'NNAL_BW_CHUNK': '16'},
+])
+def test_fallback_kernels_subprocess(env):
+    """The kernel-selection switches are read once per process, so the fallback kernels run in a subprocess: fp32
+    CUDA-core forward, fp32 fc gradient, conv filter through L2, 4-channel register tile, one launch per SDP iteration --
+    same parity bar as the default kernels."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'sdp_fallback_check.py')], env=e, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, timeout=600)
+    out = r.stdout.decode()
+    assert r.returncode == 0 and 'OK ' in out, out[-2000:]
