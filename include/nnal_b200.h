@@ -235,6 +235,12 @@ int nnal_fi_shrunk_voxels(nnal_ctx* ctx, int subject, const int64_t* inds, int64
 int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64_t n, int tau, double tol, int64_t max_iter,
                                 double gamma, double* q_out, double* t_out, double* obj_out, double* gap_out,
                                 int64_t* iters_out);
+/* Same solver, with the binary A-matrices of PW_NNAL.gen_A_matrices (PW_NNAL.py:766-814) assembled on the device from
+ * the shrunk gradients g [2][n][tau] and p1 [n] = P(class 1): p < 1e-6 -> only g0, p > 1-1e-6 -> only g1,
+ * A_i = (1-p) g0 g0^T + p g1 g1^T + diag_load I (bit-identical to the host assembly); saves the n tau^2 upload. */
+int nnal_sdp_from_shrunk(nnal_ctx* ctx, const double* g, const double* p1, int64_t n, int tau, double diag_load, double tol,
+                         int64_t max_iter, double gamma, double* q_out, double* t_out, double* obj_out, double* gap_out,
+                         int64_t* iters_out);
 
 /* ---- representativeness queries over the feature layer ------------------------------- */
 /* Rows = the samples of the current pool pass (nnal_pool_begin keep >= 1; feature width multiple of 8).

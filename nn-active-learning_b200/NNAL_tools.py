@@ -49,8 +49,20 @@ def SDP_query_distribution(A, lambda_, X_pool, k, tol=1e-4, max_iter=200000):
         raise NotImplementedError('lambda_ > 0 (feature-regularised SDP, NNAL_tools.py:625-644) stays in the reference')
     A = np.asarray(A, dtype=np.float64)
     r = get_engine().sdp_query_distribution(A, tol=tol, max_iter=max_iter)
+    return _soln(r, tol)
+
+
+def _soln(r, tol):
     return {'x': np.concatenate([r['q'], r['t']]), 'status': 'optimal' if r['gap'] <= 2 * tol else 'unknown',
             'primal objective': r['objective'], 'gap': r['gap'], 'iterations': r['iterations']}
+
+
+def SDP_query_distribution_from_shrunk(g, sel_posts, diag_load, k, tol=1e-4, max_iter=200000):
+    """``SDP_query_distribution(gen_A_matrices(...), 0, None, k)`` without materialising the A-matrices on the host:
+    ``g`` [2,B,tau] shrunk class-score gradients, ``sel_posts`` [B] = P(class 1); the A_i of PW_NNAL.py:766-814 are
+    assembled on the device in the solver's layout (bit-identical to the host assembly)."""
+    r = get_engine().sdp_from_shrunk(g, sel_posts, diag_load, tol=tol, max_iter=max_iter)
+    return _soln(r, tol)
 
 
 def solve_FIAL_SDP(A):

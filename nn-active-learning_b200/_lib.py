@@ -91,6 +91,8 @@ SIGNATURES = {
                                         c_vp]),
     'nnal_sdp_query_distribution': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, C.c_double, C.c_int64, C.c_double, c_vp,
                                               c_vp, c_f64p, c_f64p, c_i64p]),
+    'nnal_sdp_from_shrunk': (C.c_int, [c_vp, c_vp, c_vp, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_double,
+                                       c_vp, c_vp, c_f64p, c_f64p, c_i64p]),
 }
 
 NNAL_OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, 1, 2, 3, 4, 5

@@ -60,6 +60,31 @@ __global__ void sdp_transpose_kernel(const double* __restrict__ A, double* __res
   }
 }
 
+// A_i of PW_NNAL.gen_A_matrices (PW_NNAL.py:766-814) written straight into the solver's [tau*tau][n] layout:
+// p < 1e-6 -> p = 0 and only g0, p > 1-1e-6 -> p = 1 and only g1, A_i = (1-p) g0 g0^T + p g1 g1^T + diag_load I,
+// with the reference's order of operations ((1-p) * (g0_a * g0_b), then + p * (g1_a * g1_b), then + diag_load).
+__global__ void sdp_binary_A_kernel(const double* __restrict__ g, const double* __restrict__ p1, int64_t n, int tau,
+                                    double diag_load, double* __restrict__ At) {
+  const int T2 = tau * tau;
+  const int64_t total = n * T2;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int ab = (int)(e / n);
+    const int64_t i = e - (int64_t)ab * n;
+    const int a = ab / tau, b = ab % tau;
+    double p = p1[i];
+    const bool lo = p < 1e-6, hi = p > 1.0 - 1e-6;
+    if (lo) p = 0.0;
+    if (hi) p = 1.0;
+    const double* g0 = g + i * tau;
+    const double* g1 = g + (n + i) * tau;
+    const double o0 = hi ? 0.0 : g0[a] * g0[b];
+    const double o1 = lo ? 0.0 : g1[a] * g1[b];
+    double v = __dadd_rn(__dmul_rn(o0, 1.0 - p), __dmul_rn(o1, p));        // no FMA contraction: bit-identical to NumPy
+    if (a == b) v = __dadd_rn(v, diag_load);
+    At[e] = v;
+  }
+}
+
 __global__ void sdp_fill_kernel(double* __restrict__ q, int64_t n, double v) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) q[e] = v;
 }
@@ -304,10 +329,11 @@ int nnal_sdp_release(nnal_ctx* ctx) {
   return NNAL_OK;
 }
 
-extern "C" int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64_t n, int tau, double tol, int64_t max_iter,
-                                           double gamma, double* q_out, double* t_out, double* obj_out, double* gap_out,
-                                           int64_t* iters_out) {
-  if (!ctx || !A || !q_out || n <= 0 || tau <= 0) return NNAL_ERR_INVALID;
+// mode 0: A = n dense tau x tau matrices on the host; mode 1: src = shrunk gradients g [2][n][tau], p1 = P(class 1) [n]
+static int sdp_solve(nnal_ctx* ctx, int mode, const double* src, const double* p1, double diag_load, int64_t n, int tau,
+                     double tol, int64_t max_iter, double gamma, double* q_out, double* t_out, double* obj_out,
+                     double* gap_out, int64_t* iters_out) {
+  if (!ctx || !src || !q_out || n <= 0 || tau <= 0) return NNAL_ERR_INVALID;
   if (tau > SDP_MAX_TAU) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "SDP: more than 16 shrunk coordinates");
   if (!(gamma > 0.0 && gamma <= 1.0)) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "SDP: gamma must be in (0, 1]");
   if (!(tol > 0.0)) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "SDP: tol must be positive");
@@ -317,7 +343,7 @@ extern "C" int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64
   const int T2 = tau * tau;
   const int G = (int)std::min<int64_t>((n + SDP_THREADS - 1) / SDP_THREADS, SDP_MAX_GRID);
   const size_t part_doubles = (size_t)G * T2 + 2 * (size_t)G;
-  NNAL_TRY(devbuf_reserve(ctx, st->stage, (size_t)n * T2 * 8));
+  NNAL_TRY(devbuf_reserve(ctx, st->stage, mode == 0 ? (size_t)n * T2 * 8 : (size_t)n * (2 * tau + 1) * 8));
   NNAL_TRY(devbuf_reserve(ctx, st->At, (size_t)n * T2 * 8));
   NNAL_TRY(devbuf_reserve(ctx, st->qu, (size_t)n * 8 * 2));           // unnormalised weights, then the normalised result
   NNAL_TRY(devbuf_reserve(ctx, st->part[0], part_doubles * 8));
@@ -328,9 +354,17 @@ extern "C" int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64
   double* qn = qu + n;
   double* hist = (double*)st->out.p;         // [0..2] loop record, [4..] result of the final kernel
   double* res = hist + 4;
-  CUDA_TRY(ctx, cudaMemcpyAsync(st->stage.p, A, (size_t)n * T2 * 8, cudaMemcpyHostToDevice, ctx->stream));
   const int tg = (int)std::min<int64_t>((n * T2 + 255) / 256, (int64_t)ctx->sm_count * 8);
-  sdp_transpose_kernel<<<tg, 256, 0, ctx->stream>>>((const double*)st->stage.p, At, n, T2);
+  if (mode == 0) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(st->stage.p, src, (size_t)n * T2 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    sdp_transpose_kernel<<<tg, 256, 0, ctx->stream>>>((const double*)st->stage.p, At, n, T2);
+  } else {
+    double* d_g = (double*)st->stage.p;
+    double* d_p = d_g + 2 * n * tau;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_g, src, (size_t)2 * n * tau * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_p, p1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    sdp_binary_A_kernel<<<tg, 256, 0, ctx->stream>>>(d_g, d_p, n, tau, diag_load, At);
+  }
   sdp_fill_kernel<<<G, 256, 0, ctx->stream>>>(qu, n, 1.0);
   int cur = 0;
   sdp_init_kernel<<<G, SDP_THREADS, 0, ctx->stream>>>(At, qu, n, tau, (double*)st->part[cur].p);
@@ -397,4 +431,17 @@ extern "C" int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64
   if (t_out) for (int j = 0; j < tau; ++j) t_out[j] = hres[2 + j];
   if (iters_out) *iters_out = it;
   return NNAL_OK;
+}
+
+extern "C" int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64_t n, int tau, double tol, int64_t max_iter,
+                                           double gamma, double* q_out, double* t_out, double* obj_out, double* gap_out,
+                                           int64_t* iters_out) {
+  return sdp_solve(ctx, 0, A, nullptr, 0.0, n, tau, tol, max_iter, gamma, q_out, t_out, obj_out, gap_out, iters_out);
+}
+
+extern "C" int nnal_sdp_from_shrunk(nnal_ctx* ctx, const double* g, const double* p1, int64_t n, int tau, double diag_load,
+                                    double tol, int64_t max_iter, double gamma, double* q_out, double* t_out,
+                                    double* obj_out, double* gap_out, int64_t* iters_out) {
+  if (!p1 || !(diag_load >= 0.0)) return NNAL_ERR_INVALID;
+  return sdp_solve(ctx, 1, g, p1, diag_load, n, tau, tol, max_iter, gamma, q_out, t_out, obj_out, gap_out, iters_out);
 }

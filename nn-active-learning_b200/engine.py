@@ -440,6 +440,23 @@ class Engine(object):
                                                        _ptr(q), _ptr(t), C.byref(obj), C.byref(gap), C.byref(it)))
         return {'q': q, 't': t, 'objective': obj.value, 'gap': gap.value, 'iterations': it.value}
 
+    def sdp_from_shrunk(self, g, p1, diag_load, tol=1e-4, max_iter=200000, gamma=1.0):
+        """``sdp_query_distribution`` on the binary A-matrices of ``gen_A_matrices``, assembled on the device from the
+        shrunk gradients ``g`` [2,n,tau] and ``p1`` [n] = P(class 1)."""
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        p1 = np.ascontiguousarray(p1, dtype=np.float64).ravel()
+        if g.ndim != 3 or g.shape[0] != 2 or g.shape[1] != p1.size:
+            raise ValueError('g must be [2, n, tau] and p1 [n]')
+        n, tau = g.shape[1], g.shape[2]
+        q = np.empty(n, dtype=np.float64)
+        t = np.empty(tau, dtype=np.float64)
+        obj, gap, it = C.c_double(), C.c_double(), C.c_int64()
+        self.h2d_bytes += g.nbytes + p1.nbytes
+        self.d2h_bytes += q.nbytes
+        self._chk(self.lib.nnal_sdp_from_shrunk(self.h, _ptr(g), _ptr(p1), n, tau, float(diag_load), float(tol), int(max_iter),
+                                                float(gamma), _ptr(q), _ptr(t), C.byref(obj), C.byref(gap), C.byref(it)))
+        return {'q': q, 't': t, 'objective': obj.value, 'gap': gap.value, 'iterations': it.value}
+
     def fi_begin(self, k, delta):
         self._chk(self.lib.nnal_fi_begin(self.h, int(k), float(delta)))
 

@@ -158,14 +158,22 @@ def _my_slice(n):
     return int(b[rank]), int(b[rank + 1])
 
 
-def _sdp_sample(A, expr, return_solution):
+def _sdp_sample(A, expr, return_solution, shrunk=None):
     """SDP query distribution + the reference's sampler (PW_NNAL.py:154-163).  The draw uses NumPy's global
-    generator like the reference; with several ranks, rank 0's draw is broadcast."""
+    generator like the reference; with several ranks, rank 0's draw is broadcast.  ``shrunk = (g, p1, diag_load)``:
+    binary A-matrices assembled on the device instead of ``A``."""
     from . import NNAL_tools
     k = int(expr.pars['k'])
-    soln = NNAL_tools.SDP_query_distribution(A, expr.pars.get('lambda_', 0), None, k,
-                                             tol=float(expr.pars.get('sdp_tol', 1e-4)))
-    q_opt = np.array(soln['x'][:len(A)])
+    tol = float(expr.pars.get('sdp_tol', 1e-4))
+    if shrunk is not None:
+        if expr.pars.get('lambda_', 0) > 0:
+            raise NotImplementedError('lambda_ > 0 (feature-regularised SDP, NNAL_tools.py:625-644) stays in the reference')
+        soln = NNAL_tools.SDP_query_distribution_from_shrunk(shrunk[0], shrunk[1], shrunk[2], k, tol=tol)
+        nA = shrunk[0].shape[1]
+    else:
+        soln = NNAL_tools.SDP_query_distribution(A, expr.pars.get('lambda_', 0), None, k, tol=tol)
+        nA = len(A)
+    q_opt = np.array(soln['x'][:nA])
     Q_inds = NNAL_tools.sample_query_dstr(q_opt.copy(), k, replacement=True)
     if dist.is_dist():
         buf = np.full(k + 1, -1, dtype=np.int64)
@@ -198,8 +206,8 @@ def query_single_sdp(expr, model, sess, padded_imgs, pool_inds, return_solution=
     post, g = eng.fi_shrunk_voxels(0, pool_inds[sel_inds[a:e]], expr.pars['patch_shape'],
                                    _stats_list(expr.pars['stats'], len(imgs)), L.NORM_BATCH_EVAL, shape=imgs[0].shape)
     post, g = _gather_shrunk(post, g)
-    A = _A_from_shrunk(g, post[1].astype(np.float64), float(expr.pars.get('fi_diag_load', 1e-5)), as_list=False)
-    Q_inds, soln = _sdp_sample(A, expr, return_solution)
+    Q_inds, soln = _sdp_sample(None, expr, return_solution,
+                               shrunk=(g, post[1].astype(np.float64), float(expr.pars.get('fi_diag_load', 1e-5))))
     q = sel_inds[Q_inds]
     return (q, soln, sel_inds) if return_solution else q
 
@@ -241,8 +249,7 @@ def query_multimg_sdp(expr, model, sess, all_padded_imgs, pool_inds, return_solu
     post = np.concatenate(posts, axis=1) if posts else np.zeros((2, 0), dtype=np.float32)
     g = np.concatenate(gs, axis=1) if gs else np.zeros((2, 0, tau))
     post, g = _gather_shrunk(post, g)
-    A = _A_from_shrunk(g, post[1].astype(np.float64), delta, as_list=False)
-    Q_inds, soln = _sdp_sample(A, expr, return_solution)
+    Q_inds, soln = _sdp_sample(None, expr, return_solution, shrunk=(g, post[1].astype(np.float64), delta))
     Q = patch_utils.global2local_inds(G[Q_inds], sizes)
     return (Q, soln, G) if return_solution else Q
 

@@ -312,3 +312,23 @@ def test_fallback_kernels_subprocess(env):
                        stderr=subprocess.STDOUT, timeout=600)
     out = r.stdout.decode()
     assert r.returncode == 0 and 'OK ' in out, out[-2000:]
+
+
+def test_sdp_from_shrunk_equals_host_assembly(nb):
+    """nnal_sdp_from_shrunk assembles the A-matrices of gen_A_matrices on the device: same q (bit for bit -- same
+    matrices, same deterministic solver) as the host assembly + nnal_sdp_query_distribution, incl. the clamped branches."""
+    from nnal_b200.PW_NNAL import _A_from_shrunk
+    rs = np.random.RandomState(31)
+    n, tau = 3000, 7
+    g = rs.randn(2, n, tau) * 1e-2
+    p = rs.rand(n)
+    p[:4] = [1e-9, 1 - 1e-9, 0., 1.]
+    eng = nb.get_engine()
+    A = _A_from_shrunk(g, p, 1e-5, as_list=False)
+    assert all(np.array_equal(a, b) for a, b in zip(A, O.gen_A_matrices(g[0], g[1], p, 1e-5)))
+    r0 = eng.sdp_query_distribution(A, tol=1e-4)
+    r1 = eng.sdp_from_shrunk(g, p, 1e-5, tol=1e-4)
+    assert r0['iterations'] == r1['iterations'] and np.array_equal(r0['q'], r1['q']) and r0['objective'] == r1['objective']
+    soln = nb.NNAL_tools.SDP_query_distribution_from_shrunk(g, p, 1e-5, 10)
+    assert soln['status'] == 'optimal' and np.array_equal(np.array(soln['x'][:n]), r0['q'])
+    assert np.allclose(nb.NNAL_tools.solve_FIAL_SDP(list(A[:200])), eng.sdp_query_distribution(A[:200])['q'])
