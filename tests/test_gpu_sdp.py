@@ -332,3 +332,45 @@ def test_sdp_from_shrunk_equals_host_assembly(nb):
     soln = nb.NNAL_tools.SDP_query_distribution_from_shrunk(g, p, 1e-5, 10)
     assert soln['status'] == 'optimal' and np.array_equal(np.array(soln['x'][:n]), r0['q'])
     assert np.allclose(nb.NNAL_tools.solve_FIAL_SDP(list(A[:200])), eng.sdp_query_distribution(A[:200])['q'])
+
+
+def test_config1_shape_whole_image_queries(nb):
+    """BASELINE config 1 at reduced pool size: the PW1 layer dictionary on 28x28x1 inputs with 10 classes (He-normal
+    weights, U[0,1) images) -- entropy, FI-trace and the literal multiclass FI pipeline through NNAL.CNN_query."""
+    layers = O.pw1_layers(10)
+    rs = np.random.RandomState(0)
+    n = 160
+    x = rs.rand(n, 28, 28, 1).astype(np.float32)
+    w = O.he_init_weights(layers, (28, 28, 1), 1, bias_scale=0.0)
+    model = nb.NN.CNN((28, 28, 1), OrderedDict(layers), feature_layer=len(layers) - 2)
+    model.set_weights(w)
+    r = O.forward(layers, w, x, feature_layer=len(layers) - 2)
+    post = r['posteriors']
+    # entropy: argsort(-H)[:10] (NNAL.py:298-310)
+    expr = Expr(k=10, B=40, lambda_=0., batch_size=64)
+    expr.pool_images = x
+    q = nb.NNAL.CNN_query(model, expr, np.arange(n), 'entropy', None)
+    H = O.compute_entropy(post.copy())
+    kth = np.sort(-H)[9]
+    assert len(q) == 10 and np.all(-H[q] <= kth + 1e-4) and np.all(np.isin(np.where(-H < kth - 1e-4)[0], q))
+    # fi (default): top-10 of the last-layer FI trace (NNAL.py:121-139)
+    q = nb.NNAL.CNN_query(model, expr, np.arange(n), 'fi', None)
+    score = O.fi_trace_score(post, r['feature_layer'])
+    kth = np.sort(-score)[9]
+    tol = 1e-3 * np.abs(score).max()
+    assert len(q) == 10 and np.all(-score[q] <= kth + tol)
+    # fi_mode='sdp': multiclass A-matrices (ten backward passes), SDP, sampling
+    expr.pars['fi_mode'] = 'sdp'
+    np.random.seed(4)
+    u = np.random.sample(10)
+    np.random.seed(4)
+    q, soln, sel = nb.fi.query_whole_sdp(model, expr, np.arange(n), None, return_solution=True)
+    assert soln['status'] == 'optimal' and len(sel) == 40
+    po, go = O.shrunk_class_gradients(layers, w, x[sel])
+    eng = nb.get_engine()
+    _, g = eng.fi_shrunk_images(x[sel])
+    _assert_shrunk_close(g, go)
+    A = O.gen_A_matrices_multiclass(po.copy(), go)
+    qo, to, phio, gapo, ito = O.sdp_solve(A, 1e-4)
+    assert abs(soln['primal objective'] / phio - 1) < OBJ_RTOL
+    assert np.array_equal(q, sel[O.sample_query_dstr(np.array(soln['x'][:40]), 10, u)])
