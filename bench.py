@@ -536,7 +536,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=5000)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--fi-B', type=int, default=10000, help='FI pre-filter size of the extra FI round (0: skip)')
-    ap.add_argument('--sdp-B', type=int, default=2000, help='candidates of the extra literal-FI (shrunk gradients + SDP) round at 1 GPU (0: skip)')
+    ap.add_argument('--sdp-B', type=int, default=10000, help='candidates of the extra literal-FI (shrunk gradients + SDP) round at 1 GPU (0: skip)')
     ap.add_argument('--mc-T', type=int, default=10, help='MC-dropout passes of the extra MC-entropy round (0: skip)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

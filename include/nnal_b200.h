@@ -71,7 +71,8 @@ int nnal_synchronize(nnal_ctx* ctx);
 void* nnal_stream(nnal_ctx* ctx);
 
 /* Per-kernel-class device timing (CUDA events on the context stream) for bench.py's roofline leg.
- * cls: layer index (0..n_layers-1), 100 gather, 101 scores, 102 top-k. */
+ * cls: layer index (0..n_layers-1), 100 gather, 101 scores, 102 top-k, 110-112 FI setup / Gram / greedy,
+ * 120 / 121 forward / backward of the shrunk-gradient pass. */
 int nnal_profile(nnal_ctx* ctx, int enable);
 int nnal_profile_read(nnal_ctx* ctx, int cls, double* total_ms, long long* count);
 

@@ -8,9 +8,11 @@
 //   fc   : sum gW = (sum_o dz_o)(sum_i a_i),            sum gb = sum_o dz_o
 //   conv : sum gW = sum_p (sum_co dz[p,co]) box[p],     sum gb = sum_p sum_co dz[p,co],
 //          box[p] = sum over the kh x kw window at p of sum_ci x_padded[.,ci]
-// What remains is a batched DATA-gradient backward pass: fp32 forward keeping every activation, then dz walks back
-// through fc (dz W), ReLU masks, max-pool (gradient to the first maximum of each window, as tf.nn.max_pool's gradient)
-// and conv (correlation of dz with the flipped filter).  For the binary model both class gradients are multiples of one
+// What remains is a batched DATA-gradient backward pass: forward keeping every activation as fp32 (tcgen05 conv / fc
+// kernels where the forward pass has them, unfused), then dz walks back through fc (dz W: the forward's split-plane
+// tcgen05 GEMM on power-of-two scaled gradients, fp32 CUDA cores for small layers), ReLU masks, max-pool (gradient to
+// the first maximum of each window, as tf.nn.max_pool's gradient) and conv (correlation of dz with the flipped filter,
+// fp32 CUDA cores).  For the binary model both class gradients are multiples of one
 // pass, d log p_0 = p_1 h, d log p_1 = -p_0 h with h = d(z_0 - z_1), and shrink_gradient is linear, so one pass serves both.
 #include "nnal_common.cuh"
 #include <algorithm>
@@ -310,8 +312,8 @@ int conv_bwd_data(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, i
 }
 
 // ---- fc data gradient: d[M][N] = dz[M][K] . W[K][N]  (W = the layer's [out][in] weight, read as stored) -------------
-// 128x128x16 tiles, 256 threads, 8x8 register micro-tiles; fp32 throughout (gradients span too many binades for the
-// fp16 hi/lo operand planes of the forward GEMM).
+// 128x128x16 tiles, 256 threads, 8x8 register micro-tiles; fp32 throughout.  Used where the tensor-core path below
+// does not apply (layers narrower than 64 or not a multiple of 8, nnal_set_tensor_cores(0)).
 #define BW_BM 128
 #define BW_BN 128
 #define BW_BK 16
