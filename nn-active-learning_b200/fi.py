@@ -11,6 +11,12 @@ pre-filter to B (:108-115, 549-551), conditional FIs of the B candidates, select
 * replaces SDP + sampling by the deterministic greedy minimisation of the SAME objective
   ``tr((sum_i q_i A_i)^-1)`` (NNAL_tools.py:589-602) at ``q = uniform(S)`` (FI section).
 
+``expr.pars['fi_mode'] = 'sdp'`` runs the reference's own pipeline instead (``query_single_sdp``, ``query_multimg_sdp``,
+``query_whole_sdp``): conditional FIs in the reference's shrunk coordinates from one batched backward pass on the device
+(csrc/shrunk.cu), the SDP query distribution by a certified first-order device solver (csrc/sdp.cu), and
+``NNAL_tools.sample_query_dstr`` with NumPy's global generator (<= k unique positions, as upstream); optional keys
+``sdp_tol`` (default 1e-4) and ``fi_diag_load``.
+
 ``expr.pars`` keys read: ``k``, ``B`` (reference keys) and the optional ``fi_layers`` (1 or 2) and
 ``fi_diag_load`` (the reference's ``diag_load``: 1e-5 single-volume PW_NNAL.py:738-745, 1e-3 multi-volume
 :573-578)."""
