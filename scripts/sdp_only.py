@@ -14,7 +14,7 @@ from nnal_b200.PW_NNAL import _A_from_shrunk
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 rs = np.random.RandomState(0)
-shape = (96, 96, 8)
+shape = (96, 96, 8) if B <= 60000 else (128, 128, 16)
 imgs = [np.clip(rs.randn(*shape) * 30 + 100, 0, None).astype(np.float32) for _ in range(3)]
 padded = [np.pad(im, ((12, 12), (12, 12), (0, 0)), 'constant') for im in imgs]
 stats = np.array([[im.mean(), im.std()] for im in imgs], dtype=np.float64)
