@@ -260,32 +260,29 @@ def query_multimg_sdp(expr, model, sess, all_padded_imgs, pool_inds, return_solu
     return (Q, soln, G) if return_solution else Q
 
 
-def _A_multiclass_from_shrunk(sel_posteriors, g):
-    """The multiclass A-matrix assembly inlined in NNAL.CNN_query (NNAL.py:354-414) from shrunk gradients ``g``
-    [c,B,tau]: posteriors < 1e-6 zeroed IN PLACE (:361-362), the rest renormalised, all classes if fewer than 10 are
-    non-zero else the 10 largest renormalised again (:379-400), ``A_i = sum_j [g_j g_j^T / p_j + 1e-5 I]`` -- the
-    diagonal load once PER CLASS, as written (:404-409)."""
-    c, B = sel_posteriors.shape
+def _A_multiclass_from_shrunk(sel_posteriors, g, diag_load=1e-5, max_classes=10):
+    """Multiclass conditional FIs in shrunk coordinates as NNAL.CNN_query builds them inline (NNAL.py:354-414), from the
+    device's shrunk gradients ``g`` [c,B,tau].  Per candidate: posteriors below 1e-6 are zeroed IN PLACE in the caller's
+    array (:361-362) and the survivors renormalised (:364-365); with ten or more survivors only the ten most probable are
+    kept and renormalised once more (:379-400); every kept class j adds ``g_j g_j^T / p_j`` AND one ``diag_load * I``
+    (:404-409 -- the load is inside the class loop upstream, so it scales with the number of kept classes)."""
     tau = g.shape[2]
-    A = []
-    for i in range(B):
-        x_posterior = sel_posteriors[:, i]
-        x_posterior[x_posterior < 1e-6] = 0.
-        nz_classes = np.where(x_posterior > 0.)[0]
-        nz_posts = x_posterior[nz_classes] / np.sum(x_posterior[nz_classes])
-        if len(nz_classes) < 10:
-            sel_classes, new_posts = nz_classes, nz_posts
-        else:
-            sel_nz = np.argsort(-nz_posts, kind='stable')[:10]
-            sel_classes = nz_classes[sel_nz]
-            new_posts = nz_posts[sel_nz]
-            new_posts = new_posts / np.sum(new_posts)
+    load = np.eye(tau) * diag_load
+    out = []
+    for i in range(sel_posteriors.shape[1]):
+        col = sel_posteriors[:, i]                   # a view: the zeroing below is visible to the caller, as upstream
+        col[col < 1e-6] = 0.
+        keep = np.flatnonzero(col > 0.)
+        w = col[keep] / np.sum(col[keep])
+        if len(keep) >= max_classes:
+            top = np.argsort(-w, kind='stable')[:max_classes]
+            keep, w = keep[top], w[top]
+            w = w / np.sum(w)
         Ai = np.zeros((tau, tau))
-        for j in range(len(sel_classes)):
-            sg = g[sel_classes[j], i]
-            Ai += np.outer(sg, sg) / new_posts[j] + np.eye(tau) * 1e-5
-        A += [Ai]
-    return A
+        for j, cls in enumerate(keep):
+            Ai += np.outer(g[cls, i], g[cls, i]) / w[j] + load
+        out.append(Ai)
+    return out
 
 
 def query_whole_sdp(model, expr, pool_inds, session, return_solution=False):
