@@ -201,6 +201,100 @@ def main():
     gold['kc_Q'] = np.array(Qk)
     print('get_self_sims / get_cross_sims / facility-location / k-center loops: oracle == reference')
 
+    # ---- the SDP the reference hands to cvxopt (NNAL_tools.SDP_query_distribution :612-659 with lambda_ = 0, constraint
+    # matrices from inequality_cvx_matrix :661-720), captured from the UNMODIFIED reference functions: cvxopt itself is
+    # absent, so `matrix` is replaced by a shape-preserving float64 array type (what cvxopt.matrix makes of a NumPy array)
+    # and `solvers.sdp` by a recorder.  The oracle's solution must be feasible for exactly these constraints and its
+    # objective c^T x must equal tr((sum q_i A_i)^-1): this pins the PROGRAMME (not cvxopt's arithmetic).
+    class FakeMatrix(np.ndarray):
+        def __new__(cls, a):
+            arr = np.array(a, dtype=np.float64)
+            if arr.ndim == 0:
+                arr = arr.reshape(1, 1)
+            elif arr.ndim == 1:
+                arr = arr.reshape(-1, 1)              # cvxopt makes a column of a 1-D array
+            return arr.view(cls)
+
+        def trans(self):
+            return FakeMatrix(np.asarray(self).T)
+
+    captured = {}
+
+    class FakeSolvers(object):
+        options = {}
+
+        @staticmethod
+        def sdp(c, Gs=None, hs=None, A=None, b=None):
+            captured.update(c=np.asarray(c), Gs=[np.asarray(g) for g in Gs], hs=[np.asarray(h) for h in hs],
+                            A=np.asarray(A), b=np.asarray(b))
+            return {'status': 'captured', 'x': np.zeros(len(c))}
+
+    ref_tools.matrix, ref_tools.solvers = FakeMatrix, FakeSolvers
+    n_s, tau_s = 12, 3
+    sg = rs.randn(2, n_s, tau_s) * 0.05
+    sp = rs.rand(n_s)
+    A_s = O.gen_A_matrices(sg[0], sg[1], sp, 1e-3)
+    ref_tools.SDP_query_distribution(A_s, 0., None, 5)
+    c_vec, Gs, hs, A_eq, b_eq = captured['c'], captured['Gs'], captured['hs'], captured['A'], captured['b']
+    assert c_vec.shape == (n_s + tau_s, 1) and len(Gs) == tau_s + 1 and A_eq.shape == (1, n_s + tau_s)
+    qs, ts, phis, gaps, its = O.sdp_solve(A_s, 1e-8)
+    xs = np.concatenate([qs, ts])
+    assert abs((A_eq @ xs).item() - b_eq.item()) < 1e-12                      # sum q = 1
+    assert abs((c_vec[:, 0] @ xs).item() - phis) < 1e-9 * phis                # objective = sum_j t_j = tr(M^-1)
+    M_s = np.tensordot(qs, np.array(A_s), axes=(0, 0))
+    for j in range(tau_s + 1):
+        m = int(round(np.sqrt(Gs[j].shape[0])))
+        slack = (hs[j] - (Gs[j] @ xs).reshape(m, m)).astype(np.float64)     # cvxopt: G x + s = h, s >= 0 (PSD)
+        slack = (slack + slack.T) / 2
+        assert np.linalg.eigvalsh(slack).min() > -1e-9 * np.abs(slack).max(), j
+        if j < tau_s:                                                       # [[sum q_i A_i, e_j], [e_j^T, t_j]]
+            e = np.zeros((tau_s, 1)); e[j] = 1
+            blk = np.block([[M_s, e], [e.T, np.array([[ts[j]]])]])
+            assert np.allclose(slack, blk, rtol=1e-12, atol=1e-15), j
+        else:                                                               # positivity block: diag(q)
+            assert np.allclose(slack, np.diag(qs), rtol=1e-12, atol=1e-15)
+    gold['sdp_A'] = np.array(A_s)
+    gold['sdp_c'] = c_vec
+    for j in range(tau_s + 1):
+        gold['sdp_G%d' % j] = Gs[j]
+        gold['sdp_h%d' % j] = hs[j]
+    gold['sdp_Aeq'], gold['sdp_beq'] = A_eq, b_eq
+    gold['sdp_q'], gold['sdp_t'], gold['sdp_phi'] = qs, ts, np.array(phis)
+    print('SDP_query_distribution / inequality_cvx_matrix: the reference\'s programme (captured c, G, h, A, b) == '
+          'min tr((sum q_i A_i)^-1) over the simplex; oracle solution feasible, objective equal')
+
+    # ---- PW_NNAL.gen_A_matrices (:738-816), UNMODIFIED, driven by a fake session whose run() returns the explicit
+    # tf.gradients-shaped lists [gW_1, gb_1, ...] of the float64 restatement: pins the per-sample loop, the two clamped
+    # branches, shrink_gradient and the diagonal load against the oracle's closed form on the factored gradients.
+    layers_b = [('conv1', [4, 'conv', [3, 3]]), ('max1', [[2, 2], 'pool']), ('conv2', [6, 'conv', [3, 3]]),
+                ('fc1', [10, 'fc']), ('fc2', [2, 'fc'])]
+    w_b = O.he_init_weights(layers_b, (7, 7, 2), 13, bias_scale=0.1)
+    xb = rs.randn(6, 7, 7, 2)
+    tau_b = 4
+
+    class FakeModel(object):
+        x, keep_prob = 'x', 'keep_prob'
+        grad_posts = {'0': [(0, t) for t in range(2 * tau_b)], '1': [(1, t) for t in range(2 * tau_b)]}
+
+    class FakeSess(object):
+        def run(self, fetches, feed_dict=None):
+            y = fetches[0][0]
+            return O.explicit_class_gradients(layers_b, w_b, feed_dict['x'], y)
+
+    class FakeExpr(object):
+        pars = {'patch_shape': (7, 7, 1)}
+        nclass = 2
+    post_b, g_b = O.shrunk_class_gradients(layers_b, w_b, xb)
+    sel_posts_b = post_b[1].copy()
+    sel_posts_b[0], sel_posts_b[1] = 1e-7, 1 - 1e-7                          # the clamped branches (:770-793)
+    A_ref = ref_pw.gen_A_matrices(FakeExpr(), FakeModel(), FakeSess(), xb, sel_posts_b, 1e-5)
+    A_ora = O.gen_A_matrices(g_b[0], g_b[1], sel_posts_b, 1e-5)
+    assert len(A_ref) == 6 and A_ref[0].shape == (tau_b, tau_b)
+    for a, b in zip(A_ref, A_ora):
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-18)
+    gold['genA_x'], gold['genA_posts'], gold['genA_out'] = xb, sel_posts_b, np.array(A_ref)
+    print('gen_A_matrices: reference (fake session with explicit gradients) == oracle closed form')
+
     np.savez_compressed(os.path.join(GOLD, 'reference_numpy_helpers.npz'), **gold)
     print('wrote', os.path.join(GOLD, 'reference_numpy_helpers.npz'))
 

@@ -383,3 +383,13 @@ def test_config1_shape_whole_image_queries(nb):
     qo, to, phio, gapo, ito = O.sdp_solve(A, 1e-4)
     assert abs(soln['primal objective'] / phio - 1) < OBJ_RTOL
     assert np.array_equal(q, sel[O.sample_query_dstr(np.array(soln['x'][:40]), 10, u)])
+
+
+def test_sdp_device_solution_feasible_for_reference_programme(nb, golden):
+    """The device solver's (q, t) satisfies the constraints the unmodified reference hands to cvxopt (golden) and reaches
+    the reference objective c^T x of the float64 solution within the certified tolerance."""
+    from tests.util import assert_feasible_for_reference_sdp
+    r = nb.get_engine().sdp_query_distribution(golden['sdp_A'], tol=1e-6)
+    obj = assert_feasible_for_reference_sdp(golden, r['q'], r['t'] * (1 + 1e-12))
+    assert abs(obj / r['objective'] - 1) < 1e-9
+    assert 0 <= obj / float(golden['sdp_phi']) - 1 < 1e-5

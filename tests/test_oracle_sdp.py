@@ -85,3 +85,33 @@ def test_multiclass_A_assembly_matches_oracle():
     Ao = O.gen_A_matrices_multiclass(post.copy(), g)
     Ah = _A_multiclass_from_shrunk(post.copy(), g)
     assert all(np.array_equal(a, b) for a, b in zip(Ah, Ao))
+
+
+def test_sdp_programme_golden(golden):
+    """The oracle's solution is feasible for the constraint matrices built by the reference's own
+    SDP_query_distribution / inequality_cvx_matrix (golden, captured from the unmodified functions), the reference
+    objective c^T x equals tr((sum q_i A_i)^-1), and no feasible point of that programme built from another q does better."""
+    from tests.util import assert_feasible_for_reference_sdp
+    A = golden['sdp_A']
+    q, t, phi, gap, it = O.sdp_solve(A, 1e-8)
+    assert np.allclose(q, golden['sdp_q'], rtol=1e-9, atol=1e-14) and np.allclose(t, golden['sdp_t'], rtol=1e-9)
+    obj = assert_feasible_for_reference_sdp(golden, q, t)
+    assert abs(obj / phi - 1) < 1e-9 and abs(obj / float(golden['sdp_phi']) - 1) < 1e-9
+    rs = np.random.RandomState(3)
+    for _ in range(30):
+        qq = rs.dirichlet(np.ones(len(q)))
+        tt = np.diag(np.linalg.inv(np.tensordot(qq, A, axes=(0, 0))))      # the smallest feasible t for this q
+        assert assert_feasible_for_reference_sdp(golden, qq, tt * (1 + 1e-9), tol=1e-7) >= obj * (1 - 1e-7)
+
+
+def test_gen_A_matrices_golden(golden):
+    """Golden output of the UNMODIFIED PW_NNAL.gen_A_matrices (driven by a fake session, see
+    oracle/check_against_reference.py) == oracle closed form == the package's host assembly."""
+    from nnal_b200.PW_NNAL import _A_from_shrunk
+    layers = [('conv1', [4, 'conv', [3, 3]]), ('max1', [[2, 2], 'pool']), ('conv2', [6, 'conv', [3, 3]]),
+              ('fc1', [10, 'fc']), ('fc2', [2, 'fc'])]
+    w = O.he_init_weights(layers, (7, 7, 2), 13, bias_scale=0.1)
+    post, g = O.shrunk_class_gradients(layers, w, golden['genA_x'])
+    A = O.gen_A_matrices(g[0], g[1], golden['genA_posts'], 1e-5)
+    assert np.allclose(np.array(A), golden['genA_out'], rtol=1e-9, atol=1e-18)
+    assert np.array_equal(np.array(_A_from_shrunk(g, golden['genA_posts'], 1e-5)), np.array(A))

@@ -44,3 +44,19 @@ def assert_topk_equivalent(got, scores, k, tol):
     must = np.where(scores < kth - tol)[0]
     assert np.all(np.isin(must, got)), 'missed a sample clearly inside the top-k'
     assert np.all(np.diff(scores[got]) >= -tol), 'not in ascending score order'
+
+
+def assert_feasible_for_reference_sdp(golden, q, t, tol=1e-9):
+    """(q, t) against the constraint data the UNMODIFIED reference hands to cvxopt (captured by
+    oracle/check_against_reference.py from NNAL_tools.SDP_query_distribution / inequality_cvx_matrix): A x = b, every
+    slack h_j - G_j x positive semi-definite.  Returns the reference objective c^T x."""
+    x = np.concatenate([q, t])
+    assert abs((golden['sdp_Aeq'] @ x).item() - golden['sdp_beq'].item()) < 1e-9
+    tau = len(t)
+    for j in range(tau + 1):
+        G, h = golden['sdp_G%d' % j], golden['sdp_h%d' % j]
+        m = h.shape[0]
+        slack = h - (G @ x).reshape(m, m)
+        slack = (slack + slack.T) / 2
+        assert np.linalg.eigvalsh(slack).min() > -tol * np.abs(slack).max(), 'LMI %d violated' % j
+    return (golden['sdp_c'][:, 0] @ x).item()
