@@ -30,14 +30,14 @@ def import_reference():
               'matplotlib.pyplot', 'pydensecrf', 'pydensecrf.utils', 'pydensecrf.densecrf']:
         sys.modules.setdefault(m, MagicMock())
     sys.path.insert(0, REF)
-    import patch_utils, NNAL_tools, PW_NNAL   # noqa: E401
-    return patch_utils, NNAL_tools, PW_NNAL
+    import patch_utils, NNAL_tools, PW_NNAL, PW_NN   # noqa: E401
+    return patch_utils, NNAL_tools, PW_NNAL, PW_NN
 
 
 def main():
     sys.path.insert(0, ROOT)
     import oracle as O
-    ref_pu, ref_tools, ref_pw = import_reference()
+    ref_pu, ref_tools, ref_pw, ref_pwnn = import_reference()
     os.makedirs(GOLD, exist_ok=True)
     gold = {}
 
@@ -294,6 +294,130 @@ def main():
         assert np.allclose(a, b, rtol=1e-9, atol=1e-18)
     gold['genA_x'], gold['genA_posts'], gold['genA_out'] = xb, sel_posts_b, np.array(A_ref)
     print('gen_A_matrices: reference (fake session with explicit gradients) == oracle closed form')
+
+    # ---- the query dispatch itself, UNMODIFIED, over a fake TF session: PW_NN.batch_eval (:357-539; batching, gather,
+    # normalisation, sess.run, P(class 1) slice), PW_NNAL.CNN_query 'entropy' (:51-65), bin_uncertainty_filter_multimg
+    # (:684-736) and query_multimg 'entropy' (:226-230).  sess.run(model.posteriors / feature_layer) is answered by the
+    # float64 restatement of the TF graph on the float32-cast feed (TF casts the float64 patches to the placeholder's
+    # float32), so everything AROUND the graph is the reference's own code.
+    from collections import OrderedDict   # noqa: F401
+    ps_q, m_q, S_q = (5, 5, 1), 2, 3
+    shape_q = (12, 11, 4)
+    layers_q = [('conv1', [4, 'conv', [3, 3]]), ('max1', [[2, 2], 'pool']), ('fc1', [16, 'fc']), ('fc2', [12, 'fc']),
+                ('fc3', [2, 'fc'])]
+    w_q = O.he_init_weights(layers_q, (5, 5, m_q), 7, bias_scale=0.1)
+    fl_q = len(layers_q) - 2
+
+    class FakeDim(object):
+        def __init__(self, v):
+            self.value = v
+
+    class FakeTensor(object):
+        def __init__(self, name, shape):
+            self.name, self.shape = name, [FakeDim(d) for d in shape]
+
+    class QModel(object):
+        x, keep_prob = 'x', 'keep_prob'
+        posteriors = FakeTensor('posteriors', (2, None))
+        feature_layer = FakeTensor('feature_layer', (12, None))
+
+    class QSess(object):
+        def run(self, var, feed_dict=None):
+            r = O.forward(layers_q, w_q, np.asarray(feed_dict['x']).astype(np.float32), feature_layer=fl_q)
+            return r[var.name]
+
+    allp_q, pools_q, st_q = [], [], np.zeros((S_q, 2 * m_q))
+    for s_ in range(S_q):
+        imgs = [np.clip(rs.randn(*shape_q) * 30 + 100, 0, None).astype(np.float32) for _ in range(m_q)]
+        allp_q.append([np.pad(im, ((2, 2), (2, 2), (0, 0)), 'constant') for im in imgs] +
+                      [(rs.rand(*shape_q) > .5).astype(np.int8)])
+        pools_q.append(list(rs.choice(int(np.prod(shape_q)), [70, 0, 95][s_], replace=False)))
+        for j in range(m_q):
+            st_q[s_, 2 * j], st_q[s_, 2 * j + 1] = imgs[j].mean(), imgs[j].std()
+    stats0 = [[st_q[0, 2 * j], st_q[0, 2 * j + 1]] for j in range(m_q)]
+    pool0 = np.array(pools_q[0])
+
+    class QExpr(object):
+        pars = dict(k=9, B=30, lambda_=0., patch_shape=ps_q, ntb=16, stats=stats0, img_paths=[None] * m_q)
+        train_stats = st_q
+        nclass = 2
+    # batch_eval: posteriors and feature_layer, batch size not dividing n
+    rp, rf = ref_pwnn.batch_eval(QModel(), QSess(), allp_q[0][:m_q], pool0, ps_q, 16, stats0, ['posteriors', 'feature_layer'])
+    op_, of_ = O.batch_eval(layers_q, w_q, allp_q[0][:m_q], pool0, ps_q, 16, stats0, ['posteriors', 'feature_layer'])
+    assert np.array_equal(rp, op_) and np.array_equal(rf, of_)
+    # single-volume entropy query
+    rq = ref_pw.CNN_query(QExpr(), QModel(), QSess(), allp_q[0][:m_q], pool0, None, 'entropy')
+    oq, _ = O.query_entropy_single(layers_q, w_q, allp_q[0][:m_q], pool0, ps_q, 16, stats0, 9)
+    assert np.array_equal(rq, oq)
+    # multi-volume filter and entropy query (one subject with an empty pool)
+    rsel, rposts = ref_pw.bin_uncertainty_filter_multimg(QExpr(), QModel(), QSess(), allp_q, pools_q, 25)
+    osel, oposts = O.bin_uncertainty_filter_multimg(layers_q, w_q, allp_q, pools_q, ps_q, 16, st_q, 25)
+    for a, b in zip(rsel, osel):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    for a, b in zip(rposts, oposts):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    rQ = ref_pw.query_multimg(QExpr(), QModel(), QSess(), allp_q, pools_q, None, 'entropy')
+    oQ = O.query_entropy_multimg(layers_q, w_q, allp_q, pools_q, ps_q, 16, st_q, 9)
+    for a, b in zip(rQ, oQ):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    # ---- the whole single-volume 'fi' branch of PW_NNAL.CNN_query (:89-163), UNMODIFIED: posteriors -> B most uncertain
+    # -> get_patches + normalise -> gen_A_matrices (sess.run(model.grad_posts[y]) answered with the restatement's explicit
+    # gradient lists) -> refine_feature_matrix -> NNAL_tools.SDP_query_distribution (solvers.sdp answered by the oracle's
+    # solver on the A-matrices recovered from the constraint matrix it is handed) -> sample_query_dstr (np.random seeded).
+    tau_q = 4
+
+    class FiModel(QModel):
+        grad_posts = {'0': [(0, t) for t in range(2 * tau_q)], '1': [(1, t) for t in range(2 * tau_q)]}
+
+    class FiSess(QSess):
+        def run(self, var, feed_dict=None):
+            if isinstance(var, list):
+                return O.explicit_class_gradients(layers_q, w_q, np.asarray(feed_dict['x']).astype(np.float32), var[0][0])
+            return QSess.run(self, var, feed_dict)
+
+    class OracleSolvers(object):
+        options = {}
+        last = {}
+
+        @staticmethod
+        def sdp(c, Gs=None, hs=None, A=None, b=None):
+            G0 = np.asarray(Gs[0])
+            nvar = G0.shape[1]
+            d1 = int(round(np.sqrt(G0.shape[0])))
+            nq = nvar - (d1 - 1)
+            A_rec = [(-G0[:, i]).reshape(d1, d1).T[:d1 - 1, :d1 - 1] for i in range(nq)]
+            q, t, phi, gap, it = O.sdp_solve(A_rec, 1e-4)
+            OracleSolvers.last = {'A': np.array(A_rec), 'q': q, 'phi': phi}
+            return {'status': 'optimal', 'x': np.concatenate([q, t])}
+
+    ref_tools.solvers = OracleSolvers
+    np.random.seed(77)
+    u77 = np.random.sample(9)
+    np.random.seed(77)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):        # the branch prints the condition number / solver status
+        rq_fi = ref_pw.CNN_query(QExpr(), FiModel(), FiSess(), allp_q[0][:m_q], pool0, None, 'fi')
+    oq_fi, det = O.query_fi_sdp_single(layers_q, w_q, allp_q[0][:m_q], pool0, ps_q, 16, stats0, 9, 30, u77, diag_load=1e-5)
+    A_o = np.array(det['A'])                                # explicit vs closed-form shrink: round-off only
+    assert np.allclose(OracleSolvers.last['A'], A_o, rtol=1e-9, atol=1e-12 * np.abs(A_o).max())
+    assert np.array_equal(np.asarray(rq_fi), oq_fi), (rq_fi, oq_fi)
+    gold['q_fi_sdp_single'] = np.asarray(rq_fi)
+    gold['q_fi_u'] = u77
+    ref_tools.solvers = FakeSolvers
+    print("PW_NNAL.CNN_query 'fi' (gen_A_matrices + SDP_query_distribution + sample_query_dstr), unmodified over fake "
+          "session / solver: oracle.query_fi_sdp_single == reference")
+
+    gold['q_imgs'] = np.stack([np.stack(a[:m_q]) for a in allp_q])
+    gold['q_stats'] = st_q
+    for s_ in range(S_q):
+        gold['q_pool%d' % s_] = np.array(pools_q[s_], dtype=np.int64)
+        gold['q_multi%d' % s_] = np.asarray(rQ[s_], dtype=np.int64)
+        gold['q_filt%d' % s_] = np.asarray(rsel[s_], dtype=np.int64)
+    gold['q_single'] = np.asarray(rq)
+    gold['q_posts0'] = rp
+    print('PW_NN.batch_eval / PW_NNAL.CNN_query / bin_uncertainty_filter_multimg / query_multimg (entropy), unmodified '
+          'over a fake session: oracle == reference')
 
     np.savez_compressed(os.path.join(GOLD, 'reference_numpy_helpers.npz'), **gold)
     print('wrote', os.path.join(GOLD, 'reference_numpy_helpers.npz'))

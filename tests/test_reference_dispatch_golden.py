@@ -1,0 +1,80 @@
+"""Golden vectors produced by the UNMODIFIED reference query dispatch (PW_NN.batch_eval, PW_NNAL.CNN_query 'entropy' and
+'fi', bin_uncertainty_filter_multimg, query_multimg 'entropy') run over a fake TF session / fake cvxopt solver by
+oracle/check_against_reference.py -- everything around the TF graph and the SDP solve is the reference's own code.  The
+oracle must reproduce them from the stored inputs (CPU); the device path is held to them on the GPU box."""
+import numpy as np
+import pytest
+
+import oracle as O
+from tests.util import assert_topk_equivalent
+
+PS, M, S = (5, 5, 1), 2, 3
+LAYERS = [('conv1', [4, 'conv', [3, 3]]), ('max1', [[2, 2], 'pool']), ('fc1', [16, 'fc']), ('fc2', [12, 'fc']),
+          ('fc3', [2, 'fc'])]
+
+
+def _case(golden):
+    w = O.he_init_weights(LAYERS, (5, 5, M), 7, bias_scale=0.1)
+    imgs = golden['q_imgs']
+    allp = [[imgs[s][j] for j in range(M)] + [np.zeros((12, 11, 4), dtype=np.int8)] for s in range(S)]
+    pools = [list(golden['q_pool%d' % s]) for s in range(S)]
+    st = golden['q_stats']
+    stats0 = [[st[0, 2 * j], st[0, 2 * j + 1]] for j in range(M)]
+    return w, allp, pools, st, stats0
+
+
+def test_oracle_reproduces_reference_dispatch(golden):
+    w, allp, pools, st, stats0 = _case(golden)
+    pool0 = np.array(pools[0])
+    posts = O.batch_eval(LAYERS, w, allp[0][:M], pool0, PS, 16, stats0, 'posteriors')[0]
+    assert np.array_equal(posts, golden['q_posts0'])
+    q, _ = O.query_entropy_single(LAYERS, w, allp[0][:M], pool0, PS, 16, stats0, 9)
+    assert np.array_equal(q, golden['q_single'])
+    sel, _ = O.bin_uncertainty_filter_multimg(LAYERS, w, allp, pools, PS, 16, st, 25)
+    Q = O.query_entropy_multimg(LAYERS, w, allp, pools, PS, 16, st, 9)
+    for s in range(S):
+        assert np.array_equal(np.asarray(sel[s], dtype=np.int64), golden['q_filt%d' % s])
+        assert np.array_equal(np.asarray(Q[s], dtype=np.int64), golden['q_multi%d' % s])
+    qf, det = O.query_fi_sdp_single(LAYERS, w, allp[0][:M], pool0, PS, 16, stats0, 9, 30, golden['q_fi_u'], diag_load=1e-5)
+    assert np.array_equal(qf, golden['q_fi_sdp_single'])
+
+
+@pytest.mark.gpu
+def test_device_matches_reference_dispatch(golden):
+    """The product's PW_NNAL.CNN_query / query_multimg on the same inputs: the reference's selections up to ties within the
+    posterior tolerance; the literal 'fi' pipeline returns the reference's sample for the same uniform draws."""
+    from collections import OrderedDict
+    import nnal_b200
+
+    class Expr(object):
+        pass
+    w, allp, pools, st, stats0 = _case(golden)
+    pool0 = np.array(pools[0])
+    model = nnal_b200.NN.CNN((5, 5, M), OrderedDict(LAYERS), feature_layer=len(LAYERS) - 2)
+    model.set_weights(w)
+    expr = Expr()
+    expr.pars = dict(k=9, B=30, lambda_=0., patch_shape=PS, ntb=16, stats=stats0, img_paths=[None] * M)
+    expr.train_stats, expr.nclass = st, 2
+    q = nnal_b200.PW_NNAL.CNN_query(expr, model, None, allp[0][:M], pool0, None, 'entropy')
+    assert_topk_equivalent(q, np.abs(golden['q_posts0'] - .5), 9, 2e-4)
+    Q = nnal_b200.PW_NNAL.query_multimg(expr, model, None, allp, pools, None, 'entropy')
+    assert len(Q) == S and len(Q[1]) == 0
+    ref = [golden['q_multi%d' % s] for s in range(S)]
+    assert sum(len(a) for a in Q) == sum(len(a) for a in ref)
+    assert sum(len(set(np.asarray(a).tolist()) ^ set(b.tolist())) for a, b in zip(Q, ref)) <= 2      # ties at the boundary
+    expr.pars['fi_mode'] = 'sdp'
+    np.random.seed(77)                                    # the generator state the golden run sampled with
+    assert np.allclose(np.random.sample(9), golden['q_fi_u'])
+    np.random.seed(77)
+    qf, soln, sel = nnal_b200.fi.query_single_sdp(expr, model, None, allp[0][:M], pool0, return_solution=True)
+    assert soln['status'] == 'optimal'
+    # exact: the reference's sampler replayed on the device's q with the golden run's uniform draws
+    q_dev = np.array(soln['x'][:len(sel)])
+    assert np.array_equal(qf, sel[O.sample_query_dstr(q_dev.copy(), 9, golden['q_fi_u'])])
+    # the SDP objective of the golden run's pipeline (float64) within the north star's 1e-3
+    _, det = O.query_fi_sdp_single(LAYERS, w, allp[0][:M], pool0, PS, 16, stats0, 9, 30, golden['q_fi_u'], diag_load=1e-5)
+    assert abs(soln['primal objective'] / det['phi'] - 1) < 1e-3
+    # the minimiser q is not unique and the draws land in cumulative-sum bins, so single positions may differ from the
+    # reference's sample; the bulk must coincide
+    got, want = set(np.asarray(qf).tolist()), set(golden['q_fi_sdp_single'].tolist())
+    assert got <= set(sel.tolist()) and len(got & want) >= len(want) - 3, (sorted(got), sorted(want))
