@@ -404,6 +404,46 @@ def main():
     assert np.array_equal(np.asarray(rq_fi), oq_fi), (rq_fi, oq_fi)
     gold['q_fi_sdp_single'] = np.asarray(rq_fi)
     gold['q_fi_u'] = u77
+    # the multi-volume twin (:547-627, 'CVXOPT' branch) -- its live pdb.set_trace() (:612) is made a no-op
+    class MExpr(QExpr):
+        pars = dict(QExpr.pars, k=11, B=40, SDP_solver='CVXOPT')
+    ref_pw.pdb.set_trace = lambda *a, **k: None
+    np.random.seed(78)
+    u78 = np.random.sample(11)
+    np.random.seed(78)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rQ_fi = ref_pw.query_multimg(MExpr(), FiModel(), FiSess(), allp_q, pools_q, None, 'fi')
+    oQ_fi, _ = O.query_fi_sdp_multimg(layers_q, w_q, allp_q, pools_q, ps_q, 16, st_q, 11, 40, u78)
+    assert len(rQ_fi) == S_q
+    for a, b in zip(rQ_fi, oQ_fi):
+        assert np.array_equal(np.asarray(a), np.asarray(b)), (rQ_fi, oQ_fi)
+    for s_ in range(S_q):
+        gold['q_fi_sdp_multi%d' % s_] = np.asarray(rQ_fi[s_], dtype=np.int64)
+    gold['q_fi_u_multi'] = u78
+    # representativeness queries of query_multimg: 'rep-entropy' (:284-351) and 'core-set' (:353-451)
+    class RExpr(QExpr):
+        pars = dict(QExpr.pars, k=11, B=30)
+        labeled_stats = st_q
+        labeled_paths = train_paths = ['same']
+    # (upstream, these two branches call batch_eval on every subject and raise IndexError on an empty per-subject pool,
+    # PW_NN.py:447-449: subject 1 gets a pool here)
+    pools_r = [pools_q[0], list(rs.choice(int(np.prod(shape_q)), 20, replace=False)), pools_q[2]]
+    rQ_rep = ref_pw.query_multimg(RExpr(), QModel(), QSess(), allp_q, pools_r, None, 'rep-entropy')
+    oQ_rep, _ = O.query_rep_entropy_multimg(layers_q, w_q, allp_q, pools_r, ps_q, 16, st_q, 11, 30)
+    for a, b in zip(rQ_rep, oQ_rep):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    labeled_q = [list(rs.choice(int(np.prod(shape_q)), 9, replace=False)) for _ in range(S_q)]
+    ref_pw.NN.gen_batch_inds = lambda n, b: [np.arange(i, min(i + b, n)) for i in range(0, n, b)]   # NN.py helper (TF-free)
+    rQ_cs = ref_pw.query_multimg(RExpr(), QModel(), QSess(), allp_q, pools_r, labeled_q, 'core-set')
+    oQ_cs, _ = O.query_core_set_multimg(layers_q, w_q, allp_q, pools_r, labeled_q, ps_q, 16, st_q, st_q, 11)
+    for a, b in zip(rQ_cs, oQ_cs):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    for s_ in range(S_q):
+        gold['q_rep%d' % s_] = np.asarray(rQ_rep[s_], dtype=np.int64)
+        gold['q_cs%d' % s_] = np.asarray(rQ_cs[s_], dtype=np.int64)
+        gold['q_labeled%d' % s_] = np.array(labeled_q[s_], dtype=np.int64)
+        gold['q_pool_r%d' % s_] = np.array(pools_r[s_], dtype=np.int64)
+    print("PW_NNAL.query_multimg 'fi' / 'rep-entropy' / 'core-set', unmodified over fake session / solver: oracle == reference")
     ref_tools.solvers = FakeSolvers
     print("PW_NNAL.CNN_query 'fi' (gen_A_matrices + SDP_query_distribution + sample_query_dstr), unmodified over fake "
           "session / solver: oracle.query_fi_sdp_single == reference")

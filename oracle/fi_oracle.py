@@ -29,6 +29,7 @@ __all__ = [
     'last_layers_kernel', 'last_layers_dim', 'weighted_gram', 'fi_objective_from_gram',
     'sample_query_dstr', 'append_zero', 'last_layers_factors', 'greedy_fi_replay', 'query_fi_single',
     'query_fi_multimg', 'sdp_certificate', 'sdp_solve', 'sdp_solve_slsqp', 'query_fi_sdp_single',
+    'query_fi_sdp_multimg',
 ]
 
 
@@ -401,6 +402,34 @@ def query_fi_sdp_single(layers, weights, padded_imgs, pool_inds, patch_shape, nt
     q, t, phi, gap, it = sdp_solve(A, tol)
     Q = sample_query_dstr(q.copy(), k, u)
     return sel[Q], {'sel': sel, 'A': A, 'q': q, 't': t, 'phi': phi, 'gap': gap, 'g': g, 'post': post, 'x': x}
+
+
+def query_fi_sdp_multimg(layers, weights, all_padded_imgs, pool_inds, patch_shape, ntb, train_stats, k, B, u,
+                         diag_load=1e-3, tol=1e-4):
+    """PW_NNAL.query_multimg 'fi' as the reference runs it (PW_NNAL.py:547-627, 'CVXOPT' branch, lambda_ = 0, without
+    the live pdb.set_trace() of :612): B most uncertain samples of the concatenated pool (:549-551) -> per-subject
+    patches normalised by get_patches_multimg (:554-558) -> A-matrices subject by subject with diag_load 1e-3 and the
+    filter's posteriors (:566-578) -> SDP (:601-606) -> sample_query_dstr with the k uniform draws ``u`` (:614-615) ->
+    global2local_inds over the per-subject candidate counts (:617-622).  Returns (list of per-subject local positions
+    into ``pool_inds[s]``, details)."""
+    from .nnal_oracle import bin_uncertainty_filter_multimg, global2local_inds, get_patches_multimg
+    s = len(pool_inds)
+    sel_inds, sel_posts = bin_uncertainty_filter_multimg(layers, weights, all_padded_imgs, pool_inds, patch_shape, ntb,
+                                                         train_stats, B)
+    img_inds = [np.array(pool_inds[i])[sel_inds[i]] for i in range(s)]
+    patches, _ = get_patches_multimg(all_padded_imgs, img_inds, patch_shape, train_stats)
+    A = []
+    for i in range(s):
+        if len(img_inds[i]) == 0:
+            continue
+        post, g = shrunk_class_gradients(layers, weights, np.asarray(patches[i]).astype(np.float32))
+        A += gen_A_matrices(g[0], g[1], sel_posts[i], diag_load)
+    q, t, phi, gap, it = sdp_solve(A, tol)
+    draws = sample_query_dstr(q.copy(), k, u)
+    sizes = [len(sel_inds[i]) for i in range(s)]
+    local = global2local_inds(draws, sizes)
+    Q = [np.array(sel_inds[i])[local[i]] for i in range(s)]
+    return Q, {'A': A, 'q': q, 'phi': phi, 'gap': gap, 'sel_inds': sel_inds}
 
 
 def fi_objective_direct(Abar, S, delta):

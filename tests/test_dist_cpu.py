@@ -67,7 +67,10 @@ def test_single_process_matches_oracle(runs):
     u = np.random.RandomState(1000).random_sample(9)
     qs, det = O.query_fi_sdp_single(layers, w, allp[0][:m], pool0, ps, 16, stats0, 9, 30, u, diag_load=1e-3)
     assert np.array_equal(one['fi_sdp_single'], qs) and 0 < len(qs) <= 9
-    assert sum(len(one['fi_sdp_multi%d' % s]) for s in range(3)) <= 11 and len(one['fi_sdp_multi1']) == 0
+    Qs, _ = O.query_fi_sdp_multimg(layers, w, allp, pools, ps, 16, st, 11, 40, np.random.RandomState(2000).random_sample(11))
+    for s in range(3):
+        assert np.array_equal(one['fi_sdp_multi%d' % s], Qs[s])
+    assert len(one['fi_sdp_multi1']) == 0
     Q = O.query_entropy_multimg(layers, w, allp, pools, ps, 16, st, 11)
     for s in range(3):
         assert np.array_equal(one['ent_multi%d' % s], Q[s])

@@ -37,6 +37,17 @@ def test_oracle_reproduces_reference_dispatch(golden):
         assert np.array_equal(np.asarray(Q[s], dtype=np.int64), golden['q_multi%d' % s])
     qf, det = O.query_fi_sdp_single(LAYERS, w, allp[0][:M], pool0, PS, 16, stats0, 9, 30, golden['q_fi_u'], diag_load=1e-5)
     assert np.array_equal(qf, golden['q_fi_sdp_single'])
+    Qf, _ = O.query_fi_sdp_multimg(LAYERS, w, allp, pools, PS, 16, st, 11, 40, golden['q_fi_u_multi'])
+    for s in range(S):
+        assert np.array_equal(np.asarray(Qf[s], dtype=np.int64), golden['q_fi_sdp_multi%d' % s])
+    # representativeness queries (pools without an empty subject: upstream raises on one in these branches)
+    pools_r = [list(golden['q_pool_r%d' % s]) for s in range(S)]
+    labeled = [list(golden['q_labeled%d' % s]) for s in range(S)]
+    Qr, _ = O.query_rep_entropy_multimg(LAYERS, w, allp, pools_r, PS, 16, st, 11, 30)
+    Qc, _ = O.query_core_set_multimg(LAYERS, w, allp, pools_r, labeled, PS, 16, st, st, 11)
+    for s in range(S):
+        assert np.array_equal(np.asarray(Qr[s], dtype=np.int64), golden['q_rep%d' % s])
+        assert np.array_equal(np.asarray(Qc[s], dtype=np.int64), golden['q_cs%d' % s])
 
 
 @pytest.mark.gpu
