@@ -444,6 +444,67 @@ def main():
         gold['q_labeled%d' % s_] = np.array(labeled_q[s_], dtype=np.int64)
         gold['q_pool_r%d' % s_] = np.array(pools_r[s_], dtype=np.int64)
     print("PW_NNAL.query_multimg 'fi' / 'rep-entropy' / 'core-set', unmodified over fake session / solver: oracle == reference")
+    # MC-dropout queries of query_multimg: 'MC-entropy' (:232-244) and 'BALD' (:247-282), unmodified.  The fake session
+    # plays tf.nn.dropout with the oracle's counter-based masks: it counts the samples it is fed (subjects and batches
+    # arrive in pool order) to know their global pool positions and the pass they belong to.
+    from oracle import mc_oracle as Mc
+    n_tot = sum(len(p_) for p_ in pools_q)
+    drop_layers, keep_q, seed_q, first_q = [2, 3, 4], 0.6, 77, 3
+
+    class McModel(QModel):
+        dropout_rate = keep_q
+
+    class McSess(object):
+        def __init__(self):
+            self.seen = 0
+
+        def run(self, var, feed_dict=None):
+            xb_ = np.asarray(feed_dict['x']).astype(np.float32)
+            kp = feed_dict['keep_prob']
+            assert var.name == 'posteriors' and kp == keep_q
+            pass_id, off = divmod(self.seen, n_tot)
+            self.seen += xb_.shape[0]
+            pos = off + np.arange(xb_.shape[0])
+            return Mc.forward_dropout(layers_q, w_q, xb_, pos, kp, drop_layers, seed_q, first_q + pass_id)[1]
+
+    class McExpr(QExpr):
+        pars = dict(QExpr.pars, k=11, B=40, MC_iters=4)
+    for meth, key in (('MC-entropy', 'q_mc'), ('BALD', 'q_bald')):
+        rQ_mc = ref_pw.query_multimg(McExpr(), McModel(), McSess(), allp_q, pools_q, None, meth)
+        oQ_mc = Mc.query_mc_multimg(layers_q, w_q, allp_q, pools_q, ps_q, st_q, 11, 4, keep_q, drop_layers, seed_q, meth,
+                                    first_pass=first_q)[0]
+        for s_ in range(S_q):
+            assert np.array_equal(np.asarray(rQ_mc[s_]), np.asarray(oQ_mc[s_])), (meth, rQ_mc, oQ_mc)
+            gold['%s%d' % (key, s_)] = np.asarray(rQ_mc[s_], dtype=np.int64)
+    print("PW_NNAL.query_multimg 'MC-entropy' / 'BALD', unmodified over a fake session with the oracle's dropout masks: "
+          "oracle == reference")
+    # committee queries of query_multimg, no-label branch: 'ensemble' (:453-490) and 'QBC-JS' (:492-545), unmodified.
+    # expr.model_holder.perform_assign_ops(path, sess) switches the weight set the fake session evaluates.
+    wsets = [O.he_init_weights(layers_q, (5, 5, m_q), 20 + i, bias_scale=0.1) for i in range(3)]
+
+    class Holder(QModel):
+        current = [0]
+
+        def perform_assign_ops(self, path, sess):
+            Holder.current[0] = path
+
+    class CSess(object):
+        def run(self, var, feed_dict=None):
+            assert feed_dict['keep_prob'] == 1.
+            r = O.forward(layers_q, wsets[Holder.current[0]], np.asarray(feed_dict['x']).astype(np.float32), feature_layer=fl_q)
+            return r[var.name]
+
+    class CExpr(QExpr):
+        pars = dict(QExpr.pars, k=11, B=40)
+        model_holder = Holder()
+        pretrained_paths = [0, 1, 2]
+    for meth, key in (('ensemble', 'q_ens'), ('QBC-JS', 'q_qbc')):
+        rQ_c = ref_pw.query_multimg(CExpr(), None, CSess(), allp_q, pools_q, [[], [], []], meth)
+        oQ_c = Mc.query_committee_multimg(layers_q, wsets, allp_q, pools_q, ps_q, 16, st_q, 11, meth)[0]
+        for s_ in range(S_q):
+            assert np.array_equal(np.asarray(rQ_c[s_]), np.asarray(oQ_c[s_])), (meth, rQ_c, oQ_c)
+            gold['%s%d' % (key, s_)] = np.asarray(rQ_c[s_], dtype=np.int64)
+    print("PW_NNAL.query_multimg 'ensemble' / 'QBC-JS' (no-label branch), unmodified over a fake session: oracle == reference")
     ref_tools.solvers = FakeSolvers
     print("PW_NNAL.CNN_query 'fi' (gen_A_matrices + SDP_query_distribution + sample_query_dstr), unmodified over fake "
           "session / solver: oracle.query_fi_sdp_single == reference")

@@ -48,6 +48,17 @@ def test_oracle_reproduces_reference_dispatch(golden):
     for s in range(S):
         assert np.array_equal(np.asarray(Qr[s], dtype=np.int64), golden['q_rep%d' % s])
         assert np.array_equal(np.asarray(Qc[s], dtype=np.int64), golden['q_cs%d' % s])
+    # MC-dropout and committee queries (dropout masks of the golden run: seed 77, first pass 3, keep 0.6, FC layers)
+    from oracle import mc_oracle as Mc
+    for meth, key in (('MC-entropy', 'q_mc'), ('BALD', 'q_bald')):
+        Qm = Mc.query_mc_multimg(LAYERS, w, allp, pools, PS, st, 11, 4, 0.6, [2, 3, 4], 77, meth, first_pass=3)[0]
+        for s in range(S):
+            assert np.array_equal(np.asarray(Qm[s], dtype=np.int64), golden['%s%d' % (key, s)])
+    wsets = [O.he_init_weights(LAYERS, (5, 5, M), 20 + i, bias_scale=0.1) for i in range(3)]
+    for meth, key in (('ensemble', 'q_ens'), ('QBC-JS', 'q_qbc')):
+        Qc = Mc.query_committee_multimg(LAYERS, wsets, allp, pools, PS, 16, st, 11, meth)[0]
+        for s in range(S):
+            assert np.array_equal(np.asarray(Qc[s], dtype=np.int64), golden['%s%d' % (key, s)])
 
 
 @pytest.mark.gpu
