@@ -21,7 +21,8 @@ vectors in ``tests/golden/``:
   code): PW_NN.batch_eval, PW_NNAL.CNN_query 'entropy' and 'fi',
   bin_uncertainty_filter_multimg, every method of PW_NNAL.query_multimg
   (entropy, fi, rep-entropy, core-set, MC-entropy, BALD, ensemble, QBC-JS),
-  gen_A_matrices, and the SDP programme (c, G, h, A, b) that
+  NNAL.CNN_query 'entropy' / 'rep-entropy' / 'fi' (image loader replaced by an
+  in-memory pool), gen_A_matrices, and the SDP programme (c, G, h, A, b) that
   SDP_query_distribution / inequality_cvx_matrix hand to cvxopt.
 * "Parity unpinned": the arithmetic INSIDE TensorFlow 1.x (conv/pool/fc/softmax
   forward, tf.gradients, dropout masks) and inside cvxopt -- TF 1.x is not

@@ -433,7 +433,6 @@ def main():
     for a, b in zip(rQ_rep, oQ_rep):
         assert np.array_equal(np.asarray(a), np.asarray(b))
     labeled_q = [list(rs.choice(int(np.prod(shape_q)), 9, replace=False)) for _ in range(S_q)]
-    ref_pw.NN.gen_batch_inds = lambda n, b: [np.arange(i, min(i + b, n)) for i in range(0, n, b)]   # NN.py helper (TF-free)
     rQ_cs = ref_pw.query_multimg(RExpr(), QModel(), QSess(), allp_q, pools_r, labeled_q, 'core-set')
     oQ_cs, _ = O.query_core_set_multimg(layers_q, w_q, allp_q, pools_r, labeled_q, ps_q, 16, st_q, st_q, 11)
     for a, b in zip(rQ_cs, oQ_cs):
@@ -519,6 +518,67 @@ def main():
     gold['q_posts0'] = rp
     print('PW_NN.batch_eval / PW_NNAL.CNN_query / bin_uncertainty_filter_multimg / query_multimg (entropy), unmodified '
           'over a fake session: oracle == reference')
+
+    # ---- whole-image dispatch NNAL.CNN_query (:188-525) 'entropy' and 'fi', UNMODIFIED: only the image-file loader
+    # NN.load_winds (cv2, commented out upstream) is replaced by an in-memory pool; NNAL_tools.idxBatch_posteriors and
+    # NN.gen_batch_inds (random batches) are the reference's own.
+    import NNAL as ref_nnal
+    layers_w = [('conv1', [6, 'conv', [3, 3]]), ('conv2', [5, 'conv', [5, 5]]), ('max1', [[2, 2], 'pool']),
+                ('conv3', [8, 'conv', [3, 3]]), ('max2', [[2, 2], 'pool']),
+                ('fc1', [40, 'fc']), ('fc2', [24, 'fc']), ('fc3', [3, 'fc'])]
+    w_w = O.he_init_weights(layers_w, (9, 7, 2), 6, bias_scale=0.1)
+    pool_w = rs.rand(90, 9, 7, 2).astype(np.float32)
+    tau_w = 6
+
+    class WOut(object):
+        def get_shape(self):
+            return [FakeDim(3), FakeDim(None)]
+
+    class WModel(object):
+        x = 'x'
+        posteriors = FakeTensor('posteriors', (3, None))
+        output = WOut()
+        grad_posts = {str(y): [(y, t) for t in range(2 * tau_w)] for y in range(3)}
+
+        def extract_features(self, inds, expr, session):
+            return O.forward(layers_w, w_w, pool_w[np.asarray(inds)], feature_layer=len(layers_w) - 2)['feature_layer']
+
+    class WSess(object):
+        def run(self, var, feed_dict=None):
+            xw = np.asarray(feed_dict['x']).astype(np.float32)
+            if isinstance(var, dict):
+                return {key: O.explicit_class_gradients(layers_w, w_w, xw, int(key)) for key in var}
+            return O.forward(layers_w, w_w, xw)['posteriors']
+
+    class WExpr(object):
+        pars = dict(k=7, B=20, lambda_=0, batch_size=32, target_shape=None, mean=None)
+        imgs_path_file = None
+    ref_nnal.NN.load_winds = lambda inds, path_file, target_shape, mean: (pool_w[np.asarray(inds)], None)
+    ref_tools.NN.load_winds = ref_nnal.NN.load_winds
+    np.random.seed(5)
+    rq_w = ref_nnal.CNN_query(WModel(), WExpr(), np.arange(90), 'entropy', WSess())
+    oq_w = O.query_entropy_whole(layers_w, w_w, pool_w, 7)[0]
+    assert np.array_equal(np.asarray(rq_w), np.asarray(oq_w))
+    ref_tools.solvers = OracleSolvers
+    np.random.seed(6)
+    with contextlib.redirect_stdout(io.StringIO()):
+        # draws of the sampler: the reference consumes np.random for its batches first, so replay the same sequence
+        rq_wfi = ref_nnal.CNN_query(WModel(), WExpr(), np.arange(90), 'fi', WSess())
+    np.random.seed(6)
+    np.random.permutation(90)                      # NN.gen_batch_inds inside idxBatch_posteriors (n >= batch_size)
+    u_w = np.random.sample(7)
+    oq_wfi, _ = O.query_fi_sdp_whole(layers_w, w_w, pool_w, 7, 20, u_w)
+    assert np.array_equal(np.asarray(rq_wfi), oq_wfi), (rq_wfi, oq_wfi)
+    ref_tools.solvers = FakeSolvers
+    np.random.seed(7)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rq_wrep = ref_nnal.CNN_query(WModel(), WExpr(), np.arange(90), 'rep-entropy', WSess())
+    oq_wrep, _ = O.query_rep_entropy_whole(layers_w, w_w, pool_w, 7, 20)
+    assert np.array_equal(np.asarray(rq_wrep), np.asarray(oq_wrep)), (rq_wrep, oq_wrep)
+    gold['w_rep'] = np.asarray(rq_wrep)
+    gold['w_pool'], gold['w_entropy'], gold['w_fi_sdp'], gold['w_fi_u'] = pool_w, np.asarray(rq_w), np.asarray(rq_wfi), u_w
+    print("NNAL.CNN_query 'entropy' / 'rep-entropy' / 'fi' (multiclass A-matrices + SDP + sampling), unmodified over fake session / solver / "
+          "in-memory pool: oracle == reference")
 
     np.savez_compressed(os.path.join(GOLD, 'reference_numpy_helpers.npz'), **gold)
     print('wrote', os.path.join(GOLD, 'reference_numpy_helpers.npz'))

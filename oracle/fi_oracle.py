@@ -29,7 +29,7 @@ __all__ = [
     'last_layers_kernel', 'last_layers_dim', 'weighted_gram', 'fi_objective_from_gram',
     'sample_query_dstr', 'append_zero', 'last_layers_factors', 'greedy_fi_replay', 'query_fi_single',
     'query_fi_multimg', 'sdp_certificate', 'sdp_solve', 'sdp_solve_slsqp', 'query_fi_sdp_single',
-    'query_fi_sdp_multimg',
+    'query_fi_sdp_multimg', 'query_fi_sdp_whole',
 ]
 
 
@@ -430,6 +430,27 @@ def query_fi_sdp_multimg(layers, weights, all_padded_imgs, pool_inds, patch_shap
     local = global2local_inds(draws, sizes)
     Q = [np.array(sel_inds[i])[local[i]] for i in range(s)]
     return Q, {'A': A, 'q': q, 'phi': phi, 'gap': gap, 'sel_inds': sel_inds}
+
+
+def query_fi_sdp_whole(layers, weights, pool_x, k, B, u, tol=1e-4):
+    """NNAL.CNN_query 'fi' as the reference runs it (NNAL.py:312-464) with lambda_ = 0 on an in-memory pool ``pool_x``
+    [n,H,W,C]: posteriors -> uncertainty_filtering to B (:326-333) -> multiclass A-matrices in shrunk coordinates
+    (:354-414) -> SDP query distribution (:456-459) -> sample_query_dstr with the k uniform draws ``u`` (:462-464).
+    Returns (positions into the pool, details)."""
+    from .nnal_oracle import uncertainty_filtering
+    r = forward(layers, weights, pool_x)
+    posteriors = r['posteriors']
+    if B < posteriors.shape[1]:
+        sel = uncertainty_filtering(posteriors, B)
+        sel_post = posteriors[:, sel]
+    else:
+        sel = np.arange(posteriors.shape[1])
+        sel_post = posteriors
+    post, g = shrunk_class_gradients(layers, weights, pool_x[sel])
+    A = gen_A_matrices_multiclass(sel_post, g)
+    q, t, phi, gap, it = sdp_solve(A, tol)
+    Q = sample_query_dstr(q.copy(), k, u)
+    return sel[Q], {'sel': sel, 'A': A, 'q': q, 'phi': phi, 'gap': gap}
 
 
 def fi_objective_direct(Abar, S, delta):

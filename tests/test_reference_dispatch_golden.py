@@ -61,6 +61,50 @@ def test_oracle_reproduces_reference_dispatch(golden):
             assert np.array_equal(np.asarray(Qc[s], dtype=np.int64), golden['%s%d' % (key, s)])
 
 
+LAYERS_W = [('conv1', [6, 'conv', [3, 3]]), ('conv2', [5, 'conv', [5, 5]]), ('max1', [[2, 2], 'pool']),
+            ('conv3', [8, 'conv', [3, 3]]), ('max2', [[2, 2], 'pool']),
+            ('fc1', [40, 'fc']), ('fc2', [24, 'fc']), ('fc3', [3, 'fc'])]
+
+
+def test_oracle_reproduces_reference_whole_image_dispatch(golden):
+    """NNAL.CNN_query 'entropy', 'rep-entropy' and the literal multiclass 'fi' pipeline (c = 3)."""
+    w = O.he_init_weights(LAYERS_W, (9, 7, 2), 6, bias_scale=0.1)
+    x = golden['w_pool']
+    assert np.array_equal(O.query_entropy_whole(LAYERS_W, w, x, 7)[0], golden['w_entropy'])
+    assert np.array_equal(O.query_rep_entropy_whole(LAYERS_W, w, x, 7, 20)[0], golden['w_rep'])
+    assert np.array_equal(O.query_fi_sdp_whole(LAYERS_W, w, x, 7, 20, golden['w_fi_u'])[0], golden['w_fi_sdp'])
+
+
+@pytest.mark.gpu
+def test_device_matches_reference_whole_image_dispatch(golden):
+    from collections import OrderedDict
+    import nnal_b200
+
+    class Expr(object):
+        pass
+    w = O.he_init_weights(LAYERS_W, (9, 7, 2), 6, bias_scale=0.1)
+    x = golden['w_pool']
+    model = nnal_b200.NN.CNN((9, 7, 2), OrderedDict(LAYERS_W), feature_layer=len(LAYERS_W) - 2)
+    model.set_weights(w)
+    expr = Expr()
+    expr.pars = dict(k=7, B=20, lambda_=0., batch_size=32)
+    expr.pool_images = x
+    post = O.forward(LAYERS_W, w, x)['posteriors']
+    q = nnal_b200.NNAL.CNN_query(model, expr, np.arange(90), 'entropy', None)
+    assert_topk_equivalent(q, -O.compute_entropy(post.copy()), 7, 2e-4)
+    assert len(set(q.tolist()) ^ set(golden['w_entropy'].tolist())) <= 2
+    q = nnal_b200.NNAL.CNN_query(model, expr, np.arange(90), 'rep-entropy', None)
+    assert len(set(np.asarray(q).tolist()) ^ set(golden['w_rep'].tolist())) <= 2
+    expr.pars['fi_mode'] = 'sdp'
+    q, soln, sel = nnal_b200.fi.query_whole_sdp(model, expr, np.arange(90), None, return_solution=True)
+    _, det = O.query_fi_sdp_whole(LAYERS_W, w, x, 7, 20, golden['w_fi_u'])
+    assert soln['status'] == 'optimal' and abs(soln['primal objective'] / det['phi'] - 1) < 1e-3
+    assert len(set(sel.tolist()) ^ set(det['sel'].tolist())) <= 2
+    q_dev = np.array(soln['x'][:len(sel)])
+    replay = sel[O.sample_query_dstr(q_dev.copy(), 7, golden['w_fi_u'])]
+    assert len(set(replay.tolist()) & set(golden['w_fi_sdp'].tolist())) >= len(golden['w_fi_sdp']) - 3
+
+
 @pytest.mark.gpu
 def test_device_matches_reference_dispatch(golden):
     """The product's PW_NNAL.CNN_query / query_multimg on the same inputs: the reference's selections up to ties within the
