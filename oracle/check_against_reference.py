@@ -477,6 +477,18 @@ def main():
             gold['%s%d' % (key, s_)] = np.asarray(rQ_mc[s_], dtype=np.int64)
     print("PW_NNAL.query_multimg 'MC-entropy' / 'BALD', unmodified over a fake session with the oracle's dropout masks: "
           "oracle == reference")
+    # single-volume CNN_query 'MC-entropy' (:67-87) AS WRITTEN hands x_feed_dict to batch_eval in the `mask` slot: every
+    # pass runs with keep_prob = 1 and the query equals 'entropy'.  (The drop-in applies dropout, as query_multimg does.)
+    class NoDropSess(QSess):
+        def run(self, var, feed_dict=None):
+            assert feed_dict['keep_prob'] == 1.
+            return QSess.run(self, var, feed_dict)
+
+    class Mc1Expr(QExpr):
+        pars = dict(QExpr.pars, MC_iters=3)
+    rq_mc1 = ref_pw.CNN_query(Mc1Expr(), McModel(), NoDropSess(), allp_q[0][:m_q], pool0, None, 'MC-entropy')
+    assert np.array_equal(np.asarray(rq_mc1), np.asarray(rq))
+    print("PW_NNAL.CNN_query 'MC-entropy' (single volume) as written == 'entropy': x_feed_dict lands in batch_eval's mask slot")
     # committee queries of query_multimg, no-label branch: 'ensemble' (:453-490) and 'QBC-JS' (:492-545), unmodified.
     # expr.model_holder.perform_assign_ops(path, sess) switches the weight set the fake session evaluates.
     wsets = [O.he_init_weights(layers_q, (5, 5, m_q), 20 + i, bias_scale=0.1) for i in range(3)]
@@ -518,6 +530,35 @@ def main():
     gold['q_posts0'] = rp
     print('PW_NN.batch_eval / PW_NNAL.CNN_query / bin_uncertainty_filter_multimg / query_multimg (entropy), unmodified '
           'over a fake session: oracle == reference')
+
+    # ---- NNAL_tools.FC_gradnorms_batch (:725-775), UNMODIFIED over a fake session: squared gradient norms of P(class 0)
+    # w.r.t. every FC layer, back-propagated with ReLU masks ("last two layers' scores")
+    fwd_fc = O.forward(layers_q, w_q, rs.randn(13, 5, 5, m_q).astype(np.float32), keep_acts=True)
+    fc_names = [n_ for n_, sp_ in layers_q if sp_[1] == 'fc']
+    idx_of = {n_: i_ for i_, (n_, _) in enumerate(layers_q)}
+
+    class EvalW(object):
+        def __init__(self, W):
+            self.W = W
+
+        def eval(self):
+            return self.W.astype(np.float64)
+
+    class GModel(object):
+        x, keep_prob, posteriors = 'x', 'keep_prob', 'posteriors'
+        FC_inputs = [(n_, ('in', n_)) for n_ in fc_names]
+        var_dict = {n_: [EvalW(w_q[n_][0]), None] for n_ in fc_names}
+
+    class GSess(object):
+        def run(self, var, feed_dict=None):
+            if var == 'posteriors':
+                return fwd_fc['posteriors']
+            return fwd_fc['acts'][idx_of[var[1]]]['in']
+    rn = ref_tools.FC_gradnorms_batch(GModel(), np.zeros((13, 1)), GSess())
+    on = O.FC_gradnorms_batch(fwd_fc['posteriors'], [fwd_fc['acts'][idx_of[n_]]['in'] for n_ in fc_names],
+                              [w_q[n_][0].astype(np.float64) for n_ in fc_names])
+    assert rn.shape == on.shape == (3, 13) and np.array_equal(rn, on)
+    print('FC_gradnorms_batch: oracle == reference (fake session)')
 
     # ---- whole-image dispatch NNAL.CNN_query (:188-525) 'entropy' and 'fi', UNMODIFIED: only the image-file loader
     # NN.load_winds (cv2, commented out upstream) is replaced by an in-memory pool; NNAL_tools.idxBatch_posteriors and
