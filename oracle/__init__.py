@@ -22,7 +22,7 @@ vectors in ``tests/golden/``:
   bin_uncertainty_filter_multimg, every method of PW_NNAL.query_multimg
   (entropy, fi, rep-entropy, core-set, MC-entropy, BALD, ensemble, QBC-JS),
   NNAL.CNN_query 'entropy' / 'rep-entropy' / 'fi' (image loader replaced by an
-  in-memory pool), gen_A_matrices, and the SDP programme (c, G, h, A, b) that
+  in-memory pool), gen_A_matrices, FC_gradnorms_batch, LLFC_grads, LLFC_hess, and the SDP programme (c, G, h, A, b) that
   SDP_query_distribution / inequality_cvx_matrix hand to cvxopt.
 * "Parity unpinned": the arithmetic INSIDE TensorFlow 1.x (conv/pool/fc/softmax
   forward, tf.gradients, dropout masks) and inside cvxopt -- TF 1.x is not

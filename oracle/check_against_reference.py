@@ -621,6 +621,34 @@ def main():
     print("NNAL.CNN_query 'entropy' / 'rep-entropy' / 'fi' (multiclass A-matrices + SDP + sampling), unmodified over fake session / solver / "
           "in-memory pool: oracle == reference")
 
+    # ---- NN.LLFC_grads (:905-955) and NN.LLFC_hess (:874-903), UNMODIFIED over a fake session: last-layer score
+    # factors [(e_y - pi) (x) u ; (e_y - pi)] and the Hessian kron(A(pi), [u;1][u;1]^T)
+    import NN as ref_nn
+    r3 = O.forward(layers_w, w_w, pool_w[:9], feature_layer=len(layers_w) - 2)
+
+    class LModel(object):
+        posteriors, feature_layer, prediction = 'posteriors', 'feature_layer', 'prediction'
+
+    class LSess(object):
+        def __init__(self, cols):
+            self.cols = cols
+
+        def run(self, var, feed_dict=None):
+            if var == 'prediction':
+                return np.argmax(r3['posteriors'][:, self.cols], axis=0)
+            return r3[var][:, self.cols]
+    allc = np.arange(9)
+    rg, rlab = ref_nn.LLFC_grads(LModel(), LSess(allc), None)
+    og = O.LLFC_grads(r3['posteriors'], r3['feature_layer'])
+    og = og[0] if isinstance(og, tuple) else og
+    assert np.array_equal(rg, og) and np.array_equal(rlab, np.argmax(r3['posteriors'], axis=0))
+    lab = rs.randint(0, 3, 9)
+    assert np.array_equal(ref_nn.LLFC_grads(LModel(), LSess(allc), None, lab), O.LLFC_grads(r3['posteriors'], r3['feature_layer'], lab))
+    rH = ref_nn.LLFC_hess(LModel(), LSess(np.array([4])), None)
+    oH = O.LLFC_hess(r3['posteriors'][:, 4:5], r3['feature_layer'][:, 4:5])
+    assert rH.shape == oH.shape and np.allclose(rH, oH, rtol=1e-13, atol=0)
+    print('LLFC_grads / LLFC_hess: oracle == reference (fake session)')
+
     np.savez_compressed(os.path.join(GOLD, 'reference_numpy_helpers.npz'), **gold)
     print('wrote', os.path.join(GOLD, 'reference_numpy_helpers.npz'))
 
