@@ -477,6 +477,16 @@ def main():
             gold['%s%d' % (key, s_)] = np.asarray(rQ_mc[s_], dtype=np.int64)
     print("PW_NNAL.query_multimg 'MC-entropy' / 'BALD', unmodified over a fake session with the oracle's dropout masks: "
           "oracle == reference")
+    # 'random' (:32-35, :198-205): the drop-in's host code against the reference's, same generator state
+    import nnal_b200
+    np.random.seed(91)
+    rq_rand = ref_pw.CNN_query(QExpr(), None, None, allp_q[0][:m_q], pool0, None, 'random')
+    rQ_rand = ref_pw.query_multimg(QExpr(), None, None, allp_q, pools_q, None, 'random')
+    np.random.seed(91)
+    pq_rand = nnal_b200.PW_NNAL.CNN_query(QExpr(), None, None, allp_q[0][:m_q], pool0, None, 'random')
+    pQ_rand = nnal_b200.PW_NNAL.query_multimg(QExpr(), None, None, allp_q, pools_q, None, 'random')
+    assert np.array_equal(rq_rand, pq_rand) and all(np.array_equal(a, b) for a, b in zip(rQ_rand, pQ_rand))
+    print("'random' queries: drop-in host code == reference (same np.random state)")
     # single-volume CNN_query 'MC-entropy' (:67-87) AS WRITTEN hands x_feed_dict to batch_eval in the `mask` slot: every
     # pass runs with keep_prob = 1 and the query equals 'entropy'.  (The drop-in applies dropout, as query_multimg does.)
     class NoDropSess(QSess):
