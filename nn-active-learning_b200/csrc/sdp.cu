@@ -12,6 +12,8 @@
 // and is used until phi increases for the first time, then 1/2).  Convexity gives the certificate
 //     phi(q) - phi* <= max_i d_i - phi(q),
 // so the loop stops when max_i d_i / phi - 1 <= tol: the objective is then within tol (relative) of the SDP optimum.
+// The matrices are symmetric: only the tau (tau + 1) / 2 entries a <= b are stored, summed and multiplied (off-diagonal
+// entries weigh twice in <M^-2, A_i>).
 // One kernel per iteration; every CTA rebuilds M from the previous iteration's per-CTA partial sums (fixed order:
 // deterministic), inverts it in shared memory, updates its samples and writes the next partial sums.  All float64.
 #include "nnal_common.cuh"
@@ -37,26 +39,39 @@ SdpState* sdp_state(nnal_ctx* ctx) {
   return (SdpState*)ctx->sdp_state;
 }
 
-// layout of one set of per-CTA partial sums: [G][T2] sums of q_i A_i, then [G] sums of q_i, then [G] max_i d_i / phi
+// layout of one set of per-CTA partial sums: [G][Tu] packed sums of q_i A_i, then [G] sums of q_i, then [G] max_i d_i / phi
 struct Parts {
   double* M;
   double* Z;
   double* R;
 };
-__host__ __device__ inline Parts parts_of(double* base, int G, int T2) {
+__host__ __device__ inline Parts parts_of(double* base, int G, int Tu) {
   Parts p;
   p.M = base;
-  p.Z = base + (size_t)G * T2;
+  p.Z = base + (size_t)G * Tu;
   p.R = p.Z + G;
   return p;
 }
 
-__global__ void sdp_transpose_kernel(const double* __restrict__ A, double* __restrict__ At, int64_t n, int T2) {
-  const int64_t total = n * T2;
+// packed upper-triangular index u <-> (a, b), a <= b, row-major: u = a tau - a (a - 1) / 2 + (b - a)
+__host__ __device__ inline int sdp_packed(int tau) { return tau * (tau + 1) / 2; }
+__device__ __forceinline__ void sdp_unpack(int u, int tau, int& a, int& b) {
+  a = 0;
+  while (u >= tau - a) { u -= tau - a; ++a; }
+  b = a + u;
+}
+
+// dense host matrices [n][tau][tau] -> packed [Tu][n] (the mean of the two mirrored entries: the matrix itself when it
+// is exactly symmetric)
+__global__ void sdp_transpose_kernel(const double* __restrict__ A, double* __restrict__ At, int64_t n, int tau) {
+  const int Tu = sdp_packed(tau), T2 = tau * tau;
+  const int64_t total = n * Tu;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = e / T2;
-    const int ab = (int)(e - i * T2);
-    At[(int64_t)ab * n + i] = A[e];
+    const int u = (int)(e / n);
+    const int64_t i = e - (int64_t)u * n;
+    int a, b;
+    sdp_unpack(u, tau, a, b);
+    At[e] = 0.5 * (A[i * T2 + a * tau + b] + A[i * T2 + b * tau + a]);
   }
 }
 
@@ -65,12 +80,13 @@ __global__ void sdp_transpose_kernel(const double* __restrict__ A, double* __res
 // with the reference's order of operations ((1-p) * (g0_a * g0_b), then + p * (g1_a * g1_b), then + diag_load).
 __global__ void sdp_binary_A_kernel(const double* __restrict__ g, const double* __restrict__ p1, int64_t n, int tau,
                                     double diag_load, double* __restrict__ At) {
-  const int T2 = tau * tau;
-  const int64_t total = n * T2;
+  const int Tu = sdp_packed(tau);
+  const int64_t total = n * Tu;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int ab = (int)(e / n);
-    const int64_t i = e - (int64_t)ab * n;
-    const int a = ab / tau, b = ab % tau;
+    const int u = (int)(e / n);
+    const int64_t i = e - (int64_t)u * n;
+    int a, b;
+    sdp_unpack(u, tau, a, b);
     double p = p1[i];
     const bool lo = p < 1e-6, hi = p > 1.0 - 1e-6;
     if (lo) p = 0.0;
@@ -102,18 +118,18 @@ __device__ __forceinline__ double warp_max(double v) {
 
 // M = (sum of the partial sums) / Z; in-place Gauss-Jordan inverse (M is positive definite: no pivoting); P = Minv^2.
 // All threads of the CTA call this; returns phi = tr(Minv), Z and the largest ratio of the previous iterate to every
-// thread.  The G x (T2 + 2) partial values live in L2 (written by other CTAs): the reads are spread over all threads
+// thread.  The G x (Tu + 2) partial values live in L2 (written by other CTAs): the reads are spread over all threads
 // -- entry e of slice s sums the CTAs g = s, s + S, ... with four loads in flight -- because G dependent L2 round
 // trips per entry were the longest stretch of an iteration.  Fixed order: every CTA gets bit-identical sums.
 __device__ void sdp_build(const Parts in, int G, int tau, double* s_M, double* s_P, double* s_part, double& phi, double& Z,
                           double& rprev) {
-  const int T2 = tau * tau, tid = threadIdx.x;
-  const int NE = T2 + 2;                                   // entries: M (T2), Z, R
+  const int T2 = tau * tau, Tu = sdp_packed(tau), tid = threadIdx.x;
+  const int NE = Tu + 2;                                   // entries: packed M (Tu), Z, R
   const int S = NE <= SDP_THREADS ? SDP_THREADS / NE : 1;  // slices
   for (int e = tid % NE, sl = tid / NE; sl < S && e < NE; e += SDP_THREADS) {   // (one trip unless NE > 256)
-    const double* base = e < T2 ? in.M + e : (e == T2 ? in.Z : in.R);
-    const size_t step = e < T2 ? (size_t)T2 : 1;
-    const bool is_max = e == T2 + 1;
+    const double* base = e < Tu ? in.M + e : (e == Tu ? in.Z : in.R);
+    const size_t step = e < Tu ? (size_t)Tu : 1;
+    const bool is_max = e == Tu + 1;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int g = sl;
     for (; g + 3 * S < G; g += 4 * S) {
@@ -131,13 +147,17 @@ __device__ void sdp_build(const Parts in, int G, int tau, double* s_M, double* s
   }
   __syncthreads();
   double z = 0.0, r = 0.0;
-  for (int sl = 0; sl < S; ++sl) { z += s_part[sl * NE + T2]; r = fmax(r, s_part[sl * NE + T2 + 1]); }
+  for (int sl = 0; sl < S; ++sl) { z += s_part[sl * NE + Tu]; r = fmax(r, s_part[sl * NE + Tu + 1]); }
   Z = z;
   rprev = r;
-  if (tid < T2) {
+  if (tid < Tu) {
     double m = 0.0;
     for (int sl = 0; sl < S; ++sl) m += s_part[sl * NE + tid];
-    s_M[tid] = m / z;
+    int pa, pb;
+    sdp_unpack(tid, tau, pa, pb);
+    m /= z;
+    s_M[pa * tau + pb] = m;
+    s_M[pb * tau + pa] = m;
   }
   __syncthreads();
   const int a = tid / tau, b = tid % tau;
@@ -154,10 +174,12 @@ __device__ void sdp_build(const Parts in, int G, int tau, double* s_M, double* s
     if (tid < T2) s_M[tid] = v;
     __syncthreads();
   }
-  if (tid < T2) {
+  if (tid < Tu) {                       // packed weights of <M^-2, A_i>: off-diagonal entries count twice
+    int pa, pb;
+    sdp_unpack(tid, tau, pa, pb);
     double v = 0.0;
-    for (int k = 0; k < tau; ++k) v += s_M[a * tau + k] * s_M[k * tau + b];
-    s_P[tid] = v;
+    for (int k = 0; k < tau; ++k) v += s_M[pa * tau + k] * s_M[k * tau + pb];
+    s_P[tid] = pa == pb ? v : 2.0 * v;
   }
   __syncthreads();
   double t = 0.0;
@@ -166,12 +188,12 @@ __device__ void sdp_build(const Parts in, int G, int tau, double* s_M, double* s
 }
 
 // per-CTA partial sums of q_i A_i, q_i and the CTA's largest ratio
-__device__ void sdp_accumulate(const double* __restrict__ At, const double* __restrict__ qu, int64_t n, int T2, double rmax,
+__device__ void sdp_accumulate(const double* __restrict__ At, const double* __restrict__ qu, int64_t n, int Tu, double rmax,
                                Parts out, double (*s_w)[SDP_T2], double* s_r) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, j0 = (int64_t)blockIdx.x * blockDim.x + tid;
   // eight entries at a time: their shuffle chains are independent, so the reduction is issue-bound, not latency-bound
-  for (int ab0 = 0; ab0 < T2; ab0 += 8) {
+  for (int ab0 = 0; ab0 < Tu; ab0 += 8) {
     double v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = 0.0;
@@ -179,7 +201,7 @@ __device__ void sdp_accumulate(const double* __restrict__ At, const double* __re
       const double q = qu[j];
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        if (ab0 + u < T2) v[u] += q * At[(int64_t)(ab0 + u) * n + j];
+        if (ab0 + u < Tu) v[u] += q * At[(int64_t)(ab0 + u) * n + j];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -189,7 +211,7 @@ __device__ void sdp_accumulate(const double* __restrict__ At, const double* __re
     if (lane == 0) {
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        if (ab0 + u < T2) s_w[w][ab0 + u] = v[u];
+        if (ab0 + u < Tu) s_w[w][ab0 + u] = v[u];
     }
   }
   double z = 0.0;
@@ -198,10 +220,10 @@ __device__ void sdp_accumulate(const double* __restrict__ At, const double* __re
   rmax = warp_max(rmax);
   if (lane == 0) { s_r[w] = z; s_r[8 + w] = rmax; }
   __syncthreads();
-  if (tid < T2) {
+  if (tid < Tu) {
     double v = 0.0;
     for (int k = 0; k < SDP_THREADS / 32; ++k) v += s_w[k][tid];
-    out.M[(size_t)blockIdx.x * T2 + tid] = v;
+    out.M[(size_t)blockIdx.x * Tu + tid] = v;
   }
   if (tid == 0) {
     double zz = 0.0, rr = 0.0;
@@ -215,30 +237,37 @@ __global__ void __launch_bounds__(SDP_THREADS) sdp_init_kernel(const double* __r
                                                                 int64_t n, int tau, double* part_out) {
   __shared__ double s_w[SDP_THREADS / 32][SDP_T2];
   __shared__ double s_r[16];
-  sdp_accumulate(At, qu, n, tau * tau, 0.0, parts_of(part_out, gridDim.x, tau * tau), s_w, s_r);
+  sdp_accumulate(At, qu, n, sdp_packed(tau), 0.0, parts_of(part_out, gridDim.x, sdp_packed(tau)), s_w, s_r);
 }
 
 // one multiplicative update; returns max_i d_i / phi of the PREVIOUS iterate (identical in every CTA)
 __device__ double sdp_iterate(const double* __restrict__ At, double* __restrict__ qu, int64_t n, int tau, double gamma,
                               double* part_in, double* part_out, double* s_M, double* s_P, double (*s_w)[SDP_T2],
                               double* s_r, double& phi_out) {
-  const int T2 = tau * tau, G = gridDim.x;
-  const Parts in = parts_of(part_in, G, T2);
+  const int Tu = sdp_packed(tau), G = gridDim.x;
+  const Parts in = parts_of(part_in, G, Tu);
   double phi, Z, rprev;
   sdp_build(in, G, tau, s_M, s_P, &s_w[0][0], phi, Z, rprev);      // s_w doubles as the scratch of the partial read
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double rmax = 0.0;
   const double inv_phi = 1.0 / phi, inv_Z = 1.0 / Z;
   for (int64_t j = j0; j < n; j += stride) {
-    double d = 0.0;
-#pragma unroll 7
-    for (int ab = 0; ab < T2; ++ab) d += s_P[ab] * At[(int64_t)ab * n + j];
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;      // four chains: a float64 FMA waits ~8 cycles for its predecessor
+    int u = 0;
+    for (; u + 3 < Tu; u += 4) {
+      d0 += s_P[u] * At[(int64_t)u * n + j];
+      d1 += s_P[u + 1] * At[(int64_t)(u + 1) * n + j];
+      d2 += s_P[u + 2] * At[(int64_t)(u + 2) * n + j];
+      d3 += s_P[u + 3] * At[(int64_t)(u + 3) * n + j];
+    }
+    for (; u < Tu; ++u) d0 += s_P[u] * At[(int64_t)u * n + j];
+    const double d = (d0 + d1) + (d2 + d3);
     const double r = d * inv_phi;
     const double q = qu[j] * inv_Z;
     rmax = fmax(rmax, r);          // over ALL i: the optimality condition also binds where q_i has underflowed to 0
     qu[j] = q * (gamma == 0.5 ? sqrt(r) : pow(r, gamma));
   }
-  sdp_accumulate(At, qu, n, T2, rmax, parts_of(part_out, G, T2), s_w, s_r);
+  sdp_accumulate(At, qu, n, Tu, rmax, parts_of(part_out, G, Tu), s_w, s_r);
   phi_out = phi;
   return rprev;
 }
@@ -295,13 +324,13 @@ __global__ void __launch_bounds__(SDP_THREADS) sdp_final_kernel(const double* __
                                                                  double* __restrict__ q_out, double* __restrict__ res) {
   __shared__ double s_M[SDP_T2], s_P[SDP_T2], s_part[SDP_T2 + 2 + SDP_THREADS];
   __shared__ double s_r[8];
-  const int T2 = tau * tau;
+  const int Tu = sdp_packed(tau);
   double phi, Z, rprev;
-  sdp_build(parts_of(part_in, G, T2), G, tau, s_M, s_P, s_part, phi, Z, rprev);
+  sdp_build(parts_of(part_in, G, Tu), G, tau, s_M, s_P, s_part, phi, Z, rprev);
   double rmax = 0.0;
   for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
     double d = 0.0;
-    for (int ab = 0; ab < T2; ++ab) d += s_P[ab] * At[(int64_t)ab * n + j];
+    for (int u = 0; u < Tu; ++u) d += s_P[u] * At[(int64_t)u * n + j];
     rmax = fmax(rmax, d / phi);           // over ALL i: the optimality condition also binds where q_i = 0
     q_out[j] = qu[j] / Z;
   }
@@ -340,11 +369,11 @@ static int sdp_solve(nnal_ctx* ctx, int mode, const double* src, const double* p
   if (max_iter < 1) max_iter = 1;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   SdpState* st = sdp_state(ctx);
-  const int T2 = tau * tau;
+  const int T2 = tau * tau, Tu = sdp_packed(tau);
   const int G = (int)std::min<int64_t>((n + SDP_THREADS - 1) / SDP_THREADS, SDP_MAX_GRID);
-  const size_t part_doubles = (size_t)G * T2 + 2 * (size_t)G;
+  const size_t part_doubles = (size_t)G * Tu + 2 * (size_t)G;
   NNAL_TRY(devbuf_reserve(ctx, st->stage, mode == 0 ? (size_t)n * T2 * 8 : (size_t)n * (2 * tau + 1) * 8));
-  NNAL_TRY(devbuf_reserve(ctx, st->At, (size_t)n * T2 * 8));
+  NNAL_TRY(devbuf_reserve(ctx, st->At, (size_t)n * Tu * 8));
   NNAL_TRY(devbuf_reserve(ctx, st->qu, (size_t)n * 8 * 2));           // unnormalised weights, then the normalised result
   NNAL_TRY(devbuf_reserve(ctx, st->part[0], part_doubles * 8));
   NNAL_TRY(devbuf_reserve(ctx, st->part[1], part_doubles * 8));
@@ -354,10 +383,10 @@ static int sdp_solve(nnal_ctx* ctx, int mode, const double* src, const double* p
   double* qn = qu + n;
   double* hist = (double*)st->out.p;         // [0..2] loop record, [4..] result of the final kernel
   double* res = hist + 4;
-  const int tg = (int)std::min<int64_t>((n * T2 + 255) / 256, (int64_t)ctx->sm_count * 8);
+  const int tg = (int)std::min<int64_t>((n * Tu + 255) / 256, (int64_t)ctx->sm_count * 8);
   if (mode == 0) {
     CUDA_TRY(ctx, cudaMemcpyAsync(st->stage.p, src, (size_t)n * T2 * 8, cudaMemcpyHostToDevice, ctx->stream));
-    sdp_transpose_kernel<<<tg, 256, 0, ctx->stream>>>((const double*)st->stage.p, At, n, T2);
+    sdp_transpose_kernel<<<tg, 256, 0, ctx->stream>>>((const double*)st->stage.p, At, n, tau);
   } else {
     double* d_g = (double*)st->stage.p;
     double* d_p = d_g + 2 * n * tau;
