@@ -18,7 +18,7 @@ import numpy as np
 REF = os.environ.get('NNAL_REFERENCE', '/root/reference')
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-GOLD = os.path.join(ROOT, 'tests', 'golden')
+GOLD = os.environ.get('NNAL_GOLD_OUT', os.path.join(ROOT, 'tests', 'golden'))   # NNAL_GOLD_OUT: check only, write elsewhere
 
 
 def import_reference():
