@@ -396,7 +396,6 @@ def run_sdp_round(args, eng, padded, pool, st, k):
     """The reference's literal FI selection (PW_NNAL.py:117-163) for B pre-filtered candidates: shrunk class-score
     gradients (one batched backward pass instead of 2B sess.run(tf.gradients) calls), A-matrices, SDP query distribution
     (first-order solver on the device, certified gap), sampling.  Host wall time per stage (the stages synchronise)."""
-    import nnal_b200
     from nnal_b200 import NNAL_tools
     B = min(args.sdp_B, len(pool))
     cand = pool[:B]
