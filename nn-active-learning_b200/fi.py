@@ -196,7 +196,7 @@ def query_single_sdp(expr, model, sess, padded_imgs, pool_inds, return_solution=
     query distribution -> ``sample_query_dstr`` (<= k unique positions, sorted).  Positions into ``pool_inds``.
     The candidates' patches are gathered on the device; with several ranks each one back-propagates its block of the B
     candidates, the shrunk gradients (B x 2 x tau numbers) are all-gathered and every rank solves the same SDP."""
-    from .PW_NNAL import _score_pool_single, _stats_list, _A_from_shrunk
+    from .PW_NNAL import _score_pool_single, _stats_list
     B = int(expr.pars['B'])
     pool_inds = np.asarray(pool_inds)
     n = len(pool_inds)
@@ -222,7 +222,7 @@ def query_multimg_sdp(expr, model, sess, all_padded_imgs, pool_inds, return_solu
     """``PW_NNAL.query_multimg(..., 'fi')`` as the reference runs it (PW_NNAL.py:547-627): B most uncertain samples of
     the concatenated pool, per-subject A-matrices with diag_load 1e-3 (:566-578) in subject-major order, SDP,
     sampling, ``global2local_inds`` of the sampled candidates' pool positions."""
-    from .PW_NNAL import _bin_filter_core, _A_from_shrunk
+    from .PW_NNAL import _bin_filter_core
     B = int(expr.pars['B'])
     eng = get_engine()
     sorted_inds, _, lo, hi, sizes = _bin_filter_core(expr, model, sess, all_padded_imgs, pool_inds, B)
