@@ -71,7 +71,7 @@ int nnal_synchronize(nnal_ctx* ctx);
 void* nnal_stream(nnal_ctx* ctx);
 
 /* Per-kernel-class device timing (CUDA events on the context stream) for bench.py's roofline leg.
- * cls: layer index (0..n_layers-1), 100 gather, 101 scores, 102 top-k, 110-112 FI setup / Gram / greedy,
+ * cls: layer index (0..n_layers-1), 100 gather, 101 scores, 102 top-k, 110-113 FI setup / Gram / greedy / Gram solve,
  * 120 / 121 forward / backward of the shrunk-gradient pass. */
 int nnal_profile(nnal_ctx* ctx, int enable);
 int nnal_profile_read(nnal_ctx* ctx, int cls, double* total_ms, long long* count);
@@ -153,6 +153,15 @@ int nnal_pool_scores_read(nnal_ctx* ctx, double* out);
 /* k smallest scores, ascending, ties -> lowest pool position: np.argsort(score)[:k] */
 int nnal_pool_topk(nnal_ctx* ctx, int64_t k, int64_t* idx_out, double* score_out);
 
+/* Device-resident form for the multi-GPU merge (SURVEY.md 8e collective 1; the reference ranks one concatenated
+ * pool, PW_NNAL.py:724-730): writes k_pad pairs {float64 score, int64 pos_offset + pool position} of the k best
+ * samples into DEVICE memory (slots k..k_pad-1 = {+inf, INT64_MAX}); the host layer all-gathers the pair buffers of
+ * all ranks with NCCL on nnal_stream(); nnal_topk_merge_pairs then returns the global k smallest by (score,
+ * position) to HOST arrays.  d_pairs of the merge is [world][k_pad], ranks owning ascending position blocks. */
+int nnal_pool_topk_device(nnal_ctx* ctx, int64_t k, int64_t k_pad, int64_t pos_offset, void* d_pairs);
+int nnal_topk_merge_pairs(nnal_ctx* ctx, const void* d_pairs, int64_t n_pairs, int64_t k, int64_t* pos_out,
+                          double* score_out);
+
 /* ---- stand-alone scoring helpers (host float64 in/out like the NumPy originals) -------------- */
 /* NNAL_tools.compute_entropy (NNAL_tools.py:71-85): P [c][n]; zeros are treated as eps (the
  * in-place bump of the caller's array is done by the Python shim). kind as NNAL_SCORE_*. */
@@ -183,8 +192,17 @@ int nnal_fi_info(nnal_ctx* ctx, int64_t* n_cand, int* n_layers, int* d, int* d_p
  * NULL.  The result stays on the device (nnal_fi_gram_ptr: base pointer, rows = d+1, row stride ld, for
  * the NCCL all-reduce of per-GPU partials by the host layer) and is copied to H_out if non-NULL. */
 int nnal_fi_gram(nnal_ctx* ctx, const double* q, float* H_out);
+/* Same Gram over a SUBSET of the candidates -- the support of a query distribution such as the greedy selection:
+ * cand[n_sub] = candidate indices, q_sub[n_sub] their weights (n_sub = 0: H = 0, a rank that owns no selected sample). */
+int nnal_fi_gram_subset(nnal_ctx* ctx, const int64_t* cand, int64_t n_sub, const double* q_sub, float* H_out);
 void* nnal_fi_gram_ptr(nnal_ctx* ctx, int64_t* rows, int64_t* ld);
 int nnal_fi_gram_read(nnal_ctx* ctx, float* H_out);
+/* Primal FI objective through the Gram currently on the device (i.e. after the host layer's NCCL all-reduce):
+ * *tr_out = tr((delta I + scale H)^-1) by a blocked float64 Gauss-Jordan inversion on the device.  With scale = 2,
+ * tr_out + (d+1)/delta = tr((sum_i q_i F_i + delta I)^-1) for the last-layer FI F_i = (v v^T) (x) w_i [u_i;1][u_i;1]^T of
+ * NN.LLFC_hess (NN.py:891-901), the objective of NNAL_tools.py:589-602.  d_G2: optional DEVICE pointer to a second Gram
+ * of the same layout (e.g. a copy of the pool-wide one): *ratio_out = tr((delta I + scale H)^-1 (delta I + scale G2)). */
+int nnal_fi_gram_solve(nnal_ctx* ctx, double delta, double scale, const float* d_G2, double* tr_out, double* ratio_out);
 /* Greedy FI selection: k candidates minimising f(S) = tr(((1/|S|) sum_{i in S} Abar_i + delta I)^-1) step
  * by step (ties: lowest candidate index).  sel_out[k]: candidate indices in selection order; obj_out[k]:
  * f(S_t) after each step; red_out[k]: its kernel-dependent part tr((delta I + K_SS/s)^-1).  Any of

@@ -42,8 +42,7 @@ def CNN_query(model, expr, pool_inds, method_name, session, col=True, extra_feed
     if method_name == 'entropy':
         eng, lo, hi = _posteriors_on_device(model, expr, pool_inds, session)
         eng.pool_score(L.SCORE_NEG_ENTROPY, 10e-8)
-        idx, sc = eng.pool_topk(k, with_scores=True)
-        q, _ = dist.allgather_topk(sc, idx + lo, min(k, len(pool_inds)))
+        q, _ = dist.topk_global(eng, k, lo, len(pool_inds))
         return q
     if method_name == 'fi':
         from . import fi

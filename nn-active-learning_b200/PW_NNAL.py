@@ -60,8 +60,7 @@ def CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, method_name):
         k = expr.pars['k']
         eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds)
         eng.pool_score(L.SCORE_BINARY)
-        idx, sc = eng.pool_topk(k, with_scores=True)
-        q, _ = dist.allgather_topk(sc, idx + lo, min(k, len(pool_inds)))
+        q, _ = dist.topk_global(eng, k, lo, len(pool_inds))
         return q
 
     if method_name == 'MC-entropy':
@@ -70,8 +69,7 @@ def CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, method_name):
         eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds,
                                          mc=(int(expr.pars['MC_iters']), float(model.dropout_rate)))
         eng.pool_score(L.SCORE_MC_BINARY)
-        idx, sc = eng.pool_topk(k, with_scores=True)
-        q, _ = dist.allgather_topk(sc, idx + lo, min(k, len(pool_inds)))
+        q, _ = dist.topk_global(eng, k, lo, len(pool_inds))
         return q
 
     if method_name == 'fi':
@@ -159,9 +157,8 @@ def _bin_filter_core(expr, model, sess, all_padded_imgs, pool_inds, B, keep=0):
     |p - 0.5|.  Returns (sorted global positions, their posteriors, lo, hi, per-subject sizes)."""
     eng, lo, hi, img_ind_sizes, n = _pool_pass_multimg(expr, model, sess, all_padded_imgs, pool_inds, keep)
     eng.pool_score(L.SCORE_BINARY)
-    idx, sc = eng.pool_topk(B, with_scores=True)
     post_local = eng.pool_posteriors()[1, :].astype(np.float64)
-    sorted_inds, _ = dist.allgather_topk(sc, idx + lo, min(B, n))
+    sorted_inds, _ = dist.topk_global(eng, B, lo, n)
     # posteriors of the selected samples (owners contribute theirs)
     mine = (sorted_inds >= lo) & (sorted_inds < hi)
     sel_p = np.zeros(len(sorted_inds))
@@ -214,8 +211,7 @@ def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, labeled_inds, m
         eng, lo, hi, _, n = _pool_pass_multimg(expr, model, sess, all_padded_imgs, pool_inds,
                                                mc=(int(expr.pars['MC_iters']), float(model.dropout_rate)))
         eng.pool_score(L.SCORE_MC_BINARY if method_name == 'MC-entropy' else L.SCORE_NEG_BALD)
-        idx, sc = eng.pool_topk(k, with_scores=True)
-        inds, _ = dist.allgather_topk(sc, idx + lo, min(k, n))
+        inds, _ = dist.topk_global(eng, k, lo, n)
         return patch_utils.global2local_inds(inds, img_ind_sizes)
 
     if method_name in ('ensemble', 'QBC-JS'):
@@ -237,8 +233,7 @@ def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, labeled_inds, m
             if eng is not None:
                 eng.pool_ensemble_end()
         eng.pool_score(L.SCORE_MC_BINARY if method_name == 'ensemble' else L.SCORE_NEG_BALD)
-        idx, sc = eng.pool_topk(k, with_scores=True)
-        inds, _ = dist.allgather_topk(sc, idx + lo, min(k, n))
+        inds, _ = dist.topk_global(eng, k, lo, n)
         return patch_utils.global2local_inds(inds, img_ind_sizes)
 
     if method_name == 'fi':

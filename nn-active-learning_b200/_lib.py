@@ -52,6 +52,8 @@ SIGNATURES = {
     'nnal_pool_ensemble_end': (C.c_int, [c_vp]),
     'nnal_pool_scores_read': (C.c_int, [c_vp, c_vp]),
     'nnal_pool_topk': (C.c_int, [c_vp, C.c_int64, c_vp, c_vp]),
+    'nnal_pool_topk_device': (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int64, c_vp]),
+    'nnal_topk_merge_pairs': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp]),
     'nnal_entropy': (C.c_int, [c_vp, c_vp, C.c_int, C.c_int64, C.c_int, C.c_double, c_vp]),
     'nnal_topk': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, c_vp]),
     'nnal_debug_fc': (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
@@ -73,6 +75,8 @@ SIGNATURES = {
     'nnal_fi_set_factors': (C.c_int, [c_vp, C.c_int64, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     'nnal_fi_info': (C.c_int, [c_vp, c_i64p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_f64p]),
     'nnal_fi_gram': (C.c_int, [c_vp, c_vp, c_vp]),
+    'nnal_fi_gram_subset': (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),
+    'nnal_fi_gram_solve': (C.c_int, [c_vp, C.c_double, C.c_double, c_vp, c_f64p, c_f64p]),
     'nnal_fi_gram_ptr': (c_vp, [c_vp, c_i64p, c_i64p]),
     'nnal_fi_gram_read': (C.c_int, [c_vp, c_vp]),
     'nnal_fi_greedy': (C.c_int, [c_vp, C.c_int64, C.c_double, c_vp, c_vp, c_vp]),

@@ -695,6 +695,75 @@ extern "C" int nnal_pool_topk(nnal_ctx* ctx, int64_t k, int64_t* idx_out, double
   return topk_to_host(ctx, ctx->pool_score, ctx->pool_n, k, idx_out, score_out);
 }
 
+// Device-resident top-k for the multi-GPU merge (collective 1): the k best (score, global position)
+// pairs of this rank stay in DEVICE memory, the host layer all-gathers the pair buffers with NCCL on nnal_stream() and
+// nnal_topk_merge_pairs picks the global top-k -- one small device-to-host copy per query instead of a host-staged
+// exchange.  Pair = {float64 score, int64 position}; unused slots are {+inf, INT64_MAX}.
+struct TopkPair { double score; long long pos; };
+
+__global__ void topk_pack_pairs_kernel(const int64_t* __restrict__ idx, const double* __restrict__ sc, int64_t k, int64_t k_pad,
+                                       long long pos_offset, TopkPair* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k_pad; i += (int64_t)gridDim.x * blockDim.x) {
+    TopkPair p;
+    if (i < k) { p.score = sc[i]; p.pos = (long long)idx[i] + pos_offset; }
+    else { p.score = INFINITY; p.pos = 0x7fffffffffffffffll; }
+    out[i] = p;
+  }
+}
+__global__ void topk_pair_scores_kernel(const TopkPair* __restrict__ in, int64_t n, double* __restrict__ sc) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) sc[i] = in[i].score;
+}
+__global__ void topk_pair_pos_kernel(const TopkPair* __restrict__ in, const int64_t* __restrict__ idx, int64_t k,
+                                     int64_t* __restrict__ pos) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (int64_t)gridDim.x * blockDim.x) pos[i] = in[idx[i]].pos;
+}
+
+extern "C" int nnal_pool_topk_device(nnal_ctx* ctx, int64_t k, int64_t k_pad, int64_t pos_offset, void* d_pairs) {
+  if (!ctx || !d_pairs || k < 0 || k_pad < k) return NNAL_ERR_INVALID;
+  if (!ctx->pool_score) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no pool pass");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (k > ctx->pool_n) k = ctx->pool_n;
+  if (k_pad == 0) return NNAL_OK;
+  NNAL_TRY(devbuf_reserve(ctx, ctx->inds, (size_t)std::max<int64_t>(k, 1) * 16));
+  int64_t* d_idx = (int64_t*)ctx->inds.p;
+  double* d_sc = (double*)((char*)ctx->inds.p + (size_t)std::max<int64_t>(k, 1) * 8);
+  prof_begin(ctx, NNAL_PROF_TOPK);
+  if (k > 0) NNAL_TRY(nnal_k_topk(ctx, ctx->pool_score, ctx->pool_n, k, d_idx, d_sc));
+  topk_pack_pairs_kernel<<<std::min(cdiv(k_pad, 256), 1024), 256, 0, ctx->stream>>>(d_idx, d_sc, k, k_pad, (long long)pos_offset,
+                                                                                  (TopkPair*)d_pairs);
+  ctx->launches++;
+  prof_end(ctx);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return NNAL_OK;
+}
+
+// Global top-k of n_pairs gathered pairs [world][k_pad] (rank-major; every rank's list ascending by (score, position)
+// and the ranks owning ascending position blocks, so that array order breaks score ties by position, as
+// np.argsort(kind='stable') does on the concatenated pool).  pos_out / score_out: HOST arrays [k].
+extern "C" int nnal_topk_merge_pairs(nnal_ctx* ctx, const void* d_pairs, int64_t n_pairs, int64_t k, int64_t* pos_out,
+                                     double* score_out) {
+  if (!ctx || !d_pairs || n_pairs < 0 || k < 0 || k > n_pairs) return NNAL_ERR_INVALID;
+  if (k == 0) return NNAL_OK;
+  if (!pos_out) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->inds, (size_t)n_pairs * 8 + (size_t)k * 24));
+  double* d_all = (double*)ctx->inds.p;
+  int64_t* d_idx = (int64_t*)(d_all + n_pairs);
+  double* d_sc = (double*)(d_idx + k);
+  int64_t* d_pos = (int64_t*)(d_sc + k);
+  prof_begin(ctx, NNAL_PROF_TOPK);
+  topk_pair_scores_kernel<<<std::min(cdiv(n_pairs, 256), 1024), 256, 0, ctx->stream>>>((const TopkPair*)d_pairs, n_pairs, d_all);
+  NNAL_TRY(nnal_k_topk(ctx, d_all, n_pairs, k, d_idx, d_sc));
+  topk_pair_pos_kernel<<<std::min(cdiv(k, 256), 1024), 256, 0, ctx->stream>>>((const TopkPair*)d_pairs, d_idx, k, d_pos);
+  ctx->launches += 2;
+  prof_end(ctx);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(pos_out, d_pos, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (score_out) CUDA_TRY(ctx, cudaMemcpyAsync(score_out, d_sc, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // stand-alone helpers
 // ---------------------------------------------------------------------------------------------

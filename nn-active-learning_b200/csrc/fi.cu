@@ -75,6 +75,13 @@ struct State {
   size_t plane_cap = 0;
   double* wq = nullptr;
   int64_t wq_cap = 0;
+  // Gram over a candidate subset (rows with non-zero weight)
+  int64_t* sub_rows = nullptr;
+  double* sub_wq = nullptr;
+  int64_t sub_cap = 0;
+  // float64 workspace of nnal_fi_gram_solve: M (np x np), row panel, column panel, inverted pivot block, results
+  double *gj_M = nullptr, *gj_R = nullptr, *gj_C = nullptr, *gj_D = nullptr, *gj_out = nullptr;
+  int gj_np = 0;
 };
 
 static State* get(nnal_ctx* ctx) {
@@ -589,6 +596,136 @@ __global__ void __launch_bounds__(256) gram_planes_kernel(const float* __restric
   }
 }
 
+// candidate subset -> factor rows and Gram weights:  rows_sub[j] = row of candidate cand[j],  wq_sub[j] = q_sub[j] w[cand[j]]
+__global__ void gram_subset_kernel(const int64_t* __restrict__ rows, const double* __restrict__ w, const int64_t* __restrict__ cand,
+                                   const double* __restrict__ q_sub, int64_t n_sub, int64_t* __restrict__ rows_sub,
+                                   double* __restrict__ wq_sub) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_sub; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = cand[j];
+    rows_sub[j] = rows ? rows[c] : c;
+    wq_sub[j] = q_sub[j] * w[c];
+  }
+}
+
+// ---- primal objective through the Gram: tr((delta I + scale H)^-1) by blocked Gauss-Jordan in float64 ------------------
+// (SPD: no pivoting.)  M is np x np, np = n rounded up to GJ_B with an identity tail.  Per block pivot p:
+//   D = M_pp^-1 (invert_reg_kernel<2>);  R_j = D M_pj,  C_i = M_ip (gj_panels_kernel);
+//   M_ij -= C_i R_j (i,j != p),  M_pj = R_j,  M_ip = -C_i D,  M_pp = D   (gj_update_kernel, one 64 x 64 tile per CTA).
+constexpr int GJ_B = 64;
+constexpr size_t GJ_SMEM = (size_t)(GJ_B * (GJ_B + 2) + GJ_B * GJ_B) * sizeof(double);
+
+__global__ void __launch_bounds__(256) gj_init_kernel(const float* __restrict__ H, int64_t ld, int n, int np, double delta,
+                                                      double scale, double* __restrict__ M) {
+  const int64_t total = (int64_t)np * np;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / np), j = (int)(e - (int64_t)i * np);
+    double v;
+    if (i < n && j < n) v = scale * (double)H[(int64_t)i * ld + j] + (i == j ? delta : 0.0);
+    else v = i == j ? 1.0 : 0.0;
+    M[e] = v;
+  }
+}
+
+// acc[4][4] += X[64x64] Y[64x64] for the thread's 4 x 4 sub-tile (rows 4 ty.., columns 4 tx..); X is staged transposed
+__device__ __forceinline__ void gj_tile_mm(const double* __restrict__ X, int64_t ldx, const double* __restrict__ Y, int64_t ldy,
+                                           double (*Xs)[GJ_B + 2], double (*Ys)[GJ_B], double acc[4][4]) {
+  const int tid = threadIdx.x;
+  for (int e = tid; e < GJ_B * GJ_B; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    Xs[c][r] = X[(int64_t)r * ldx + c];
+    Ys[r][c] = Y[(int64_t)r * ldy + c];
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll 8
+  for (int k = 0; k < GJ_B; ++k) {
+    const double2 x01 = *reinterpret_cast<const double2*>(&Xs[k][4 * ty]);
+    const double2 x23 = *reinterpret_cast<const double2*>(&Xs[k][4 * ty + 2]);
+    const double2 y01 = *reinterpret_cast<const double2*>(&Ys[k][4 * tx]);
+    const double2 y23 = *reinterpret_cast<const double2*>(&Ys[k][4 * tx + 2]);
+    const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
+    const double yv[4] = {y01.x, y01.y, y23.x, y23.y};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fma(xv[a], yv[b], acc[a][b]);
+  }
+}
+
+__global__ void __launch_bounds__(256) gj_panels_kernel(const double* __restrict__ M, int np, int p, const double* __restrict__ D,
+                                                        double* __restrict__ R, double* __restrict__ Cp) {
+  extern __shared__ __align__(16) double gj_sm[];
+  double (*Xs)[GJ_B + 2] = reinterpret_cast<double (*)[GJ_B + 2]>(gj_sm);
+  double (*Ys)[GJ_B] = reinterpret_cast<double (*)[GJ_B]>(gj_sm + GJ_B * (GJ_B + 2));
+  const int j = blockIdx.x;
+  if (j == p) return;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  // column panel copy: C_j = M[j-block rows][p-block columns]
+  for (int e = tid; e < GJ_B * GJ_B; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    Cp[((int64_t)j * GJ_B + r) * GJ_B + c] = M[((int64_t)j * GJ_B + r) * np + (int64_t)p * GJ_B + c];
+  }
+  double acc[4][4] = {};
+  gj_tile_mm(D, GJ_B, M + (int64_t)p * GJ_B * np + (int64_t)j * GJ_B, np, Xs, Ys, acc);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) R[(int64_t)(4 * ty + a) * np + (int64_t)j * GJ_B + 4 * tx + b] = acc[a][b];
+}
+
+__global__ void __launch_bounds__(256) gj_update_kernel(double* __restrict__ M, int np, int p, const double* __restrict__ D,
+                                                        const double* __restrict__ R, const double* __restrict__ Cp) {
+  extern __shared__ __align__(16) double gj_sm[];
+  double (*Xs)[GJ_B + 2] = reinterpret_cast<double (*)[GJ_B + 2]>(gj_sm);
+  double (*Ys)[GJ_B] = reinterpret_cast<double (*)[GJ_B]>(gj_sm + GJ_B * (GJ_B + 2));
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  double* T = M + (int64_t)bi * GJ_B * np + (int64_t)bj * GJ_B;
+  if (bi == p) {
+    const double* src = bj == p ? D : R + (int64_t)bj * GJ_B;
+    const int64_t lds = bj == p ? GJ_B : np;
+    for (int e = tid; e < GJ_B * GJ_B; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      T[(int64_t)r * np + c] = src[(int64_t)r * lds + c];
+    }
+    return;
+  }
+  double acc[4][4] = {};
+  if (bj == p) gj_tile_mm(Cp + (int64_t)bi * GJ_B * GJ_B, GJ_B, D, GJ_B, Xs, Ys, acc);
+  else gj_tile_mm(Cp + (int64_t)bi * GJ_B * GJ_B, GJ_B, R + (int64_t)bj * GJ_B, np, Xs, Ys, acc);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      double* o = T + (int64_t)(4 * ty + a) * np + 4 * tx + b;
+      *o = bj == p ? -acc[a][b] : *o - acc[a][b];
+    }
+}
+
+// out[0] = sum_{i<n} Minv_ii;  out[1] = sum_{i,j<n} Minv_ij (delta [i==j] + scale2 G2_ij)  (G2 may be null)
+__global__ void __launch_bounds__(256) gj_reduce_kernel(const double* __restrict__ M, int n, int np, const float* __restrict__ G2,
+                                                        int64_t ld2, double delta, double scale2, double* __restrict__ out) {
+  double tr = 0.0, ra = 0.0;
+  const int64_t total = (int64_t)n * n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / n), j = (int)(e - (int64_t)i * n);
+    const double m = M[(int64_t)i * np + j];
+    if (i == j) tr += m;
+    if (G2) ra = fma(m, scale2 * (double)G2[(int64_t)i * ld2 + j] + (i == j ? delta : 0.0), ra);
+  }
+  tr = warp_sum(tr);
+  ra = warp_sum(ra);
+  __shared__ double s0[8], s1[8];
+  if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = tr; s1[threadIdx.x >> 5] = ra; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int q = 0; q < 8; ++q) { a += s0[q]; b += s1[q]; }
+    atomicAdd(&out[0], a);
+    atomicAdd(&out[1], b);
+  }
+}
+
 static int warp_grid(nnal_ctx* ctx, int64_t n) {
   int64_t blocks = (n + 7) / 8;
   int64_t cap = (int64_t)ctx->sm_count * 16;
@@ -729,7 +866,8 @@ int nnal_fi_release(nnal_ctx* ctx) {
   if (!ctx->fi_state) return NNAL_OK;
   State* s = (State*)ctx->fi_state;
   void* ptrs[] = {s->gids, s->rows, s->ownU, s->ownA, s->w, s->sw, s->diag, s->avail, s->beta2, s->kcols, s->kss, s->C, s->inv_ws,
-                  s->red, s->win_sw, s->win_u, s->win_a, s->sel, s->blk_loss, s->blk_idx, s->sc, s->H, s->Xh, s->Xl, s->wq};
+                  s->red, s->win_sw, s->win_u, s->win_a, s->sel, s->blk_loss, s->blk_idx, s->sc, s->H, s->Xh, s->Xl, s->wq,
+                  s->sub_rows, s->sub_wq, s->gj_M, s->gj_R, s->gj_C, s->gj_D, s->gj_out};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete s;
   ctx->fi_state = nullptr;
@@ -1010,11 +1148,8 @@ extern "C" int nnal_fi_result(nnal_ctx* ctx, int64_t k, int64_t* gids_out, doubl
 }
 
 // ---- weighted Gram on tensor cores -----------------------------------------------------------------------
-extern "C" int nnal_fi_gram(nnal_ctx* ctx, const double* q, float* H_out) {
-  if (!ctx) return NNAL_ERR_INVALID;
-  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  State* s = (State*)ctx->fi_state;
+// H = sum_{j<n} wq[j] [u;1][u;1]^T over the factor rows `rows[j]` (null: j), into s->H (device)
+static int gram_core(nnal_ctx* ctx, State* s, const int64_t* rows, const double* wq, int64_t n) {
   const int Dg = s->d + 1;
   const int ld = (Dg + 7) / 8 * 8;
   if (s->Hd != Dg) {
@@ -1022,6 +1157,60 @@ extern "C" int nnal_fi_gram(nnal_ctx* ctx, const double* q, float* H_out) {
     s->Hd = Dg; s->Hld = ld;
   }
   CUDA_TRY(ctx, cudaMemsetAsync(s->H, 0, (size_t)Dg * ld * 4, ctx->stream));
+  if (n <= 0) return NNAL_OK;
+  prof_begin(ctx, NNAL_PROF_FI_SETUP);
+  CUDA_TRY(ctx, cudaMemsetAsync(&s->sc->gmax_bits, 0, 4, ctx->stream));
+  fi::gram_max_kernel<<<fi::warp_grid(ctx, n), 256, 0, ctx->stream>>>(s->U, rows, wq, n, s->d, s->sc);
+  ctx->launches++;
+  prof_end(ctx);
+  fi::DevScalars h;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&h, s->sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  float gmax;
+  memcpy(&gmax, &h.gmax_bits, 4);
+  if (!(gmax > 0.f && gmax < 3.0e38f)) return NNAL_OK;
+  int ex;
+  frexpf(gmax, &ex);
+  int e = 13 - ex;                                    // scaled operands below 2^13: the K-sum of squares stays finite in fp32
+  e = std::max(-60, std::min(60, e));
+  const float scale = ldexpf(1.f, e), inv2 = ldexpf(1.f, -2 * e);
+  const int64_t CH = 65536;
+  const int64_t ldp = std::min<int64_t>(CH, (n + 7) / 8 * 8);
+  const size_t plane = (size_t)Dg * ldp;
+  if (s->plane_cap < plane) {
+    NNAL_TRY(fi::ensure(ctx, s->Xh, 0, plane));
+    NNAL_TRY(fi::ensure(ctx, s->Xl, 0, plane));
+    s->plane_cap = plane;
+  }
+  for (int64_t i0 = 0; i0 < n; i0 += CH) {
+    const int64_t nc = std::min(CH, n - i0);
+    prof_begin(ctx, NNAL_PROF_FI_SETUP);
+    dim3 grid(cdiv(ldp, 32), cdiv(Dg, 32)), block(32, 8);
+    fi::gram_planes_kernel<<<grid, block, 0, ctx->stream>>>(s->U, rows, wq, i0, nc, ldp, s->d, scale, s->Xh, s->Xl);
+    ctx->launches++;
+    prof_end(ctx);
+    prof_begin(ctx, NNAL_PROF_FI_GRAM);
+    int rc = nnal_tc_gemm_planes(ctx, s->Xh, s->Xl, ldp, Dg, s->Xh, s->Xl, ldp, Dg, nc, nullptr, inv2, 0, i0 > 0 ? 1 : 0, s->H,
+                                 ld, nullptr, nullptr, 0);
+    prof_end(ctx);
+    NNAL_TRY(rc);
+  }
+  return NNAL_OK;
+}
+
+static int gram_finish(nnal_ctx* ctx, State* s, float* H_out) {
+  if (H_out)
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(H_out, (size_t)s->Hd * 4, s->H, (size_t)s->Hld * 4, (size_t)s->Hd * 4, s->Hd, cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return NNAL_OK;
+}
+
+extern "C" int nnal_fi_gram(nnal_ctx* ctx, const double* q, float* H_out) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  State* s = (State*)ctx->fi_state;
   if (s->n > 0) {
     if (s->wq_cap < s->n) { NNAL_TRY(fi::ensure(ctx, s->wq, 0, (size_t)s->n)); s->wq_cap = s->n; }
     const double* d_q = nullptr;
@@ -1032,48 +1221,84 @@ extern "C" int nnal_fi_gram(nnal_ctx* ctx, const double* q, float* H_out) {
     }
     prof_begin(ctx, NNAL_PROF_FI_SETUP);
     fi::wq_kernel<<<std::min(cdiv(s->n, 256), ctx->sm_count * 8), 256, 0, ctx->stream>>>(s->w, d_q, s->n, s->wq);
-    CUDA_TRY(ctx, cudaMemsetAsync(&s->sc->gmax_bits, 0, 4, ctx->stream));
-    fi::gram_max_kernel<<<fi::warp_grid(ctx, s->n), 256, 0, ctx->stream>>>(s->U, s->R(), s->wq, s->n, s->d, s->sc);
-    ctx->launches += 2;
+    ctx->launches++;
     prof_end(ctx);
-    fi::DevScalars h;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&h, s->sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    float gmax;
-    memcpy(&gmax, &h.gmax_bits, 4);
-    if (gmax > 0.f && gmax < 3.0e38f) {
-      int ex;
-      frexpf(gmax, &ex);
-      int e = 13 - ex;                                    // scaled operands below 2^13: the K-sum of squares stays finite in fp32
-      e = std::max(-60, std::min(60, e));
-      const float scale = ldexpf(1.f, e), inv2 = ldexpf(1.f, -2 * e);
-      const int64_t CH = 65536;
-      const int64_t ldp = std::min<int64_t>(CH, (s->n + 7) / 8 * 8);
-      const size_t plane = (size_t)Dg * ldp;
-      if (s->plane_cap < plane) {
-        NNAL_TRY(fi::ensure(ctx, s->Xh, 0, plane));
-        NNAL_TRY(fi::ensure(ctx, s->Xl, 0, plane));
-        s->plane_cap = plane;
-      }
-      for (int64_t i0 = 0; i0 < s->n; i0 += CH) {
-        const int64_t nc = std::min(CH, s->n - i0);
-        prof_begin(ctx, NNAL_PROF_FI_SETUP);
-        dim3 grid(cdiv(ldp, 32), cdiv(Dg, 32)), block(32, 8);
-        fi::gram_planes_kernel<<<grid, block, 0, ctx->stream>>>(s->U, s->R(), s->wq, i0, nc, ldp, s->d, scale, s->Xh, s->Xl);
-        ctx->launches++;
-        prof_end(ctx);
-        prof_begin(ctx, NNAL_PROF_FI_GRAM);
-        int rc = nnal_tc_gemm_planes(ctx, s->Xh, s->Xl, ldp, Dg, s->Xh, s->Xl, ldp, Dg, nc, nullptr, inv2, 0, i0 > 0 ? 1 : 0, s->H,
-                                     ld, nullptr, nullptr, 0);
-        prof_end(ctx);
-        NNAL_TRY(rc);
-      }
+  }
+  NNAL_TRY(gram_core(ctx, s, s->R(), s->wq, s->n));
+  return gram_finish(ctx, s, H_out);
+}
+
+// Gram over a SUBSET of the candidates (the support of a query distribution, e.g. the greedy selection):
+// cand[n_sub] = candidate indices, q_sub[n_sub] their weights.
+extern "C" int nnal_fi_gram_subset(nnal_ctx* ctx, const int64_t* cand, int64_t n_sub, const double* q_sub, float* H_out) {
+  if (!ctx || n_sub < 0 || (n_sub > 0 && (!cand || !q_sub))) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state) NNAL_FAIL(ctx, NNAL_ERR_STATE, "FI candidates not set");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  State* s = (State*)ctx->fi_state;
+  for (int64_t j = 0; j < n_sub; ++j)
+    if (cand[j] < 0 || cand[j] >= s->n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "candidate index out of range");
+  if (n_sub > 0) {
+    if (s->sub_cap < n_sub) {
+      NNAL_TRY(fi::ensure(ctx, s->sub_rows, 0, (size_t)n_sub));
+      NNAL_TRY(fi::ensure(ctx, s->sub_wq, 0, (size_t)n_sub));
+      s->sub_cap = n_sub;
     }
+    NNAL_TRY(devbuf_reserve(ctx, ctx->fi_ws, (size_t)n_sub * 16));
+    int64_t* d_c = (int64_t*)ctx->fi_ws.p;
+    double* d_q = (double*)((char*)ctx->fi_ws.p + (size_t)n_sub * 8);
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_c, cand, (size_t)n_sub * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_q, q_sub, (size_t)n_sub * 8, cudaMemcpyHostToDevice, ctx->stream));
+    fi::gram_subset_kernel<<<std::min(cdiv(n_sub, 256), ctx->sm_count * 8), 256, 0, ctx->stream>>>(s->R(), s->w, d_c, d_q, n_sub, s->sub_rows,
+                                                                                                 s->sub_wq);
+    ctx->launches++;
   }
-  if (H_out) {
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(H_out, (size_t)Dg * 4, s->H, (size_t)ld * 4, (size_t)Dg * 4, Dg, cudaMemcpyDeviceToHost, ctx->stream));
+  NNAL_TRY(gram_core(ctx, s, s->sub_rows, s->sub_wq, n_sub));
+  return gram_finish(ctx, s, H_out);
+}
+
+// Primal FI objective through the Gram left on the device (after the host layer's NCCL all-reduce of the per-GPU
+// partials): *tr_out = tr((delta I + scale H)^-1) -- with scale = 2 and the (d+1)/delta of the null space of v v^T this is
+// tr((sum_i q_i F_i + delta I)^-1) for the last-layer FI F_i = (v v^T) (x) w_i [u_i;1][u_i;1]^T (NN.py:891-901,
+// NNAL_tools.py:589-602).  d_G2 (optional DEVICE pointer, same layout as the Gram): *ratio_out =
+// tr((delta I + scale H)^-1 (delta I + scale G2)), the Fisher-information ratio of a second (e.g. pool-wide) Gram against H.
+extern "C" int nnal_fi_gram_solve(nnal_ctx* ctx, double delta, double scale, const float* d_G2, double* tr_out, double* ratio_out) {
+  if (!ctx || !(delta > 0) || !tr_out) return NNAL_ERR_INVALID;
+  if (!ctx->fi_state || !((State*)ctx->fi_state)->H) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no Gram computed");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  State* s = (State*)ctx->fi_state;
+  const int n = s->Hd, B = fi::GJ_B;
+  const int np = (n + B - 1) / B * B, P = np / B;
+  if (s->gj_np != np) {
+    NNAL_TRY(fi::ensure(ctx, s->gj_M, 0, (size_t)np * np));
+    NNAL_TRY(fi::ensure(ctx, s->gj_R, 0, (size_t)B * np));
+    NNAL_TRY(fi::ensure(ctx, s->gj_C, 0, (size_t)np * B));
+    NNAL_TRY(fi::ensure(ctx, s->gj_D, 0, (size_t)B * B));
+    NNAL_TRY(fi::ensure(ctx, s->gj_out, 0, (size_t)2));
+    s->gj_np = np;
   }
+  static bool attr_gj = false;
+  if (!attr_gj) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(fi::gj_panels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fi::GJ_SMEM));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(fi::gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fi::GJ_SMEM));
+    attr_gj = true;
+  }
+  prof_begin(ctx, NNAL_PROF_FI_SOLVE);
+  fi::gj_init_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(s->H, s->Hld, n, np, delta, scale, s->gj_M);
+  for (int p = 0; p < P; ++p) {
+    fi::invert_reg_kernel<2><<<1, 1024, 0, ctx->stream>>>(s->gj_M + (size_t)p * B * np + (size_t)p * B, np, B, 0.0, s->gj_D, B, s->sc);
+    fi::gj_panels_kernel<<<P, 256, fi::GJ_SMEM, ctx->stream>>>(s->gj_M, np, p, s->gj_D, s->gj_R, s->gj_C);
+    fi::gj_update_kernel<<<dim3(P, P), 256, fi::GJ_SMEM, ctx->stream>>>(s->gj_M, np, p, s->gj_D, s->gj_R, s->gj_C);
+  }
+  CUDA_TRY(ctx, cudaMemsetAsync(s->gj_out, 0, 16, ctx->stream));
+  fi::gj_reduce_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(s->gj_M, n, np, d_G2, s->Hld, delta, scale, s->gj_out);
+  ctx->launches += 2 + 3 * P;
+  prof_end(ctx);
+  CUDA_TRY(ctx, cudaGetLastError());
+  double out[2];
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, s->gj_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *tr_out = out[0];
+  if (ratio_out) *ratio_out = d_G2 ? out[1] : 0.0;
   return NNAL_OK;
 }
 

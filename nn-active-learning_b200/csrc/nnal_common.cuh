@@ -169,6 +169,7 @@ static inline void prof_end(nnal_ctx* ctx) {
 #define NNAL_PROF_FI_SETUP 110
 #define NNAL_PROF_FI_GRAM 111
 #define NNAL_PROF_FI_GREEDY 112
+#define NNAL_PROF_FI_SOLVE 113
 #define NNAL_PROF_BW_FORWARD 120
 #define NNAL_PROF_BW_BACKWARD 121
 

@@ -69,6 +69,68 @@ def allgather_topk(scores, positions, k):
     return P[order], S[order]
 
 
+def engine_stream(eng):
+    """Context manager making the engine's CUDA stream torch's current stream, so that NCCL collectives issued
+    inside it are ordered with the library's kernels (no host synchronisation)."""
+    import contextlib
+    import torch
+    if getattr(eng, 'message_device', 'cpu') != 'cuda':
+        return contextlib.nullcontext()
+    return torch.cuda.stream(torch.cuda.ExternalStream(eng.stream))
+
+
+class _DevPtr(object):
+    """Exposes a raw device pointer of the library to torch (``torch.as_tensor(_DevPtr(...), device='cuda')``)
+    through the CUDA array interface -- no copy; the engine keeps the memory alive."""
+
+    def __init__(self, ptr, shape, typestr, strides=None):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False),
+                                         'version': 2, 'strides': strides}
+
+
+def device_view(ptr, shape, typestr='<f4'):
+    import torch
+    return torch.as_tensor(_DevPtr(ptr, shape, typestr), device='cuda')
+
+
+def topk_global(eng, k, lo, n_total):
+    """The k pool samples with the smallest (score, global position) over ALL ranks' current pool scores
+    (``np.argsort(score, kind='stable')[:k]`` of the concatenated pool, PW_NNAL.py:724-730); ``lo`` = global
+    position of this rank's first sample.  Returns (positions, scores), identical on every rank.
+    NCCL: every rank leaves its k best (score, position) pairs on the device, ONE packed
+    ``all_gather_into_tensor`` on the engine's stream, device-side merge, one k-element read-back."""
+    k = int(min(max(int(k), 0), int(n_total)))
+    if not is_dist():
+        idx, sc = eng.pool_topk(k, with_scores=True)
+        return idx + lo, sc
+    td = _td()
+    if td.get_backend() != 'nccl' or not hasattr(eng, 'pool_topk_device'):
+        idx, sc = eng.pool_topk(k, with_scores=True)          # gloo (CPU tests over the NumPy fake engine)
+        return allgather_topk(sc, idx + lo, k)
+    import torch
+    world = td.get_world_size()
+    if k == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0)
+    with engine_stream(eng):
+        send = torch.empty(k * 16, dtype=torch.uint8, device='cuda')
+        recv = torch.empty(world * k * 16, dtype=torch.uint8, device='cuda')
+        eng.pool_topk_device(k, k, lo, send.data_ptr())
+        td.all_gather_into_tensor(recv, send)
+        pos, sc = eng.topk_merge_pairs(recv.data_ptr(), world * k, k)
+    return pos, sc
+
+
+def allreduce_device_f32_(eng, ptr, count):
+    """In-place NCCL sum all-reduce of ``count`` float32 values at device pointer ``ptr`` (library memory), on
+    the engine's stream.  Returns the bytes reduced (0 in a single process)."""
+    if not is_dist():
+        return 0
+    with engine_stream(eng):
+        t = device_view(ptr, (int(count),), '<f4')
+        _td().all_reduce(t)
+    return int(count) * 4
+
+
 def allgather_concat(arr):
     """Concatenate per-rank 1-D arrays (rank order) on every rank."""
     import torch

@@ -320,6 +320,20 @@ class Engine(object):
         self._chk(self.lib.nnal_pool_topk(self.h, k, _ptr(idx), _ptr(sc) if with_scores else None))
         return (idx, sc) if with_scores else idx
 
+    def pool_topk_device(self, k, k_pad, pos_offset, d_pairs_ptr):
+        """k best (score, pos_offset + position) pairs of the current pool scores into DEVICE memory (16 B each)."""
+        self._chk(self.lib.nnal_pool_topk_device(self.h, int(k), int(k_pad), int(pos_offset), C.c_void_p(int(d_pairs_ptr))))
+
+    def topk_merge_pairs(self, d_pairs_ptr, n_pairs, k):
+        """Global k smallest of ``n_pairs`` gathered pairs -> (positions, scores) on the host; padding slots dropped."""
+        k = int(k)
+        pos = np.empty(k, dtype=np.int64)
+        sc = np.empty(k, dtype=np.float64)
+        self.d2h_bytes += pos.nbytes + sc.nbytes
+        self._chk(self.lib.nnal_topk_merge_pairs(self.h, C.c_void_p(int(d_pairs_ptr)), int(n_pairs), k, _ptr(pos), _ptr(sc)))
+        valid = pos != np.iinfo(np.int64).max
+        return pos[valid], sc[valid]
+
     # ------------------------------------------------------------------
     # Fisher information
     # ------------------------------------------------------------------
@@ -367,6 +381,31 @@ class Engine(object):
             self.d2h_bytes += out.nbytes
         self._chk(self.lib.nnal_fi_gram(self.h, None if q is None else _ptr(q), None if out is None else _ptr(out)))
         return out
+
+    def fi_gram_subset(self, cand, q_sub, read=False):
+        """Gram over the candidate subset ``cand`` (indices into the candidate list) with weights ``q_sub``; stays on
+        the device unless ``read``."""
+        cand = np.ascontiguousarray(cand, dtype=np.int64).ravel()
+        q_sub = np.ascontiguousarray(q_sub, dtype=np.float64).ravel()
+        if cand.size != q_sub.size:
+            raise ValueError('one weight per subset candidate expected')
+        d = self.fi_info()['d']
+        out = np.empty((d + 1, d + 1), dtype=np.float32) if read else None
+        self.h2d_bytes += cand.nbytes + q_sub.nbytes
+        if read:
+            self.d2h_bytes += out.nbytes
+        self._chk(self.lib.nnal_fi_gram_subset(self.h, _ptr(cand) if cand.size else None, cand.size,
+                                               _ptr(q_sub) if cand.size else None, None if out is None else _ptr(out)))
+        return out
+
+    def fi_gram_solve(self, delta, scale=2.0, d_G2_ptr=None):
+        """(tr((delta I + scale H)^-1), tr((delta I + scale H)^-1 (delta I + scale G2)) or None) for the Gram H on the
+        device, float64 blocked Gauss-Jordan."""
+        tr, ra = C.c_double(), C.c_double()
+        self._chk(self.lib.nnal_fi_gram_solve(self.h, float(delta), float(scale),
+                                              None if d_G2_ptr is None else C.c_void_p(int(d_G2_ptr)), C.byref(tr), C.byref(ra)))
+        self.d2h_bytes += 16
+        return tr.value, (ra.value if d_G2_ptr is not None else None)
 
     def fi_gram_device(self):
         """(device pointer, rows, row stride) of the Gram left on the device by ``fi_gram``."""

@@ -36,20 +36,21 @@ def greedy_select(eng, k, delta, gids=None):
     fixed-size message per rank (its local best: loss, id, factor rows, K_SS row) and every rank applies the
     same global winner.  ``gids``: global candidate ids of
     this rank's candidates (ascending), used for the result and for tie-breaking (lowest id).
-    Returns (selected global ids in selection order, objective after each step)."""
+    Returns (selected global ids in selection order, objective after each step, its kernel-dependent part
+    ``tr((delta I + K_SS/s)^-1)`` -- the full objective is ``(D - s)/delta`` plus that)."""
     n_local = eng.fi_info()['n']
     if gids is None:
         gids = np.arange(n_local, dtype=np.int64)
     if not dist.is_dist():
-        sel, obj, _ = eng.fi_greedy(k, delta)
-        return gids[sel], obj
+        sel, obj, red = eng.fi_greedy(k, delta)
+        return gids[sel], obj, red
     import torch
     import torch.distributed as td
     rank, world = dist.rank_world()
     n_total = int(dist.allreduce_sum_(torch.tensor([n_local], dtype=torch.int64, device=dist._device())).item())
     k = min(int(k), n_total)
     if k == 0:
-        return np.zeros(0, dtype=np.int64), np.zeros(0)
+        return np.zeros(0, dtype=np.int64), np.zeros(0), np.zeros(0)
     D = eng.fi_info()['D']
     eng.fi_begin(k, delta)
     eng.fi_set_gids(gids)
@@ -68,7 +69,97 @@ def greedy_select(eng, k, delta, gids=None):
             eng.fi_step_apply_gathered(t, recv.data_ptr(), world, rank)
     sel, red = eng.fi_result(k)
     s = np.arange(1, k + 1, dtype=np.float64)
-    return sel, (D - s) / delta + red
+    return sel, (D - s) / delta + red, red
+
+
+last_report = None          # dict left by the last FI query run with expr.pars['fi_report'] = True (see gram_report)
+
+
+def gram_allreduce(eng):
+    """Sums the per-GPU Gram partials left on the device by ``fi_gram`` / ``fi_gram_subset`` over all ranks: NCCL
+    all-reduce of the (d+1) x ld float32 matrix on the engine's stream (SURVEY.md 8e collective 2).  In place; returns the
+    bytes reduced (0 in a single process).  gloo / fake engine (CPU tests): the host copy is reduced instead."""
+    if not dist.is_dist():
+        return 0
+    if getattr(eng, 'message_device', 'cpu') != 'cuda':
+        return eng.fi_gram_allreduce_host()
+    ptr, rows, ld = eng.fi_gram_device()
+    return dist.allreduce_device_f32_(eng, ptr, rows * ld)
+
+
+def gram_report(eng, sel_gids, gids, delta, cand_rows=None, pool_gram=True):
+    """Primal (Gram) form of the FI objective for the selection ``sel_gids`` (global candidate ids) on the engine's
+    current candidate set (``gids``: global ids of the local candidates, ascending).
+
+    Every rank builds its partial of the weighted penultimate-feature Gram ``H = sum_i q_i w_i [u_i;1][u_i;1]^T`` on
+    tensor cores -- (a) over ALL its candidates at ``q = 1/n`` (the pool's last-layer Fisher information) and (b) over
+    its members of the selection at ``q = uniform(S)`` -- the partials are summed with an NCCL all-reduce, and the
+    reference's objective ``tr((sum_i q_i A_i)^-1)`` (NNAL_tools.py:589-602) restricted to the last layer,
+    ``tr((delta I + 2 H_S)^-1) + (d+1)/delta``, is evaluated on the device, together with the Fisher-information ratio
+    ``tr((delta I + 2 H_S)^-1 (delta I + 2 H_pool))``.  ``dual_last_layer`` is the same objective through the k x k
+    kernel of the selected samples (float64, host): the two must agree, on every rank."""
+    import torch
+    rank, world = dist.rank_world()
+    gids = np.asarray(gids, dtype=np.int64)
+    sel_gids = np.asarray(sel_gids, dtype=np.int64)
+    k = len(sel_gids)
+    n_local = len(gids)
+    d = eng.fi_info()['d']
+    n_total = n_local
+    if dist.is_dist():
+        n_total = int(dist.allreduce_sum_(torch.tensor([n_local], dtype=torch.int64, device=dist._device())).item())
+    rep = {'k': int(k), 'n_candidates': int(n_total), 'delta': float(delta), 'gram_bytes': 0}
+    cuda = getattr(eng, 'message_device', 'cpu') == 'cuda'
+    G2 = None
+    if pool_gram and n_total > 0:
+        eng.fi_gram(np.full(n_local, 1. / n_total), read=False)
+        rep['gram_bytes'] = gram_allreduce(eng)
+        if cuda:
+            ptr, rows, ld = eng.fi_gram_device()
+            with dist.engine_stream(eng):
+                G2 = dist.device_view(ptr, (rows * ld,), '<f4').clone()
+        else:
+            G2 = eng.fi_gram_read().copy()
+    # members of the selection owned by this rank (gids is ascending)
+    pos = np.searchsorted(gids, sel_gids)
+    pos = np.minimum(pos, max(n_local - 1, 0))
+    mine = (gids[pos] == sel_gids) if n_local else np.zeros(k, dtype=bool)
+    loc = pos[mine]
+    eng.fi_gram_subset(loc, np.full(len(loc), 1. / max(k, 1)))
+    gram_allreduce(eng)
+    tr, ratio = eng.fi_gram_solve(delta, 2.0, None if G2 is None else (G2.data_ptr() if cuda else G2))
+    rep['primal_last_layer'] = tr + (d + 1) / delta
+    rep['primal_reduced'] = tr - (d + 1 - min(k, d + 1)) / delta
+    rep['fi_ratio'] = ratio
+    # dual form of the same last-layer objective from the selected samples' rows (k x k, float64 on the host)
+    rows_local = loc if cand_rows is None else np.asarray(cand_rows)[loc]
+    F = eng.pool_feature_rows(rows_local).astype(np.float64) if len(loc) else np.zeros((0, d))
+    p1 = eng.pool_posteriors()[1].astype(np.float64)[rows_local] if len(loc) else np.zeros(0)
+    blk = np.zeros((k, d + 2))
+    blk[np.nonzero(mine)[0], :d] = F
+    blk[np.nonzero(mine)[0], d] = 1.
+    blk[np.nonzero(mine)[0], d + 1] = p1
+    if dist.is_dist():
+        t = torch.from_numpy(blk).to(dist._device())
+        dist.allreduce_sum_(t)
+        blk = t.cpu().numpy()
+    Ut, p = blk[:, :d + 1], blk[:, d + 1]
+    sw = np.sqrt(p * (1. - p))
+    K1 = 2. * (Ut @ Ut.T) * np.outer(sw, sw) / max(k, 1)
+    lam = np.linalg.eigvalsh(K1) if k else np.zeros(0)
+    red = float(np.sum(1. / (delta + np.maximum(lam, 0.))))
+    rep['dual_reduced'] = red
+    rep['dual_last_layer'] = (2 * (d + 1) - k) / delta + red
+    return rep
+
+
+def _maybe_report(expr, eng, chosen, gids, delta, obj):
+    """``expr.pars['fi_report'] = True``: leave the Gram-form (primal) evaluation of the selection in ``fi.last_report``."""
+    global last_report
+    if not expr.pars.get('fi_report', False):
+        return
+    last_report = gram_report(eng, chosen, gids, delta)
+    last_report['dual_objective'] = float(obj[-1]) if len(obj) else None
 
 
 def _pars(expr, default_delta):
@@ -87,8 +178,7 @@ def query_single(expr, model, sess, padded_imgs, pool_inds, return_objective=Fal
     if B < n:
         eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=0)
         eng.pool_score(L.SCORE_BINARY)
-        idx, sc = eng.pool_topk(B, with_scores=True)
-        sel_inds, _ = dist.allgather_topk(sc, idx + lo, B)
+        sel_inds, _ = dist.topk_global(eng, B, lo, n)
         own = (sel_inds >= lo) & (sel_inds < hi)
         mine = sel_inds[own]
         # second pass over this rank's candidates, keeping the factors of the last FC layers
@@ -103,8 +193,11 @@ def query_single(expr, model, sess, padded_imgs, pool_inds, return_objective=Fal
         own = (sel_inds >= lo) & (sel_inds < hi)
     eng.fi_set_candidates(None, nl)
     gids = np.nonzero(own)[0].astype(np.int64)
-    chosen, obj = greedy_select(eng, min(k, len(sel_inds)), delta, gids)
+    chosen, obj, red = greedy_select(eng, min(k, len(sel_inds)), delta, gids)
+    _maybe_report(expr, eng, chosen, gids, delta, obj)
     q = sel_inds[chosen]
+    if return_objective == 'reduced':
+        return q, obj, red
     return (q, obj) if return_objective else q
 
 
@@ -142,8 +235,11 @@ def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, return_objectiv
         off += ni
     eng.fi_set_candidates(None, nl)
     gids = np.nonzero(own)[0].astype(np.int64)
-    chosen, obj = greedy_select(eng, min(k, len(G)), delta, gids)
+    chosen, obj, red = greedy_select(eng, min(k, len(G)), delta, gids)
+    _maybe_report(expr, eng, chosen, gids, delta, obj)
     Q = patch_utils.global2local_inds(G[chosen], sizes)
+    if return_objective == 'reduced':
+        return Q, obj, red
     return (Q, obj) if return_objective else Q
 
 
@@ -203,8 +299,7 @@ def query_single_sdp(expr, model, sess, padded_imgs, pool_inds, return_solution=
     eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=0)
     if B < n:
         eng.pool_score(L.SCORE_BINARY)
-        idx, sc = eng.pool_topk(B, with_scores=True)
-        sel_inds, _ = dist.allgather_topk(sc, idx + lo, B)
+        sel_inds, _ = dist.topk_global(eng, B, lo, n)
     else:
         sel_inds = np.arange(n, dtype=np.int64)
     imgs = list(padded_imgs)
@@ -297,8 +392,7 @@ def query_whole_sdp(model, expr, pool_inds, session, return_solution=False):
     eng, lo, hi = _posteriors_on_device(model, expr, pool_inds, session, keep=0)
     if B < n:
         eng.pool_score(L.SCORE_NEG_ENTROPY, 1e-8)
-        idx, sc = eng.pool_topk(B, with_scores=True)
-        sel_inds, _ = dist.allgather_topk(sc, idx + lo, B)
+        sel_inds, _ = dist.topk_global(eng, B, lo, n)
     else:
         sel_inds = np.arange(n, dtype=np.int64)
     a, e = _my_slice(len(sel_inds))
@@ -323,17 +417,15 @@ def query_whole(model, expr, pool_inds, session):
     eng, lo, hi = _posteriors_on_device(model, expr, pool_inds, session, keep=1)
     if eng.n_class != 2:
         eng.pool_score(L.SCORE_NEG_FI_TRACE)
-        idx, sc = eng.pool_topk(k, with_scores=True)
-        q, _ = dist.allgather_topk(sc, idx + lo, min(k, n))
+        q, _ = dist.topk_global(eng, k, lo, n)
         return q
     if B < n:
         eng.pool_score(L.SCORE_NEG_ENTROPY, 1e-8)
-        idx, sc = eng.pool_topk(B, with_scores=True)
-        sel_inds, _ = dist.allgather_topk(sc, idx + lo, B)
+        sel_inds, _ = dist.topk_global(eng, B, lo, n)
     else:
         sel_inds = np.arange(n, dtype=np.int64)
     own = (sel_inds >= lo) & (sel_inds < hi)
     eng.fi_set_candidates(sel_inds[own] - lo, 1)
     gids = np.nonzero(own)[0].astype(np.int64)
-    chosen, _ = greedy_select(eng, min(k, len(sel_inds)), delta, gids)
+    chosen, _, _ = greedy_select(eng, min(k, len(sel_inds)), delta, gids)
     return sel_inds[chosen]

@@ -98,8 +98,7 @@ def query_rep_entropy_whole(model, expr, pool_inds, session):
     eng, lo, hi = _posteriors_on_device(model, expr, pool_inds, session, keep=1)
     if B < n:
         eng.pool_score(L.SCORE_NEG_ENTROPY, 1e-8)
-        idx, sc = eng.pool_topk(B, with_scores=True)
-        sel_inds, _ = dist.allgather_topk(sc, idx + lo, B)
+        sel_inds, _ = dist.topk_global(eng, B, lo, n)
     else:
         sel_inds = np.arange(n, dtype=np.int64)
     own = (sel_inds >= lo) & (sel_inds < hi)

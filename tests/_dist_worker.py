@@ -57,6 +57,14 @@ def run(rank, world, out):
     expr.pars['B'] = 10 ** 6                 # no pre-filter: every rank's whole block is a candidate
     q, obj = nnal_b200.fi.query_single(expr, model, None, allp[0][:m], pool0, return_objective=True)
     res['fi_all'], res['fi_all_obj'] = q, obj
+    # Gram (primal) form of the objective for the selection: per-rank partial Grams, all-reduce, (d+1)^2 inverse
+    expr.pars.update(B=30, fi_layers=1, fi_report=True)
+    q, obj = nnal_b200.fi.query_single(expr, model, None, allp[0][:m], pool0, return_objective=True)
+    rep = nnal_b200.fi.last_report
+    res['fi_rep_sel'], res['fi_rep_dual_obj'] = q, np.array([obj[-1]])
+    res['fi_rep'] = np.array([rep['primal_last_layer'], rep['dual_last_layer'], rep['fi_ratio'], rep['primal_reduced'],
+                              rep['dual_reduced']])
+    expr.pars.update(fi_layers=2, fi_report=False, B=10 ** 6)
     # the reference's literal FI pipeline (shrunk A-matrices -> SDP -> sampling): every rank evaluates the same B
     # candidates, rank 0's draw is broadcast
     expr.pars.update(B=30, fi_mode='sdp', fi_diag_load=1e-3)

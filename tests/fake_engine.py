@@ -422,6 +422,40 @@ class FakeEngine(object):
     def fi_result(self, k):
         return np.array(self._sel[:k], dtype=np.int64), np.array(self._red[:k])
 
+    # -- weighted Gram / primal objective (float64 through the oracle) ------------------------------------
+    def _gram(self, idx, q):
+        d = self.fi_info()['d']
+        Ut = np.concatenate([self.fi_U[idx], np.ones((len(idx), 1))], axis=1) if len(idx) else np.zeros((0, d + 1))
+        wq = np.asarray(q, dtype=np.float64) * self.fi_w[idx]
+        self.fi_H = (Ut * wq[:, None]).T @ Ut
+        return self.fi_H
+
+    def fi_gram(self, q=None, read=True):
+        n = len(self.fi_p1)
+        H = self._gram(np.arange(n), np.full(n, 1. / max(n, 1)) if q is None else q)
+        return H.astype(np.float32) if read else None
+
+    def fi_gram_subset(self, cand, q_sub, read=False):
+        H = self._gram(np.asarray(cand, dtype=np.int64), q_sub)
+        return H.astype(np.float32) if read else None
+
+    def fi_gram_read(self):
+        return self.fi_H.copy()
+
+    def fi_gram_allreduce_host(self):
+        import torch
+        import torch.distributed as td
+        t = torch.from_numpy(np.ascontiguousarray(self.fi_H))
+        td.all_reduce(t)
+        self.fi_H = t.numpy()
+        return self.fi_H.size * 4
+
+    def fi_gram_solve(self, delta, scale=2.0, d_G2_ptr=None):
+        n = self.fi_H.shape[0]
+        Minv = np.linalg.inv(delta * np.eye(n) + scale * self.fi_H)
+        ratio = None if d_G2_ptr is None else float(np.sum(Minv * (delta * np.eye(n) + scale * np.asarray(d_G2_ptr))))
+        return float(np.trace(Minv)), ratio
+
     # -- the reference's literal FI pipeline (shrunk gradients + SDP), through the float64 oracle ------------
     def fi_shrunk_tau(self):
         return sum(1 for _, sp in self.layers if sp[1] != 'pool')

@@ -117,6 +117,20 @@ def test_single_process_matches_oracle(runs):
     assert np.array_equal(one['fi_sdp_whole'], sel[draws])
 
 
+def test_gram_allreduce_primal_equals_dual(runs):
+    """Per-rank partial Grams summed by an all-reduce give the same primal objective tr((delta I + 2H)^-1) + (d+1)/delta
+    on every rank and world size, equal to the dual (kernel) objective the greedy loop reports (last-layer FI)."""
+    one, two, three = runs
+    for r in [one] + list(two) + list(three):
+        primal, dual, ratio, pred, dred = r['fi_rep']
+        assert abs(primal / r['fi_rep_dual_obj'][0] - 1) < 1e-9
+        assert abs(primal / dual - 1) < 1e-9
+        assert abs(pred / dred - 1) < 1e-6            # the kernel-dependent part alone
+        assert np.isfinite(ratio) and ratio > 0
+        assert np.array_equal(r['fi_rep_sel'], one['fi_rep_sel'])
+        assert np.allclose(r['fi_rep'], one['fi_rep'], rtol=1e-9)
+
+
 def test_collective_primitives(runs):
     for multi in runs[1:]:
         world = len(multi)

@@ -41,13 +41,28 @@ def _oracle_kernel(p1, U, A, Wl, two):
     return Kt, D
 
 
-def assert_greedy_equivalent(Kt, D, delta, sel, obj, rtol=OBJ_RTOL):
-    """``sel`` must be a valid greedy trajectory up to ties within ``rtol``; ``obj`` its objectives."""
+def reduced_objectives(Kt, delta, sel):
+    """tr((delta I + Kt_SS/s)^-1) for every prefix S of ``sel`` -- the kernel-dependent part of the objective (the
+    rest, (D - s)/delta, is a constant ~1e12 that would hide any error at rtol 1e-3)."""
+    out = []
+    for s in range(1, len(sel) + 1):
+        S = list(sel[:s])
+        out.append(np.trace(np.linalg.inv(delta * np.eye(s) + Kt[np.ix_(S, S)] / float(s))))
+    return np.array(out)
+
+
+def assert_greedy_equivalent(Kt, D, delta, sel, red, rtol=OBJ_RTOL, red_oracle=None):
+    """``sel`` must be a valid greedy trajectory up to ties within ``rtol``; ``red`` the REDUCED objective
+    tr((delta I + K_SS/s)^-1) reported for it per step, which must equal the float64 value for that same selection and,
+    at the last step, the oracle's own greedy value (``red_oracle``)."""
     sel = np.asarray(sel)
     assert len(np.unique(sel)) == len(sel)
     rep = O.greedy_fi_replay(Kt, D, delta, sel)
     assert np.all(rep[:, 0] <= rep[:, 1] * (1 + rtol) + 1e-300), 'picked a candidate clearly worse than the best'
-    assert np.allclose(obj, rep[:, 2], rtol=rtol), 'objective off by %g' % np.abs(obj / rep[:, 2] - 1).max()
+    want = reduced_objectives(Kt, delta, sel)
+    assert np.allclose(red, want, rtol=rtol), 'reduced objective off by %g' % np.abs(red / want - 1).max()
+    if red_oracle is not None:
+        assert abs(red[-1] / red_oracle[len(sel) - 1] - 1) < rtol, 'final reduced objective differs from the oracle greedy'
 
 
 @pytest.mark.parametrize('two', [False, True])
@@ -65,9 +80,9 @@ def test_fi_greedy_given_factors(nb, two, n, d, dp, k):
     So, oo, ro = O.greedy_fi_rank1(Kt, D, delta, k, return_reduced=True)
     # kernel entries carry ~1e-8 relative error (float32 FMA chains flushed into float64 sums): the kernel-dependent
     # part of the objective is reproduced to ~1e-5, far inside the 1e-3 of the north star
-    assert_greedy_equivalent(Kt, D, delta, sel, obj, rtol=1e-4)
+    assert_greedy_equivalent(Kt, D, delta, sel, red, rtol=1e-4, red_oracle=ro)
     assert len(set(sel.tolist()) ^ set(So.tolist())) <= 2
-    assert np.allclose(red[:len(ro)], ro, rtol=1e-4) or not np.array_equal(sel, So)
+    assert np.allclose(obj, (D - np.arange(1, len(sel) + 1)) / delta + red, rtol=1e-12)
 
 
 def test_fi_greedy_edge_cases(nb):
@@ -161,6 +176,60 @@ def test_fi_gram_equals_dual_objective(nb):
     assert abs(O.fi_objective_from_gram(H, 2, delta) / obj[-1] - 1) < OBJ_RTOL
 
 
+@pytest.mark.parametrize('n,d,k', [(300, 127, 20), (900, 320, 64)])
+def test_fi_gram_subset_and_solve(nb, n, d, k):
+    """Gram over the support of a query distribution + the float64 Gauss-Jordan primal objective on the device:
+    tr((delta I + 2 H_S)^-1) against NumPy, and the Fisher-information ratio against a second (pool-wide) Gram."""
+    import torch
+    p1, U, A, Wl = _factors(n, d, 8, n + 1)
+    eng = nb.get_engine()
+    eng.fi_set_factors(p1, U)
+    rs = np.random.RandomState(3)
+    S = rs.choice(n, k, replace=False)
+    w = p1 * (1 - p1)
+    Hp = eng.fi_gram(None)                                       # pool-wide Gram, q = 1/n
+    ptr, rows, ld = eng.fi_gram_device()
+    from nnal_b200 import dist
+    G2 = dist.device_view(ptr, (rows * ld,), '<f4').clone()
+    torch.cuda.synchronize()
+    Hs = eng.fi_gram_subset(S, np.full(k, 1. / k), read=True)
+    Ut = np.concatenate([U.astype(np.float64), np.ones((n, 1))], axis=1)
+    Hso = (Ut[S] * (w[S] / k)[:, None]).T @ Ut[S]
+    assert np.abs(Hs - Hso).max() < 1e-5 * np.abs(Hso).max()
+    for delta in (1e-2, 1e-3):
+        tr, ratio = eng.fi_gram_solve(delta, 2.0, G2.data_ptr())
+        Minv = np.linalg.inv(delta * np.eye(d + 1) + 2. * Hs.astype(np.float64))
+        assert abs(tr / np.trace(Minv) - 1) < 1e-9               # same float32 Gram in, float64 arithmetic
+        want = np.sum(Minv * (delta * np.eye(d + 1) + 2. * Hp.astype(np.float64)))
+        assert abs(ratio / want - 1) < 1e-8
+        # against the dual (kernel) form of the same objective
+        Kss = 2. * (Ut[S] @ Ut[S].T) * np.sqrt(np.outer(w[S], w[S]))
+        dual = (d + 1 - k) / delta + np.trace(np.linalg.inv(delta * np.eye(k) + Kss / k))
+        assert abs(tr / dual - 1) < OBJ_RTOL
+    # empty subset: H = 0
+    H0 = eng.fi_gram_subset(np.zeros(0, dtype=np.int64), np.zeros(0), read=True)
+    assert not H0.any()
+    tr, _ = eng.fi_gram_solve(1e-2)
+    assert abs(tr / ((d + 1) / 1e-2) - 1) < 1e-12
+
+
+def test_pw_fi_report_primal_equals_dual(nb):
+    """fi_report: the selection's Gram (tensor cores) -> primal objective == the dual objective of the greedy loop
+    (last-layer FI, multi-volume diag_load 1e-3)."""
+    ps, imgs, padded, stats, pool, layers, w = _pw_setup(260, 90)
+    model = nb.NN.create_PW1(2)
+    model.set_weights(w)
+    expr = Expr(k=10, B=80, lambda_=0., patch_shape=ps, ntb=128, stats=stats, fi_layers=1, fi_diag_load=1e-3, fi_report=True)
+    q, obj, red = nb.fi.query_single(expr, model, None, padded, pool, return_objective='reduced')
+    rep = nb.fi.last_report
+    assert rep['k'] == 10 and rep['n_candidates'] == 80
+    assert abs(rep['primal_last_layer'] / obj[-1] - 1) < 1e-6
+    assert abs(rep['dual_last_layer'] / obj[-1] - 1) < 1e-9
+    assert abs(rep['dual_reduced'] / red[-1] - 1) < 1e-4
+    assert abs(rep['primal_reduced'] / red[-1] - 1) < 2e-2       # float32 Gram: the kernel part is ~1e-6 of the trace
+    assert rep['fi_ratio'] > 0
+
+
 def _pw_setup(n_pool, seed, shape=(40, 36, 6)):
     ps = (25, 25, 1)
     imgs = synth_volume(shape, 3, seed)
@@ -183,7 +252,7 @@ def test_pw_fi_query_single(nb, nl, B):
     model.set_weights(w)
     k = 12
     expr = Expr(k=k, B=B, lambda_=0., patch_shape=ps, ntb=128, stats=stats, fi_layers=nl, fi_diag_load=1e-5)
-    q, obj = nb.fi.query_single(expr, model, None, padded, pool, return_objective=True)
+    q, obj, red = nb.fi.query_single(expr, model, None, padded, pool, return_objective='reduced')
     q2 = nb.PW_NNAL.CNN_query(expr, model, None, padded, pool, None, 'fi')
     assert np.array_equal(q, q2)
     qo, oo, det = O.query_fi_single(layers, w, padded, pool, ps, 128, stats, k, B, nl, 1e-5)
@@ -192,8 +261,8 @@ def test_pw_fi_query_single(nb, nl, B):
     assert np.all(np.isin(q, sel))
     pos = {int(v): i for i, v in enumerate(sel)}
     S_gpu = np.array([pos[int(v)] for v in q])
-    assert_greedy_equivalent(det['Kt'], det['D'], 1e-5, S_gpu, obj)
-    assert np.allclose(obj, oo, rtol=OBJ_RTOL) or set(q.tolist()) != set(qo.tolist())
+    ro = reduced_objectives(det['Kt'], 1e-5, [pos[int(v)] for v in qo])          # the oracle's own greedy trajectory
+    assert_greedy_equivalent(det['Kt'], det['D'], 1e-5, S_gpu, red, red_oracle=ro)
 
 
 def test_pw_fi_query_multimg(nb):
@@ -217,7 +286,7 @@ def test_pw_fi_query_multimg(nb):
     k, B = 8, 50
     expr = Expr(k=k, B=B, lambda_=0., patch_shape=ps, ntb=128, SDP_solver='CVXOPT')
     expr.train_stats = st
-    Q, obj = nb.fi.query_multimg(expr, model, None, allp, pools, return_objective=True)
+    Q, obj, red = nb.fi.query_multimg(expr, model, None, allp, pools, return_objective='reduced')
     Q2 = nb.PW_NNAL.query_multimg(expr, model, None, allp, pools, None, 'fi')
     assert len(Q) == S and len(Q[1]) == 0 and sum(len(a) for a in Q) == k
     assert all(np.array_equal(a, b) for a, b in zip(Q, Q2))
@@ -234,9 +303,13 @@ def test_pw_fi_query_multimg(nb):
     cand = np.concatenate([[offs[s] + {int(v): i for i, v in enumerate(sel_inds[s])}[int(v)] for v in Q[s]]
                            for s in range(S)]).astype(int)
     Kss = det['Kt'][np.ix_(cand, cand)]
-    f_set = O.fi_objective_dual(Kss, k, det['D'], 1e-3)
-    assert abs(f_set / obj[-1] - 1) < OBJ_RTOL
-    assert abs(obj[-1] / oo[-1] - 1) < OBJ_RTOL
+    red_set = np.trace(np.linalg.inv(1e-3 * np.eye(k) + Kss / float(k)))          # reduced objective of the GPU's set, float64
+    assert abs(red_set / red[-1] - 1) < OBJ_RTOL
+    cand_o = np.concatenate([[offs[s] + {int(v): i for i, v in enumerate(sel_inds[s])}[int(v)] for v in Qo[s]]
+                             for s in range(S)]).astype(int)
+    Kso = det['Kt'][np.ix_(cand_o, cand_o)]
+    assert abs(red[-1] / np.trace(np.linalg.inv(1e-3 * np.eye(k) + Kso / float(k))) - 1) < OBJ_RTOL
+    assert abs(obj[-1] - ((det['D'] - k) / 1e-3 + red[-1])) <= 1e-12 * obj[-1]
 
 
 def test_whole_image_fi_trace_score(nb):
