@@ -27,6 +27,10 @@ typedef struct nnal_ctx nnal_ctx;
 #define NNAL_ERR_STATE 3        /* call order violated (e.g. scoring before a pool pass) */
 #define NNAL_ERR_UNSUPPORTED 4  /* shape outside what the kernels cover */
 #define NNAL_ERR_NO_DEVICE 5    /* no CUDA device / not an sm_100 part: there is NO CPU fallback */
+#define NNAL_ERR_OVERFLOW 6     /* an input, weight or activation left the fp16 operand range of the tensor-core path
+                                   (|x| > 65504 or not finite): results of the pass are invalid.  Returned by the calls that
+                                   hand pool results to the caller; the reference's fp32 TF path has no such limit --
+                                   rescale the input or switch to the FP32 kernels with nnal_set_tensor_cores(ctx, 0). */
 
 /* layer kinds of NN.CNN's layer_dict (NN.py:98-108): [out,'conv',[kh,kw]] / [[p,p],'pool'] / [out,'fc'] */
 #define NNAL_LAYER_CONV 0
@@ -69,6 +73,11 @@ int nnal_set_tensor_cores(nnal_ctx* ctx, int enable);
 int nnal_synchronize(nnal_ctx* ctx);
 /* the context's CUDA stream (cudaStream_t) so host code can record CUDA events on it */
 void* nnal_stream(nnal_ctx* ctx);
+
+/* 64-bit content hash of a caller-owned HOST array (multi-threaded, ~50 GB/s): the host layer re-uploads a volume or a
+ * weight set exactly when its full content changed since the last query (the reference passes the same padded volumes
+ * every AL iteration, PW_AL.py:848-853, and fine-tunes the weights in between). */
+int nnal_host_hash(const void* data, uint64_t bytes, uint64_t* out);
 
 /* Per-kernel-class device timing (CUDA events on the context stream) for bench.py's roofline leg.
  * cls: layer index (0..n_layers-1), 100 gather, 101 scores, 102 top-k, 110-113 FI setup / Gram / greedy / Gram solve,
@@ -290,7 +299,11 @@ int nnal_cs_greedy(nnal_ctx* ctx, int64_t k, int64_t* sel_out, double* val_out);
 /* feature rows of the given pool positions as [n][d] float32 on the host (row-major) */
 int nnal_pool_feature_rows(nnal_ctx* ctx, const int64_t* pos, int64_t n, float* out);
 
-/* ---- test hook ---------------------------------------------------------------------------- */
+/* ---- test hooks --------------------------------------------------------------------------- */
+/* Declares a pool of n samples with the given float64 scores (no model, no pool pass): drives nnal_pool_topk /
+ * nnal_pool_topk_device with arbitrary scores in tests. */
+int nnal_debug_set_pool_scores(nnal_ctx* ctx, const double* scores, int64_t n);
+
 /* One FC layer out[M][N] = act(A[M][K] W[N][K]^T + b) on host buffers, on the tcgen05 GEMM
  * (use_tc=1) or the FP32 CUDA-core GEMM (use_tc=0); lets tests check the kernels in isolation. */
 int nnal_debug_fc(nnal_ctx* ctx, const float* A, const float* W, const float* b, int64_t M, int N, int K, int relu,

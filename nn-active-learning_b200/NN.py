@@ -70,12 +70,20 @@ class CNN(object):
         shapes = self.weight_shapes()
         for name, (ws, bs) in shapes.items():
             W, b = weights[name]
-            W = np.asarray(W, dtype=np.float32)
-            b = np.asarray(b, dtype=np.float32)
+            W = np.array(W, dtype=np.float32)          # private copies: later edits of the caller's arrays do not leak in
+            b = np.array(b, dtype=np.float32)
             if W.shape != ws or b.size != bs[0]:
                 raise ValueError('layer %s: expected W%s b%s, got W%s b%s' % (name, ws, bs, W.shape, b.shape))
-            self.var_dict[name] = [W, b.reshape(bs)]
+            W.setflags(write=False)
+            b = b.reshape(bs)
+            b.setflags(write=False)
+            self.var_dict[name] = [W, b]
         self._version += 1
+
+    def weights_token(self):
+        """Changes whenever the weights do (``set_weights`` is the only way in, and it stores read-only copies): lets the
+        engine skip re-hashing 145 MB of weights on every query."""
+        return self._version
 
     def get_weights(self, sess=None):
         if not self.var_dict:
@@ -139,7 +147,8 @@ class ReferenceModelAdapter(object):
         self._version = 0
 
     def refresh(self):
-        """Call after the reference fine-tunes the model so the next query re-uploads."""
+        """Kept for callers of the first release; no longer needed: the engine re-reads the variables on every query and
+        re-uploads whenever their content changed (``Engine.set_model``)."""
         self._version += 1
 
     def get_weights(self, sess=None):

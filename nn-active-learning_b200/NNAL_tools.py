@@ -41,8 +41,10 @@ def SDP_query_distribution(A, lambda_, X_pool, k, tol=1e-4, max_iter=200000):
     minimising ``tr((sum_i q_i A_i)^-1)`` over the simplex.  ``A`` is the list of tau x tau conditional FIs of
     ``gen_A_matrices``.  Returns a dict shaped like cvxopt's ``solvers.sdp`` solution: ``soln['x']`` =
     ``[q_1..q_n, t_1..t_tau]`` (callers slice ``soln['x'][:n]``, PW_NNAL.py:157), ``soln['status']`` = 'optimal' when
-    the duality certificate ``max_i tr(M^-1 A_i M^-1)/tr(M^-1) - 1`` of the returned q is below ``tol`` (so the
-    objective is within ``tol`` of the SDP optimum), else 'unknown'; plus 'primal objective', 'gap', 'iterations'.
+    the duality certificate ``max_i tr(M^-1 A_i M^-1)/tr(M^-1) - 1`` of the returned q is at most ``2 tol`` (the loop
+    stops once the certificate of the previous iterate is below ``tol``; the value reported in ``soln['gap']`` is
+    recomputed for the returned q and bounds the relative distance of the objective from the SDP optimum), else
+    'unknown'; plus 'primal objective', 'gap', 'iterations'.
     The regularised variant (``lambda_ > 0``: ``-lambda sum q_i |f_i|^2`` with ``F q = 0``, :625-644) is not
     part of the replaced path."""
     if lambda_ > 0:

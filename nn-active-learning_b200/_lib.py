@@ -25,6 +25,7 @@ SIGNATURES = {
     'nnal_set_tensor_cores': (C.c_int, [c_vp, C.c_int]),
     'nnal_synchronize': (C.c_int, [c_vp]),
     'nnal_stream': (c_vp, [c_vp]),
+    'nnal_host_hash': (C.c_int, [c_vp, C.c_uint64, C.POINTER(C.c_uint64)]),
     'nnal_profile': (C.c_int, [c_vp, C.c_int]),
     'nnal_profile_read': (C.c_int, [c_vp, C.c_int, c_f64p, C.POINTER(C.c_longlong)]),
     'nnal_model_layer_info': (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong),
@@ -56,6 +57,7 @@ SIGNATURES = {
     'nnal_topk_merge_pairs': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, c_vp, c_vp]),
     'nnal_entropy': (C.c_int, [c_vp, c_vp, C.c_int, C.c_int64, C.c_int, C.c_double, c_vp]),
     'nnal_topk': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, c_vp]),
+    'nnal_debug_set_pool_scores': (C.c_int, [c_vp, c_vp, C.c_int64]),
     'nnal_debug_fc': (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
     'nnal_debug_conv': (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, c_vp]),
@@ -99,7 +101,7 @@ SIGNATURES = {
                                        c_vp, c_vp, c_f64p, c_f64p, c_i64p]),
 }
 
-NNAL_OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, 1, 2, 3, 4, 5
+NNAL_OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_OVERFLOW = 0, 1, 2, 3, 4, 5, 6
 LAYER_CONV, LAYER_POOL, LAYER_FC = 0, 1, 2
 F32, F64 = 0, 1
 NORM_NONE, NORM_BATCH_EVAL, NORM_MULTIMG = 0, 1, 2
@@ -111,6 +113,10 @@ _lib = None
 
 class NnalError(RuntimeError):
     pass
+
+
+class NnalOverflowError(NnalError, OverflowError):
+    """An input, weight or activation left the fp16 operand range of the tensor-core path (NNAL_ERR_OVERFLOW)."""
 
 
 def load():

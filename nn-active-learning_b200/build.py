@@ -9,7 +9,7 @@ OUT = os.path.join(HERE, 'libnnal_b200.so')
 SOURCES = ['capi.cu', 'volume.cu', 'forward.cu', 'forward_simt.cu', 'score.cu', 'gemm_tc.cu', 'conv_tc.cu', 'conv_wt.cu', 'fi.cu', 'sims.cu', 'shrunk.cu', 'sdp.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-         '-Xcompiler', '-fPIC']
+         '-Xcompiler', '-fPIC', '-Xcompiler', '-pthread']
 
 
 def needs_build():
@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
         if verbose:
             print(out)
     cmd = [NVCC, '-shared', '-o', OUT] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart_static',
-                                                   '-Xcompiler', '-fPIC']
+                                                   '-Xcompiler', '-fPIC', '-Xcompiler', '-pthread', '-lpthread']
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         sys.stderr.write(r.stdout.decode())

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <algorithm>
+#include <thread>
 
 static const int NNAL_VERSION = 100;
 static const int64_t DEFAULT_CHUNK = 16384;   // samples per forward chunk (measured: 8192 -> 16384 = +1.5 %, flat beyond)
@@ -15,6 +16,86 @@ static int64_t chunk_size() {
 }
 
 extern "C" int nnal_version(void) { return NNAL_VERSION; }
+
+// ---- content hash of caller-owned HOST arrays (volumes, weights) -------------------------------------------------
+// The host layer skips an upload only when the FULL content of the arrays is unchanged (the reference passes the same
+// padded volumes on every query and fine-tunes the weights between queries; a sampled checksum or object identity would
+// miss in-place edits).  64-bit multiply-xor hash over 8-byte words, 4 MiB chunks hashed independently on up to 16
+// threads and combined in chunk order: the value does not depend on the thread count; ~50 GB/s on the box's host cores.
+static uint64_t hash_chunk(const unsigned char* p, size_t n, uint64_t seed) {
+  const uint64_t K = 0x9E3779B97F4A7C15ull;
+  uint64_t h0 = seed ^ K, h1 = seed + 0xC2B2AE3D27D4EB4Full, h2 = ~seed, h3 = seed * K + 1;
+  size_t i = 0;
+  for (; i + 32 <= n; i += 32) {
+    uint64_t w[4];
+    memcpy(w, p + i, 32);
+    h0 = (h0 ^ w[0]) * K; h1 = (h1 ^ w[1]) * K; h2 = (h2 ^ w[2]) * K; h3 = (h3 ^ w[3]) * K;
+  }
+  uint64_t t = 0;
+  for (int sh = 0; i < n; ++i, sh = (sh + 8) & 63) t ^= (uint64_t)p[i] << sh;
+  uint64_t h = (h0 ^ (h1 >> 29) ^ (h2 << 17) ^ (h3 >> 41) ^ t ^ (uint64_t)n) * K;
+  h ^= h >> 32;
+  return h * K;
+}
+
+extern "C" int nnal_host_hash(const void* data, uint64_t bytes, uint64_t* out) {
+  if (!out || (!data && bytes)) return NNAL_ERR_INVALID;
+  const size_t CH = (size_t)4 << 20;
+  const size_t nch = (size_t)((bytes + CH - 1) / CH);
+  std::vector<uint64_t> hs(nch ? nch : 1, 0);
+  const unsigned char* p = (const unsigned char*)data;
+  auto work = [&](size_t first, size_t step) {
+    for (size_t c = first; c < nch; c += step) hs[c] = hash_chunk(p + c * CH, (size_t)std::min<uint64_t>(CH, bytes - c * CH), c + 1);
+  };
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::max(1u, std::min(std::min(nt, 16u), (unsigned)std::max<size_t>(nch, 1)));
+  if (nt <= 1) work(0, 1);
+  else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, (size_t)t, (size_t)nt);
+    for (auto& t : th) t.join();
+  }
+  uint64_t h = 0x1234567ull ^ bytes;
+  for (size_t c = 0; c < nch; ++c) h = (h ^ hs[c]) * 0x9E3779B97F4A7C15ull + c;
+  *out = h;
+  return NNAL_OK;
+}
+
+// ---- fp16 range guard (see nnal_common.cuh) ------------------------------------------------------------------
+static std::vector<int (*)(unsigned int*)>& ovf_binders() {
+  static std::vector<int (*)(unsigned int*)> v;      // function-local: constructed before the first registrar runs
+  return v;
+}
+void nnal_ovf_register(int (*bind)(unsigned int*)) { ovf_binders().push_back(bind); }
+
+static int ovf_bind_device(nnal_ctx* ctx) {
+  static unsigned int* words[64] = {nullptr};        // one flag word per device, shared by its contexts, never freed
+  if (ctx->device < 0 || ctx->device >= 64) return NNAL_ERR_NO_DEVICE;
+  if (!words[ctx->device]) {
+    unsigned int* w = nullptr;
+    if (cudaMalloc(&w, 256) != cudaSuccess || cudaMemset(w, 0, 256) != cudaSuccess) return NNAL_ERR_CUDA;
+    for (auto bind : ovf_binders())
+      if (bind(w) != 0) return NNAL_ERR_CUDA;
+    words[ctx->device] = w;
+  }
+  ctx->ovf_word = words[ctx->device];
+  if (cudaMallocHost(&ctx->ovf_host, 64) != cudaSuccess) return NNAL_ERR_CUDA;
+  *ctx->ovf_host = 0;
+  return NNAL_OK;
+}
+
+int nnal_ovf_enqueue(nnal_ctx* ctx) {
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ovf_host, ctx->ovf_word, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return NNAL_OK;
+}
+int nnal_ovf_test(nnal_ctx* ctx) {
+  if (*ctx->ovf_host == 0) return NNAL_OK;
+  *ctx->ovf_host = 0;
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->ovf_word, 0, 4, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  NNAL_FAIL(ctx, NNAL_ERR_OVERFLOW, "an input, weight or activation left the fp16 operand range (|x| > 65504 or not finite): the "
+                                    "tensor-core path would saturate it; rescale the input or call nnal_set_tensor_cores(ctx, 0)");
+}
 
 extern "C" int nnal_ctx_create(int device, nnal_ctx** out) {
   if (!out) return NNAL_ERR_INVALID;
@@ -29,6 +110,7 @@ extern "C" int nnal_ctx_create(int device, nnal_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return NNAL_ERR_CUDA; }
+  if (ovf_bind_device(ctx) != NNAL_OK) { cudaStreamDestroy(ctx->stream); delete ctx; return NNAL_ERR_CUDA; }
   const char* f = getenv("NNAL_FORCE_SIMT");
   ctx->use_tc = (f && atoi(f)) ? 0 : 1;
   const char* fw = getenv("NNAL_CONV_WT");   // 0: conv_tc.cu only, 1: conv_wt.cu where faster, 2 (default): + pool fusion, 3: wherever supported
@@ -91,6 +173,7 @@ extern "C" int nnal_ctx_destroy(nnal_ctx* ctx) {
   free_buf(ctx->featbuf); free_buf(ctx->prevbuf); free_buf(ctx->logits); free_buf(ctx->splitA[0]); free_buf(ctx->splitA[1]);
   free_buf(ctx->topk_ws); free_buf(ctx->fi_ws);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->ovf_host) cudaFreeHost(ctx->ovf_host);
   delete ctx;
   return NNAL_OK;
 }
@@ -482,7 +565,7 @@ extern "C" int nnal_pool_mc_read(nnal_ctx* ctx, double* av_post, double* av_ent)
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (av_post) CUDA_TRY(ctx, cudaMemcpyAsync(av_post, ctx->pool_mc_post, (size_t)ctx->pool_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (av_ent) CUDA_TRY(ctx, cudaMemcpyAsync(av_ent, ctx->pool_mc_ent, (size_t)ctx->pool_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  NNAL_SYNC_CHECKED(ctx);
   return NNAL_OK;
 }
 
@@ -575,7 +658,7 @@ extern "C" int nnal_pool_posteriors(nnal_ctx* ctx, float* out) {
   if (!ctx->pool_post) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no pool pass");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->pool_post, (size_t)ctx->pool_n * ctx->n_class * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  NNAL_SYNC_CHECKED(ctx);
   return NNAL_OK;
 }
 
@@ -607,7 +690,7 @@ extern "C" int nnal_pool_features(nnal_ctx* ctx, int64_t start, int64_t n, float
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->act[0].p, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  NNAL_SYNC_CHECKED(ctx);
   return NNAL_OK;
 }
 
@@ -636,7 +719,7 @@ extern "C" int nnal_pool_feature_rows(nnal_ctx* ctx, const int64_t* pos, int64_t
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->act[0].p, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  NNAL_SYNC_CHECKED(ctx);
   return NNAL_OK;
 }
 
@@ -669,7 +752,7 @@ extern "C" int nnal_pool_scores_read(nnal_ctx* ctx, double* out) {
   if (!ctx->pool_score) NNAL_FAIL(ctx, NNAL_ERR_STATE, "no pool pass");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->pool_score, (size_t)ctx->pool_n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  NNAL_SYNC_CHECKED(ctx);
   return NNAL_OK;
 }
 
@@ -684,7 +767,7 @@ static int topk_to_host(nnal_ctx* ctx, const double* d_score, int64_t n, int64_t
   prof_end(ctx);
   CUDA_TRY(ctx, cudaMemcpyAsync(idx_out, d_idx, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (score_out) CUDA_TRY(ctx, cudaMemcpyAsync(score_out, d_sc, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  NNAL_SYNC_CHECKED(ctx);
   return NNAL_OK;
 }
 
@@ -760,7 +843,7 @@ extern "C" int nnal_topk_merge_pairs(nnal_ctx* ctx, const void* d_pairs, int64_t
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaMemcpyAsync(pos_out, d_pos, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (score_out) CUDA_TRY(ctx, cudaMemcpyAsync(score_out, d_sc, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  NNAL_SYNC_CHECKED(ctx);
   return NNAL_OK;
 }
 
@@ -790,6 +873,22 @@ extern "C" int nnal_topk(nnal_ctx* ctx, const double* scores, int64_t n, int64_t
   NNAL_TRY(devbuf_reserve(ctx, ctx->act[1], (size_t)n * 8));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->act[1].p, scores, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   return topk_to_host(ctx, (const double*)ctx->act[1].p, n, k, idx_out, nullptr);
+}
+
+// test hook: declare a pool of n samples whose SCORES are given (no model, no pool pass) -- lets tests drive the top-k /
+// merge kernels with arbitrary scores (exact ties, ragged ranks)
+extern "C" int nnal_debug_set_pool_scores(nnal_ctx* ctx, const double* scores, int64_t n) {
+  if (!ctx || n < 0 || (n > 0 && !scores)) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->pool_cap_score < (size_t)std::max<int64_t>(n, 1)) {
+    if (ctx->pool_score) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CUDA_TRY(ctx, cudaFree(ctx->pool_score)); ctx->pool_score = nullptr; }
+    CUDA_TRY(ctx, cudaMalloc(&ctx->pool_score, (size_t)std::max<int64_t>(n, 1) * sizeof(double)));
+    ctx->pool_cap_score = (size_t)std::max<int64_t>(n, 1);
+  }
+  if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pool_score, scores, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->pool_n = n;
+  return NNAL_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -831,6 +930,7 @@ extern "C" int nnal_debug_fc(nnal_ctx* ctx, const float* A, const float* W, cons
       ctx->err = std::string("debug_fc: ") + cudaGetErrorString(cudaGetLastError()); rc = NNAL_ERR_CUDA;
     }
   }
+  if (rc == NNAL_OK && nnal_ovf_enqueue(ctx) == NNAL_OK && cudaStreamSynchronize(ctx->stream) == cudaSuccess) rc = nnal_ovf_test(ctx);
   cleanup();
   return rc;
 }
@@ -905,6 +1005,7 @@ extern "C" int nnal_debug_conv(nnal_ctx* ctx, const float* x, const float* W, co
       ctx->err = std::string("debug_conv: ") + cudaGetErrorString(cudaGetLastError()); rc = NNAL_ERR_CUDA;
     }
   }
+  if (rc == NNAL_OK && nnal_ovf_enqueue(ctx) == NNAL_OK && cudaStreamSynchronize(ctx->stream) == cudaSuccess) rc = nnal_ovf_test(ctx);
   cleanup();
   return rc;
 }

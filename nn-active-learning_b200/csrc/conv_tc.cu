@@ -449,6 +449,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
               for (int j = 0; j < 16; ++j) {
                 if (c0 + j < C::COUT_REAL) {
                   const float r = v[j] * p.w_scale_inv + bb[j];
+                  nnal_ovf_note(r);
                   atomicMax(pc + j, __float_as_uint(r > 0.f ? fminf(r, 65504.f) : 0.f));
                 }
               }
@@ -456,8 +457,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
               uint32_t hi[8], lo[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float x0 = fminf(fmaxf(v[2 * j] * p.w_scale_inv + bb[2 * j], 0.f), 65504.f);
-                const float x1 = fminf(fmaxf(v[2 * j + 1] * p.w_scale_inv + bb[2 * j + 1], 0.f), 65504.f);
+                const float r0 = v[2 * j] * p.w_scale_inv + bb[2 * j], r1 = v[2 * j + 1] * p.w_scale_inv + bb[2 * j + 1];
+                nnal_ovf_note(fmaxf(r0, r1));                                // (fmaxf drops a NaN operand: checked apart)
+                if (r0 != r0 || r1 != r1) nnal_ovf_note(r0 + r1);
+                const float x0 = fminf(fmaxf(r0, 0.f), 65504.f);
+                const float x1 = fminf(fmaxf(r1, 0.f), 65504.f);
                 const __half2 h = __floats2half2_rn(x0, x1);              // .x (low half) = x0
                 const float2 hf = __half22float2(h);
                 const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);

@@ -342,6 +342,7 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmHiL, const __grid_constant_
                 for (int h = 0; h < NCH; ++h) {
                   if (off < chlim[h] && !(p.flags & 1)) {                 // -1 (padding / garbage column) fails too
                     const float rr = z[h][2 * i + k] * p.w_scale_inv + bias[h];
+                    nnal_ovf_note(rr);
                     const float o = rr > 0.f ? fminf(rr, 65504.f) : 0.f;
                     atomicMax(pooled + off + co[h], __float_as_uint(o));  // o >= +0: uint order == float order
                   }
@@ -358,6 +359,7 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmHiL, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float rr = z[h][j] * p.w_scale_inv + bias[h];
+                nnal_ovf_note(rr);
                 const float o = rr > 0.f ? fminf(rr, 65504.f) : 0.f;
                 const nnal_h hh = __float2half_rn(o);
                 P[j] = nnal_pack2(hh, __float2half_rn(o - __half2float(hh)));

@@ -907,7 +907,7 @@ extern "C" int nnal_fi_set_candidates(nnal_ctx* ctx, const int64_t* cand, int64_
   int rc = fi::run_setup(ctx, s, ctx->pool_post + ctx->pool_n, nullptr);
   prof_end(ctx);
   NNAL_TRY(rc);
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // `cand` is caller-owned host memory
+  NNAL_SYNC_CHECKED(ctx);                                 // `cand` is caller-owned host memory; fp16 range flag of the pool pass
   return NNAL_OK;
 }
 
@@ -1202,7 +1202,7 @@ static int gram_finish(nnal_ctx* ctx, State* s, float* H_out) {
   if (H_out)
     CUDA_TRY(ctx, cudaMemcpy2DAsync(H_out, (size_t)s->Hd * 4, s->H, (size_t)s->Hld * 4, (size_t)s->Hd * 4, s->Hd, cudaMemcpyDeviceToHost,
                                     ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  NNAL_SYNC_CHECKED(ctx);
   return NNAL_OK;
 }
 

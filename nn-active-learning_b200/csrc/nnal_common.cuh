@@ -15,6 +15,7 @@
 #define NNAL_ERR_STATE 3
 #define NNAL_ERR_UNSUPPORTED 4
 #define NNAL_ERR_NO_DEVICE 5
+#define NNAL_ERR_OVERFLOW 6
 
 enum { NNAL_LAYER_CONV = 0, NNAL_LAYER_POOL = 1, NNAL_LAYER_FC = 2 };
 enum { NNAL_F32 = 0, NNAL_F64 = 1 };
@@ -25,8 +26,29 @@ enum { NNAL_F32 = 0, NNAL_F64 = 1 };
 // tolerance at 1e5-sample pools; fp16 terms have the same MMA rate.)  Weights are pre-scaled by a
 // power of two so that their lo terms stay in fp16's normal range; epilogues undo the scale.
 typedef __half nnal_h;
+// fp16 range guard.  Operands are clamped to +-65504 before the hi/lo split; a value that hits the clamp (or is not
+// finite) sets a device flag, and every entry point that hands results to the caller returns NNAL_ERR_OVERFLOW when the
+// flag is up -- a model or input outside fp16's range fails loudly instead of returning saturated posteriors.  The flag
+// word is one per device (capi.cu); every translation unit holds a pointer to it in a static __device__ variable that is
+// bound when a context is created (nnal_ovf_register collects the per-unit binders at load time).
+void nnal_ovf_register(int (*bind)(unsigned int*));
 #ifdef __CUDACC__
+static __device__ unsigned int* nnal_ovf_ptr;
+__device__ __forceinline__ void nnal_ovf_note(float x) {
+  if (!(fabsf(x) <= 65504.f)) {
+    unsigned int* p = nnal_ovf_ptr;
+    if (p) atomicOr(p, 1u);
+  }
+}
+static int nnal_ovf_bind_tu(unsigned int* word) {
+  return cudaMemcpyToSymbol(nnal_ovf_ptr, &word, sizeof(word)) == cudaSuccess ? 0 : 1;
+}
+namespace {
+struct NnalOvfRegistrar { NnalOvfRegistrar() { nnal_ovf_register(&nnal_ovf_bind_tu); } };
+static NnalOvfRegistrar nnal_ovf_registrar_instance;
+}
 __device__ __forceinline__ void nnal_split(float x, nnal_h& h, nnal_h& l) {
+  nnal_ovf_note(x);
   x = fminf(fmaxf(x, -65504.f), 65504.f);
   h = __float2half_rn(x);
   l = __float2half_rn(x - __half2float(h));
@@ -126,6 +148,8 @@ struct nnal_ctx {
   double* pool_mc_ent = nullptr;         // [pool_n] running mean of the per-pass binary entropies (PW_NNAL.py:262-268)
   size_t pool_cap_mc = 0;
   DevBuf act_mc;                         // third activation buffer: the conv trunk's output must survive the T tail passes
+  unsigned int* ovf_word = nullptr;      // device flag set by nnal_ovf_note (shared by the contexts of one device)
+  unsigned int* ovf_host = nullptr;      // pinned host copy read by nnal_ovf_test
 };
 
 #define CUDA_TRY(ctx, expr)                                                            \
@@ -174,6 +198,16 @@ static inline void prof_end(nnal_ctx* ctx) {
 #define NNAL_PROF_BW_BACKWARD 121
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// fp16 range guard: enqueue the flag read on the stream (before a synchronisation the caller does anyway), then test it
+int nnal_ovf_enqueue(nnal_ctx* ctx);
+int nnal_ovf_test(nnal_ctx* ctx);
+#define NNAL_SYNC_CHECKED(ctx)                                                         \
+  do {                                                                                 \
+    NNAL_TRY(nnal_ovf_enqueue(ctx));                                                   \
+    CUDA_TRY(ctx, cudaStreamSynchronize((ctx)->stream));                               \
+    NNAL_TRY(nnal_ovf_test(ctx));                                                      \
+  } while (0)
 
 // ---- kernels launchers (defined in the individual .cu files) -------------------------
 // volume.cu

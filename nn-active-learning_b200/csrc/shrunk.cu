@@ -746,7 +746,7 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
       CUDA_TRY(ctx, cudaMemcpyAsync(post_out + (size_t)y * n_total + o, (const float*)st->post.p + (size_t)y * nb,
                                     (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   }
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));     // the workspaces are reused by the next chunk
+  NNAL_SYNC_CHECKED(ctx);                                // the workspaces are reused by the next chunk
   return NNAL_OK;
 }
 

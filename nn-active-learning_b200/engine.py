@@ -28,8 +28,8 @@ class Engine(object):
         self.device = device
         self._model_key = None
         self._model_ref = None
+        self._model_token = None
         self._vol_keys = {}
-        self._vol_refs = {}
         self._m = {}
         self.volume_cache = os.environ.get('NNAL_VOLUME_CACHE', '1') != '0'
         self.h2d_bytes = 0
@@ -42,6 +42,8 @@ class Engine(object):
             msg = msg.decode() if msg else ''
             if rc == L.ERR_INVALID:
                 raise ValueError(msg or 'invalid argument')
+            if rc == L.ERR_OVERFLOW:
+                raise L.NnalOverflowError(msg)
             raise L.NnalError('libnnal_b200 error %d: %s' % (rc, msg))
 
     def close(self):
@@ -87,6 +89,11 @@ class Engine(object):
                                                       int(offset), d1, d2, d3,
                                                       None if st is None else _ptr(st), int(norm_mode)))
 
+    def _load_scores_for_test(self, scores):
+        s = np.ascontiguousarray(scores, dtype=np.float64).ravel()
+        self._chk(self.lib.nnal_debug_set_pool_scores(self.h, _ptr(s) if s.size else None, s.size))
+        self._pool_n = s.size
+
     def debug_fc(self, A, W, b, relu, use_tc):
         A = np.ascontiguousarray(A, dtype=np.float32)
         W = np.ascontiguousarray(W, dtype=np.float32)
@@ -115,15 +122,27 @@ class Engine(object):
     # ------------------------------------------------------------------
     # model
     # ------------------------------------------------------------------
+    def host_hash(self, a):
+        """64-bit content hash of a C-contiguous host array (multi-threaded in the library)."""
+        a = np.ascontiguousarray(a)
+        out = C.c_uint64()
+        self._chk(self.lib.nnal_host_hash(_ptr(a), a.nbytes, C.byref(out)))
+        return out.value
+
     def set_model(self, model, sess=None):
         """Uploads ``model`` (an ``nnal_b200.NN.CNN``, or any object exposing ``layer_dict``,
         ``input_shape``, ``feature_layer_index`` and ``get_weights(sess)``) unless the same
-        weights are already resident."""
-        # the resident weights are reused only for the very same model OBJECT (a reference is kept, so its
-        # id cannot be recycled by a new object) at an unchanged weight version
-        key = getattr(model, '_version', 0)
-        if self._model_ref is model and key == self._model_key:
+        weights are already resident.
+
+        The weights are read from the model on EVERY call (``var.eval()`` for a live reference model, NN.py:391-394)
+        and re-uploaded when the content hash of any array, the layer list or the input shape changed: a model that
+        the reference fine-tuned between two queries is picked up without any ``refresh()`` call."""
+        # fast path for models that own PRIVATE copies of their weights and version them (nnal_b200.NN.CNN: set_weights is
+        # the only way in and it copies): same object, same version -> nothing to do.  Everything else is re-read.
+        token = model.weights_token() if hasattr(model, 'weights_token') else None
+        if token is not None and self._model_ref is model and token == self._model_token:
             return
+        weights = model.get_weights(sess)
         layers = list(model.layer_dict.items()) if isinstance(model.layer_dict, dict) else list(model.layer_dict)
         specs = (L.LayerSpec * len(layers))()
         for i, (name, spec) in enumerate(layers):
@@ -137,21 +156,25 @@ class Engine(object):
                 raise ValueError("Layer's type should be either 'fc', 'conv' or 'pool'.")
         H, W, Cc = model.input_shape
         fl = model.feature_layer_index if model.feature_layer_index is not None else -1
-        self._chk(self.lib.nnal_model_set(self.h, specs, len(layers), int(H), int(W), int(Cc), int(fl)))
-        weights = model.get_weights(sess)
+        arrs = []
         for i, (name, spec) in enumerate(layers):
             if spec[1] == 'pool':
                 continue
             Wt, b = weights[name]
-            Wt = np.ascontiguousarray(Wt, dtype=np.float32)
-            b = np.ascontiguousarray(np.ravel(b), dtype=np.float32)
+            arrs.append((i, np.ascontiguousarray(Wt, dtype=np.float32), np.ascontiguousarray(np.ravel(b), dtype=np.float32)))
+        key = (tuple((n, str(sp)) for n, sp in layers), (int(H), int(W), int(Cc)), int(fl),
+               tuple((a.shape, self.host_hash(a), self.host_hash(b)) for _, a, b in arrs))
+        self._model_ref, self._model_token = (model, token) if token is not None else (None, None)
+        if key == self._model_key:
+            return
+        self._chk(self.lib.nnal_model_set(self.h, specs, len(layers), int(H), int(W), int(Cc), int(fl)))
+        for i, Wt, b in arrs:
             self.h2d_bytes += Wt.nbytes + b.nbytes
             self._chk(self.lib.nnal_model_set_weights(self.h, i, _ptr(Wt), _ptr(b)))
         nc, fd, pd = C.c_int(), C.c_int(), C.c_int()
         self._chk(self.lib.nnal_model_info(self.h, C.byref(nc), C.byref(fd), C.byref(pd)))
         self.n_class, self.feat_dim, self.prev_dim = nc.value, fd.value, pd.value
         self._model_key = key
-        self._model_ref = model
 
     # ------------------------------------------------------------------
     # volumes
@@ -172,15 +195,14 @@ class Engine(object):
             raise ValueError('all modalities must be 3-D arrays of one shape')
         if any(a.dtype != arrs[0].dtype for a in arrs):
             arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
-        # Cache: the reference passes the same (never modified) padded arrays on every query.  A
-        # subject is skipped only if the very same array OBJECTS (kept alive here, so their memory
-        # cannot be recycled) with an unchanged sampled checksum are passed again.
-        key = tuple((a.shape, a.dtype.str, float(a.ravel()[::max(1, a.size // 4096)].sum(dtype=np.float64)))
-                    for a in arrs) + (tuple(pads),)
-        cached = self._vol_refs.get(subject)
-        if (self.volume_cache and cached is not None and self._vol_keys.get(subject) == key and
-                len(cached) == len(imgs) and all(x is y for x, y in zip(cached, imgs))):
-            return
+        # Cache: the reference passes the same padded arrays on every query (PW_AL.py:848-853).  A subject is skipped
+        # only if the FULL content of every modality is unchanged (64-bit hash over all bytes, nnal_host_hash): an
+        # in-place edit anywhere in a volume triggers a re-upload.
+        key = None
+        if self.volume_cache:
+            key = tuple((a.shape, a.dtype.str, self.host_hash(a)) for a in arrs) + (tuple(int(p) for p in pads),)
+            if self._vol_keys.get(subject) == key:
+                return
         ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         X, Y, Z = arrs[0].shape
         dt = L.F64 if arrs[0].dtype == np.float64 else L.F32
@@ -188,11 +210,9 @@ class Engine(object):
         self._chk(self.lib.nnal_volume_set(self.h, int(subject), len(arrs), ptrs, dt, X, Y, Z,
                                            int(pads[0]), int(pads[1]), int(pads[2])))
         self._vol_keys[subject] = key
-        self._vol_refs[subject] = list(imgs)
 
     def invalidate_volumes(self):
         self._vol_keys = {}
-        self._vol_refs = {}
 
     # ------------------------------------------------------------------
     # gather

@@ -342,8 +342,10 @@ def query_multimg_sdp(expr, model, sess, all_padded_imgs, pool_inds, return_solu
         eng.upload(i, imgs)
         stats = np.array([[expr.train_stats[i, 2 * j], expr.train_stats[i, 2 * j + 1]] for j in range(m)],
                          dtype=np.float64)
+        # the gradient patches come from get_patches_multimg upstream (PW_NNAL.py:553-559): EVERY channel of modality
+        # block ch/d3 is normalised (patch_utils.py:1203-1207), unlike batch_eval's channels 0..m-1 of the posterior pass
         post, g = eng.fi_shrunk_voxels(i, np.asarray(pool_inds[i])[local], expr.pars['patch_shape'], stats,
-                                       L.NORM_BATCH_EVAL, shape=imgs[0].shape)
+                                       L.NORM_MULTIMG, shape=imgs[0].shape)
         posts.append(post)
         gs.append(g)
     tau = eng.fi_shrunk_tau()

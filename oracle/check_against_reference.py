@@ -420,6 +420,37 @@ def main():
     for s_ in range(S_q):
         gold['q_fi_sdp_multi%d' % s_] = np.asarray(rQ_fi[s_], dtype=np.int64)
     gold['q_fi_u_multi'] = u78
+    # the same branch with d3 = 3 (patch 5x5x3, m = 2 -> 6 channels): the posterior pass normalises channels 0..m-1 only
+    # (PW_NN.batch_eval, PW_NN.py:503-506) while the gradient patches come from get_patches_multimg, which normalises whole
+    # modality blocks ch/d3 (patch_utils.py:1203-1207) -- the two differ as soon as d3 > 1
+    ps_3 = (5, 5, 3)
+    w_3 = O.he_init_weights(layers_q, (5, 5, m_q * 3), 8, bias_scale=0.1)
+    # (channels m..m*d3-1 reach the posterior pass unnormalised, ~100: shrink conv1 so that the posteriors do not saturate
+    # into exact ties, which np.argsort's unstable sort and the oracle's stable one would break differently)
+    w_3['conv1'] = (w_3['conv1'][0] * np.float32(0.01), w_3['conv1'][1])
+    allp_3 = [[np.pad(im, ((0, 0), (0, 0), (1, 1)), 'constant') for im in sub[:m_q]] + [sub[m_q]] for sub in allp_q]
+
+    class Q3Sess(object):
+        def run(self, var, feed_dict=None):
+            x = np.asarray(feed_dict['x']).astype(np.float32)
+            if isinstance(var, list):
+                return O.explicit_class_gradients(layers_q, w_3, x, var[0][0])
+            return O.forward(layers_q, w_3, x, feature_layer=fl_q)[var.name]
+
+    class M3Expr(QExpr):
+        pars = dict(QExpr.pars, k=11, B=40, SDP_solver='CVXOPT', patch_shape=ps_3)
+    np.random.seed(79)
+    u79 = np.random.sample(11)
+    np.random.seed(79)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rQ_3 = ref_pw.query_multimg(M3Expr(), FiModel(), Q3Sess(), allp_3, pools_q, None, 'fi')
+    oQ_3, _ = O.query_fi_sdp_multimg(layers_q, w_3, allp_3, pools_q, ps_3, 16, st_q, 11, 40, u79)
+    for a, b in zip(rQ_3, oQ_3):
+        assert np.array_equal(np.asarray(a), np.asarray(b)), (rQ_3, oQ_3)
+    for s_ in range(S_q):
+        gold['q_fi_sdp_multi_d3_%d' % s_] = np.asarray(rQ_3[s_], dtype=np.int64)
+    gold['q_fi_u_d3'] = u79
+    print("PW_NNAL.query_multimg 'fi' with d3 = 3 (block-wise normalisation of the gradient patches): oracle == reference")
     # representativeness queries of query_multimg: 'rep-entropy' (:284-351) and 'core-set' (:353-451)
     class RExpr(QExpr):
         pars = dict(QExpr.pars, k=11, B=30)

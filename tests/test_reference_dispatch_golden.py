@@ -23,6 +23,17 @@ def _case(golden):
     return w, allp, pools, st, stats0
 
 
+def _case_d3(golden):
+    """The d3 = 3 twin of the case: same volumes padded by one more slice in z, a 6-channel input model whose first conv is
+    shrunk so that the unnormalised channels do not saturate the posteriors (oracle/check_against_reference.py)."""
+    w3 = O.he_init_weights(LAYERS, (5, 5, M * 3), 8, bias_scale=0.1)
+    w3['conv1'] = (w3['conv1'][0] * np.float32(0.01), w3['conv1'][1])
+    imgs = golden['q_imgs']
+    allp3 = [[np.pad(imgs[s][j], ((0, 0), (0, 0), (1, 1)), 'constant') for j in range(M)] + [np.zeros((12, 11, 4), dtype=np.int8)]
+             for s in range(S)]
+    return w3, allp3
+
+
 def test_oracle_reproduces_reference_dispatch(golden):
     w, allp, pools, st, stats0 = _case(golden)
     pool0 = np.array(pools[0])
@@ -40,6 +51,11 @@ def test_oracle_reproduces_reference_dispatch(golden):
     Qf, _ = O.query_fi_sdp_multimg(LAYERS, w, allp, pools, PS, 16, st, 11, 40, golden['q_fi_u_multi'])
     for s in range(S):
         assert np.array_equal(np.asarray(Qf[s], dtype=np.int64), golden['q_fi_sdp_multi%d' % s])
+    # d3 = 3: posterior pass normalised on channels 0..m-1, gradient patches block-wise (get_patches_multimg)
+    w3, allp3 = _case_d3(golden)
+    Q3, _ = O.query_fi_sdp_multimg(LAYERS, w3, allp3, pools, (5, 5, 3), 16, st, 11, 40, golden['q_fi_u_d3'])
+    for s in range(S):
+        assert np.array_equal(np.asarray(Q3[s], dtype=np.int64), golden['q_fi_sdp_multi_d3_%d' % s])
     # representativeness queries (pools without an empty subject: upstream raises on one in these branches)
     pools_r = [list(golden['q_pool_r%d' % s]) for s in range(S)]
     labeled = [list(golden['q_labeled%d' % s]) for s in range(S)]
@@ -144,3 +160,38 @@ def test_device_matches_reference_dispatch(golden):
     # reference's sample; the bulk must coincide
     got, want = set(np.asarray(qf).tolist()), set(golden['q_fi_sdp_single'].tolist())
     assert got <= set(sel.tolist()) and len(got & want) >= len(want) - 3, (sorted(got), sorted(want))
+
+
+@pytest.mark.gpu
+def test_device_multimg_sdp_d3_block_normalisation(golden):
+    """query_multimg 'fi' (literal pipeline) with a 5x5x3 patch: the device gathers the gradient patches with the
+    block-wise normalisation of get_patches_multimg (every channel of modality block ch/d3), the posterior pass with
+    batch_eval's channels 0..m-1 -- the A-matrices and the SDP objective of the reference's run follow."""
+    from collections import OrderedDict
+    import nnal_b200
+
+    class Expr(object):
+        pass
+    _, _, pools, st, _ = _case(golden)
+    w3, allp3 = _case_d3(golden)
+    model = nnal_b200.NN.CNN((5, 5, M * 3), OrderedDict(LAYERS), feature_layer=len(LAYERS) - 2)
+    model.set_weights(w3)
+    expr = Expr()
+    expr.pars = dict(k=11, B=40, lambda_=0., patch_shape=(5, 5, 3), ntb=16, SDP_solver='CVXOPT', fi_mode='sdp')
+    expr.train_stats, expr.nclass = st, 2
+    np.random.seed(79)
+    Q, soln, G = nnal_b200.fi.query_multimg_sdp(expr, model, None, allp3, pools, return_solution=True)
+    _, det = O.query_fi_sdp_multimg(LAYERS, w3, allp3, pools, (5, 5, 3), 16, st, 11, 40, golden['q_fi_u_d3'])
+    assert soln['status'] == 'optimal'
+    assert abs(soln['primal objective'] / det['phi'] - 1) < 1e-3
+    # the reference's sampler replayed on the device's q with the golden run's draws: the bulk of the sample coincides
+    sizes = [len(x) for x in det['sel_inds']]
+    q_dev = np.array(soln['x'][:sum(sizes)])
+    draws = O.sample_query_dstr(q_dev.copy(), 11, golden['q_fi_u_d3'])
+    local = O.global2local_inds(draws, sizes)
+    got = set()
+    want = set()
+    for s in range(S):
+        got |= set((s, int(v)) for v in np.asarray(det['sel_inds'][s])[local[s]])
+        want |= set((s, int(v)) for v in golden['q_fi_sdp_multi_d3_%d' % s])
+    assert len(got & want) >= len(want) - 2, (sorted(got), sorted(want))
