@@ -74,6 +74,8 @@ int nnal_synchronize(nnal_ctx* ctx);
 /* the context's CUDA stream (cudaStream_t) so host code can record CUDA events on it */
 void* nnal_stream(nnal_ctx* ctx);
 
+/* free / total bytes of the context's device (cudaMemGetInfo): the host layer sizes what it keeps resident with it */
+int nnal_device_memory(nnal_ctx* ctx, uint64_t* free_bytes, uint64_t* total_bytes);
 /* 64-bit content hash of a caller-owned HOST array (multi-threaded, ~50 GB/s): the host layer re-uploads a volume or a
  * weight set exactly when its full content changed since the last query (the reference passes the same padded volumes
  * every AL iteration, PW_AL.py:848-853, and fine-tunes the weights in between). */
@@ -97,7 +99,8 @@ int nnal_model_set(nnal_ctx* ctx, const nnal_layer_spec* specs, int n_layers, in
  * reference's flatten order in = c*(W*H)+w*H+h (NN.py:296-301), b[out]. */
 int nnal_model_set_weights(nnal_ctx* ctx, int layer, const float* W, const float* b);
 int nnal_model_info(nnal_ctx* ctx, int* n_class, int* feat_dim, int* prev_dim);
-/* multiply-accumulates per sample of layer `layer` and whether it runs on the tensor-core path */
+/* multiply-accumulates per sample of layer `layer` and the kernel family it runs on: 0 FP32 CUDA cores, 1 tcgen05
+ * (conv_tc_kernel / fc_tc_kernel), 2 tcgen05 weight-stationary conv (conv_wt_kernel) */
 int nnal_model_layer_info(nnal_ctx* ctx, int layer, int* type, long long* macs_per_sample, int* uses_tc);
 
 /* ---- volumes: the padded multi-modality images the query functions receive ----------------- */
@@ -106,6 +109,11 @@ int nnal_model_layer_info(nnal_ctx* ctx, int layer, int* type, long long* macs_p
  * padding on the device (get_patches(..., padded=False), patch_utils.py:1118-1132). */
 int nnal_volume_set(nnal_ctx* ctx, int subject, int m, const void* const* mods, int dtype, int64_t X, int64_t Y,
                     int64_t Z, int64_t pad_x, int64_t pad_y, int64_t pad_z);
+/* Same, from DEVICE memory: d_stage = the m modality arrays back to back, each C-contiguous (X,Y,Z).  Multi-GPU host
+ * layer: every rank copies 1/world of each volume host->device and the parts are all-gathered over NVLink (NCCL on
+ * nnal_stream()), so a volume crosses PCIe once per box instead of once per GPU. */
+int nnal_volume_set_device(nnal_ctx* ctx, int subject, int m, const void* d_stage, int dtype, int64_t X, int64_t Y,
+                           int64_t Z, int64_t pad_x, int64_t pad_y, int64_t pad_z);
 int nnal_volume_clear(nnal_ctx* ctx);
 
 /* ---- patch gather: replaces patch_utils.get_patches (patch_utils.py:1087-1173) --------------- */

@@ -90,13 +90,15 @@ class CNN(object):
             raise RuntimeError('model has no weights: call set_weights / load_weights first')
         return {k: (v[0], v[1]) for k, v in self.var_dict.items()}
 
-    def initialize(self, seed=None):
-        """He-normal weights, zero biases (NN.py:1430-1470)."""
+    def initialize(self, seed=None, bias_scale=0.):
+        """He-normal weights ``N(0, 2/fan_in)``, zero biases (NN.py:1430-1470); ``bias_scale`` > 0 draws ``N(0, bias_scale^2)``
+        biases instead (synthetic workloads that exercise the bias path)."""
         rs = np.random.RandomState(seed)
         w = {}
         for name, (ws, bs) in self.weight_shapes().items():
             fan_in = ws[0] * ws[1] * ws[2] if len(ws) > 2 else ws[1]
-            w[name] = ((rs.randn(*ws) * np.sqrt(2. / fan_in)).astype(np.float32), np.zeros(bs, np.float32))
+            W = (rs.randn(*ws) * np.sqrt(2. / fan_in)).astype(np.float32)
+            w[name] = (W, (rs.randn(*bs) * bias_scale).astype(np.float32))
         self.set_weights(w)
 
     def save_weights(self, file_path):

@@ -19,7 +19,7 @@ def _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=0, mc=Non
     eng = get_engine()
     eng.set_model(model, sess)
     imgs = list(padded_imgs)
-    eng.upload(0, imgs)
+    eng.upload(0, imgs, shared=True)             # every rank is handed the same volume: PCIe carries 1/world of it per rank
     pool_inds = np.asarray(pool_inds)
     n = len(pool_inds)
     rank, world = dist.rank_world()
@@ -77,6 +77,12 @@ def CNN_query(expr, model, sess, padded_imgs, pool_inds, tr_inds, method_name):
         if expr.pars.get('fi_mode', 'greedy') == 'sdp':
             return fi.query_single_sdp(expr, model, sess, padded_imgs, pool_inds)
         return fi.query_single(expr, model, sess, padded_imgs, pool_inds)
+
+    if method_name == 'entropy+fi':
+        # not a reference method name: ONE pool pass answering both queries (a query round as SURVEY.md 8d defines it);
+        # returns (q_entropy, q_fi), each exactly what the single-method call returns
+        from . import fi
+        return fi.query_single(expr, model, sess, padded_imgs, pool_inds, also_entropy=True)
 
     raise NotImplementedError('query method %r is not part of the replaced path' % method_name)
 
@@ -241,6 +247,10 @@ def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, labeled_inds, m
         if expr.pars.get('fi_mode', 'greedy') == 'sdp':
             return fi.query_multimg_sdp(expr, model, sess, all_padded_imgs, pool_inds)
         return fi.query_multimg(expr, model, sess, all_padded_imgs, pool_inds)
+
+    if method_name == 'entropy+fi':
+        from . import fi
+        return fi.query_multimg(expr, model, sess, all_padded_imgs, pool_inds, also_entropy=True)
 
     if method_name == 'rep-entropy':
         from . import rep

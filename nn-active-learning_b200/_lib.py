@@ -25,6 +25,7 @@ SIGNATURES = {
     'nnal_set_tensor_cores': (C.c_int, [c_vp, C.c_int]),
     'nnal_synchronize': (C.c_int, [c_vp]),
     'nnal_stream': (c_vp, [c_vp]),
+    'nnal_device_memory': (C.c_int, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     'nnal_host_hash': (C.c_int, [c_vp, C.c_uint64, C.POINTER(C.c_uint64)]),
     'nnal_profile': (C.c_int, [c_vp, C.c_int]),
     'nnal_profile_read': (C.c_int, [c_vp, C.c_int, c_f64p, C.POINTER(C.c_longlong)]),
@@ -35,6 +36,8 @@ SIGNATURES = {
     'nnal_model_info': (C.c_int, [c_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'nnal_volume_set': (C.c_int, [c_vp, C.c_int, C.c_int, C.POINTER(c_vp), C.c_int, C.c_int64, C.c_int64,
                                   C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    'nnal_volume_set_device': (C.c_int, [c_vp, C.c_int, C.c_int, c_vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                         C.c_int64, C.c_int64]),
     'nnal_volume_clear': (C.c_int, [c_vp]),
     'nnal_gather': (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
     'nnal_gather_device_f32': (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),

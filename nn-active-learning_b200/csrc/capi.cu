@@ -17,6 +17,16 @@ static int64_t chunk_size() {
 
 extern "C" int nnal_version(void) { return NNAL_VERSION; }
 
+extern "C" int nnal_device_memory(nnal_ctx* ctx, uint64_t* free_bytes, uint64_t* total_bytes) {
+  if (!ctx) return NNAL_ERR_INVALID;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  size_t f = 0, t = 0;
+  CUDA_TRY(ctx, cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return NNAL_OK;
+}
+
 // ---- content hash of caller-owned HOST arrays (volumes, weights) -------------------------------------------------
 // The host layer skips an upload only when the FULL content of the arrays is unchanged (the reference passes the same
 // padded volumes on every query and fine-tunes the weights between queries; a sampled checksum or object identity would
@@ -223,7 +233,13 @@ extern "C" int nnal_model_layer_info(nnal_ctx* ctx, int layer, int* type, long l
   if (L.type == NNAL_LAYER_CONV) macs = (long long)L.out_h * L.out_w * L.out_c * L.kh * L.kw * L.in_c;
   else if (L.type == NNAL_LAYER_FC) macs = (long long)L.in_dim * L.out_dim;
   if (macs_per_sample) *macs_per_sample = macs;
-  if (uses_tc) *uses_tc = nnal_layer_on_tc(ctx, layer) ? 1 : 0;
+  if (uses_tc) {
+    *uses_tc = nnal_layer_on_tc(ctx, layer) ? 1 : 0;
+    // 2: the weight-stationary tcgen05 conv kernel (conv_wt.cu) -- same choice as the forward driver makes
+    if (*uses_tc && L.type == NNAL_LAYER_CONV &&
+        (ctx->use_wt >= 3 ? nnal_wt_conv_supported(ctx, L) : ctx->use_wt >= 1 && nnal_wt_conv_preferred(ctx, L)))
+      *uses_tc = 2;
+  }
   return NNAL_OK;
 }
 
@@ -335,6 +351,18 @@ extern "C" int nnal_model_set_weights(nnal_ctx* ctx, int layer, const float* W, 
 // ---------------------------------------------------------------------------------------------
 // volumes
 // ---------------------------------------------------------------------------------------------
+static int volume_finish(nnal_ctx* ctx, Volume& v, const void* d_stage, int m, int dtype, int64_t X, int64_t Y, int64_t Z,
+                         int64_t px, int64_t py, int64_t pz, size_t out_bytes) {
+  if (v.bytes < out_bytes) {
+    if (v.data) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CUDA_TRY(ctx, cudaFree(v.data)); v.data = nullptr; }
+    CUDA_TRY(ctx, cudaMalloc(&v.data, out_bytes));
+    v.bytes = out_bytes;
+  }
+  v.m = m; v.X = X + 2 * px; v.Y = Y + 2 * py; v.Z = Z + 2 * pz; v.dtype = dtype;
+  NNAL_TRY(nnal_k_relayout(ctx, d_stage, dtype, m, X, Y, Z, px, py, pz, v.data));
+  return NNAL_OK;
+}
+
 extern "C" int nnal_volume_set(nnal_ctx* ctx, int subject, int m, const void* const* mods, int dtype, int64_t X, int64_t Y,
                                int64_t Z, int64_t px, int64_t py, int64_t pz) {
   if (!ctx || !mods || m <= 0 || subject < 0 || X <= 0 || Y <= 0 || Z <= 0 || px < 0 || py < 0 || pz < 0) return NNAL_ERR_INVALID;
@@ -351,14 +379,22 @@ extern "C" int nnal_volume_set(nnal_ctx* ctx, int subject, int m, const void* co
     CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->stage.p + (size_t)j * in_elems * esz, mods[j], in_elems * esz,
                                   cudaMemcpyHostToDevice, ctx->stream));
   }
-  if (v.bytes < out_bytes) {
-    if (v.data) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CUDA_TRY(ctx, cudaFree(v.data)); v.data = nullptr; }
-    CUDA_TRY(ctx, cudaMalloc(&v.data, out_bytes));
-    v.bytes = out_bytes;
-  }
-  v.m = m; v.X = X + 2 * px; v.Y = Y + 2 * py; v.Z = Z + 2 * pz; v.dtype = dtype;
-  NNAL_TRY(nnal_k_relayout(ctx, ctx->stage.p, dtype, m, X, Y, Z, px, py, pz, v.data));
-  return NNAL_OK;
+  return volume_finish(ctx, v, ctx->stage.p, m, dtype, X, Y, Z, px, py, pz, out_bytes);
+}
+
+// Same, with the m modality arrays already in DEVICE memory (d_stage: m consecutive C-contiguous (X,Y,Z) arrays).  Used
+// by the multi-GPU host layer: every rank copies 1/world of each volume over PCIe and the parts are all-gathered over
+// NVLink (NCCL, on nnal_stream()) instead of every rank pulling the same volume through its own PCIe link.
+extern "C" int nnal_volume_set_device(nnal_ctx* ctx, int subject, int m, const void* d_stage, int dtype, int64_t X, int64_t Y,
+                                      int64_t Z, int64_t px, int64_t py, int64_t pz) {
+  if (!ctx || !d_stage || m <= 0 || subject < 0 || X <= 0 || Y <= 0 || Z <= 0 || px < 0 || py < 0 || pz < 0) return NNAL_ERR_INVALID;
+  if (dtype != NNAL_F32 && dtype != NNAL_F64) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "volume dtype must be NNAL_F32 or NNAL_F64");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((int)ctx->vols.size() <= subject) ctx->vols.resize(subject + 1);
+  Volume& v = ctx->vols[subject];
+  const size_t esz = dtype == NNAL_F64 ? 8 : 4;
+  const size_t out_bytes = (size_t)(X + 2 * px) * (Y + 2 * py) * (Z + 2 * pz) * m * esz;
+  return volume_finish(ctx, v, d_stage, m, dtype, X, Y, Z, px, py, pz, out_bytes);
 }
 
 static int check_gather_args(nnal_ctx* ctx, int subject, int64_t n, int d1, int d2, int d3, const Volume** vout) {

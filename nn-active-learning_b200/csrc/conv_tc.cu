@@ -445,21 +445,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             if (valid && C::POOL) {
               // post-ReLU values are >= +0, so their bit patterns order like unsigned integers
               uint32_t* pc = my_pooled + ((y >> 1) * C::PWO + (x >> 1)) * C::PSTRIDE + c0;
+              uint32_t amax = 0u;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 if (c0 + j < C::COUT_REAL) {
                   const float r = v[j] * p.w_scale_inv + bb[j];
-                  nnal_ovf_note(r);
+                  nnal_ovf_track(amax, r);
                   atomicMax(pc + j, __float_as_uint(r > 0.f ? fminf(r, 65504.f) : 0.f));
                 }
               }
+              nnal_ovf_commit(amax);
             } else if (valid) {
-              uint32_t hi[8], lo[8];
+              uint32_t hi[8], lo[8], amax = 0u;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float r0 = v[2 * j] * p.w_scale_inv + bb[2 * j], r1 = v[2 * j + 1] * p.w_scale_inv + bb[2 * j + 1];
-                nnal_ovf_note(fmaxf(r0, r1));                                // (fmaxf drops a NaN operand: checked apart)
-                if (r0 != r0 || r1 != r1) nnal_ovf_note(r0 + r1);
+                nnal_ovf_track(amax, r0);
+                nnal_ovf_track(amax, r1);
                 const float x0 = fminf(fmaxf(r0, 0.f), 65504.f);
                 const float x1 = fminf(fmaxf(r1, 0.f), 65504.f);
                 const __half2 h = __floats2half2_rn(x0, x1);              // .x (low half) = x0
@@ -468,6 +470,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 hi[j] = *reinterpret_cast<const uint32_t*>(&h);
                 lo[j] = *reinterpret_cast<const uint32_t*>(&l);
               }
+              nnal_ovf_commit(amax);
               uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
               uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
               dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -495,8 +498,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
               const float o0 = __uint_as_float(pc[2 * j]), o1 = __uint_as_float(pc[2 * j + 1]);
               pc[2 * j] = 0u; pc[2 * j + 1] = 0u;
               nnal_h h0, h1, l0, l1;
-              nnal_split(o0, h0, l0);
-              nnal_split(o1, h1, l1);
+              nnal_split_unchecked(o0, h0, l0);                    // clamped (and flagged) when they entered the raster
+              nnal_split_unchecked(o1, h1, l1);
               hi[j] = nnal_pack2(h0, h1);
               lo[j] = nnal_pack2(l0, l1);
             }

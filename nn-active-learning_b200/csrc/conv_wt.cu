@@ -329,6 +329,7 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmHiL, const __grid_constant_
               else { z[0][2 * i + k] = sa; z[NCH - 1][2 * i + k] = sb_; }
             }
           if (sb + C::NEW < NSB) issue(sb + C::NEW);                      // next sub-block in flight during the stores
+          uint32_t amax = 0u;                                             // fp16 range guard: largest |value| of the sub-block
           if (C::POOL) {
             // output offsets (or -1) of this thread's positions from the table; one shared-memory atomicMax per output
             const int* ot = otab + t * C::TILE_N + sb * 32 + 2 * m;
@@ -342,7 +343,7 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmHiL, const __grid_constant_
                 for (int h = 0; h < NCH; ++h) {
                   if (off < chlim[h] && !(p.flags & 1)) {                 // -1 (padding / garbage column) fails too
                     const float rr = z[h][2 * i + k] * p.w_scale_inv + bias[h];
-                    nnal_ovf_note(rr);
+                    nnal_ovf_track(amax, rr);
                     const float o = rr > 0.f ? fminf(rr, 65504.f) : 0.f;
                     atomicMax(pooled + off + co[h], __float_as_uint(o));  // o >= +0: uint order == float order
                   }
@@ -359,7 +360,7 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmHiL, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float rr = z[h][j] * p.w_scale_inv + bias[h];
-                nnal_ovf_note(rr);
+                nnal_ovf_track(amax, rr);
                 const float o = rr > 0.f ? fminf(rr, 65504.f) : 0.f;
                 const nnal_h hh = __float2half_rn(o);
                 P[j] = nnal_pack2(hh, __float2half_rn(o - __half2float(hh)));
@@ -389,6 +390,7 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmHiL, const __grid_constant_
               }
             }
           }
+          nnal_ovf_commit(amax);
         }
         tc_fence_before();
         __syncwarp();

@@ -310,15 +310,18 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
               for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             if (p.out_hi) {
-              uint32_t hi[8], lo[8];
+              uint32_t hi[8], lo[8], amax = 0u;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 nnal_h h0, h1, l0, l1;
-                nnal_split(v[2 * j], h0, l0);
-                nnal_split(v[2 * j + 1], h1, l1);
+                nnal_ovf_track(amax, v[2 * j]);
+                nnal_ovf_track(amax, v[2 * j + 1]);
+                nnal_split_unchecked(v[2 * j], h0, l0);
+                nnal_split_unchecked(v[2 * j + 1], h1, l1);
                 hi[j] = nnal_pack2(h0, h1);
                 lo[j] = nnal_pack2(l0, l1);
               }
+              nnal_ovf_commit(amax);
               uint4* dh = reinterpret_cast<uint4*>(p.out_hi + (size_t)row * p.ld_split + col0);
               uint4* dl = reinterpret_cast<uint4*>(p.out_lo + (size_t)row * p.ld_split + col0);
               dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);

@@ -47,6 +47,20 @@ namespace {
 struct NnalOvfRegistrar { NnalOvfRegistrar() { nnal_ovf_register(&nnal_ovf_bind_tu); } };
 static NnalOvfRegistrar nnal_ovf_registrar_instance;
 }
+// hot epilogues: track the largest |x| bit pattern of a thread's tile (NaN / Inf patterns sort above every finite value:
+// two integer ops per element, no branch) and test it once per tile
+__device__ __forceinline__ void nnal_ovf_track(uint32_t& m, float x) { m = max(m, __float_as_uint(x) & 0x7fffffffu); }
+__device__ __forceinline__ void nnal_ovf_commit(uint32_t m) {
+  if (m > 0x477fe000u) {                      // bits of 65504.f
+    unsigned int* p = nnal_ovf_ptr;
+    if (p) atomicOr(p, 1u);
+  }
+}
+__device__ __forceinline__ void nnal_split_unchecked(float x, nnal_h& h, nnal_h& l) {
+  x = fminf(fmaxf(x, -65504.f), 65504.f);
+  h = __float2half_rn(x);
+  l = __float2half_rn(x - __half2float(h));
+}
 __device__ __forceinline__ void nnal_split(float x, nnal_h& h, nnal_h& l) {
   nnal_ovf_note(x);
   x = fminf(fmaxf(x, -65504.f), 65504.f);

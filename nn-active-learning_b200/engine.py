@@ -57,6 +57,13 @@ class Engine(object):
         except Exception:
             pass
 
+    factor_budget = 0.35       # fraction of the device memory the FC factors of a whole pool pass may occupy (fi._one_pass)
+
+    def factor_budget_bytes(self):
+        free, total = C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.nnal_device_memory(self.h, C.byref(free), C.byref(total)))
+        return int(self.factor_budget * total.value)
+
     def synchronize(self):
         self._chk(self.lib.nnal_synchronize(self.h))
 
@@ -188,8 +195,10 @@ class Engine(object):
             return np.ascontiguousarray(a, dtype=np.float32)      # exact
         return np.ascontiguousarray(a, dtype=np.float64)          # exact up to 2^53
 
-    def set_volume(self, subject, imgs, pads=(0, 0, 0)):
-        """``imgs``: list of m arrays (X,Y,Z) of one subject (already padded unless ``pads``)."""
+    def set_volume(self, subject, imgs, pads=(0, 0, 0), shared=False):
+        """``imgs``: list of m arrays (X,Y,Z) of one subject (already padded unless ``pads``).  ``shared``: every rank
+        passes this same volume in this same call (replicated single-volume pools): with NCCL each rank then copies 1/world
+        of it over PCIe and the parts are all-gathered over NVLink."""
         arrs = [self._as_device_dtype(a) for a in imgs]
         if any(a.ndim != 3 or a.shape != arrs[0].shape for a in arrs):
             raise ValueError('all modalities must be 3-D arrays of one shape')
@@ -201,15 +210,61 @@ class Engine(object):
         key = None
         if self.volume_cache:
             key = tuple((a.shape, a.dtype.str, self.host_hash(a)) for a in arrs) + (tuple(int(p) for p in pads),)
-            if self._vol_keys.get(subject) == key:
-                return
-        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        hit = key is not None and self._vol_keys.get(subject) == key
+        if shared:
+            hit = self._all_ranks_agree(hit)          # the sharded upload is a collective: skip it only if EVERY rank can
+        if hit:
+            return
         X, Y, Z = arrs[0].shape
         dt = L.F64 if arrs[0].dtype == np.float64 else L.F32
+        if shared and self._upload_sharded(subject, arrs, dt, pads):
+            self._vol_keys[subject] = key
+            return
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         self.h2d_bytes += sum(a.nbytes for a in arrs)
         self._chk(self.lib.nnal_volume_set(self.h, int(subject), len(arrs), ptrs, dt, X, Y, Z,
                                            int(pads[0]), int(pads[1]), int(pads[2])))
         self._vol_keys[subject] = key
+
+    @staticmethod
+    def _all_ranks_agree(flag):
+        from . import dist
+        if not dist.is_dist():
+            return flag
+        import torch
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dist._device())
+        dist._td().all_reduce(t, op=dist._td().ReduceOp.MIN)
+        return bool(t.item())
+
+    def _upload_sharded(self, subject, arrs, dt, pads):
+        """Every rank holds the same host arrays: copy this rank's 1/world slice of each modality host->device and
+        all-gather the slices over NVLink on the engine's stream.  Returns False when not applicable."""
+        from . import dist
+        if not dist.is_dist() or dist._td().get_backend() != 'nccl':
+            return False
+        import torch
+        td = dist._td()
+        rank, world = dist.rank_world()
+        X, Y, Z = arrs[0].shape
+        elems = X * Y * Z
+        chunk = -(-elems // world)
+        tdt = torch.float64 if arrs[0].dtype == np.float64 else torch.float32
+        with dist.engine_stream(self):
+            # modality j is gathered straight into its slot; the padding of the last chunk spills into the start of the
+            # next slot and is overwritten by that modality's own gather (same stream: ordered); one spare chunk at the end
+            stage = torch.empty(len(arrs) * elems + chunk, dtype=tdt, device='cuda')
+            send = torch.zeros(chunk, dtype=tdt, device='cuda')
+            for j, a in enumerate(arrs):
+                flat = a.reshape(-1)
+                a0, a1 = min(rank * chunk, elems), min((rank + 1) * chunk, elems)
+                if a1 > a0:
+                    send[:a1 - a0].copy_(torch.from_numpy(flat[a0:a1]), non_blocking=True)
+                    self.h2d_bytes += (a1 - a0) * a.itemsize
+                td.all_gather_into_tensor(stage[j * elems:j * elems + world * chunk], send)
+            self._chk(self.lib.nnal_volume_set_device(self.h, int(subject), len(arrs), C.c_void_p(stage.data_ptr()), dt, X, Y, Z,
+                                                      int(pads[0]), int(pads[1]), int(pads[2])))
+            torch.cuda.current_stream().synchronize()       # `stage` / `send` are released after the re-layout kernel ran
+        return True
 
     def invalidate_volumes(self):
         self._vol_keys = {}
@@ -240,8 +295,8 @@ class Engine(object):
                                        None if st is None else _ptr(st), int(norm_mode), _ptr(out)))
         return out
 
-    def upload(self, subject, imgs, pads=(0, 0, 0)):
-        self.set_volume(subject, imgs, pads)
+    def upload(self, subject, imgs, pads=(0, 0, 0), shared=False):
+        self.set_volume(subject, imgs, pads, shared)
         self._m[subject] = len(imgs)
 
     def gather_device(self, subject, d_inds_ptr, n, patch_shape, stats, norm_mode, d_out_ptr):

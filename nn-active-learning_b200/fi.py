@@ -112,8 +112,19 @@ def gram_report(eng, sel_gids, gids, delta, cand_rows=None, pool_gram=True):
     cuda = getattr(eng, 'message_device', 'cpu') == 'cuda'
     G2 = None
     if pool_gram and n_total > 0:
+        ev = None
+        if cuda:
+            stream = torch.cuda.ExternalStream(eng.stream)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record(stream)
         eng.fi_gram(np.full(n_local, 1. / n_total), read=False)
+        if ev:
+            ev[1].record(stream)
         rep['gram_bytes'] = gram_allreduce(eng)
+        if ev:
+            ev[2].record(stream)
+            ev[2].synchronize()
+            rep['gram_ms'], rep['allreduce_ms'] = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
         if cuda:
             ptr, rows, ld = eng.fi_gram_device()
             with dist.engine_stream(eng):
@@ -153,12 +164,12 @@ def gram_report(eng, sel_gids, gids, delta, cand_rows=None, pool_gram=True):
     return rep
 
 
-def _maybe_report(expr, eng, chosen, gids, delta, obj):
+def _maybe_report(expr, eng, chosen, gids, delta, obj, cand_rows=None):
     """``expr.pars['fi_report'] = True``: leave the Gram-form (primal) evaluation of the selection in ``fi.last_report``."""
     global last_report
     if not expr.pars.get('fi_report', False):
         return
-    last_report = gram_report(eng, chosen, gids, delta)
+    last_report = gram_report(eng, chosen, gids, delta, cand_rows)
     last_report['dual_objective'] = float(obj[-1]) if len(obj) else None
 
 
@@ -168,79 +179,131 @@ def _pars(expr, default_delta):
     return nl, delta
 
 
-def query_single(expr, model, sess, padded_imgs, pool_inds, return_objective=False):
-    """``PW_NNAL.CNN_query(..., 'fi')``: positions into ``pool_inds`` (greedy selection order)."""
+def _one_pass(eng, n_local, nl):
+    """Keep the FC factors of the WHOLE local pool in one pass (and index the B candidates in place) when they fit the
+    factor budget -- a fraction of the device memory, ``Engine.factor_budget`` -- instead of re-running gather + forward
+    over the candidates (what the reference does, PW_NNAL.py:117-131).  Same factors either way: the forward pass does not
+    depend on which samples share a chunk."""
+    per = 4 * (eng.feat_dim + (eng.prev_dim if nl == 2 else 0))
+    return n_local * per <= eng.factor_budget_bytes()
+
+
+def _ret(q, obj, red, q_ent, return_objective, also_entropy):
+    out = (q, obj, red) if return_objective == 'reduced' else ((q, obj) if return_objective else q)
+    if also_entropy:
+        return (q_ent,) + (out if isinstance(out, tuple) else (out,))
+    return out
+
+
+def query_single(expr, model, sess, padded_imgs, pool_inds, return_objective=False, also_entropy=False):
+    """``PW_NNAL.CNN_query(..., 'fi')``: positions into ``pool_inds`` (greedy selection order).
+    ``also_entropy``: the same pool pass also answers the ``'entropy'`` query (k smallest |p - 0.5|, PW_NNAL.py:51-65);
+    returns ``(q_entropy, q_fi[, ...])`` -- the combined round of ``method_name = 'entropy+fi'``."""
     from .PW_NNAL import _score_pool_single, _stats_list
     k, B = int(expr.pars['k']), int(expr.pars['B'])
     nl, delta = _pars(expr, 1e-5)
     pool_inds = np.asarray(pool_inds)
     n = len(pool_inds)
-    if B < n:
-        eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=0)
+    eng = get_engine()
+    eng.set_model(model, sess)
+    rank, world = dist.rank_world()
+    b = dist.shard_bounds(n, world)
+    one_pass = B >= n or _one_pass(eng, int(b[rank + 1] - b[rank]), nl)
+    eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=nl if one_pass else 0)
+    q_ent = None
+    cand_rows = None
+    if B < n or also_entropy:
         eng.pool_score(L.SCORE_BINARY)
-        sel_inds, _ = dist.topk_global(eng, B, lo, n)
+    if B < n:
+        sel_inds, _ = dist.topk_global(eng, max(B, k) if also_entropy else B, lo, n)
+        if also_entropy:
+            q_ent, sel_inds = sel_inds[:k], sel_inds[:B]          # both lists are prefixes of one ascending ranking
         own = (sel_inds >= lo) & (sel_inds < hi)
         mine = sel_inds[own]
-        # second pass over this rank's candidates, keeping the factors of the last FC layers
-        eng.pool_begin(len(mine), nl)
-        if len(mine):
-            imgs = list(padded_imgs)
-            eng.pool_eval(0, pool_inds[mine], 0, expr.pars['patch_shape'], _stats_list(expr.pars['stats'], len(imgs)),
-                          L.NORM_BATCH_EVAL, shape=imgs[0].shape)
+        if one_pass:
+            cand_rows = mine - lo                                 # candidates = rows of the pool pass, indexed in place
+            eng.fi_set_candidates(cand_rows, nl)
+        else:
+            # second pass over this rank's candidates, keeping the factors of the last FC layers
+            eng.pool_begin(len(mine), nl)
+            if len(mine):
+                imgs = list(padded_imgs)
+                eng.pool_eval(0, pool_inds[mine], 0, expr.pars['patch_shape'], _stats_list(expr.pars['stats'], len(imgs)),
+                              L.NORM_BATCH_EVAL, shape=imgs[0].shape)
+            eng.fi_set_candidates(None, nl)
     else:
-        eng, lo, hi = _score_pool_single(expr, model, sess, padded_imgs, pool_inds, keep=nl)
+        if also_entropy:
+            q_ent, _ = dist.topk_global(eng, k, lo, n)
         sel_inds = np.arange(n, dtype=np.int64)
         own = (sel_inds >= lo) & (sel_inds < hi)
-    eng.fi_set_candidates(None, nl)
+        eng.fi_set_candidates(None, nl)
     gids = np.nonzero(own)[0].astype(np.int64)
     chosen, obj, red = greedy_select(eng, min(k, len(sel_inds)), delta, gids)
-    _maybe_report(expr, eng, chosen, gids, delta, obj)
-    q = sel_inds[chosen]
-    if return_objective == 'reduced':
-        return q, obj, red
-    return (q, obj) if return_objective else q
+    _maybe_report(expr, eng, chosen, gids, delta, obj, cand_rows)
+    return _ret(sel_inds[chosen], obj, red, q_ent, return_objective, also_entropy)
 
 
-def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, return_objective=False):
+def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, return_objective=False, also_entropy=False):
     """``PW_NNAL.query_multimg(..., 'fi')``: list of S arrays of local positions into ``pool_inds[s]``.
     Candidate order = the reference's: subject-major, uncertainty order inside a subject
-    (``A += gen_A_matrices(...)`` per subject, PW_NNAL.py:566-578)."""
-    from .PW_NNAL import _bin_filter_core
+    (``A += gen_A_matrices(...)`` per subject, PW_NNAL.py:566-578); without a pre-filter (``B >= n``) the candidates are
+    the pool in its own (subject-major) order."""
+    from .PW_NNAL import _pool_pass_multimg
     k, B = int(expr.pars['k']), int(expr.pars['B'])
     nl, delta = _pars(expr, 1e-3)
     eng = get_engine()
-    sorted_inds, _, lo, hi, sizes = _bin_filter_core(expr, model, sess, all_padded_imgs, pool_inds, B)
+    eng.set_model(model, sess)
     s = len(pool_inds)
     m = len(all_padded_imgs[0]) - 1
+    sizes = [len(pool_inds[i]) for i in range(s)]
+    n = int(np.sum(sizes))
+    rank, world = dist.rank_world()
+    b = dist.shard_bounds(n, world)
+    one_pass = B >= n or _one_pass(eng, int(b[rank + 1] - b[rank]), nl)
+    eng, lo, hi, sizes, n = _pool_pass_multimg(expr, model, sess, all_padded_imgs, pool_inds, keep=nl if one_pass else 0)
     cum = np.append(-1, np.cumsum(sizes) - 1)
-    set_of = cum.searchsorted(sorted_inds) - 1
-    order = np.argsort(set_of, kind='stable')
-    G = sorted_inds[order]                       # global positions, subject-major candidate order
-    G_set = set_of[order]
-    own = (G >= lo) & (G < hi)
-    eng.pool_begin(int(own.sum()), nl)
-    off = 0
-    for i in range(s):
-        sel = own & (G_set == i)
-        ni = int(sel.sum())
-        if ni == 0:
-            continue
-        local = G[sel] - (cum[i] + 1)
-        imgs = list(all_padded_imgs[i][:-1])
-        eng.upload(i, imgs)
-        stats = np.array([[expr.train_stats[i, 2 * j], expr.train_stats[i, 2 * j + 1]] for j in range(m)],
-                         dtype=np.float64)
-        eng.pool_eval(i, np.asarray(pool_inds[i])[local], off, expr.pars['patch_shape'], stats, L.NORM_BATCH_EVAL,
-                      shape=imgs[0].shape)
-        off += ni
-    eng.fi_set_candidates(None, nl)
+    q_ent = None
+    cand_rows = None
+    if B < n or also_entropy:
+        eng.pool_score(L.SCORE_BINARY)
+    if also_entropy:
+        q_ent = patch_utils.global2local_inds(dist.topk_global(eng, k, lo, n)[0], sizes)
+    if B < n:
+        sorted_inds, _ = dist.topk_global(eng, B, lo, n)
+        set_of = cum.searchsorted(sorted_inds) - 1
+        order = np.argsort(set_of, kind='stable')
+        G = sorted_inds[order]                       # global positions, subject-major candidate order
+        G_set = set_of[order]
+        own = (G >= lo) & (G < hi)
+        if one_pass:
+            cand_rows = G[own] - lo
+            eng.fi_set_candidates(cand_rows, nl)
+        else:
+            eng.pool_begin(int(own.sum()), nl)
+            off = 0
+            for i in range(s):
+                sel = own & (G_set == i)
+                ni = int(sel.sum())
+                if ni == 0:
+                    continue
+                local = G[sel] - (cum[i] + 1)
+                imgs = list(all_padded_imgs[i][:-1])
+                eng.upload(i, imgs)
+                stats = np.array([[expr.train_stats[i, 2 * j], expr.train_stats[i, 2 * j + 1]] for j in range(m)],
+                                 dtype=np.float64)
+                eng.pool_eval(i, np.asarray(pool_inds[i])[local], off, expr.pars['patch_shape'], stats, L.NORM_BATCH_EVAL,
+                              shape=imgs[0].shape)
+                off += ni
+            eng.fi_set_candidates(None, nl)
+    else:
+        G = np.arange(n, dtype=np.int64)
+        own = (G >= lo) & (G < hi)
+        eng.fi_set_candidates(None, nl)
     gids = np.nonzero(own)[0].astype(np.int64)
     chosen, obj, red = greedy_select(eng, min(k, len(G)), delta, gids)
-    _maybe_report(expr, eng, chosen, gids, delta, obj)
+    _maybe_report(expr, eng, chosen, gids, delta, obj, cand_rows)
     Q = patch_utils.global2local_inds(G[chosen], sizes)
-    if return_objective == 'reduced':
-        return Q, obj, red
-    return (Q, obj) if return_objective else Q
+    return _ret(Q, obj, red, q_ent, return_objective, also_entropy)
 
 
 def _gather_shrunk(post, g):

@@ -57,6 +57,13 @@ def run(rank, world, out):
     expr.pars['B'] = 10 ** 6                 # no pre-filter: every rank's whole block is a candidate
     q, obj = nnal_b200.fi.query_single(expr, model, None, allp[0][:m], pool0, return_objective=True)
     res['fi_all'], res['fi_all_obj'] = q, obj
+    # combined round: ONE pool pass answers 'entropy' and 'fi'; and the two-pass candidate evaluation gives the same answer
+    expr.pars.update(B=30)
+    qe, qf = nnal_b200.PW_NNAL.CNN_query(expr, model, None, allp[0][:m], pool0, None, 'entropy+fi')
+    res['combo_ent'], res['combo_fi'] = qe, qf
+    engine._engine.one_pass = False
+    res['fi_two_pass'] = nnal_b200.PW_NNAL.CNN_query(expr, model, None, allp[0][:m], pool0, None, 'fi')
+    engine._engine.one_pass = True
     # Gram (primal) form of the objective for the selection: per-rank partial Grams, all-reduce, (d+1)^2 inverse
     expr.pars.update(B=30, fi_layers=1, fi_report=True)
     q, obj = nnal_b200.fi.query_single(expr, model, None, allp[0][:m], pool0, return_objective=True)
@@ -85,6 +92,13 @@ def run(rank, world, out):
     for s in range(len(Q)):
         res['fi_multi%d' % s] = np.asarray(Q[s])
     res['fi_multi_obj'] = obj
+    Qe, Qf = nnal_b200.PW_NNAL.query_multimg(expr, model, None, allp, pools, None, 'entropy+fi')
+    engine._engine.one_pass = False
+    Q2 = nnal_b200.PW_NNAL.query_multimg(expr, model, None, allp, pools, None, 'fi')
+    engine._engine.one_pass = True
+    for s in range(len(Q)):
+        res['combo_multi_ent%d' % s], res['combo_multi_fi%d' % s] = np.asarray(Qe[s]), np.asarray(Qf[s])
+        res['fi_multi_two_pass%d' % s] = np.asarray(Q2[s])
     expr.pars['fi_mode'] = 'sdp'
     np.random.seed(2000 + rank)
     Q = nnal_b200.PW_NNAL.query_multimg(expr, model, None, allp, pools, None, 'fi')

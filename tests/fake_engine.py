@@ -14,6 +14,15 @@ class FakeEngine(object):
         self.vols = {}
         self._m = {}
 
+    one_pass = True          # tests flip this to exercise the two-pass candidate evaluation as well
+
+    def factor_budget_bytes(self):
+        return 1 << 60 if self.one_pass else 0
+
+    @property
+    def prev_dim(self):
+        return self._prev_dim()
+
     # -- model / volumes ---------------------------------------------------
     def set_model(self, model, sess=None):
         self.layers = [(k, v) for k, v in model.layer_dict.items()]
@@ -21,7 +30,7 @@ class FakeEngine(object):
         self.n_class = int(self.layers[-1][1][0])
         self.feature_layer = model.feature_layer_index if model.feature_layer_index is not None else len(self.layers) - 2
 
-    def upload(self, subject, imgs, pads=(0, 0, 0)):
+    def upload(self, subject, imgs, pads=(0, 0, 0), shared=False):
         self.vols[subject] = [np.asarray(a) for a in imgs]
         self._m[subject] = len(imgs)
 

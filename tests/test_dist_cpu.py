@@ -117,6 +117,24 @@ def test_single_process_matches_oracle(runs):
     assert np.array_equal(one['fi_sdp_whole'], sel[draws])
 
 
+def test_combined_round_and_two_pass_agree(runs):
+    """'entropy+fi' (one pool pass) returns exactly what the two single-method queries return; evaluating the B candidates
+    in a second pass (factors of the whole pool do not fit) selects the same samples as indexing them in place."""
+    for r in [runs[0]] + list(runs[1]) + list(runs[2]):
+        assert np.array_equal(r['combo_ent'], r['ent_single'])
+        assert np.array_equal(r['combo_fi'], r['fi_single'])
+        assert np.array_equal(r['fi_two_pass'], r['fi_single'])
+        for s in range(3):
+            assert np.array_equal(r['combo_multi_fi%d' % s], r['fi_multi%d' % s])
+            assert np.array_equal(r['fi_multi_two_pass%d' % s], r['fi_multi%d' % s])
+    one = runs[0]
+    from tests._dist_worker import make_case
+    ps, m, layers, w, allp, pools, st, _ = make_case()
+    Q = O.query_entropy_multimg(layers, w, allp, pools, ps, 16, st, 11)
+    for s in range(3):
+        assert np.array_equal(one['combo_multi_ent%d' % s], Q[s])
+
+
 def test_gram_allreduce_primal_equals_dual(runs):
     """Per-rank partial Grams summed by an all-reduce give the same primal objective tr((delta I + 2H)^-1) + (d+1)/delta
     on every rank and world size, equal to the dual (kernel) objective the greedy loop reports (last-layer FI)."""

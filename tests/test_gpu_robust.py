@@ -75,7 +75,7 @@ def test_overflow_flag_isolated_layers(nb):
     A[3, 5] = np.nan
     with pytest.raises(L.NnalOverflowError):
         eng.debug_fc(A, W, b, 1, 1)
-    out = eng.debug_fc(A, W, b, 1, 0)                         # FP32 CUDA-core GEMM: NaN propagates like in TF, no error
+    out = eng.debug_fc(A, W, b, 0, 0)                         # FP32 CUDA-core GEMM (no activation): NaN propagates, no error
     assert np.isnan(out[3]).all() and np.isfinite(out[4]).all()
 
 
