@@ -101,9 +101,17 @@ class CNN(object):
             w[name] = (W, (rs.randn(*bs) * bias_scale).astype(np.float32))
         self.set_weights(w)
 
+    @staticmethod
+    def _is_hdf5(file_path):
+        return str(file_path).lower().endswith(('.h5', '.hdf5', '.hdf'))
+
     def save_weights(self, file_path):
-        """NPZ with the key layout of NN.save_weights' HDF5 groups (NN.py:379-396):
-        ``<layer>/Weight`` and ``<layer>/Bias``."""
+        """NN.save_weights (NN.py:379-396): ``<layer>/Weight`` and ``<layer>/Bias`` -- as HDF5 groups/datasets when the
+        path ends in .h5/.hdf5 (written by ``nnal_b200.hdf5``: h5py's default on-disk format), else as the keys of an NPZ."""
+        if self._is_hdf5(file_path):
+            from . import hdf5
+            hdf5.write_weights(file_path, {name: (W, b) for name, (W, b) in self.var_dict.items()})
+            return
         d = {}
         for name, (W, b) in self.var_dict.items():
             d[name + '/Weight'] = W
@@ -111,22 +119,27 @@ class CNN(object):
         np.savez(file_path, **d)
 
     def load_weights(self, file_path):
+        """Inverse of ``save_weights``; HDF5 files are the reference's own weight files (NN.py:379-396)."""
+        if self._is_hdf5(file_path):
+            from . import hdf5
+            try:
+                w = hdf5.read_weights(file_path)
+            except NotImplementedError:
+                import h5py                              # layouts outside the built-in reader (chunked, filtered, ...)
+                with h5py.File(file_path, 'r') as f:
+                    w = {name: (np.array(f[name]['Weight']), np.array(f[name]['Bias'])) for name in self.weight_shapes()}
+            missing = [name for name in self.weight_shapes() if name not in w]
+            if missing:
+                raise KeyError('weight file %s has no group(s) %s' % (file_path, ', '.join(missing)))
+            self.set_weights({name: w[name] for name in self.weight_shapes()})
+            return
         z = np.load(file_path)
         self.set_weights({name: (z[name + '/Weight'], z[name + '/Bias']) for name in self.weight_shapes()})
 
     def perform_assign_ops(self, file_path, sess=None):
-        """NN.CNN.perform_assign_ops (NN.py:397-419): load the weights saved at ``file_path`` into the model.
-        NPZ files written by ``save_weights`` (same ``<layer>/Weight``, ``<layer>/Bias`` keys as the reference's
-        HDF5 groups); HDF5 itself is read when h5py is importable."""
-        if str(file_path).endswith(('.h5', '.hdf5')):
-            try:
-                import h5py
-            except ImportError:
-                raise NotImplementedError('h5py is not available here: convert the weight file to NPZ (save_weights)')
-            with h5py.File(file_path, 'r') as f:
-                self.set_weights({name: (np.array(f[name]['Weight']), np.array(f[name]['Bias'])) for name in self.weight_shapes()})
-        else:
-            self.load_weights(file_path)
+        """NN.CNN.perform_assign_ops (NN.py:397-419): load the weights saved at ``file_path`` into the model (the
+        reference's HDF5 files, or NPZ files with the same ``<layer>/Weight``, ``<layer>/Bias`` keys)."""
+        self.load_weights(file_path)
 
     def get_gradients(self, grad_layers=[]):
         """Records which layers the FI score factors cover (NN.py:621-645)."""

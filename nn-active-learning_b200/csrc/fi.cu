@@ -68,6 +68,12 @@ struct State {
   long long* blk_idx = nullptr;
   int blk_cap = 0;
   DevScalars* sc = nullptr;
+  unsigned int* ticket = nullptr;        // last-block election of the fused eval + pick kernel
+  // the t x t inverse of step t+1 runs on a side stream while the (memory-bound) kernel column of step t is computed
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_kss = nullptr, ev_inv = nullptr;
+  int inv_ready_for = -1;                // step whose inverse has been enqueued on the side stream (-1: none)
+  int64_t k_run = 0;                     // number of steps of the current selection (nnal_fi_begin)
   // Gram
   float* H = nullptr;
   int Hd = 0, Hld = 0;
@@ -168,29 +174,6 @@ __global__ void __launch_bounds__(256) column_kernel(const float* __restrict__ U
     pair_dots(U + r * d, A ? A + r * dp : nullptr, wu, wa, beta2, d, dp, nl, lane, uu, aa, mm);
     if (lane == 0) kcol[i] = sw[i] * s_w * pair_kernel(uu, aa, mm, nl);
   }
-}
-
-// Step-t winner = local candidate *idx_ptr: copies its factors into the winner slot and extends the winners'
-// kernel K_SS by row/column t, read back from the kernel columns already computed:
-//   K_SS[t][a] = kcols[a][winner] (a < t),  K_SS[t][t] = Kt_winner,winner.
-__global__ void copy_winner_kernel(const float* __restrict__ U, const float* __restrict__ A, const int64_t* __restrict__ rows,
-                                   const double* __restrict__ sw, const double* __restrict__ diag,
-                                   const double* __restrict__ kcols, int64_t kn, const long long* __restrict__ idx_ptr, int t,
-                                   int d, int dp, float* __restrict__ win_u, float* __restrict__ win_a,
-                                   double* __restrict__ win_sw, double* __restrict__ kss, int64_t kss_ld) {
-  const long long i = *idx_ptr;
-  if (i < 0) return;
-  const int64_t r = rows ? rows[i] : i;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-  for (int k = tid; k < d; k += nt) win_u[k] = U[r * d + k];
-  if (A)
-    for (int k = tid; k < dp; k += nt) win_a[k] = A[r * dp + k];
-  for (int a = tid; a <= t; a += nt) {
-    const double v = a < t ? kcols[(int64_t)a * kn + i] : diag[i];
-    kss[(int64_t)t * kss_ld + a] = v;
-    kss[(int64_t)a * kss_ld + t] = v;
-  }
-  if (tid == 0) *win_sw = sw[i];
 }
 
 // Register-tiled Gauss-Jordan for t <= 32 RT: 1024 threads as a 32 x 32 grid, thread (ty,tx) owns the RT x RT
@@ -330,11 +313,26 @@ constexpr int EVAL_CAND = 32, EVAL_SUB = 8;      // candidates per CTA (= lanes)
 // the SAME C elements (shared-memory broadcast: one wavefront per 16 bytes) and consecutive k values.
 // MODE 2: C and the CTA's 32 x t slice of the kernel columns staged in shared memory (t <= 128);
 // MODE 1: C in shared memory; MODE 0: everything from global memory (large t).
+// arguments of the tail that the LAST CTA of eval_kernel runs: global arg-min over the block results, selection record,
+// and (single-process greedy, copy = 1) the winner's factors + row t of the winners' kernel K_SS -- what used to be two
+// more launches (pick_kernel, copy_winner_kernel) per greedy step
+struct TailArgs {
+  unsigned int* ticket;
+  DevScalars* sc;
+  int commit, copy;
+  unsigned char* avail;
+  long long* sel;
+  double* red;
+  const float* U; const float* A; const int64_t* rows; const double* sw;
+  int d, dp;
+  float* win_u; float* win_a; double* win_sw; double* kss; int64_t kss_ld;
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(256) eval_kernel(const double* __restrict__ kcols, int64_t kn, const double* __restrict__ diag,
                                                     const unsigned char* __restrict__ avail, const double* __restrict__ Cg, int t,
                                                     int ldc, int64_t n, double alpha, double* __restrict__ blk_loss,
-                                                    long long* __restrict__ blk_idx) {
+                                                    long long* __restrict__ blk_idx, TailArgs ta) {
   extern __shared__ double sm_d[];
   __shared__ double part_r[EVAL_SUB][EVAL_CAND], part_e[EVAL_SUB][EVAL_CAND];
   const double* Cs = Cg;
@@ -411,44 +409,68 @@ __global__ void __launch_bounds__(256) eval_kernel(const double* __restrict__ kc
     }
     if (lane == 0) { blk_loss[blockIdx.x] = loss; blk_idx[blockIdx.x] = idx; }
   }
-}
-
-// final arg-min over the block results; commit = 1 also removes the winner from the candidate set and
-// records the selection and the reduced objective  red_t = (t+1) (tr C + loss*)
-__global__ void __launch_bounds__(256) pick_kernel(const double* __restrict__ blk_loss, const long long* __restrict__ blk_idx,
-                                                    int nblk, int t, DevScalars* sc, int commit, unsigned char* __restrict__ avail,
-                                                    long long* __restrict__ sel, double* __restrict__ red) {
-  double loss = INFINITY;
-  long long idx = 0x7fffffffffffffffll;
-  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
-    const double ol = blk_loss[b];
-    const long long oi = blk_idx[b];
-    if (ol < loss || (ol == loss && oi < idx)) { loss = ol; idx = oi; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ol = __shfl_xor_sync(0xffffffffu, loss, o);
-    const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ol < loss || (ol == loss && oi < idx)) { loss = ol; idx = oi; }
-  }
-  __shared__ double wl[8];
-  __shared__ long long wi[8];
-  if ((threadIdx.x & 31) == 0) { wl[threadIdx.x >> 5] = loss; wi[threadIdx.x >> 5] = idx; }
-  __syncthreads();
+  // ---- tail: the last CTA to finish picks the global winner
+  __shared__ unsigned int s_last;
+  __shared__ long long s_win;
   if (threadIdx.x == 0) {
-    for (int q = 1; q < 8; ++q)
-      if (wl[q] < loss || (wl[q] == loss && wi[q] < idx)) { loss = wl[q]; idx = wi[q]; }
-    const bool found = loss < INFINITY;
-    if (!found) idx = -1;
-    sc->best_loss = loss;
-    sc->best_idx = idx;
-    if (t == 0) sc->trC = 0.0;
-    if (commit) {
-      if (found) avail[idx] = 0;
-      sel[t] = idx;
-      red[t] = (double)(t + 1) * (sc->trC + loss);
-    }
+    __threadfence();
+    s_last = atomicAdd(ta.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
   }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {
+    double loss = INFINITY;
+    long long idx = 0x7fffffffffffffffll;
+    const volatile double* vl = blk_loss;
+    const volatile long long* vi = blk_idx;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) {
+      const double ol = vl[b];
+      const long long oi = vi[b];
+      if (ol < loss || (ol == loss && oi < idx)) { loss = ol; idx = oi; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ol = __shfl_xor_sync(0xffffffffu, loss, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ol < loss || (ol == loss && oi < idx)) { loss = ol; idx = oi; }
+    }
+    if (lane == 0) { part_r[0][sub] = loss; part_e[0][sub] = __longlong_as_double(idx); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int q = 1; q < 8; ++q) {
+        const double wl = part_r[0][q];
+        const long long wi = __double_as_longlong(part_e[0][q]);
+        if (wl < loss || (wl == loss && wi < idx)) { loss = wl; idx = wi; }
+      }
+      const bool found = loss < INFINITY;
+      if (!found) idx = -1;
+      ta.sc->best_loss = loss;
+      ta.sc->best_idx = idx;
+      if (t == 0) ta.sc->trC = 0.0;
+      if (ta.commit) {
+        if (found) ta.avail[idx] = 0;
+        ta.sel[t] = idx;
+        ta.red[t] = (double)(t + 1) * (ta.sc->trC + loss);
+      }
+      *ta.ticket = 0u;                                   // ready for the next step's launch
+      s_win = idx;
+    }
+    __syncthreads();
+  }
+  if (!ta.copy) return;
+  const long long i = s_win;
+  if (i < 0) return;
+  const int64_t row = ta.rows ? ta.rows[i] : i;
+  for (int k = threadIdx.x; k < ta.d; k += 256) ta.win_u[k] = ta.U[row * ta.d + k];
+  if (ta.A)
+    for (int k = threadIdx.x; k < ta.dp; k += 256) ta.win_a[k] = ta.A[row * ta.dp + k];
+  for (int a = threadIdx.x; a <= t; a += 256) {
+    const double v = a < t ? kcols[(int64_t)a * kn + i] : diag[i];
+    ta.kss[(int64_t)t * ta.kss_ld + a] = v;
+    ta.kss[(int64_t)a * ta.kss_ld + t] = v;
+  }
+  if (threadIdx.x == 0) *ta.win_sw = ta.sw[i];
 }
 
 __global__ void mark_taken_kernel(unsigned char* avail, long long idx) { avail[idx] = 0; }
@@ -744,6 +766,8 @@ static int alloc_candidates(nnal_ctx* ctx, State* s, int64_t n) {
   if (!s->sc) {
     CUDA_TRY(ctx, cudaMalloc(&s->sc, sizeof(DevScalars)));
     CUDA_TRY(ctx, cudaMemsetAsync(s->sc, 0, sizeof(DevScalars), ctx->stream));
+    CUDA_TRY(ctx, cudaMalloc(&s->ticket, 64));
+    CUDA_TRY(ctx, cudaMemsetAsync(s->ticket, 0, 64, ctx->stream));
   }
   return NNAL_OK;
 }
@@ -786,15 +810,16 @@ static int alloc_greedy(nnal_ctx* ctx, State* s, int64_t k) {
 }
 
 // C = ((t+1) delta I + K_SS[0:t,0:t])^-1 and its trace (t >= 1)
-static int run_invert(nnal_ctx* ctx, State* s, int t) {
+static int run_invert(nnal_ctx* ctx, State* s, int t, cudaStream_t stream = nullptr) {
+  if (!stream) stream = ctx->stream;
   const double alpha = (double)(t + 1) * s->delta;
   const int ldc = (t + 7) / 8 * 8;
   if (t <= 32) {
-    invert_reg_kernel<1><<<1, 1024, 0, ctx->stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->sc);
+    invert_reg_kernel<1><<<1, 1024, 0, stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->sc);
   } else if (t <= 64) {
-    invert_reg_kernel<2><<<1, 1024, 0, ctx->stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->sc);
+    invert_reg_kernel<2><<<1, 1024, 0, stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->sc);
   } else if (t <= 128) {
-    invert_reg_kernel<4><<<1, 1024, 0, ctx->stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->sc);
+    invert_reg_kernel<4><<<1, 1024, 0, stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->sc);
   } else {
     static bool attr_inv = false;
     const int use_smem = t <= T_SMEM ? 1 : 0;
@@ -804,20 +829,52 @@ static int run_invert(nnal_ctx* ctx, State* s, int t) {
                                          (int)(((size_t)T_SMEM * (T_SMEM | 1) + T_SMEM) * sizeof(double))));
       attr_inv = true;
     }
-    invert_kernel<<<1, 1024, smem, ctx->stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->inv_ws, use_smem, s->sc);
+    invert_kernel<<<1, 1024, smem, stream>>>(s->kss, s->kcap, t, alpha, s->C, ldc, s->inv_ws, use_smem, s->sc);
   }
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
 }
 
+// K_SS has just been extended by row/column t-1 on the main stream: start the inverse of step t on the side stream so that
+// it overlaps the kernel column of step t-1 (a memory-bound pass over all candidates that does not touch K_SS or C).
+static int invert_async(nnal_ctx* ctx, State* s, int t) {
+  if (t < 1 || t >= s->k_run) return NNAL_OK;
+  if (!s->side) {
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&s->ev_kss, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&s->ev_inv, cudaEventDisableTiming));
+  }
+  CUDA_TRY(ctx, cudaEventRecord(s->ev_kss, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(s->side, s->ev_kss, 0));
+  NNAL_TRY(run_invert(ctx, s, t, s->side));
+  CUDA_TRY(ctx, cudaEventRecord(s->ev_inv, s->side));
+  s->inv_ready_for = t;
+  return NNAL_OK;
+}
+
+// the inverse of step t: already in flight on the side stream (wait for it) or computed here
+static int need_invert(nnal_ctx* ctx, State* s, int t) {
+  if (t < 1) return NNAL_OK;
+  if (s->inv_ready_for == t) {
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_inv, 0));
+    s->inv_ready_for = -1;
+    return NNAL_OK;
+  }
+  return run_invert(ctx, s, t);
+}
+
 // steps 1-3 of greedy step t: inverse, candidate evaluation, arg-min
-static int step_select(nnal_ctx* ctx, State* s, int t, int commit) {
+static int step_select(nnal_ctx* ctx, State* s, int t, int commit, int copy = 0) {
   const double alpha = (double)(t + 1) * s->delta;
   const int ldc = (t + 7) / 8 * 8;
   static bool attr_eval = false;
-  if (t > 0) NNAL_TRY(run_invert(ctx, s, t));
+  NNAL_TRY(need_invert(ctx, s, t));
   const int nblk = cdiv(s->n, EVAL_CAND);
+  TailArgs ta;
+  ta.ticket = s->ticket; ta.sc = s->sc; ta.commit = commit; ta.copy = copy; ta.avail = s->avail; ta.sel = s->sel; ta.red = s->red;
+  ta.U = s->U; ta.A = s->nl == 2 ? s->A : nullptr; ta.rows = s->R(); ta.sw = s->sw; ta.d = s->d; ta.dp = s->dp;
+  ta.win_u = s->win_u; ta.win_a = s->win_a; ta.win_sw = s->win_sw; ta.kss = s->kss; ta.kss_ld = s->kcap;
   if (!attr_eval) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(eval_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 * 128 + 128 * EVAL_CAND) * sizeof(double))));
     CUDA_TRY(ctx, cudaFuncSetAttribute(eval_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -826,16 +883,15 @@ static int step_select(nnal_ctx* ctx, State* s, int t, int commit) {
   }
   if (t <= 128) {
     eval_kernel<2><<<nblk, 256, ((size_t)t * ldc + (size_t)t * EVAL_CAND) * sizeof(double), ctx->stream>>>(
-        s->kcols, s->kcols_n, s->diag, s->avail, s->C, t, ldc, s->n, alpha, s->blk_loss, s->blk_idx);
+        s->kcols, s->kcols_n, s->diag, s->avail, s->C, t, ldc, s->n, alpha, s->blk_loss, s->blk_idx, ta);
   } else if (t <= T_SMEM) {
     eval_kernel<1><<<nblk, 256, (size_t)t * ldc * sizeof(double), ctx->stream>>>(s->kcols, s->kcols_n, s->diag, s->avail, s->C, t,
-                                                                                ldc, s->n, alpha, s->blk_loss, s->blk_idx);
+                                                                                ldc, s->n, alpha, s->blk_loss, s->blk_idx, ta);
   } else {
     eval_kernel<0><<<nblk, 256, 0, ctx->stream>>>(s->kcols, s->kcols_n, s->diag, s->avail, s->C, t, ldc, s->n, alpha, s->blk_loss,
-                                                 s->blk_idx);
+                                                 s->blk_idx, ta);
   }
-  pick_kernel<<<1, 256, 0, ctx->stream>>>(s->blk_loss, s->blk_idx, nblk, t, s->sc, commit, s->avail, s->sel, s->red);
-  ctx->launches += 2;
+  ctx->launches += 1;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
 }
@@ -869,6 +925,8 @@ int nnal_fi_release(nnal_ctx* ctx) {
                   s->red, s->win_sw, s->win_u, s->win_a, s->sel, s->blk_loss, s->blk_idx, s->sc, s->H, s->Xh, s->Xl, s->wq,
                   s->sub_rows, s->sub_wq, s->gj_M, s->gj_R, s->gj_C, s->gj_D, s->gj_out};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (s->ticket) cudaFree(s->ticket);
+  if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); cudaEventDestroy(s->ev_kss); cudaEventDestroy(s->ev_inv); }
   delete s;
   ctx->fi_state = nullptr;
   return NNAL_OK;
@@ -961,6 +1019,9 @@ extern "C" int nnal_fi_begin(nnal_ctx* ctx, int64_t k, double delta) {
   if (k > 4096) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "greedy FI selection supports k <= 4096");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   State* s = (State*)ctx->fi_state;
+  if (s->side) CUDA_TRY(ctx, cudaStreamSynchronize(s->side));
+  s->inv_ready_for = -1;
+  s->k_run = k;
   s->delta = delta;
   NNAL_TRY(fi::alloc_greedy(ctx, s, std::max<int64_t>(k, 1)));
   if (s->n) CUDA_TRY(ctx, cudaMemsetAsync(s->avail, 1, (size_t)s->n, ctx->stream));
@@ -972,13 +1033,12 @@ extern "C" int nnal_fi_greedy(nnal_ctx* ctx, int64_t k, double delta, int64_t* s
   NNAL_TRY(nnal_fi_begin(ctx, k, delta));
   State* s = (State*)ctx->fi_state;
   if (k > s->n) k = s->n;
+  s->k_run = k;
   if (k == 0) return NNAL_OK;
   prof_begin(ctx, NNAL_PROF_FI_GREEDY);
   for (int t = 0; t < (int)k; ++t) {
-    NNAL_TRY(fi::step_select(ctx, s, t, 1));
-    fi::copy_winner_kernel<<<8, 256, 0, ctx->stream>>>(s->U, s->A, s->R(), s->sw, s->diag, s->kcols, s->kcols_n, &s->sc->best_idx, t,
-                                                      s->d, s->dp, s->win_u, s->win_a, s->win_sw, s->kss, s->kcap);
-    ctx->launches++;
+    NNAL_TRY(fi::step_select(ctx, s, t, 1, 1));           // inverse (side stream), evaluation, arg-min, winner copy, K_SS row
+    NNAL_TRY(fi::invert_async(ctx, s, t + 1));            // next step's inverse overlaps this step's kernel column
     NNAL_TRY(fi::step_column(ctx, s, t));
   }
   prof_end(ctx);
@@ -1005,7 +1065,7 @@ extern "C" int nnal_fi_step_local_best(nnal_ctx* ctx, int64_t step, double* loss
     NNAL_TRY(fi::step_select(ctx, s, (int)step, 0));
   } else {
     // a rank without candidates still needs tr C of the shared winners' system
-    if (step > 0) NNAL_TRY(fi::run_invert(ctx, s, (int)step));
+    NNAL_TRY(fi::need_invert(ctx, s, (int)step));
   }
   fi::DevScalars h;
   CUDA_TRY(ctx, cudaMemcpyAsync(&h, s->sc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1108,7 +1168,7 @@ extern "C" int nnal_fi_step_pack(nnal_ctx* ctx, int64_t step, void* d_msg) {
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const int t = (int)step;
   if (s->n > 0) NNAL_TRY(fi::step_select(ctx, s, t, 0));
-  else if (t > 0) NNAL_TRY(fi::run_invert(ctx, s, t));
+  else NNAL_TRY(fi::need_invert(ctx, s, t));
   fi::pack_msg_kernel<<<8, 256, 0, ctx->stream>>>(s->U, s->A, s->R(), s->use_gids ? s->gids : nullptr, s->sw, s->diag, s->kcols,
                                                  s->kcols_n, s->sc, t, (int)s->kcap, s->d, s->dp, s->n > 0 ? 1 : 0,
                                                  (unsigned char*)d_msg);
@@ -1130,6 +1190,7 @@ extern "C" int nnal_fi_step_apply_gathered(nnal_ctx* ctx, int64_t step, const vo
                                                    s->sc, s->avail, s->win_u, s->nl == 2 ? s->win_a : nullptr, s->win_sw, s->kss,
                                                    s->sel, s->red);
   ctx->launches++;
+  NNAL_TRY(fi::invert_async(ctx, s, t + 1));
   NNAL_TRY(fi::step_column(ctx, s, t));
   return NNAL_OK;
 }
