@@ -278,6 +278,16 @@ int nnal_sdp_from_shrunk(nnal_ctx* ctx, const double* g, const double* p1, int64
                          int64_t max_iter, double gamma, double* q_out, double* t_out, double* obj_out, double* gap_out,
                          int64_t* iters_out);
 
+/* ---- last-layer influence recursion ---------------------------------------------------------- */
+/* Replaces PW_NNAL.stoch_approx_IF (PW_NNAL.py:851-881) with NN.LLFC_grads / NN.LLFC_hess (NN.py:874-955): V_0 = G,
+ * V_{t+1} = (G + V_t) - H_t V_t / scale for t < T, where column i of G is the last-layer log-loss gradient of pool sample i
+ * at label labels[i], [(e_y - pi) (x) u ; (e_y - pi)], and H_t = -LLFC_hess of training sample t = (diag pi - pi pi^T) (x)
+ * [u;1][u;1]^T (the iteration's random draw: the caller passes the factors in iteration order).  Factored on the device:
+ * the ((d+1)c)^2 Hessian is never formed.  pool_post [c][n], pool_U [n][d], tr_post [T][c], tr_U [T][d] float32 (what
+ * model.posteriors / model.feature_layer return); V_out [(d+1)c][n] float64, rows = W (class-major, a*d+k) then biases. */
+int nnal_if_lissa(nnal_ctx* ctx, int64_t n, int c, int d, const float* pool_post, const float* pool_U, const int64_t* labels,
+                  int64_t T, const float* tr_post, const float* tr_U, double scale, double* V_out);
+
 /* ---- representativeness queries over the feature layer ------------------------------- */
 /* Rows = the samples of the current pool pass (nnal_pool_begin keep >= 1; feature width multiple of 8).
  * 'rep-entropy' (NNAL.py:466-523, PW_NNAL.py:284-351): cols [B][d] = feature rows of the B most uncertain samples

@@ -34,6 +34,7 @@ class CNN(object):
             self.dropout_layers, self.dropout_rate = [], 1.
         self.probes = list(probes)
         self.keep_prob = _Placeholder('keep_prob')
+        self.x = _Placeholder('x')             # key of the patches in a reference-style feed_dict ({model.x: patches})
         self.var_dict = {}
         self.grad_layers = []
         self._version = 0
@@ -192,3 +193,57 @@ def create_PW1(nclass, dropout_rate=1., learning_rate=None, optimizer_name=None,
                 feature_layer=len(d) - 2, dropout=[[6, 7, 8], dropout_rate], probes=[5])
     model.get_gradients()
     return model
+
+
+def _last_layer_factors(model, sess, feed_dict):
+    """posteriors [c,n] and feature_layer [d,n] (float32, the layouts of ``sess.run(model.posteriors / feature_layer)``,
+    NN.py:184-188, 173-176) of the samples fed as ``feed_dict[model.x]`` -- one forward pass on the device."""
+    from .engine import get_engine
+    x = np.asarray(feed_dict[model.x], dtype=np.float32)
+    eng = get_engine()
+    eng.set_model(model, sess)
+    n = x.shape[0]
+    eng.pool_begin(n, 1)
+    eng.pool_eval_images(x, 0)
+    post = eng.pool_posteriors()
+    U = eng.pool_feature_rows(np.arange(n, dtype=np.int64)).T
+    return post, np.ascontiguousarray(U)
+
+
+def LLFC_grads(model, sess, feed_dict, labels=None):
+    """NN.LLFC_grads (NN.py:905-955): gradients of the log-loss w.r.t. the last FC layer, ``[(e_y - pi) (x) u ; (e_y - pi)]``
+    as a ``((d+1)c, n)`` matrix (rows: W class-major, then the biases).  ``labels`` None: the model's own predictions are used
+    and returned as well (:928-931, 951-953).  The forward pass runs on the device; the assembly is the reference's NumPy
+    (including its float32 ``pi * u`` product)."""
+    pies, U = _last_layer_factors(model, sess, feed_dict)
+    c, n = pies.shape
+    d = U.shape[0]
+    rep_U = np.tile(U, (c, 1))
+    pies_dot_U = np.repeat(pies, d, axis=0) * rep_U
+    flag = labels is None
+    if flag:
+        labels = np.argmax(pies, axis=0)
+    hot_labels = np.zeros((c, n))
+    for j in range(c):
+        hot_labels[j, np.asarray(labels) == j] = 1
+    dJ_dW = np.repeat(hot_labels, d, axis=0) * rep_U - pies_dot_U
+    dJ_db = hot_labels - pies
+    G = np.concatenate((dJ_dW, dJ_db), axis=0)
+    return (G, labels) if flag else G
+
+
+def LLFC_hess(model, sess, feed_dict):
+    """NN.LLFC_hess (NN.py:874-903): explicit ``((d+1)c)^2`` Hessian of the soft-max loss w.r.t. the last FC layer for ONE
+    sample, ``[[kron(A,uu^T), kron(A,u)],[kron(A,u^T), A]]`` with ``A = -(diag pi - pi pi^T)``.  Kept for callers that want
+    the matrix (537 MB at PW1); the query / influence paths use its factored form and never build it."""
+    pi, u = _last_layer_factors(model, sess, feed_dict)
+    d = u.shape[0]
+    c = pi.shape[0]
+    repM = np.repeat(pi, c, axis=1) - np.eye(c)
+    A = np.diag(pi[:, 0]) @ repM.T
+    H = np.zeros(((d + 1) * c, (d + 1) * c))
+    H[:c * d, :c * d] = np.kron(A, np.outer(u, u))
+    H[:c * d, c * d:] = np.kron(A, u)
+    H[c * d:, :c * d] = np.kron(A, u.T)
+    H[c * d:, c * d:] = A
+    return H

@@ -261,3 +261,29 @@ def query_multimg(expr, model, sess, all_padded_imgs, pool_inds, labeled_inds, m
         return rep.query_core_set_multimg(expr, model, sess, all_padded_imgs, pool_inds, labeled_inds)
 
     raise NotImplementedError('query method %r is not part of the replaced path' % method_name)
+
+
+def stoch_approx_IF(model, sess, tr_patches, pool_patches, max_iter, scale=50):
+    """PW_NNAL.stoch_approx_IF (PW_NNAL.py:851-881): stochastic approximation of the pool samples' influence through the
+    last FC layer.  ``grads`` = NN.LLFC_grads of the pool at its predicted (weak) labels; ``V_0 = grads``; per iteration a
+    random training patch ``np.random.randint(ntr)`` (NumPy's global generator, one draw per iteration as upstream, :873) and
+    ``V <- grads + V - H V / scale`` with ``H = -NN.LLFC_hess`` of it.  Returns ``(V_t [(d+1)c, n], weak_labels)``.
+
+    The pool and the drawn training patches go through ONE batched forward pass each on the device, and the recursion runs
+    there in factored form (``nnal_if_lissa``): the reference builds a ((d+1)c)^2 Hessian per iteration."""
+    from .NN import _last_layer_factors
+    from .engine import get_engine
+    tr_patches = np.asarray(tr_patches)
+    ntr = tr_patches.shape[0]
+    pool_post, pool_U = _last_layer_factors(model, sess, {model.x: pool_patches})
+    weak_labels = np.argmax(pool_post, axis=0)
+    draws = np.array([np.random.randint(ntr) for _ in range(int(max_iter))], dtype=np.int64)
+    uniq, inv = np.unique(draws, return_inverse=True)
+    if len(uniq):
+        tp, tU = _last_layer_factors(model, sess, {model.x: tr_patches[uniq]})
+        tr_post, tr_U = tp.T[inv], tU.T[inv]
+    else:
+        tr_post = np.zeros((0, pool_post.shape[0]), dtype=np.float32)
+        tr_U = np.zeros((0, pool_U.shape[0]), dtype=np.float32)
+    V = get_engine().if_lissa(pool_post, pool_U.T, weak_labels, tr_post, tr_U, float(scale))
+    return V, weak_labels

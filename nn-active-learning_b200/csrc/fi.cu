@@ -69,10 +69,7 @@ struct State {
   int blk_cap = 0;
   DevScalars* sc = nullptr;
   unsigned int* ticket = nullptr;        // last-block election of the fused eval + pick kernel
-  // the t x t inverse of step t+1 runs on a side stream while the (memory-bound) kernel column of step t is computed
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_kss = nullptr, ev_inv = nullptr;
-  int inv_ready_for = -1;                // step whose inverse has been enqueued on the side stream (-1: none)
+  int inv_ready_for = -1;                // step whose inverse was computed by CTA 0 of the previous column kernel (-1: none)
   int64_t k_run = 0;                     // number of steps of the current selection (nnal_fi_begin)
   // Gram
   float* H = nullptr;
@@ -159,14 +156,33 @@ __global__ void __launch_bounds__(256) setup_kernel(const float* __restrict__ U,
 
 // kernel column of the step-t winner against every local candidate:
 //   kcols[t][i] = sqrt(w_i) sqrt(w_win) <gbar_i, gbar_win>
-__global__ void __launch_bounds__(256) column_kernel(const float* __restrict__ U, const float* __restrict__ A,
-                                                      const int64_t* __restrict__ rows, const double* __restrict__ sw,
-                                                      const float* __restrict__ beta2, const float* __restrict__ wu,
-                                                      const float* __restrict__ wa, const double* __restrict__ wsw,
-                                                      int64_t n, int d, int dp, int nl, double* __restrict__ kcol) {
+//
+// CTA 0 does not take candidates: it inverts the winners' system of the NEXT step, C = ((t+2) delta I + K_SS[0:t+1])^-1,
+// which only needs the K_SS row the previous kernel wrote.  The inversion is a latency-bound single-CTA job (one barrier per
+// pivot, ~70 us at t = 100) and the column is a bandwidth-bound pass over every candidate's factor rows (~60 us at 10k
+// candidates): run as one launch they overlap, and CTA 0 being dispatched first guarantees it an SM (a separate stream does
+// not: the column's CTAs fill every SM for the whole kernel).
+struct InvArgs { const double* kss; int64_t kss_ld; int t; double alpha; double* C; int ldc; DevScalars* sc; };
+template <int RT>
+__device__ __forceinline__ void invert_reg_body(const double* __restrict__ kss, int64_t kss_ld, int t, double alpha,
+                                                double* __restrict__ Cout, int ldc, DevScalars* sc);
+
+__global__ void __launch_bounds__(1024) column_kernel(const float* __restrict__ U, const float* __restrict__ A,
+                                                       const int64_t* __restrict__ rows, const double* __restrict__ sw,
+                                                       const float* __restrict__ beta2, const float* __restrict__ wu,
+                                                       const float* __restrict__ wa, const double* __restrict__ wsw,
+                                                       int64_t n, int d, int dp, int nl, double* __restrict__ kcol, InvArgs inv) {
+  if (blockIdx.x == 0) {
+    if (inv.t >= 1) {
+      if (inv.t <= 32) invert_reg_body<1>(inv.kss, inv.kss_ld, inv.t, inv.alpha, inv.C, inv.ldc, inv.sc);
+      else if (inv.t <= 64) invert_reg_body<2>(inv.kss, inv.kss_ld, inv.t, inv.alpha, inv.C, inv.ldc, inv.sc);
+      else invert_reg_body<4>(inv.kss, inv.kss_ld, inv.t, inv.alpha, inv.C, inv.ldc, inv.sc);
+    }
+    return;
+  }
   const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t warp = ((int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)(gridDim.x - 1) * blockDim.x) >> 5;
   const double s_w = *wsw;
   for (int64_t i = warp; i < n; i += nwarps) {
     const int64_t r = rows ? rows[i] : i;
@@ -180,8 +196,8 @@ __global__ void __launch_bounds__(256) column_kernel(const float* __restrict__ U
 // elements M[ty+32a][tx+32b]; per pivot the owners publish row p and column p through (double-buffered) shared
 // memory: one barrier per pivot.  Writes C (row stride ldc, zero padded) and tr C.
 template <int RT>
-__global__ void __launch_bounds__(1024) invert_reg_kernel(const double* __restrict__ kss, int64_t kss_ld, int t, double alpha,
-                                                           double* __restrict__ Cout, int ldc, DevScalars* sc) {
+__device__ __forceinline__ void invert_reg_body(const double* __restrict__ kss, int64_t kss_ld, int t, double alpha,
+                                                double* __restrict__ Cout, int ldc, DevScalars* sc) {
   __shared__ double rowp[2][32 * RT], colp[2][32 * RT];
   __shared__ double red[32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -255,6 +271,12 @@ __global__ void __launch_bounds__(1024) invert_reg_kernel(const double* __restri
     for (int q = 0; q < 32; ++q) sacc += red[q];
     sc->trC = sacc;
   }
+}
+
+template <int RT>
+__global__ void __launch_bounds__(1024) invert_reg_kernel(const double* __restrict__ kss, int64_t kss_ld, int t, double alpha,
+                                                           double* __restrict__ Cout, int ldc, DevScalars* sc) {
+  invert_reg_body<RT>(kss, kss_ld, t, alpha, Cout, ldc, sc);
 }
 
 // C = (alpha I + K_SS[0:t,0:t])^-1 by in-place Gauss-Jordan (SPD: no pivoting), one CTA, float64.
@@ -462,9 +484,32 @@ __global__ void __launch_bounds__(256) eval_kernel(const double* __restrict__ kc
   const long long i = s_win;
   if (i < 0) return;
   const int64_t row = ta.rows ? ta.rows[i] : i;
-  for (int k = threadIdx.x; k < ta.d; k += 256) ta.win_u[k] = ta.U[row * ta.d + k];
-  if (ta.A)
-    for (int k = threadIdx.x; k < ta.dp; k += 256) ta.win_a[k] = ta.A[row * ta.dp + k];
+  // one CTA copies the winner's factor rows: keep many 16-byte loads in flight per thread (a dependent load/store loop
+  // of 32 iterations costs 30 us here)
+  auto copy_row = [&](const float* __restrict__ src, float* __restrict__ dst, int len) {
+    if ((len & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      const int n4 = len >> 2;
+      for (int k0 = 0; k0 < n4; k0 += 256 * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = k0 + j * 256 + threadIdx.x;
+          if (k < n4) v[j] = s4[k];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = k0 + j * 256 + threadIdx.x;
+          if (k < n4) d4[k] = v[j];
+        }
+      }
+    } else {
+      for (int k = threadIdx.x; k < len; k += 256) dst[k] = src[k];
+    }
+  };
+  copy_row(ta.U + row * ta.d, ta.win_u, ta.d);
+  if (ta.A) copy_row(ta.A + row * ta.dp, ta.win_a, ta.dp);
   for (int a = threadIdx.x; a <= t; a += 256) {
     const double v = a < t ? kcols[(int64_t)a * kn + i] : diag[i];
     ta.kss[(int64_t)t * ta.kss_ld + a] = v;
@@ -810,8 +855,8 @@ static int alloc_greedy(nnal_ctx* ctx, State* s, int64_t k) {
 }
 
 // C = ((t+1) delta I + K_SS[0:t,0:t])^-1 and its trace (t >= 1)
-static int run_invert(nnal_ctx* ctx, State* s, int t, cudaStream_t stream = nullptr) {
-  if (!stream) stream = ctx->stream;
+static int run_invert(nnal_ctx* ctx, State* s, int t) {
+  cudaStream_t stream = ctx->stream;
   const double alpha = (double)(t + 1) * s->delta;
   const int ldc = (t + 7) / 8 * 8;
   if (t <= 32) {
@@ -836,28 +881,10 @@ static int run_invert(nnal_ctx* ctx, State* s, int t, cudaStream_t stream = null
   return NNAL_OK;
 }
 
-// K_SS has just been extended by row/column t-1 on the main stream: start the inverse of step t on the side stream so that
-// it overlaps the kernel column of step t-1 (a memory-bound pass over all candidates that does not touch K_SS or C).
-static int invert_async(nnal_ctx* ctx, State* s, int t) {
-  if (t < 1 || t >= s->k_run) return NNAL_OK;
-  if (!s->side) {
-    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
-    CUDA_TRY(ctx, cudaEventCreateWithFlags(&s->ev_kss, cudaEventDisableTiming));
-    CUDA_TRY(ctx, cudaEventCreateWithFlags(&s->ev_inv, cudaEventDisableTiming));
-  }
-  CUDA_TRY(ctx, cudaEventRecord(s->ev_kss, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamWaitEvent(s->side, s->ev_kss, 0));
-  NNAL_TRY(run_invert(ctx, s, t, s->side));
-  CUDA_TRY(ctx, cudaEventRecord(s->ev_inv, s->side));
-  s->inv_ready_for = t;
-  return NNAL_OK;
-}
-
-// the inverse of step t: already in flight on the side stream (wait for it) or computed here
+// the inverse of step t: already computed by CTA 0 of the previous step's column kernel, or computed here
 static int need_invert(nnal_ctx* ctx, State* s, int t) {
   if (t < 1) return NNAL_OK;
   if (s->inv_ready_for == t) {
-    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_inv, 0));
     s->inv_ready_for = -1;
     return NNAL_OK;
   }
@@ -899,10 +926,18 @@ static int step_select(nnal_ctx* ctx, State* s, int t, int commit, int copy = 0)
 // the winner slot is filled and K_SS extended: compute kernel column t over the local candidates
 static int step_column(nnal_ctx* ctx, State* s, int t) {
   if (s->n > 0) {
-    column_kernel<<<warp_grid(ctx, s->n), 256, 0, ctx->stream>>>(s->U, s->A, s->R(), s->sw, s->beta2, s->win_u,
-                                                                s->nl == 2 ? s->win_a : nullptr, s->win_sw, s->n, s->d, s->dp,
-                                                                s->nl, s->kcols + (int64_t)t * s->kcols_n);
+    InvArgs inv;
+    const int tn = t + 1;                                   // the next step's system: K_SS rows 0..t are complete
+    const bool fuse = tn < s->k_run && tn <= 128;
+    inv.kss = s->kss; inv.kss_ld = s->kcap; inv.t = fuse ? tn : 0; inv.alpha = (double)(tn + 1) * s->delta;
+    inv.C = s->C; inv.ldc = (tn + 7) / 8 * 8; inv.sc = s->sc;
+    // 32 warps per CTA, one candidate per warp and pass; at most 2 CTAs per SM
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((s->n + 31) / 32, (int64_t)ctx->sm_count * 4));
+    column_kernel<<<(int)blocks + 1, 1024, 0, ctx->stream>>>(s->U, s->A, s->R(), s->sw, s->beta2, s->win_u,
+                                                            s->nl == 2 ? s->win_a : nullptr, s->win_sw, s->n, s->d, s->dp,
+                                                            s->nl, s->kcols + (int64_t)t * s->kcols_n, inv);
     ctx->launches++;
+    if (fuse) s->inv_ready_for = tn;
   }
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
@@ -926,7 +961,6 @@ int nnal_fi_release(nnal_ctx* ctx) {
                   s->sub_rows, s->sub_wq, s->gj_M, s->gj_R, s->gj_C, s->gj_D, s->gj_out};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->ticket) cudaFree(s->ticket);
-  if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); cudaEventDestroy(s->ev_kss); cudaEventDestroy(s->ev_inv); }
   delete s;
   ctx->fi_state = nullptr;
   return NNAL_OK;
@@ -1019,7 +1053,6 @@ extern "C" int nnal_fi_begin(nnal_ctx* ctx, int64_t k, double delta) {
   if (k > 4096) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "greedy FI selection supports k <= 4096");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   State* s = (State*)ctx->fi_state;
-  if (s->side) CUDA_TRY(ctx, cudaStreamSynchronize(s->side));
   s->inv_ready_for = -1;
   s->k_run = k;
   s->delta = delta;
@@ -1037,9 +1070,8 @@ extern "C" int nnal_fi_greedy(nnal_ctx* ctx, int64_t k, double delta, int64_t* s
   if (k == 0) return NNAL_OK;
   prof_begin(ctx, NNAL_PROF_FI_GREEDY);
   for (int t = 0; t < (int)k; ++t) {
-    NNAL_TRY(fi::step_select(ctx, s, t, 1, 1));           // inverse (side stream), evaluation, arg-min, winner copy, K_SS row
-    NNAL_TRY(fi::invert_async(ctx, s, t + 1));            // next step's inverse overlaps this step's kernel column
-    NNAL_TRY(fi::step_column(ctx, s, t));
+    NNAL_TRY(fi::step_select(ctx, s, t, 1, 1));           // evaluation, arg-min, winner copy, K_SS row: one launch
+    NNAL_TRY(fi::step_column(ctx, s, t));                 // kernel column of the winner + (CTA 0) the next step's inverse
   }
   prof_end(ctx);
   std::vector<double> red((size_t)k);
@@ -1190,7 +1222,6 @@ extern "C" int nnal_fi_step_apply_gathered(nnal_ctx* ctx, int64_t step, const vo
                                                    s->sc, s->avail, s->win_u, s->nl == 2 ? s->win_a : nullptr, s->win_sw, s->kss,
                                                    s->sel, s->red);
   ctx->launches++;
-  NNAL_TRY(fi::invert_async(ctx, s, t + 1));
   NNAL_TRY(fi::step_column(ctx, s, t));
   return NNAL_OK;
 }

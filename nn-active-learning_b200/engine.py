@@ -571,6 +571,26 @@ class Engine(object):
                                                 float(gamma), _ptr(q), _ptr(t), C.byref(obj), C.byref(gap), C.byref(it)))
         return {'q': q, 't': t, 'objective': obj.value, 'gap': gap.value, 'iterations': it.value}
 
+    def if_lissa(self, pool_post, pool_U, labels, tr_post, tr_U, scale):
+        """Last-layer influence recursion (``nnal_if_lissa``): ``pool_post`` [c,n], ``pool_U`` [n,d], ``labels`` [n],
+        ``tr_post`` [T,c], ``tr_U`` [T,d] in iteration order -> V [(d+1)c, n] float64."""
+        pool_post = np.ascontiguousarray(pool_post, dtype=np.float32)
+        pool_U = np.ascontiguousarray(pool_U, dtype=np.float32)
+        labels = np.ascontiguousarray(labels, dtype=np.int64).ravel()
+        tr_post = np.ascontiguousarray(tr_post, dtype=np.float32)
+        tr_U = np.ascontiguousarray(tr_U, dtype=np.float32)
+        c, n = pool_post.shape
+        d = pool_U.shape[1]
+        T = tr_post.shape[0]
+        if pool_U.shape[0] != n or labels.size != n or tr_U.shape != (T, d) or (T and tr_post.shape[1] != c):
+            raise ValueError('inconsistent factor shapes')
+        V = np.empty(((d + 1) * c, n), dtype=np.float64)
+        self.h2d_bytes += pool_post.nbytes + pool_U.nbytes + labels.nbytes + tr_post.nbytes + tr_U.nbytes
+        self.d2h_bytes += V.nbytes
+        self._chk(self.lib.nnal_if_lissa(self.h, n, c, d, _ptr(pool_post), _ptr(pool_U), _ptr(labels), T,
+                                         _ptr(tr_post) if T else None, _ptr(tr_U) if T else None, float(scale), _ptr(V)))
+        return V
+
     def fi_begin(self, k, delta):
         self._chk(self.lib.nnal_fi_begin(self.h, int(k), float(delta)))
 

@@ -690,6 +690,30 @@ def main():
     assert rH.shape == oH.shape and np.allclose(rH, oH, rtol=1e-13, atol=0)
     print('LLFC_grads / LLFC_hess: oracle == reference (fake session)')
 
+    # ---- PW_NNAL.stoch_approx_IF (:851-881), UNMODIFIED over a fake session that answers posteriors / feature_layer /
+    # prediction for whatever patches it is fed: LiSSA recursion V <- grads + V - H V / scale through the last FC layer
+    r_all = O.forward(layers_w, w_w, pool_w, feature_layer=len(layers_w) - 2)
+
+    class IfModel(object):
+        x, keep_prob = 'x', 'keep_prob'
+        posteriors, feature_layer, prediction = 'posteriors', 'feature_layer', 'prediction'
+
+    class IfSess(object):
+        def run(self, var, feed_dict=None):
+            r = O.forward(layers_w, w_w, np.asarray(feed_dict['x']).astype(np.float32), feature_layer=len(layers_w) - 2)
+            return np.argmax(r['posteriors'], axis=0) if var == 'prediction' else r[var]
+    tr_x, pl_x = pool_w[:12], pool_w[40:47]
+    np.random.seed(31)
+    draws_if = [np.random.randint(12) for _ in range(25)]
+    np.random.seed(31)
+    rV, rlab_if = ref_pw.stoch_approx_IF(IfModel(), IfSess(), tr_x, pl_x, 25, 20)
+    oV, olab_if = O.stoch_approx_IF(r_all['posteriors'][:, 40:47], r_all['feature_layer'][:, 40:47], r_all['posteriors'][:, :12],
+                                    r_all['feature_layer'][:, :12], draws_if, 20.)
+    assert np.array_equal(rlab_if, olab_if) and rV.shape == oV.shape
+    assert np.allclose(rV, oV, rtol=1e-10, atol=1e-12 * np.abs(oV).max())
+    gold['if_V'], gold['if_labels'], gold['if_draws'] = rV, np.asarray(rlab_if), np.array(draws_if)
+    print('PW_NNAL.stoch_approx_IF: oracle == reference (fake session, seeded np.random)')
+
     np.savez_compressed(os.path.join(GOLD, 'reference_numpy_helpers.npz'), **gold)
     print('wrote', os.path.join(GOLD, 'reference_numpy_helpers.npz'))
 

@@ -23,7 +23,7 @@ from .nnal_oracle import forward, stable_topk, batch_eval, get_patches, normaliz
 __all__ = [
     'class_score_factors', 'explicit_class_gradients', 'shrink_gradient',
     'shrunk_class_gradients', 'gen_A_matrices', 'gen_A_matrices_multiclass',
-    'LLFC_grads', 'LLFC_hess', 'FC_gradnorms_batch', 'fi_trace_score',
+    'LLFC_grads', 'LLFC_hess', 'stoch_approx_IF', 'FC_gradnorms_batch', 'fi_trace_score',
     'mnist_fi_score', 'sdp_objective', 'fi_objective_direct', 'greedy_fi_direct',
     'fi_objective_dual', 'greedy_fi_dual_bruteforce', 'greedy_fi_rank1',
     'last_layers_kernel', 'last_layers_dim', 'weighted_gram', 'fi_objective_from_gram',
@@ -269,6 +269,21 @@ def LLFC_hess(pi, u):
     H[c * d:, :c * d] = np.kron(A, u.T)
     H[c * d:, c * d:] = A
     return H
+
+
+def stoch_approx_IF(pool_post, pool_U, tr_post, tr_U, draws, scale=50.):
+    """PW_NNAL.stoch_approx_IF (PW_NNAL.py:851-881): stochastic (LiSSA-style) approximation of the influence of the
+    pool samples through the last FC layer.  ``grads`` = LLFC_grads of the pool at its predicted (weak) labels (:861-866);
+    ``V_0 = grads``; per iteration one random training sample r_t (``draws[t]``; upstream ``np.random.randint(ntr)``,
+    :873), ``H = -LLFC_hess`` of it (:874-876), ``V_{t+1} = grads + V_t - H V_t / scale`` (:879).  ``pool_post`` [c,n],
+    ``pool_U`` [d,n] = model.posteriors / model.feature_layer of the pool; ``tr_post`` [c,ntr], ``tr_U`` [d,ntr] those of the
+    training patches.  Returns (V [(d+1)c, n], weak labels [n]); dense, as written upstream."""
+    grads, weak = LLFC_grads(pool_post, pool_U)
+    V = grads
+    for r in draws:
+        H = -LLFC_hess(tr_post[:, r:r + 1], tr_U[:, r:r + 1])
+        V = grads + V - H @ V / scale
+    return V, weak
 
 
 def FC_gradnorms_batch(J, fc_inputs, fc_weights):
