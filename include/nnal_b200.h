@@ -271,6 +271,14 @@ int nnal_fi_shrunk_voxels(nnal_ctx* ctx, int subject, const int64_t* inds, int64
 int nnal_sdp_query_distribution(nnal_ctx* ctx, const double* A, int64_t n, int tau, double tol, int64_t max_iter,
                                 double gamma, double* q_out, double* t_out, double* obj_out, double* gap_out,
                                 int64_t* iters_out);
+/* NNAL_tools.SDP_query_distribution with lambda_ > 0 (NNAL_tools.py:625-644): objective sum_j t_j - lambda_ sum_i q_i |x_i|^2
+ * and the extra equalities X q = 0, X [d][n] (float64, row-major) = the zero-mean refined feature matrix ref_F of
+ * PW_NNAL.py:146-151 / NNAL.py:417-447 (d < n, d <= 4096).  Feasible multiplicative natural-gradient method on the device
+ * (every iterate satisfies q >= 0, sum q = 1, X q = 0 to rounding), stopped at the convexity certificate
+ * (max_i g_i - nu) / max(|objective|, tr M^-1) <= tol.  *obj_out = tr((sum q_i A_i)^-1) - lambda_ sum_i q_i |x_i|^2. */
+int nnal_sdp_query_distribution_reg(nnal_ctx* ctx, const double* A, int64_t n, int tau, double lambda_, const double* X, int d,
+                                    double tol, int64_t max_iter, double* q_out, double* t_out, double* obj_out, double* gap_out,
+                                    int64_t* iters_out);
 /* Same solver, with the binary A-matrices of PW_NNAL.gen_A_matrices (PW_NNAL.py:766-814) assembled on the device from
  * the shrunk gradients g [2][n][tau] and p1 [n] = P(class 1): p < 1e-6 -> only g0, p > 1-1e-6 -> only g1,
  * A_i = (1-p) g0 g0^T + p g1 g1^T + diag_load I (bit-identical to the host assembly); saves the n tau^2 upload. */

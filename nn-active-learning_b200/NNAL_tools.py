@@ -37,19 +37,20 @@ def shrink_gradient(grad, method, args=None):
 
 
 def SDP_query_distribution(A, lambda_, X_pool, k, tol=1e-4, max_iter=200000):
-    """NNAL_tools.SDP_query_distribution (NNAL_tools.py:612-659) for ``lambda_ == 0``: the query distribution
-    minimising ``tr((sum_i q_i A_i)^-1)`` over the simplex.  ``A`` is the list of tau x tau conditional FIs of
-    ``gen_A_matrices``.  Returns a dict shaped like cvxopt's ``solvers.sdp`` solution: ``soln['x']`` =
-    ``[q_1..q_n, t_1..t_tau]`` (callers slice ``soln['x'][:n]``, PW_NNAL.py:157), ``soln['status']`` = 'optimal' when
-    the duality certificate ``max_i tr(M^-1 A_i M^-1)/tr(M^-1) - 1`` of the returned q is at most ``2 tol`` (the loop
-    stops once the certificate of the previous iterate is below ``tol``; the value reported in ``soln['gap']`` is
+    """NNAL_tools.SDP_query_distribution (NNAL_tools.py:612-659): the query distribution minimising
+    ``tr((sum_i q_i A_i)^-1)`` over the simplex; with ``lambda_ > 0`` the objective gains ``-lambda_ sum_i q_i |x_i|^2`` and
+    the constraints ``X_pool q = 0`` (:625-644; ``X_pool`` [d, n] = the zero-mean refined feature matrix).  ``A`` is the list
+    of tau x tau conditional FIs of ``gen_A_matrices``.  Returns a dict shaped like cvxopt's ``solvers.sdp`` solution:
+    ``soln['x']`` = ``[q_1..q_n, t_1..t_tau]`` (callers slice ``soln['x'][:n]``, PW_NNAL.py:157), ``soln['status']`` =
+    'optimal' when the duality certificate ``max_i tr(M^-1 A_i M^-1)/tr(M^-1) - 1`` of the returned q is at most ``2 tol`` (the
+    loop stops once the certificate of the previous iterate is below ``tol``; the value reported in ``soln['gap']`` is
     recomputed for the returned q and bounds the relative distance of the objective from the SDP optimum), else
-    'unknown'; plus 'primal objective', 'gap', 'iterations'.
-    The regularised variant (``lambda_ > 0``: ``-lambda sum q_i |f_i|^2`` with ``F q = 0``, :625-644) is not
-    part of the replaced path."""
-    if lambda_ > 0:
-        raise NotImplementedError('lambda_ > 0 (feature-regularised SDP, NNAL_tools.py:625-644) stays in the reference')
+    'unknown'; plus 'primal objective', 'gap', 'iterations'."""
     A = np.asarray(A, dtype=np.float64)
+    if lambda_ > 0:
+        r = get_engine().sdp_query_distribution_reg(A, lambda_, np.asarray(X_pool, dtype=np.float64), tol=tol,
+                                                    max_iter=min(int(max_iter), 50000))
+        return _soln(r, tol)
     r = get_engine().sdp_query_distribution(A, tol=tol, max_iter=max_iter)
     return _soln(r, tol)
 

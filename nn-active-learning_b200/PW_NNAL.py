@@ -287,3 +287,18 @@ def stoch_approx_IF(model, sess, tr_patches, pool_patches, max_iter, scale=50):
         tr_U = np.zeros((0, pool_U.shape[0]), dtype=np.float32)
     V = get_engine().if_lissa(pool_post, pool_U.T, weak_labels, tr_post, tr_U, float(scale))
     return V, weak_labels
+
+
+def refine_feature_matrix(F, B):
+    """PW_NNAL.refine_feature_matrix (PW_NNAL.py:819-849): rows of the feature matrix ``F`` [d, n] that make it full row-rank
+    with a moderate condition number -- the int(B/2) rows with the most positive entries, then the tail of that list is
+    dropped until the rank is full and until cond <= 1e6 (never below one row).  Host NumPy like upstream (the matrix is
+    B/2 x B at most); returns a copy."""
+    order = np.argsort(-np.sum(F > 0, axis=1))[:int(B / 2)]
+    while np.linalg.matrix_rank(F[order, :]) < len(order):
+        order = order[:-1]
+    while np.linalg.cond(F[order, :]) > 1e6:
+        order = order[:-1]
+        if len(order) == 1:
+            break
+    return F[order, :].copy()

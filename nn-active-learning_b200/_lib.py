@@ -101,6 +101,8 @@ SIGNATURES = {
     'nnal_if_lissa': (C.c_int, [c_vp, C.c_int64, C.c_int, C.c_int, c_vp, c_vp, c_vp, C.c_int64, c_vp, c_vp, C.c_double, c_vp]),
     'nnal_sdp_query_distribution': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, C.c_double, C.c_int64, C.c_double, c_vp,
                                               c_vp, c_f64p, c_f64p, c_i64p]),
+    'nnal_sdp_query_distribution_reg': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, C.c_double, c_vp, C.c_int, C.c_double, C.c_int64,
+                                                  c_vp, c_vp, c_f64p, c_f64p, c_i64p]),
     'nnal_sdp_from_shrunk': (C.c_int, [c_vp, c_vp, c_vp, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_double,
                                        c_vp, c_vp, c_f64p, c_f64p, c_i64p]),
 }

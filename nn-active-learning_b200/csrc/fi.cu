@@ -85,6 +85,8 @@ struct State {
   // float64 workspace of nnal_fi_gram_solve: M (np x np), row panel, column panel, inverted pivot block, results
   double *gj_M = nullptr, *gj_R = nullptr, *gj_C = nullptr, *gj_D = nullptr, *gj_out = nullptr;
   int gj_np = 0;
+  double *gj_R2 = nullptr, *gj_C2 = nullptr, *gj_D2 = nullptr;       // panels of nnal_gj64_invert (caller-owned matrix)
+  int gj_aux_np = 0;
 };
 
 static State* get(nnal_ctx* ctx) {
@@ -958,7 +960,7 @@ int nnal_fi_release(nnal_ctx* ctx) {
   State* s = (State*)ctx->fi_state;
   void* ptrs[] = {s->gids, s->rows, s->ownU, s->ownA, s->w, s->sw, s->diag, s->avail, s->beta2, s->kcols, s->kss, s->C, s->inv_ws,
                   s->red, s->win_sw, s->win_u, s->win_a, s->sel, s->blk_loss, s->blk_idx, s->sc, s->H, s->Xh, s->Xl, s->wq,
-                  s->sub_rows, s->sub_wq, s->gj_M, s->gj_R, s->gj_C, s->gj_D, s->gj_out};
+                  s->sub_rows, s->sub_wq, s->gj_M, s->gj_R, s->gj_C, s->gj_D, s->gj_out, s->gj_R2, s->gj_C2, s->gj_D2};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->ticket) cudaFree(s->ticket);
   delete s;
@@ -1391,6 +1393,41 @@ extern "C" int nnal_fi_gram_solve(nnal_ctx* ctx, double delta, double scale, con
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   *tr_out = out[0];
   if (ratio_out) *ratio_out = d_G2 ? out[1] : 0.0;
+  return NNAL_OK;
+}
+
+// In-place inverse of a symmetric positive-definite float64 matrix M (np x np, np a multiple of 64, row-major) by the same
+// blocked Gauss-Jordan (used by the regularised SDP solver in sdp.cu for its d_f x d_f normal equations).
+int nnal_gj64_invert(nnal_ctx* ctx, double* M, int np) {
+  const int B = fi::GJ_B;
+  if (np <= 0 || np % B) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "gj64: size must be a positive multiple of 64");
+  State* s = fi::get(ctx);
+  if (!s->sc) {
+    CUDA_TRY(ctx, cudaMalloc(&s->sc, sizeof(fi::DevScalars)));
+    CUDA_TRY(ctx, cudaMemsetAsync(s->sc, 0, sizeof(fi::DevScalars), ctx->stream));
+    CUDA_TRY(ctx, cudaMalloc(&s->ticket, 64));
+    CUDA_TRY(ctx, cudaMemsetAsync(s->ticket, 0, 64, ctx->stream));
+  }
+  if (s->gj_aux_np < np) {
+    NNAL_TRY(fi::ensure(ctx, s->gj_R2, 0, (size_t)B * np));
+    NNAL_TRY(fi::ensure(ctx, s->gj_C2, 0, (size_t)np * B));
+    NNAL_TRY(fi::ensure(ctx, s->gj_D2, 0, (size_t)B * B));
+    s->gj_aux_np = np;
+  }
+  static bool attr_gj2 = false;
+  if (!attr_gj2) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(fi::gj_panels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fi::GJ_SMEM));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(fi::gj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fi::GJ_SMEM));
+    attr_gj2 = true;
+  }
+  const int P = np / B;
+  for (int p = 0; p < P; ++p) {
+    fi::invert_reg_kernel<2><<<1, 1024, 0, ctx->stream>>>(M + (size_t)p * B * np + (size_t)p * B, np, B, 0.0, s->gj_D2, B, s->sc);
+    fi::gj_panels_kernel<<<P, 256, fi::GJ_SMEM, ctx->stream>>>(M, np, p, s->gj_D2, s->gj_R2, s->gj_C2);
+    fi::gj_update_kernel<<<dim3(P, P), 256, fi::GJ_SMEM, ctx->stream>>>(M, np, p, s->gj_D2, s->gj_R2, s->gj_C2);
+  }
+  ctx->launches += 3 * P;
+  CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
 }
 

@@ -296,4 +296,5 @@ int nnal_sdp_release(nnal_ctx*);
 int nnal_upload_stats(nnal_ctx*, const double* stats, int m, int norm_mode, double** d_stats);
 int nnal_check_gather_args(nnal_ctx*, int subject, int64_t n, int d1, int d2, int d3, const Volume** vout);
 // fi.cu
+int nnal_gj64_invert(nnal_ctx*, double* M, int np);      // in-place inverse of an SPD float64 matrix, np % 64 == 0
 int nnal_k_fi_trace_scores(nnal_ctx*, const float* post, int c, int64_t n, const float* feat, int d, double* score);

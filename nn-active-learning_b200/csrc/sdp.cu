@@ -20,6 +20,8 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
+#include <vector>
 
 namespace cg = cooperative_groups;
 
@@ -458,6 +460,336 @@ static int sdp_solve(nnal_ctx* ctx, int mode, const double* src, const double* p
   if (obj_out) *obj_out = hres[0];
   if (gap_out) *gap_out = hres[1];
   if (t_out) for (int j = 0; j < tau; ++j) t_out[j] = hres[2 + j];
+  if (iters_out) *iters_out = it;
+  return NNAL_OK;
+}
+
+// =====================================================================================================================
+// lambda_ > 0: the feature-regularised programme of NNAL_tools.SDP_query_distribution (NNAL_tools.py:625-644)
+//     minimise  Phi(q) = tr(M(q)^-1) - lambda c^T q,  c_i = |x_i|^2      s.t.  q >= 0,  1^T q = 1,  X q = 0
+// (X = the zero-mean refined feature matrix [d][n]; upstream's vector c :630-632 and equalities A x = b :635-644).
+// Multiplicative natural-gradient method that keeps every iterate feasible (oracle/fi_oracle.py:sdp_solve_reg):
+//     h = d + lambda c,  d_i = <M^-2, A_i>;   (X diag(q) X^T) mu = X (q.h);   g = h - X^T mu;   nu = q.g;
+//     q_i <- q_i (1 + theta (g_i / nu - 1)),   theta in (0,1] keeps q > 0 and is halved until Phi decreases (Armijo);
+//     certificate  Phi(q) - Phi* <= max_i g_i - nu  (convexity; valid for any mu).
+// The O(n d^2) weighted normal equations and the O(n tau^2) sums run on the device (float64), the tau x tau algebra and
+// the line search -- M(q + theta D) = M(q) + theta M(D) is linear -- on the host.
+namespace reg {
+
+constexpr int RT = 256;
+
+// out[u] = sum_i w_i At[u][i] (u < Tu),  out[Tu] = sum_i w_i c_i,  out[Tu+1] = sum_i w_i      (one CTA per entry)
+__global__ void __launch_bounds__(RT) msum_kernel(const double* __restrict__ At, const double* __restrict__ w, const double* __restrict__ c,
+                                                 int64_t n, int Tu, double* __restrict__ out) {
+  const int u = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += RT) {
+    const double v = u < Tu ? At[(int64_t)u * n + i] : (u == Tu ? c[i] : 1.0);
+    acc = fma(w[i], v, acc);
+  }
+  acc = warp_sum(acc);
+  __shared__ double sh[RT / 32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < RT / 32; ++k) t += sh[k];
+    out[u] = t;
+  }
+}
+
+__global__ void norms_kernel(const double* __restrict__ X, int64_t n, int d, double* __restrict__ c) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int a = 0; a < d; ++a) { const double v = X[(int64_t)a * n + i]; acc = fma(v, v, acc); }
+    c[i] = acc;
+  }
+}
+
+struct PArg { double P[SDP_MAX_TAU * (SDP_MAX_TAU + 1) / 2]; };
+
+// h_i = <M^-2, A_i> + lambda c_i  and  qh_i = q_i h_i
+__global__ void h_kernel(const double* __restrict__ At, const double* __restrict__ q, const double* __restrict__ c, int64_t n, int Tu,
+                         PArg pa, double lambda_, double* __restrict__ h, double* __restrict__ qh) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double d = 0.0;
+    for (int u = 0; u < Tu; ++u) d = fma(pa.P[u], At[(int64_t)u * n + i], d);
+    const double hv = d + lambda_ * c[i];
+    h[i] = hv;
+    qh[i] = q[i] * hv;
+  }
+}
+
+// W[a][b] = sum_i q_i X[a][i] X[b][i] (+ ridge on the diagonal, identity on the padding), 64 x 64 tile per CTA, float64
+__global__ void __launch_bounds__(256) wgram_kernel(const double* __restrict__ X, const double* __restrict__ q, int64_t n, int d, int np,
+                                                    double* __restrict__ W) {
+  __shared__ double Xa[32][65], Xb[32][65];
+  const int a0 = blockIdx.y * 64, b0 = blockIdx.x * 64;
+  if (b0 > a0) return;                                     // lower triangle; mirrored below
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  double acc[4][4] = {};
+  for (int64_t i0 = 0; i0 < n; i0 += 32) {
+    for (int e = tid; e < 64 * 32; e += 256) {
+      const int r = e >> 5, cidx = e & 31;
+      const int64_t i = i0 + cidx;
+      const double qi = i < n ? q[i] : 0.0;
+      Xa[cidx][r] = (a0 + r < d && i < n) ? X[(int64_t)(a0 + r) * n + i] * qi : 0.0;
+      Xb[cidx][r] = (b0 + r < d && i < n) ? X[(int64_t)(b0 + r) * n + i] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      double xa[4], xb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { xa[j] = Xa[k][4 * ty + j]; xb[j] = Xb[k][4 * tx + j]; }
+#pragma unroll
+      for (int ia = 0; ia < 4; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < 4; ++ib) acc[ia][ib] = fma(xa[ia], xb[ib], acc[ia][ib]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int ia = 0; ia < 4; ++ia)
+#pragma unroll
+    for (int ib = 0; ib < 4; ++ib) {
+      const int a = a0 + 4 * ty + ia, b = b0 + 4 * tx + ib;
+      double v = acc[ia][ib];
+      if (a >= d || b >= d) v = a == b ? 1.0 : 0.0;
+      W[(size_t)a * np + b] = v;
+      W[(size_t)b * np + a] = v;
+    }
+}
+
+__global__ void ridge_kernel(double* __restrict__ W, int d, int np, double rel) {
+  __shared__ double tr;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int a = 0; a < d; ++a) t += W[(size_t)a * np + a];
+    tr = t;
+  }
+  __syncthreads();
+  for (int a = threadIdx.x; a < d; a += blockDim.x) W[(size_t)a * np + a] += rel * tr / d;
+}
+
+// y[a] = sum_i X[a][i] v[i]   (one CTA per feature row)
+__global__ void __launch_bounds__(RT) xv_kernel(const double* __restrict__ X, const double* __restrict__ v, int64_t n, double* __restrict__ y) {
+  const int a = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += RT) acc = fma(X[(int64_t)a * n + i], v[i], acc);
+  acc = warp_sum(acc);
+  __shared__ double sh[RT / 32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < RT / 32; ++k) t += sh[k];
+    y[a] = t;
+  }
+}
+
+// mu = Winv rhs (one CTA per row)
+__global__ void __launch_bounds__(RT) mv_kernel(const double* __restrict__ Winv, int np, int d, const double* __restrict__ rhs, double* __restrict__ mu) {
+  const int a = blockIdx.x;
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < d; b += RT) acc = fma(Winv[(size_t)a * np + b], rhs[b], acc);
+  acc = warp_sum(acc);
+  __shared__ double sh[RT / 32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < RT / 32; ++k) t += sh[k];
+    mu[a] = t;
+  }
+}
+
+// g_i = h_i - sum_a X[a][i] mu_a;  per-CTA partials of  nu = q.g,  s2 = q.g^2,  gmax = max g
+__global__ void __launch_bounds__(RT) g_kernel(const double* __restrict__ X, const double* __restrict__ mu, const double* __restrict__ h,
+                                              const double* __restrict__ q, int64_t n, int d, double* __restrict__ g, double* __restrict__ part) {
+  double nu = 0.0, s2 = 0.0, gm = -1e300;
+  for (int64_t i = (int64_t)blockIdx.x * RT + threadIdx.x; i < n; i += (int64_t)gridDim.x * RT) {
+    double acc = 0.0;
+    for (int a = 0; a < d; ++a) acc = fma(X[(int64_t)a * n + i], mu[a], acc);
+    const double gv = h[i] - acc;
+    g[i] = gv;
+    nu = fma(q[i], gv, nu);
+    s2 = fma(q[i] * gv, gv, s2);
+    gm = fmax(gm, gv);
+  }
+  nu = warp_sum(nu); s2 = warp_sum(s2); gm = warp_max(gm);
+  __shared__ double sh[3][RT / 32];
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = nu; sh[1][threadIdx.x >> 5] = s2; sh[2][threadIdx.x >> 5] = gm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0, c = -1e300;
+    for (int k = 0; k < RT / 32; ++k) { a += sh[0][k]; b += sh[1][k]; c = fmax(c, sh[2][k]); }
+    part[3 * blockIdx.x] = a; part[3 * blockIdx.x + 1] = b; part[3 * blockIdx.x + 2] = c;
+  }
+}
+
+// D_i = q_i (g_i / nu - 1);  per-CTA minimum of r_i = g_i / nu - 1 over the live entries (q_i > 0)
+__global__ void __launch_bounds__(RT) delta_kernel(const double* __restrict__ q, const double* __restrict__ g, int64_t n, double nu,
+                                                  double* __restrict__ D, double* __restrict__ part) {
+  double rmin = 1e300;
+  for (int64_t i = (int64_t)blockIdx.x * RT + threadIdx.x; i < n; i += (int64_t)gridDim.x * RT) {
+    const double r = g[i] / nu - 1.0;
+    D[i] = q[i] * r;
+    if (q[i] > 0.0) rmin = fmin(rmin, r);
+  }
+  rmin = -warp_max(-rmin);
+  __shared__ double sh[RT / 32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = rmin;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 1e300;
+    for (int k = 0; k < RT / 32; ++k) m = fmin(m, sh[k]);
+    part[blockIdx.x] = m;
+  }
+}
+
+__global__ void axpy_kernel(double* __restrict__ q, const double* __restrict__ D, int64_t n, double theta) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    q[i] = fmax(fma(theta, D[i], q[i]), 0.0);
+}
+
+// host: inverse of the packed symmetric tau x tau matrix, trace, packed weights of <M^-2, .>; false if not positive definite
+static bool host_inverse(const double* Mp, int tau, double* Minv, double* P, double* phi) {
+  double m[SDP_MAX_TAU][SDP_MAX_TAU];
+  int u = 0;
+  for (int a = 0; a < tau; ++a)
+    for (int b = a; b < tau; ++b, ++u) m[a][b] = m[b][a] = Mp[u];
+  for (int k = 0; k < tau; ++k) {
+    if (!(m[k][k] > 0.0)) return false;
+    const double piv = 1.0 / m[k][k];
+    double row[SDP_MAX_TAU], col[SDP_MAX_TAU];
+    for (int j = 0; j < tau; ++j) { row[j] = m[k][j]; col[j] = m[j][k]; }
+    for (int a = 0; a < tau; ++a)
+      for (int b = 0; b < tau; ++b) {
+        if (a == k && b == k) m[a][b] = piv;
+        else if (a == k) m[a][b] = row[b] * piv;
+        else if (b == k) m[a][b] = -col[a] * piv;
+        else m[a][b] -= col[a] * row[b] * piv;
+      }
+  }
+  double t = 0.0;
+  for (int a = 0; a < tau; ++a) t += m[a][a];
+  *phi = t;
+  if (!(t == t) || t <= 0.0) return false;
+  u = 0;
+  for (int a = 0; a < tau; ++a)
+    for (int b = a; b < tau; ++b, ++u) {
+      double v = 0.0;
+      for (int k = 0; k < tau; ++k) v += m[a][k] * m[k][b];
+      if (P) P[u] = a == b ? v : 2.0 * v;
+    }
+  if (Minv)
+    for (int a = 0; a < tau; ++a)
+      for (int b = 0; b < tau; ++b) Minv[a * tau + b] = m[a][b];
+  return true;
+}
+
+}  // namespace reg
+
+extern "C" int nnal_sdp_query_distribution_reg(nnal_ctx* ctx, const double* A, int64_t n, int tau, double lambda_, const double* X,
+                                               int d, double tol, int64_t max_iter, double* q_out, double* t_out, double* obj_out,
+                                               double* gap_out, int64_t* iters_out) {
+  if (!ctx || !A || !X || !q_out || n <= 0 || tau <= 0 || d <= 0) return NNAL_ERR_INVALID;
+  if (tau > SDP_MAX_TAU) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "SDP: more than 16 shrunk coordinates");
+  if (!(lambda_ >= 0.0) || !(tol > 0.0)) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "SDP: lambda_ must be >= 0 and tol > 0");
+  if (d >= n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "SDP: X q = 0 with d >= n equalities leaves no freedom (refine the feature matrix)");
+  if (d > 4096 || n > (1 << 20)) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "regularised SDP: at most 4096 feature rows");
+  if (max_iter < 1) max_iter = 1;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  SdpState* st = sdp_state(ctx);
+  const int T2 = tau * tau, Tu = sdp_packed(tau);
+  const int np = (d + 63) / 64 * 64;
+  const int G = (int)std::min<int64_t>((n + reg::RT - 1) / reg::RT, 64);
+  // workspace: [A stage n T2] | At [Tu n] | X [d n] | q, c, h, qh, g, D [6 n] | W [np np] | rhs, mu [2 np] | small [256]
+  NNAL_TRY(devbuf_reserve(ctx, st->stage, (size_t)n * T2 * 8));
+  NNAL_TRY(devbuf_reserve(ctx, st->At, (size_t)n * Tu * 8));
+  const size_t wdoubles = (size_t)d * n + 6 * (size_t)n + (size_t)np * np + 2 * (size_t)np + 512;
+  NNAL_TRY(devbuf_reserve(ctx, st->qu, wdoubles * 8));
+  double* At = (double*)st->At.p;
+  double* Xd = (double*)st->qu.p;
+  double* q = Xd + (size_t)d * n;
+  double* c = q + n; double* h = c + n; double* qh = h + n; double* g = qh + n; double* D = g + n;
+  double* W = D + n;
+  double* rhs = W + (size_t)np * np; double* mu = rhs + np;
+  double* small = mu + np;                                  // [0..Tu+1] sums, [200..] partials
+  CUDA_TRY(ctx, cudaMemcpyAsync(st->stage.p, A, (size_t)n * T2 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(Xd, X, (size_t)d * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const int tg = (int)std::min<int64_t>((n * Tu + 255) / 256, (int64_t)ctx->sm_count * 8);
+  sdp_transpose_kernel<<<tg, 256, 0, ctx->stream>>>((const double*)st->stage.p, At, n, tau);
+  sdp_fill_kernel<<<G, 256, 0, ctx->stream>>>(q, n, 1.0 / (double)n);
+  reg::norms_kernel<<<G, 256, 0, ctx->stream>>>(Xd, n, d, c);
+  ctx->launches += 3;
+  std::vector<double> hs(Tu + 2), hd(Tu + 2), part(3 * 64 + 64);
+  double Mp[SDP_MAX_TAU * (SDP_MAX_TAU + 1) / 2], Mtry[SDP_MAX_TAU * (SDP_MAX_TAU + 1) / 2], Minv[SDP_T2];
+  reg::PArg pa;
+  double phi = 0.0, cq = 0.0, Phi = 0.0, gap = 1e300;
+  auto sums = [&](const double* w, std::vector<double>& out) -> int {
+    reg::msum_kernel<<<Tu + 2, reg::RT, 0, ctx->stream>>>(At, w, c, n, Tu, small);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaMemcpyAsync(out.data(), small, (size_t)(Tu + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NNAL_OK;
+  };
+  int64_t it = 0;
+  bool fresh = true;
+  for (;; ++it) {
+    if (fresh || it % 64 == 0) {                            // M(q), c.q from scratch (otherwise carried along the line search)
+      NNAL_TRY(sums(q, hs));
+      for (int u = 0; u < Tu; ++u) Mp[u] = hs[u];
+      cq = hs[Tu];
+      fresh = false;
+    }
+    if (!reg::host_inverse(Mp, tau, Minv, pa.P, &phi)) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "SDP: sum_i q_i A_i is not positive definite");
+    Phi = phi - lambda_ * cq;
+    reg::h_kernel<<<G, 256, 0, ctx->stream>>>(At, q, c, n, Tu, pa, lambda_, h, qh);
+    reg::wgram_kernel<<<dim3(np / 64, np / 64), 256, 0, ctx->stream>>>(Xd, q, n, d, np, W);
+    reg::ridge_kernel<<<1, 256, 0, ctx->stream>>>(W, d, np, 1e-14);
+    reg::xv_kernel<<<d, reg::RT, 0, ctx->stream>>>(Xd, qh, n, rhs);
+    ctx->launches += 4;
+    NNAL_TRY(nnal_gj64_invert(ctx, W, np));
+    reg::mv_kernel<<<d, reg::RT, 0, ctx->stream>>>(W, np, d, rhs, mu);
+    reg::g_kernel<<<G, reg::RT, 0, ctx->stream>>>(Xd, mu, h, q, n, d, g, small + 200);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaMemcpyAsync(part.data(), small + 200, (size_t)3 * G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double nu = 0.0, s2 = 0.0, gmax = -1e300;
+    for (int b = 0; b < G; ++b) { nu += part[3 * b]; s2 += part[3 * b + 1]; gmax = std::max(gmax, part[3 * b + 2]); }
+    gap = (gmax - nu) / std::max(std::fabs(Phi), phi);
+    if (!(gap == gap)) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "SDP: the regularised programme broke down (singular feature normal equations)");
+    if (gap <= tol || it >= max_iter) break;
+    reg::delta_kernel<<<G, reg::RT, 0, ctx->stream>>>(q, g, n, nu, D, small + 200);
+    ctx->launches++;
+    NNAL_TRY(sums(D, hd));                                  // M(D), c.D (the sync also covers the partial minima below)
+    CUDA_TRY(ctx, cudaMemcpyAsync(part.data(), small + 200, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double rmin = 1e300;
+    for (int b = 0; b < G; ++b) rmin = std::min(rmin, part[b]);
+    double theta = rmin < 0.0 ? std::min(1.0, 0.99 * (-1.0 / rmin)) : 1.0;
+    const double slope = (s2 - nu * nu) / nu;               // Var_q(g) / nu >= 0
+    double phin = 0.0;
+    for (;;) {
+      for (int u = 0; u < Tu; ++u) Mtry[u] = Mp[u] + theta * hd[u];
+      const bool ok = reg::host_inverse(Mtry, tau, nullptr, nullptr, &phin);
+      const double Pn = phin - lambda_ * (cq + theta * hd[Tu]);
+      if ((ok && Pn <= Phi - 1e-4 * theta * slope) || theta < 1e-12) break;
+      theta *= 0.5;
+    }
+    reg::axpy_kernel<<<G, 256, 0, ctx->stream>>>(q, D, n, theta);
+    ctx->launches++;
+    for (int u = 0; u < Tu; ++u) Mp[u] = Mtry[u];
+    cq += theta * hd[Tu];
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(q_out, q, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (obj_out) *obj_out = Phi;
+  if (gap_out) *gap_out = gap;
+  if (t_out) for (int j = 0; j < tau; ++j) t_out[j] = Minv[j * tau + j];
   if (iters_out) *iters_out = it;
   return NNAL_OK;
 }

@@ -554,6 +554,23 @@ class Engine(object):
                                                        _ptr(q), _ptr(t), C.byref(obj), C.byref(gap), C.byref(it)))
         return {'q': q, 't': t, 'objective': obj.value, 'gap': gap.value, 'iterations': it.value}
 
+    def sdp_query_distribution_reg(self, A, lambda_, X, tol=1e-4, max_iter=20000):
+        """The feature-regularised programme (``lambda_ > 0``, NNAL_tools.py:625-644): min tr((sum q_i A_i)^-1) - lambda sum
+        q_i |x_i|^2 over {q >= 0, sum q = 1, X q = 0}; ``A`` [n,tau,tau], ``X`` [d,n] float64."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if A.ndim != 3 or A.shape[1] != A.shape[2] or X.ndim != 2 or X.shape[1] != A.shape[0]:
+            raise ValueError('A must be [n, tau, tau] and X [d, n]')
+        n, tau = A.shape[0], A.shape[1]
+        q = np.empty(n, dtype=np.float64)
+        t = np.empty(tau, dtype=np.float64)
+        obj, gap, it = C.c_double(), C.c_double(), C.c_int64()
+        self.h2d_bytes += A.nbytes + X.nbytes
+        self.d2h_bytes += q.nbytes
+        self._chk(self.lib.nnal_sdp_query_distribution_reg(self.h, _ptr(A), n, tau, float(lambda_), _ptr(X), X.shape[0], float(tol),
+                                                           int(max_iter), _ptr(q), _ptr(t), C.byref(obj), C.byref(gap), C.byref(it)))
+        return {'q': q, 't': t, 'objective': obj.value, 'gap': gap.value, 'iterations': it.value}
+
     def sdp_from_shrunk(self, g, p1, diag_load, tol=1e-4, max_iter=200000, gamma=1.0):
         """``sdp_query_distribution`` on the binary A-matrices of ``gen_A_matrices``, assembled on the device from the
         shrunk gradients ``g`` [2,n,tau] and ``p1`` [n] = P(class 1)."""

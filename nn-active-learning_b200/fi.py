@@ -323,20 +323,23 @@ def _my_slice(n):
     return int(b[rank]), int(b[rank + 1])
 
 
-def _sdp_sample(A, expr, return_solution, shrunk=None):
+def _sdp_sample(A, expr, return_solution, shrunk=None, ref_F=None):
     """SDP query distribution + the reference's sampler (PW_NNAL.py:154-163).  The draw uses NumPy's global
     generator like the reference; with several ranks, rank 0's draw is broadcast.  ``shrunk = (g, p1, diag_load)``:
-    binary A-matrices assembled on the device instead of ``A``."""
+    binary A-matrices assembled on the device instead of ``A``.  ``ref_F`` [d, B]: the zero-mean refined feature matrix of
+    the ``lambda_ > 0`` programme (PW_NNAL.py:139-155)."""
     from . import NNAL_tools
     k = int(expr.pars['k'])
     tol = float(expr.pars.get('sdp_tol', 1e-4))
-    if shrunk is not None:
-        if expr.pars.get('lambda_', 0) > 0:
-            raise NotImplementedError('lambda_ > 0 (feature-regularised SDP, NNAL_tools.py:625-644) stays in the reference')
+    lambda_ = expr.pars.get('lambda_', 0)
+    if shrunk is not None and not (lambda_ > 0):
         soln = NNAL_tools.SDP_query_distribution_from_shrunk(shrunk[0], shrunk[1], shrunk[2], k, tol=tol)
         nA = shrunk[0].shape[1]
     else:
-        soln = NNAL_tools.SDP_query_distribution(A, expr.pars.get('lambda_', 0), None, k, tol=tol)
+        if shrunk is not None:                       # regularised programme: the solver takes explicit A-matrices
+            from .PW_NNAL import _A_from_shrunk
+            A = _A_from_shrunk(shrunk[0], shrunk[1], shrunk[2], as_list=False)
+        soln = NNAL_tools.SDP_query_distribution(A, lambda_ if ref_F is not None else 0, ref_F, k, tol=tol)
         nA = len(A)
     q_opt = np.array(soln['x'][:nA])
     Q_inds = NNAL_tools.sample_query_dstr(q_opt.copy(), k, replacement=True)
@@ -370,8 +373,19 @@ def query_single_sdp(expr, model, sess, padded_imgs, pool_inds, return_solution=
     post, g = eng.fi_shrunk_voxels(0, pool_inds[sel_inds[a:e]], expr.pars['patch_shape'],
                                    _stats_list(expr.pars['stats'], len(imgs)), L.NORM_BATCH_EVAL, shape=imgs[0].shape)
     post, g = _gather_shrunk(post, g)
+    ref_F = None
+    if expr.pars.get('lambda_', 0) > 0:
+        # PW_NNAL.py:139-151: feature_layer of the B candidates (batch_eval), refined to full row rank, rows made zero-mean.
+        # (B candidates through one more forward pass on every rank: the matrix is B/2 x B at most.)
+        from .PW_NNAL import refine_feature_matrix
+        eng.pool_begin(len(sel_inds), 1)
+        eng.pool_eval(0, pool_inds[sel_inds], 0, expr.pars['patch_shape'], _stats_list(expr.pars['stats'], len(imgs)),
+                      L.NORM_BATCH_EVAL, shape=imgs[0].shape)
+        F = eng.pool_features().astype(np.float64)
+        ref_F = refine_feature_matrix(F, B)
+        ref_F -= np.mean(ref_F, axis=1, keepdims=True)
     Q_inds, soln = _sdp_sample(None, expr, return_solution,
-                               shrunk=(g, post[1].astype(np.float64), float(expr.pars.get('fi_diag_load', 1e-5))))
+                               shrunk=(g, post[1].astype(np.float64), float(expr.pars.get('fi_diag_load', 1e-5))), ref_F=ref_F)
     q = sel_inds[Q_inds]
     return (q, soln, sel_inds) if return_solution else q
 
@@ -464,7 +478,29 @@ def query_whole_sdp(model, expr, pool_inds, session, return_solution=False):
     post, g = eng.fi_shrunk_images(_pool_images(expr, pool_inds[sel_inds[a:e]]))
     post, g = _gather_shrunk(post, g)
     A = _A_multiclass_from_shrunk(post.astype(np.float64), g)
-    Q_inds, soln = _sdp_sample(A, expr, return_solution)
+    ref_F = None
+    if expr.pars.get('lambda_', 0) > 0:
+        # NNAL.py:414-447: features of the B candidates (model.extract_features), the int(B/2) rows with the most positive
+        # entries, tail dropped until full row rank (warning below 10 rows) and cond <= 1e6 (a single row left switches the
+        # regulariser off, :440-442), rows made zero-mean
+        import warnings
+        eng.pool_begin(len(sel_inds), 1)
+        eng.pool_eval_images(_pool_images(expr, pool_inds[sel_inds]), 0)
+        F = eng.pool_features().astype(np.float64)
+        order = np.argsort(-np.sum(F > 0, axis=1))[:int(B / 2)]
+        while np.linalg.matrix_rank(F[order, :]) < len(order):
+            order = order[:-1]
+            if len(order) < 10:
+                warnings.warn("Few features (%d) are selected" % len(order))
+        off = False
+        while np.linalg.cond(F[order, :]) > 1e6:
+            order = order[:-1]
+            if len(order) == 1:
+                off = True
+                break
+        if not off:
+            ref_F = F[order, :] - np.mean(F[order, :], axis=1, keepdims=True)
+    Q_inds, soln = _sdp_sample(A, expr, return_solution, ref_F=ref_F)
     q = sel_inds[Q_inds]
     return (q, soln, sel_inds) if return_solution else q
 

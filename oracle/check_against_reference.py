@@ -260,6 +260,24 @@ def main():
         gold['sdp_h%d' % j] = hs[j]
     gold['sdp_Aeq'], gold['sdp_beq'] = A_eq, b_eq
     gold['sdp_q'], gold['sdp_t'], gold['sdp_phi'] = qs, ts, np.array(phis)
+    # the same with lambda_ > 0 (:625-644): c = [-lambda |x_i|^2 ; 1], equalities [X_pool, 0; 1^T, 0] x = [0; 1].  The oracle's
+    # feasible multiplicative solver must satisfy exactly these constraints, with c^T x = tr(M^-1) - lambda sum q_i |x_i|^2.
+    lam_s = 0.3
+    X_s = np.maximum(rs.randn(4, n_s), 0)
+    X_s = X_s - X_s.mean(axis=1, keepdims=True)
+    ref_tools.SDP_query_distribution(A_s, lam_s, X_s, 5)
+    c_r, A_r, b_r = captured['c'], captured['A'], captured['b']
+    assert A_r.shape == (5, n_s + tau_s) and b_r.shape[0] == 5
+    qr, tr_, Phir, gapr, itr = O.sdp_solve_reg(A_s, lam_s, X_s, 1e-9)
+    xr = np.concatenate([qr, tr_])
+    assert np.abs(A_r @ xr - b_r[:, 0]).max() < 1e-12                          # X q = 0 and sum q = 1
+    assert abs((c_r[:, 0] @ xr).item() - Phir) < 1e-9 * abs(Phir)             # objective = sum t_j - lambda sum q_i |x_i|^2
+    assert qr.min() >= 0
+    q_sl, Phi_sl = O.sdp_solve_reg_slsqp(A_s, lam_s, X_s)
+    assert abs(Phir / Phi_sl - 1) < 1e-6
+    gold['sdpr_X'], gold['sdpr_lambda'] = X_s, np.array(lam_s)
+    gold['sdpr_c'], gold['sdpr_Aeq'], gold['sdpr_beq'] = c_r, A_r, b_r
+    gold['sdpr_q'], gold['sdpr_Phi'] = qr, np.array(Phir)
     print('SDP_query_distribution / inequality_cvx_matrix: the reference\'s programme (captured c, G, h, A, b) == '
           'min tr((sum q_i A_i)^-1) over the simplex; oracle solution feasible, objective equal')
 
@@ -386,8 +404,16 @@ def main():
             d1 = int(round(np.sqrt(G0.shape[0])))
             nq = nvar - (d1 - 1)
             A_rec = [(-G0[:, i]).reshape(d1, d1).T[:d1 - 1, :d1 - 1] for i in range(nq)]
-            q, t, phi, gap, it = O.sdp_solve(A_rec, 1e-4)
-            OracleSolvers.last = {'A': np.array(A_rec), 'q': q, 'phi': phi}
+            Aeq = np.asarray(A)
+            if Aeq.shape[0] > 1:                       # lambda_ > 0: recover X_pool and lambda from the equalities and c
+                X = Aeq[:-1, :nq]
+                cn = np.sum(X ** 2, axis=0)
+                lam = float(np.median(-np.asarray(c)[:nq, 0][cn > 0] / cn[cn > 0]))
+                q, t, phi, gap, it = O.sdp_solve_reg(A_rec, lam, X, 1e-4)
+                OracleSolvers.last = {'A': np.array(A_rec), 'q': q, 'phi': phi, 'X': X, 'lambda': lam}
+            else:
+                q, t, phi, gap, it = O.sdp_solve(A_rec, 1e-4)
+                OracleSolvers.last = {'A': np.array(A_rec), 'q': q, 'phi': phi}
             return {'status': 'optimal', 'x': np.concatenate([q, t])}
 
     ref_tools.solvers = OracleSolvers
@@ -404,6 +430,19 @@ def main():
     assert np.array_equal(np.asarray(rq_fi), oq_fi), (rq_fi, oq_fi)
     gold['q_fi_sdp_single'] = np.asarray(rq_fi)
     gold['q_fi_u'] = u77
+    # the same branch with lambda_ > 0: feature_layer of the candidates -> refine_feature_matrix -> zero-mean rows -> the
+    # regularised programme (:139-155)
+    class LExpr(QExpr):
+        pars = dict(QExpr.pars, lambda_=0.2)
+    np.random.seed(77)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rq_fil = ref_pw.CNN_query(LExpr(), FiModel(), FiSess(), allp_q[0][:m_q], pool0, None, 'fi')
+    oq_fil, detl = O.query_fi_sdp_single(layers_q, w_q, allp_q[0][:m_q], pool0, ps_q, 16, stats0, 9, 30, u77, diag_load=1e-5,
+                                         lambda_=0.2)
+    assert abs(OracleSolvers.last['lambda'] - 0.2) < 1e-12
+    assert np.array_equal(OracleSolvers.last['X'], detl['ref_F'])             # same refined, centred feature rows
+    assert np.array_equal(np.asarray(rq_fil), oq_fil), (rq_fil, oq_fil)
+    gold['q_fi_sdp_single_lambda'] = np.asarray(rq_fil)
     # the multi-volume twin (:547-627, 'CVXOPT' branch) -- its live pdb.set_trace() (:612) is made a no-op
     class MExpr(QExpr):
         pars = dict(QExpr.pars, k=11, B=40, SDP_solver='CVXOPT')

@@ -23,7 +23,7 @@ from .nnal_oracle import forward, stable_topk, batch_eval, get_patches, normaliz
 __all__ = [
     'class_score_factors', 'explicit_class_gradients', 'shrink_gradient',
     'shrunk_class_gradients', 'gen_A_matrices', 'gen_A_matrices_multiclass',
-    'LLFC_grads', 'LLFC_hess', 'stoch_approx_IF', 'FC_gradnorms_batch', 'fi_trace_score',
+    'LLFC_grads', 'LLFC_hess', 'stoch_approx_IF', 'sdp_solve_reg', 'sdp_solve_reg_slsqp', 'refine_feature_matrix', 'FC_gradnorms_batch', 'fi_trace_score',
     'mnist_fi_score', 'sdp_objective', 'fi_objective_direct', 'greedy_fi_direct',
     'fi_objective_dual', 'greedy_fi_dual_bruteforce', 'greedy_fi_rank1',
     'last_layers_kernel', 'last_layers_dim', 'weighted_gram', 'fi_objective_from_gram',
@@ -377,6 +377,78 @@ def sdp_solve(A, tol=1e-4, max_iter=200000, gamma=0.5):
         it += 1
 
 
+def sdp_solve_reg(A, lambda_, X_pool, tol=1e-4, max_iter=20000):
+    """The regularised query-distribution problem of NNAL_tools.SDP_query_distribution with ``lambda_ > 0``
+    (NNAL_tools.py:625-644): objective ``sum_j t_j - lambda sum_i q_i |x_i|^2`` (``c`` vector :630-632) under the extra
+    equalities ``X_pool q = 0`` next to ``sum q = 1`` (:635-644), ``X_pool`` [d, n] = the zero-mean refined feature matrix.
+    With t_j = (M^-1)_jj:  minimise  Phi(q) = tr(M(q)^-1) - lambda c^T q,  c_i = |x_i|^2, over {q >= 0, 1^T q = 1, X q = 0}.
+
+    Solved by a multiplicative (natural-gradient) method that keeps EVERY iterate feasible: with d_i = <M^-2, A_i>,
+    h = d + lambda c, the multipliers mu of X q = 0 are the weighted regression of h on the features,
+    (X diag(q) X^T) mu = X (q.h); then g = h - X^T mu, nu = q.g, and  q_i <- q_i (1 + theta (g_i / nu - 1))  preserves
+    1^T q = 1 and X q = 0 for every theta, is a descent direction (dPhi = -theta Var_q(g) / nu) and has the KKT points as
+    fixed points.  theta: largest step in (0, 1] that keeps q > 0, halved until Phi decreases (Armijo).  By convexity
+    Phi(q) - Phi* <= max_i g_i - nu for any mu: the loop stops when that, relative to |Phi| (or tr M^-1), is below ``tol``.
+    Returns (q, t = diag(M^-1), Phi, gap, iterations)."""
+    A = np.asarray(A, dtype=np.float64)
+    X = np.asarray(X_pool, dtype=np.float64)
+    n, tau, _ = A.shape
+    Af = A.reshape(n, -1)
+    c = np.sum(X ** 2, axis=0)
+    q = np.ones(n) / n
+
+    def value(qq):
+        Mi = np.linalg.inv((qq @ Af).reshape(tau, tau))
+        return np.trace(Mi) - lambda_ * (c @ qq), Mi
+    Phi, Mi = value(q)
+    it = 0
+    while True:
+        h = Af @ (Mi @ Mi).ravel() + lambda_ * c
+        W = (X * q) @ X.T
+        W += np.eye(len(W)) * (1e-14 * np.trace(W) / max(len(W), 1))
+        mu = np.linalg.solve(W, X @ (q * h))
+        g = h - X.T @ mu
+        nu = q @ g
+        scale = max(abs(Phi), np.trace(Mi))
+        gap = (g.max() - nu) / scale
+        if gap <= tol or it >= max_iter:
+            return q, np.diag(Mi).copy(), Phi, gap, it
+        r = g / nu - 1.
+        neg = r < 0
+        theta = min(1., 0.99 * np.min(-1. / r[neg])) if neg.any() else 1.
+        slope = (q @ (g * g) - nu * nu) / nu                     # = Var_q(g) / nu >= 0
+        while True:
+            qn = q * (1. + theta * r)
+            Pn, Mn = value(qn)
+            if Pn <= Phi - 1e-4 * theta * slope or theta < 1e-12:
+                break
+            theta *= .5
+        q, Phi, Mi = qn, Pn, Mn
+        it += 1
+
+
+def sdp_solve_reg_slsqp(A, lambda_, X_pool):
+    """Independent check of ``sdp_solve_reg`` for SMALL n: the same convex programme handed to scipy's SLSQP."""
+    from scipy.optimize import minimize
+    A = np.asarray(A, dtype=np.float64)
+    X = np.asarray(X_pool, dtype=np.float64)
+    n, tau, _ = A.shape
+    Af = A.reshape(n, -1)
+    c = np.sum(X ** 2, axis=0)
+
+    def f(q):
+        Mi = np.linalg.inv((q @ Af).reshape(tau, tau))
+        return np.trace(Mi) - lambda_ * (c @ q), -(Af @ (Mi @ Mi).ravel()) - lambda_ * c
+    scale = abs(f(np.ones(n) / n)[0])
+    E = np.concatenate([X, np.ones((1, n))], axis=0)
+    b = np.zeros(len(E))
+    b[-1] = 1.
+    res = minimize(lambda q: tuple(v / scale for v in f(q)), np.ones(n) / n, jac=True, method='SLSQP', bounds=[(0., 1.)] * n,
+                   constraints=[{'type': 'eq', 'fun': lambda q: E @ q - b, 'jac': lambda q: E}],
+                   options={'maxiter': 3000, 'ftol': 1e-15})
+    return res.x, f(res.x)[0]
+
+
 def sdp_solve_slsqp(A, q0=None):
     """Independent check of ``sdp_solve`` for SMALL n: the same convex programme handed to
     scipy's SLSQP (equality sum q = 1, bounds q >= 0, analytic gradient).  Returns (q, phi)."""
@@ -398,8 +470,26 @@ def sdp_solve_slsqp(A, q0=None):
     return q, f(q)[0]
 
 
+def refine_feature_matrix(F, B):
+    """PW_NNAL.refine_feature_matrix (PW_NNAL.py:819-849): the int(B/2) feature rows with the most positive entries
+    (:826-828), the last one dropped while the matrix is rank deficient (:830-834) and while its condition number exceeds
+    1e6 (:837-842, stopping at a single row)."""
+    nnz_feats = np.sum(F > 0, axis=1)
+    feat_inds = np.argsort(-nnz_feats)[:int(B / 2)]
+    ref_F = F[feat_inds, :]
+    while np.linalg.matrix_rank(ref_F) < len(feat_inds):
+        feat_inds = feat_inds[:-1]
+        ref_F = F[feat_inds, :]
+    while np.linalg.cond(ref_F) > 1e6:
+        feat_inds = feat_inds[:-1]
+        ref_F = F[feat_inds, :]
+        if len(feat_inds) == 1:
+            break
+    return ref_F
+
+
 def query_fi_sdp_single(layers, weights, padded_imgs, pool_inds, patch_shape, ntb, stats, k, B, u,
-                        diag_load=1e-5, tol=1e-4):
+                        diag_load=1e-5, tol=1e-4, lambda_=0.):
     """PW_NNAL.CNN_query 'fi' as the reference runs it (PW_NNAL.py:89-163) with lambda_ = 0:
     posteriors -> the B most uncertain (:107-115) -> re-gather + normalise (:122-131) ->
     gen_A_matrices in shrunk coordinates (:133-137) -> SDP query distribution (:154-157) ->
@@ -414,9 +504,17 @@ def query_fi_sdp_single(layers, weights, padded_imgs, pool_inds, patch_shape, nt
     x = normalize_batch_eval(get_patches(padded_imgs, pool_inds[sel], patch_shape), stats).astype(np.float32)
     post, g = shrunk_class_gradients(layers, weights, x)
     A = gen_A_matrices(g[0], g[1], posts[sel], diag_load)
-    q, t, phi, gap, it = sdp_solve(A, tol)
+    ref_F = None
+    if lambda_ > 0:
+        # PW_NNAL.py:139-155: features of the candidates, refined, rows made zero-mean, regularised programme
+        F = batch_eval(layers, weights, padded_imgs, pool_inds[sel], patch_shape, ntb, stats, 'feature_layer')[0]
+        ref_F = refine_feature_matrix(F, len(sel) if B >= len(pool_inds) else B)
+        ref_F = ref_F - np.repeat(np.expand_dims(np.mean(ref_F, axis=1), axis=1), F.shape[1], axis=1)
+        q, t, phi, gap, it = sdp_solve_reg(A, lambda_, ref_F, tol)
+    else:
+        q, t, phi, gap, it = sdp_solve(A, tol)
     Q = sample_query_dstr(q.copy(), k, u)
-    return sel[Q], {'sel': sel, 'A': A, 'q': q, 't': t, 'phi': phi, 'gap': gap, 'g': g, 'post': post, 'x': x}
+    return sel[Q], {'sel': sel, 'A': A, 'q': q, 't': t, 'phi': phi, 'gap': gap, 'g': g, 'post': post, 'x': x, 'ref_F': ref_F}
 
 
 def query_fi_sdp_multimg(layers, weights, all_padded_imgs, pool_inds, patch_shape, ntb, train_stats, k, B, u,

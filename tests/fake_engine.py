@@ -481,6 +481,10 @@ class FakeEngine(object):
         q, t, phi, gap, it = O.sdp_solve(np.asarray(A), tol, max_iter, 0.5)    # the monotone exponent; the device may start faster
         return {'q': q, 't': t, 'objective': phi, 'gap': gap, 'iterations': it}
 
+    def sdp_query_distribution_reg(self, A, lambda_, X, tol=1e-4, max_iter=20000):
+        q, t, Phi, gap, it = O.sdp_solve_reg(np.asarray(A), lambda_, np.asarray(X), tol, max_iter)
+        return {'q': q, 't': t, 'objective': Phi, 'gap': gap, 'iterations': it}
+
     def sdp_from_shrunk(self, g, p1, diag_load, tol=1e-4, max_iter=200000, gamma=1.0):
         return self.sdp_query_distribution(O.gen_A_matrices(g[0], g[1], np.asarray(p1, dtype=np.float64), diag_load), tol, max_iter)
 

@@ -141,8 +141,6 @@ def test_sdp_query_distribution(nb, n, tau, delta, scale):
     assert soln['status'] == 'optimal' and len(soln['x']) == n + tau
     assert np.allclose(np.array(soln['x'][:n]), q)
     assert abs(np.sum(soln['x'][n:]) / phi - 1) < 1e-9
-    with pytest.raises(NotImplementedError):
-        nb.NNAL_tools.SDP_query_distribution(list(A), 0.1, None, 10)
 
 
 def test_sdp_matches_slsqp_small(nb):
@@ -393,3 +391,78 @@ def test_sdp_device_solution_feasible_for_reference_programme(nb, golden):
     obj = assert_feasible_for_reference_sdp(golden, r['q'], r['t'] * (1 + 1e-12))
     assert abs(obj / r['objective'] - 1) < 1e-9
     assert 0 <= obj / float(golden['sdp_phi']) - 1 < 1e-5
+
+
+def _centred_features(d, n, seed):
+    rs = np.random.RandomState(seed)
+    X = np.maximum(rs.randn(d, n), 0)
+    return X - X.mean(axis=1, keepdims=True)
+
+
+@pytest.mark.parametrize('n,tau,d,lam', [(60, 5, 25, 2.0), (400, 7, 70, 0.05), (900, 7, 200, 0.5), (130, 3, 1, 1.0)])
+def test_sdp_regularised_matches_oracle(nb, n, tau, d, lam):
+    """lambda_ > 0 (NNAL_tools.py:625-644) on the device: every constraint holds to rounding, the objective equals the
+    float64 oracle's (itself checked against SLSQP and the reference's captured programme) well inside 1e-3."""
+    A = np.array(_rand_A(n, tau, 1e-3, n + d, 0.05))
+    X = _centred_features(d, n, n)
+    r = nb.get_engine().sdp_query_distribution_reg(A, lam, X, tol=1e-5)
+    q = r['q']
+    assert q.min() >= 0 and abs(q.sum() - 1) < 1e-10
+    assert np.abs(X @ q).max() < 1e-9 * np.abs(X).max()
+    M = np.tensordot(q, A, axes=(0, 0))
+    Phi = np.trace(np.linalg.inv(M)) - lam * (np.sum(X ** 2, axis=0) @ q)
+    assert abs(r['objective'] - Phi) < 1e-9 * abs(Phi)            # the reported objective is the objective of the returned q
+    assert np.allclose(r['t'], np.diag(np.linalg.inv(M)), rtol=1e-9)
+    qo, to, Phio, gapo, ito = O.sdp_solve_reg(A, lam, X, 1e-7)
+    assert r['gap'] <= 1e-5 and Phi >= Phio - 1e-6 * abs(Phio)    # nobody beats the (tighter) oracle optimum ...
+    assert abs(Phi / Phio - 1) < 1e-4                             # ... and the device is within its certificate of it
+    soln = nb.NNAL_tools.SDP_query_distribution(list(A), lam, X, 10, tol=1e-5)
+    assert soln['status'] == 'optimal' and np.allclose(np.array(soln['x'][:n]), q)
+
+
+def test_sdp_regularised_small_vs_slsqp_and_reference_programme(nb, golden):
+    """Independent solver at small n, and feasibility for the constraint data the UNMODIFIED reference builds for
+    lambda_ > 0 (c, A_eq, b_eq captured by oracle/check_against_reference.py)."""
+    A, X, lam = golden['sdp_A'], golden['sdpr_X'], float(golden['sdpr_lambda'])
+    r = nb.get_engine().sdp_query_distribution_reg(A, lam, X, tol=1e-7)
+    x = np.concatenate([r['q'], r['t']])
+    assert np.abs(golden['sdpr_Aeq'] @ x - golden['sdpr_beq'][:, 0]).max() < 1e-10       # X q = 0, sum q = 1
+    assert abs((golden['sdpr_c'][:, 0] @ x).item() - r['objective']) < 1e-9 * abs(r['objective'])
+    assert abs(r['objective'] / float(golden['sdpr_Phi']) - 1) < 1e-5
+    q2, Phi2 = O.sdp_solve_reg_slsqp(A, lam, X)
+    assert abs(r['objective'] / Phi2 - 1) < 1e-5
+    assert_feasible_lmis(golden, r['q'], r['t'])
+
+
+def assert_feasible_lmis(golden, q, t):
+    """The LMIs are those of the lambda_ = 0 programme (inequality_cvx_matrix does not depend on lambda_)."""
+    x = np.concatenate([q, t])
+    tau = len(t)
+    for j in range(tau + 1):
+        G, h = golden['sdp_G%d' % j], golden['sdp_h%d' % j]
+        m = h.shape[0]
+        slack = h - (G @ x).reshape(m, m)
+        slack = (slack + slack.T) / 2
+        assert np.linalg.eigvalsh(slack).min() > -1e-9 * np.abs(slack).max(), j
+
+
+def test_pw_fi_query_sdp_single_regularised_dispatch(nb, golden):
+    """PW_NNAL.CNN_query 'fi' with lambda_ > 0 on the inputs of the golden run of the unmodified reference: candidates'
+    features -> refine_feature_matrix -> zero-mean rows -> regularised programme -> sampler."""
+    from collections import OrderedDict
+    from tests.test_reference_dispatch_golden import LAYERS, M, PS, _case
+    w, allp, pools, st, stats0 = _case(golden)
+    pool0 = np.array(pools[0])
+    model = nb.NN.CNN((5, 5, M), OrderedDict(LAYERS), feature_layer=len(LAYERS) - 2)
+    model.set_weights(w)
+    expr = Expr(k=9, B=30, lambda_=0.2, patch_shape=PS, ntb=16, stats=stats0, fi_mode='sdp')
+    np.random.seed(77)
+    qf, soln, sel = nb.fi.query_single_sdp(expr, model, None, allp[0][:M], pool0, return_solution=True)
+    _, det = O.query_fi_sdp_single(LAYERS, w, allp[0][:M], pool0, PS, 16, stats0, 9, 30, golden['q_fi_u'], diag_load=1e-5, lambda_=0.2)
+    assert soln['status'] == 'optimal'
+    assert abs(soln['primal objective'] / det['phi'] - 1) < 1e-3
+    q_dev = np.array(soln['x'][:len(sel)])
+    assert np.abs(det['ref_F'] @ q_dev).max() < 1e-6 * np.abs(det['ref_F']).max()      # the oracle's constraints hold for the device's q
+    assert np.array_equal(qf, sel[O.sample_query_dstr(q_dev.copy(), 9, golden['q_fi_u'])])
+    got, want = set(np.asarray(qf).tolist()), set(golden['q_fi_sdp_single_lambda'].tolist())
+    assert got <= set(sel.tolist()) and len(got & want) >= len(want) - 3, (sorted(got), sorted(want))

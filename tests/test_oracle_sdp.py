@@ -115,3 +115,26 @@ def test_gen_A_matrices_golden(golden):
     A = O.gen_A_matrices(g[0], g[1], golden['genA_posts'], 1e-5)
     assert np.allclose(np.array(A), golden['genA_out'], rtol=1e-9, atol=1e-18)
     assert np.array_equal(np.array(_A_from_shrunk(g, golden['genA_posts'], 1e-5)), np.array(A))
+
+
+def test_sdp_solve_reg_matches_slsqp_and_reference_programme(golden):
+    """lambda_ > 0: the oracle's feasible multiplicative solver against SLSQP, and against the equalities / objective vector
+    the unmodified reference hands to cvxopt (captured: sdpr_c, sdpr_Aeq, sdpr_beq)."""
+    rs = np.random.RandomState(3)
+    for n, tau, d, lam in [(20, 3, 6, 0.05), (40, 4, 15, 0.5)]:
+        A, _, _ = _rand_A(n, tau, 1e-3, n)
+        X = np.maximum(rs.randn(d, n), 0)
+        X -= X.mean(axis=1, keepdims=True)
+        q, t, Phi, gap, it = O.sdp_solve_reg(A, lam, X, 1e-7)
+        q2, Phi2 = O.sdp_solve_reg_slsqp(A, lam, X)
+        assert abs(Phi / Phi2 - 1) < 1e-6 and gap <= 1e-7
+        assert q.min() >= 0 and abs(q.sum() - 1) < 1e-12 and np.abs(X @ q).max() < 1e-12
+    A, X, lam = golden['sdp_A'], golden['sdpr_X'], float(golden['sdpr_lambda'])
+    q, t, Phi, gap, it = O.sdp_solve_reg(A, lam, X, 1e-9)
+    x = np.concatenate([q, t])
+    assert np.abs(golden['sdpr_Aeq'] @ x - golden['sdpr_beq'][:, 0]).max() < 1e-12
+    assert abs((golden['sdpr_c'][:, 0] @ x).item() - Phi) < 1e-9 * abs(Phi)
+    assert np.allclose(q, golden['sdpr_q'], atol=1e-9) and abs(Phi - float(golden['sdpr_Phi'])) < 1e-9 * abs(Phi)
+    # the regulariser and the equalities only ever cost A-optimality: the plain optimum is a lower bound of tr(M^-1)
+    q0, t0, phi0, gap0, it0 = O.sdp_solve(A, 1e-8)
+    assert t.sum() >= phi0 * (1 - 1e-7)
