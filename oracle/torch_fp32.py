@@ -12,25 +12,28 @@ import torch.nn.functional as F
 
 
 class TorchForward(object):
-    def __init__(self, layers, weights, feature_layer=None, threads=None):
+    def __init__(self, layers, weights, feature_layer=None, threads=None, dtype=torch.float32):
+        """``dtype=torch.float64`` gives a fast float64 oracle for full-size pools (same arithmetic as
+        ``oracle.nnal_oracle.forward``, BLAS summation order)."""
         if threads:
             torch.set_num_threads(threads)
         self.layers = list(layers)
         self.feature_layer = feature_layer
+        self.dtype = dtype
         self.params = {}
         for name, spec in self.layers:
             if spec[1] == 'conv':
                 W, b = weights[name]
-                self.params[name] = (torch.from_numpy(np.ascontiguousarray(np.transpose(W, (3, 2, 0, 1)))).float(),
-                                     torch.from_numpy(np.ravel(b).copy()).float())
+                self.params[name] = (torch.from_numpy(np.ascontiguousarray(np.transpose(W, (3, 2, 0, 1)))).to(dtype),
+                                     torch.from_numpy(np.ravel(b).copy()).to(dtype))
             elif spec[1] == 'fc':
                 W, b = weights[name]
-                self.params[name] = (torch.from_numpy(np.ascontiguousarray(W)).float(),
-                                     torch.from_numpy(np.ravel(b).copy()).float())
+                self.params[name] = (torch.from_numpy(np.ascontiguousarray(W)).to(dtype),
+                                     torch.from_numpy(np.ravel(b).copy()).to(dtype))
 
     @torch.no_grad()
     def __call__(self, x):
-        h = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).permute(0, 3, 1, 2)
+        h = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.dtype).permute(0, 3, 1, 2)
         flat = False
         feat = None
         n_layers = len(self.layers)

