@@ -67,8 +67,8 @@ int nnal_ctx_destroy(nnal_ctx* ctx);
 const char* nnal_last_error(nnal_ctx* ctx);
 /* kernels launched by this context so far (bench.py's gpu_launches) */
 long long nnal_launch_count(nnal_ctx* ctx);
-/* 0: every conv/fc layer on the FP32 CUDA-core kernels; 1 (default): tcgen05 tensor-core kernels
- * (3-term bf16 split, FP32 accumulate) for the shapes they cover. */
+/* 0: every conv/fc layer on the FP32 CUDA-core kernels (no fp16 operand range limit); 1 (default): tcgen05 tensor-core
+ * kernels (fp16 hi/lo split operands, 3 MMAs per product, FP32 accumulate) for the shapes they cover. */
 int nnal_set_tensor_cores(nnal_ctx* ctx, int enable);
 int nnal_synchronize(nnal_ctx* ctx);
 /* the context's CUDA stream (cudaStream_t) so host code can record CUDA events on it */
@@ -326,6 +326,11 @@ int nnal_cs_greedy(nnal_ctx* ctx, int64_t k, int64_t* sel_out, double* val_out);
 int nnal_pool_feature_rows(nnal_ctx* ctx, const int64_t* pos, int64_t n, float* out);
 
 /* ---- test hooks --------------------------------------------------------------------------- */
+/* Kernel-selection switches for TESTS (there are no environment variables): "chunk" / "bw_chunk" (samples per chunk of the
+ * forward / shrunk-gradient pass), "no_fused_gather", "conv_wt" (0..3), "conv_x16" (set before the weights are uploaded),
+ * "wt_flags", "sdp_no_coop", "bw_no_ws", "bw_no_tc8", "bw_no_tc", "bw_simt_fwd" select fallback kernels so that every code
+ * path can be held to the same parity bar.  The product path never calls this. */
+int nnal_debug_option(nnal_ctx* ctx, const char* name, long value);
 /* Declares a pool of n samples with the given float64 scores (no model, no pool pass): drives nnal_pool_topk /
  * nnal_pool_topk_device with arbitrary scores in tests. */
 int nnal_debug_set_pool_scores(nnal_ctx* ctx, const double* scores, int64_t n);

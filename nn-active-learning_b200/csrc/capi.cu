@@ -9,10 +9,26 @@
 static const int NNAL_VERSION = 100;
 static const int64_t DEFAULT_CHUNK = 16384;   // samples per forward chunk (measured: 8192 -> 16384 = +1.5 %, flat beyond)
 
-static int64_t chunk_size() {
-  const char* e = getenv("NNAL_CHUNK");
-  if (e) { long v = atol(e); if (v > 0) return v; }
-  return DEFAULT_CHUNK;
+static int64_t chunk_size(const nnal_ctx* ctx) { return ctx->dbg.chunk > 0 ? ctx->dbg.chunk : DEFAULT_CHUNK; }
+
+// test hook: kernel-selection switches (see DebugOpts).  Unknown names are an error.
+extern "C" int nnal_debug_option(nnal_ctx* ctx, const char* name, long value) {
+  if (!ctx || !name) return NNAL_ERR_INVALID;
+  const std::string n(name);
+  DebugOpts& d = ctx->dbg;
+  if (n == "chunk") d.chunk = value;
+  else if (n == "bw_chunk") d.bw_chunk = value;
+  else if (n == "no_fused_gather") d.no_fused_gather = (int)value;
+  else if (n == "wt_flags") d.wt_flags = (int)value;
+  else if (n == "sdp_no_coop") d.sdp_no_coop = (int)value;
+  else if (n == "bw_no_ws") d.bw_no_ws = (int)value;
+  else if (n == "bw_no_tc8") d.bw_no_tc8 = (int)value;
+  else if (n == "bw_no_tc") d.bw_no_tc = (int)value;
+  else if (n == "bw_simt_fwd") d.bw_simt_fwd = (int)value;
+  else if (n == "conv_wt") ctx->use_wt = (int)value;       // 0 conv_tc.cu only, 1 conv_wt.cu where faster, 2 (default) + pool fusion, 3 wherever supported
+  else if (n == "conv_x16") ctx->use_x16 = (int)value;     // conv1 on the x-im2col'd input (set BEFORE the weights are uploaded)
+  else NNAL_FAIL(ctx, NNAL_ERR_INVALID, "unknown debug option");
+  return NNAL_OK;
 }
 
 extern "C" int nnal_version(void) { return NNAL_VERSION; }
@@ -121,12 +137,9 @@ extern "C" int nnal_ctx_create(int device, nnal_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return NNAL_ERR_CUDA; }
   if (ovf_bind_device(ctx) != NNAL_OK) { cudaStreamDestroy(ctx->stream); delete ctx; return NNAL_ERR_CUDA; }
-  const char* f = getenv("NNAL_FORCE_SIMT");
-  ctx->use_tc = (f && atoi(f)) ? 0 : 1;
-  const char* fw = getenv("NNAL_CONV_WT");   // 0: conv_tc.cu only, 1: conv_wt.cu where faster, 2 (default): + pool fusion, 3: wherever supported
-  ctx->use_wt = fw ? atoi(fw) : 2;
-  const char* fx = getenv("NNAL_CONV_X16");
-  ctx->use_x16 = fx ? atoi(fx) : 0;      // measured: conv1 4.2 -> 3.2 ms but the gather writes twice the bytes (0.84 -> 1.6 ms): off by default
+  ctx->use_tc = 1;
+  ctx->use_wt = 2;                       // conv_wt.cu where it is the faster kernel, with the fused max-pool
+  ctx->use_x16 = 0;                      // measured: conv1 4.2 -> 3.2 ms but the gather writes twice the bytes (0.84 -> 1.6 ms): off
   *out = ctx;
   return NNAL_OK;
 }
@@ -632,10 +645,10 @@ static int pool_eval_impl(nnal_ctx* ctx, int subject, const int64_t* inds, bool 
   if (!inds) return NNAL_ERR_INVALID;
   double* d_stats;
   NNAL_TRY(upload_stats(ctx, stats, v->m, norm_mode, &d_stats));
-  const int64_t chunk = std::min(chunk_size(), n);
+  const int64_t chunk = std::min(chunk_size(ctx), n);
   NNAL_TRY(reserve_forward(ctx, chunk));
   // gather straight into the first conv's tensor-core input planes when it takes them
-  const bool fused_ok = getenv("NNAL_NO_FUSED_GATHER") == nullptr;
+  const bool fused_ok = !ctx->dbg.no_fused_gather;
   const bool fused16 = fused_ok && nnal_first_layer_wants_x16(ctx) && nnal_k_gather_x16_supported(*v, d1, d2, d3);
   const bool fused = fused_ok && !fused16 && nnal_first_layer_wants_split8(ctx) && nnal_k_gather_split_supported(*v, d3);
   const int64_t* d_inds = inds;
@@ -678,7 +691,7 @@ extern "C" int nnal_pool_eval_images(nnal_ctx* ctx, const float* x, int64_t n, i
   if (n < 0 || offset < 0 || offset + n > ctx->pool_n) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "pool range out of bounds");
   if (n == 0) return NNAL_OK;
   if (!x) return NNAL_ERR_INVALID;
-  const int64_t chunk = std::min(chunk_size(), n);
+  const int64_t chunk = std::min(chunk_size(ctx), n);
   NNAL_TRY(reserve_forward(ctx, chunk));
   const size_t per = (size_t)ctx->in_h * ctx->in_w * ctx->in_c;
   for (int64_t o = 0; o < n; o += chunk) {

@@ -531,7 +531,7 @@ static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal
   }
   Params p;
   p.wpack = (const uint8_t*)L.Wt; p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.n = (int)n; p.w_scale_inv = L.w_scale_inv;
-  { const char* f = getenv("NNAL_WT_FLAGS"); p.flags = f ? atoi(f) : 0; }
+  p.flags = ctx->dbg.wt_flags;
   const int ngroups = (int)((n + C::G - 1) / C::G);
   const int grid = ngroups < ctx->sm_count ? ngroups : ctx->sm_count;
   conv_wt_kernel<C><<<grid, C::THREADS, C::SMEM, ctx->stream>>>(tmHiL, tmLoL, tmHiU, tmLoU, p);

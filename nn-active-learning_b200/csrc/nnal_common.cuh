@@ -110,7 +110,19 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+// Test-only switches (nnal_debug_option): they select FALLBACK kernels or chunk sizes so that tests can hold every code path
+// to the same parity bar.  The product never sets them; there are no environment variables.
+struct DebugOpts {
+  long chunk = 0;              // samples per forward chunk (0: default)
+  long bw_chunk = 0;           // samples per chunk of the shrunk-gradient pass (0: default)
+  int no_fused_gather = 0;     // fp32 gather + separate split pass instead of the gather that writes conv1's planes
+  int wt_flags = 0;            // conv_wt.cu timing experiments: 1 skip the epilogue stores, 2 skip the lo plane
+  int sdp_no_coop = 0;         // one launch per SDP iteration instead of the cooperative loop
+  int bw_no_ws = 0, bw_no_tc8 = 0, bw_no_tc = 0, bw_simt_fwd = 0;   // shrunk.cu fallbacks
+};
+
 struct nnal_ctx {
+  DebugOpts dbg;
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;

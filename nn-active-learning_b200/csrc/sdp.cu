@@ -404,7 +404,7 @@ static int sdp_solve(nnal_ctx* ctx, int mode, const double* src, const double* p
   int64_t it = 0;
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
-  static const bool no_coop = getenv("NNAL_SDP_NO_COOP") != nullptr;
+  const bool no_coop = ctx->dbg.sdp_no_coop != 0;
   bool done = false;
   if (coop && !no_coop) {
     const double* a_At = At;

@@ -43,11 +43,7 @@ BwState* bw_state(nnal_ctx* ctx) {
   return (BwState*)ctx->bw_state;
 }
 
-int64_t bw_chunk() {
-  const char* e = getenv("NNAL_BW_CHUNK");
-  if (e) { long v = atol(e); if (v > 0) return v; }
-  return 2048;
-}
+int64_t bw_chunk(const nnal_ctx* ctx) { return ctx->dbg.bw_chunk > 0 ? ctx->dbg.bw_chunk : 2048; }
 
 inline int grid_for(const nnal_ctx* ctx, int64_t total, int per_sm) {
   int64_t b = (total + 255) / 256, cap = (int64_t)ctx->sm_count * per_sm;
@@ -284,7 +280,7 @@ int conv_bwd_pick(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, i
   const size_t tile = ((size_t)(L.in_h + L.kh - 1) * (L.in_w + L.kw - 1) * conv_bwd_cp(L.out_c) + 3) / 4 * 4 * sizeof(float);
   const size_t wbytes = (size_t)L.kh * L.kw * L.in_c * L.out_c * sizeof(float);
   if (tile > 200 * 1024) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient tile exceeds shared memory");
-  static const bool no_ws = getenv("NNAL_BW_NO_WS") != nullptr;
+  const bool no_ws = ctx->dbg.bw_no_ws != 0;
   const bool ws = !no_ws && tile + wbytes <= 220 * 1024;
   if constexpr (TC == 8) {
     if (ws) return conv_bwd_launch<4, TC, true, 512>(ctx, L, dz, d_in, n, tile + wbytes);
@@ -305,7 +301,7 @@ int conv_bwd_pick(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, i
 int conv_bwd_data(nnal_ctx* ctx, const Layer& L, const float* dz, float* d_in, int64_t n) {
   if (n == 0) return NNAL_OK;
   if (L.in_c > 256) NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient: more than 256 input channels");
-  static const bool no_tc8 = getenv("NNAL_BW_NO_TC8") != nullptr;
+  const bool no_tc8 = ctx->dbg.bw_no_tc8 != 0;
   if (!no_tc8 && L.in_c % 8 == 0 && L.in_h * L.in_w >= 400) return conv_bwd_pick<8>(ctx, L, dz, d_in, n);
   if (L.in_c % 4 == 0) return conv_bwd_pick<4>(ctx, L, dz, d_in, n);
   return conv_bwd_pick<1>(ctx, L, dz, d_in, n);
@@ -453,7 +449,7 @@ __global__ void __launch_bounds__(256) bw_split_transposed_kernel(const float* _
 }
 
 bool fc_bwd_tc_eligible(const nnal_ctx* ctx, const Layer& L) {
-  static const bool off = getenv("NNAL_BW_NO_TC") != nullptr;
+  const bool off = ctx->dbg.bw_no_tc != 0;
   return !off && L.type == NNAL_LAYER_FC && L.out_dim >= 64 && L.in_dim >= 64 && L.out_dim % 8 == 0 &&
          L.in_dim % 8 == 0;
 }
@@ -644,7 +640,7 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
   NNAL_TRY(devbuf_reserve(ctx, st->sred, (size_t)nb * tau * sizeof(double)));
   float* acts = (float*)st->acts.p;
   auto in_of = [&](int i) -> const float* { return i == 0 ? (const float*)ctx->xin.p : acts + offs[i - 1]; };
-  static const bool simt_fwd = getenv("NNAL_BW_SIMT_FWD") != nullptr;
+  const bool simt_fwd = ctx->dbg.bw_simt_fwd != 0;
   prof_begin(ctx, NNAL_PROF_BW_FORWARD);
   for (int i = 0; i < nl; ++i) {
     const Layer& L = ctx->layers[i];
@@ -782,7 +778,7 @@ extern "C" int nnal_fi_shrunk_images(nnal_ctx* ctx, const float* x, int64_t n, f
   NNAL_TRY(check_model(ctx));
   if (n == 0) return NNAL_OK;
   BwState* st = bw_state(ctx);
-  const int64_t chunk = std::min(bw_chunk(), n);
+  const int64_t chunk = std::min(bw_chunk(ctx), n);
   const size_t per = (size_t)ctx->in_h * ctx->in_w * ctx->in_c;
   NNAL_TRY(devbuf_reserve(ctx, ctx->xin, (size_t)chunk * per * sizeof(float)));
   for (int64_t o = 0; o < n; o += chunk) {
@@ -806,7 +802,7 @@ extern "C" int nnal_fi_shrunk_voxels(nnal_ctx* ctx, int subject, const int64_t* 
   double* d_stats;
   NNAL_TRY(nnal_upload_stats(ctx, stats, v->m, norm_mode, &d_stats));
   BwState* st = bw_state(ctx);
-  const int64_t chunk = std::min(bw_chunk(), n);
+  const int64_t chunk = std::min(bw_chunk(ctx), n);
   const size_t per = (size_t)ctx->in_h * ctx->in_w * ctx->in_c;
   NNAL_TRY(devbuf_reserve(ctx, ctx->xin, (size_t)chunk * per * sizeof(float)));
   NNAL_TRY(devbuf_reserve(ctx, ctx->inds, (size_t)n * 8));

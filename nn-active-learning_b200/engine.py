@@ -31,7 +31,7 @@ class Engine(object):
         self._model_token = None
         self._vol_keys = {}
         self._m = {}
-        self.volume_cache = os.environ.get('NNAL_VOLUME_CACHE', '1') != '0'
+        self.volume_cache = True
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -95,6 +95,10 @@ class Engine(object):
         self._chk(self.lib.nnal_pool_eval_device_inds(self.h, int(subject), C.c_void_p(int(d_inds_ptr)), int(n),
                                                       int(offset), d1, d2, d3,
                                                       None if st is None else _ptr(st), int(norm_mode)))
+
+    def debug_option(self, name, value):
+        """Test-only kernel-selection switch (``nnal_debug_option``)."""
+        self._chk(self.lib.nnal_debug_option(self.h, str(name).encode(), int(value)))
 
     def _load_scores_for_test(self, scores):
         s = np.ascontiguousarray(scores, dtype=np.float64).ravel()

@@ -94,7 +94,7 @@ def test_mc_entropy_single_volume(nb):
 
 
 def test_mc_masks_independent_of_chunking_and_sharding(nb):
-    """Same running means whether the pool is evaluated in one piece, in small chunks (NNAL_CHUNK), or as two shards
+    """Same running means whether the pool is evaluated in one piece, in small chunks (debug option "chunk"), or as two shards
     with their global position offsets (what two ranks do)."""
     ps, imgs, padded, stats, pool, layers, w = _pw_setup(333, 90)
     keep, T, seed = 0.7, 3, 7
@@ -115,11 +115,11 @@ def test_mc_masks_independent_of_chunking_and_sharding(nb):
             eng.pool_mc_config(0, 1., [])
         return eng.pool_mc_means()
     whole = run(0, len(pool))
-    os.environ['NNAL_CHUNK'] = '100'
+    eng.debug_option('chunk', 100)
     try:
         chunked = run(0, len(pool))
     finally:
-        del os.environ['NNAL_CHUNK']
+        eng.debug_option('chunk', 0)
     assert np.array_equal(whole[0], chunked[0]) and np.array_equal(whole[1], chunked[1])
     a, b = run(0, 150), run(150, len(pool))
     assert np.array_equal(np.concatenate([a[0], b[0]]), whole[0])

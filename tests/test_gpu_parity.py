@@ -310,16 +310,16 @@ def test_fused_gather_matches_unfused(nb):
     model = nb.NN.create_PW1(2)
     model.set_weights(w)
     a = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
-    os.environ['NNAL_NO_FUSED_GATHER'] = '1'
+    nb.get_engine().debug_option('no_fused_gather', 1)
     try:
         b = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
     finally:
-        del os.environ['NNAL_NO_FUSED_GATHER']
+        nb.get_engine().debug_option('no_fused_gather', 0)
     assert np.array_equal(a, b)
 
 
 def test_x_im2col_gather_path_matches(nb):
-    """NNAL_CONV_X16=1: the gather writes conv1's x-im2col'd planes (16 elements per position) and conv1 runs as a 5 x 1
+    """debug option conv_x16 = 1: the gather writes conv1's x-im2col'd planes (16 elements per position) and conv1 runs as a 5 x 1
     filter over 16 channels.  Same posteriors as the default path within accumulation-order noise, and the fused and
     unfused (fp32 gather + x-im2col split) variants of it agree bit for bit."""
     import os
@@ -327,19 +327,15 @@ def test_x_im2col_gather_path_matches(nb):
     model = nb.NN.create_PW1(2)
     model.set_weights(w)
     ref = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
-    os.environ['NNAL_CONV_X16'] = '1'
     try:
         nb.reset_engine()
+        nb.get_engine().debug_option('conv_x16', 1)          # before the weights are uploaded: conv1's packed form differs
         model2 = nb.NN.create_PW1(2)
         model2.set_weights(w)
         a = nb.PW_NN.batch_eval(model2, None, padded, pool, ps, 100, stats, 'posteriors')[0]
-        os.environ['NNAL_NO_FUSED_GATHER'] = '1'
-        try:
-            b = nb.PW_NN.batch_eval(model2, None, padded, pool, ps, 100, stats, 'posteriors')[0]
-        finally:
-            del os.environ['NNAL_NO_FUSED_GATHER']
+        nb.get_engine().debug_option('no_fused_gather', 1)
+        b = nb.PW_NN.batch_eval(model2, None, padded, pool, ps, 100, stats, 'posteriors')[0]
     finally:
-        del os.environ['NNAL_CONV_X16']
         nb.reset_engine()
     assert np.array_equal(a, b)
     assert np.abs(a - ref).max() < 2e-5

@@ -76,8 +76,11 @@ def test_shrunk_gradients_chunking(nb, monkeypatch):
     eng = nb.get_engine()
     eng.set_model(model, None)
     p1, g1 = eng.fi_shrunk_images(x)
-    monkeypatch.setenv('NNAL_BW_CHUNK', '16')
-    p2, g2 = eng.fi_shrunk_images(x)
+    eng.debug_option('bw_chunk', 16)
+    try:
+        p2, g2 = eng.fi_shrunk_images(x)
+    finally:
+        eng.debug_option('bw_chunk', 0)
     assert np.array_equal(g1, g2) and np.array_equal(p1, p2)
     p3, g3 = eng.fi_shrunk_images(x[:0])
     assert g3.shape == (3, 0, 6)
@@ -300,25 +303,30 @@ def test_shrunk_error_paths(nb):
     assert np.abs(g1 - g2).max() > 0
 
 
-@pytest.mark.parametrize('env', [
+@pytest.mark.parametrize('opts', [
     {},
-    {'NNAL_BW_SIMT_FWD': '1', 'NNAL_BW_NO_TC': '1', 'NNAL_BW_NO_WS': '1', 'NNAL_BW_NO_TC8': '1', 'NNAL_SDP_NO_COOP': '1'},
-    {'NNAL_BW_NO_WS': '1', 'NNAL_BW_CHUNK': '16'},
+    {'bw_simt_fwd': 1, 'bw_no_tc': 1, 'bw_no_ws': 1, 'bw_no_tc8': 1, 'sdp_no_coop': 1},
+    {'bw_no_ws': 1, 'bw_chunk': 16},
 ])
-def test_fallback_kernels_subprocess(env):
-    """The kernel-selection switches are read once per process, so the fallback kernels run in a subprocess: fp32
-    CUDA-core forward, fp32 fc gradient, conv filter through L2, 4-channel register tile, one launch per SDP iteration --
-    same parity bar as the default kernels."""
+def test_fallback_kernels(nb, opts):
+    """The fallback kernels behind the test-only switches (nnal_debug_option): fp32 CUDA-core forward, fp32 fc gradient,
+    conv filter through L2, 4-channel register tile, one launch per SDP iteration -- same parity bar as the default kernels."""
+    import importlib.util
     import os
-    import subprocess
-    import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    e = dict(os.environ)
-    e.update(env)
-    r = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'sdp_fallback_check.py')], env=e, stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, timeout=600)
-    out = r.stdout.decode()
-    assert r.returncode == 0 and 'OK ' in out, out[-2000:]
+    spec = importlib.util.spec_from_file_location('sdp_fallback_check', os.path.join(root, 'scripts', 'sdp_fallback_check.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    eng = nb.get_engine()
+    for k, v in opts.items():
+        eng.debug_option(k, v)
+    try:
+        mod.check()
+    finally:
+        for k in opts:
+            eng.debug_option(k, 0)
+    with pytest.raises(ValueError):
+        eng.debug_option('no_such_switch', 1)
 
 
 def test_sdp_from_shrunk_equals_host_assembly(nb):
