@@ -73,3 +73,40 @@ __device__ __forceinline__ void dot_um(const float* __restrict__ u, const float*
   mm = sm;
 }
 
+
+// Same inner products with the CANDIDATE row stored as fp16 (u16) and the winner row x in float32: the large-candidate-set
+// variant of the kernel column (fi.cu): the pass is bound by the bytes of the candidate rows, fp16 halves them.  The fp16 value
+// is exact in float32, products and sums as above.  d % 8 == 0.
+#include <cuda_fp16.h>
+__device__ __forceinline__ void dot_um_h8(const uint4 raw, const float* __restrict__ x, const float* __restrict__ beta2, int k,
+                                          bool mask, double& su, double& sm) {
+  const float4 q0 = *reinterpret_cast<const float4*>(x + k), q1 = *reinterpret_cast<const float4*>(x + k + 4);
+  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+  const float2 p01 = __half22float2(h2[0]), p23 = __half22float2(h2[1]), p45 = __half22float2(h2[2]), p67 = __half22float2(h2[3]);
+  float f0 = p01.x * q0.x, f1 = p01.y * q0.y, f2 = p23.x * q0.z, f3 = p23.y * q0.w;
+  f0 = fmaf(p45.x, q1.x, f0); f1 = fmaf(p45.y, q1.y, f1); f2 = fmaf(p67.x, q1.z, f2); f3 = fmaf(p67.y, q1.w, f3);
+  su += ((double)f0 + (double)f1) + ((double)f2 + (double)f3);
+  if (mask) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta2 + k)), b1 = __ldg(reinterpret_cast<const float4*>(beta2 + k + 4));
+    float g0 = (p01.x > 0.f && q0.x > 0.f) ? b0.x : 0.f, g1 = (p01.y > 0.f && q0.y > 0.f) ? b0.y : 0.f;
+    float g2 = (p23.x > 0.f && q0.z > 0.f) ? b0.z : 0.f, g3 = (p23.y > 0.f && q0.w > 0.f) ? b0.w : 0.f;
+    g0 += (p45.x > 0.f && q1.x > 0.f) ? b1.x : 0.f; g1 += (p45.y > 0.f && q1.y > 0.f) ? b1.y : 0.f;
+    g2 += (p67.x > 0.f && q1.z > 0.f) ? b1.z : 0.f; g3 += (p67.y > 0.f && q1.w > 0.f) ? b1.w : 0.f;
+    sm += ((double)g0 + (double)g1) + ((double)g2 + (double)g3);
+  }
+}
+__device__ __forceinline__ void dot_um_h(const __half* __restrict__ u16, const float* __restrict__ x,
+                                         const float* __restrict__ beta2, int d, bool mask, int lane, double& uu, double& mm) {
+  double su = 0.0, sm = 0.0;
+  int k = lane * 8;
+  for (; k + 3 * 256 < d; k += 4 * 256) {                 // four 16-byte candidate loads in flight per lane
+    uint4 raw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) raw[j] = *reinterpret_cast<const uint4*>(u16 + k + j * 256);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dot_um_h8(raw[j], x, beta2, k + j * 256, mask, su, sm);
+  }
+  for (; k < d; k += 256) dot_um_h8(*reinterpret_cast<const uint4*>(u16 + k), x, beta2, k, mask, su, sm);
+  uu = su;
+  mm = sm;
+}

@@ -29,6 +29,14 @@
 namespace fi {
 
 constexpr int T_SMEM = 152;          // largest t whose t x t float64 system fits one CTA's shared memory
+// From this many candidates on, the kernel column of a greedy step -- a pass over every candidate's factor rows, 32 KB per
+// candidate in float32: 4 GB per step at 125k candidates, HBM-bound -- reads compact fp16 copies of the rows (the winner's
+// row stays float32; K_jj, the winners' own factors and everything downstream stay float64/float32).  The rounding moves a
+// kernel entry by ~6e-6 relative (max 2.4e-5 on PW1 factors): the reduced objective the loop reports stays within 3e-5 of the
+// float64 value of the selected set and the selected SET is unchanged on the pools tried (order may swap at near-ties) --
+// inside the 1e-3 of the north star, but not inside the 1e-4 the small-pool parity tests hold the float32 path to, hence
+// the threshold.
+constexpr int64_t F16_MIN = 32768;
 
 struct DevScalars {
   double best_loss;
@@ -69,6 +77,10 @@ struct State {
   int blk_cap = 0;
   DevScalars* sc = nullptr;
   unsigned int* ticket = nullptr;        // last-block election of the fused eval + pick kernel
+  // large candidate sets: compact fp16 copies of the candidates' factor rows for the kernel-column pass (see F16_MIN)
+  __half *U16 = nullptr, *A16 = nullptr;
+  size_t cap_u16 = 0, cap_a16 = 0;
+  bool use16 = false;
   int inv_ready_for = -1;                // step whose inverse was computed by CTA 0 of the previous column kernel (-1: none)
   int64_t k_run = 0;                     // number of steps of the current selection (nnal_fi_begin)
   // Gram
@@ -164,6 +176,18 @@ __global__ void __launch_bounds__(256) setup_kernel(const float* __restrict__ U,
 // pivot, ~70 us at t = 100) and the column is a bandwidth-bound pass over every candidate's factor rows (~60 us at 10k
 // candidates): run as one launch they overlap, and CTA 0 being dispatched first guarantees it an SM (a separate stream does
 // not: the column's CTAs fill every SM for the whole kernel).
+__global__ void __launch_bounds__(256) rows_to_f16_kernel(const float* __restrict__ src, const int64_t* __restrict__ rows, int64_t n,
+                                                          int d, __half* __restrict__ dst) {
+  const int64_t total = n * (int64_t)(d / 2);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / (d / 2);
+    const int k = (int)(e - i * (d / 2)) * 2;
+    const int64_t r = rows ? rows[i] : i;
+    const float2 v = *reinterpret_cast<const float2*>(src + r * d + k);
+    *reinterpret_cast<__half2*>(dst + i * d + k) = __floats2half2_rn(v.x, v.y);
+  }
+}
+
 struct InvArgs { const double* kss; int64_t kss_ld; int t; double alpha; double* C; int ldc; DevScalars* sc; };
 template <int RT>
 __device__ __forceinline__ void invert_reg_body(const double* __restrict__ kss, int64_t kss_ld, int t, double alpha,
@@ -173,7 +197,8 @@ __global__ void __launch_bounds__(1024) column_kernel(const float* __restrict__ 
                                                        const int64_t* __restrict__ rows, const double* __restrict__ sw,
                                                        const float* __restrict__ beta2, const float* __restrict__ wu,
                                                        const float* __restrict__ wa, const double* __restrict__ wsw,
-                                                       int64_t n, int d, int dp, int nl, double* __restrict__ kcol, InvArgs inv) {
+                                                       int64_t n, int d, int dp, int nl, double* __restrict__ kcol, InvArgs inv,
+                                                       const __half* __restrict__ U16, const __half* __restrict__ A16) {
   if (blockIdx.x == 0) {
     if (inv.t >= 1) {
       if (inv.t <= 32) invert_reg_body<1>(inv.kss, inv.kss_ld, inv.t, inv.alpha, inv.C, inv.ldc, inv.sc);
@@ -186,6 +211,16 @@ __global__ void __launch_bounds__(1024) column_kernel(const float* __restrict__ 
   const int64_t warp = ((int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)(gridDim.x - 1) * blockDim.x) >> 5;
   const double s_w = *wsw;
+  if (U16) {                                               // compact fp16 candidate rows (row i = candidate i)
+    for (int64_t i = warp; i < n; i += nwarps) {
+      double s0, s1 = 0.0, s2, dummy;
+      dot_um_h(U16 + i * d, wu, beta2, d, nl == 2, lane, s0, s2);
+      if (nl == 2) dot_um_h(A16 + i * dp, wa, nullptr, dp, false, lane, s1, dummy);
+      const double uu = warp_sum(s0), aa = warp_sum(s1), mm = warp_sum(s2);
+      if (lane == 0) kcol[i] = sw[i] * s_w * pair_kernel(uu, aa, mm, nl);
+    }
+    return;
+  }
   for (int64_t i = warp; i < n; i += nwarps) {
     const int64_t r = rows ? rows[i] : i;
     double uu, aa, mm;
@@ -820,6 +855,16 @@ static int alloc_candidates(nnal_ctx* ctx, State* s, int64_t n) {
 }
 
 static int run_setup(nnal_ctx* ctx, State* s, const float* post1, const double* p1_given) {
+  s->use16 = s->n >= F16_MIN && s->d % 8 == 0 && (s->nl == 1 || s->dp % 8 == 0);
+  if (s->use16) {
+    const size_t nu = (size_t)s->n * s->d, na = s->nl == 2 ? (size_t)s->n * s->dp : 0;
+    if (s->cap_u16 < nu) { NNAL_TRY(ensure(ctx, s->U16, 0, nu)); s->cap_u16 = nu; }
+    if (na && s->cap_a16 < na) { NNAL_TRY(ensure(ctx, s->A16, 0, na)); s->cap_a16 = na; }
+    const int grid = ctx->sm_count * 16;
+    rows_to_f16_kernel<<<grid, 256, 0, ctx->stream>>>(s->U, s->R(), s->n, s->d, s->U16);
+    if (na) rows_to_f16_kernel<<<grid, 256, 0, ctx->stream>>>(s->A, s->R(), s->n, s->dp, s->A16);
+    ctx->launches += na ? 2 : 1;
+  }
   if (s->n == 0) return NNAL_OK;
   setup_kernel<<<warp_grid(ctx, s->n), 256, 0, ctx->stream>>>(s->U, s->A, s->R(), post1, p1_given, s->beta2, s->n, s->d,
                                                              s->dp, s->nl, s->w, s->sw, s->diag, s->avail);
@@ -937,7 +982,8 @@ static int step_column(nnal_ctx* ctx, State* s, int t) {
     const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((s->n + 31) / 32, (int64_t)ctx->sm_count * 4));
     column_kernel<<<(int)blocks + 1, 1024, 0, ctx->stream>>>(s->U, s->A, s->R(), s->sw, s->beta2, s->win_u,
                                                             s->nl == 2 ? s->win_a : nullptr, s->win_sw, s->n, s->d, s->dp,
-                                                            s->nl, s->kcols + (int64_t)t * s->kcols_n, inv);
+                                                            s->nl, s->kcols + (int64_t)t * s->kcols_n, inv,
+                                                            s->use16 ? s->U16 : nullptr, s->use16 ? s->A16 : nullptr);
     ctx->launches++;
     if (fuse) s->inv_ready_for = tn;
   }
@@ -960,7 +1006,7 @@ int nnal_fi_release(nnal_ctx* ctx) {
   State* s = (State*)ctx->fi_state;
   void* ptrs[] = {s->gids, s->rows, s->ownU, s->ownA, s->w, s->sw, s->diag, s->avail, s->beta2, s->kcols, s->kss, s->C, s->inv_ws,
                   s->red, s->win_sw, s->win_u, s->win_a, s->sel, s->blk_loss, s->blk_idx, s->sc, s->H, s->Xh, s->Xl, s->wq,
-                  s->sub_rows, s->sub_wq, s->gj_M, s->gj_R, s->gj_C, s->gj_D, s->gj_out, s->gj_R2, s->gj_C2, s->gj_D2};
+                  s->sub_rows, s->sub_wq, s->gj_M, s->gj_R, s->gj_C, s->gj_D, s->gj_out, s->gj_R2, s->gj_C2, s->gj_D2, s->U16, s->A16};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->ticket) cudaFree(s->ticket);
   delete s;
