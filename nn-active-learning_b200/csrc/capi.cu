@@ -25,6 +25,7 @@ extern "C" int nnal_debug_option(nnal_ctx* ctx, const char* name, long value) {
   else if (n == "bw_no_tc8") d.bw_no_tc8 = (int)value;
   else if (n == "bw_no_tc") d.bw_no_tc = (int)value;
   else if (n == "bw_simt_fwd") d.bw_simt_fwd = (int)value;
+  else if (n == "fi_flags") d.fi_flags = (int)value;
   else if (n == "conv_wt") ctx->use_wt = (int)value;       // 0 conv_tc.cu only, 1 conv_wt.cu where faster, 2 (default) + pool fusion, 3 wherever supported
   else if (n == "conv_x16") ctx->use_x16 = (int)value;     // conv1 on the x-im2col'd input (set BEFORE the weights are uploaded)
   else NNAL_FAIL(ctx, NNAL_ERR_INVALID, "unknown debug option");

@@ -82,6 +82,12 @@ struct State {
   size_t cap_u16 = 0, cap_a16 = 0;
   bool use16 = false;
   int inv_ready_for = -1;                // step whose inverse was computed by CTA 0 of the previous column kernel (-1: none)
+  // pipelined step (k_run <= PIPE_MAX_T): shifted inverses (two buffers), their traces, speculative column cache
+  double *pipeP = nullptr, *pipeTr = nullptr, *spec_cols = nullptr;
+  void *spec_state = nullptr, *spec_plan = nullptr;
+  int64_t spec_n = 0;
+  int pipe_have = -1;                    // last step whose service CTA ran (its shifted inverse is in buffer step & 1)
+  bool pipe = false, spec = false;
   int64_t k_run = 0;                     // number of steps of the current selection (nnal_fi_begin)
   // Gram
   float* H = nullptr;
@@ -555,6 +561,637 @@ __global__ void __launch_bounds__(256) eval_kernel(const double* __restrict__ kc
   if (threadIdx.x == 0) *ta.win_sw = ta.sw[i];
 }
 
+// =====================================================================================================================
+// Pipelined greedy step (selections of k <= PIPE_MAX_T steps).
+//
+// What bounds a greedy step at 10k candidates (measured, scripts/fi_only.py): candidate evaluation 21 us, the t x t
+// inverse 36 us on average (a latency-bound single-CTA job, 70 us at t = 100), the winner's kernel column 60 us (one pass
+// over every candidate's factor rows).  Three changes take all but the evaluation off the critical path:
+//
+//  (1) The inverse one step AHEAD.  Step t needs C_t = (a_t I + K_t)^-1, a_t = (t+1) delta, K_t = the winners' kernel.
+//      K_t is known when step t-1 has picked, but a "shifted" inverse P_{t-1} = (a_t I + K_{t-1})^-1 only needs the
+//      winners up to step t-2: it is computed by a SERVICE CTA (CTA 0, dispatched first) of step t-1's evaluation kernel,
+//      concurrently with that evaluation, and step t obtains C_t from it by the O(t^2) bordering identity
+//          C_t = [ P + v v^T / s   -v / s ]      v = P r,  s = a_t + K_tt - r.v,   r = K_t[t-1, 0:t-1],
+//                [   -v^T / s       1 / s ]      tr C_t = tr P + (|v|^2 + 1) / s
+//      which every CTA applies in shared memory (same code, same data: bit-identical C in every CTA and on every rank).
+//  (2) Blocked Gauss-Jordan for the service CTA: 8 pivots per block step (8 x 8 pivot block inverted by one warp with
+//      shuffles, rank-8 register-tile update) -- 3 barriers per 8 pivots instead of 8, ~2.7x faster than one pivot at a time.
+//  (3) Speculative kernel columns (single-process selection).  The next winner is nearly always one of the current
+//      runners-up (CPU replay on PW1 factors: inside the top 4 of the previous step's ranking in 95 % of the steps), and
+//      a kernel column K(., j) does not depend on the selection.  The pass over the candidates' rows is HBM-bound, so it
+//      computes the columns of the winner AND of the best runners-up for the bytes of one (their rows are staged in shared
+//      memory) and keeps the extra columns in a small cache; a step whose winner is cached copies the column instead of
+//      reading 32 KB per candidate.  Per (candidate, winner) pair the arithmetic is that of dot_um, bit for bit.
+// =====================================================================================================================
+constexpr int PIPE_MAX_T = 128;
+constexpr int SPEC_SLOTS = 16;       // cached speculative columns
+constexpr int SPEC_COLS = 4;         // columns per pass: the winner + 3 runners-up
+constexpr int PIPE_LDP = 128;        // row stride of the shifted inverses
+
+struct SpecPlan { int hit; int ncols; long long cand[SPEC_COLS]; int slot[SPEC_COLS]; };
+struct SpecState { long long tags[SPEC_SLOTS]; int fifo; int pad; };
+
+struct PipeArgs {
+  const double* P_prev;      // (a_t I + K_{t-1})^-1, (t-1) x (t-1), row stride PIPE_LDP
+  const double* trP_prev;
+  double* P_next;            // service CTA: (a_{t+1} I + K_t)^-1
+  double* trP_next;
+  const double* kss; int64_t kss_ld;
+  double alpha_next;
+  int do_next;
+  int rounds;                // pairs of 32-candidate groups per candidate CTA
+  SpecState* spec; SpecPlan* plan;     // null: no speculation
+};
+
+// C_t in shared memory from the shifted inverse (see above).  All threads of the CTA; returns tr C_t (same value in every
+// thread).  scratch: 2 * PIPE_MAX_T + 8 doubles.
+__device__ __forceinline__ double border_build(double* __restrict__ Cs, int ldc, int t, const PipeArgs& pa, double alpha,
+                                               double* __restrict__ scratch) {
+  const int tp = t - 1;
+  double* r = scratch;
+  double* v = scratch + PIPE_MAX_T;
+  double* sc = scratch + 2 * PIPE_MAX_T;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  for (int e0 = tid; e0 < tp * tp; e0 += 8 * nt) {          // eight loads in flight per thread
+    double pv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * nt;
+      const int i = e / tp, j = e - i * tp;
+      pv[u] = e < tp * tp ? pa.P_prev[i * PIPE_LDP + j] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * nt;
+      const int i = e / tp, j = e - i * tp;
+      if (e < tp * tp) Cs[i * ldc + j] = pv[u];
+    }
+  }
+  for (int j = tid; j < tp; j += nt) r[j] = pa.kss[(int64_t)tp * pa.kss_ld + j];
+  __syncthreads();
+  for (int i = warp; i < tp; i += nw) {
+    double a = 0.0;
+    for (int j = lane; j < tp; j += 32) a = fma(Cs[i * ldc + j], r[j], a);
+    a = warp_sum(a);
+    if (lane == 0) v[i] = a;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double rv = 0.0, vv = 0.0;
+    for (int j = lane; j < tp; j += 32) { rv = fma(r[j], v[j], rv); vv = fma(v[j], v[j], vv); }
+    rv = warp_sum(rv);
+    vv = warp_sum(vv);
+    if (lane == 0) {
+      const double s = alpha + pa.kss[(int64_t)tp * pa.kss_ld + tp] - rv;
+      const double is = 1.0 / s;
+      sc[0] = is;
+      sc[1] = (tp > 0 ? *pa.trP_prev : 0.0) + (vv + 1.0) * is;
+    }
+  }
+  __syncthreads();
+  const double is = sc[0];
+  for (int e = tid; e < t * ldc; e += nt) {
+    const int i = e / ldc, j = e - i * ldc;
+    double c;
+    if (j >= t) c = 0.0;
+    else if (i < tp && j < tp) c = fma(v[i] * is, v[j], Cs[e]);
+    else if (i == tp && j == tp) c = is;
+    else c = -v[i < tp ? i : j] * is;
+    Cs[e] = c;
+  }
+  const double trC = sc[1];
+  __syncthreads();
+  return trC;
+}
+
+// 1/x for x > 0: float reciprocal + two Newton steps in float64 (the relative error squares per step: 1e-7 -> 1e-14 -> below
+// one ulp).  An IEEE division is a ~40-instruction dependent sequence, and eight of them in a row are the critical path of a
+// block step of gj_blocked.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y = (double)__frcp_rn((float)x);
+  y = fma(y, fma(-x, y, 1.0), y);
+  y = fma(y, fma(-x, y, 1.0), y);
+  return y;
+}
+
+// Blocked in-place Gauss-Jordan inverse of alpha I + K[0:t,0:t] (SPD, no pivoting) by one CTA of 1024 threads: 32 x 32
+// thread grid, thread (ty,tx) owns M[ty+32a][tx+32b], a,b < RT.  Block step p eliminates rows/columns 8p..8p+7 with the
+// uniform update  M <- M' - Cm Rm:  M' = M with block row and block column p zeroed, Cm = block column p (its own 8 x 8
+// part replaced by -I), Rm = D^-1 [block row p with D replaced by I], D = the 8 x 8 pivot block.
+// sm: 5 * 8 * 32 RT + 64 doubles.
+template <int RT>
+__device__ void gj_blocked(const double* __restrict__ kss, int64_t kss_ld, int t, double alpha, double* __restrict__ out,
+                           double* __restrict__ tr_out, double* __restrict__ sm) {
+  constexpr int T = 32 * RT;
+  double* Rraw = sm;                  // [2][8][T]
+  double* Cc = Rraw + 2 * 8 * T;      // [2][8][T]
+  double* Rm = Cc + 2 * 8 * T;        // [8][T]
+  double* Dinv = Rm + 8 * T;          // [8][8]
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  double m[RT][RT];
+#pragma unroll
+  for (int a = 0; a < RT; ++a)
+#pragma unroll
+    for (int b = 0; b < RT; ++b) {
+      const int i = ty + 32 * a, j = tx + 32 * b;
+      m[a][b] = (i < t && j < t) ? kss[(int64_t)i * kss_ld + j] + (i == j ? alpha : 0.0) : (i == j ? 1.0 : 0.0);
+    }
+  const int nblk = (t + 7) >> 3;
+  for (int p = 0; p < nblk; ++p) {
+    double* Rr = Rraw + (p & 1) * 8 * T;
+    double* Cb = Cc + (p & 1) * 8 * T;
+    const int pq = p >> 2, ph = p & 3;                 // rows/columns 32 pq + 8 ph .. + 7
+    const bool rowin = (ty >> 3) == ph, colin = (tx >> 3) == ph;
+#pragma unroll
+    for (int a = 0; a < RT; ++a)
+#pragma unroll
+      for (int b = 0; b < RT; ++b) {
+        const bool ri = rowin && a == pq, ci = colin && b == pq;
+        if (ri) Rr[(ty & 7) * T + tx + 32 * b] = m[a][b];
+        if (ci) Cb[(tx & 7) * T + ty + 32 * a] = ri ? ((ty & 7) == (tx & 7) ? -1.0 : 0.0) : m[a][b];
+        if (ri || ci) m[a][b] = 0.0;
+      }
+    __syncthreads();
+    if (threadIdx.x < 32) {                            // 8 x 8 pivot block: lane q (and its mirrors q + 8, ..) holds row q
+      const int q = tx & 7;
+      double row[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) row[c] = Rr[q * T + 8 * p + c];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const double inv = fast_rcp(__shfl_sync(0xffffffffu, row[kk], kk));
+        const double ci = q == kk ? -1.0 : row[kk];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const double rkc = __shfl_sync(0xffffffffu, c == kk ? 1.0 : row[c], kk) * inv;     // scaled pivot row
+          row[c] = fma(-ci, rkc, (q == kk || c == kk) ? 0.0 : row[c]);
+        }
+      }
+      if (tx < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Dinv[q * 8 + c] = row[c];
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 8 * T; e += 1024) {
+      const int q = e / T, j = e - q * T;
+      double v;
+      if ((j >> 3) == p) v = Dinv[q * 8 + (j & 7)];
+      else {
+        v = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) v = fma(Dinv[q * 8 + rr], Rr[rr * T + j], v);
+      }
+      Rm[e] = v;
+    }
+    __syncthreads();
+    const bool last_rows = ty + 32 * (RT - 1) < 8 * nblk;      // warp-uniform: rows past the last block stay identity rows
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      double cc[RT], nr[RT];
+#pragma unroll
+      for (int a = 0; a < RT; ++a) cc[a] = Cb[q * T + ty + 32 * a];
+#pragma unroll
+      for (int b = 0; b < RT; ++b) nr[b] = Rm[q * T + tx + 32 * b];
+#pragma unroll
+      for (int a = 0; a < RT; ++a) {
+        if (a < RT - 1 || last_rows) {
+#pragma unroll
+          for (int b = 0; b < RT; ++b) m[a][b] = fma(-cc[a], nr[b], m[a][b]);
+        }
+      }
+    }
+  }
+  double tr = 0.0;
+#pragma unroll
+  for (int a = 0; a < RT; ++a)
+#pragma unroll
+    for (int b = 0; b < RT; ++b) {
+      const int i = ty + 32 * a, j = tx + 32 * b;
+      if (i < t && j < t) out[i * PIPE_LDP + j] = m[a][b];
+      if (i == j && i < t) tr += m[a][b];
+    }
+  tr = warp_sum(tr);
+  __syncthreads();
+  if (tx == 0) sm[ty] = tr;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int q = 0; q < 32; ++q) s += sm[q];
+    *tr_out = s;
+  }
+}
+
+__device__ __forceinline__ bool loss_less(double la, long long ia, double lb, long long ib) { return la < lb || (la == lb && ia < ib); }
+
+// Evaluation of step t, pipelined form (t <= PIPE_MAX_T).  grid = 1 + candidate CTAs, 1024 threads.
+//   CTA 0 (service): tr C_t for the protocols, then the shifted inverse of the NEXT step.
+//   CTA c >= 1: C_t by bordering, then `rounds` tiles of `cpc` candidates (cpc a multiple of 4, <= 128; the host sizes cpc so
+//   that one tile per CTA covers all candidates with every SM busy).  A tile is the product Y = C K (t x t by t x cpc) with
+//   both operands in shared memory, register-tiled: warp w owns candidates 4w..4w+3, lane l the rows 4l..4l+3 of Y (16
+//   accumulators); r_j = k_j.y_j and e_j = |y_j|^2 are warp reductions.  Every CTA leaves its two best candidates
+//   (blk_loss/blk_idx[2 c], [2 c + 1]); the last CTA to finish picks the global winner, and (speculation) plans the column
+//   pass: a cache hit, or the winner + the best uncached runners-up.
+__global__ void __launch_bounds__(1024, 1) eval_pipe_kernel(const double* __restrict__ kcols, int64_t kn, const double* __restrict__ diag,
+                                                            const unsigned char* __restrict__ avail, int t, int ldc, int64_t n,
+                                                            double alpha, double* __restrict__ blk_loss,
+                                                            long long* __restrict__ blk_idx, int cpc, TailArgs ta, PipeArgs pa) {
+  extern __shared__ double sm_d[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* Cs = sm_d;                                   // [t][ldc] + 128 doubles of slack (rows >= t of a lane's tile read past the end)
+  double* Ks = Cs + (size_t)t * ldc + 128;             // [t + 4][cpc]
+  double* scratch = Ks + (size_t)(t + 4) * cpc;        // 2 PIPE_MAX_T + 8
+  if (blockIdx.x == 0) {
+    if (t == 0) {
+      if (tid == 0) { *pa.trP_next = 0.0; ta.sc->trC = 0.0; }
+      return;
+    }
+    const double trC = border_build(Cs, ldc, t, pa, alpha, scratch);
+    if (tid == 0) ta.sc->trC = trC;
+    if (!pa.do_next) return;
+    __syncthreads();
+    if (t <= 32) gj_blocked<1>(pa.kss, pa.kss_ld, t, pa.alpha_next, pa.P_next, pa.trP_next, sm_d);
+    else if (t <= 64) gj_blocked<2>(pa.kss, pa.kss_ld, t, pa.alpha_next, pa.P_next, pa.trP_next, sm_d);
+    else if (t <= 96) gj_blocked<3>(pa.kss, pa.kss_ld, t, pa.alpha_next, pa.P_next, pa.trP_next, sm_d);
+    else gj_blocked<4>(pa.kss, pa.kss_ld, t, pa.alpha_next, pa.P_next, pa.trP_next, sm_d);
+    return;
+  }
+  double trC = 0.0;
+  if (t >= 1) trC = border_build(Cs, ldc, t, pa, alpha, scratch);
+  double bl1 = INFINITY, bl2 = INFINITY;               // the CTA's two best (kept by every thread of a warp, merged below)
+  long long bi1 = 0x7fffffffffffffffll, bi2 = 0x7fffffffffffffffll;
+  const int ntx = cpc >> 2;                            // warps with candidates
+  for (int rd = 0; rd < pa.rounds; ++rd) {
+    const int64_t j0 = ((int64_t)(blockIdx.x - 1) * pa.rounds + rd) * cpc;
+    if (j0 >= n) break;
+    // K tile: eight loads in flight per thread
+    const int tot = t * cpc;
+    for (int e0 = tid; e0 < tot; e0 += 8 * 1024) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * 1024;
+        const int bq = e / cpc, c = e - bq * cpc;
+        v[u] = (e < tot && j0 + c < n) ? kcols[(int64_t)bq * kn + j0 + c] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (e0 + u * 1024 < tot) Ks[e0 + u * 1024] = v[u];
+    }
+    for (int e = tot + tid; e < (t + 4) * cpc; e += 1024) Ks[e] = 0.0;     // rows t..t+3 (read by the lane that straddles t)
+    __syncthreads();
+    if (warp < ntx) {
+      const int a0 = 4 * lane;
+      double rr[4] = {0.0, 0.0, 0.0, 0.0}, ee[4] = {0.0, 0.0, 0.0, 0.0};
+      double dg[4];
+      bool av[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {                    // issued before the product: their latency hides behind it
+        const int64_t j = j0 + 4 * warp + c;
+        av[c] = j < n && avail[j];
+        dg[c] = diag[j < n ? j : 0];
+      }
+      if (a0 < t) {
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[i][c] = 0.0;
+        const double* cp = Cs + a0;
+        const double* kp = Ks + 4 * warp;
+#pragma unroll 2
+        for (int bq = 0; bq < t; ++bq) {
+          const double2 c01 = *reinterpret_cast<const double2*>(cp + (size_t)bq * ldc);
+          const double2 c23 = *reinterpret_cast<const double2*>(cp + (size_t)bq * ldc + 2);
+          const double2 k01 = *reinterpret_cast<const double2*>(kp + (size_t)bq * cpc);
+          const double2 k23 = *reinterpret_cast<const double2*>(kp + (size_t)bq * cpc + 2);
+          const double cv[4] = {c01.x, c01.y, c23.x, c23.y}, kv[4] = {k01.x, k01.y, k23.x, k23.y};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][c] = fma(cv[i], kv[c], acc[i][c]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (a0 + i < t) {
+            const double2 k01 = *reinterpret_cast<const double2*>(kp + (size_t)(a0 + i) * cpc);
+            const double2 k23 = *reinterpret_cast<const double2*>(kp + (size_t)(a0 + i) * cpc + 2);
+            const double kv[4] = {k01.x, k01.y, k23.x, k23.y};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { rr[c] = fma(kv[c], acc[i][c], rr[c]); ee[c] = fma(acc[i][c], acc[i][c], ee[c]); }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double r = warp_sum(rr[c]), e2 = warp_sum(ee[c]);
+        const int64_t j = j0 + 4 * warp + c;
+        double loss = INFINITY;
+        if (av[c]) {
+          loss = (1.0 + e2) / (alpha + (dg[c] - r));
+          if (!(loss == loss)) loss = INFINITY;
+        }
+        const long long idx = (j < n) ? (long long)j : 0x7fffffffffffffffll;
+        if (loss_less(loss, idx, bl1, bi1)) { bl2 = bl1; bi2 = bi1; bl1 = loss; bi1 = idx; }
+        else if (loss_less(loss, idx, bl2, bi2)) { bl2 = loss; bi2 = idx; }
+      }
+    }
+    __syncthreads();
+  }
+  // the CTA's two best over its warps (every lane of a warp holds the warp's pair)
+  {
+    double* ml = scratch;                               // [64]
+    long long* mi = reinterpret_cast<long long*>(scratch + 64);
+    if (lane == 0) { ml[2 * warp] = bl1; mi[2 * warp] = bi1; ml[2 * warp + 1] = bl2; mi[2 * warp + 1] = bi2; }
+    __syncthreads();
+    if (tid == 0) {
+      double l1 = INFINITY, l2 = INFINITY;
+      long long i1 = 0x7fffffffffffffffll, i2 = 0x7fffffffffffffffll;
+      for (int q = 0; q < 64; ++q) {
+        if (loss_less(ml[q], mi[q], l1, i1)) { l2 = l1; i2 = i1; l1 = ml[q]; i1 = mi[q]; }
+        else if (loss_less(ml[q], mi[q], l2, i2)) { l2 = ml[q]; i2 = mi[q]; }
+      }
+      const int g = blockIdx.x - 1;
+      blk_loss[2 * g] = l1; blk_idx[2 * g] = i1; blk_loss[2 * g + 1] = l2; blk_idx[2 * g + 1] = i2;
+    }
+  }
+  const int64_t ngroups = gridDim.x - 1;
+  // ---- tail: the last candidate CTA to finish picks the global winner
+  __shared__ unsigned int s_last;
+  __shared__ double s_rl[32];
+  __shared__ long long s_ri[32];
+  __shared__ long long s_chosen[SPEC_COLS + SPEC_SLOTS + 4];
+  __shared__ int s_nch, s_ncols, s_done;
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(ta.ticket, 1u) == gridDim.x - 2 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const volatile double* vl = blk_loss;
+  const volatile long long* vi = blk_idx;
+  const int64_t nent = 2 * ngroups;
+  // block-wide arg-min over the group lists, skipping the ids in s_chosen[0..nch)
+  auto block_best = [&](int nch, double& bl, long long& bi) {
+    double loss = INFINITY;
+    long long idx = 0x7fffffffffffffffll;
+    for (int64_t b = tid; b < nent; b += 1024) {
+      const double ol = vl[b];
+      const long long oi = vi[b];
+      bool skip = false;
+      for (int c = 0; c < nch; ++c) skip |= (s_chosen[c] == oi);
+      if (!skip && loss_less(ol, oi, loss, idx)) { loss = ol; idx = oi; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ol = __shfl_xor_sync(0xffffffffu, loss, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (loss_less(ol, oi, loss, idx)) { loss = ol; idx = oi; }
+    }
+    if (lane == 0) { s_rl[warp] = loss; s_ri[warp] = idx; }
+    __syncthreads();
+    bl = s_rl[0]; bi = s_ri[0];
+    for (int q = 1; q < 32; ++q)
+      if (loss_less(s_rl[q], s_ri[q], bl, bi)) { bl = s_rl[q]; bi = s_ri[q]; }
+    __syncthreads();
+  };
+  double loss; long long idx;
+  block_best(0, loss, idx);
+  const bool found = loss < INFINITY;
+  if (!found) idx = -1;
+  if (tid == 0) {
+    ta.sc->best_loss = loss;
+    ta.sc->best_idx = idx;
+    if (ta.commit) {
+      if (found) ta.avail[idx] = 0;
+      ta.sel[t] = idx;
+      ta.red[t] = (double)(t + 1) * (trC + loss);
+    }
+    *ta.ticket = 0u;
+  }
+  if (!ta.copy || idx < 0) {
+    if (tid == 0 && pa.plan) { pa.plan->hit = -1; pa.plan->ncols = 0; }
+    return;
+  }
+  const long long i = idx;
+  for (int a = tid; a <= t; a += 1024) {
+    const double v = a < t ? kcols[(int64_t)a * kn + i] : diag[i];
+    ta.kss[(int64_t)t * ta.kss_ld + a] = v;
+    ta.kss[(int64_t)a * ta.kss_ld + t] = v;
+  }
+  if (!pa.plan) {
+    // no speculation: the column kernel reads the winner's factor rows from the winner slot
+    const int64_t row = ta.rows ? ta.rows[i] : i;
+    for (int k = tid; k < ta.d; k += 1024) ta.win_u[k] = ta.U[row * ta.d + k];
+    if (ta.A) for (int k = tid; k < ta.dp; k += 1024) ta.win_a[k] = ta.A[row * ta.dp + k];
+    if (tid == 0) *ta.win_sw = ta.sw[i];
+    return;
+  }
+  // ---- plan of the column pass
+  __shared__ long long s_tags[SPEC_SLOTS];
+  if (tid < SPEC_SLOTS) s_tags[tid] = pa.spec->tags[tid];
+  __syncthreads();
+  if (tid == 0) {
+    int hit = -1;
+    for (int q = 0; q < SPEC_SLOTS; ++q) if (s_tags[q] == i) hit = q;
+    pa.plan->hit = hit;
+    if (hit >= 0) pa.spec->tags[hit] = -1;
+    s_done = hit >= 0;
+    s_chosen[0] = i;
+    s_nch = 1;
+    s_ncols = 1;
+    pa.plan->cand[0] = i;
+    pa.plan->slot[0] = -1;
+    if (hit >= 0) pa.plan->ncols = 0;
+  }
+  __syncthreads();
+  if (s_done) return;
+  for (int round = 0; round < SPEC_COLS - 1 + SPEC_SLOTS; ++round) {
+    double bl; long long bi;
+    block_best(s_nch, bl, bi);
+    if (tid == 0) {
+      if (!(bl < INFINITY)) s_done = 1;
+      else {
+        s_chosen[s_nch++] = bi;
+        bool cached = false;
+        for (int q = 0; q < SPEC_SLOTS; ++q) cached |= (s_tags[q] == bi);
+        if (!cached) {
+          const int slot = pa.spec->fifo;
+          pa.spec->fifo = (slot + 1) % SPEC_SLOTS;
+          pa.spec->tags[slot] = bi;
+          s_tags[slot] = bi;
+          pa.plan->cand[s_ncols] = bi;
+          pa.plan->slot[s_ncols] = slot;
+          if (++s_ncols == SPEC_COLS) s_done = 1;
+        }
+      }
+    }
+    __syncthreads();
+    if (s_done) break;
+  }
+  if (tid == 0) pa.plan->ncols = s_ncols;
+}
+
+// The inner products of dot_um for NC winners at once: the candidate row is loaded once, the winners' rows come from
+// shared memory.  Per (candidate, winner) pair the operations and their order are exactly dot_um's.
+template <int NC>
+__device__ __forceinline__ void dot_um_multi(const float* __restrict__ u, const float* __restrict__ xs, int xstride,
+                                             const float* __restrict__ beta2, int d, bool mask, int lane, double (&uu)[NC],
+                                             double (&mm)[NC]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { uu[c] = 0.0; mm[c] = 0.0; }
+  int k = lane * 4;
+  for (; k + 3 * 128 < d; k += 4 * 128) {
+    float4 p[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = *reinterpret_cast<const float4*>(u + k + i * 128);
+    if (mask) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(beta2 + k + i * 128));
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      float4 q[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const float4*>(xs + (size_t)c * xstride + k + i * 128);
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f0 = fmaf(p[i].x, q[i].x, f0);
+        f1 = fmaf(p[i].y, q[i].y, f1);
+        f2 = fmaf(p[i].z, q[i].z, f2);
+        f3 = fmaf(p[i].w, q[i].w, f3);
+      }
+      uu[c] += ((double)f0 + (double)f1) + ((double)f2 + (double)f3);
+      if (mask) {
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          g0 += (p[i].x > 0.f && q[i].x > 0.f) ? b[i].x : 0.f;
+          g1 += (p[i].y > 0.f && q[i].y > 0.f) ? b[i].y : 0.f;
+          g2 += (p[i].z > 0.f && q[i].z > 0.f) ? b[i].z : 0.f;
+          g3 += (p[i].w > 0.f && q[i].w > 0.f) ? b[i].w : 0.f;
+        }
+        mm[c] += ((double)g0 + (double)g1) + ((double)g2 + (double)g3);
+      }
+    }
+  }
+  for (; k < d; k += 128) {
+    const float4 p = *reinterpret_cast<const float4*>(u + k);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mask) b = __ldg(reinterpret_cast<const float4*>(beta2 + k));
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float4 q = *reinterpret_cast<const float4*>(xs + (size_t)c * xstride + k);
+      uu[c] += ((double)(p.x * q.x) + (double)(p.y * q.y)) + ((double)(p.z * q.z) + (double)(p.w * q.w));
+      if (mask)
+        mm[c] += (double)((p.x > 0.f && q.x > 0.f) ? b.x : 0.f) + (double)((p.y > 0.f && q.y > 0.f) ? b.y : 0.f) +
+                 (double)((p.z > 0.f && q.z > 0.f) ? b.z : 0.f) + (double)((p.w > 0.f && q.w > 0.f) ? b.w : 0.f);
+    }
+  }
+}
+
+// fp16 candidate rows (see dot_um_h)
+template <int NC>
+__device__ __forceinline__ void dot_um_h_multi(const __half* __restrict__ u16, const float* __restrict__ xs, int xstride,
+                                               const float* __restrict__ beta2, int d, bool mask, int lane, double (&uu)[NC],
+                                               double (&mm)[NC]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { uu[c] = 0.0; mm[c] = 0.0; }
+  int k = lane * 8;
+  for (; k + 3 * 256 < d; k += 4 * 256) {
+    uint4 raw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) raw[j] = *reinterpret_cast<const uint4*>(u16 + k + j * 256);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dot_um_h8(raw[j], xs + (size_t)c * xstride, beta2, k + j * 256, mask, uu[c], mm[c]);
+  }
+  for (; k < d; k += 256) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(u16 + k);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) dot_um_h8(raw, xs + (size_t)c * xstride, beta2, k, mask, uu[c], mm[c]);
+  }
+}
+
+struct ColArgs {
+  const float* U; const float* A; const int64_t* rows; const double* sw; const float* beta2;
+  int64_t n; int d, dp, nl;
+  double* kcol;              // kcols[t]
+  double* spec_cols; int64_t spec_ld;
+  const __half* U16; const __half* A16;
+  const SpecPlan* plan;
+};
+
+template <int NC>
+__device__ __forceinline__ void column_pass(const ColArgs& ca, const float* __restrict__ xs, int xstride, const long long* cand,
+                                            double* const* dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double swc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) swc[c] = ca.sw[cand[c]];
+  const float* xa = xs + ca.d;                       // per winner: [u row (d) | a row (dp)]
+  for (int64_t i = warp; i < ca.n; i += nwarps) {
+    double uu[NC], mm[NC], aa[NC], dm[NC];
+    if (ca.U16) {
+      dot_um_h_multi<NC>(ca.U16 + i * ca.d, xs, xstride, ca.beta2, ca.d, ca.nl == 2, lane, uu, mm);
+      if (ca.nl == 2) dot_um_h_multi<NC>(ca.A16 + i * ca.dp, xa, xstride, nullptr, ca.dp, false, lane, aa, dm);
+    } else {
+      const int64_t r = ca.rows ? ca.rows[i] : i;
+      dot_um_multi<NC>(ca.U + r * ca.d, xs, xstride, ca.beta2, ca.d, ca.nl == 2, lane, uu, mm);
+      if (ca.nl == 2) dot_um_multi<NC>(ca.A + r * ca.dp, xa, xstride, nullptr, ca.dp, false, lane, aa, dm);
+    }
+    const double swi = ca.sw[i];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double a = ca.nl == 2 ? warp_sum(aa[c]) : 0.0;
+      const double u = warp_sum(uu[c]), m = warp_sum(mm[c]);
+      if (lane == 0) dst[c][i] = swi * swc[c] * pair_kernel(u, a, m, ca.nl);
+    }
+  }
+}
+
+// Kernel columns of one greedy step, driven by the plan the evaluation's tail left: a cache hit copies the cached column;
+// otherwise one pass over the candidates' rows computes the winner's column and the speculative ones.
+__global__ void __launch_bounds__(512, 1) column_spec_kernel(ColArgs ca) {
+  extern __shared__ float xs_f[];
+  const SpecPlan pl = *ca.plan;
+  if (pl.hit >= 0) {
+    const double* src = ca.spec_cols + (int64_t)pl.hit * ca.spec_ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ca.n; i += (int64_t)gridDim.x * blockDim.x) ca.kcol[i] = src[i];
+    return;
+  }
+  const int nc = pl.ncols;
+  if (nc <= 0) return;
+  const int xstride = ca.d + ca.dp;
+  __shared__ long long cand[SPEC_COLS];
+  __shared__ double* dst[SPEC_COLS];
+  if (threadIdx.x < SPEC_COLS) {
+    cand[threadIdx.x] = pl.cand[threadIdx.x < nc ? threadIdx.x : 0];
+    dst[threadIdx.x] = pl.slot[threadIdx.x] < 0 || threadIdx.x >= nc ? ca.kcol : ca.spec_cols + (int64_t)pl.slot[threadIdx.x] * ca.spec_ld;
+  }
+  for (int c = 0; c < nc; ++c) {
+    const int64_t r = ca.rows ? ca.rows[pl.cand[c]] : pl.cand[c];
+    const float4* su = reinterpret_cast<const float4*>(ca.U + r * ca.d);
+    float4* du = reinterpret_cast<float4*>(xs_f + (size_t)c * xstride);
+    for (int k = threadIdx.x; k < ca.d / 4; k += blockDim.x) du[k] = su[k];
+    if (ca.nl == 2) {
+      const float4* sa = reinterpret_cast<const float4*>(ca.A + r * ca.dp);
+      float4* da = reinterpret_cast<float4*>(xs_f + (size_t)c * xstride + ca.d);
+      for (int k = threadIdx.x; k < ca.dp / 4; k += blockDim.x) da[k] = sa[k];
+    }
+  }
+  __syncthreads();
+  if (nc == 1) column_pass<1>(ca, xs_f, xstride, cand, dst);
+  else if (nc == 2) column_pass<2>(ca, xs_f, xstride, cand, dst);
+  else if (nc == 3) column_pass<3>(ca, xs_f, xstride, cand, dst);
+  else column_pass<4>(ca, xs_f, xstride, cand, dst);
+}
+
 __global__ void mark_taken_kernel(unsigned char* avail, long long idx) { avail[idx] = 0; }
 
 // ---- device-resident multi-rank step: every rank packs its local best into a fixed-size message, the messages
@@ -892,12 +1529,85 @@ static int alloc_greedy(nnal_ctx* ctx, State* s, int64_t k) {
     s->win_d = s->d;
     s->win_dp = s->dp;
   }
-  const int nblk = cdiv(std::max<int64_t>(s->n, 1), EVAL_CAND);
+  const int nblk = std::max(cdiv(std::max<int64_t>(s->n, 1), EVAL_CAND), 2 * ctx->sm_count);   // (pipelined evaluation: two entries per CTA)
   if (s->blk_cap < nblk) {
     NNAL_TRY(ensure(ctx, s->blk_loss, 0, (size_t)nblk));
     NNAL_TRY(ensure(ctx, s->blk_idx, 0, (size_t)nblk));
     s->blk_cap = nblk;
   }
+  if (!s->pipeP) {
+    NNAL_TRY(ensure(ctx, s->pipeP, 0, (size_t)2 * PIPE_MAX_T * PIPE_LDP));
+    NNAL_TRY(ensure(ctx, s->pipeTr, 0, (size_t)2));
+    CUDA_TRY(ctx, cudaMalloc(&s->spec_state, sizeof(SpecState)));
+    CUDA_TRY(ctx, cudaMalloc(&s->spec_plan, sizeof(SpecPlan)));
+  }
+  return NNAL_OK;
+}
+
+// dynamic shared memory of eval_pipe_kernel at step t (candidate CTAs: C, the K slice of 64 candidates, partial sums, bordering
+// scratch; service CTA: the blocked Gauss-Jordan panels)
+constexpr size_t PIPE_SMEM_MAX = 226 * 1024;          // dynamic shared memory an eval_pipe_kernel launch may ask for
+static size_t pipe_smem(int t, int cpc) {
+  const int ldc = (t + 7) / 8 * 8;
+  const size_t cand = ((size_t)t * ldc + 128 + (size_t)(t + 4) * cpc + 2 * PIPE_MAX_T + 8) * sizeof(double);
+  const size_t serv = ((size_t)5 * 8 * PIPE_MAX_T + 64) * sizeof(double);
+  return std::max(cand, serv);
+}
+
+__global__ void __launch_bounds__(1024, 1) shifted_inverse_kernel(const double* kss, int64_t kss_ld, int t, double alpha, double* P,
+                                                                  double* trP) {
+  extern __shared__ double sm_d[];
+  if (t <= 32) gj_blocked<1>(kss, kss_ld, t, alpha, P, trP, sm_d);
+  else if (t <= 64) gj_blocked<2>(kss, kss_ld, t, alpha, P, trP, sm_d);
+  else if (t <= 96) gj_blocked<3>(kss, kss_ld, t, alpha, P, trP, sm_d);
+  else gj_blocked<4>(kss, kss_ld, t, alpha, P, trP, sm_d);
+}
+
+// pipelined evaluation of step t (see eval_pipe_kernel); with n == 0 only the service CTA runs (tr C for the protocols)
+static int step_select_pipe(nnal_ctx* ctx, State* s, int t, int commit, int copy) {
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(eval_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM_MAX));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(shifted_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem(1, 4)));
+    attr = true;
+  }
+  const double alpha = (double)(t + 1) * s->delta;
+  if (t >= 2 && s->pipe_have != t - 1) {
+    // steps taken out of order (or the previous step evaluated elsewhere): the shifted inverse of step t - 1 directly
+    shifted_inverse_kernel<<<1, 1024, pipe_smem(1, 4), ctx->stream>>>(s->kss, s->kcap, t - 1, alpha, s->pipeP + (size_t)((t - 1) & 1) * PIPE_MAX_T * PIPE_LDP,
+                                                                  s->pipeTr + ((t - 1) & 1));
+    ctx->launches++;
+  }
+  const int ldc = (t + 7) / 8 * 8;
+  // tiles of cpc candidates (multiple of 4, <= 128): one tile per CTA and round, every SM but the service CTA's busy
+  // (the widest tile is what fits next to C at the LAST step of the run, so that the tiling is the same at every step)
+  const int max_cta = std::max(1, ctx->sm_count - 1);
+  const int t_last = (int)std::max<int64_t>(1, s->k_run - 1);
+  int cpc_cap = 128;
+  while (cpc_cap > 4 && pipe_smem(t_last, cpc_cap) > PIPE_SMEM_MAX) cpc_cap -= 4;
+  const int rounds = (int)std::max<int64_t>(1, (s->n + (int64_t)cpc_cap * max_cta - 1) / ((int64_t)cpc_cap * max_cta));
+  const int cpc = (int)std::max<int64_t>(4, 4 * ((s->n + (int64_t)4 * rounds * max_cta - 1) / ((int64_t)4 * rounds * max_cta)));
+  const int ncta = s->n > 0 ? (int)((s->n + (int64_t)rounds * cpc - 1) / ((int64_t)rounds * cpc)) : 0;
+  TailArgs ta;
+  ta.ticket = s->ticket; ta.sc = s->sc; ta.commit = commit; ta.copy = copy; ta.avail = s->avail; ta.sel = s->sel; ta.red = s->red;
+  ta.U = s->U; ta.A = s->nl == 2 ? s->A : nullptr; ta.rows = s->R(); ta.sw = s->sw; ta.d = s->d; ta.dp = s->dp;
+  ta.win_u = s->win_u; ta.win_a = s->win_a; ta.win_sw = s->win_sw; ta.kss = s->kss; ta.kss_ld = s->kcap;
+  PipeArgs pa;
+  pa.P_prev = s->pipeP + (size_t)((t + 1) & 1) * PIPE_MAX_T * PIPE_LDP;
+  pa.trP_prev = s->pipeTr + ((t + 1) & 1);
+  pa.P_next = s->pipeP + (size_t)(t & 1) * PIPE_MAX_T * PIPE_LDP;
+  pa.trP_next = s->pipeTr + (t & 1);
+  pa.kss = s->kss; pa.kss_ld = s->kcap;
+  pa.alpha_next = (double)(t + 2) * s->delta;
+  pa.do_next = (t + 1 < s->k_run) ? 1 : 0;
+  pa.rounds = rounds;
+  pa.spec = (copy && s->spec) ? (SpecState*)s->spec_state : nullptr;
+  pa.plan = (copy && s->spec) ? (SpecPlan*)s->spec_plan : nullptr;
+  eval_pipe_kernel<<<1 + ncta, 1024, pipe_smem(t, cpc), ctx->stream>>>(s->kcols, s->kcols_n, s->diag, s->avail, t, ldc, s->n, alpha, s->blk_loss,
+                                                                 s->blk_idx, cpc, ta, pa);
+  ctx->launches++;
+  s->pipe_have = t;
+  CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
 }
 
@@ -929,8 +1639,10 @@ static int run_invert(nnal_ctx* ctx, State* s, int t) {
 }
 
 // the inverse of step t: already computed by CTA 0 of the previous step's column kernel, or computed here
+static int step_select_pipe(nnal_ctx* ctx, State* s, int t, int commit, int copy);
 static int need_invert(nnal_ctx* ctx, State* s, int t) {
-  if (t < 1) return NNAL_OK;
+  if (s->pipe) return s->n > 0 ? NNAL_OK : step_select_pipe(ctx, s, t, 0, 0);     // (no candidates: the service CTA alone)
+  if (t < 1 || (ctx->dbg.fi_flags & 4)) return NNAL_OK;
   if (s->inv_ready_for == t) {
     s->inv_ready_for = -1;
     return NNAL_OK;
@@ -940,6 +1652,7 @@ static int need_invert(nnal_ctx* ctx, State* s, int t) {
 
 // steps 1-3 of greedy step t: inverse, candidate evaluation, arg-min
 static int step_select(nnal_ctx* ctx, State* s, int t, int commit, int copy = 0) {
+  if (s->pipe) return step_select_pipe(ctx, s, t, commit, copy);
   const double alpha = (double)(t + 1) * s->delta;
   const int ldc = (t + 7) / 8 * 8;
   static bool attr_eval = false;
@@ -971,11 +1684,31 @@ static int step_select(nnal_ctx* ctx, State* s, int t, int commit, int copy = 0)
 }
 
 // the winner slot is filled and K_SS extended: compute kernel column t over the local candidates
-static int step_column(nnal_ctx* ctx, State* s, int t) {
+static int step_column(nnal_ctx* ctx, State* s, int t, bool spec = false) {
+  if (s->n > 0 && spec) {
+    static bool attr = false;
+    const size_t smem = (size_t)SPEC_COLS * (s->d + s->dp) * sizeof(float);
+    if (!attr) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(column_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr = true;
+    }
+    ColArgs ca;
+    ca.U = s->U; ca.A = s->nl == 2 ? s->A : nullptr; ca.rows = s->R(); ca.sw = s->sw; ca.beta2 = s->beta2;
+    ca.n = s->n; ca.d = s->d; ca.dp = s->dp; ca.nl = s->nl;
+    ca.kcol = s->kcols + (int64_t)t * s->kcols_n;
+    ca.spec_cols = s->spec_cols; ca.spec_ld = s->spec_n;
+    ca.U16 = s->use16 ? s->U16 : nullptr; ca.A16 = s->use16 ? s->A16 : nullptr;
+    ca.plan = (const SpecPlan*)s->spec_plan;
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((s->n + 15) / 16, (int64_t)ctx->sm_count));
+    column_spec_kernel<<<(int)blocks, 512, smem, ctx->stream>>>(ca);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return NNAL_OK;
+  }
   if (s->n > 0) {
     InvArgs inv;
     const int tn = t + 1;                                   // the next step's system: K_SS rows 0..t are complete
-    const bool fuse = tn < s->k_run && tn <= 128;
+    const bool fuse = !s->pipe && tn < s->k_run && tn <= 128;
     inv.kss = s->kss; inv.kss_ld = s->kcap; inv.t = fuse ? tn : 0; inv.alpha = (double)(tn + 1) * s->delta;
     inv.C = s->C; inv.ldc = (tn + 7) / 8 * 8; inv.sc = s->sc;
     // 32 warps per CTA, one candidate per warp and pass; at most 2 CTAs per SM
@@ -1006,7 +1739,8 @@ int nnal_fi_release(nnal_ctx* ctx) {
   State* s = (State*)ctx->fi_state;
   void* ptrs[] = {s->gids, s->rows, s->ownU, s->ownA, s->w, s->sw, s->diag, s->avail, s->beta2, s->kcols, s->kss, s->C, s->inv_ws,
                   s->red, s->win_sw, s->win_u, s->win_a, s->sel, s->blk_loss, s->blk_idx, s->sc, s->H, s->Xh, s->Xl, s->wq,
-                  s->sub_rows, s->sub_wq, s->gj_M, s->gj_R, s->gj_C, s->gj_D, s->gj_out, s->gj_R2, s->gj_C2, s->gj_D2, s->U16, s->A16};
+                  s->sub_rows, s->sub_wq, s->gj_M, s->gj_R, s->gj_C, s->gj_D, s->gj_out, s->gj_R2, s->gj_C2, s->gj_D2, s->U16, s->A16,
+                  s->pipeP, s->pipeTr, s->spec_cols, s->spec_state, s->spec_plan};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->ticket) cudaFree(s->ticket);
   delete s;
@@ -1105,6 +1839,9 @@ extern "C" int nnal_fi_begin(nnal_ctx* ctx, int64_t k, double delta) {
   s->k_run = k;
   s->delta = delta;
   NNAL_TRY(fi::alloc_greedy(ctx, s, std::max<int64_t>(k, 1)));
+  s->pipe = false;                       // (nnal_fi_greedy switches the pipelined step on together with the speculative columns)
+  s->pipe_have = -1;
+  s->spec = false;
   if (s->n) CUDA_TRY(ctx, cudaMemsetAsync(s->avail, 1, (size_t)s->n, ctx->stream));
   return NNAL_OK;
 }
@@ -1116,10 +1853,26 @@ extern "C" int nnal_fi_greedy(nnal_ctx* ctx, int64_t k, double delta, int64_t* s
   if (k > s->n) k = s->n;
   s->k_run = k;
   if (k == 0) return NNAL_OK;
+  // speculative kernel columns: vector loads from shared-memory copies of the winners' rows
+  // and the pipelined step: single-process selections of up to PIPE_MAX_T steps.  On its own (flag 16) the pipelined step is
+  // SLOWER than the plain one at small candidate counts (n = 3000: 50 vs 35 us per step: every CTA rebuilds C from the shifted
+  // inverse), so the multi-rank protocols, whose per-rank candidate sets are small, keep the plain step.
+  s->pipe = k <= fi::PIPE_MAX_T && !(ctx->dbg.fi_flags & 8);
+  s->spec = s->pipe && !(ctx->dbg.fi_flags & 16) && s->d % 4 == 0 && (s->nl == 1 || s->dp % 4 == 0) &&
+            (size_t)fi::SPEC_COLS * (s->d + s->dp) * sizeof(float) <= 220 * 1024;
+  if (!s->spec && !(ctx->dbg.fi_flags & 16)) s->pipe = false;
+  if (s->spec) {
+    if (s->spec_n < s->kcols_n) {
+      NNAL_TRY(fi::ensure(ctx, s->spec_cols, 0, (size_t)fi::SPEC_SLOTS * s->kcols_n));
+      s->spec_n = s->kcols_n;
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(s->spec_state, 0xff, sizeof(fi::SpecState), ctx->stream));            // tags = -1
+    CUDA_TRY(ctx, cudaMemsetAsync(&((fi::SpecState*)s->spec_state)->fifo, 0, sizeof(int), ctx->stream));
+  }
   prof_begin(ctx, NNAL_PROF_FI_GREEDY);
   for (int t = 0; t < (int)k; ++t) {
-    NNAL_TRY(fi::step_select(ctx, s, t, 1, 1));           // evaluation, arg-min, winner copy, K_SS row: one launch
-    NNAL_TRY(fi::step_column(ctx, s, t));                 // kernel column of the winner + (CTA 0) the next step's inverse
+    if (!(ctx->dbg.fi_flags & 2)) NNAL_TRY(fi::step_select(ctx, s, t, 1, 1));   // evaluation, arg-min, K_SS row, column plan: one launch
+    if (!(ctx->dbg.fi_flags & 1)) NNAL_TRY(fi::step_column(ctx, s, t, s->spec)); // kernel column(s), or the cached column
   }
   prof_end(ctx);
   std::vector<double> red((size_t)k);

@@ -119,6 +119,8 @@ struct DebugOpts {
   int wt_flags = 0;            // conv_wt.cu timing experiments: 1 skip the epilogue stores, 2 skip the lo plane
   int sdp_no_coop = 0;         // one launch per SDP iteration instead of the cooperative loop
   int bw_no_ws = 0, bw_no_tc8 = 0, bw_no_tc = 0, bw_simt_fwd = 0;   // shrunk.cu fallbacks
+  int fi_flags = 0;            // fi.cu: 1 skip the column pass, 2 skip the evaluation, 4 skip stand-alone inversions (timing experiments, results are garbage);
+                               // 8 one-pivot-at-a-time inverse inside the column kernel instead of the pipelined step, 16 no speculative columns (tests)
 };
 
 struct nnal_ctx {

@@ -137,6 +137,29 @@ def test_fi_greedy_large_candidate_set_f16_rows(nb):
     assert abs(red[-1] / ro[-1] - 1) < OBJ_RTOL
 
 
+@pytest.mark.parametrize('n,d,dp,k,two', [(3000, 256, 128, 40, True), (700, 64, 32, 128, True), (900, 128, 64, 33, False)])
+def test_fi_greedy_pipelined_and_speculative_equal_plain(nb, n, d, dp, k, two):
+    """The single-process greedy runs a pipelined step (shifted inverse one step ahead + bordering) with speculative
+    kernel columns (csrc/fi.cu).  Neither may change the result: the same selection, in the same order, as the plain step
+    (debug flag 8) and as the pipelined step without speculation (flag 16); reduced objectives equal to 1e-9 (the inverse
+    is reached by a different, equally stable, elimination order)."""
+    p1, U, A, Wl = _factors(n, d, dp, 3 * n + k)
+    eng = nb.get_engine()
+    eng.fi_set_factors(p1, U, A if two else None, Wl if two else None)
+    out = {}
+    try:
+        for flag in (0, 16, 8):
+            eng.debug_option('fi_flags', flag)
+            out[flag] = eng.fi_greedy(k, 1e-3)
+    finally:
+        eng.debug_option('fi_flags', 0)
+    for flag in (16, 8):
+        assert np.array_equal(out[0][0], out[flag][0]), 'selection differs (flag %d)' % flag
+        assert np.allclose(out[0][2], out[flag][2], rtol=1e-9), np.abs(out[0][2] / out[flag][2] - 1).max()
+    Kt, D = _oracle_kernel(p1, U, A, Wl, two)
+    assert_greedy_equivalent(Kt, D, 1e-3, out[0][0], out[0][2], rtol=1e-4)
+
+
 def test_fi_greedy_edge_cases(nb):
     eng = nb.get_engine()
     p1, U, A, Wl = _factors(5, 16, 8, 1)

@@ -159,6 +159,7 @@ def test_device_topk_merge_matches_global_stable_sort(nb):
                 e.synchronize()
                 bufs.append(buf)
             recv = torch.cat(bufs)
+            torch.cuda.synchronize()
             pos, sc = engs[0].topk_merge_pairs(recv.data_ptr(), len(n_per) * k, k)
         finally:
             for e in engs:
@@ -172,9 +173,11 @@ def test_device_topk_merge_matches_global_stable_sort(nb):
         buf = torch.zeros(50 * 16, dtype=torch.uint8, device='cuda')
         e._load_scores_for_test(scores[3])
         e.pool_topk_device(50, 50, 7, buf.data_ptr())
+        e.synchronize()                                   # the library's stream is not torch's: order the two by hand
         two = torch.cat([buf, buf.clone()])
         two[50 * 16:].view(torch.float64).view(-1, 2)[:, 0] = float('inf')
         two[50 * 16:].view(torch.int64).view(-1, 2)[:, 1] = np.iinfo(np.int64).max
+        torch.cuda.synchronize()
         pos, sc = e.topk_merge_pairs(two.data_ptr(), 100, 100)
     finally:
         e.close()
