@@ -790,8 +790,8 @@ __device__ __forceinline__ bool loss_less(double la, long long ia, double lb, lo
 //   CTA c >= 1: C_t by bordering, then `rounds` tiles of `cpc` candidates (cpc a multiple of 4, <= 128; the host sizes cpc so
 //   that one tile per CTA covers all candidates with every SM busy).  A tile is the product Y = C K (t x t by t x cpc) with
 //   both operands in shared memory, register-tiled: warp w owns candidates 4w..4w+3, lane l the rows 4l..4l+3 of Y (16
-//   accumulators); r_j = k_j.y_j and e_j = |y_j|^2 are warp reductions.  Every CTA leaves its two best candidates
-//   (blk_loss/blk_idx[2 c], [2 c + 1]); the last CTA to finish picks the global winner, and (speculation) plans the column
+//   accumulators); r_j = k_j.y_j and e_j = |y_j|^2 are warp reductions.  Every warp leaves its two best candidates
+//   (blk_loss/blk_idx); the last CTA to finish picks the global winner, and (speculation) plans the column
 //   pass: a cache hit, or the winner + the best uncached runners-up.
 __global__ void __launch_bounds__(1024, 1) eval_pipe_kernel(const double* __restrict__ kcols, int64_t kn, const double* __restrict__ diag,
                                                             const unsigned char* __restrict__ avail, int t, int ldc, int64_t n,
@@ -898,24 +898,13 @@ __global__ void __launch_bounds__(1024, 1) eval_pipe_kernel(const double* __rest
     }
     __syncthreads();
   }
-  // the CTA's two best over its warps (every lane of a warp holds the warp's pair)
-  {
-    double* ml = scratch;                               // [64]
-    long long* mi = reinterpret_cast<long long*>(scratch + 64);
-    if (lane == 0) { ml[2 * warp] = bl1; mi[2 * warp] = bi1; ml[2 * warp + 1] = bl2; mi[2 * warp + 1] = bi2; }
-    __syncthreads();
-    if (tid == 0) {
-      double l1 = INFINITY, l2 = INFINITY;
-      long long i1 = 0x7fffffffffffffffll, i2 = 0x7fffffffffffffffll;
-      for (int q = 0; q < 64; ++q) {
-        if (loss_less(ml[q], mi[q], l1, i1)) { l2 = l1; i2 = i1; l1 = ml[q]; i1 = mi[q]; }
-        else if (loss_less(ml[q], mi[q], l2, i2)) { l2 = ml[q]; i2 = mi[q]; }
-      }
-      const int g = blockIdx.x - 1;
-      blk_loss[2 * g] = l1; blk_idx[2 * g] = i1; blk_loss[2 * g + 1] = l2; blk_idx[2 * g + 1] = i2;
-    }
+  // every warp leaves its two best (the runners-up of the speculation are looked for among these lists: candidates come in
+  // uncertainty order, so the best ones sit next to each other and per-CTA lists would hide most of them)
+  if (lane == 0) {
+    const int64_t g = (int64_t)(blockIdx.x - 1) * 32 + warp;
+    blk_loss[2 * g] = bl1; blk_idx[2 * g] = bi1; blk_loss[2 * g + 1] = bl2; blk_idx[2 * g + 1] = bi2;
   }
-  const int64_t ngroups = gridDim.x - 1;
+  const int64_t ngroups = (int64_t)(gridDim.x - 1) * 32;
   // ---- tail: the last candidate CTA to finish picks the global winner
   __shared__ unsigned int s_last;
   __shared__ double s_rl[32];
@@ -1529,7 +1518,7 @@ static int alloc_greedy(nnal_ctx* ctx, State* s, int64_t k) {
     s->win_d = s->d;
     s->win_dp = s->dp;
   }
-  const int nblk = std::max(cdiv(std::max<int64_t>(s->n, 1), EVAL_CAND), 2 * ctx->sm_count);   // (pipelined evaluation: two entries per CTA)
+  const int nblk = std::max(cdiv(std::max<int64_t>(s->n, 1), EVAL_CAND), 64 * ctx->sm_count);   // (pipelined evaluation: two entries per warp)
   if (s->blk_cap < nblk) {
     NNAL_TRY(ensure(ctx, s->blk_loss, 0, (size_t)nblk));
     NNAL_TRY(ensure(ctx, s->blk_idx, 0, (size_t)nblk));

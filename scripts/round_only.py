@@ -6,6 +6,7 @@
 import argparse
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -35,6 +36,10 @@ for r in range(args.rounds):
     eng.pool_score(L.SCORE_BINARY)
     top, _ = dist.topk_global(eng, max(B, k), 0, n)
     eng.fi_set_candidates(top[:B], 2)
+    eng.synchronize()
+    t0 = time.perf_counter()
     chosen, obj, red = fimod.greedy_select(eng, k, Bn.FI_DELTA, np.arange(B, dtype=np.int64))
+    eng.synchronize()
+    print('greedy %.2f ms' % (1e3 * (time.perf_counter() - t0)))
 eng.synchronize()
 print('rounds', args.rounds, 'launches', eng.launches, 'entropy', Bn.digest(top[:k]), 'fi', Bn.digest(top[:B][chosen]), 'red', red[-1])
