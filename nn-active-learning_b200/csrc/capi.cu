@@ -19,6 +19,7 @@ extern "C" int nnal_debug_option(nnal_ctx* ctx, const char* name, long value) {
   if (n == "chunk") d.chunk = value;
   else if (n == "bw_chunk") d.bw_chunk = value;
   else if (n == "no_fused_gather") d.no_fused_gather = (int)value;
+  else if (n == "no_fused_conv1") d.no_fused_conv1 = (int)value;
   else if (n == "wt_flags") d.wt_flags = (int)value;
   else if (n == "sdp_no_coop") d.sdp_no_coop = (int)value;
   else if (n == "bw_no_ws") d.bw_no_ws = (int)value;
@@ -650,8 +651,11 @@ static int pool_eval_impl(nnal_ctx* ctx, int subject, const int64_t* inds, bool 
   NNAL_TRY(reserve_forward(ctx, chunk));
   // gather straight into the first conv's tensor-core input planes when it takes them
   const bool fused_ok = !ctx->dbg.no_fused_gather;
-  const bool fused16 = fused_ok && nnal_first_layer_wants_x16(ctx) && nnal_k_gather_x16_supported(*v, d1, d2, d3);
-  const bool fused = fused_ok && !fused16 && nnal_first_layer_wants_split8(ctx) && nnal_k_gather_split_supported(*v, d3);
+  // conv1 gathers its own input when it can (PW1's first layer on a 3-modality float32 volume): no gather kernel at all
+  const bool fusedc1 = fused_ok && !ctx->dbg.no_fused_conv1 && nnal_layer_on_tc(ctx, 0) &&
+                       nnal_tc_conv1_fused_supported(ctx, ctx->layers[0], *v, d1, d2, d3);
+  const bool fused16 = fused_ok && !fusedc1 && nnal_first_layer_wants_x16(ctx) && nnal_k_gather_x16_supported(*v, d1, d2, d3);
+  const bool fused = fused_ok && !fusedc1 && !fused16 && nnal_first_layer_wants_split8(ctx) && nnal_k_gather_split_supported(*v, d3);
   const int64_t* d_inds = inds;
   if (!inds_on_device) {
     NNAL_TRY(devbuf_reserve(ctx, ctx->inds, (size_t)n * 8));
@@ -660,6 +664,12 @@ static int pool_eval_impl(nnal_ctx* ctx, int subject, const int64_t* inds, bool 
   }
   for (int64_t o = 0; o < n; o += chunk) {
     int64_t nb = std::min(chunk, n - o);
+    if (fusedc1) {
+      ctx->fg.vol = v; ctx->fg.d_inds = d_inds + o; ctx->fg.h_stats = stats; ctx->fg.norm_mode = norm_mode;
+      ctx->fg.d1 = d1; ctx->fg.d2 = d2; ctx->fg.d3 = d3;
+      NNAL_TRY(nnal_forward_chunk(ctx, nb, offset + o, 3));
+      continue;
+    }
     prof_begin(ctx, NNAL_PROF_GATHER);
     if (fused16) {
       nnal_h* hi = (nnal_h*)ctx->xin.p;

@@ -43,7 +43,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// backoff_ns > 0: sleep between polls -- for the waits of warps that are far from the critical path (epilogue, gather
+// producers): a polling warp takes issue slots from the warps that share its scheduler
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned backoff_ns = 0) {
   uint32_t ok = 0;
   long long t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
@@ -55,6 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
+    if (backoff_ns) __nanosleep(backoff_ns);
     if ((spin & 0xfff) == 0xfff) {
       long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -142,11 +145,14 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t* a, uint32_t* b) {
 }
 
 // Compile-time geometry of one conv layer
-template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_, bool POOL_ = false, bool DUAL_ = false, int KW_ = 0, int NWG_ = 2>
+template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_, bool POOL_ = false, bool DUAL_ = false, int KW_ = 0, int NWG_ = 2, bool GATHER_ = false>
 struct Cfg {
+  static constexpr bool GATHER = GATHER_;                 // the input is gathered from the volume by producer warps (x-im2col'd conv1)
+  static constexpr int NGW = GATHER_ ? 8 : 0;             // ... this many of them
+  static constexpr int GW0 = 4 + 4 * NWG_ + 1;            // first gather warp
   static constexpr int NWG = 2;                           // epilogue warpgroups, one per accumulator: warpgroup wg drains every other tile group
   static_assert(NWG_ == 2, "tile-level splits over more warpgroups were measured slower: extra warps on the issuing warp's scheduler delay the MMAs");
-  static constexpr int THREADS = 32 * (4 + 4 * NWG_ + 1); // 4 service warps, 4 * NWG epilogue warps, the second MMA issuer
+  static constexpr int THREADS = 32 * (4 + 4 * NWG_ + 1 + NGW); // 4 service warps, 4 * NWG epilogue warps, the second MMA issuer, gather warps
   static constexpr int NISSUE = DUAL_ ? 2 : 1;            // MMA-issuing threads (tiles of a group alternate between them)
   static constexpr bool POOL = POOL_;                     // fuse the following 2x2/s2 SAME max-pool into the epilogue
   // CIN / COUT are the padded operand extents (multiples of 8 / 16); the *_REAL values are the layer's
@@ -189,6 +195,16 @@ struct Cfg {
   static_assert(TMEM_COLS_USED <= 512, "TMEM budget");
   static_assert(SMEM <= 232448, "shared memory budget");
   static_assert(!POOL || (G == 1 && NG == 1), "fused pooling: one sample = one tile group = one epilogue warpgroup");
+  static_assert(!GATHER || (G == 1 && KW == 1 && CIN == 16 && KH == 5 && H == 25 && W == 25), "fused gather: conv1 of PW1 in the x-im2col'd form");
+};
+
+// fused gather (Cfg::GATHER): the [Z][X][Y][m] float32 volume, the raveled voxel ids of the samples, normalisation table
+struct GatherArgs {
+  const float* vol;
+  int64_t Xp, Yp, Zp;
+  const int64_t* inds;
+  NormTab tab;
+  int flags;                 // timing experiments (debug option wt_flags): 1 no normalise/split, 2 no operand assembly, 4 neither fetch
 };
 
 struct ConvParams {
@@ -202,7 +218,7 @@ struct ConvParams {
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, ConvParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, ConvParams p, GatherArgs ga) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -227,13 +243,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
   __shared__ __align__(16) float sbias[(C::COUT + 15) / 16 * 16];
   for (int i = threadIdx.x; i < (C::COUT + 15) / 16 * 16; i += blockDim.x) sbias[i] = i < C::COUT_REAL ? p.bias[i] : 0.f;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && lane == 0 && !C::GATHER) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmHi));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmLo));
   }
   if (warp == 1 && lane == 0) {
     // two MMA-issuing threads (see below): every "MMAs retired" barrier collects one commit from each
-    for (int b = 0; b < 2; ++b) { mbar_init(in_full(b), 1); mbar_init(in_empty(b), C::NISSUE); }
+    for (int b = 0; b < 2; ++b) { mbar_init(in_full(b), C::GATHER ? C::NGW : 1); mbar_init(in_empty(b), C::NISSUE); }
     for (int s = 0; s < 3; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), C::NISSUE); }
     for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), C::NISSUE); mbar_init(acc_empty(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -269,9 +285,98 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (C::GATHER && warp >= C::GW0) {
+    // ===== input producers (fused gather): the patch is read from the volume, normalised (float64, as batch_eval) and split
+    // ONCE into a packed staging array, then every thread assembles the x-im2col'd rows of its positions -- element
+    // dx * 3 + ch of position (i, k) = value (i, k + dx - 2, ch), zero outside the patch, element 15 = 0 -- straight into the
+    // UMMA operand planes (plane q = elements 8q..8q+7, 16 bytes per raster position; rows -2, -1, 25, 26 of the raster stay
+    // zero from the initial clear).  What the stand-alone gather wrote to HBM (and conv1 read back through 16-byte TMA rows)
+    // never leaves the SM.
+    constexpr int NPOS = C::H * C::W, CH = 3, ROW = C::W * CH, NT = C::GATHER ? 32 * C::NGW : 32;
+    constexpr int NE = NPOS * CH, PER = (NE + NT - 1) / NT;
+    __shared__ uint32_t sv[NE];                          // packed (hi | lo << 16)
+    const int pt = threadIdx.x - 32 * C::GW0;
+    const int64_t Y0 = ga.Yp - (C::W - 1), Z0 = ga.Zp;
+    // this thread's elements of a patch: e = pt + u NT -> (row i, offset r in the row, channel); the same for every sample
+    int eoff[PER];
+    double mu[3], sg[3], rs[3];                          // by u % 3: element u has channel (pt + (NT % 3) u) % 3 (ROW = 0 mod 3)
+    static_assert(!C::GATHER || (NT % 3 != 0 && ROW % 3 == 0), "channel pattern of the per-thread elements");
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int e = pt + u * NT;
+      const int i = e / ROW, r = e - i * ROW;
+      eoff[u] = e < NE ? (int)(i * ga.Yp * CH + r) : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int ch = (pt + (NT % 3) * q) % 3;
+      const bool on = ga.tab.on[ch];
+      mu[q] = on ? ga.tab.mu[ch] : 0.0;
+      sg[q] = on ? ga.tab.sg[ch] : 1.0;
+      rs[q] = on ? ga.tab.rs[ch] : 1.0;                  // (x - 0) / 1 = x, exactly
+    }
+    // all loads of a patch are issued before the first is used, and the NEXT patch is fetched while this one is assembled
+    float raw[PER];
+    auto fetch = [&](int g) {
+      const int64_t ind = ga.inds[g];
+      const int64_t z = ind % Z0;
+      const int64_t t = ind / Z0;
+      const int64_t y = t % Y0;
+      const int64_t x = t / Y0;
+      const float* pbase = ga.vol + ((z * ga.Xp + x) * ga.Yp + y) * CH;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) raw[u] = eoff[u] >= 0 ? pbase[eoff[u]] : 0.f;
+    };
+    if ((int)blockIdx.x < ngroups) fetch(blockIdx.x);
+    uint32_t it = 0;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+      const int b = it % C::NBUF;
+      const uint32_t ph = (it / C::NBUF) & 1;
+      if (!(ga.flags & 1)) {
+        // branch-free per element (the fp16 range check is one test per thread and patch): fifteen independent chains
+        uint32_t amax = 0u;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+          const int e = pt + u * NT;
+          const float v = (float)norm_apply((double)raw[u], mu[u % 3], sg[u % 3], rs[u % 3]);
+          nnal_ovf_track(amax, v);
+          nnal_h h, l;
+          nnal_split_unchecked(v, h, l);
+          if (e < NE) sv[e] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+        }
+        nnal_ovf_commit(amax);
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory");
+      if (g + (int)gridDim.x < ngroups && !(ga.flags & 4)) fetch(g + gridDim.x);
+      mbar_wait(in_empty(b), ph ^ 1, C::GATHER ? 200 : 0);
+      uint8_t* dst = base_ptr + (size_t)b * C::IN_BYTES;
+      for (int pos = pt; pos < NPOS && !(ga.flags & 2); pos += NT) {
+        const int i = pos / C::W, k = pos - i * C::W;
+        uint32_t hw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 15; ++j) {
+          const int dx = j / 3, ch = j - dx * 3;
+          const int kk = k + dx - 2;
+          if (kk >= 0 && kk < C::W) {
+            const uint32_t w = sv[(i * C::W + kk) * CH + ch];
+            hw[j >> 1] |= (w & 0xffffu) << ((j & 1) * 16);
+            lw[j >> 1] |= (w >> 16) << ((j & 1) * 16);
+          }
+        }
+        const size_t o = (size_t)((i + C::PH) * C::WP + k) * 16;
+        *reinterpret_cast<uint4*>(dst + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(dst + C::PLANE + o) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        *reinterpret_cast<uint4*>(dst + 2 * C::PLANE + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        *reinterpret_cast<uint4*>(dst + 3 * C::PLANE + o) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core's reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(in_full(b));
+      asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory");           // sv is rewritten by the next sample
+    }
+  } else if (warp == 0) {
     // ===== input producer: Q 4-D TMA boxes {8ch, WP, HP, G} per (hi|lo), zero-filled borders =====
-    if (lane == 0) {
+    if (lane == 0 && !C::GATHER) {
       uint32_t it = 0;
       for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
         const int b = it % C::NBUF;
@@ -409,7 +514,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         const int a = it % C::NACC;
         uint32_t* my_pooled = pooled + a * C::POOL_WORDS;           // one pooled raster per accumulator (= per sample in flight)
         const uint32_t ph_acc = (it / C::NACC) & 1;
-        mbar_wait(acc_full(a), ph_acc);
+        mbar_wait(acc_full(a), ph_acc, C::GATHER ? 200 : 0);
         tc_fence_after();
 #pragma unroll 1
         for (int tl = 0; tl < C::TG; ++tl) {
@@ -456,21 +561,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
               }
               nnal_ovf_commit(amax);
             } else if (valid) {
-              uint32_t hi[8], lo[8], amax = 0u;
+              // post-ReLU values are >= 0: no clamp; a value beyond fp16 rounds to Inf, which the SIMD max below catches (the
+              // lo term is garbage then, and the call fails with NNAL_ERR_OVERFLOW) -- 7 instead of 10 instructions per output
+              uint32_t hi[8], lo[8], hmax = 0u;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float r0 = v[2 * j] * p.w_scale_inv + bb[2 * j], r1 = v[2 * j + 1] * p.w_scale_inv + bb[2 * j + 1];
-                nnal_ovf_track(amax, r0);
-                nnal_ovf_track(amax, r1);
-                const float x0 = fminf(fmaxf(r0, 0.f), 65504.f);
-                const float x1 = fminf(fmaxf(r1, 0.f), 65504.f);
+                const float x0 = fmaxf(fmaf(v[2 * j], p.w_scale_inv, bb[2 * j]), 0.f);
+                const float x1 = fmaxf(fmaf(v[2 * j + 1], p.w_scale_inv, bb[2 * j + 1]), 0.f);
                 const __half2 h = __floats2half2_rn(x0, x1);              // .x (low half) = x0
                 const float2 hf = __half22float2(h);
                 const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
                 hi[j] = *reinterpret_cast<const uint32_t*>(&h);
                 lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                nnal_ovf_track_h2(hmax, hi[j]);
               }
-              nnal_ovf_commit(amax);
+              nnal_ovf_commit_h2(hmax);
               uint4* dh = reinterpret_cast<uint4*>(p.out_hi + obase + c0);
               uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
               dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -585,6 +690,8 @@ typedef Cfg<25, 25, 3, 24, 5, 1, 7, 2, 3, true> CfgConv1;     // PW1 conv1: 3 in
 // becomes 5 x 1 over 16 channels: K = 5 taps x 16 = 80 instead of 25 taps x 8 (3 real) = 200, no x padding (5 M tiles
 // instead of 6): 50 MMAs per sample instead of 156
 typedef Cfg<25, 25, 16, 24, 5, 1, 5, 2, 3, true, false, false, 1> CfgConv1X;
+// ... and with the gather fused in (the kernel reads the volume itself)
+typedef Cfg<25, 25, 16, 24, 5, 1, 5, 2, 3, true, false, false, 1, 2, true> CfgConv1XG;
 typedef Cfg<25, 25, 24, 32, 5, 1, 8, 2, 3, true> CfgConv2;    // PW1 conv2: 6 M tiles in 2 groups of 3
 // conv3/conv4: the concatenated form was measured for conv3 (TG = 2, N = 96 + 48): 2.63 ms vs 2.61 ms per 100k samples
 // -- with only two accumulators in rotation the MMAs wait on each other (scripts/microbench/mma_rate.cu: 129 cycles
@@ -616,10 +723,18 @@ static int pack(nnal_ctx* ctx, Layer& L) { return pack_from<C>(ctx, L.W, (void**
 
 template <class C>
 static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
-                  nnal_h* out_lo, int64_t n, const void* wpack = nullptr) {
+                  nnal_h* out_lo, int64_t n, const void* wpack = nullptr, const GatherArgs* gather = nullptr) {
   CUtensorMap tmHi, tmLo;
-  NNAL_TRY(make_act_tmap(ctx, &tmHi, in_hi, (int)n, C::H, C::W, C::CIN, C::WP, C::HP, C::G));
-  NNAL_TRY(make_act_tmap(ctx, &tmLo, in_lo, (int)n, C::H, C::W, C::CIN, C::WP, C::HP, C::G));
+  GatherArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  if (C::GATHER) {
+    memset(&tmHi, 0, sizeof(tmHi));
+    memset(&tmLo, 0, sizeof(tmLo));
+    ga = *gather;
+  } else {
+    NNAL_TRY(make_act_tmap(ctx, &tmHi, in_hi, (int)n, C::H, C::W, C::CIN, C::WP, C::HP, C::G));
+    NNAL_TRY(make_act_tmap(ctx, &tmLo, in_lo, (int)n, C::H, C::W, C::CIN, C::WP, C::HP, C::G));
+  }
   static bool attr = false;
   if (!attr) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -629,7 +744,7 @@ static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal
   p.wpack = (const uint8_t*)(wpack ? wpack : L.Wh); p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.n = (int)n; p.w_scale_inv = L.w_scale_inv;
   const int ngroups = (int)((n + C::G - 1) / C::G);
   const int grid = ngroups < ctx->sm_count ? ngroups : ctx->sm_count;
-  conv_tc_kernel<C><<<grid, C::THREADS, C::SMEM, ctx->stream>>>(tmHi, tmLo, p);
+  conv_tc_kernel<C><<<grid, C::THREADS, C::SMEM, ctx->stream>>>(tmHi, tmLo, p, ga);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return NNAL_OK;
@@ -710,6 +825,17 @@ int nnal_tc_conv_x16(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const n
                      int64_t n) {
   if (n == 0) return NNAL_OK;
   return ctc::launch<ctc::CfgConv1X>(ctx, L, in_hi, in_lo, out_hi, out_lo, n, L.Wx);
+}
+bool nnal_tc_conv1_fused_supported(const nnal_ctx* ctx, const Layer& L, const Volume& v, int d1, int d2, int d3) {
+  return nnal_tc_conv_x16_supported(ctx, L) && v.dtype == NNAL_F32 && v.m == 3 && d1 == 25 && d2 == 25 && d3 == 1;
+}
+int nnal_tc_conv1_fused(nnal_ctx* ctx, const Layer& L, const FusedGather& fg, nnal_h* out_hi, nnal_h* out_lo, int64_t n) {
+  if (n == 0) return NNAL_OK;
+  ctc::GatherArgs ga;
+  ga.vol = (const float*)fg.vol->data; ga.Xp = fg.vol->X; ga.Yp = fg.vol->Y; ga.Zp = fg.vol->Z; ga.inds = fg.d_inds;
+  ga.tab = nnal_make_norm_tab(*fg.vol, fg.d3, fg.h_stats, fg.norm_mode);
+  ga.flags = ctx->dbg.wt_flags;
+  return ctc::launch<ctc::CfgConv1XG>(ctx, L, nullptr, nullptr, out_hi, out_lo, n, L.Wx, &ga);
 }
 // conv + the following 2x2/s2 SAME max-pool in one kernel: output planes are [n][ceil(H/2)][ceil(W/2)][Cout]
 bool nnal_tc_conv_pool_supported(const nnal_ctx*, const Layer& L) {

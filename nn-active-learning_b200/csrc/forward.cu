@@ -54,6 +54,7 @@ bool nnal_first_layer_wants_x16(const nnal_ctx* ctx) {
 int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset, int input_format) {
   const bool input_is_split8 = input_format == 1;
   bool input_is_x16 = input_format == 2;
+  const bool fused_conv1 = input_format == 3;           // the first conv gathers its own input (ctx->fg)
   const int nl = (int)ctx->layers.size();
   Act cur;
   cur.f32 = (float*)ctx->xin.p;
@@ -156,6 +157,13 @@ int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset, int input_form
           NNAL_TRY(nnal_k_split_x16(ctx, cur.f32, o2.hi, o2.lo, nb * L.in_h * L.in_w, L.in_w, L.in_c, L.kw));
           o2.split = true; cur = o2;
           input_is_x16 = true;
+        }
+        if (i == 0 && fused_conv1) {
+          Act o; next_buf(oe, o);
+          NNAL_TRY(nnal_tc_conv1_fused(ctx, L, ctx->fg, o.hi, o.lo, nb));
+          o.split = true; cur = o;
+          prof_end(ctx);
+          continue;
         }
         if (i == 0 && input_is_x16) {
           Act o; next_buf(oe, o);

@@ -56,6 +56,15 @@ __device__ __forceinline__ void nnal_ovf_commit(uint32_t m) {
     if (p) atomicOr(p, 1u);
   }
 }
+// epilogues that round post-ReLU values (>= 0) to fp16 pairs: the largest hi-term bit pattern per 16-bit lane (one SIMD
+// max per pair), tested once per tile -- an Inf (the rounding of anything >= 65520) or NaN pattern raises the flag
+__device__ __forceinline__ void nnal_ovf_track_h2(uint32_t& m, uint32_t h2bits) { m = __vmaxu2(m, h2bits); }
+__device__ __forceinline__ void nnal_ovf_commit_h2(uint32_t m) {
+  if ((m & 0xffffu) >= 0x7c00u || (m >> 16) >= 0x7c00u) {
+    unsigned int* p = nnal_ovf_ptr;
+    if (p) atomicOr(p, 1u);
+  }
+}
 __device__ __forceinline__ void nnal_split_unchecked(float x, nnal_h& h, nnal_h& l) {
   x = fminf(fmaxf(x, -65504.f), 65504.f);
   h = __float2half_rn(x);
@@ -103,6 +112,25 @@ struct Volume {
   size_t bytes = 0;
 };
 
+// per OUTPUT channel (C <= 8) normalisation table of the fused gathers: (x - mu) / sigma in float64 (volume.cu)
+struct NormTab { double mu[8], sg[8], rs[8]; int on[8]; };
+#ifdef __CUDACC__
+__device__ __forceinline__ double norm_apply(double v, double mu, double sg, double rs) {
+  const double a = v - mu;
+  if (rs != rs) return a / sg;               // no usable reciprocal: true division
+  const double q0 = a * rs;
+  const double r = fma(-q0, sg, a);
+  return fma(r, rs, q0);
+}
+#endif
+// what the first conv layer needs to gather its own input (conv_tc.cu, gather fused into conv1): set by the pool pass
+struct FusedGather {
+  const Volume* vol = nullptr;
+  const int64_t* d_inds = nullptr;       // raveled voxel ids of the chunk (device)
+  const double* h_stats = nullptr;       // [m][2] (host)
+  int norm_mode = 0, d1 = 0, d2 = 0, d3 = 0;
+};
+
 struct ProfRec { int cls; cudaEvent_t a, b; };
 
 struct DevBuf {
@@ -116,6 +144,7 @@ struct DebugOpts {
   long chunk = 0;              // samples per forward chunk (0: default)
   long bw_chunk = 0;           // samples per chunk of the shrunk-gradient pass (0: default)
   int no_fused_gather = 0;     // fp32 gather + separate split pass instead of the gather that writes conv1's planes
+  int no_fused_conv1 = 0;      // stand-alone gather kernel + conv1 instead of the conv1 that gathers its own input
   int wt_flags = 0;            // conv_wt.cu timing experiments: 1 skip the epilogue stores, 2 skip the lo plane
   int sdp_no_coop = 0;         // one launch per SDP iteration instead of the cooperative loop
   int bw_no_ws = 0, bw_no_tc8 = 0, bw_no_tc = 0, bw_simt_fwd = 0;   // shrunk.cu fallbacks
@@ -134,6 +163,7 @@ struct nnal_ctx {
   int in_h = 0, in_w = 0, in_c = 0, n_class = 0, feature_layer = -1, feat_dim = 0;
   int fc_first = -1;                     // index of first fc layer
   int use_tc = 1;                        // tensor-core (tcgen05) path for conv/fc where supported
+  FusedGather fg;                        // valid during nnal_forward_chunk(.., input_format 3)
   int use_x16 = 0;                       // conv1 on x-im2col'd input (3 channels x 5 filter columns folded into 16 channels); NNAL_CONV_X16=1
   int use_wt = 2;                        // conv_wt.cu: 0 never, 1 where it is the faster kernel, 2 (default) + fused max-pool, 3 wherever it covers the layer
   // volumes
@@ -279,6 +309,10 @@ int nnal_k_split_pad(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t
 int nnal_k_merge_flat(nnal_ctx*, const nnal_h* hi, const nnal_h* lo, float* out, int64_t count);
 bool nnal_tc_conv_supported(const nnal_ctx*, const Layer&);
 bool nnal_tc_conv_x16_supported(const nnal_ctx*, const Layer&);
+// conv1 that gathers, normalises and x-im2col's its own input from the volume (no gather kernel, no input planes in HBM)
+bool nnal_tc_conv1_fused_supported(const nnal_ctx*, const Layer&, const Volume&, int d1, int d2, int d3);
+int nnal_tc_conv1_fused(nnal_ctx*, const Layer&, const FusedGather&, nnal_h* out_hi, nnal_h* out_lo, int64_t n);
+NormTab nnal_make_norm_tab(const Volume& v, int d3, const double* h_stats, int norm_mode);
 int nnal_tc_prepare_conv_x16(nnal_ctx*, Layer&);
 int nnal_tc_conv_x16(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi, nnal_h* out_lo, int64_t n);
 int nnal_k_split_x16(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t rows, int W, int C, int KW);
@@ -300,7 +334,8 @@ int nnal_wt_conv(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_
 int nnal_k_conv_simt_split(nnal_ctx*, const Layer&, const float* in, nnal_h* out_hi, nnal_h* out_lo, int64_t n);
 int nnal_k_pool_split(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
                       nnal_h* out_lo, int64_t n);
-// input_format: 0 fp32 NHWC in xin, 1 fp16 hi/lo planes padded to 8 channels, 2 x-im2col'd fp16 hi/lo planes (16 per position)
+// input_format: 0 fp32 NHWC in xin, 1 fp16 hi/lo planes padded to 8 channels, 2 x-im2col'd fp16 hi/lo planes (16 per position),
+// 3 none: the first conv gathers its input from the volume (ctx->fg)
 int nnal_forward_chunk(nnal_ctx*, int64_t nb, int64_t offset, int input_format = 0);
 bool nnal_first_layer_wants_split8(const nnal_ctx*);
 bool nnal_first_layer_wants_x16(const nnal_ctx*);

@@ -69,16 +69,6 @@ int nnal_k_relayout(nnal_ctx* ctx, const void* stage, int dtype, int m, int64_t 
 // computed in floating point; checked on the host) at 3 flops instead of a ~35-instruction DDIV: the
 // gather stays on the HBM roofline.
 // ------------------------------------------------------------------------------------------
-struct NormTab { double mu[8], sg[8], rs[8]; int on[8]; };   // per OUTPUT channel (C <= 8)
-
-__device__ __forceinline__ double norm_apply(double v, double mu, double sg, double rs) {
-  const double a = v - mu;
-  if (rs != rs) return a / sg;               // no usable reciprocal: true division
-  const double q0 = a * rs;
-  const double r = fma(-q0, sg, a);
-  return fma(r, rs, q0);
-}
-
 // generic kernel: any C, element-wise sweep with incremental (row, column, channel) indices -- no divisions
 template <typename TV, typename TO>
 __global__ void __launch_bounds__(256) gather_kernel(const TV* __restrict__ vol, int m, int64_t Xp, int64_t Yp,
@@ -306,12 +296,11 @@ bool nnal_k_gather_x16_supported(const Volume& v, int d1, int d2, int d3) {
 // host copy of the stats ([m][2]) is needed to build the per-output-channel table passed by value
 bool nnal_k_gather_split_supported(const Volume& v, int d3) { return v.dtype == NNAL_F32 && v.m * d3 <= 8; }
 
-static NormTab make_norm_tab(const Volume& v, int d3, const double* h_stats, int norm_mode);
 
 int nnal_k_gather_x16(nnal_ctx* ctx, const Volume& v, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
                       const double* h_stats, int norm_mode, nnal_h* out_hi, nnal_h* out_lo) {
   if (n == 0) return NNAL_OK;
-  const NormTab tab = make_norm_tab(v, d3, h_stats, norm_mode);
+  const NormTab tab = nnal_make_norm_tab(v, d3, h_stats, norm_mode);
   int grid = (int)(n < (int64_t)ctx->sm_count * 16 ? n : (int64_t)ctx->sm_count * 16);
   gather_x16_kernel<<<grid, 256, (size_t)d1 * d2 * v.m * sizeof(uint32_t), ctx->stream>>>((const float*)v.data, v.m, v.X, v.Y, v.Z, d_inds, n,
                                                                                           d1, d2, tab, out_hi, out_lo);
@@ -323,7 +312,7 @@ int nnal_k_gather_x16(nnal_ctx* ctx, const Volume& v, const int64_t* d_inds, int
 int nnal_k_gather_split(nnal_ctx* ctx, const Volume& v, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
                         const double* h_stats, int norm_mode, nnal_h* out_hi, nnal_h* out_lo) {
   if (n == 0) return NNAL_OK;
-  const NormTab tab = make_norm_tab(v, d3, h_stats, norm_mode);
+  const NormTab tab = nnal_make_norm_tab(v, d3, h_stats, norm_mode);
   int grid = (int)(n < (int64_t)ctx->sm_count * 32 ? n : (int64_t)ctx->sm_count * 32);
   gather_split_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)v.data, v.m, v.X, v.Y, v.Z, d_inds, n, d1, d2, d3, tab, out_hi,
                                                      out_lo);
@@ -332,7 +321,7 @@ int nnal_k_gather_split(nnal_ctx* ctx, const Volume& v, const int64_t* d_inds, i
   return NNAL_OK;
 }
 
-static NormTab make_norm_tab(const Volume& v, int d3, const double* h_stats, int norm_mode) {
+NormTab nnal_make_norm_tab(const Volume& v, int d3, const double* h_stats, int norm_mode) {
   NormTab tab;
   const int C = v.m * d3;
   for (int ch = 0; ch < 8; ++ch) {

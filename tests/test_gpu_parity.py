@@ -304,17 +304,43 @@ def test_conv_fused_pool(nb, H, Cin, Cout, ks, mode, n):
 # ------------------------------------------------------------------ fused gather / device-resident paths
 def test_fused_gather_matches_unfused(nb):
     """The gather that writes conv1's fp16 hi/lo planes directly must give the same posteriors as the
-    fp32 gather + split pass it replaces (bit-identical: same float64 normalisation, same split)."""
-    import os
+    fp32 gather + split pass it replaces (bit-identical: same float64 normalisation, same split); the default pool pass
+    -- conv1 gathering its own input, in the x-im2col'd form -- agrees with both within accumulation-order noise."""
     ps, imgs, padded, stats, pool, layers, w = _pw_setup(300, 44)
     model = nb.NN.create_PW1(2)
     model.set_weights(w)
-    a = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
-    nb.get_engine().debug_option('no_fused_gather', 1)
+    eng = nb.get_engine()
+    d = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
     try:
+        eng.debug_option('no_fused_conv1', 1)
+        a = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
+        eng.debug_option('no_fused_gather', 1)
         b = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
     finally:
-        nb.get_engine().debug_option('no_fused_gather', 0)
+        eng.debug_option('no_fused_gather', 0)
+        eng.debug_option('no_fused_conv1', 0)
+    assert np.array_equal(a, b)
+    assert np.abs(d - a).max() < 2e-5
+    want = O.batch_eval(layers, w, padded, pool, ps, 100, stats, 'posteriors')[0]
+    assert np.abs(d - want).max() < POST_TOL
+
+
+def test_conv1_gathering_its_input_equals_x_im2col_path(nb):
+    """conv1 with the gather fused in (default) runs the same MMAs on the same operand planes as the stand-alone x-im2col
+    gather + conv1 (debug options conv_x16 = 1, no_fused_conv1 = 1): bit-identical posteriors, ragged last chunk included."""
+    ps, imgs, padded, stats, pool, layers, w = _pw_setup(777, 46)
+    try:
+        nb.reset_engine()
+        eng = nb.get_engine()
+        eng.debug_option('conv_x16', 1)
+        eng.debug_option('chunk', 200)
+        model = nb.NN.create_PW1(2)
+        model.set_weights(w)
+        a = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
+        eng.debug_option('no_fused_conv1', 1)
+        b = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
+    finally:
+        nb.reset_engine()
     assert np.array_equal(a, b)
 
 
@@ -330,6 +356,7 @@ def test_x_im2col_gather_path_matches(nb):
     try:
         nb.reset_engine()
         nb.get_engine().debug_option('conv_x16', 1)          # before the weights are uploaded: conv1's packed form differs
+        nb.get_engine().debug_option('no_fused_conv1', 1)    # (the default pool pass lets conv1 gather its own input)
         model2 = nb.NN.create_PW1(2)
         model2.set_weights(w)
         a = nb.PW_NN.batch_eval(model2, None, padded, pool, ps, 100, stats, 'posteriors')[0]
