@@ -294,11 +294,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     // never leaves the SM.
     constexpr int NPOS = C::H * C::W, CH = 3, ROW = C::W * CH, NT = C::GATHER ? 32 * C::NGW : 32;
     constexpr int NE = NPOS * CH, PER = (NE + NT - 1) / NT;
-    __shared__ uint32_t sv[NE];                          // packed (hi | lo << 16)
+    // staging: fp16 hi and lo terms of the patch, row-major [25][RS] with 6 zero halves before and after the 75 values of a
+    // row, so that the 15 values a position needs -- (k - 2 .. k + 2) x 3 channels -- are 15 CONSECUTIVE halves starting at
+    // half 3 k: eight 32-bit words per plane, shifted by one half when k is odd (funnel shift), no bounds tests
+    constexpr int RS = 88, RSW = RS / 2;
+    __shared__ __align__(16) uint16_t svh[C::H * RS], svl[C::H * RS];
     const int pt = threadIdx.x - 32 * C::GW0;
     const int64_t Y0 = ga.Yp - (C::W - 1), Z0 = ga.Zp;
     // this thread's elements of a patch: e = pt + u NT -> (row i, offset r in the row, channel); the same for every sample
     int eoff[PER];
+    short srow[PER];                                     // index of the element in the staging rows
+    for (int e = pt; e < C::H * RS; e += NT) { svh[e] = 0; svl[e] = 0; }     // (pads stay zero; the values are rewritten per patch)
+    asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory");
     double mu[3], sg[3], rs[3];                          // by u % 3: element u has channel (pt + (NT % 3) u) % 3 (ROW = 0 mod 3)
     static_assert(!C::GATHER || (NT % 3 != 0 && ROW % 3 == 0), "channel pattern of the per-thread elements");
 #pragma unroll
@@ -306,6 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
       const int e = pt + u * NT;
       const int i = e / ROW, r = e - i * ROW;
       eoff[u] = e < NE ? (int)(i * ga.Yp * CH + r) : -1;
+      srow[u] = (short)(i * RS + 6 + r);
     }
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
@@ -342,7 +350,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
           nnal_ovf_track(amax, v);
           nnal_h h, l;
           nnal_split_unchecked(v, h, l);
-          if (e < NE) sv[e] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+          if (e < NE) { svh[srow[u]] = __half_as_ushort(h); svl[srow[u]] = __half_as_ushort(l); }
         }
         nnal_ovf_commit(amax);
       }
@@ -350,19 +358,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
       if (g + (int)gridDim.x < ngroups && !(ga.flags & 4)) fetch(g + gridDim.x);
       mbar_wait(in_empty(b), ph ^ 1, C::GATHER ? 200 : 0);
       uint8_t* dst = base_ptr + (size_t)b * C::IN_BYTES;
+      const uint32_t* wh = reinterpret_cast<const uint32_t*>(svh);
+      const uint32_t* wl = reinterpret_cast<const uint32_t*>(svl);
       for (int pos = pt; pos < NPOS && !(ga.flags & 2); pos += NT) {
         const int i = pos / C::W, k = pos - i * C::W;
-        uint32_t hw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int w0 = i * RSW + ((3 * k) >> 1);
+        const uint32_t sh = (k & 1) * 16u, top = (k & 1) ? 0xffffffffu : 0x0000ffffu;     // element 15 of a position is zero
+        uint32_t a[9], c[9], hw[8], lw[8];
 #pragma unroll
-        for (int j = 0; j < 15; ++j) {
-          const int dx = j / 3, ch = j - dx * 3;
-          const int kk = k + dx - 2;
-          if (kk >= 0 && kk < C::W) {
-            const uint32_t w = sv[(i * C::W + kk) * CH + ch];
-            hw[j >> 1] |= (w & 0xffffu) << ((j & 1) * 16);
-            lw[j >> 1] |= (w >> 16) << ((j & 1) * 16);
-          }
-        }
+        for (int j = 0; j < 8; ++j) { a[j] = wh[w0 + j]; c[j] = wl[w0 + j]; }
+        a[8] = 0u; c[8] = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { hw[j] = __funnelshift_r(a[j], a[j + 1], sh); lw[j] = __funnelshift_r(c[j], c[j + 1], sh); }
+        hw[7] &= top; lw[7] &= top;
         const size_t o = (size_t)((i + C::PH) * C::WP + k) * 16;
         *reinterpret_cast<uint4*>(dst + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         *reinterpret_cast<uint4*>(dst + C::PLANE + o) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
@@ -435,7 +443,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         tc_fence_after();
         const uint32_t a_hi16 = (in_base + b * C::IN_BYTES) >> 4;
 #pragma unroll 1
-        for (int tg = 0; tg < C::NG; ++tg, ++it_acc) {
+        for (int tgi = 0; tgi < C::NG; ++tgi, ++it_acc) {
+          // two tile groups of unequal size (conv1: 3 + 2 tiles): every other sample takes them in reverse order, so that
+          // the two epilogue warpgroups (one per accumulator) drain 5 tiles each per two samples instead of 6 and 4
+          const int tg = (C::NG == 2 && (it_in & 1)) ? C::NG - 1 - tgi : tgi;
           const int a = it_acc % C::NACC;
           const uint32_t ph_acc = (it_acc / C::NACC) & 1;
           mbar_wait(acc_empty(a), ph_acc ^ 1);
@@ -495,7 +506,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             __syncwarp();
           }
           if (elect_one_sync()) {
-            if (tg == C::NG - 1) umma_commit(in_empty(b));
+            if (tgi == C::NG - 1) umma_commit(in_empty(b));
             umma_commit(acc_full(a));
           }
           __syncwarp();
@@ -506,11 +517,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     // ===== epilogue: two warpgroups, warpgroup wg drains accumulator wg (every other tile group) =====
     const int qd = warp & 3;
     const int wg = (warp - 4) >> 2;
-    uint32_t it = 0;
-    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    uint32_t it = 0, it_s = 0;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it_s) {
 #pragma unroll 1
-      for (int tg = 0; tg < C::NG; ++tg, ++it) {
+      for (int tgi = 0; tgi < C::NG; ++tgi, ++it) {
         if ((int)(it % C::NACC) != wg) continue;
+        const int tg = (C::NG == 2 && (it_s & 1)) ? C::NG - 1 - tgi : tgi;       // (same order as the MMA issuer)
         const int a = it % C::NACC;
         uint32_t* my_pooled = pooled + a * C::POOL_WORDS;           // one pooled raster per accumulator (= per sample in flight)
         const uint32_t ph_acc = (it / C::NACC) & 1;
