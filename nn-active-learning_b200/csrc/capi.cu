@@ -5,6 +5,7 @@
 #include <cmath>
 #include <algorithm>
 #include <thread>
+#include <cstring>
 
 static const int NNAL_VERSION = 100;
 static const int64_t DEFAULT_CHUNK = 16384;   // samples per forward chunk (measured: 8192 -> 16384 = +1.5 %, flat beyond)
@@ -27,6 +28,7 @@ extern "C" int nnal_debug_option(nnal_ctx* ctx, const char* name, long value) {
   else if (n == "bw_no_tc") d.bw_no_tc = (int)value;
   else if (n == "bw_simt_fwd") d.bw_simt_fwd = (int)value;
   else if (n == "fi_flags") d.fi_flags = (int)value;
+  else if (n == "plain_upload") d.plain_upload = (int)value;
   else if (n == "conv_wt") ctx->use_wt = (int)value;       // 0 conv_tc.cu only, 1 conv_wt.cu where faster, 2 (default) + pool fusion, 3 wherever supported
   else if (n == "conv_x16") ctx->use_x16 = (int)value;     // conv1 on the x-im2col'd input (set BEFORE the weights are uploaded)
   else NNAL_FAIL(ctx, NNAL_ERR_INVALID, "unknown debug option");
@@ -157,6 +159,7 @@ static void free_layers(nnal_ctx* ctx) {
   }
   ctx->layers.clear();
 }
+static void upload_stage_release(nnal_ctx* ctx);
 static void free_buf(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 static void free_pool(nnal_ctx* ctx) {
   if (ctx->pool_post) cudaFree(ctx->pool_post);
@@ -194,6 +197,7 @@ extern "C" int nnal_ctx_destroy(nnal_ctx* ctx) {
   nnal_bw_release(ctx);
   nnal_sdp_release(ctx);
   nnal_tc_release(ctx);
+  upload_stage_release(ctx);
   free_buf(ctx->stage); free_buf(ctx->inds); free_buf(ctx->act[0]); free_buf(ctx->act[1]); free_buf(ctx->xin);
   free_buf(ctx->featbuf); free_buf(ctx->prevbuf); free_buf(ctx->logits); free_buf(ctx->splitA[0]); free_buf(ctx->splitA[1]);
   free_buf(ctx->topk_ws); free_buf(ctx->fi_ws);
@@ -364,6 +368,91 @@ extern "C" int nnal_model_set_weights(nnal_ctx* ctx, int layer, const float* W, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// host -> device copies of large PAGEABLE arrays (what np.pad hands the reference's callers): the driver's own staging
+// moves them at ~9 GB/s on this box (one thread), a pinned source at 51 GB/s.  Here T host threads copy 4 MB pieces into
+// their own pinned double buffers and issue the DMA of each piece on their own stream, so the link, not one core's memcpy,
+// is the bound.  Pinned (or registered) sources take the plain cudaMemcpyAsync path.
+// ---------------------------------------------------------------------------------------------
+struct UploadStage {
+  static constexpr int T = 8, SLOTS = 2;
+  static constexpr size_t PIECE = (size_t)4 << 20;
+  unsigned char* pinned = nullptr;             // [T][SLOTS][PIECE]
+  cudaStream_t streams[T] = {};
+  cudaEvent_t ev[T][SLOTS] = {};
+};
+struct H2DSeg { void* dst; const void* src; size_t bytes; };
+
+static void upload_stage_release(nnal_ctx* ctx) {
+  UploadStage* u = (UploadStage*)ctx->upload_state;
+  if (!u) return;
+  for (int t = 0; t < UploadStage::T; ++t) {
+    if (u->streams[t]) cudaStreamDestroy(u->streams[t]);
+    for (int s = 0; s < UploadStage::SLOTS; ++s) if (u->ev[t][s]) cudaEventDestroy(u->ev[t][s]);
+  }
+  if (u->pinned) cudaFreeHost(u->pinned);
+  delete u;
+  ctx->upload_state = nullptr;
+}
+
+static bool host_ptr_is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// copies every segment into device memory; returns with all copies COMPLETE or enqueued on ctx->stream
+static int h2d_segments(nnal_ctx* ctx, const std::vector<H2DSeg>& segs) {
+  size_t total = 0;
+  bool pageable = false;
+  for (const H2DSeg& s : segs) { total += s.bytes; pageable = pageable || host_ptr_is_pageable(s.src); }
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nt = (int)std::max(1u, std::min(hw ? hw : 1u, (unsigned)UploadStage::T));
+  if (!pageable || total < 4 * UploadStage::PIECE || nt < 2 || ctx->dbg.plain_upload) {
+    for (const H2DSeg& s : segs) CUDA_TRY(ctx, cudaMemcpyAsync(s.dst, s.src, s.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return NNAL_OK;
+  }
+  UploadStage* u = (UploadStage*)ctx->upload_state;
+  if (!u) {
+    u = new UploadStage();
+    ctx->upload_state = u;
+    CUDA_TRY(ctx, cudaHostAlloc((void**)&u->pinned, (size_t)UploadStage::T * UploadStage::SLOTS * UploadStage::PIECE, cudaHostAllocDefault));
+    for (int t = 0; t < UploadStage::T; ++t) {
+      CUDA_TRY(ctx, cudaStreamCreateWithFlags(&u->streams[t], cudaStreamNonBlocking));
+      for (int s = 0; s < UploadStage::SLOTS; ++s) CUDA_TRY(ctx, cudaEventCreateWithFlags(&u->ev[t][s], cudaEventDisableTiming));
+    }
+  }
+  // the destination may still be read by work queued on the library's stream (the previous subject's re-layout)
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<H2DSeg> pieces;
+  for (const H2DSeg& s : segs)
+    for (size_t o = 0; o < s.bytes; o += UploadStage::PIECE)
+      pieces.push_back({(char*)s.dst + o, (const char*)s.src + o, std::min(UploadStage::PIECE, s.bytes - o)});
+  std::vector<cudaError_t> errs(nt, cudaSuccess);
+  auto work = [&](int t) {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    int used = 0;
+    for (size_t c = t; c < pieces.size() && e == cudaSuccess; c += nt, ++used) {
+      const int s = used % UploadStage::SLOTS;
+      unsigned char* slot = u->pinned + ((size_t)t * UploadStage::SLOTS + s) * UploadStage::PIECE;
+      if (used >= UploadStage::SLOTS) e = cudaEventSynchronize(u->ev[t][s]);       // the slot's previous DMA has drained
+      if (e != cudaSuccess) break;
+      memcpy(slot, pieces[c].src, pieces[c].bytes);
+      e = cudaMemcpyAsync(pieces[c].dst, slot, pieces[c].bytes, cudaMemcpyHostToDevice, u->streams[t]);
+      if (e == cudaSuccess) e = cudaEventRecord(u->ev[t][s], u->streams[t]);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(u->streams[t]);
+    errs[t] = e;
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& t : th) t.join();
+  for (int t = 0; t < nt; ++t)
+    if (errs[t] != cudaSuccess) { ctx->err = std::string("staged host->device copy: ") + cudaGetErrorString(errs[t]); return NNAL_ERR_CUDA; }
+  return NNAL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // volumes
 // ---------------------------------------------------------------------------------------------
 static int volume_finish(nnal_ctx* ctx, Volume& v, const void* d_stage, int m, int dtype, int64_t X, int64_t Y, int64_t Z,
@@ -389,11 +478,12 @@ extern "C" int nnal_volume_set(nnal_ctx* ctx, int subject, int m, const void* co
   size_t in_elems = (size_t)X * Y * Z;
   size_t out_bytes = (size_t)(X + 2 * px) * (Y + 2 * py) * (Z + 2 * pz) * m * esz;
   NNAL_TRY(devbuf_reserve(ctx, ctx->stage, in_elems * m * esz));
+  std::vector<H2DSeg> segs;
   for (int j = 0; j < m; ++j) {
     if (!mods[j]) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "null modality pointer");
-    CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->stage.p + (size_t)j * in_elems * esz, mods[j], in_elems * esz,
-                                  cudaMemcpyHostToDevice, ctx->stream));
+    segs.push_back({(char*)ctx->stage.p + (size_t)j * in_elems * esz, mods[j], in_elems * esz});
   }
+  NNAL_TRY(h2d_segments(ctx, segs));
   return volume_finish(ctx, v, ctx->stage.p, m, dtype, X, Y, Z, px, py, pz, out_bytes);
 }
 

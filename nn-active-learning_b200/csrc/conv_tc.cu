@@ -133,6 +133,18 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_wait(uint32_t* a, uint32_t* b) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(b[0]),
+                 "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])
+               :
+               : "memory");
+}
 // waits for every outstanding tcgen05.ld of the thread; both register sets are in/out operands so that their uses stay below
 __device__ __forceinline__ void tmem_ld16_wait(uint32_t* a, uint32_t* b) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -145,7 +157,7 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t* a, uint32_t* b) {
 }
 
 // Compile-time geometry of one conv layer
-template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_, bool POOL_ = false, bool DUAL_ = false, int KW_ = 0, int NWG_ = 2, bool GATHER_ = false>
+template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_, bool POOL_ = false, bool DUAL_ = false, int KW_ = 0, int NWG_ = 2, bool GATHER_ = false, int NACC_ = 2>
 struct Cfg {
   static constexpr bool GATHER = GATHER_;                 // the input is gathered from the volume by producer warps (x-im2col'd conv1)
   static constexpr int NGW = GATHER_ ? 8 : 0;             // ... this many of them
@@ -160,7 +172,11 @@ struct Cfg {
   static constexpr int CIN = (CIN_REAL + 7) / 8 * 8, COUT = (COUT_REAL + 15) / 16 * 16;
   static constexpr int H = H_, W = W_, KS = KS_, G = G_;
   static constexpr int KPS = KPS_;                       // K-steps per weight stage
-  static constexpr int NBUF = NBUF_, NACC = 2, TG = TG_;  // TG: M tiles per accumulator (tile group)
+  // NACC accumulators in rotation, tile group it -> accumulator it % NACC -> epilogue warpgroup it % 2.  With NACC = 2 a
+  // warpgroup owns ONE accumulator: it idles while the tensor core refills it (conv1: the epilogue warps waited 50 % of the
+  // time, profiles/r2_conv1_fused.md); with NACC = 4 it alternates between two and the MMAs run a tile group ahead.
+  static constexpr int NBUF = NBUF_, NACC = NACC_, TG = TG_;  // TG: M tiles per accumulator (tile group)
+  static_assert(NACC_ == 2 || NACC_ == 4, "accumulators in rotation");
   static constexpr bool CAT = CAT_;                      // A_hi x [W_hi;W_lo] in one MMA (2 MMAs per K-step) or three separate MMAs
   static constexpr int KH = KS_, KW = KW_ > 0 ? KW_ : KS_;   // KW_ = 1: filter columns folded into the channels by an x-im2col'd input
   static constexpr int PH = KH / 2, PW = KW / 2;
@@ -194,7 +210,7 @@ struct Cfg {
   static_assert(COUT % 16 == 0 && 2 * COUT <= 256, "UMMA N");
   static_assert(TMEM_COLS_USED <= 512, "TMEM budget");
   static_assert(SMEM <= 232448, "shared memory budget");
-  static_assert(!POOL || (G == 1 && NG == 1), "fused pooling: one sample = one tile group = one epilogue warpgroup");
+  static_assert(!POOL || (G == 1 && NG == 1 && NACC == 2), "fused pooling: one sample = one tile group = one epilogue warpgroup");
   static_assert(!GATHER || (G == 1 && KW == 1 && CIN == 16 && KH == 5 && H == 25 && W == 25), "fused gather: conv1 of PW1 in the x-im2col'd form");
 };
 
@@ -204,7 +220,7 @@ struct GatherArgs {
   int64_t Xp, Yp, Zp;
   const int64_t* inds;
   NormTab tab;
-  int flags;                 // timing experiments (debug option wt_flags): 1 no normalise/split, 2 no operand assembly, 4 neither fetch
+  int flags;                 // debug option wt_flags -- timing experiments: 1 no normalise/split, 2 no operand assembly, 4 no fetch; tests: 8 float64 normalisation
 };
 
 struct ConvParams {
@@ -232,9 +248,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
   auto w_full = [&](int s) { return bar0 + 8u * (4 + s); };
   auto w_empty = [&](int s) { return bar0 + 8u * (7 + s); };
   auto acc_full = [&](int a) { return bar0 + 8u * (10 + a); };
-  auto acc_empty = [&](int a) { return bar0 + 8u * (12 + a); };
+  auto acc_empty = [&](int a) { return bar0 + 8u * (14 + a); };
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + C::NBUF * C::IN_BYTES + C::WSTAGES * C::W_STAGE_BYTES + 8 * 14);
+      reinterpret_cast<volatile uint32_t*>(base_ptr + C::NBUF * C::IN_BYTES + C::WSTAGES * C::W_STAGE_BYTES + 8 * 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ngroups = (p.n + C::G - 1) / C::G;
@@ -251,7 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     // two MMA-issuing threads (see below): every "MMAs retired" barrier collects one commit from each
     for (int b = 0; b < 2; ++b) { mbar_init(in_full(b), C::GATHER ? C::NGW : 1); mbar_init(in_empty(b), C::NISSUE); }
     for (int s = 0; s < 3; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), C::NISSUE); }
-    for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), C::NISSUE); mbar_init(acc_empty(a), 4); }
+    for (int a = 0; a < C::NACC; ++a) { mbar_init(acc_full(a), C::NISSUE); mbar_init(acc_empty(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -293,20 +309,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     // zero from the initial clear).  What the stand-alone gather wrote to HBM (and conv1 read back through 16-byte TMA rows)
     // never leaves the SM.
     constexpr int NPOS = C::H * C::W, CH = 3, ROW = C::W * CH, NT = C::GATHER ? 32 * C::NGW : 32;
-    constexpr int NE = NPOS * CH, PER = (NE + NT - 1) / NT;
+    constexpr int NE = NPOS * CH, PER = (NE + NT - 1) / NT, NPP = (NPOS + NT - 1) / NT;
     // staging: fp16 hi and lo terms of the patch, row-major [25][RS] with 6 zero halves before and after the 75 values of a
     // row, so that the 15 values a position needs -- (k - 2 .. k + 2) x 3 channels -- are 15 CONSECUTIVE halves starting at
-    // half 3 k: eight 32-bit words per plane, shifted by one half when k is odd (funnel shift), no bounds tests
+    // half 3 k: eight 32-bit words per plane, shifted by one half when k is odd (funnel shift), no bounds tests.  Two copies:
+    // sample s is staged while the stragglers still assemble sample s - 1 (one named barrier per sample).
     constexpr int RS = 88, RSW = RS / 2;
-    __shared__ __align__(16) uint16_t svh[C::H * RS], svl[C::H * RS];
+    __shared__ __align__(16) uint16_t svh[2][C::H * RS], svl[2][C::H * RS];
     const int pt = threadIdx.x - 32 * C::GW0;
     const int64_t Y0 = ga.Yp - (C::W - 1), Z0 = ga.Zp;
+    const bool small = Y0 < (1ll << 31) && Z0 < (1ll << 31);
     // this thread's elements of a patch: e = pt + u NT -> (row i, offset r in the row, channel); the same for every sample
     int eoff[PER];
     short srow[PER];                                     // index of the element in the staging rows
-    for (int e = pt; e < C::H * RS; e += NT) { svh[e] = 0; svl[e] = 0; }     // (pads stay zero; the values are rewritten per patch)
+    for (int e = pt; e < 2 * C::H * RS; e += NT) { (&svh[0][0])[e] = 0; (&svl[0][0])[e] = 0; }   // (pads stay zero; the values are rewritten per patch)
     asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory");
-    double mu[3], sg[3], rs[3];                          // by u % 3: element u has channel (pt + (NT % 3) u) % 3 (ROW = 0 mod 3)
     static_assert(!C::GATHER || (NT % 3 != 0 && ROW % 3 == 0), "channel pattern of the per-thread elements");
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
@@ -315,6 +332,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
       eoff[u] = e < NE ? (int)(i * ga.Yp * CH + r) : -1;
       srow[u] = (short)(i * RS + 6 + r);
     }
+    // this thread's raster positions pos = pt + j NT: first staging word, odd-column flag, byte offset in an operand plane
+    short aw0[NPP], aodd[NPP];
+    int aoff[NPP];
+#pragma unroll
+    for (int j = 0; j < NPP; ++j) {
+      const int pos = pt + j * NT;
+      const int i = pos / C::W, k = pos - i * C::W;
+      aw0[j] = (short)(i * RSW + ((3 * k) >> 1));
+      aodd[j] = (short)(k & 1);
+      aoff[j] = pos < NPOS ? ((i + C::PH) * C::WP + k) * 16 : -1;
+    }
+    // normalisation (x - mu) / sigma of channel q = u % 3 (element u has channel (pt + (NT % 3) u) % 3, ROW = 0 mod 3).
+    // Default: float32 two-term arithmetic, ((x - mu_hi) - mu_lo) * (r_hi + r_lo) with r = 1 / sigma: within 2^-22 of the
+    // float64 quotient, i.e. below what the fp16 hi/lo split keeps anyway -- the float64 pipe is 30x slower than the float32
+    // one on this chip and its eight divisions per thread took 44 % of the producers' time (profiles/r2_conv1_fused.md).
+    // exact (debug option wt_flags & 8, or a sigma without a usable reciprocal): the float64 sequence of batch_eval.
+    double mu[3], sg[3], rs[3];
+    float mh[3], ml[3], rh[3], rl[3];
+    bool exact = (ga.flags & 8) != 0;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       const int ch = (pt + (NT % 3) * q) % 3;
@@ -322,65 +358,93 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
       mu[q] = on ? ga.tab.mu[ch] : 0.0;
       sg[q] = on ? ga.tab.sg[ch] : 1.0;
       rs[q] = on ? ga.tab.rs[ch] : 1.0;                  // (x - 0) / 1 = x, exactly
+      mh[q] = (float)mu[q]; ml[q] = (float)(mu[q] - (double)mh[q]);
+      rh[q] = (float)rs[q]; rl[q] = (float)(rs[q] - (double)rh[q]);
     }
-    // all loads of a patch are issued before the first is used, and the NEXT patch is fetched while this one is assembled
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) exact = exact || (ga.tab.on[ch] && !(ga.tab.rs[ch] == ga.tab.rs[ch]));
+    // voxel id -> address of the patch corner (32-bit divisions whenever the id fits)
+    auto corner = [&](int64_t ind) -> const float* {
+      int64_t x, y, z;
+      if (small && (uint64_t)ind <= 0xffffffffull) {
+        const uint32_t i32 = (uint32_t)ind, z0 = (uint32_t)Z0, y0 = (uint32_t)Y0;
+        const uint32_t t = i32 / z0, xx = t / y0;
+        z = i32 - t * z0; y = t - xx * y0; x = xx;
+      } else {
+        z = ind % Z0;
+        const int64_t t = ind / Z0;
+        y = t % Y0;
+        x = t / Y0;
+      }
+      return ga.vol + ((z * ga.Xp + x) * ga.Yp + y) * CH;
+    };
+    // all loads of a patch are issued before the first is used, the NEXT patch is fetched while this one is assembled, and
+    // the voxel id of the patch after that is already on its way (its latency was 10 % of the producers' time)
     float raw[PER];
-    auto fetch = [&](int g) {
-      const int64_t ind = ga.inds[g];
-      const int64_t z = ind % Z0;
-      const int64_t t = ind / Z0;
-      const int64_t y = t % Y0;
-      const int64_t x = t / Y0;
-      const float* pbase = ga.vol + ((z * ga.Xp + x) * ga.Yp + y) * CH;
+    auto fetch = [&](int64_t ind) {
+      const float* pbase = corner(ind);
 #pragma unroll
       for (int u = 0; u < PER; ++u) raw[u] = eoff[u] >= 0 ? pbase[eoff[u]] : 0.f;
     };
-    if ((int)blockIdx.x < ngroups) fetch(blockIdx.x);
+    const int stride = (int)gridDim.x;
+    int64_t ind_next = 0;
+    if ((int)blockIdx.x < ngroups) fetch(ga.inds[blockIdx.x]);
+    if ((int)blockIdx.x + stride < ngroups) ind_next = ga.inds[blockIdx.x + stride];
     uint32_t it = 0;
-    for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
-      const int b = it % C::NBUF;
+    for (int g = blockIdx.x; g < ngroups; g += stride, ++it) {
+      const int b = it % C::NBUF, sb = it & 1;
       const uint32_t ph = (it / C::NBUF) & 1;
+      uint16_t* sh_ = svh[sb];
+      uint16_t* sl_ = svl[sb];
       if (!(ga.flags & 1)) {
-        // branch-free per element (the fp16 range check is one test per thread and patch): fifteen independent chains
+        // branch-free per element (the fp16 range check is one test per thread and patch): independent chains
         uint32_t amax = 0u;
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
           const int e = pt + u * NT;
-          const float v = (float)norm_apply((double)raw[u], mu[u % 3], sg[u % 3], rs[u % 3]);
+          float v;
+          if (exact) v = (float)norm_apply((double)raw[u], mu[u % 3], sg[u % 3], rs[u % 3]);
+          else {
+            const float d = (raw[u] - mh[u % 3]) - ml[u % 3];
+            v = fmaf(d, rl[u % 3], d * rh[u % 3]);
+          }
           nnal_ovf_track(amax, v);
           nnal_h h, l;
           nnal_split_unchecked(v, h, l);
-          if (e < NE) { svh[srow[u]] = __half_as_ushort(h); svl[srow[u]] = __half_as_ushort(l); }
+          if (e < NE) { sh_[srow[u]] = __half_as_ushort(h); sl_[srow[u]] = __half_as_ushort(l); }
         }
         nnal_ovf_commit(amax);
       }
       asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory");
-      if (g + (int)gridDim.x < ngroups && !(ga.flags & 4)) fetch(g + gridDim.x);
+      if (g + stride < ngroups && !(ga.flags & 4)) {
+        fetch(ind_next);
+        if (g + 2 * stride < ngroups) ind_next = ga.inds[g + 2 * stride];
+      }
       mbar_wait(in_empty(b), ph ^ 1, C::GATHER ? 200 : 0);
       uint8_t* dst = base_ptr + (size_t)b * C::IN_BYTES;
-      const uint32_t* wh = reinterpret_cast<const uint32_t*>(svh);
-      const uint32_t* wl = reinterpret_cast<const uint32_t*>(svl);
-      for (int pos = pt; pos < NPOS && !(ga.flags & 2); pos += NT) {
-        const int i = pos / C::W, k = pos - i * C::W;
-        const int w0 = i * RSW + ((3 * k) >> 1);
-        const uint32_t sh = (k & 1) * 16u, top = (k & 1) ? 0xffffffffu : 0x0000ffffu;     // element 15 of a position is zero
+      const uint32_t* wh = reinterpret_cast<const uint32_t*>(sh_);
+      const uint32_t* wl = reinterpret_cast<const uint32_t*>(sl_);
+#pragma unroll
+      for (int j = 0; j < NPP; ++j) {
+        if (aoff[j] < 0 || (ga.flags & 2)) continue;
+        const int w0 = aw0[j];
+        const uint32_t sh = (uint32_t)aodd[j] * 16u, top = aodd[j] ? 0xffffffffu : 0x0000ffffu;     // element 15 of a position is zero
         uint32_t a[9], c[9], hw[8], lw[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a[j] = wh[w0 + j]; c[j] = wl[w0 + j]; }
+        for (int t = 0; t < 8; ++t) { a[t] = wh[w0 + t]; c[t] = wl[w0 + t]; }
         a[8] = 0u; c[8] = 0u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { hw[j] = __funnelshift_r(a[j], a[j + 1], sh); lw[j] = __funnelshift_r(c[j], c[j + 1], sh); }
+        for (int t = 0; t < 8; ++t) { hw[t] = __funnelshift_r(a[t], a[t + 1], sh); lw[t] = __funnelshift_r(c[t], c[t + 1], sh); }
         hw[7] &= top; lw[7] &= top;
-        const size_t o = (size_t)((i + C::PH) * C::WP + k) * 16;
-        *reinterpret_cast<uint4*>(dst + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(dst + C::PLANE + o) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-        *reinterpret_cast<uint4*>(dst + 2 * C::PLANE + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        *reinterpret_cast<uint4*>(dst + 3 * C::PLANE + o) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        uint8_t* o = dst + aoff[j];
+        *reinterpret_cast<uint4*>(o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(o + C::PLANE) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        *reinterpret_cast<uint4*>(o + 2 * C::PLANE) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        *reinterpret_cast<uint4*>(o + 3 * C::PLANE) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core's reads
       __syncwarp();
       if (lane == 0) mbar_arrive(in_full(b));
-      asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory");           // sv is rewritten by the next sample
     }
   } else if (warp == 0) {
     // ===== input producer: Q 4-D TMA boxes {8ch, WP, HP, G} per (hi|lo), zero-filled borders =====
@@ -521,7 +585,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it_s) {
 #pragma unroll 1
       for (int tgi = 0; tgi < C::NG; ++tgi, ++it) {
-        if ((int)(it % C::NACC) != wg) continue;
+        if ((int)(it & 1) != wg) continue;
         const int tg = (C::NG == 2 && (it_s & 1)) ? C::NG - 1 - tgi : tgi;       // (same order as the MMA issuer)
         const int a = it % C::NACC;
         uint32_t* my_pooled = pooled + a * C::POOL_WORDS;           // one pooled raster per accumulator (= per sample in flight)
@@ -541,7 +605,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
           const size_t obase = (((size_t)sample * C::H + y) * C::W + x) * C::COUT_REAL;
           const uint32_t tcol = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * C::ACC_COLS + tl * C::TILE_COLS);
 #pragma unroll 1
-          for (int c0 = 0; c0 < C::COUT_REAL; c0 += 16) {
+          for (int c0 = 0; c0 + 16 <= C::COUT_REAL; c0 += 16) {
             // The epilogue is instruction bound (4 warps per accumulator, ~1 instruction per 5 cycles each): one wait for
             // both TMEM loads, the bias from shared memory as 4 broadcast 16-byte loads, packed fp16 conversions.
             float v[16];
@@ -565,11 +629,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
               uint32_t amax = 0u;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                if (c0 + j < C::COUT_REAL) {
-                  const float r = v[j] * p.w_scale_inv + bb[j];
-                  nnal_ovf_track(amax, r);
-                  atomicMax(pc + j, __float_as_uint(r > 0.f ? fminf(r, 65504.f) : 0.f));
-                }
+                const float r = v[j] * p.w_scale_inv + bb[j];
+                nnal_ovf_track(amax, r);
+                atomicMax(pc + j, __float_as_uint(r > 0.f ? fminf(r, 65504.f) : 0.f));
               }
               nnal_ovf_commit(amax);
             } else if (valid) {
@@ -592,10 +654,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
               uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
               dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              if (c0 + 8 < C::COUT_REAL) {                     // COUT_REAL is a multiple of 8
-                dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+          }
+          if (C::COUT_REAL % 16 == 8) {
+            // the last 8 channels (conv1: 24 = 16 + 8) on their own 8-column loads, not as half of a padded 16
+            static_assert(C::COUT_REAL % 16 == 0 || !C::POOL, "pooled epilogue: multiples of 16 channels");
+            constexpr int c0 = C::COUT_REAL / 16 * 16;
+            uint32_t rv[8], rw[8];
+            tmem_ld8_issue(tcol + c0, rv);
+            if (C::CAT) tmem_ld8_issue(tcol + C::COUT + c0, rw);
+            tmem_ld8_wait(rv, rw);
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0), b1 = *reinterpret_cast<const float4*>(sbias + c0 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            if (valid) {
+              uint32_t hi[4], lo[4], hmax = 0u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float s0 = C::CAT ? __uint_as_float(rv[2 * j]) + __uint_as_float(rw[2 * j]) : __uint_as_float(rv[2 * j]);
+                const float s1 = C::CAT ? __uint_as_float(rv[2 * j + 1]) + __uint_as_float(rw[2 * j + 1]) : __uint_as_float(rv[2 * j + 1]);
+                const float x0 = fmaxf(fmaf(s0, p.w_scale_inv, bb[2 * j]), 0.f);
+                const float x1 = fmaxf(fmaf(s1, p.w_scale_inv, bb[2 * j + 1]), 0.f);
+                const __half2 h = __floats2half2_rn(x0, x1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+                lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                nnal_ovf_track_h2(hmax, hi[j]);
               }
+              nnal_ovf_commit_h2(hmax);
+              *reinterpret_cast<uint4*>(p.out_hi + obase + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(p.out_lo + obase + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
           }
         }
@@ -703,7 +793,7 @@ typedef Cfg<25, 25, 3, 24, 5, 1, 7, 2, 3, true> CfgConv1;     // PW1 conv1: 3 in
 // instead of 6): 50 MMAs per sample instead of 156
 typedef Cfg<25, 25, 16, 24, 5, 1, 5, 2, 3, true, false, false, 1> CfgConv1X;
 // ... and with the gather fused in (the kernel reads the volume itself)
-typedef Cfg<25, 25, 16, 24, 5, 1, 5, 2, 3, true, false, false, 1, 2, true> CfgConv1XG;
+typedef Cfg<25, 25, 16, 24, 5, 1, 5, 2, 2, true, false, false, 1, 2, true, 4> CfgConv1XG;   // 5 M tiles in groups of 2 + 2 + 1, four accumulators of 2 x 64 columns
 typedef Cfg<25, 25, 24, 32, 5, 1, 8, 2, 3, true> CfgConv2;    // PW1 conv2: 6 M tiles in 2 groups of 3
 // conv3/conv4: the concatenated form was measured for conv3 (TG = 2, N = 96 + 48): 2.63 ms vs 2.61 ms per 100k samples
 // -- with only two accumulators in rotation the MMAs wait on each other (scripts/microbench/mma_rate.cu: 129 cycles

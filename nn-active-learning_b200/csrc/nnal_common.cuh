@@ -148,6 +148,7 @@ struct DebugOpts {
   int wt_flags = 0;            // conv_wt.cu timing experiments: 1 skip the epilogue stores, 2 skip the lo plane
   int sdp_no_coop = 0;         // one launch per SDP iteration instead of the cooperative loop
   int bw_no_ws = 0, bw_no_tc8 = 0, bw_no_tc = 0, bw_simt_fwd = 0;   // shrunk.cu fallbacks
+  int plain_upload = 0;        // volumes: one cudaMemcpyAsync per modality even from pageable memory (instead of the threaded pinned staging)
   int fi_flags = 0;            // fi.cu: 1 skip the column pass, 2 skip the evaluation, 4 skip stand-alone inversions (timing experiments, results are garbage);
                                // 8 one-pivot-at-a-time inverse inside the column kernel instead of the pipelined step, 16 no speculative columns (tests)
 };
@@ -208,6 +209,7 @@ struct nnal_ctx {
   DevBuf act_mc;                         // third activation buffer: the conv trunk's output must survive the T tail passes
   unsigned int* ovf_word = nullptr;      // device flag set by nnal_ovf_note (shared by the contexts of one device)
   unsigned int* ovf_host = nullptr;      // pinned host copy read by nnal_ovf_test
+  void* upload_state = nullptr;          // pinned staging ring + copy streams for pageable volumes (capi.cu)
 };
 
 #define CUDA_TRY(ctx, expr)                                                            \

@@ -326,8 +326,10 @@ def test_fused_gather_matches_unfused(nb):
 
 
 def test_conv1_gathering_its_input_equals_x_im2col_path(nb):
-    """conv1 with the gather fused in (default) runs the same MMAs on the same operand planes as the stand-alone x-im2col
-    gather + conv1 (debug options conv_x16 = 1, no_fused_conv1 = 1): bit-identical posteriors, ragged last chunk included."""
+    """conv1 with the gather fused in runs the same MMAs on the same operand planes as the stand-alone x-im2col gather + conv1
+    (debug options conv_x16 = 1, no_fused_conv1 = 1): with the float64 normalisation of batch_eval (wt_flags = 8) the
+    posteriors are bit-identical, ragged last chunk included; the default float32 two-term normalisation (error below the
+    2^-22 the fp16 hi/lo operands keep) moves them by less than 2e-6."""
     ps, imgs, padded, stats, pool, layers, w = _pw_setup(777, 46)
     try:
         nb.reset_engine()
@@ -336,12 +338,18 @@ def test_conv1_gathering_its_input_equals_x_im2col_path(nb):
         eng.debug_option('chunk', 200)
         model = nb.NN.create_PW1(2)
         model.set_weights(w)
+        d = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
+        eng.debug_option('wt_flags', 8)
         a = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
+        eng.debug_option('wt_flags', 0)
         eng.debug_option('no_fused_conv1', 1)
         b = nb.PW_NN.batch_eval(model, None, padded, pool, ps, 100, stats, 'posteriors')[0]
     finally:
         nb.reset_engine()
     assert np.array_equal(a, b)
+    assert np.abs(d - a).max() < 2e-6
+    want = O.batch_eval(layers, w, padded, pool, ps, 100, stats, 'posteriors')[0]
+    assert np.abs(d - want).max() < POST_TOL
 
 
 def test_x_im2col_gather_path_matches(nb):

@@ -182,3 +182,27 @@ def test_device_topk_merge_matches_global_stable_sort(nb):
     finally:
         e.close()
     assert len(pos) == 50 and np.array_equal(pos, 7 + np.argsort(scores[3], kind='stable')[:50])
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_large_pageable_volume_upload_is_exact(nb, dtype):
+    """Volumes beyond 16 MB in pageable host memory go through the threaded pinned staging (4 MB pieces on 8 copy
+    streams); the gathered patches are bit-identical to NumPy slicing, and to the plain single-copy upload."""
+    ps = (25, 25, 1)
+    shape = (131, 127, 97) if dtype == np.float32 else (101, 97, 67)     # odd sizes: the last piece of a modality is partial
+    rs = np.random.RandomState(5)
+    imgs = [rs.standard_normal(shape).astype(dtype) for _ in range(3)]
+    padded = pad_imgs(imgs, ps)
+    assert sum(p.nbytes for p in padded) > (16 << 20)
+    pool = rs.choice(int(np.prod(shape)), 300, replace=False).astype(np.int64)
+    eng = nb.get_engine()
+    eng.volume_cache = False
+    try:
+        got = nb.patch_utils.get_patches(padded, pool, ps)
+        eng.debug_option('plain_upload', 1)
+        plain = nb.patch_utils.get_patches(padded, pool, ps)
+    finally:
+        eng.debug_option('plain_upload', 0)
+        eng.volume_cache = True
+    want = O.get_patches(padded, pool, ps)
+    assert got.dtype == want.dtype and np.array_equal(got, want) and np.array_equal(plain, want)
