@@ -43,18 +43,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// backoff_ns > 0: sleep between polls -- for the waits of warps that are far from the critical path (epilogue, gather
-// producers): a polling warp takes issue slots from the warps that share its scheduler
+// try_wait with a suspend-time hint: the thread is parked by the hardware until the phase completes (or the hint, 10 ms,
+// runs out) -- it takes no issue slots from the warps that share its scheduler and wakes up at once.  (Round 2 had
+// __nanosleep(200) between polls for the warps "off the critical path": with two input buffers and two to four accumulators
+// every hand-off IS on the critical path, and the sleeps made the empty synchronisation skeleton of the fused conv1 cost
+// 1800 cycles per sample -- flags 55 experiment in profiles/r2_conv1_fused.md.)  `backoff_ns` > 0 selects the old polling.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned backoff_ns = 0) {
   uint32_t ok = 0;
   long long t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     if (ok) return;
     if (backoff_ns) __nanosleep(backoff_ns);
@@ -165,7 +168,7 @@ struct Cfg {
   static constexpr int NWG = 2;                           // epilogue warpgroups, one per accumulator: warpgroup wg drains every other tile group
   static_assert(NWG_ == 2, "tile-level splits over more warpgroups were measured slower: extra warps on the issuing warp's scheduler delay the MMAs");
   static constexpr int THREADS = 32 * (4 + 4 * NWG_ + 1 + NGW); // 4 service warps, 4 * NWG epilogue warps, the second MMA issuer, gather warps
-  static constexpr int NISSUE = DUAL_ ? 2 : 1;            // MMA-issuing threads (tiles of a group alternate between them)
+  static constexpr int NISSUE = DUAL_ ? 2 : 1;            // MMA-issuing threads that share a tile group (its tiles alternate between them)
   static constexpr bool POOL = POOL_;                     // fuse the following 2x2/s2 SAME max-pool into the epilogue
   // CIN / COUT are the padded operand extents (multiples of 8 / 16); the *_REAL values are the layer's
   static constexpr int CIN_REAL = CIN_REAL_, COUT_REAL = COUT_REAL_;
@@ -339,7 +342,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     for (int j = 0; j < NPP; ++j) {
       const int pos = pt + j * NT;
       const int i = pos / C::W, k = pos - i * C::W;
-      aw0[j] = (short)(i * RSW + ((3 * k) >> 1));
+      aw0[j] = pos < NPOS ? (short)(i * RSW + ((3 * k) >> 1)) : (short)0;
       aodd[j] = (short)(k & 1);
       aoff[j] = pos < NPOS ? ((i + C::PH) * C::WP + k) * 16 : -1;
     }
@@ -417,25 +420,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
       }
       asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory");
       if (g + stride < ngroups && !(ga.flags & 4)) {
+        // (the id is warp-uniform and ptxas would move it to a uniform register -- i.e. wait for the load -- right where it
+        // was issued, a whole sample earlier; the empty asm hides that it is the load's result until here)
+        asm volatile("" : "+l"(ind_next));
         fetch(ind_next);
         if (g + 2 * stride < ngroups) ind_next = ga.inds[g + 2 * stride];
       }
-      mbar_wait(in_empty(b), ph ^ 1, C::GATHER ? 200 : 0);
+      mbar_wait(in_empty(b), ph ^ 1, 0);
       uint8_t* dst = base_ptr + (size_t)b * C::IN_BYTES;
       const uint32_t* wh = reinterpret_cast<const uint32_t*>(sh_);
       const uint32_t* wl = reinterpret_cast<const uint32_t*>(sl_);
+      // (the loads of position j + 1 are issued before the stores of position j: the compiler cannot move shared-memory
+      // loads above shared-memory stores by itself, and their latency was a third of the assembly time)
+      uint32_t a[9], c[9];
+      a[8] = 0u; c[8] = 0u;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { a[t] = wh[aw0[0] + t]; c[t] = wl[aw0[0] + t]; }
 #pragma unroll
       for (int j = 0; j < NPP; ++j) {
-        if (aoff[j] < 0 || (ga.flags & 2)) continue;
-        const int w0 = aw0[j];
         const uint32_t sh = (uint32_t)aodd[j] * 16u, top = aodd[j] ? 0xffffffffu : 0x0000ffffu;     // element 15 of a position is zero
-        uint32_t a[9], c[9], hw[8], lw[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) { a[t] = wh[w0 + t]; c[t] = wl[w0 + t]; }
-        a[8] = 0u; c[8] = 0u;
+        uint32_t hw[8], lw[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) { hw[t] = __funnelshift_r(a[t], a[t + 1], sh); lw[t] = __funnelshift_r(c[t], c[t + 1], sh); }
         hw[7] &= top; lw[7] &= top;
+        if (j + 1 < NPP) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) { a[t] = wh[aw0[j + 1] + t]; c[t] = wl[aw0[j + 1] + t]; }
+        }
+        if (aoff[j] < 0 || (ga.flags & 2)) continue;
         uint8_t* o = dst + aoff[j];
         *reinterpret_cast<uint4*>(o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         *reinterpret_cast<uint4*>(o + C::PLANE) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
@@ -590,12 +602,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         const int a = it % C::NACC;
         uint32_t* my_pooled = pooled + a * C::POOL_WORDS;           // one pooled raster per accumulator (= per sample in flight)
         const uint32_t ph_acc = (it / C::NACC) & 1;
-        mbar_wait(acc_full(a), ph_acc, C::GATHER ? 200 : 0);
+        mbar_wait(acc_full(a), ph_acc, 0);
         tc_fence_after();
+        // The epilogue warps are latency bound (one or two warps per scheduler, every TMEM load ~100 and every bias load ~30
+        // cycles away): the accumulator loads run ONE 16-channel piece ahead of the arithmetic -- the load of the next piece
+        // (or of the next tile's first piece) is issued before the current one is converted and stored -- and the bias is
+        // fetched before the wait.  Pieces: NC16 of 16 channels + one of 8 when COUT_REAL = 8 mod 16 (conv1: 24 = 16 + 8).
+        constexpr int NC16 = C::COUT_REAL / 16, TAIL8 = (C::COUT_REAL % 16 == 8) ? 1 : 0, NPC = NC16 + TAIL8;
+        static_assert(C::COUT_REAL % 8 == 0 && (!C::POOL || TAIL8 == 0), "output channels: multiples of 8 (16 with the fused pool)");
+        const int ntl = (C::T - tg * C::TG) < C::TG ? (C::T - tg * C::TG) : C::TG;
+        const uint32_t tcol0 = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * C::ACC_COLS);
+        uint32_t rv[16], rw[16];
+        tmem_ld16_issue(tcol0, rv);                              // hi.hi + lo.hi (CAT) or the full sum
+        if (C::CAT) tmem_ld16_issue(tcol0 + C::COUT, rw);        // hi.lo
 #pragma unroll 1
-        for (int tl = 0; tl < C::TG; ++tl) {
+        for (int tl = 0; tl < ntl; ++tl) {
           const int t = tg * C::TG + tl;
-          if (t >= C::T) break;
           const int pos = t * 128 + qd * 32 + lane;              // padded-raster position of this thread's row
           const int gs = pos / (C::HP * C::WP);
           const int rem = pos - gs * (C::HP * C::WP);
@@ -603,25 +625,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
           const int sample = g * C::G + gs;
           const bool valid = gs < C::G && y < C::H && x < C::W && sample < p.n;
           const size_t obase = (((size_t)sample * C::H + y) * C::W + x) * C::COUT_REAL;
-          const uint32_t tcol = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * C::ACC_COLS + tl * C::TILE_COLS);
-#pragma unroll 1
-          for (int c0 = 0; c0 + 16 <= C::COUT_REAL; c0 += 16) {
-            // The epilogue is instruction bound (4 warps per accumulator, ~1 instruction per 5 cycles each): one wait for
-            // both TMEM loads, the bias from shared memory as 4 broadcast 16-byte loads, packed fp16 conversions.
-            float v[16];
-            {
-              uint32_t rv[16], rw[16];
-              tmem_ld16_issue(tcol + c0, rv);                    // hi.hi + lo.hi (CAT) or the full sum
-              if (C::CAT) tmem_ld16_issue(tcol + C::COUT + c0, rw);   // hi.lo
-              tmem_ld16_wait(rv, rw);
+          const uint32_t tcol = tcol0 + (uint32_t)(tl * C::TILE_COLS);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = C::CAT ? __uint_as_float(rv[j]) + __uint_as_float(rw[j]) : __uint_as_float(rv[j]);
-            }
+          for (int ci = 0; ci < NPC; ++ci) {
+            const int c0 = ci * 16;
+            const bool is8 = TAIL8 && ci == NC16;                // (compile-time after unrolling)
             float bb[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < (is8 ? 2 : 4); ++j) {
               const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
               bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
+            }
+            tmem_ld16_wait(rv, rw);
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < (is8 ? 8 : 16); ++j) v[j] = C::CAT ? __uint_as_float(rv[j]) + __uint_as_float(rw[j]) : __uint_as_float(rv[j]);
+            // next piece: the following one of this tile, or the first of the next tile
+            if (ci + 1 < NPC) {
+              if (TAIL8 && ci + 1 == NC16) {
+                tmem_ld8_issue(tcol + c0 + 16, rv);
+                if (C::CAT) tmem_ld8_issue(tcol + C::COUT + c0 + 16, rw);
+              } else {
+                tmem_ld16_issue(tcol + c0 + 16, rv);
+                if (C::CAT) tmem_ld16_issue(tcol + C::COUT + c0 + 16, rw);
+              }
+            } else if (tl + 1 < ntl) {
+              tmem_ld16_issue(tcol + C::TILE_COLS, rv);
+              if (C::CAT) tmem_ld16_issue(tcol + C::TILE_COLS + C::COUT, rw);
             }
             if (valid && C::POOL) {
               // post-ReLU values are >= +0, so their bit patterns order like unsigned integers
@@ -639,7 +669,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
               // lo term is garbage then, and the call fails with NNAL_ERR_OVERFLOW) -- 7 instead of 10 instructions per output
               uint32_t hi[8], lo[8], hmax = 0u;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < (is8 ? 4 : 8); ++j) {
                 const float x0 = fmaxf(fmaf(v[2 * j], p.w_scale_inv, bb[2 * j]), 0.f);
                 const float x1 = fmaxf(fmaf(v[2 * j + 1], p.w_scale_inv, bb[2 * j + 1]), 0.f);
                 const __half2 h = __floats2half2_rn(x0, x1);              // .x (low half) = x0
@@ -654,38 +684,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
               uint4* dl = reinterpret_cast<uint4*>(p.out_lo + obase + c0);
               dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-              dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            }
-          }
-          if (C::COUT_REAL % 16 == 8) {
-            // the last 8 channels (conv1: 24 = 16 + 8) on their own 8-column loads, not as half of a padded 16
-            static_assert(C::COUT_REAL % 16 == 0 || !C::POOL, "pooled epilogue: multiples of 16 channels");
-            constexpr int c0 = C::COUT_REAL / 16 * 16;
-            uint32_t rv[8], rw[8];
-            tmem_ld8_issue(tcol + c0, rv);
-            if (C::CAT) tmem_ld8_issue(tcol + C::COUT + c0, rw);
-            tmem_ld8_wait(rv, rw);
-            const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0), b1 = *reinterpret_cast<const float4*>(sbias + c0 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            if (valid) {
-              uint32_t hi[4], lo[4], hmax = 0u;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float s0 = C::CAT ? __uint_as_float(rv[2 * j]) + __uint_as_float(rw[2 * j]) : __uint_as_float(rv[2 * j]);
-                const float s1 = C::CAT ? __uint_as_float(rv[2 * j + 1]) + __uint_as_float(rw[2 * j + 1]) : __uint_as_float(rv[2 * j + 1]);
-                const float x0 = fmaxf(fmaf(s0, p.w_scale_inv, bb[2 * j]), 0.f);
-                const float x1 = fmaxf(fmaf(s1, p.w_scale_inv, bb[2 * j + 1]), 0.f);
-                const __half2 h = __floats2half2_rn(x0, x1);
-                const float2 hf = __half22float2(h);
-                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-                lo[j] = *reinterpret_cast<const uint32_t*>(&l);
-                nnal_ovf_track_h2(hmax, hi[j]);
+              if (!is8) {
+                dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
               }
-              nnal_ovf_commit_h2(hmax);
-              *reinterpret_cast<uint4*>(p.out_hi + obase + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(p.out_lo + obase + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
           }
         }
