@@ -160,8 +160,9 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t* a, uint32_t* b) {
 }
 
 // Compile-time geometry of one conv layer
-template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_, bool POOL_ = false, bool DUAL_ = false, int KW_ = 0, int NWG_ = 2, bool GATHER_ = false, int NACC_ = 2>
+template <int H_, int W_, int CIN_REAL_, int COUT_REAL_, int KS_, int G_, int KPS_, int NBUF_, int TG_, bool CAT_, bool POOL_ = false, bool DUAL_ = false, int KW_ = 0, int NWG_ = 2, bool GATHER_ = false, int NACC_ = 2, bool RAW_ = false>
 struct Cfg {
+  static constexpr bool RAW = RAW_;                       // epilogue writes acc * scale as float32, no bias, no ReLU (data-gradient convolutions)
   static constexpr bool GATHER = GATHER_;                 // the input is gathered from the volume by producer warps (x-im2col'd conv1)
   static constexpr int NGW = GATHER_ ? 8 : 0;             // ... this many of them
   static constexpr int GW0 = 4 + 4 * NWG_ + 1;            // first gather warp
@@ -213,6 +214,7 @@ struct Cfg {
   static_assert(COUT % 16 == 0 && 2 * COUT <= 256, "UMMA N");
   static_assert(TMEM_COLS_USED <= 512, "TMEM budget");
   static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(!(POOL && RAW_), "raw float32 output: unpooled");
   static_assert(!POOL || (G == 1 && NG == 1 && NACC == 2), "fused pooling: one sample = one tile group = one epilogue warpgroup");
   static_assert(!GATHER || (G == 1 && KW == 1 && CIN == 16 && KH == 5 && H == 25 && W == 25), "fused gather: conv1 of PW1 in the x-im2col'd form");
 };
@@ -231,6 +233,7 @@ struct ConvParams {
   const float* bias;
   nnal_h* out_hi;     // [n][H][W][COUT]
   nnal_h* out_lo;
+  float* out_f32;     // RAW: [n][H][W][COUT_REAL] float32
   int n;
   float w_scale_inv;
 };
@@ -260,7 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
   uint32_t* pooled = reinterpret_cast<uint32_t*>(base_ptr + C::NBUF * C::IN_BYTES + C::WSTAGES * C::W_STAGE_BYTES + 256);
   for (int i = threadIdx.x; i < C::POOL_BYTES / 4; i += blockDim.x) pooled[i] = 0u;
   __shared__ __align__(16) float sbias[(C::COUT + 15) / 16 * 16];
-  for (int i = threadIdx.x; i < (C::COUT + 15) / 16 * 16; i += blockDim.x) sbias[i] = i < C::COUT_REAL ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < (C::COUT + 15) / 16 * 16; i += blockDim.x) sbias[i] = (!C::RAW && i < C::COUT_REAL) ? p.bias[i] : 0.f;
 
   if (warp == 0 && lane == 0 && !C::GATHER) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmHi));
@@ -664,6 +667,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 atomicMax(pc + j, __float_as_uint(r > 0.f ? fminf(r, 65504.f) : 0.f));
               }
               nnal_ovf_commit(amax);
+            } else if (valid && C::RAW) {
+              float4* d4 = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
+#pragma unroll
+              for (int j = 0; j < (is8 ? 2 : 4); ++j)
+                d4[j] = make_float4(v[4 * j] * p.w_scale_inv, v[4 * j + 1] * p.w_scale_inv, v[4 * j + 2] * p.w_scale_inv,
+                                    v[4 * j + 3] * p.w_scale_inv);
             } else if (valid) {
               // post-ReLU values are >= 0: no clamp; a value beyond fp16 rounds to Inf, which the SIMD max below catches (the
               // lo term is garbage then, and the call fails with NNAL_ERR_OVERFLOW) -- 7 instead of 10 instructions per output
@@ -827,7 +836,8 @@ static int pack(nnal_ctx* ctx, Layer& L) { return pack_from<C>(ctx, L.W, (void**
 
 template <class C>
 static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
-                  nnal_h* out_lo, int64_t n, const void* wpack = nullptr, const GatherArgs* gather = nullptr) {
+                  nnal_h* out_lo, int64_t n, const void* wpack = nullptr, const GatherArgs* gather = nullptr, float* out_f32 = nullptr,
+                  float scale_inv = 0.f) {
   CUtensorMap tmHi, tmLo;
   GatherArgs ga;
   memset(&ga, 0, sizeof(ga));
@@ -845,7 +855,7 @@ static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal
     attr = true;
   }
   ConvParams p;
-  p.wpack = (const uint8_t*)(wpack ? wpack : L.Wh); p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.n = (int)n; p.w_scale_inv = L.w_scale_inv;
+  p.wpack = (const uint8_t*)(wpack ? wpack : L.Wh); p.bias = L.b; p.out_hi = out_hi; p.out_lo = out_lo; p.out_f32 = out_f32; p.n = (int)n; p.w_scale_inv = C::RAW ? scale_inv : L.w_scale_inv;
   const int ngroups = (int)((n + C::G - 1) / C::G);
   const int grid = ngroups < ctx->sm_count ? ngroups : ctx->sm_count;
   conv_tc_kernel<C><<<grid, C::THREADS, C::SMEM, ctx->stream>>>(tmHi, tmLo, p, ga);
@@ -960,4 +970,62 @@ int nnal_tc_conv(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_
   if (ctc::matches<ctc::CfgConv3>(L)) return ctc::launch<ctc::CfgConv3>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
   if (ctc::matches<ctc::CfgConv4>(L)) return ctc::launch<ctc::CfgConv4>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
   NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv shape not covered by the tensor-core kernel");
+}
+
+// ---- data-gradient convolutions (shrunk.cu): d_in = correlation of dz with the flipped, transposed filter ------------------
+// d_in[y][x][ci] = sum_{dy,dx,co} dz[y - dy + ph][x - dx + pw][co] W[dy][dx][ci][co] is the SAME-padded forward convolution of dz
+// (Cout channels) with W'[dy'][dx'][co][ci] = W[kh-1-dy'][kw-1-dx'][ci][co]: the same shift-GEMM kernel with the roles of the
+// channel counts swapped, a raw float32 epilogue (no bias, no ReLU) and dz as power-of-two scaled fp16 hi/lo planes.
+namespace ctc {
+//                 H   W  CIN COUT KS G KPS NBUF TG CAT  POOL   DUAL  KW NWG GATHER NACC RAW
+typedef Cfg<25, 25, 32, 24, 5, 1, 5, 1, 3, true, false, false, 0, 2, false, 2, true> CfgBwd2;   // PW1 conv2: one 108 KB input raster (no room for two)
+typedef Cfg<13, 13, 48, 32, 3, 1, 9, 2, 2, true, false, false, 0, 2, false, 2, true> CfgBwd3;   // PW1 conv3 (weights resident)
+typedef Cfg<13, 13, 96, 48, 3, 1, 3, 2, 2, true, false, false, 0, 2, false, 2, true> CfgBwd4;   // PW1 conv4
+
+template <class C>
+static bool matches_bwd(const Layer& L) {
+  return L.type == NNAL_LAYER_CONV && L.in_h == C::H && L.in_w == C::W && L.out_c == C::CIN_REAL && L.in_c == C::COUT_REAL &&
+         L.kh == C::KS && L.kw == C::KS;
+}
+// W fp32 [kh][kw][cin][cout] -> W' fp32 [kh][kw][cout][cin], taps reversed
+__global__ void flip_transpose_kernel(const float* __restrict__ W, float* __restrict__ Wf, int KH, int KW, int CIN, int COUT) {
+  const int total = KH * KW * CIN * COUT;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int ci = e % CIN, co = (e / CIN) % COUT, tap = e / (CIN * COUT);
+    const int dy = tap / KW, dx = tap % KW;
+    Wf[e] = W[((size_t)((KH - 1 - dy) * KW + (KW - 1 - dx)) * CIN + ci) * COUT + co];
+  }
+}
+template <class C>
+static int prepare_bwd(nnal_ctx* ctx, const Layer& L, void** packed) {
+  float* Wf = nullptr;
+  const int total = L.kh * L.kw * L.in_c * L.out_c;
+  CUDA_TRY(ctx, cudaMalloc(&Wf, (size_t)total * sizeof(float)));
+  flip_transpose_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(L.W, Wf, L.kh, L.kw, L.in_c, L.out_c);
+  ctx->launches++;
+  int rc = pack_from<C>(ctx, Wf, packed, L.w_scale);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(Wf);
+  return rc;
+}
+}  // namespace ctc
+
+bool nnal_tc_conv_bwd_supported(const nnal_ctx*, const Layer& L) {
+  return L.has_weights && (ctc::matches_bwd<ctc::CfgBwd2>(L) || ctc::matches_bwd<ctc::CfgBwd3>(L) || ctc::matches_bwd<ctc::CfgBwd4>(L));
+}
+// *packed: device buffer with the flipped, transposed filter in the kernel's operand layout (allocated here when null)
+int nnal_tc_conv_bwd_prepare(nnal_ctx* ctx, const Layer& L, void** packed) {
+  if (ctc::matches_bwd<ctc::CfgBwd2>(L)) return ctc::prepare_bwd<ctc::CfgBwd2>(ctx, L, packed);
+  if (ctc::matches_bwd<ctc::CfgBwd3>(L)) return ctc::prepare_bwd<ctc::CfgBwd3>(ctx, L, packed);
+  if (ctc::matches_bwd<ctc::CfgBwd4>(L)) return ctc::prepare_bwd<ctc::CfgBwd4>(ctx, L, packed);
+  NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient shape not covered by the tensor-core kernel");
+}
+// dz_hi / dz_lo: planes [n][H][W][Cout] of dz * 2^e; d_in [n][H][W][Cin] float32 = acc * scale_inv (scale_inv = 2^-e / w_scale)
+int nnal_tc_conv_bwd(nnal_ctx* ctx, const Layer& L, const void* packed, const nnal_h* dz_hi, const nnal_h* dz_lo, float* d_in,
+                     int64_t n, float scale_inv) {
+  if (n == 0) return NNAL_OK;
+  if (ctc::matches_bwd<ctc::CfgBwd2>(L)) return ctc::launch<ctc::CfgBwd2>(ctx, L, dz_hi, dz_lo, nullptr, nullptr, n, packed, nullptr, d_in, scale_inv);
+  if (ctc::matches_bwd<ctc::CfgBwd3>(L)) return ctc::launch<ctc::CfgBwd3>(ctx, L, dz_hi, dz_lo, nullptr, nullptr, n, packed, nullptr, d_in, scale_inv);
+  if (ctc::matches_bwd<ctc::CfgBwd4>(L)) return ctc::launch<ctc::CfgBwd4>(ctx, L, dz_hi, dz_lo, nullptr, nullptr, n, packed, nullptr, d_in, scale_inv);
+  NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient shape not covered by the tensor-core kernel");
 }

@@ -321,6 +321,11 @@ int nnal_k_split_x16(nnal_ctx*, const float* in, nnal_h* hi, nnal_h* lo, int64_t
 bool nnal_k_gather_x16_supported(const Volume&, int d1, int d2, int d3);
 int nnal_k_gather_x16(nnal_ctx*, const Volume&, const int64_t* d_inds, int64_t n, int d1, int d2, int d3,
                       const double* h_stats, int norm_mode, nnal_h* out_hi, nnal_h* out_lo);
+// data-gradient convolutions on the tensor cores (conv_tc.cu; used by shrunk.cu)
+bool nnal_tc_conv_bwd_supported(const nnal_ctx*, const Layer&);
+int nnal_tc_conv_bwd_prepare(nnal_ctx*, const Layer&, void** packed);
+int nnal_tc_conv_bwd(nnal_ctx*, const Layer&, const void* packed, const nnal_h* dz_hi, const nnal_h* dz_lo, float* d_in, int64_t n,
+                     float scale_inv);
 bool nnal_tc_conv_pool_supported(const nnal_ctx*, const Layer&);
 int nnal_tc_conv_pool(nnal_ctx*, const Layer&, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi, nnal_h* out_lo,
                       int64_t n);

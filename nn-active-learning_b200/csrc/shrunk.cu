@@ -35,6 +35,7 @@ struct TWeight {
 struct BwState {
   DevBuf acts, g[2], post, gout, sred, amax;
   std::vector<TWeight> wt;
+  std::vector<void*> cw;          // conv layers: flipped, transposed filter packed for the tensor-core data-gradient convolution
   unsigned long long wt_version = ~0ull;
 };
 
@@ -457,6 +458,8 @@ bool fc_bwd_tc_eligible(const nnal_ctx* ctx, const Layer& L) {
 void free_transposed(BwState* st) {
   for (auto& t : st->wt) { if (t.h) cudaFree(t.h); if (t.l) cudaFree(t.l); }
   st->wt.clear();
+  for (void* p : st->cw) if (p) cudaFree(p);
+  st->cw.clear();
 }
 
 int ensure_transposed(nnal_ctx* ctx, BwState* st) {
@@ -464,8 +467,13 @@ int ensure_transposed(nnal_ctx* ctx, BwState* st) {
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   free_transposed(st);
   st->wt.resize(ctx->layers.size());
+  st->cw.assign(ctx->layers.size(), nullptr);
   for (size_t i = 1; i < ctx->layers.size(); ++i) {        // layer 0 needs no data gradient
     const Layer& L = ctx->layers[i];
+    if (L.type == NNAL_LAYER_CONV && L.has_weights && nnal_tc_conv_bwd_supported(ctx, L)) {      // (bw_no_tc is tested at use)
+      NNAL_TRY(nnal_tc_conv_bwd_prepare(ctx, L, &st->cw[i]));
+      continue;
+    }
     if (!fc_bwd_tc_eligible(ctx, L) || !L.has_weights) continue;
     TWeight& t = st->wt[i];
     t.Kp = (L.out_dim + 63) / 64 * 64;
@@ -482,11 +490,11 @@ int ensure_transposed(nnal_ctx* ctx, BwState* st) {
   return NNAL_OK;
 }
 
-int fc_bwd_data_tc(nnal_ctx* ctx, BwState* st, const Layer& L, const TWeight& t, const float* dz, float* d_in, int64_t n) {
+// exponent e of the power of two that lifts the largest |dz| of the chunk to [2^13, 2^14); *zero: every entry is zero
+int gradient_exponent(nnal_ctx* ctx, BwState* st, const float* dz, int64_t cnt, int* e_out, bool* zero) {
   NNAL_TRY(devbuf_reserve(ctx, st->amax, 256));
   unsigned int* d_max = (unsigned int*)st->amax.p;
   CUDA_TRY(ctx, cudaMemsetAsync(d_max, 0, 4, ctx->stream));
-  const int64_t cnt = n * L.out_dim;
   absmax_kernel<<<grid_for(ctx, cnt, 8), 256, 0, ctx->stream>>>(dz, cnt, d_max);
   ctx->launches++;
   unsigned int bits = 0;
@@ -494,14 +502,21 @@ int fc_bwd_data_tc(nnal_ctx* ctx, BwState* st, const Layer& L, const TWeight& t,
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   float mx;
   memcpy(&mx, &bits, 4);
-  if (!(mx > 0.f)) {                                        // all-zero gradient (every unit masked): so is the result
+  *zero = !(mx > 0.f);
+  int ex = 0;
+  if (!*zero) frexpf(mx, &ex);                              // mx = f 2^ex, f in [0.5, 1)
+  *e_out = std::max(-100, std::min(100, 14 - ex));
+  return NNAL_OK;
+}
+
+int fc_bwd_data_tc(nnal_ctx* ctx, BwState* st, const Layer& L, const TWeight& t, const float* dz, float* d_in, int64_t n) {
+  int e;
+  bool zero;
+  NNAL_TRY(gradient_exponent(ctx, st, dz, n * L.out_dim, &e, &zero));
+  if (zero) {                                               // all-zero gradient (every unit masked): so is the result
     CUDA_TRY(ctx, cudaMemsetAsync(d_in, 0, (size_t)n * L.in_dim * sizeof(float), ctx->stream));
     return NNAL_OK;
   }
-  int ex;
-  frexpf(mx, &ex);                                          // mx = f 2^ex, f in [0.5, 1)
-  int e = 14 - ex;
-  e = std::max(-100, std::min(100, e));
   const float s = ldexpf(1.f, e);
   const size_t plane = (size_t)n * t.Kp * sizeof(nnal_h);
   NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[0], plane));
@@ -514,6 +529,31 @@ int fc_bwd_data_tc(nnal_ctx* ctx, BwState* st, const Layer& L, const TWeight& t,
   // out[n][in] = (1 / (s w_scale)) A[n][out] . B[in][out]^T
   return nnal_tc_gemm_planes(ctx, Ah, Al, t.Kp, n, t.h, t.l, t.Kp, L.in_dim, L.out_dim, nullptr,
                              ldexpf(1.f, -e) * L.w_scale_inv, 0, 0, d_in, L.in_dim, nullptr, nullptr, 0);
+}
+
+// ---- conv data gradient on the tensor cores ------------------------------------------------------------------------
+// The forward pass's shift-GEMM kernel (conv_tc.cu) on dz: fp16 hi/lo planes of dz * 2^e (same scaling as the fc gradient),
+// the flipped, transposed filter packed once per weight set, float32 output.  Replaces conv_bwd_data_kernel (fp32 CUDA cores,
+// 15 of the 23 ms of the backward pass at B = 10,000) for PW1's conv2 / conv3 / conv4.
+int conv_bwd_data_tc(nnal_ctx* ctx, BwState* st, const Layer& L, const void* packed, const float* dz, float* d_in, int64_t n) {
+  int e;
+  bool zero;
+  const int64_t rows = n * L.out_h * L.out_w;
+  NNAL_TRY(gradient_exponent(ctx, st, dz, rows * L.out_c, &e, &zero));
+  if (zero) {
+    CUDA_TRY(ctx, cudaMemsetAsync(d_in, 0, (size_t)n * L.in_h * L.in_w * L.in_c * sizeof(float), ctx->stream));
+    return NNAL_OK;
+  }
+  const size_t plane = (size_t)rows * L.out_c * sizeof(nnal_h);       // out_c is a multiple of 8 for every supported shape
+  NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[0], plane));
+  NNAL_TRY(devbuf_reserve(ctx, ctx->splitA[1], plane));
+  nnal_h* Ah = (nnal_h*)ctx->splitA[0].p;
+  nnal_h* Al = (nnal_h*)ctx->splitA[1].p;
+  bw_split_kernel<<<grid_for(ctx, rows * (int64_t)(L.out_c / 2), 16), 256, 0, ctx->stream>>>(dz, Ah, Al, rows, L.out_c, L.out_c,
+                                                                                             ldexpf(1.f, e));
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return nnal_tc_conv_bwd(ctx, L, packed, Ah, Al, d_in, n, ldexpf(1.f, -e) * L.w_scale_inv);
 }
 
 // ---- block reduction in float64 ----------------------------------------------------------------------------------
@@ -722,7 +762,11 @@ int shrunk_chunk(nnal_ctx* ctx, BwState* st, int64_t nb, int64_t n_total, int64_
         shrink_conv_kernel<<<(unsigned)nb, 256, sm, ctx->stream>>>(d, in_of(i), L.in_h, L.in_w, L.in_c, L.out_c, L.kh, L.kw,
                                                                    inv, S, tau, t);
         ctx->launches++;
-        if (i > 0) { NNAL_TRY(conv_bwd_data(ctx, L, d, other, nb)); d = other; pp ^= 1; }
+        if (i > 0) {
+          if (ctx->use_tc && !ctx->dbg.bw_no_tc && st->cw[i]) NNAL_TRY(conv_bwd_data_tc(ctx, st, L, st->cw[i], d, other, nb));
+          else NNAL_TRY(conv_bwd_data(ctx, L, d, other, nb));
+          d = other; pp ^= 1;
+        }
       }
       --t;
     }

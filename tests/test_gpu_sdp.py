@@ -115,6 +115,41 @@ def test_shrunk_gradients_pw1_and_A_matrices(nb):
     assert abs(O.sdp_objective(A, q) / O.sdp_objective(Ao, q) - 1) < OBJ_RTOL
 
 
+def test_conv_data_gradient_tensor_core_vs_cuda_core(nb):
+    """PW1's conv2 / conv3 / conv4 data gradients run as tcgen05 shift-GEMM convolutions of dz with the flipped, transposed
+    filter (conv_tc.cu, fp16 hi/lo planes of the power-of-two scaled gradient); debug option bw_no_tc = 1 selects the fp32
+    CUDA-core kernels (and the fp32 fc gradient).  Both meet the oracle's bar and agree with each other, ragged chunk included."""
+    ps, imgs, padded, stats, pool, layers, w = _pw_setup(150, 91)
+    model = nb.NN.create_PW1(2)
+    model.set_weights(w)
+    eng = nb.get_engine()
+    eng.set_model(model, None)
+    eng.upload(0, padded)
+    st = np.array(stats, dtype=np.float64)
+    eng.debug_option('bw_chunk', 64)
+    try:
+        l0 = eng.launches
+        post, g = eng.fi_shrunk_voxels(0, pool, ps, st, shape=padded[0].shape)
+        l_tc = eng.launches - l0
+        eng.debug_option('bw_no_tc', 1)
+        l0 = eng.launches
+        post2, g2 = eng.fi_shrunk_voxels(0, pool, ps, st, shape=padded[0].shape)
+        l_simt = eng.launches - l0
+    finally:
+        eng.debug_option('bw_no_tc', 0)
+        eng.debug_option('bw_chunk', 0)
+    assert l_tc > l_simt                    # (absmax + split launches of the three conv layers: the tensor-core path did run)
+    x = O.normalize_batch_eval(O.get_patches(padded, pool, ps), stats).astype(np.float32)
+    po, go = O.shrunk_class_gradients(layers, w, x)
+    def worst(a, b):
+        floor = 1e-3 * np.abs(b).max()
+        return max(np.abs(a[:, :, t] - b[:, :, t]).max() / max(np.abs(b[:, :, t]).max(), floor) for t in range(b.shape[2]))
+    print('tensor-core vs oracle %.3g, CUDA-core vs oracle %.3g, tensor-core vs CUDA-core %.3g' % (worst(g, go), worst(g2, go), worst(g, g2)))
+    _assert_shrunk_close(g, g2)
+    _assert_shrunk_close(g, go, outliers=0.02)
+    _assert_shrunk_close(g2, go, outliers=0.02)
+
+
 def _rand_A(n, tau, delta, seed, scale):
     rs = np.random.RandomState(seed)
     s = rs.randn(n, tau) * scale * np.exp(rs.randn(1, tau))
