@@ -314,6 +314,12 @@ def run_ours(args, rank, world):
             mark(3)
         return q_ent, sel[chosen], red
 
+    # The interpreter's cyclic collector walks every tracked object of the process (torch, NumPy, this harness: millions) whenever
+    # a generation-2 collection triggers -- 20-80 ms pauses at random steps of the host-timed e2e leg.  Objects alive now are
+    # moved to the permanent generation (they are never garbage); objects created later are collected as usual.
+    import gc
+    gc.collect()
+    gc.freeze()
     # untimed: the API path of the e2e leg once through as well (a fresh box pages the Python / NumPy / library code of that
     # path in from the image on first use; the timed e2e steps further down come W more untimed steps later)
     expr0 = Expr()
