@@ -813,6 +813,17 @@ typedef Cfg<25, 25, 24, 32, 5, 1, 8, 2, 3, true> CfgConv2;    // PW1 conv2: 6 M 
 typedef Cfg<13, 13, 32, 48, 3, 2, 6, 2, 4, false> CfgConv3;   // PW1 conv3: 2 samples, 4 M tiles
 typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2, false, false, true> CfgConv4;   // PW1 conv4: 2 M tiles, one per issuing thread
 typedef Cfg<13, 13, 48, 96, 3, 1, 3, 2, 2, false, true, true> CfgConv4Pool;   // ... with the following 2x2 max-pool fused (shared-memory atomicMax raster)
+// The same layer dict on a 28 x 28 x 1 input (BASELINE config 1, the reference's small CNN on MNIST-sized images): 28 x 28 and
+// 14 x 14 rasters.  Round 2 ran these on the FP32 CUDA-core kernels; the kernel template is shape-generic, a shape only needs
+// its tile plan.  conv2's 96 KB raster leaves room for one input buffer.
+typedef Cfg<28, 28, 1, 24, 5, 1, 7, 2, 3, true> CfgS1Conv1;    // 7 M tiles in groups of 3 + 3 + 1, weights resident
+typedef Cfg<28, 28, 24, 32, 5, 1, 8, 1, 3, true> CfgS1Conv2;
+typedef Cfg<14, 14, 32, 48, 3, 2, 6, 2, 4, false> CfgS1Conv3;  // 2 samples, 4 M tiles
+typedef Cfg<14, 14, 48, 96, 3, 1, 3, 2, 2, false, false, true> CfgS1Conv4;
+typedef Cfg<14, 14, 48, 96, 3, 1, 3, 2, 2, false, true, true> CfgS1Conv4Pool;
+// every forward configuration / every configuration with the fused pool
+#define NNAL_CTC_FWD(X) X(CfgConv1) X(CfgConv2) X(CfgConv3) X(CfgConv4) X(CfgS1Conv1) X(CfgS1Conv2) X(CfgS1Conv3) X(CfgS1Conv4)
+#define NNAL_CTC_POOL(X) X(CfgConv4Pool) X(CfgS1Conv4Pool)
 
 template <class C>
 static bool matches(const Layer& L) {
@@ -868,16 +879,17 @@ static int launch(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal
 
 bool nnal_tc_conv_supported(const nnal_ctx*, const Layer& L) {
   if (L.type != NNAL_LAYER_CONV || !L.Wh) return false;
-  return ctc::matches<ctc::CfgConv1>(L) || ctc::matches<ctc::CfgConv2>(L) || ctc::matches<ctc::CfgConv3>(L) ||
-         ctc::matches<ctc::CfgConv4>(L);
+#define X(C) if (ctc::matches<ctc::C>(L)) return true;
+  NNAL_CTC_FWD(X)
+#undef X
+  return false;
 }
 
 int nnal_tc_prepare_conv(nnal_ctx* ctx, Layer& L) {
   if (L.type != NNAL_LAYER_CONV) return NNAL_OK;
-  if (ctc::matches<ctc::CfgConv1>(L)) return ctc::pack<ctc::CfgConv1>(ctx, L);
-  if (ctc::matches<ctc::CfgConv2>(L)) return ctc::pack<ctc::CfgConv2>(ctx, L);
-  if (ctc::matches<ctc::CfgConv3>(L)) return ctc::pack<ctc::CfgConv3>(ctx, L);
-  if (ctc::matches<ctc::CfgConv4>(L)) return ctc::pack<ctc::CfgConv4>(ctx, L);
+#define X(C) if (ctc::matches<ctc::C>(L)) return ctc::pack<ctc::C>(ctx, L);
+  NNAL_CTC_FWD(X)
+#undef X
   return NNAL_OK;
 }
 
@@ -953,22 +965,27 @@ int nnal_tc_conv1_fused(nnal_ctx* ctx, const Layer& L, const FusedGather& fg, nn
 }
 // conv + the following 2x2/s2 SAME max-pool in one kernel: output planes are [n][ceil(H/2)][ceil(W/2)][Cout]
 bool nnal_tc_conv_pool_supported(const nnal_ctx*, const Layer& L) {
-  return L.type == NNAL_LAYER_CONV && L.Wh && ctc::matches<ctc::CfgConv4Pool>(L);
+  if (L.type != NNAL_LAYER_CONV || !L.Wh) return false;
+#define X(C) if (ctc::matches<ctc::C>(L)) return true;
+  NNAL_CTC_POOL(X)
+#undef X
+  return false;
 }
 int nnal_tc_conv_pool(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
                       nnal_h* out_lo, int64_t n) {
   if (n == 0) return NNAL_OK;
-  if (ctc::matches<ctc::CfgConv4Pool>(L)) return ctc::launch<ctc::CfgConv4Pool>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
+#define X(C) if (ctc::matches<ctc::C>(L)) return ctc::launch<ctc::C>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
+  NNAL_CTC_POOL(X)
+#undef X
   NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv+pool shape not covered by the tensor-core kernel");
 }
 
 int nnal_tc_conv(nnal_ctx* ctx, const Layer& L, const nnal_h* in_hi, const nnal_h* in_lo, nnal_h* out_hi,
                  nnal_h* out_lo, int64_t n) {
   if (n == 0) return NNAL_OK;
-  if (ctc::matches<ctc::CfgConv1>(L)) return ctc::launch<ctc::CfgConv1>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
-  if (ctc::matches<ctc::CfgConv2>(L)) return ctc::launch<ctc::CfgConv2>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
-  if (ctc::matches<ctc::CfgConv3>(L)) return ctc::launch<ctc::CfgConv3>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
-  if (ctc::matches<ctc::CfgConv4>(L)) return ctc::launch<ctc::CfgConv4>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
+#define X(C) if (ctc::matches<ctc::C>(L)) return ctc::launch<ctc::C>(ctx, L, in_hi, in_lo, out_hi, out_lo, n);
+  NNAL_CTC_FWD(X)
+#undef X
   NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv shape not covered by the tensor-core kernel");
 }
 
@@ -981,6 +998,11 @@ namespace ctc {
 typedef Cfg<25, 25, 32, 24, 5, 1, 5, 1, 3, true, false, false, 0, 2, false, 2, true> CfgBwd2;   // PW1 conv2: one 108 KB input raster (no room for two)
 typedef Cfg<13, 13, 48, 32, 3, 1, 9, 2, 2, true, false, false, 0, 2, false, 2, true> CfgBwd3;   // PW1 conv3 (weights resident)
 typedef Cfg<13, 13, 96, 48, 3, 1, 3, 2, 2, true, false, false, 0, 2, false, 2, true> CfgBwd4;   // PW1 conv4
+// ... and of the same layer dict on a 28 x 28 x 1 input (config 1)
+typedef Cfg<28, 28, 32, 24, 5, 1, 5, 1, 3, true, false, false, 0, 2, false, 2, true> CfgS1Bwd2;
+typedef Cfg<14, 14, 48, 32, 3, 1, 9, 2, 2, true, false, false, 0, 2, false, 2, true> CfgS1Bwd3;
+typedef Cfg<14, 14, 96, 48, 3, 1, 3, 2, 2, true, false, false, 0, 2, false, 2, true> CfgS1Bwd4;
+#define NNAL_CTC_BWD(X) X(CfgBwd2) X(CfgBwd3) X(CfgBwd4) X(CfgS1Bwd2) X(CfgS1Bwd3) X(CfgS1Bwd4)
 
 template <class C>
 static bool matches_bwd(const Layer& L) {
@@ -1011,21 +1033,25 @@ static int prepare_bwd(nnal_ctx* ctx, const Layer& L, void** packed) {
 }  // namespace ctc
 
 bool nnal_tc_conv_bwd_supported(const nnal_ctx*, const Layer& L) {
-  return L.has_weights && (ctc::matches_bwd<ctc::CfgBwd2>(L) || ctc::matches_bwd<ctc::CfgBwd3>(L) || ctc::matches_bwd<ctc::CfgBwd4>(L));
+  if (!L.has_weights) return false;
+#define X(C) if (ctc::matches_bwd<ctc::C>(L)) return true;
+  NNAL_CTC_BWD(X)
+#undef X
+  return false;
 }
 // *packed: device buffer with the flipped, transposed filter in the kernel's operand layout (allocated here when null)
 int nnal_tc_conv_bwd_prepare(nnal_ctx* ctx, const Layer& L, void** packed) {
-  if (ctc::matches_bwd<ctc::CfgBwd2>(L)) return ctc::prepare_bwd<ctc::CfgBwd2>(ctx, L, packed);
-  if (ctc::matches_bwd<ctc::CfgBwd3>(L)) return ctc::prepare_bwd<ctc::CfgBwd3>(ctx, L, packed);
-  if (ctc::matches_bwd<ctc::CfgBwd4>(L)) return ctc::prepare_bwd<ctc::CfgBwd4>(ctx, L, packed);
+#define X(C) if (ctc::matches_bwd<ctc::C>(L)) return ctc::prepare_bwd<ctc::C>(ctx, L, packed);
+  NNAL_CTC_BWD(X)
+#undef X
   NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient shape not covered by the tensor-core kernel");
 }
 // dz_hi / dz_lo: planes [n][H][W][Cout] of dz * 2^e; d_in [n][H][W][Cin] float32 = acc * scale_inv (scale_inv = 2^-e / w_scale)
 int nnal_tc_conv_bwd(nnal_ctx* ctx, const Layer& L, const void* packed, const nnal_h* dz_hi, const nnal_h* dz_lo, float* d_in,
                      int64_t n, float scale_inv) {
   if (n == 0) return NNAL_OK;
-  if (ctc::matches_bwd<ctc::CfgBwd2>(L)) return ctc::launch<ctc::CfgBwd2>(ctx, L, dz_hi, dz_lo, nullptr, nullptr, n, packed, nullptr, d_in, scale_inv);
-  if (ctc::matches_bwd<ctc::CfgBwd3>(L)) return ctc::launch<ctc::CfgBwd3>(ctx, L, dz_hi, dz_lo, nullptr, nullptr, n, packed, nullptr, d_in, scale_inv);
-  if (ctc::matches_bwd<ctc::CfgBwd4>(L)) return ctc::launch<ctc::CfgBwd4>(ctx, L, dz_hi, dz_lo, nullptr, nullptr, n, packed, nullptr, d_in, scale_inv);
+#define X(C) if (ctc::matches_bwd<ctc::C>(L)) return ctc::launch<ctc::C>(ctx, L, dz_hi, dz_lo, nullptr, nullptr, n, packed, nullptr, d_in, scale_inv);
+  NNAL_CTC_BWD(X)
+#undef X
   NNAL_FAIL(ctx, NNAL_ERR_UNSUPPORTED, "conv gradient shape not covered by the tensor-core kernel");
 }

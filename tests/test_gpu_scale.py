@@ -75,6 +75,12 @@ def test_config1_full_pool_2000(nb):
     q = nb.NNAL.CNN_query(model, expr, np.arange(2000), 'entropy', None)
     got = nb.get_engine().pool_posteriors().astype(np.float64)
     assert np.abs(got - post).max() < 1e-4
+    # the 28 x 28 / 14 x 14 conv shapes of this model have their own tcgen05 tile plans (conv_tc.cu CfgS1Conv1-4): no layer
+    # with weights falls back to the FP32 CUDA-core kernels
+    eng = nb.get_engine()
+    for i, (name, spec) in enumerate(layers[:-1]):
+        if spec[1] in ('conv', 'fc'):
+            assert eng.layer_info(i)[2] != 0, '%s runs on CUDA cores' % name
     H = O.compute_entropy(post.copy())
     assert_topk_equivalent(q, -H, 10, 1e-3 * np.abs(H).max())
     q = nb.NNAL.CNN_query(model, expr, np.arange(2000), 'fi', None)
