@@ -264,6 +264,8 @@ def run_ours(args, rank, world):
     import nnal_b200
     from nnal_b200 import _lib as L
     from nnal_b200 import dist, fi as fimod
+    if args.no_p2p:
+        fimod.p2p_enabled = False
 
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
@@ -472,6 +474,8 @@ def run_ours(args, rank, world):
                'entropy_half_s': det['entropy_half_s'], 'fi_half_s': det['fi_half_s']}
 
     cfg = workload_config(args, world)
+    if world > 1:
+        cfg['greedy_step_exchange'] = fimod.last_exchange
     if strong:
         cfg['config3_check'] = {kk: strong[kk] for kk in ('pool', 'subjects', 'hash_entropy', 'hash_fi', 'primal_vs_dual_rel')}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -846,6 +850,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--fi-B', type=int, default=10000, help='FI pre-filter size of the query round')
     ap.add_argument('--sdp-B', type=int, default=10000, help='candidates of the extra literal-FI (shrunk gradients + SDP) round at 1 GPU (0: skip)')
+    ap.add_argument('--no-p2p', action='store_true', help='greedy step messages through NCCL all-gather instead of the peer-memory exchange')
     ap.add_argument('--mc-T', type=int, default=10, help='MC-dropout passes of the extra MC-entropy round (0: skip)')
     ap.add_argument('--config4-slices', type=int, default=180, help='slices of the config-4 full-volume gather at 1 GPU (0: skip)')
     ap.add_argument('--strong-pool', type=int, default=1000000, help='fixed pool of the config-3 strong-scaling leg (0: skip)')

@@ -248,6 +248,18 @@ int nnal_fi_step_pack(nnal_ctx* ctx, int64_t step, void* d_msg);
 int nnal_fi_step_apply_gathered(nnal_ctx* ctx, int64_t step, const void* d_msgs, int world, int rank);
 int nnal_fi_result(nnal_ctx* ctx, int64_t k, int64_t* gids_out, double* red_out);
 
+/* All-gather of the per-step messages over NVLink peer memory instead of NCCL (csrc/p2p.cu): 100 dependent steps of one small
+ * message each are latency bound, and one kernel that stores into the peers' buffers and spins on their flags costs a third of
+ * an NCCL call.  The reference has no distributed code; the contract is SURVEY.md 8e, collective 3.
+ * nnal_p2p_alloc: (collective) allocate this rank's receive buffer for `world` slots of `slot_bytes` (multiple of 16) and return
+ * its 64-byte CUDA IPC handle; nnal_p2p_open: open the peers' handles (`handles` = world x 64 bytes in rank order, own entry
+ * ignored); nnal_p2p_allgather: enqueue exchange number `seq` (the same, increasing by one per call, on every rank) of the
+ * `nbytes` at `d_send` on nnal_stream(); *d_recv = device address of the gathered [world][slot_bytes] buffer, valid for the
+ * kernels enqueued after it until exchange seq + 2. */
+int nnal_p2p_alloc(nnal_ctx* ctx, int world, int rank, int64_t slot_bytes, unsigned char* handle_out);
+int nnal_p2p_open(nnal_ctx* ctx, const unsigned char* handles);
+int nnal_p2p_allgather(nnal_ctx* ctx, const void* d_send, int64_t nbytes, uint64_t seq, void** d_recv);
+
 /* ---- the reference's own FI coordinates: shrunk class-score gradients + SDP query distribution ------------------ */
 /* Replaces the 2B single-sample sess.run(model.grad_posts[y]) calls of PW_NNAL.gen_A_matrices (PW_NNAL.py:773-807;
  * graph built by NN.get_gradients NN.py:621-645, all trainable layers) followed by NNAL_tools.shrink_gradient(grad,'sum')

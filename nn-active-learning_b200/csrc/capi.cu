@@ -160,6 +160,7 @@ static void free_layers(nnal_ctx* ctx) {
   ctx->layers.clear();
 }
 static void upload_stage_release(nnal_ctx* ctx);
+int nnal_p2p_release(nnal_ctx* ctx);       // p2p.cu
 static void free_buf(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 static void free_pool(nnal_ctx* ctx) {
   if (ctx->pool_post) cudaFree(ctx->pool_post);
@@ -198,6 +199,7 @@ extern "C" int nnal_ctx_destroy(nnal_ctx* ctx) {
   nnal_sdp_release(ctx);
   nnal_tc_release(ctx);
   upload_stage_release(ctx);
+  nnal_p2p_release(ctx);
   free_buf(ctx->stage); free_buf(ctx->inds); free_buf(ctx->act[0]); free_buf(ctx->act[1]); free_buf(ctx->xin);
   free_buf(ctx->featbuf); free_buf(ctx->prevbuf); free_buf(ctx->logits); free_buf(ctx->splitA[0]); free_buf(ctx->splitA[1]);
   free_buf(ctx->topk_ws); free_buf(ctx->fi_ws);

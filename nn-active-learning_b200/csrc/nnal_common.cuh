@@ -210,6 +210,7 @@ struct nnal_ctx {
   unsigned int* ovf_word = nullptr;      // device flag set by nnal_ovf_note (shared by the contexts of one device)
   unsigned int* ovf_host = nullptr;      // pinned host copy read by nnal_ovf_test
   void* upload_state = nullptr;          // pinned staging ring + copy streams for pageable volumes (capi.cu)
+  void* p2p_state = nullptr;             // peer-memory exchange buffers of the multi-GPU greedy step (p2p.cu)
 };
 
 #define CUDA_TRY(ctx, expr)                                                            \

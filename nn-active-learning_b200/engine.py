@@ -650,6 +650,21 @@ class Engine(object):
     def fi_step_apply_gathered(self, step, d_msgs_ptr, world, rank):
         self._chk(self.lib.nnal_fi_step_apply_gathered(self.h, int(step), C.c_void_p(int(d_msgs_ptr)), int(world), int(rank)))
 
+    # peer-memory exchange of the greedy step messages (csrc/p2p.cu)
+    def p2p_alloc(self, world, rank, slot_bytes):
+        h = (C.c_ubyte * 64)()
+        self._chk(self.lib.nnal_p2p_alloc(self.h, int(world), int(rank), int(slot_bytes), C.cast(h, C.c_void_p)))
+        return bytes(h)
+
+    def p2p_open(self, handles):
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        self._chk(self.lib.nnal_p2p_open(self.h, C.cast(buf, C.c_void_p)))
+
+    def p2p_allgather(self, d_send_ptr, nbytes, seq):
+        out = C.c_void_p()
+        self._chk(self.lib.nnal_p2p_allgather(self.h, C.c_void_p(int(d_send_ptr)), int(nbytes), int(seq), C.byref(out)))
+        return out.value
+
     def fi_result(self, k):
         sel = np.empty(int(k), dtype=np.int64)
         red = np.empty(int(k), dtype=np.float64)

@@ -60,16 +60,76 @@ def greedy_select(eng, k, delta, gids=None):
     nbytes = eng.fi_msg_bytes()
     dev = eng.message_device
     send = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-    recv = torch.zeros(world * nbytes, dtype=torch.uint8, device=dev)
+    global last_exchange
+    p2p = _p2p_ready(eng, world, rank, nbytes)
+    last_exchange = 'nvlink peer memory (csrc/p2p.cu)' if p2p else 'all_gather_into_tensor'
+    recv = None if p2p else torch.zeros(world * nbytes, dtype=torch.uint8, device=dev)
     ctx = torch.cuda.stream(torch.cuda.ExternalStream(eng.stream)) if dev == 'cuda' else contextlib.nullcontext()
     with ctx:
         for t in range(k):
             eng.fi_step_pack(t, send.data_ptr())
-            td.all_gather_into_tensor(recv, send)
-            eng.fi_step_apply_gathered(t, recv.data_ptr(), world, rank)
+            if p2p:
+                # one kernel: peer stores of the message into every rank's buffer over NVLink + flag wait (csrc/p2p.cu)
+                gathered = eng.p2p_allgather(send.data_ptr(), nbytes, eng._p2p_seq)
+                eng._p2p_seq += 1
+            else:
+                td.all_gather_into_tensor(recv, send)
+                gathered = recv.data_ptr()
+            eng.fi_step_apply_gathered(t, gathered, world, rank)
+        if p2p:
+            eng.synchronize()          # `send` is read by the last exchange kernel
     sel, red = eng.fi_result(k)
     s = np.arange(1, k + 1, dtype=np.float64)
     return sel, (D - s) / delta + red, red
+
+
+last_exchange = None        # how the last multi-rank greedy_select moved its step messages
+p2p_enabled = True          # peer-memory exchange of the greedy step messages where CUDA IPC works; False: NCCL all-gather
+
+
+def _p2p_ready(eng, world, rank, nbytes):
+    """Sets up (once per message size) the peer-memory exchange of csrc/p2p.cu: every rank allocates its receive buffer, the
+    64-byte CUDA IPC handles are all-gathered and opened.  Collective; returns False on every rank if any rank cannot (gloo /
+    fake engine, IPC refused by the container) -- the loop then uses ``all_gather_into_tensor``."""
+    import torch
+    import torch.distributed as td
+    if not p2p_enabled or getattr(eng, 'message_device', 'cpu') != 'cuda' or not hasattr(eng, 'p2p_alloc') or \
+            td.get_backend() != 'nccl' or world > 16:
+        return False
+    if getattr(eng, '_p2p_key', None) == (world, rank, nbytes):
+        return True
+    if getattr(eng, '_p2p_key', None) == 'failed':
+        return False
+    def agreed(ok):
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device='cuda')
+        td.all_reduce(flag, op=td.ReduceOp.MIN)
+        return int(flag.item()) == 1
+    if getattr(eng, '_p2p_key', None) is not None:
+        eng.synchronize()              # a buffer of another message size is replaced: nobody may still be using it
+        td.barrier()
+    ok, h = True, None
+    try:
+        h = eng.p2p_alloc(world, rank, nbytes)
+    except Exception:
+        ok = False
+    if agreed(ok):
+        mine = torch.frombuffer(bytearray(h), dtype=torch.uint8).cuda()
+        allh = torch.empty(world * 64, dtype=torch.uint8, device='cuda')
+        td.all_gather_into_tensor(allh, mine)
+        try:
+            eng.p2p_open(allh.cpu().numpy().tobytes())
+        except Exception:
+            ok = False
+        ok = agreed(ok)
+    else:
+        ok = False
+    if not ok:
+        eng._p2p_key = 'failed'
+        return False
+    eng._p2p_key = (world, rank, nbytes)
+    if not hasattr(eng, '_p2p_seq'):
+        eng._p2p_seq = 0
+    return True
 
 
 last_report = None          # dict left by the last FI query run with expr.pars['fi_report'] = True (see gram_report)
