@@ -259,6 +259,10 @@ int nnal_fi_result(nnal_ctx* ctx, int64_t k, int64_t* gids_out, double* red_out)
 int nnal_p2p_alloc(nnal_ctx* ctx, int world, int rank, int64_t slot_bytes, unsigned char* handle_out);
 int nnal_p2p_open(nnal_ctx* ctx, const unsigned char* handles);
 int nnal_p2p_allgather(nnal_ctx* ctx, const void* d_send, int64_t nbytes, uint64_t seq, void** d_recv);
+/* same-process variant of nnal_p2p_open (several contexts in one process): nnal_p2p_base returns this context's buffer,
+ * nnal_p2p_open_local takes the `world` buffers in rank order */
+int nnal_p2p_base(nnal_ctx* ctx, void** own_base);
+int nnal_p2p_open_local(nnal_ctx* ctx, void* const* bases);
 
 /* ---- the reference's own FI coordinates: shrunk class-score gradients + SDP query distribution ------------------ */
 /* Replaces the 2B single-sample sess.run(model.grad_posts[y]) calls of PW_NNAL.gen_A_matrices (PW_NNAL.py:773-807;

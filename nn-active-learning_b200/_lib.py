@@ -97,6 +97,8 @@ SIGNATURES = {
     'nnal_p2p_alloc': (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int64, c_vp]),
     'nnal_p2p_open': (C.c_int, [c_vp, c_vp]),
     'nnal_p2p_allgather': (C.c_int, [c_vp, c_vp, C.c_int64, C.c_uint64, c_vp]),
+    'nnal_p2p_base': (C.c_int, [c_vp, c_vp]),
+    'nnal_p2p_open_local': (C.c_int, [c_vp, c_vp]),
     'nnal_fi_step_apply': (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int64, C.c_int, C.c_int64]),
     'nnal_fi_shrunk_tau': (C.c_int, [c_vp, C.POINTER(C.c_int)]),
     'nnal_fi_shrunk_images': (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),

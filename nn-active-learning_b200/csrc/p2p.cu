@@ -1,6 +1,6 @@
 // Small all-gather over NVLink peer memory for the per-step messages of the multi-GPU greedy selection (SURVEY.md 8e,
 // collective 3): 100 dependent steps, one 34 KB message per rank and step -- latency, not bandwidth.  An NCCL all-gather costs
-// 12-15 us per step here; this kernel costs one launch: block d of rank r stores r's message into slot r of rank d's receive
+// ~10 us more per step at 8 GPUs (greedy k = 100: 10.5 vs 9.5 ms, profiles/r2_bench_n8_*.json); this kernel is one launch: block d of rank r stores r's message into slot r of rank d's receive
 // buffer (peer stores through NVSwitch), publishes flag (d <- r) with a system-scope release, and waits for flag (r <- d).
 //
 // Every rank allocates one buffer  [flags: 16 x u32, padded to 1 KB][2 parities][world slots][slot bytes]  with cudaMalloc,
@@ -106,6 +106,28 @@ extern "C" int nnal_p2p_open(nnal_ctx* ctx, const unsigned char* handles) {
     CUDA_TRY(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     s->peers.base[r] = (unsigned char*)p;
     s->opened[r] = true;
+  }
+  return NNAL_OK;
+}
+
+// Same-process form (several contexts in one process -- the GPU tests, or a host that drives all GPUs from one process): the
+// peers' buffers are addressable as they are.  own_base: this rank's buffer (for the other contexts' nnal_p2p_open_local).
+extern "C" int nnal_p2p_base(nnal_ctx* ctx, void** own_base) {
+  if (!ctx || !own_base) return NNAL_ERR_INVALID;
+  p2p::State* s = p2p::get(ctx);
+  if (!s) NNAL_FAIL(ctx, NNAL_ERR_STATE, "nnal_p2p_alloc not called");
+  *own_base = s->base;
+  return NNAL_OK;
+}
+extern "C" int nnal_p2p_open_local(nnal_ctx* ctx, void* const* bases) {
+  if (!ctx || !bases) return NNAL_ERR_INVALID;
+  p2p::State* s = p2p::get(ctx);
+  if (!s) NNAL_FAIL(ctx, NNAL_ERR_STATE, "nnal_p2p_alloc not called");
+  for (int r = 0; r < s->world; ++r) {
+    if (r == s->rank) continue;
+    if (!bases[r]) NNAL_FAIL(ctx, NNAL_ERR_INVALID, "null peer buffer");
+    s->peers.base[r] = (unsigned char*)bases[r];
+    s->opened[r] = false;                                  // not an IPC mapping: nothing to close
   }
   return NNAL_OK;
 }

@@ -660,6 +660,15 @@ class Engine(object):
         buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
         self._chk(self.lib.nnal_p2p_open(self.h, C.cast(buf, C.c_void_p)))
 
+    def p2p_base(self):
+        out = C.c_void_p()
+        self._chk(self.lib.nnal_p2p_base(self.h, C.byref(out)))
+        return out.value
+
+    def p2p_open_local(self, bases):
+        arr = (C.c_void_p * len(bases))(*[int(b) for b in bases])
+        self._chk(self.lib.nnal_p2p_open_local(self.h, C.cast(arr, C.c_void_p)))
+
     def p2p_allgather(self, d_send_ptr, nbytes, seq):
         out = C.c_void_p()
         self._chk(self.lib.nnal_p2p_allgather(self.h, C.c_void_p(int(d_send_ptr)), int(nbytes), int(seq), C.byref(out)))

@@ -206,3 +206,40 @@ def test_large_pageable_volume_upload_is_exact(nb, dtype):
         eng.volume_cache = True
     want = O.get_patches(padded, pool, ps)
     assert got.dtype == want.dtype and np.array_equal(got, want) and np.array_equal(plain, want)
+
+
+def test_peer_memory_allgather_protocol(nb):
+    """csrc/p2p.cu, the all-gather of the greedy step messages over peer memory: three contexts on one GPU open each other's
+    buffers (same-process form of the IPC set-up) and run 40 back-to-back exchanges, nothing but stream order and the flags
+    between them.  Every rank must see every rank's message of THAT exchange (two slot parities, monotonic flag values)."""
+    import torch
+    from nnal_b200 import dist
+    world, nbytes, steps = 3, 4096 + 64, 40
+    engs = [nb.Engine(0) for _ in range(world)]
+    try:
+        for r, e in enumerate(engs):
+            e.p2p_alloc(world, r, nbytes)
+        bases = [e.p2p_base() for e in engs]
+        for e in engs:
+            e.p2p_open_local(bases)
+        # payload of (rank r, exchange q): bytes (r * 31 + q * 7 + i) mod 251, all prepared before the first launch
+        i = torch.arange(nbytes, dtype=torch.int64, device='cuda')
+        send = [[((r * 31 + q * 7 + i) % 251).to(torch.uint8) for q in range(steps)] for r in range(world)]
+        got = [torch.zeros(steps, world * nbytes, dtype=torch.uint8, device='cuda') for _ in range(world)]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.ExternalStream(e.stream) for e in engs]
+        for q in range(steps):
+            for r, e in enumerate(engs):
+                ptr = e.p2p_allgather(send[r][q].data_ptr(), nbytes, 1000 + q)      # (sequence numbers need not start at 0)
+                with torch.cuda.stream(streams[r]):
+                    got[r][q].copy_(dist.device_view(ptr, (world * nbytes,), '|u1'))
+        for e in engs:
+            e.synchronize()
+        want = torch.stack([torch.cat([send[r][q] for r in range(world)]) for q in range(steps)])
+        for r in range(world):
+            assert torch.equal(got[r], want), 'rank %d' % r
+        with pytest.raises(ValueError):
+            engs[0].p2p_allgather(send[0][0].data_ptr(), nbytes + 16, 0)          # larger than the slot
+    finally:
+        for e in engs:
+            e.close()
