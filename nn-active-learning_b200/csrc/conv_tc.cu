@@ -1,7 +1,10 @@
 // tcgen05 implicit-GEMM convolution (SAME, stride 1, bias, ReLU) for the patch CNN (sm_100a).
 //
-// Replaces tf.nn.conv2d + bias + relu of NN.CNN.add_conv (NN.py:258-301) for layers whose input has
-// a multiple of 8 channels (conv2/conv3/conv4 of PW1).  Precision: 3-term bf16 split as in gemm_tc.cu.
+// Replaces tf.nn.conv2d + bias + relu of NN.CNN.add_conv (NN.py:258-301) -- conv1 (with the patch gather of
+// patch_utils.get_patches / PW_NN.batch_eval fused in), conv3, conv4 (+ max2) of PW1, the same layer dict on 28 x 28 x 1 images
+// (BASELINE config 1), and the conv DATA gradients of the shrunk-gradient pass (tf.gradients, NN.py:621-645) as forward
+// convolutions with the flipped, transposed filter (raw float32 epilogue).  conv2 of PW1 runs on conv_wt.cu.
+// Precision: fp16 hi/lo split operands, three products per term, FP32 accumulation in TMEM, as gemm_tc.cu.
 //
 // "Shift" implicit GEMM -- no im2col is ever materialised:
 //   * A group of G samples is TMA-loaded ONCE into shared memory as zero-padded rasters (TMA
@@ -26,8 +29,11 @@
 //     once per tile group): 2 x TG x 2Cout accumulator columns fit TMEM, so the epilogue of one tile group
 //     overlaps the MMAs of the next.
 // Warp roles: warp 0 input TMA, warp 3 weight producer, warps 1 and 12 MMA issuers, warp 2 TMEM allocator,
-// warps 4-11 epilogue (TMEM -> +bias, ReLU -> fp16 hi/lo NHWC in global memory, or the fused max-pool raster):
-// two warpgroups, one per accumulator.
+// warps 4-11 epilogue (TMEM -> +bias, ReLU -> fp16 hi/lo NHWC in global memory, the fused max-pool raster, or raw float32):
+// two warpgroups, each draining one (NACC = 2) or two (NACC = 4) accumulators in rotation; GATHER: warps 13-20 are the
+// input producers instead of the TMA (volume -> normalise -> split -> x-im2col'd operand planes in shared memory).
+// What bounds these kernels is the SM's shared-memory data path -- the tensor core's operand fetch of narrow-N MMAs plus
+// everything the LSU moves -- not tensor math (profiles/r2_conv1_fused.md).
 #include "nnal_common.cuh"
 #include <cuda.h>
 
@@ -781,7 +787,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// activation tensor [n][H][W][C] bf16 viewed as 4-D (c, x, y, sample) with box {8, WP, HP, G}
+// activation tensor [n][H][W][C] fp16 viewed as 4-D (c, x, y, sample) with box {8, WP, HP, G}
 static int make_act_tmap(nnal_ctx* ctx, CUtensorMap* tm, const void* ptr, int n, int H, int W, int C, int WP, int HP, int G) {
   EncodeTiledFn enc = get_encode();
   if (!enc) NNAL_FAIL(ctx, NNAL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");

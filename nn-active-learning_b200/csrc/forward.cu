@@ -1,5 +1,5 @@
 // Forward driver: walks the layer list for one chunk of samples and picks, per layer, the tensor-core
-// kernel (bf16 hi/lo operand planes) or the FP32 CUDA-core kernel, converting the activation format
+// kernel (fp16 hi/lo operand planes) or the FP32 CUDA-core kernel, converting the activation format
 // only where two neighbouring layers disagree.  Replaces one sess.run(model.posteriors / feature_layer)
 // of PW_NN.batch_eval (PW_NN.py:522-524).
 #include "nnal_common.cuh"
@@ -25,7 +25,7 @@ bool layer_on_tc(const nnal_ctx* ctx, int i) {
   return false;
 }
 
-// does the consumer of layer i's output (skipping pools) want bf16 hi/lo planes?
+// does the consumer of layer i's output (skipping pools) want fp16 hi/lo planes?
 bool consumer_wants_split(const nnal_ctx* ctx, int i) {
   const int nl = (int)ctx->layers.size();
   int j = i + 1;
@@ -73,7 +73,7 @@ int nnal_forward_chunk(nnal_ctx* ctx, int64_t nb, int64_t offset, int input_form
   }
   int pp = 0;
   auto next_buf = [&](int64_t elems, Act& o) {
-    // both formats occupy 4 bytes per element: fp32, or a bf16 hi plane followed by a bf16 lo plane
+    // both formats occupy 4 bytes per element: fp32, or an fp16 hi plane followed by an fp16 lo plane
     o.f32 = (float*)ctx->act[pp].p;
     o.hi = (nnal_h*)ctx->act[pp].p;
     o.lo = o.hi + nb * elems;

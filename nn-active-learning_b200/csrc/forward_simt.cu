@@ -114,7 +114,7 @@ static int conv_simt_launch(nnal_ctx* ctx, const Layer& L, const float* in, floa
 int nnal_k_conv_simt(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64_t n) {
   return conv_simt_launch(ctx, L, in, out, nullptr, nullptr, n);
 }
-// same kernel, output written as bf16 hi/lo planes (operand format of the tensor-core layers)
+// same kernel, output written as fp16 hi/lo planes (operand format of the tensor-core layers)
 int nnal_k_conv_simt_split(nnal_ctx* ctx, const Layer& L, const float* in, nnal_h* out_hi, nnal_h* out_lo, int64_t n) {
   return conv_simt_launch(ctx, L, in, nullptr, out_hi, out_lo, n);
 }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ in,
   }
 }
 
-// max-pool on bf16 hi/lo planes: the max of x = hi + lo is the pair whose sum is largest (exact).
+// max-pool on fp16 hi/lo planes: the max of x = hi + lo is the pair whose sum is largest (exact).
 // One thread pools 8 channels (one 16-byte vector of each plane) of one output position.
 __device__ __forceinline__ void pool8_update(const uint4& h, const uint4& l, float* m, uint32_t* bh, uint32_t* bl) {
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};

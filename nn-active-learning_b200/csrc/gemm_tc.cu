@@ -4,10 +4,12 @@
 //
 // Precision: the north-star tolerance (posteriors within 1e-4 absolute of the float64 oracle) rules out
 // single-pass bf16 / fp16 / tf32 operands (measured: 2e-3 / 1.2e-4 / 1.1e-4 max posterior error on PW1,
-// DESIGN.md §precision).  Operands are therefore split into two bf16 terms x = hi + lo
-// (hi = bf16(x), lo = bf16(x - hi)) and each K-step issues three kind::f16 MMAs
-//   hi.hi + hi.lo + lo.hi      (lo.lo ~ 2^-18 relative is dropped)
-// into one FP32 TMEM accumulator: ~2^-16 relative operand error, 2e-6 max posterior error.
+// DESIGN.md 4).  Operands are therefore split into two fp16 terms x = hi + lo
+// (hi = fp16(x), lo = fp16(x - hi); weights scaled by a power of two so that the lo terms stay normal) and each K-step issues
+// three kind::f16 MMAs
+//   hi.hi + hi.lo + lo.hi      (lo.lo ~ 2^-22 relative is dropped)
+// into FP32 TMEM accumulators (chunks of 8 k-blocks, summed with round-to-nearest in registers: the tensor core accumulates
+// with round-toward-zero): 1.1e-5 ... 2.3e-5 max posterior error measured on PW1.
 //
 // Structure (one persistent CTA per SM, 384 threads):
 //   warp 0    : TMA producer  -- cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B) of A_hi, A_lo, W_hi, W_lo
@@ -146,7 +148,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 struct FcParams {
   const float* bias;
   float* out;
-  nnal_h* out_hi;     // optional: bf16 split planes of the activated output (next layer's A operand)
+  nnal_h* out_hi;     // optional: fp16 split planes of the activated output (next layer's A operand)
   nnal_h* out_lo;
   int ld_split;              // row stride (elements) of the split planes
   int M, N, num_kb, relu, ldo;
@@ -383,7 +385,7 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
   }
 }
 
-// fp32 [M][K] -> bf16 hi/lo planes [M][Kp] (zero padded columns)
+// fp32 [M][K] -> fp16 hi/lo planes [M][Kp] (zero padded columns)
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ in, nnal_h* __restrict__ hi,
                                                      nnal_h* __restrict__ lo, int64_t M, int K, int Kp, float scale) {
   const int64_t total = M * (int64_t)(Kp / 2);
@@ -423,7 +425,7 @@ static int get_state(nnal_ctx* ctx, TcState** out) {
   return NNAL_OK;
 }
 
-// 2-D bf16 tensor [rows][ld] (ld elements per row, `cols` valid) with a {64, box_rows} SWIZZLE_128B box
+// 2-D fp16 tensor [rows][ld] (ld elements per row, `cols` valid) with a {64, box_rows} SWIZZLE_128B box
 static int make_tmap(nnal_ctx* ctx, TcState* st, CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld,
                      uint32_t box_rows) {
   cuuint64_t dims[2] = {cols, rows};
@@ -446,7 +448,7 @@ bool nnal_tc_fc_supported(const nnal_ctx*, const Layer& L) {
          (L.in_dim % 8) == 0;
 }
 
-// Builds the bf16 hi/lo planes of an FC weight (called from nnal_model_set_weights).
+// Builds the fp16 hi/lo planes of an FC weight (called from nnal_model_set_weights).
 int nnal_tc_prepare_conv(nnal_ctx* ctx, Layer& L);
 int nnal_tc_prepare_layer(nnal_ctx* ctx, Layer& L) {
   if (L.type == NNAL_LAYER_CONV) {
@@ -527,7 +529,7 @@ int nnal_tc_fc(nnal_ctx* ctx, const Layer& L, const float* in, float* out, int64
   return nnal_tc_fc_planes(ctx, L, Ah, Al, Kp, out, nullptr, nullptr, n);
 }
 
-// flat fp32 <-> bf16 hi/lo conversions (format changes between CUDA-core and tensor-core layers)
+// flat fp32 <-> fp16 hi/lo conversions (format changes between CUDA-core and tensor-core layers)
 __global__ void __launch_bounds__(256) split_flat_kernel(const float* __restrict__ in, nnal_h* __restrict__ hi,
                                                           nnal_h* __restrict__ lo, int64_t count) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
@@ -542,7 +544,7 @@ __global__ void __launch_bounds__(256) merge_flat_kernel(const nnal_h* __restric
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
     out[e] = nnal_merge(hi[e], lo[e]);
 }
-// fp32 [rows][C] -> bf16 hi/lo [rows][Cp] with zero-padded channels (conv1: 3 -> 8, one UMMA chunk per pixel)
+// fp32 [rows][C] -> fp16 hi/lo [rows][Cp] with zero-padded channels (conv1: 3 -> 8, one UMMA chunk per pixel)
 __global__ void __launch_bounds__(256) split_pad_kernel(const float* __restrict__ in, nnal_h* __restrict__ hi,
                                                          nnal_h* __restrict__ lo, int64_t rows, int C, int Cp) {
   const int64_t total = rows * Cp;

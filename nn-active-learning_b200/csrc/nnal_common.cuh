@@ -94,7 +94,7 @@ struct Layer {
   bool has_weights = false;
   float* W = nullptr;                    // conv: [kh][kw][cin][cout]; fc: [out][in_native]
   float* b = nullptr;
-  // bf16 split planes for the tensor-core path (hi = bf16(x), lo = bf16(x - hi))
+  // fp16 split planes for the tensor-core path (hi = fp16(x), lo = fp16(x - hi))
   nnal_h* Wh = nullptr;
   nnal_h* Wl = nullptr;
   void* Wt = nullptr;                    // conv: weight blocks of the weight-stationary kernel (conv_wt.cu)
@@ -173,7 +173,7 @@ struct nnal_ctx {
   std::vector<double> stats_host;        // normalisation table being uploaded (mu, sigma, 1/sigma per modality)
   // workspaces
   DevBuf inds, act[2], xin, featbuf, prevbuf, logits;
-  DevBuf splitA[2];                      // bf16 hi/lo activation planes
+  DevBuf splitA[2];                      // fp16 hi/lo activation planes
   // pool state
   int64_t pool_n = 0;
   int keep = 0;                          // 0: posteriors only, 1: + features (fc_{L-1} out), 2: + previous fc out
